@@ -1,0 +1,154 @@
+/*
+ * b2o.h -- C ABI of libb2o.so: B200 (sm_100a) matrix-free operator-apply engine.
+ *
+ * This is the drop-in boundary for the `mul!(res, op, v, α, β)` hot path of
+ * JuliaSmoothOptimizers/LinearOperators.jl v2.14.2.  The reference has NO FFI: its
+ * boundary is Julia dispatch -- an `AbstractLinearOperator` whose `prod!/tprod!/ctprod!`
+ * closures (src/abstract.jl:46-59) are invoked by the generic `mul!`
+ * (src/operations.jl:22-32).  Each entry point below is what such a closure body
+ * would `ccall`; the comment on each names the reference closure it replaces.
+ * INTEGRATION.md shows the Julia-side binding (and the ctypes one the tests use).
+ *
+ * Conventions
+ *  - plain C: raw device pointers, sizes, scalars by value.  No torch / CUDA types
+ *    (a `cudaStream_t` is passed as `void*`).
+ *  - every function returns a b2o_status; never throws/aborts.  The message for the
+ *    last failure on the calling thread is returned by b2o_last_error().
+ *  - `res_len` / `v_len` are the lengths of the caller's vectors: a mismatch with the
+ *    operator shape returns B2O_ESHAPE("shape mismatch") *before* any work, like
+ *    src/operations.jl:23-24.
+ *  - when beta == 0 `res` is never read (src/constructors.jl:63-66): it may be
+ *    uninitialised memory (NaNs do not propagate).
+ *  - calls enqueue on the context's stream and return; they synchronise only when a
+ *    host-visible scalar is part of the reference semantics (push! acceptance tests).
+ *  - one in-flight call per context (the reference's operators share scratch the same
+ *    way: src/abstract.jl:151-153, src/lbfgs.jl:127).
+ *  - no allocation after handle creation (reference contract: test/test_lbfgs.jl:199-217).
+ *  - row-partitioned mode: after b2o_comm_init() every vector argument is the calling
+ *    rank's contiguous row slab and every inner product is all-reduced over ranks.
+ */
+#ifndef B2O_H
+#define B2O_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  B2O_OK = 0,
+  B2O_ESHAPE = 1,       /* LinearOperatorException("shape mismatch")            */
+  B2O_EARG = 2,         /* bad argument (null pointer, index out of range, ...) */
+  B2O_ECUDA = 3,        /* CUDA runtime error                                   */
+  B2O_ENCCL = 4,        /* NCCL error                                           */
+  B2O_ESTATE = 5,       /* wrong push! variant for this operator (ErrorException, src/lbfgs.jl:296-298,332-334) */
+  B2O_ENOMEM = 6,
+  B2O_EUNSUPPORTED = 7  /* dtype / feature not built                             */
+} b2o_status;
+
+typedef enum { B2O_F64 = 0, B2O_F32 = 1, B2O_BF16 = 2 } b2o_dtype;
+
+typedef struct b2o_ctx_s b2o_ctx;
+typedef struct b2o_qn_s b2o_qn;       /* LBFGSOperator / InverseLBFGSOperator / LSR1Operator state */
+typedef struct b2o_index_s b2o_index; /* opRestriction / opExtension index set */
+
+/* ---- library / context ------------------------------------------------------------------ */
+int b2o_version(void);
+const char *b2o_last_error(void);
+/* device: CUDA ordinal; stream: cudaStream_t to enqueue on (NULL -> the context creates its own). */
+int b2o_ctx_create(int device, void *stream, b2o_ctx **out);
+int b2o_ctx_destroy(b2o_ctx *ctx);
+int b2o_ctx_sync(b2o_ctx *ctx);
+/* tuning knobs of the streaming kernels: "tile_rows" (1024|2048|4096), "stages", "grid", "threads" */
+int b2o_ctx_set_option(b2o_ctx *ctx, const char *key, int64_t value);
+/* number of libb2o kernels launched through this context since creation */
+int b2o_ctx_launch_count(b2o_ctx *ctx, int64_t *out);
+/* average device time (ms) of the dominant streaming kernel over the launches since the last reset,
+ * measured with CUDA events on the context stream; reset=1 clears the accumulator. */
+int b2o_ctx_kernel_time(b2o_ctx *ctx, int reset, double *ms_total, int64_t *launches);
+
+/* device-memory helpers so a host without a CUDA binding (C, the ctypes tests) can drive the ABI.
+ * A Julia caller passes CuArray pointers instead and never needs these. */
+int b2o_malloc(b2o_ctx *ctx, size_t bytes, void **dptr);
+int b2o_free(b2o_ctx *ctx, void *dptr);
+int b2o_host_alloc(b2o_ctx *ctx, size_t bytes, void **hptr); /* pinned */
+int b2o_host_free(b2o_ctx *ctx, void *hptr);
+int b2o_memcpy_h2d(b2o_ctx *ctx, void *dst, const void *src, size_t bytes); /* stream-ordered + sync */
+int b2o_memcpy_d2h(b2o_ctx *ctx, void *dst, const void *src, size_t bytes);
+int b2o_memset_zero(b2o_ctx *ctx, void *dptr, size_t bytes);
+/* synthetic data: x[i] = lo + (hi-lo)*u(seed,i), the counter-based generator shared bit-for-bit
+ * with oracle/b2o_oracle.c:orc_fill_uniform (bench + parity tests at sizes too big to copy). */
+int b2o_fill_uniform(b2o_ctx *ctx, int dtype, void *dptr, int64_t n, uint64_t seed, double lo, double hi);
+/* dot(a,b) on device, result to host (used by the tests' size-independent properties) */
+int b2o_dot(b2o_ctx *ctx, int dtype, const void *a, const void *b, int64_t n, double *out);
+
+/* ---- leaf operators (src/special-operators.jl, src/linalg.jl) ---------------------------- */
+/* mulSquareOpDiagonal! :125-131 and mulOpDiagonal! :144-151.  res[0:nmin) = (alpha*d)*v (+beta*res);
+ * res[nmin:nrow) = 0 regardless of beta.  `d` is borrowed per call (the reference aliases it). */
+int b2o_diag_apply(b2o_ctx *ctx, int dtype, int64_t nrow, int64_t ncol, const void *d, int64_t d_len,
+                   void *res, int64_t res_len, const void *v, int64_t v_len, double alpha, double beta);
+/* mulOpEye! :36-44 (rectangular tail is 0 when beta==0, else the scalar beta). */
+int b2o_eye_apply(b2o_ctx *ctx, int dtype, int64_t nrow, int64_t ncol, void *res, int64_t res_len,
+                  const void *v, int64_t v_len, double alpha, double beta);
+/* mulOpOnes! :79-85  res .= alpha*sum(v) (+beta*res) */
+int b2o_ones_apply(b2o_ctx *ctx, int dtype, int64_t nrow, int64_t ncol, void *res, int64_t res_len,
+                   const void *v, int64_t v_len, double alpha, double beta);
+/* mulOpZeros! :102-108 */
+int b2o_zeros_apply(b2o_ctx *ctx, int dtype, int64_t nrow, int64_t ncol, void *res, int64_t res_len,
+                    int64_t v_len, double alpha, double beta);
+/* mulHouseholder! src/linalg.jl:77-83  res = alpha*(v - 2*dot(h,v)*h) (+beta*res); one launch */
+int b2o_householder_apply(b2o_ctx *ctx, int dtype, int64_t n, const void *h, void *res, int64_t res_len,
+                          const void *v, int64_t v_len, double alpha, double beta);
+/* opRestriction ctor :187-201: idx1 = HOST array of k 1-based indices; out-of-range -> B2O_EARG
+ * ("indices should be between 1 and ncol").  Duplicates are legal. */
+int b2o_index_create(b2o_ctx *ctx, const int64_t *idx1, int64_t k, int64_t ncol, b2o_index **out);
+int b2o_index_destroy(b2o_index *ix);
+/* mulRestrict! :167-169  res .= v[I]  (alpha, beta ignored by the reference) */
+int b2o_restrict_apply(b2o_index *ix, int dtype, void *res, int64_t res_len, const void *v, int64_t v_len);
+/* multRestrict! :171-174  res .= 0; res[I] = u  (duplicates: last occurrence wins) */
+int b2o_extend_apply(b2o_index *ix, int dtype, void *res, int64_t res_len, const void *u, int64_t u_len);
+
+/* ---- quasi-Newton operators (src/lbfgs.jl, src/lsr1.jl) ---------------------------------- */
+/* LBFGSOperator(T,n;mem,scaling,damped,σ₂,σ₃) :168-208 (inverse=0) / InverseLBFGSOperator :112-160 (inverse=1) */
+int b2o_lbfgs_create(b2o_ctx *ctx, int dtype, int64_t n, int mem, int scaling, int damped, double sigma2,
+                     double sigma3, int inverse, b2o_qn **out);
+/* LSR1Operator(T,n;mem,scaling) src/lsr1.jl:86-113 */
+int b2o_lsr1_create(b2o_ctx *ctx, int dtype, int64_t n, int mem, int scaling, b2o_qn **out);
+int b2o_qn_destroy(b2o_qn *op);
+/* prod! closure: lbfgs_multiply :117-154 / :173-202, lsr1_multiply src/lsr1.jl:89-107.  One persistent launch. */
+int b2o_qn_apply(b2o_qn *op, void *res, int64_t res_len, const void *x, int64_t x_len, double alpha, double beta);
+/* same, HOST buffers: H2D copy of x, apply, D2H copy of res, stream sync (the end-to-end path). */
+int b2o_qn_apply_host(b2o_qn *op, void *res_host, const void *x_host, int64_t len, double alpha, double beta);
+/* push!(op,s,y) src/lbfgs.jl:269-287, src/lsr1.jl:119-184.  *accepted = 0 when the pair is rejected
+ * (not an error, the reference returns op silently).  Synchronises (host-side acceptance tests). */
+int b2o_qn_push(b2o_qn *op, const void *s, const void *y, int64_t len, int *accepted);
+/* push!(op,s,y,Bs) src/lbfgs.jl:289-321 (forward damped; Bs is caller scratch of len n) */
+int b2o_lbfgs_push_damped_fwd(b2o_qn *op, const void *s, const void *y, void *Bs, int64_t len, int *accepted);
+/* push!(op,s,y,α,g,Bs) src/lbfgs.jl:323-357 (inverse damped; y is overwritten with the damped y) */
+int b2o_lbfgs_push_damped_inv(b2o_qn *op, const void *s, void *y, double alpha, const void *g, void *Bs,
+                              int64_t len, int *accepted);
+/* diag! src/lbfgs.jl:379-395 (forward only: inverse -> B2O_ESTATE), src/lsr1.jl:196-211 */
+int b2o_qn_diag(b2o_qn *op, void *d, int64_t d_len);
+/* reset! src/lbfgs.jl:401-427, src/lsr1.jl:217-240 */
+int b2o_qn_reset(b2o_qn *op);
+/* state access (checkpoint/resume and parity tests).  which: 0=s 1=y 2=a 3=b; k0 = 0-based ring slot.
+ * scalars: insert1 (1-based data.insert), gamma (scaling_factor), opnorm_upper_bound,
+ * ys[mem], aux[mem] (LBFGS inverse: α scratch; LBFGS forward: norm_b; LSR1: as). */
+int b2o_qn_get_col(b2o_qn *op, int which, int k0, void *dst_device);
+int b2o_qn_set_col(b2o_qn *op, int which, int k0, const void *src_device);
+int b2o_qn_get_scalars(b2o_qn *op, int *insert1, double *gamma, double *opnorm_ub, double *ys, double *aux);
+int b2o_qn_set_scalars(b2o_qn *op, int insert1, double gamma, double opnorm_ub, const double *ys, const double *aux);
+/* algorithmic DRAM bytes of one apply (SURVEY §8d / DESIGN.md), for the roofline */
+int b2o_qn_apply_bytes(b2o_qn *op, double beta, double *bytes);
+
+/* ---- row-partitioned multi-GPU (one process per GPU) ------------------------------------- */
+/* id: 128-byte ncclUniqueId produced on rank 0 by b2o_comm_unique_id and broadcast by the host
+ * (torch.distributed / MPI / files).  After init every inner product of this context is all-reduced. */
+int b2o_comm_unique_id(void *id128);
+int b2o_comm_init(b2o_ctx *ctx, const void *id128, int nranks, int rank);
+int b2o_comm_destroy(b2o_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

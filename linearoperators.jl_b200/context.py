@@ -1,0 +1,105 @@
+"""Execution context: one CUDA device + stream + libb2o workspace (b2o_ctx).
+
+torch is used here for what the task allows it for -- device memory (vectors are torch CUDA tensors
+whose raw pointers go across the C ABI), streams and torch.distributed rendezvous -- nothing else."""
+import ctypes
+
+from . import _lib
+
+_default = {}
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class Context:
+    def __init__(self, device=0, stream=None):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise _lib.B2OError("no CUDA device: the B200 operator-apply engine has no CPU fallback")
+        self.lib = _lib.load()
+        self.device = int(device)
+        torch.cuda.set_device(self.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        self.stream = stream
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.b2o_ctx_create(self.device, ctypes.c_void_p(stream.cuda_stream), ctypes.byref(h)))
+        self.handle = h
+        self.nranks, self.rank = 1, 0
+
+    # -- plumbing
+    def sync(self):
+        _lib.check(self.lib.b2o_ctx_sync(self.handle))
+
+    def set_option(self, key, value):
+        _lib.check(self.lib.b2o_ctx_set_option(self.handle, key.encode(), int(value)))
+
+    def launch_count(self):
+        n = ctypes.c_int64()
+        _lib.check(self.lib.b2o_ctx_launch_count(self.handle, ctypes.byref(n)))
+        return n.value
+
+    def kernel_time(self, reset=False):
+        ms, n = ctypes.c_double(), ctypes.c_int64()
+        _lib.check(self.lib.b2o_ctx_kernel_time(self.handle, int(reset), ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
+
+    def empty(self, n, dtype=None):
+        torch = _torch()
+        return torch.empty(int(n), dtype=dtype or torch.float64, device="cuda:%d" % self.device)
+
+    def zeros(self, n, dtype=None):
+        torch = _torch()
+        return torch.zeros(int(n), dtype=dtype or torch.float64, device="cuda:%d" % self.device)
+
+    def fill_uniform(self, x, seed, lo=0.0, hi=1.0):
+        """x[i] = lo + (hi-lo)*u(seed,i) with the generator shared with the oracle."""
+        torch = _torch()
+        dt = _lib.B2O_F64 if x.dtype == torch.float64 else _lib.B2O_F32
+        _lib.check(self.lib.b2o_fill_uniform(self.handle, dt, ctypes.c_void_p(x.data_ptr()), x.numel(), int(seed),
+                                             float(lo), float(hi)))
+        return x
+
+    def uniform(self, n, seed, lo=0.0, hi=1.0):
+        return self.fill_uniform(self.empty(n), seed, lo, hi)
+
+    def dot(self, a, b):
+        out = ctypes.c_double()
+        _lib.check(self.lib.b2o_dot(self.handle, _lib.B2O_F64, ctypes.c_void_p(a.data_ptr()),
+                                    ctypes.c_void_p(b.data_ptr()), a.numel(), ctypes.byref(out)))
+        return out.value
+
+    # -- row-partitioned multi-GPU: torch.distributed is only the rendezvous for the NCCL unique id
+    def init_comm_from_torch(self, group=None):
+        import torch.distributed as dist
+        torch = _torch()
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        buf = (ctypes.c_ubyte * 128)()
+        if rank == 0:
+            _lib.check(self.lib.b2o_comm_unique_id(buf))
+        t = torch.tensor(list(buf), dtype=torch.uint8)
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda(self.device)
+        dist.broadcast(t, src=0, group=group)
+        raw = bytes(t.cpu().tolist())
+        idbuf = (ctypes.c_ubyte * 128).from_buffer_copy(raw)
+        _lib.check(self.lib.b2o_comm_init(self.handle, idbuf, world, rank))
+        self.nranks, self.rank = world, rank
+
+    def close(self):
+        if self.handle:
+            self.lib.b2o_ctx_destroy(self.handle)
+            self.handle = None
+
+
+def default_context(device=None):
+    torch = _torch()
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    ctx = _default.get(device)
+    if ctx is None:
+        ctx = _default[device] = Context(device)
+    return ctx

@@ -1,0 +1,163 @@
+// b2o_internal.cuh -- shared host/device plumbing of libb2o (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/b2o.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libb2o is written for sm_100a (B200) only"
+#endif
+
+// ------------------------------------------------------------------ errors
+void b2o_set_error(const char *fmt, ...);
+#define B2O_FAIL(code, ...)      \
+  do {                           \
+    b2o_set_error(__VA_ARGS__);  \
+    return (code);               \
+  } while (0)
+#define B2O_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      b2o_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__,     \
+                    cudaGetErrorString(_e));                                                    \
+      return B2O_ECUDA;                                                                         \
+    }                                                                                           \
+  } while (0)
+#define B2O_TRY(expr)            \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != B2O_OK) return _s; \
+  } while (0)
+
+// ------------------------------------------------------------------ context
+constexpr int B2O_MAX_COLS = 128;      // column streams one launch can address
+constexpr int B2O_MAX_GRID = 1024;     // upper bound on persistent grid
+constexpr int B2O_WS_DOTS = 512;       // doubles reserved for reduced scalars
+
+struct b2o_ctx_s {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  // workspace (allocated once at create; nothing allocates per call)
+  double *d_partials = nullptr;             // [B2O_MAX_GRID][B2O_MAX_COLS]
+  double *d_dots = nullptr;                 // [B2O_WS_DOTS] reduced scalars
+  unsigned long long *d_bar = nullptr;      // [0] grid-barrier counter (monotonic), [1] arrival counter (split mode)
+  unsigned long long bar_base = 0;          // host mirror of d_bar[0]
+  double *h_scal = nullptr;                 // pinned, B2O_WS_DOTS doubles
+  // staging for *_host entry points (grown on first use, then reused)
+  void *stage_x = nullptr, *stage_res = nullptr;
+  size_t stage_bytes = 0;
+  // tuning
+  int tile_rows = 2048;
+  int stages = 0;        // 0 -> as many as shared memory allows
+  int grid = 0;          // 0 -> one CTA per SM
+  // accounting
+  int64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool time_kernels = false;
+  double kern_ms = 0.0;
+  int64_t kern_n = 0;
+  // multi-GPU (row partition); comm is an ncclComm_t, resolved lazily through dlopen
+  void *nccl_comm = nullptr;
+  int nranks = 1, rank = 0;
+};
+
+int b2o_allreduce_sum_f64(b2o_ctx *ctx, double *dptr, int count);  // no-op when nranks == 1
+
+static inline int b2o_check_dtype_f64(int dtype) {
+  if (dtype != B2O_F64) B2O_FAIL(B2O_EUNSUPPORTED, "dtype %d not supported by this entry point (Float64 only)", dtype);
+  return B2O_OK;
+}
+
+// generic helpers implemented in b2o_ctx.cu / b2o_util.cu
+int b2o_pair_dots(b2o_ctx *ctx, int npairs, const double *const *u, const double *const *v, int64_t n, double *d_out);
+int b2o_read_scalars(b2o_ctx *ctx, const double *d_src, int count, double *h_dst);  // D2H + sync via pinned
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------ device helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar,
+                                              uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// streaming (evict-first) 16-byte global load/store for user vectors
+__device__ __forceinline__ double2 ldg_stream2(const double *p) {
+  double2 r;
+  asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream2(double *p, double2 v) {
+  asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+// grid-wide barrier for co-resident (cooperatively launched) persistent kernels.  `ctr` only ever
+// grows; `target` = value it must reach.  Every thread of every CTA calls it.
+__device__ __forceinline__ void grid_barrier(unsigned long long *ctr, unsigned long long target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1ULL);
+    while (ld_acquire_u64(ctr) < target) { __nanosleep(32); }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+#endif  // __CUDACC__

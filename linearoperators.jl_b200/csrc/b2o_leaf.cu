@@ -1,0 +1,461 @@
+// b2o_leaf.cu -- leaf operators of src/special-operators.jl and src/linalg.jl:
+// opDiagonal, opEye, opOnes, opZeros, opHouseholder (streaming, 16-byte vectorised) and
+// opRestriction / opExtension (gather / scatter, bit-exact index work).
+#include "b2o_internal.cuh"
+#include <algorithm>
+#include <unordered_set>
+
+// ------------------------------------------------------------------ streaming elementwise kernel
+enum { EW_DIAG = 0, EW_EYE = 1, EW_ZEROS = 2, EW_ONES = 3, EW_HOUSE = 4 };
+
+struct EwArgs {
+  int op;
+  const double *a;     // DIAG: d ; HOUSE: h
+  const double *v;     // input vector
+  double *res;
+  int64_t nmin;        // rows with the elementwise formula
+  int64_t nrow;        // rows of res; [nmin,nrow) get `tail`
+  double alpha, beta, tail;
+  const double *dscal; // ONES: sum(v) ; HOUSE: dot(h,v)   (device scalar)
+};
+
+template <int OP>
+__device__ __forceinline__ double ew_one(const EwArgs &p, double a, double v, double r, double scal) {
+  double t;
+  if (OP == EW_DIAG) t = (p.alpha * a) * v;            // α .* d .* v                  special-operators.jl:127
+  else if (OP == EW_EYE) t = p.alpha * v;              // α .* v                        :38
+  else if (OP == EW_ZEROS) return (p.beta != 0.0) ? r * p.beta : 0.0;  // res .*= β    :106
+  else if (OP == EW_ONES) t = scal;                    // α * sum(v)                    :81
+  else t = p.alpha * (v - scal * a);                   // α .* (v .- 2τ .* h)           linalg.jl:79
+  return (p.beta != 0.0) ? t + p.beta * r : t;
+}
+
+constexpr int EW_UNROLL = 4;
+
+template <int OP, bool VEC>
+__global__ void __launch_bounds__(256) ew_kernel(const __grid_constant__ EwArgs p) {
+  constexpr bool NEED_A = (OP == EW_DIAG || OP == EW_HOUSE);
+  constexpr bool NEED_V = (OP == EW_DIAG || OP == EW_EYE || OP == EW_HOUSE);
+  double scal = 0.0;
+  if (OP == EW_ONES) scal = p.alpha * (*p.dscal);
+  if (OP == EW_HOUSE) scal = 2 * (*p.dscal);
+  const bool need_r = p.beta != 0.0;
+  if (VEC) {
+    const int64_t nvec = p.nmin >> 1;
+    const int64_t base = (int64_t)blockIdx.x * (256 * EW_UNROLL) + threadIdx.x;
+    double2 a[EW_UNROLL], v[EW_UNROLL], r[EW_UNROLL];
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {
+      const int64_t i = base + u * 256;
+      a[u] = v[u] = r[u] = make_double2(0.0, 0.0);
+      if (i < nvec) {
+        if (NEED_A) a[u] = ldg_stream2(p.a + 2 * i);
+        if (NEED_V) v[u] = ldg_stream2(p.v + 2 * i);
+        if (need_r) r[u] = ldg_stream2(p.res + 2 * i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {
+      const int64_t i = base + u * 256;
+      if (i < nvec) {
+        double2 o;
+        o.x = ew_one<OP>(p, a[u].x, v[u].x, r[u].x, scal);
+        o.y = ew_one<OP>(p, a[u].y, v[u].y, r[u].y, scal);
+        stg_stream2(p.res + 2 * i, o);
+      }
+    }
+    // odd element of the elementwise part + the tail are handled by the last block
+    if (blockIdx.x == gridDim.x - 1) {
+      if ((p.nmin & 1) && threadIdx.x == 0) {
+        const int64_t i = p.nmin - 1;
+        p.res[i] = ew_one<OP>(p, NEED_A ? p.a[i] : 0.0, NEED_V ? p.v[i] : 0.0, need_r ? p.res[i] : 0.0, scal);
+      }
+      for (int64_t i = p.nmin + threadIdx.x; i < p.nrow; i += 256) p.res[i] = p.tail;
+    }
+  } else {
+    const int64_t base = (int64_t)blockIdx.x * (256 * EW_UNROLL) + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {
+      const int64_t i = base + u * 256;
+      if (i < p.nmin)
+        p.res[i] = ew_one<OP>(p, NEED_A ? p.a[i] : 0.0, NEED_V ? p.v[i] : 0.0, need_r ? p.res[i] : 0.0, scal);
+    }
+    if (blockIdx.x == gridDim.x - 1)
+      for (int64_t i = p.nmin + threadIdx.x; i < p.nrow; i += 256) p.res[i] = p.tail;
+  }
+}
+
+template <int OP>
+static int ew_launch(b2o_ctx *c, EwArgs &p) {
+  if (p.nrow <= 0) return B2O_OK;
+  const bool vec = (((uintptr_t)p.a | (uintptr_t)p.v | (uintptr_t)p.res) % 16) == 0;
+  const int64_t units = vec ? (p.nmin >> 1) : p.nmin;
+  const int64_t per_block = 256 * EW_UNROLL;
+  const int64_t grid = std::max<int64_t>(1, (units + per_block - 1) / per_block);
+  if (grid > 0x7fffffff) B2O_FAIL(B2O_EARG, "vector too long");
+  if (vec)
+    ew_kernel<OP, true><<<(unsigned)grid, 256, 0, c->stream>>>(p);
+  else
+    ew_kernel<OP, false><<<(unsigned)grid, 256, 0, c->stream>>>(p);
+  c->launches++;
+  B2O_CUDA(cudaGetLastError());
+  return B2O_OK;
+}
+
+static int check_ptrs8(const void *a, const void *b, const void *c) {
+  if (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) % 8) B2O_FAIL(B2O_EARG, "vectors must be 8-byte aligned");
+  return B2O_OK;
+}
+
+// ------------------------------------------------------------------ opDiagonal
+extern "C" int b2o_diag_apply(b2o_ctx *c, int dtype, int64_t nrow, int64_t ncol, const void *d, int64_t d_len, void *res,
+                              int64_t res_len, const void *v, int64_t v_len, double alpha, double beta) {
+  if (!c) B2O_FAIL(B2O_EARG, "null context");
+  B2O_TRY(b2o_check_dtype_f64(dtype));
+  if (nrow < 0 || ncol < 0) B2O_FAIL(B2O_EARG, "negative size");
+  if (v_len != ncol || res_len != nrow) B2O_FAIL(B2O_ESHAPE, "shape mismatch");
+  const int64_t nmin = std::min(nrow, ncol);
+  if (d_len < nmin) B2O_FAIL(B2O_EARG, "diagonal shorter than min(nrow,ncol)");
+  if (nrow > 0 && (!res || (nmin > 0 && (!d || !v)))) B2O_FAIL(B2O_EARG, "null vector");
+  B2O_TRY(check_ptrs8(d, v, res));
+  B2O_CUDA(cudaSetDevice(c->device));
+  EwArgs p;
+  memset(&p, 0, sizeof(p));
+  p.op = EW_DIAG;
+  p.a = (const double *)d;
+  p.v = (const double *)v;
+  p.res = (double *)res;
+  p.nmin = nmin;
+  p.nrow = nrow;
+  p.alpha = alpha;
+  p.beta = beta;
+  p.tail = 0.0;  // res[(n_min+1):end] .= 0 regardless of β                 special-operators.jl:150
+  return ew_launch<EW_DIAG>(c, p);
+}
+
+// ------------------------------------------------------------------ opEye
+extern "C" int b2o_eye_apply(b2o_ctx *c, int dtype, int64_t nrow, int64_t ncol, void *res, int64_t res_len, const void *v,
+                             int64_t v_len, double alpha, double beta) {
+  if (!c) B2O_FAIL(B2O_EARG, "null context");
+  B2O_TRY(b2o_check_dtype_f64(dtype));
+  if (nrow < 0 || ncol < 0) B2O_FAIL(B2O_EARG, "negative size");
+  if (v_len != ncol || res_len != nrow) B2O_FAIL(B2O_ESHAPE, "shape mismatch");
+  if (nrow > 0 && (!res || (ncol > 0 && !v))) B2O_FAIL(B2O_EARG, "null vector");
+  B2O_TRY(check_ptrs8(nullptr, v, res));
+  B2O_CUDA(cudaSetDevice(c->device));
+  EwArgs p;
+  memset(&p, 0, sizeof(p));
+  p.op = EW_EYE;
+  p.v = (const double *)v;
+  p.res = (double *)res;
+  p.nmin = std::min(nrow, ncol);
+  p.nrow = nrow;
+  p.alpha = alpha;
+  p.beta = beta;
+  p.tail = (beta == 0.0) ? 0.0 : beta;  // res[(n_min+1):end] .= β  (Q2)     special-operators.jl:39,42
+  return ew_launch<EW_EYE>(c, p);
+}
+
+// ------------------------------------------------------------------ opZeros
+extern "C" int b2o_zeros_apply(b2o_ctx *c, int dtype, int64_t nrow, int64_t ncol, void *res, int64_t res_len, int64_t v_len,
+                               double alpha, double beta) {
+  if (!c) B2O_FAIL(B2O_EARG, "null context");
+  B2O_TRY(b2o_check_dtype_f64(dtype));
+  if (v_len != ncol || res_len != nrow) B2O_FAIL(B2O_ESHAPE, "shape mismatch");
+  if (nrow > 0 && !res) B2O_FAIL(B2O_EARG, "null vector");
+  B2O_TRY(check_ptrs8(nullptr, nullptr, res));
+  B2O_CUDA(cudaSetDevice(c->device));
+  EwArgs p;
+  memset(&p, 0, sizeof(p));
+  p.op = EW_ZEROS;
+  p.res = (double *)res;
+  p.nmin = nrow;
+  p.nrow = nrow;
+  p.alpha = alpha;
+  p.beta = beta;
+  return ew_launch<EW_ZEROS>(c, p);
+}
+
+// ------------------------------------------------------------------ sums (opOnes) -- pair_dots with v = null means "times one"
+extern "C" int b2o_ones_apply(b2o_ctx *c, int dtype, int64_t nrow, int64_t ncol, void *res, int64_t res_len, const void *v,
+                              int64_t v_len, double alpha, double beta) {
+  if (!c) B2O_FAIL(B2O_EARG, "null context");
+  B2O_TRY(b2o_check_dtype_f64(dtype));
+  if (v_len != ncol || res_len != nrow) B2O_FAIL(B2O_ESHAPE, "shape mismatch");
+  if ((nrow > 0 && !res) || (ncol > 0 && !v)) B2O_FAIL(B2O_EARG, "null vector");
+  B2O_TRY(check_ptrs8(nullptr, v, res));
+  B2O_CUDA(cudaSetDevice(c->device));
+  const double *u[1] = {(const double *)v}, *w[1] = {nullptr};
+  B2O_TRY(b2o_pair_dots(c, 1, u, w, ncol, c->d_dots + 320));   // sum(v), all-reduced when row-partitioned
+  EwArgs p;
+  memset(&p, 0, sizeof(p));
+  p.op = EW_ONES;
+  p.res = (double *)res;
+  p.nmin = nrow;
+  p.nrow = nrow;
+  p.alpha = alpha;
+  p.beta = beta;
+  p.dscal = c->d_dots + 320;
+  return ew_launch<EW_ONES>(c, p);
+}
+
+// ------------------------------------------------------------------ opHouseholder: one cooperative launch
+struct HouseArgs {
+  const double *h, *v;
+  double *res;
+  int64_t n;
+  double alpha, beta;
+  double *partials;
+  unsigned long long *bar;
+  unsigned long long bar_target;
+  int vec;
+};
+__global__ void __launch_bounds__(512) householder_kernel(const __grid_constant__ HouseArgs p) {
+  __shared__ double sred[16];
+  __shared__ double s_t2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+  double acc0 = 0.0, acc1 = 0.0;
+  if (p.vec) {
+    const int64_t nvec = p.n >> 1;
+    for (int64_t i = tid; i < nvec; i += nth) {
+      double2 a = *reinterpret_cast<const double2 *>(p.h + 2 * i), b = *reinterpret_cast<const double2 *>(p.v + 2 * i);
+      acc0 = fma(a.x, b.x, acc0);
+      acc1 = fma(a.y, b.y, acc1);
+    }
+    if ((p.n & 1) && tid == 0) acc0 = fma(p.h[p.n - 1], p.v[p.n - 1], acc0);
+  } else {
+    for (int64_t i = tid; i < p.n; i += nth) acc0 = fma(p.h[i], p.v[i], acc0);
+  }
+  double s = warp_sum(acc0 + acc1);
+  if (lane == 0) sred[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sred[w];
+    p.partials[blockIdx.x] = t;
+  }
+  grid_barrier(p.bar, p.bar_target);
+  if (warp == 0) {
+    double t = 0.0;
+    for (int b = lane; b < (int)gridDim.x; b += 32) t += __ldcg(&p.partials[b]);
+    t = warp_sum(t);
+    if (lane == 0) s_t2 = 2 * t;          // 2 * dot(h, v)                      linalg.jl:79
+  }
+  __syncthreads();
+  const double t2 = s_t2;
+  const bool need_r = p.beta != 0.0;
+  // second pass in reverse so the tail of pass 1 is served from L2
+  if (p.vec) {
+    const int64_t nvec = p.n >> 1;
+    for (int64_t i = nvec - 1 - tid; i >= 0; i -= nth) {
+      double2 a = *reinterpret_cast<const double2 *>(p.h + 2 * i), b = *reinterpret_cast<const double2 *>(p.v + 2 * i), o;
+      o.x = p.alpha * (b.x - t2 * a.x);
+      o.y = p.alpha * (b.y - t2 * a.y);
+      if (need_r) {
+        double2 r = *reinterpret_cast<const double2 *>(p.res + 2 * i);
+        o.x = o.x + p.beta * r.x;
+        o.y = o.y + p.beta * r.y;
+      }
+      stg_stream2(p.res + 2 * i, o);
+    }
+    if ((p.n & 1) && tid == 0) {
+      const int64_t i = p.n - 1;
+      double o = p.alpha * (p.v[i] - t2 * p.h[i]);
+      p.res[i] = need_r ? o + p.beta * p.res[i] : o;
+    }
+  } else {
+    for (int64_t i = tid; i < p.n; i += nth) {
+      double o = p.alpha * (p.v[i] - t2 * p.h[i]);
+      p.res[i] = need_r ? o + p.beta * p.res[i] : o;
+    }
+  }
+}
+
+extern "C" int b2o_householder_apply(b2o_ctx *c, int dtype, int64_t n, const void *h, void *res, int64_t res_len,
+                                     const void *v, int64_t v_len, double alpha, double beta) {
+  if (!c) B2O_FAIL(B2O_EARG, "null context");
+  B2O_TRY(b2o_check_dtype_f64(dtype));
+  if (v_len != n || res_len != n) B2O_FAIL(B2O_ESHAPE, "shape mismatch");
+  if (n > 0 && (!h || !res || !v)) B2O_FAIL(B2O_EARG, "null vector");
+  B2O_TRY(check_ptrs8(h, v, res));
+  if (n == 0) return B2O_OK;
+  B2O_CUDA(cudaSetDevice(c->device));
+  if (c->nranks > 1) {
+    // row-partitioned: dot -> all-reduce -> update
+    const double *u[1] = {(const double *)h}, *w[1] = {(const double *)v};
+    B2O_TRY(b2o_pair_dots(c, 1, u, w, n, c->d_dots + 320));
+    EwArgs p;
+    memset(&p, 0, sizeof(p));
+    p.op = EW_HOUSE;
+    p.a = (const double *)h;
+    p.v = (const double *)v;
+    p.res = (double *)res;
+    p.nmin = n;
+    p.nrow = n;
+    p.alpha = alpha;
+    p.beta = beta;
+    p.dscal = c->d_dots + 320;
+    return ew_launch<EW_HOUSE>(c, p);
+  }
+  static thread_local int blocks_per_sm = 0;
+  if (!blocks_per_sm) {
+    B2O_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, householder_kernel, 512, 0));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+  }
+  HouseArgs p;
+  p.h = (const double *)h;
+  p.v = (const double *)v;
+  p.res = (double *)res;
+  p.n = n;
+  p.alpha = alpha;
+  p.beta = beta;
+  p.partials = c->d_partials;
+  p.bar = c->d_bar;
+  p.vec = (((uintptr_t)h | (uintptr_t)v | (uintptr_t)res) % 16) == 0;
+  int64_t want = (n / 2 + 511) / 512;
+  int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->num_sms * std::min(blocks_per_sm, 4)));
+  grid = std::min(grid, B2O_MAX_GRID);
+  p.bar_target = c->bar_base + (unsigned long long)grid;
+  void *kargs[] = {(void *)&p};
+  B2O_CUDA(cudaLaunchCooperativeKernel((const void *)householder_kernel, dim3(grid), dim3(512), kargs, 0, c->stream));
+  c->bar_base += (unsigned long long)grid;
+  c->launches++;
+  return B2O_OK;
+}
+
+// ------------------------------------------------------------------ opRestriction / opExtension
+struct b2o_index_s {
+  b2o_ctx *ctx;
+  int64_t k, ncol;
+  int64_t *d_idx0;    // [k] 0-based source rows (gather)
+  int64_t *d_wpos;    // [kw] positions in u that win their target (scatter; duplicates: last occurrence wins)
+  int64_t kw;
+};
+
+extern "C" int b2o_index_create(b2o_ctx *c, const int64_t *idx1, int64_t k, int64_t ncol, b2o_index **out) {
+  if (!c || !out || (k > 0 && !idx1)) B2O_FAIL(B2O_EARG, "null argument");
+  if (k < 0 || ncol < 0) B2O_FAIL(B2O_EARG, "negative size");
+  for (int64_t i = 0; i < k; ++i)
+    if (idx1[i] < 1 || idx1[i] > ncol)
+      B2O_FAIL(B2O_EARG, "indices should be between 1 and %lld", (long long)ncol);   // special-operators.jl:188
+  B2O_CUDA(cudaSetDevice(c->device));
+  std::vector<int64_t> idx0(k), wpos;
+  for (int64_t i = 0; i < k; ++i) idx0[i] = idx1[i] - 1;
+  {
+    std::unordered_set<int64_t> seen;
+    seen.reserve((size_t)k * 2 + 1);
+    for (int64_t i = k - 1; i >= 0; --i)
+      if (seen.insert(idx0[i]).second) wpos.push_back(i);
+    std::reverse(wpos.begin(), wpos.end());
+  }
+  b2o_index *ix = new b2o_index_s();
+  ix->ctx = c;
+  ix->k = k;
+  ix->ncol = ncol;
+  ix->kw = (int64_t)wpos.size();
+  ix->d_idx0 = ix->d_wpos = nullptr;
+  cudaError_t e1 = cudaMalloc(&ix->d_idx0, sizeof(int64_t) * std::max<int64_t>(k, 1));
+  cudaError_t e2 = cudaMalloc(&ix->d_wpos, sizeof(int64_t) * std::max<int64_t>(ix->kw, 1));
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(ix->d_idx0);
+    cudaFree(ix->d_wpos);
+    delete ix;
+    B2O_FAIL(B2O_ENOMEM, "index allocation failed");
+  }
+  if (k > 0) {
+    B2O_CUDA(cudaMemcpy(ix->d_idx0, idx0.data(), sizeof(int64_t) * k, cudaMemcpyHostToDevice));
+    B2O_CUDA(cudaMemcpy(ix->d_wpos, wpos.data(), sizeof(int64_t) * ix->kw, cudaMemcpyHostToDevice));
+  }
+  *out = ix;
+  return B2O_OK;
+}
+extern "C" int b2o_index_destroy(b2o_index *ix) {
+  if (!ix) return B2O_OK;
+  cudaSetDevice(ix->ctx->device);
+  cudaStreamSynchronize(ix->ctx->stream);
+  cudaFree(ix->d_idx0);
+  cudaFree(ix->d_wpos);
+  delete ix;
+  return B2O_OK;
+}
+
+template <typename E>
+__global__ void __launch_bounds__(256) gather_kernel(E *__restrict__ res, const E *__restrict__ v,
+                                                     const int64_t *__restrict__ idx0, int64_t k) {
+  const int64_t base = (int64_t)blockIdx.x * (256 * 4) + threadIdx.x;
+  int64_t src[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int64_t i = base + u * 256;
+    src[u] = (i < k) ? __ldcs(&idx0[i]) : -1;
+  }
+  E val[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    if (src[u] >= 0) val[u] = __ldg(&v[src[u]]);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int64_t i = base + u * 256;
+    if (i < k) __stcs(&res[i], val[u]);
+  }
+}
+template <typename E>
+__global__ void __launch_bounds__(256) scatter_kernel(E *__restrict__ res, const E *__restrict__ u,
+                                                      const int64_t *__restrict__ idx0,
+                                                      const int64_t *__restrict__ wpos, int64_t kw) {
+  const int64_t base = (int64_t)blockIdx.x * (256 * 4) + threadIdx.x;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int64_t w = base + q * 256;
+    if (w < kw) {
+      const int64_t i = __ldcs(&wpos[w]);
+      res[__ldcs(&idx0[i])] = __ldcs(&u[i]);
+    }
+  }
+}
+
+static int elem_size(int dtype) { return dtype == B2O_F64 ? 8 : dtype == B2O_F32 ? 4 : dtype == B2O_BF16 ? 2 : 0; }
+
+extern "C" int b2o_restrict_apply(b2o_index *ix, int dtype, void *res, int64_t res_len, const void *v, int64_t v_len) {
+  if (!ix) B2O_FAIL(B2O_EARG, "null index");
+  if (v_len != ix->ncol || res_len != ix->k) B2O_FAIL(B2O_ESHAPE, "shape mismatch");
+  const int es = elem_size(dtype);
+  if (es != 8 && es != 4) B2O_FAIL(B2O_EUNSUPPORTED, "restriction supports 8- and 4-byte elements");
+  if (ix->k == 0) return B2O_OK;
+  if (!res || !v) B2O_FAIL(B2O_EARG, "null vector");
+  b2o_ctx *c = ix->ctx;
+  B2O_CUDA(cudaSetDevice(c->device));
+  const unsigned grid = (unsigned)((ix->k + 1023) / 1024);
+  if (es == 8)
+    gather_kernel<double><<<grid, 256, 0, c->stream>>>((double *)res, (const double *)v, ix->d_idx0, ix->k);
+  else
+    gather_kernel<float><<<grid, 256, 0, c->stream>>>((float *)res, (const float *)v, ix->d_idx0, ix->k);
+  c->launches++;
+  B2O_CUDA(cudaGetLastError());
+  return B2O_OK;
+}
+
+extern "C" int b2o_extend_apply(b2o_index *ix, int dtype, void *res, int64_t res_len, const void *u, int64_t u_len) {
+  if (!ix) B2O_FAIL(B2O_EARG, "null index");
+  if (u_len != ix->k || res_len != ix->ncol) B2O_FAIL(B2O_ESHAPE, "shape mismatch");
+  const int es = elem_size(dtype);
+  if (es != 8 && es != 4) B2O_FAIL(B2O_EUNSUPPORTED, "extension supports 8- and 4-byte elements");
+  if (ix->ncol == 0) return B2O_OK;
+  if (!res || (ix->k > 0 && !u)) B2O_FAIL(B2O_EARG, "null vector");
+  b2o_ctx *c = ix->ctx;
+  B2O_CUDA(cudaSetDevice(c->device));
+  B2O_CUDA(cudaMemsetAsync(res, 0, (size_t)ix->ncol * es, c->stream));          // res .= 0   special-operators.jl:172
+  if (ix->kw > 0) {
+    const unsigned grid = (unsigned)((ix->kw + 1023) / 1024);
+    if (es == 8)
+      scatter_kernel<double><<<grid, 256, 0, c->stream>>>((double *)res, (const double *)u, ix->d_idx0, ix->d_wpos, ix->kw);
+    else
+      scatter_kernel<float><<<grid, 256, 0, c->stream>>>((float *)res, (const float *)u, ix->d_idx0, ix->d_wpos, ix->kw);
+    c->launches++;
+    B2O_CUDA(cudaGetLastError());
+  }
+  return B2O_OK;
+}

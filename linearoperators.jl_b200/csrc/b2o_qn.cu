@@ -1,0 +1,937 @@
+// b2o_qn.cu -- LBFGSOperator / InverseLBFGSOperator / LSR1Operator handles (src/lbfgs.jl, src/lsr1.jl):
+// state, apply (persistent kernels in b2o_qn_kernels.cuh), push!, diag!, reset!, state access.
+#include "b2o_qn_kernels.cuh"
+#include <float.h>
+#include <math.h>
+#include <algorithm>
+
+constexpr int64_t B2O_PITCH_ALIGN = 4096;  // rows; every supported tile size divides it
+
+struct b2o_qn_s {
+  b2o_ctx *ctx = nullptr;
+  int kind = 0;  // 0 = L-BFGS, 1 = L-SR1
+  int64_t n = 0, pitch = 0;
+  int mem = 1;
+  bool scaling = true, damped = false, inverse = false;
+  double gamma = 1.0, sigma2 = 0.99, sigma3 = 10.0, opnorm_ub = 1.0;
+  double *S = nullptr, *Y = nullptr, *A = nullptr, *B = nullptr;  // [mem][pitch], zero padded
+  double *q = nullptr, *tmp = nullptr;                            // [pitch]
+  double *d_alpha = nullptr;                                      // [mem] device copy of data.α (inverse)
+  std::vector<double> ys, aux;  // aux: inverse L-BFGS α (host mirror, lazily), forward norm_b, L-SR1 as
+  int ins0 = 0;
+  double *col(double *base, int k0) const { return base + (size_t)k0 * (size_t)pitch; }
+};
+
+static inline int pmod(int a, int m) {
+  int r = a % m;
+  return r < 0 ? r + m : r;
+}
+
+// ------------------------------------------------------------------ small elementwise helpers (push!/diag!, not the hot path)
+// out = a*x + b*y   (y may be null -> out = a*x);  rounding as the reference's broadcasts (no fma)
+__global__ void axpby_kernel(double *out, double a, const double *x, double b, const double *y, int64_t n) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = y ? a * x[i] + b * y[i] : a * x[i];
+}
+// out = x / d
+__global__ void div_kernel(double *out, const double *x, double d, int64_t n) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = x[i] / d;
+}
+// out = x / sqrt(*dscal)   (device scalar)
+__global__ void div_sqrt_dev_kernel(double *out, const double *x, const double *dscal, int64_t n) {
+  const double d = sqrt(*dscal);
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = x[i] / d;
+}
+
+// out[j] = base(j), then sequentially out[j] (+|-)= coef_t * col_t[j];  coef_t = dots[t] / cdiv[t].
+// base: mode 0: P1[j]/g ; mode 1: P0[j] - P1[j]/g.   Fused reductions: red[0] = out·u0 ; red[1] = out·out.
+struct LincombArgs {
+  const double *cols[B2O_MAX_COLS];
+  double cdiv[B2O_MAX_COLS];
+  signed char sign[B2O_MAX_COLS];
+  int nterms;
+  int base_mode;
+  const double *P0, *P1;
+  double g;
+  const double *dots;  // device coefficients
+  const double *u0;    // may be null
+  double *out;
+  int64_t n;
+  double *partials;    // [grid][2]
+  double *red;         // [2]
+  unsigned long long *arrive;
+};
+__global__ void __launch_bounds__(256) lincomb_kernel(const __grid_constant__ LincombArgs a) {
+  __shared__ double scoef[B2O_MAX_COLS];
+  __shared__ double sred[2][8];
+  __shared__ bool is_last;
+  for (int t = threadIdx.x; t < a.nterms; t += blockDim.x) scoef[t] = a.dots[t] / a.cdiv[t];
+  __syncthreads();
+  double r0 = 0.0, r1 = 0.0;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+    double v = a.base_mode == 0 ? a.P1[i] / a.g : a.P0[i] - a.P1[i] / a.g;
+    for (int t = 0; t < a.nterms; ++t) {
+      double c = scoef[t] * a.cols[t][i];
+      v = a.sign[t] > 0 ? v + c : v - c;
+    }
+    a.out[i] = v;
+    if (a.u0) r0 = fma(v, a.u0[i], r0);
+    r1 = fma(v, v, r1);
+  }
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  r0 = warp_sum(r0);
+  r1 = warp_sum(r1);
+  if (lane == 0) {
+    sred[0][warp] = r0;
+    sred[1][warp] = r1;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += sred[threadIdx.x][w];
+    a.partials[(size_t)blockIdx.x * 2 + threadIdx.x] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = atomicAdd(a.arrive, 1ULL);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (warp < 2) {
+      double s = 0.0;
+      for (int b = lane; b < gridDim.x; b += 32) s += __ldcg(&a.partials[(size_t)b * 2 + warp]);
+      s = warp_sum(s);
+      if (lane == 0) a.red[warp] = s;
+    }
+    if (threadIdx.x == 0) *a.arrive = 0ULL;
+  }
+}
+
+// diag!: d = 1 (/γ) ; d += b_k^2 - a_k^2  (L-BFGS :379-395)  |  d += a_k^2/as_k  (L-SR1 :196-211)
+struct DiagArgs {
+  const double *c0[B2O_MAX_MEM];
+  const double *c1[B2O_MAX_MEM];
+  double cdiv[B2O_MAX_MEM];
+  int nact, kind, scaling;
+  double gamma;
+  double *d;
+  int64_t n;
+};
+__global__ void qn_diag_kernel(const __grid_constant__ DiagArgs a) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+    double d = 1.0;
+    if (a.scaling) d = d / a.gamma;
+    for (int k = 0; k < a.nact; ++k) {
+      if (a.kind == 0) {
+        double av = a.c0[k][i], bv = a.c1[k][i];
+        d = d + (bv * bv - av * av);
+      } else {
+        double av = a.c0[k][i];
+        d = d + (av * av) / a.cdiv[k];
+      }
+    }
+    a.d[i] = d;
+  }
+}
+
+static inline int ew_grid(b2o_ctx *c, int64_t n) {
+  int64_t want = (n + 255) / 256;
+  int64_t cap = (int64_t)c->num_sms * 8;
+  return (int)std::max<int64_t>(1, std::min(want, cap));
+}
+static int ew_axpby(b2o_ctx *c, double *out, double a, const double *x, double b, const double *y, int64_t n) {
+  if (n <= 0) return B2O_OK;
+  axpby_kernel<<<ew_grid(c, n), 256, 0, c->stream>>>(out, a, x, b, y, n);
+  c->launches++;
+  B2O_CUDA(cudaGetLastError());
+  return B2O_OK;
+}
+
+// ------------------------------------------------------------------ create / destroy
+static int qn_alloc(b2o_qn *q) {
+  b2o_ctx *c = q->ctx;
+  B2O_CUDA(cudaSetDevice(c->device));
+  const size_t colb = (size_t)q->pitch * sizeof(double);
+  auto alloc0 = [&](double **p, size_t bytes) -> int {
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      B2O_FAIL(B2O_ENOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    B2O_CUDA(cudaMemsetAsync(*p, 0, bytes, c->stream));
+    return B2O_OK;
+  };
+  B2O_TRY(alloc0(&q->S, colb * q->mem));
+  B2O_TRY(alloc0(&q->Y, colb * q->mem));
+  if (q->kind == 1 || !q->inverse) B2O_TRY(alloc0(&q->A, colb * q->mem));
+  if (q->kind == 0 && !q->inverse) B2O_TRY(alloc0(&q->B, colb * q->mem));
+  B2O_TRY(alloc0(&q->q, colb));
+  B2O_TRY(alloc0(&q->tmp, colb));
+  B2O_TRY(alloc0(&q->d_alpha, sizeof(double) * B2O_MAX_MEM));
+  q->ys.assign(q->mem, 0.0);
+  q->aux.assign(q->mem, 0.0);
+  return B2O_OK;
+}
+
+extern "C" int b2o_qn_destroy(b2o_qn *q) {
+  if (!q) return B2O_OK;
+  cudaSetDevice(q->ctx->device);
+  cudaStreamSynchronize(q->ctx->stream);
+  cudaFree(q->S);
+  cudaFree(q->Y);
+  cudaFree(q->A);
+  cudaFree(q->B);
+  cudaFree(q->q);
+  cudaFree(q->tmp);
+  cudaFree(q->d_alpha);
+  delete q;
+  return B2O_OK;
+}
+
+static int qn_create_common(b2o_ctx *ctx, int dtype, int64_t n, int mem, b2o_qn **out, b2o_qn **made) {
+  if (!ctx || !out) B2O_FAIL(B2O_EARG, "null argument");
+  B2O_TRY(b2o_check_dtype_f64(dtype));
+  if (n < 0) B2O_FAIL(B2O_EARG, "n must be >= 0");
+  if (mem < 1) mem = 1;  // LBFGSData clamps mem to max(mem,1) (src/lbfgs.jl:37)
+  if (mem > B2O_MAX_MEM) B2O_FAIL(B2O_EUNSUPPORTED, "mem=%d exceeds the built maximum %d", mem, B2O_MAX_MEM);
+  b2o_qn *q = new b2o_qn_s();
+  q->ctx = ctx;
+  q->n = n;
+  q->pitch = std::max<int64_t>(B2O_PITCH_ALIGN, (n + B2O_PITCH_ALIGN - 1) / B2O_PITCH_ALIGN * B2O_PITCH_ALIGN);
+  q->mem = mem;
+  *made = q;
+  return B2O_OK;
+}
+
+extern "C" int b2o_lbfgs_create(b2o_ctx *ctx, int dtype, int64_t n, int mem, int scaling, int damped, double sigma2,
+                                double sigma3, int inverse, b2o_qn **out) {
+  b2o_qn *q = nullptr;
+  B2O_TRY(qn_create_common(ctx, dtype, n, mem, out, &q));
+  q->kind = 0;
+  q->scaling = scaling != 0;
+  q->damped = damped != 0;
+  q->inverse = inverse != 0;
+  q->sigma2 = sigma2;
+  q->sigma3 = sigma3;
+  int st = qn_alloc(q);
+  if (st != B2O_OK) {
+    b2o_qn_destroy(q);
+    return st;
+  }
+  *out = q;
+  return B2O_OK;
+}
+
+extern "C" int b2o_lsr1_create(b2o_ctx *ctx, int dtype, int64_t n, int mem, int scaling, b2o_qn **out) {
+  b2o_qn *q = nullptr;
+  B2O_TRY(qn_create_common(ctx, dtype, n, mem, out, &q));
+  q->kind = 1;
+  q->scaling = scaling != 0;
+  int st = qn_alloc(q);
+  if (st != B2O_OK) {
+    b2o_qn_destroy(q);
+    return st;
+  }
+  *out = q;
+  return B2O_OK;
+}
+
+// ------------------------------------------------------------------ launch plumbing
+struct LaunchCfg {
+  int R, stages, grid, group;
+  SmemLayout L;
+};
+static int plan_launch(b2o_ctx *c, int64_t ntiles, int ncols, bool need_accs, LaunchCfg *cfg) {
+  cfg->R = c->tile_rows;
+  cfg->group = need_accs ? std::max(1, std::min(ncols, 40)) : 0;
+  const size_t max_smem = 227 * 1024;
+  int stages = 32;
+  for (;; --stages) {
+    cfg->L = smem_layout(cfg->R, stages, cfg->group);
+    if (cfg->L.total <= max_smem) break;
+    if (stages <= 2) B2O_FAIL(B2O_ECUDA, "shared memory plan does not fit");
+  }
+  if (c->stages > 0) stages = std::min(stages, std::max(2, c->stages));
+  cfg->stages = stages;
+  cfg->L = smem_layout(cfg->R, stages, cfg->group);
+  int g = c->grid > 0 ? c->grid : c->num_sms;
+  g = std::min(g, c->num_sms);  // co-residency: 1 CTA per SM
+  cfg->grid = (int)std::max<int64_t>(1, std::min<int64_t>(g, ntiles));
+  return B2O_OK;
+}
+
+template <typename K, typename Args>
+static int launch_persistent(b2o_ctx *c, K kern, const LaunchCfg &cfg, Args &args, bool cooperative) {
+  static thread_local const void *configured[64];
+  static thread_local int nconfigured = 0;
+  bool seen = false;
+  for (int i = 0; i < nconfigured; ++i) seen |= (configured[i] == (const void *)kern);
+  if (!seen) {
+    B2O_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (nconfigured < 64) configured[nconfigured++] = (const void *)kern;
+  }
+  if (c->time_kernels) B2O_CUDA(cudaEventRecord(c->ev0, c->stream));
+  void *kargs[] = {(void *)&args};
+  if (cooperative) {
+    B2O_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(cfg.grid), dim3(B2O_NTHREADS), kargs, cfg.L.total,
+                                         c->stream));
+  } else {
+    B2O_CUDA(cudaLaunchKernel((const void *)kern, dim3(cfg.grid), dim3(B2O_NTHREADS), kargs, cfg.L.total, c->stream));
+  }
+  c->launches++;
+  if (c->time_kernels) {
+    B2O_CUDA(cudaEventRecord(c->ev1, c->stream));
+    B2O_CUDA(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    B2O_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->kern_ms += ms;
+    c->kern_n++;
+  }
+  return B2O_OK;
+}
+
+template <int OP>
+static int launch_compact_R(b2o_ctx *c, const LaunchCfg &cfg, CompactArgs &a, bool coop) {
+  switch (cfg.R) {
+    case 1024: return launch_persistent(c, qn_compact_kernel<1024, OP>, cfg, a, coop);
+    case 2048: return launch_persistent(c, qn_compact_kernel<2048, OP>, cfg, a, coop);
+    case 4096: return launch_persistent(c, qn_compact_kernel<4096, OP>, cfg, a, coop);
+  }
+  B2O_FAIL(B2O_EARG, "bad tile_rows");
+}
+static int launch_twoloop_R(b2o_ctx *c, const LaunchCfg &cfg, TwoLoopArgs &a, bool coop) {
+  switch (cfg.R) {
+    case 1024: return launch_persistent(c, qn_twoloop_kernel<1024>, cfg, a, coop);
+    case 2048: return launch_persistent(c, qn_twoloop_kernel<2048>, cfg, a, coop);
+    case 4096: return launch_persistent(c, qn_twoloop_kernel<4096>, cfg, a, coop);
+  }
+  B2O_FAIL(B2O_EARG, "bad tile_rows");
+}
+
+// ordered list of active ring slots, oldest -> newest: k = mod(insert+i-2, mem)+1, ys[k] != 0
+// (src/lbfgs.jl:189-191, :141-143; src/lsr1.jl:98-100)
+static int active_old_to_new(const b2o_qn *q, int *slots) {
+  int na = 0;
+  for (int i = 1; i <= q->mem; ++i) {
+    int k = pmod(q->ins0 + i - 1, q->mem);
+    if (q->ys[k] != 0) slots[na++] = k;
+  }
+  return na;
+}
+
+// ------------------------------------------------------------------ apply
+static int qn_apply_compact(b2o_qn *q, double *res, const double *x, double alpha, double beta) {
+  b2o_ctx *c = q->ctx;
+  int slots[B2O_MAX_MEM];
+  const int na = active_old_to_new(q, slots);
+  CompactArgs a;
+  memset(&a, 0, sizeof(a));
+  if (q->kind == 0) {
+    for (int i = 0; i < na; ++i) {
+      a.cols[2 * i] = q->col(q->A, slots[i]);
+      a.cols[2 * i + 1] = q->col(q->B, slots[i]);
+      a.cdiv[2 * i] = a.cdiv[2 * i + 1] = 1.0;
+    }
+    a.ncols = 2 * na;
+  } else {
+    for (int i = 0; i < na; ++i) {
+      a.cols[i] = q->col(q->A, slots[i]);
+      a.cdiv[i] = q->aux[slots[i]];
+    }
+    a.ncols = na;
+  }
+  a.x = x;
+  a.res = res;
+  a.n = q->n;
+  LaunchCfg cfg;
+  cfg.R = c->tile_rows;
+  a.ntiles = (q->n + cfg.R - 1) / cfg.R;
+  B2O_TRY(plan_launch(c, a.ntiles, a.ncols, true, &cfg));
+  a.alpha = alpha;
+  a.beta = beta;
+  a.gamma = q->gamma;
+  a.scaling = q->scaling ? 1 : 0;
+  a.x_al16 = ((uintptr_t)x % 16) == 0;
+  a.res_al16 = ((uintptr_t)res % 16) == 0;
+  a.partials = c->d_partials;
+  a.dots = c->d_dots;
+  a.bar = c->d_bar;
+  a.arrive = c->d_bar + 1;
+  a.stages = cfg.stages;
+  a.group = std::max(1, cfg.group);
+  a.accs_off = (uint32_t)cfg.L.accs_off;
+  a.coef_off = (uint32_t)cfg.L.coef_off;
+  a.bar_off = (uint32_t)cfg.L.bar_off;
+  if (q->n == 0) return B2O_OK;
+  const bool split = c->nranks > 1 && a.ncols > 0;
+  auto launch = [&](bool coop) -> int {
+    return q->kind == 0 ? launch_compact_R<OP_LBFGS_FWD>(c, cfg, a, coop) : launch_compact_R<OP_LSR1>(c, cfg, a, coop);
+  };
+  if (!split) {
+    a.mode = a.ncols > 0 ? MODE_FUSED : MODE_PHASE2;
+    a.bar_target = c->bar_base + (unsigned long long)cfg.grid;
+    B2O_TRY(launch(a.ncols > 0));
+    if (a.ncols > 0) c->bar_base += (unsigned long long)cfg.grid;
+  } else {
+    // row-partitioned: local dots -> one all-reduce of ncols scalars -> combine
+    a.mode = MODE_PHASE1;
+    B2O_TRY(launch(false));
+    B2O_TRY(b2o_allreduce_sum_f64(c, c->d_dots, a.ncols));
+    a.mode = MODE_PHASE2;
+    B2O_TRY(launch(false));
+  }
+  return B2O_OK;
+}
+
+// A == 0 (fresh / reset operator): q = x; scaling && q *= γ; res = α q (+ β res)
+__global__ void twoloop_empty_kernel(double *res, const double *x, double alpha, double beta, double gamma, int scaling,
+                                     int64_t n) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double q = x[i];
+    if (scaling) q = q * gamma;
+    res[i] = (beta != 0.0) ? alpha * q + beta * res[i] : alpha * q;
+  }
+}
+
+static int qn_apply_twoloop(b2o_qn *q, double *res, const double *x, double alpha, double beta) {
+  b2o_ctx *c = q->ctx;
+  int o2n[B2O_MAX_MEM];
+  const int na = active_old_to_new(q, o2n);
+  if (q->n == 0) return B2O_OK;
+  if (na == 0) {
+    twoloop_empty_kernel<<<ew_grid(c, q->n), 256, 0, c->stream>>>(res, x, alpha, beta, q->gamma, q->scaling ? 1 : 0, q->n);
+    c->launches++;
+    B2O_CUDA(cudaGetLastError());
+    return B2O_OK;
+  }
+  TwoLoopArgs a;
+  memset(&a, 0, sizeof(a));
+  // loop 1 runs newest -> oldest: k = mod(insert-i-1, mem)+1 (src/lbfgs.jl:130-131) = reverse of o2n
+  for (int i = 0; i < na; ++i) {
+    int k = o2n[na - 1 - i];
+    a.s[i] = q->col(q->S, k);
+    a.y[i] = q->col(q->Y, k);
+    a.ys[i] = q->ys[k];
+  }
+  a.nact = na;
+  a.x = x;
+  a.res = res;
+  a.q = q->q;
+  a.alpha_out = q->d_alpha;
+  a.n = q->n;
+  LaunchCfg cfg;
+  cfg.R = c->tile_rows;
+  a.ntiles = (q->n + cfg.R - 1) / cfg.R;
+  B2O_TRY(plan_launch(c, a.ntiles, 0, false, &cfg));
+  a.alpha = alpha;
+  a.beta = beta;
+  a.gamma = q->gamma;
+  a.scaling = q->scaling ? 1 : 0;
+  a.x_al16 = ((uintptr_t)x % 16) == 0;
+  a.res_al16 = ((uintptr_t)res % 16) == 0;
+  a.partials = c->d_partials;
+  a.dots = c->d_dots;
+  a.bar = c->d_bar;
+  a.arrive = c->d_bar + 1;
+  a.stages = cfg.stages;
+  a.coef_off = (uint32_t)cfg.L.coef_off;
+  a.bar_off = (uint32_t)cfg.L.bar_off;
+  const int nsweeps = 2 * na + 1;
+  if (c->nranks <= 1) {
+    a.sweep_begin = 0;
+    a.sweep_end = nsweeps;
+    a.bar_target = c->bar_base + (unsigned long long)cfg.grid;
+    B2O_TRY(launch_twoloop_R(c, cfg, a, true));
+    c->bar_base += (unsigned long long)cfg.grid * (unsigned long long)(2 * na);
+  } else {
+    // row-partitioned: one launch + one NCCL all-reduce per inner product (north_star / SURVEY §8e)
+    for (int w = 0; w < nsweeps; ++w) {
+      a.sweep_begin = w;
+      a.sweep_end = w + 1;
+      B2O_TRY(launch_twoloop_R(c, cfg, a, false));
+      if (w < nsweeps - 1) B2O_TRY(b2o_allreduce_sum_f64(c, c->d_dots, 1));
+    }
+  }
+  return B2O_OK;
+}
+
+static int qn_apply_dev(b2o_qn *q, double *res, const double *x, double alpha, double beta) {
+  if (q->kind == 0 && q->inverse) return qn_apply_twoloop(q, res, x, alpha, beta);
+  return qn_apply_compact(q, res, x, alpha, beta);
+}
+
+extern "C" int b2o_qn_apply(b2o_qn *q, void *res, int64_t res_len, const void *x, int64_t x_len, double alpha,
+                            double beta) {
+  if (!q) B2O_FAIL(B2O_EARG, "null operator");
+  if (x_len != q->n || res_len != q->n) B2O_FAIL(B2O_ESHAPE, "shape mismatch");
+  if ((!res || !x) && q->n > 0) B2O_FAIL(B2O_EARG, "null vector");
+  if (((uintptr_t)res | (uintptr_t)x) % 8) B2O_FAIL(B2O_EARG, "vectors must be 8-byte aligned");
+  B2O_CUDA(cudaSetDevice(q->ctx->device));
+  return qn_apply_dev(q, (double *)res, (const double *)x, alpha, beta);
+}
+
+static int ensure_stage(b2o_ctx *c, size_t bytes) {
+  if (c->stage_bytes >= bytes) return B2O_OK;
+  if (c->stage_x) cudaFree(c->stage_x);
+  if (c->stage_res) cudaFree(c->stage_res);
+  c->stage_x = c->stage_res = nullptr;
+  c->stage_bytes = 0;
+  cudaError_t e1 = cudaMalloc(&c->stage_x, bytes), e2 = cudaMalloc(&c->stage_res, bytes);
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    cudaGetLastError();
+    B2O_FAIL(B2O_ENOMEM, "staging allocation of %zu bytes failed", bytes);
+  }
+  c->stage_bytes = bytes;
+  return B2O_OK;
+}
+
+extern "C" int b2o_qn_apply_host(b2o_qn *q, void *res_host, const void *x_host, int64_t len, double alpha, double beta) {
+  if (!q) B2O_FAIL(B2O_EARG, "null operator");
+  if (len != q->n) B2O_FAIL(B2O_ESHAPE, "shape mismatch");
+  b2o_ctx *c = q->ctx;
+  B2O_CUDA(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)q->n * sizeof(double);
+  B2O_TRY(ensure_stage(c, std::max<size_t>(bytes, 16)));
+  B2O_CUDA(cudaMemcpyAsync(c->stage_x, x_host, bytes, cudaMemcpyHostToDevice, c->stream));
+  if (beta != 0.0) B2O_CUDA(cudaMemcpyAsync(c->stage_res, res_host, bytes, cudaMemcpyHostToDevice, c->stream));
+  B2O_TRY(qn_apply_dev(q, (double *)c->stage_res, (const double *)c->stage_x, alpha, beta));
+  B2O_CUDA(cudaMemcpyAsync(res_host, c->stage_res, bytes, cudaMemcpyDeviceToHost, c->stream));
+  B2O_CUDA(cudaStreamSynchronize(c->stream));
+  return B2O_OK;
+}
+
+extern "C" int b2o_qn_apply_bytes(b2o_qn *q, double beta, double *bytes) {
+  if (!q || !bytes) B2O_FAIL(B2O_EARG, "null argument");
+  int slots[B2O_MAX_MEM];
+  const int na = active_old_to_new(q, slots);
+  double per_row;
+  if (q->kind == 0 && q->inverse) per_row = na > 0 ? 8.0 * na + 2.0 : 2.0;   // (8m+2) n E   SURVEY App. A
+  else if (q->kind == 0) per_row = na > 0 ? 4.0 * na + 3.0 : 2.0;            // (4m+3) n E
+  else per_row = na > 0 ? 2.0 * na + 3.0 : 2.0;                              // (2m+3) n E
+  if (beta != 0.0) per_row += 1.0;
+  *bytes = per_row * 8.0 * (double)q->n;
+  return B2O_OK;
+}
+
+// ------------------------------------------------------------------ push!
+static int lincomb_launch(b2o_ctx *c, LincombArgs &a) {
+  a.partials = c->d_partials;
+  a.arrive = c->d_bar + 1;
+  int grid = ew_grid(c, a.n);
+  lincomb_kernel<<<grid, 256, 0, c->stream>>>(a);
+  c->launches++;
+  B2O_CUDA(cudaGetLastError());
+  return B2O_OK;
+}
+
+// dots of `ncols` columns against v into d_out[0..ncols) (8 per pass)
+static int multi_dots(b2o_ctx *c, int ncols, const double *const *cols, const double *v, int64_t n, double *d_out) {
+  for (int off = 0; off < ncols; off += 8) {
+    int np = std::min(8, ncols - off);
+    const double *u[8], *w[8];
+    for (int p = 0; p < np; ++p) {
+      u[p] = cols[off + p];
+      w[p] = v;
+    }
+    B2O_TRY(b2o_pair_dots(c, np, u, w, n, d_out + off));
+  }
+  return B2O_OK;
+}
+
+// push_common!  src/lbfgs.jl:210-255.  s, y device vectors (y may be the damped y); ys, yy host scalars.
+static int lbfgs_push_common(b2o_qn *q, const double *s, const double *y, double ys, double yy) {
+  b2o_ctx *c = q->ctx;
+  const int64_t n = q->n;
+  const int mem = q->mem, ins = q->ins0;
+  const size_t bytes = (size_t)n * sizeof(double);
+  B2O_CUDA(cudaMemcpyAsync(q->col(q->S, ins), s, bytes, cudaMemcpyDeviceToDevice, c->stream));   // :220
+  B2O_CUDA(cudaMemcpyAsync(q->col(q->Y, ins), y, bytes, cudaMemcpyDeviceToDevice, c->stream));   // :221
+  q->ys[ins] = ys;                                                                              // :222
+  if (q->scaling) {                                                                             // :223-227
+    if (q->gamma != 0) q->opnorm_ub -= 1 / q->gamma;
+    q->gamma = ys / yy;
+    if (q->gamma != 0) q->opnorm_ub += 1 / q->gamma;
+  }
+  if (!q->inverse) {
+    double *bi = q->col(q->B, ins);
+    q->opnorm_ub -= q->aux[ins] * q->aux[ins];                                                  // :231
+    if (n > 0) {
+      div_kernel<<<ew_grid(c, n), 256, 0, c->stream>>>(bi, y, sqrt(ys), n);                     // :232 b = y ./ sqrt(ys)
+      c->launches++;
+    }
+    {
+      const double *u[1] = {bi}, *v[1] = {bi};
+      double nb2 = 0;
+      B2O_TRY(b2o_pair_dots(c, 1, u, v, n, c->d_dots + 300));
+      B2O_TRY(b2o_read_scalars(c, c->d_dots + 300, 1, &nb2));
+      q->aux[ins] = sqrt(nb2);                                                                  // :233 norm_b
+    }
+    q->opnorm_ub += q->aux[ins] * q->aux[ins];
+    // rebuild every a_k, oldest -> newest (the new pair is last): k = mod(insert+i-1, mem)+1   :236-250
+    int prev[B2O_MAX_MEM];
+    int nprev = 0;
+    for (int i = 1; i <= mem; ++i) {
+      const int k = pmod(ins + i, mem);
+      if (q->ys[k] == 0) continue;
+      const double *sk = q->col(q->S, k);
+      double *ak = q->col(q->A, k);
+      LincombArgs a;
+      memset(&a, 0, sizeof(a));
+      const double *dcols[B2O_MAX_COLS];
+      for (int j = 0; j < nprev; ++j) {
+        // a[k] .+= dot(b[l], s[k]) .* b[l] ; a[k] .-= dot(a[l], s[k]) .* a[l]                   :244-245
+        a.cols[2 * j] = q->col(q->B, prev[j]);
+        a.sign[2 * j] = +1;
+        a.cols[2 * j + 1] = q->col(q->A, prev[j]);
+        a.sign[2 * j + 1] = -1;
+        a.cdiv[2 * j] = a.cdiv[2 * j + 1] = 1.0;
+        dcols[2 * j] = a.cols[2 * j];
+        dcols[2 * j + 1] = a.cols[2 * j + 1];
+      }
+      a.nterms = 2 * nprev;
+      B2O_TRY(multi_dots(c, a.nterms, dcols, sk, n, c->d_dots));
+      a.base_mode = 0;  // a[k] .= s[k] ./ γ                                                     :239
+      a.P1 = sk;
+      a.g = q->gamma;
+      a.dots = c->d_dots;
+      a.u0 = sk;
+      a.out = ak;
+      a.n = n;
+      a.red = c->d_dots + 256;
+      if (n > 0) {
+        B2O_TRY(lincomb_launch(c, a));
+        B2O_TRY(b2o_allreduce_sum_f64(c, c->d_dots + 256, 2));
+        div_sqrt_dev_kernel<<<ew_grid(c, n), 256, 0, c->stream>>>(ak, ak, c->d_dots + 256, n);   // :248
+        c->launches++;
+      }
+      prev[nprev++] = k;
+    }
+    B2O_CUDA(cudaGetLastError());
+  }
+  q->ins0 = pmod(ins + 1, mem);                                                                 // :253
+  return B2O_OK;
+}
+
+static int check_vec(const b2o_qn *q, const void *p, int64_t len) {
+  if (len != q->n) B2O_FAIL(B2O_ESHAPE, "shape mismatch");
+  if (!p && q->n > 0) B2O_FAIL(B2O_EARG, "null vector");
+  if ((uintptr_t)p % 8) B2O_FAIL(B2O_EARG, "vectors must be 8-byte aligned");
+  return B2O_OK;
+}
+
+static int lsr1_push(b2o_qn *q, const double *s, const double *y, int *accepted);
+
+extern "C" int b2o_lbfgs_push_damped_fwd(b2o_qn *q, const void *s_, const void *y_, void *Bs_, int64_t len, int *accepted) {
+  if (!q || q->kind != 0) B2O_FAIL(B2O_EARG, "not an L-BFGS operator");
+  if (!q->damped) B2O_FAIL(B2O_ESTATE, "This push! should be used for damped operators");
+  if (q->inverse) B2O_FAIL(B2O_ESTATE, "This function be used for forward operators. Use push!(op, s, y, α, g, Bs) instead.");
+  B2O_TRY(check_vec(q, s_, len));
+  B2O_TRY(check_vec(q, y_, len));
+  B2O_TRY(check_vec(q, Bs_, len));
+  b2o_ctx *c = q->ctx;
+  B2O_CUDA(cudaSetDevice(c->device));
+  const double *s = (const double *)s_, *y = (const double *)y_;
+  double *Bs = (double *)Bs_;
+  const int64_t n = q->n;
+  B2O_TRY(qn_apply_dev(q, Bs, s, 1.0, 0.0));                                                    // :305
+  const double *u[3] = {y, s, y}, *v[3] = {s, Bs, y};
+  double h[3];
+  B2O_TRY(b2o_pair_dots(c, 3, u, v, n, c->d_dots + 300));
+  B2O_TRY(b2o_read_scalars(c, c->d_dots + 300, 3, h));
+  double ys = h[0], sBs = h[1], yy = h[2];
+  bool damp = false;
+  double th = 0;
+  if (ys < (1 - q->sigma2) * sBs) {                                                             // :308-314
+    th = q->sigma2 * sBs / (sBs - ys);
+    damp = true;
+  } else if (ys > (1 + q->sigma3) * sBs) {
+    th = q->sigma3 * sBs / (ys - sBs);
+    damp = true;
+  }
+  const double *yuse = y;
+  if (damp) {
+    B2O_TRY(ew_axpby(c, q->tmp, th, y, 1 - th, Bs, n));                                         // :316 damped y
+    ys = th * ys + (1 - th) * sBs;
+    yuse = q->tmp;
+    if (q->scaling) {
+      const double *u2[1] = {q->tmp}, *v2[1] = {q->tmp};
+      B2O_TRY(b2o_pair_dots(c, 1, u2, v2, n, c->d_dots + 300));
+      B2O_TRY(b2o_read_scalars(c, c->d_dots + 300, 1, &yy));
+    }
+  }
+  B2O_TRY(lbfgs_push_common(q, s, yuse, ys, yy));
+  if (accepted) *accepted = 1;
+  return B2O_OK;
+}
+
+extern "C" int b2o_lbfgs_push_damped_inv(b2o_qn *q, const void *s_, void *y_, double alpha, const void *g_, void *Bs_,
+                                         int64_t len, int *accepted) {
+  if (!q || q->kind != 0) B2O_FAIL(B2O_EARG, "not an L-BFGS operator");
+  if (!q->damped) B2O_FAIL(B2O_ESTATE, "This push! should be used for damped operators");
+  if (!q->inverse) B2O_FAIL(B2O_ESTATE, "This function be used for inverse operators. Use push!(op, s, y, Bs) instead.");
+  B2O_TRY(check_vec(q, s_, len));
+  B2O_TRY(check_vec(q, y_, len));
+  B2O_TRY(check_vec(q, g_, len));
+  B2O_TRY(check_vec(q, Bs_, len));
+  b2o_ctx *c = q->ctx;
+  B2O_CUDA(cudaSetDevice(c->device));
+  const double *s = (const double *)s_, *g = (const double *)g_;
+  double *y = (double *)y_, *Bs = (double *)Bs_;
+  const int64_t n = q->n;
+  B2O_TRY(ew_axpby(c, Bs, -alpha, g, 0.0, nullptr, n));                                         // :341 Bs .= -α .* g
+  const double *u[3] = {y, s, y}, *v[3] = {s, Bs, y};
+  double h[3];
+  B2O_TRY(b2o_pair_dots(c, 3, u, v, n, c->d_dots + 300));
+  B2O_TRY(b2o_read_scalars(c, c->d_dots + 300, 3, h));
+  double ys = h[0], sBs = h[1], yy = h[2];
+  bool damp = false;
+  double th = 0;
+  if (ys < (1 - q->sigma2) * sBs) {
+    th = q->sigma2 * sBs / (sBs - ys);
+    damp = true;
+  } else if (ys > (1 + q->sigma3) * sBs) {
+    th = q->sigma3 * sBs / (ys - sBs);
+    damp = true;
+  }
+  if (damp) {
+    B2O_TRY(ew_axpby(c, y, th, y, 1 - th, Bs, n));                                              // :352 y .= θ y + (1-θ) Bs
+    ys = th * ys + (1 - th) * sBs;
+    if (q->scaling) {
+      const double *u2[1] = {y}, *v2[1] = {y};
+      B2O_TRY(b2o_pair_dots(c, 1, u2, v2, n, c->d_dots + 300));
+      B2O_TRY(b2o_read_scalars(c, c->d_dots + 300, 1, &yy));
+    }
+  }
+  B2O_TRY(lbfgs_push_common(q, s, y, ys, yy));
+  if (accepted) *accepted = 1;
+  return B2O_OK;
+}
+
+extern "C" int b2o_qn_push(b2o_qn *q, const void *s_, const void *y_, int64_t len, int *accepted) {
+  if (!q) B2O_FAIL(B2O_EARG, "null operator");
+  B2O_TRY(check_vec(q, s_, len));
+  B2O_TRY(check_vec(q, y_, len));
+  b2o_ctx *c = q->ctx;
+  B2O_CUDA(cudaSetDevice(c->device));
+  const double *s = (const double *)s_, *y = (const double *)y_;
+  if (accepted) *accepted = 0;
+  if (q->kind == 1) return lsr1_push(q, s, y, accepted);
+  if (q->damped) {
+    // push!(op,s,y) on a damped operator forwards to push!(op,s,y,similar(s)) (src/lbfgs.jl:274-276), which
+    // errors for inverse operators (:296-298).  The library scratch q->q plays the role of similar(s).
+    if (q->inverse) B2O_FAIL(B2O_ESTATE, "This function be used for forward operators. Use push!(op, s, y, α, g, Bs) instead.");
+    return b2o_lbfgs_push_damped_fwd(q, s_, y_, q->q, len, accepted);
+  }
+  const double *u[2] = {y, y}, *v[2] = {s, y};
+  double h[2];
+  B2O_TRY(b2o_pair_dots(c, 2, u, v, q->n, c->d_dots + 300));
+  B2O_TRY(b2o_read_scalars(c, c->d_dots + 300, 2, h));
+  if (h[0] <= DBL_EPSILON) return B2O_OK;                                                       // :281 rejected
+  B2O_TRY(lbfgs_push_common(q, s, y, h[0], h[1]));
+  if (accepted) *accepted = 1;
+  return B2O_OK;
+}
+
+// push!  src/lsr1.jl:119-184
+static int lsr1_push(b2o_qn *q, const double *s, const double *y, int *accepted) {
+  b2o_ctx *c = q->ctx;
+  const int64_t n = q->n;
+  const int mem = q->mem;
+  const size_t bytes = (size_t)n * sizeof(double);
+  double *t = q->tmp;
+  B2O_CUDA(cudaMemcpyAsync(t, y, bytes, cudaMemcpyDeviceToDevice, c->stream));                  // :124
+  B2O_TRY(qn_apply_dev(q, t, s, -1.0, 1.0));                                                    // :125 ymBs = y - B s
+  const double *u[5] = {y, s, y, t, t}, *v[5] = {s, s, y, s, t};
+  double h[5];
+  B2O_TRY(b2o_pair_dots(c, 5, u, v, n, c->d_dots + 300));
+  B2O_TRY(b2o_read_scalars(c, c->d_dots + 300, 5, h));
+  const double ys = h[0], sNorm = sqrt(h[1]), yy = h[2];
+  const double eps = DBL_EPSILON;
+  const bool well_defined = fabs(h[3]) >= eps + eps * sqrt(h[4]) * sNorm;                       // :131
+  bool sufficient_curvature = true, scaling_condition = true;
+  if (q->scaling) {                                                                             // :135-143
+    const double yNorm = sqrt(yy);
+    sufficient_curvature = fabs(ys) >= eps * yNorm * sNorm;
+    if (sufficient_curvature) {
+      const double sf = ys / yy;
+      LincombArgs a;
+      memset(&a, 0, sizeof(a));
+      a.nterms = 0;
+      a.base_mode = 1;  // tmp .= y .- s ./ sf
+      a.P0 = y;
+      a.P1 = s;
+      a.g = sf;
+      a.dots = c->d_dots;
+      a.out = t;
+      a.n = n;
+      a.red = c->d_dots + 256;
+      double r[2] = {0, 0};
+      if (n > 0) {
+        B2O_TRY(lincomb_launch(c, a));
+        B2O_TRY(b2o_allreduce_sum_f64(c, c->d_dots + 256, 2));
+        B2O_TRY(b2o_read_scalars(c, c->d_dots + 256, 2, r));
+      }
+      scaling_condition = sqrt(r[1]) >= eps * yNorm * sNorm;
+    }
+  }
+  if (!(well_defined && sufficient_curvature && scaling_condition)) return B2O_OK;              // :145-149 rejected
+  const int ins = q->ins0;
+  B2O_CUDA(cudaMemcpyAsync(q->col(q->S, ins), s, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  B2O_CUDA(cudaMemcpyAsync(q->col(q->Y, ins), y, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  q->ys[ins] = ys;
+  q->opnorm_ub = 1.0;                                                                           // :156
+  if (q->scaling) {
+    q->gamma = ys / yy;
+    if (q->gamma != 0) q->opnorm_ub = 1 / fabs(q->gamma);
+  }
+  q->ins0 = pmod(ins + 1, mem);                                                                 // :163
+  int prev[B2O_MAX_MEM];
+  int nprev = 0;
+  for (int i = 1; i <= mem; ++i) {                                                              // :166
+    const int k = pmod(q->ins0 + i - 1, mem);
+    if (q->ys[k] == 0) continue;
+    const double *sk = q->col(q->S, k), *yk = q->col(q->Y, k);
+    double *ak = q->col(q->A, k);
+    LincombArgs a;
+    memset(&a, 0, sizeof(a));
+    const double *dcols[B2O_MAX_COLS];
+    for (int j = 0; j < nprev; ++j) {
+      a.cols[j] = q->col(q->A, prev[j]);                                                        // as = dot(a[l], s[k]) / as[l]
+      a.sign[j] = -1;                                                                           // a[k] .-= as .* a[l]   :173-174
+      a.cdiv[j] = q->aux[prev[j]];
+      dcols[j] = a.cols[j];
+    }
+    a.nterms = nprev;
+    B2O_TRY(multi_dots(c, a.nterms, dcols, sk, n, c->d_dots));
+    a.base_mode = 1;  // a[k] .= y[k] .- s[k] ./ γ                                               :169
+    a.P0 = yk;
+    a.P1 = sk;
+    a.g = q->gamma;
+    a.dots = c->d_dots;
+    a.u0 = sk;
+    a.out = ak;
+    a.n = n;
+    a.red = c->d_dots + 256;
+    double r[2] = {0, 0};
+    if (n > 0) {
+      B2O_TRY(lincomb_launch(c, a));
+      B2O_TRY(b2o_allreduce_sum_f64(c, c->d_dots + 256, 2));
+      B2O_TRY(b2o_read_scalars(c, c->d_dots + 256, 2, r));
+    }
+    q->aux[k] = r[0];                                                                           // :177 as[k] = dot(a[k], s[k])
+    if (q->aux[k] != 0) q->opnorm_ub += r[1] / fabs(q->aux[k]);                                 // :179
+    prev[nprev++] = k;
+  }
+  if (accepted) *accepted = 1;
+  return B2O_OK;
+}
+
+// ------------------------------------------------------------------ diag! / reset! / state
+extern "C" int b2o_qn_diag(b2o_qn *q, void *d, int64_t d_len) {
+  if (!q) B2O_FAIL(B2O_EARG, "null operator");
+  if (q->kind == 0 && q->inverse)
+    B2O_FAIL(B2O_ESTATE, "only the diagonal of a forward L-BFGS approximation is available");  // src/lbfgs.jl:380-382
+  B2O_TRY(check_vec(q, d, d_len));
+  b2o_ctx *c = q->ctx;
+  B2O_CUDA(cudaSetDevice(c->device));
+  if (q->n == 0) return B2O_OK;
+  int slots[B2O_MAX_MEM];
+  const int na = active_old_to_new(q, slots);
+  DiagArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int i = 0; i < na; ++i) {
+    a.c0[i] = q->col(q->A, slots[i]);
+    a.c1[i] = q->kind == 0 ? q->col(q->B, slots[i]) : nullptr;
+    a.cdiv[i] = q->kind == 1 ? q->aux[slots[i]] : 1.0;
+  }
+  a.nact = na;
+  a.kind = q->kind;
+  a.scaling = q->scaling ? 1 : 0;
+  a.gamma = q->gamma;
+  a.d = (double *)d;
+  a.n = q->n;
+  qn_diag_kernel<<<ew_grid(c, q->n), 256, 0, c->stream>>>(a);
+  c->launches++;
+  B2O_CUDA(cudaGetLastError());
+  return B2O_OK;
+}
+
+extern "C" int b2o_qn_reset(b2o_qn *q) {
+  if (!q) B2O_FAIL(B2O_EARG, "null operator");
+  b2o_ctx *c = q->ctx;
+  B2O_CUDA(cudaSetDevice(c->device));
+  const size_t colb = (size_t)q->pitch * sizeof(double) * q->mem;
+  B2O_CUDA(cudaMemsetAsync(q->S, 0, colb, c->stream));
+  B2O_CUDA(cudaMemsetAsync(q->Y, 0, colb, c->stream));
+  if (q->A) B2O_CUDA(cudaMemsetAsync(q->A, 0, colb, c->stream));
+  if (q->B) B2O_CUDA(cudaMemsetAsync(q->B, 0, colb, c->stream));
+  std::fill(q->ys.begin(), q->ys.end(), 0.0);
+  // L-BFGS reset! zeroes α but leaves norm_b / opnorm_upper_bound (Q8, src/lbfgs.jl:401-415); L-SR1 zeroes `as`.
+  if (q->kind == 1 || q->inverse) std::fill(q->aux.begin(), q->aux.end(), 0.0);
+  q->gamma = 1.0;
+  q->ins0 = 0;
+  return B2O_OK;
+}
+
+static double *qn_base(b2o_qn *q, int which) {
+  switch (which) {
+    case 0: return q->S;
+    case 1: return q->Y;
+    case 2: return q->A;
+    case 3: return q->B;
+  }
+  return nullptr;
+}
+extern "C" int b2o_qn_get_col(b2o_qn *q, int which, int k0, void *dst) {
+  if (!q || !dst) B2O_FAIL(B2O_EARG, "null argument");
+  double *base = qn_base(q, which);
+  if (!base || k0 < 0 || k0 >= q->mem) B2O_FAIL(B2O_EARG, "no such column (which=%d, k0=%d)", which, k0);
+  B2O_CUDA(cudaMemcpyAsync(dst, q->col(base, k0), (size_t)q->n * sizeof(double), cudaMemcpyDeviceToDevice, q->ctx->stream));
+  return B2O_OK;
+}
+extern "C" int b2o_qn_set_col(b2o_qn *q, int which, int k0, const void *src) {
+  if (!q || !src) B2O_FAIL(B2O_EARG, "null argument");
+  double *base = qn_base(q, which);
+  if (!base || k0 < 0 || k0 >= q->mem) B2O_FAIL(B2O_EARG, "no such column (which=%d, k0=%d)", which, k0);
+  B2O_CUDA(cudaMemcpyAsync(q->col(base, k0), src, (size_t)q->n * sizeof(double), cudaMemcpyDeviceToDevice, q->ctx->stream));
+  return B2O_OK;
+}
+extern "C" int b2o_qn_get_scalars(b2o_qn *q, int *insert1, double *gamma, double *opnorm_ub, double *ys, double *aux) {
+  if (!q) B2O_FAIL(B2O_EARG, "null operator");
+  if (insert1) *insert1 = q->ins0 + 1;
+  if (gamma) *gamma = q->gamma;
+  if (opnorm_ub) *opnorm_ub = q->opnorm_ub;
+  if (ys) memcpy(ys, q->ys.data(), sizeof(double) * q->mem);
+  if (aux) {
+    if (q->kind == 0 && q->inverse) {
+      // data.α lives on the device in loop-1 (newest -> oldest) order; scatter back to ring slots
+      int o2n[B2O_MAX_MEM];
+      const int na = active_old_to_new(q, o2n);
+      double h[B2O_MAX_MEM];
+      B2O_TRY(b2o_read_scalars(q->ctx, q->d_alpha, B2O_MAX_MEM, h));
+      for (int i = 0; i < na; ++i) q->aux[o2n[na - 1 - i]] = h[i];
+    }
+    memcpy(aux, q->aux.data(), sizeof(double) * q->mem);
+  }
+  return B2O_OK;
+}
+extern "C" int b2o_qn_set_scalars(b2o_qn *q, int insert1, double gamma, double opnorm_ub, const double *ys,
+                                  const double *aux) {
+  if (!q) B2O_FAIL(B2O_EARG, "null operator");
+  if (insert1 < 1 || insert1 > q->mem) B2O_FAIL(B2O_EARG, "insert out of range");
+  q->ins0 = insert1 - 1;
+  q->gamma = gamma;
+  q->opnorm_ub = opnorm_ub;
+  if (ys) q->ys.assign(ys, ys + q->mem);
+  if (aux) q->aux.assign(aux, aux + q->mem);
+  return B2O_OK;
+}

@@ -1,0 +1,458 @@
+// b2o_qn_kernels.cuh -- persistent kernels for the quasi-Newton applies.
+//
+//  qn_compact_kernel<R,OP> : forward LBFGSOperator (src/lbfgs.jl:173-202) and LSR1Operator
+//                            (src/lsr1.jl:89-107) applies.  Phase 1 streams every active column once and
+//                            takes all dots against x; grid barrier; phase 2 re-streams the columns and
+//                            writes res.  Algorithmic DRAM bytes (2*ncols+3)*8*n (+8n if beta != 0).
+//  qn_twoloop_kernel<R>    : InverseLBFGSOperator two-loop recursion (src/lbfgs.jl:117-154) as 2A+1
+//                            sweeps, the axpy of step i fused with the dot of step i+1.
+//                            Algorithmic DRAM bytes (8A+2)*8*n.
+#pragma once
+#include "b2o_stream.cuh"
+
+enum { OP_LBFGS_FWD = 0, OP_LSR1 = 1 };
+enum { MODE_FUSED = 0, MODE_PHASE1 = 1, MODE_PHASE2 = 2 };
+
+struct CompactArgs {
+  const double *cols[B2O_MAX_COLS];  // active columns in reference order (LBFGS: a_k,b_k pairs oldest->newest)
+  double cdiv[B2O_MAX_COLS];         // LSR1: as[k]
+  int ncols;
+  const double *x;
+  double *res;
+  int64_t n, ntiles;
+  double alpha, beta, gamma;
+  int scaling;
+  int x_al16, res_al16;
+  double *partials;                  // [grid][ncols]
+  double *dots;                      // [ncols] (split mode)
+  unsigned long long *bar;           // grid barrier counter (monotonic)
+  unsigned long long bar_target;
+  unsigned long long *arrive;        // last-block counter (split mode)
+  int mode, stages, group;
+  uint32_t accs_off, coef_off, bar_off;
+};
+
+template <int R, int OP>
+__global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __grid_constant__ CompactArgs p) {
+  constexpr int EPT = R / B2O_NCONS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Ring rg;
+  rg.buf = reinterpret_cast<double *>(smem_raw);
+  double *accs = reinterpret_cast<double *>(smem_raw + p.accs_off);
+  double *coef = reinterpret_cast<double *>(smem_raw + p.coef_off);
+  rg.full = reinterpret_cast<uint64_t *>(smem_raw + p.bar_off);
+  rg.empty = rg.full + p.stages;
+  rg.stages = p.stages;
+  __shared__ bool s_is_last;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool is_producer = warp == B2O_CONS_WARPS;
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&rg.full[s], 1);
+      mbar_init(&rg.empty[s], B2O_CONS_WARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  RingPos pos(p.stages);
+  const int64_t grid = gridDim.x;
+  const int64_t my_tiles = (p.ntiles > (int64_t)blockIdx.x) ? (p.ntiles - 1 - blockIdx.x) / grid + 1 : 0;
+  const int ncols = p.ncols;
+
+  // ------------------------------------------------------------------ phase 1: all dots against x
+  if (p.mode != MODE_PHASE2 && ncols > 0) {
+    for (int g0 = 0; g0 < ncols; g0 += p.group) {
+      const int gc = min(p.group, ncols - g0);
+      if (is_producer) {
+        if (lane == 0) {
+          for (int64_t i = 0; i < my_tiles; ++i) {
+            const int64_t t = blockIdx.x + i * grid;
+            for (int c = 0; c < gc; ++c) producer_push<R>(rg, pos, p.cols[g0 + c] + t * R);
+          }
+        }
+        __syncwarp();
+      } else {
+        for (int c = 0; c < gc; ++c) accs[c * B2O_NCONS + tid] = 0.0;
+        double xr[EPT], xn[EPT];
+        if (my_tiles > 0) load_user_tile<R>(p.x, (int64_t)blockIdx.x * R, p.n, p.x_al16, xn);
+        for (int64_t i = 0; i < my_tiles; ++i) {
+          const int64_t t = blockIdx.x + i * grid;
+#pragma unroll
+          for (int j = 0; j < EPT; ++j) xr[j] = xn[j];
+          if (i + 1 < my_tiles) load_user_tile<R>(p.x, (t + grid) * R, p.n, p.x_al16, xn);
+          for (int c = 0; c < gc; ++c) {
+            mbar_wait(&rg.full[pos.slot], pos.par);
+            const double2 *b = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R);
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < EPT / 2; ++j) {
+              double2 v = b[j * B2O_NCONS + tid];
+              s0 = fma(v.x, xr[2 * j], s0);
+              s1 = fma(v.y, xr[2 * j + 1], s1);
+            }
+            accs[c * B2O_NCONS + tid] += s0 + s1;
+            consumer_release(rg, pos.slot);
+            pos.advance();
+          }
+        }
+        consumers_sync();
+        for (int c = warp; c < gc; c += B2O_CONS_WARPS) {
+          double s = 0.0;
+#pragma unroll
+          for (int w = 0; w < B2O_CONS_WARPS; ++w) s += accs[c * B2O_NCONS + w * 32 + lane];
+          s = warp_sum(s);
+          if (lane == 0) p.partials[(size_t)blockIdx.x * ncols + g0 + c] = s;
+        }
+        consumers_sync();
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------ reduce the dots
+  unsigned long long bar_target = p.bar_target;
+  if (ncols > 0) {
+    if (p.mode == MODE_FUSED) {
+      grid_barrier(p.bar, bar_target);
+      bar_target += gridDim.x;
+      if (!is_producer) {
+        for (int c = warp; c < ncols; c += B2O_CONS_WARPS) {
+          double s = 0.0;
+          for (int b = lane; b < (int)grid; b += 32) s += __ldcg(&p.partials[(size_t)b * ncols + c]);
+          s = warp_sum(s);
+          if (lane == 0) coef[c] = s;
+        }
+      }
+      __syncthreads();
+    } else if (p.mode == MODE_PHASE1) {
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        unsigned long long tk = atomicAdd(p.arrive, 1ULL);
+        s_is_last = (tk == gridDim.x - 1);
+      }
+      __syncthreads();
+      if (s_is_last) {
+        __threadfence();
+        if (!is_producer) {
+          for (int c = warp; c < ncols; c += B2O_CONS_WARPS) {
+            double s = 0.0;
+            for (int b = lane; b < (int)grid; b += 32) s += __ldcg(&p.partials[(size_t)b * ncols + c]);
+            s = warp_sum(s);
+            if (lane == 0) p.dots[c] = s;
+          }
+        }
+        if (tid == 0) *p.arrive = 0ULL;
+      }
+      return;
+    } else {
+      for (int c = tid; c < ncols; c += B2O_NTHREADS) coef[c] = __ldcg(&p.dots[c]);
+      __syncthreads();
+    }
+  } else if (p.mode == MODE_PHASE1) {
+    return;
+  }
+
+  // ------------------------------------------------------------------ phase 2: combine and write res
+  if (is_producer) {
+    if (lane == 0) {
+      for (int64_t i = my_tiles - 1; i >= 0; --i) {   // reverse order: the tail of phase 1 is still in L2
+        const int64_t t = blockIdx.x + i * grid;
+        for (int c = 0; c < ncols; ++c) producer_push<R>(rg, pos, p.cols[c] + t * R);
+      }
+    }
+    __syncwarp();
+  } else {
+    const double alpha = p.alpha, beta = p.beta, gamma = p.gamma;
+    double xn[EPT], q[EPT], rold[EPT];
+    if (my_tiles > 0) load_user_tile<R>(p.x, (blockIdx.x + (my_tiles - 1) * grid) * R, p.n, p.x_al16, xn);
+    for (int64_t i = my_tiles - 1; i >= 0; --i) {
+      const int64_t t = blockIdx.x + i * grid;
+      if (beta != 0.0) load_user_tile<R>(p.res, t * R, p.n, p.res_al16, rold);
+      if (OP == OP_LBFGS_FWD) {
+        // q .= x ; scaling && (q ./= γ)                                   src/lbfgs.jl:183-186
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) q[j] = p.scaling ? xn[j] / gamma : xn[j];
+      } else {
+        // q .= α .* x ./ γ (.+ β .* q)                                    src/lsr1.jl:92-96
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+          double v = (alpha * xn[j]) / gamma;
+          q[j] = (beta != 0.0) ? v + beta * rold[j] : v;
+        }
+      }
+      if (i > 0) load_user_tile<R>(p.x, (t - grid) * R, p.n, p.x_al16, xn);
+      if (OP == OP_LBFGS_FWD) {
+        for (int c = 0; c < ncols; c += 2) {
+          // q .+= bx .* b[k] .- ax .* a[k]                                src/lbfgs.jl:194
+          const uint32_t sa = pos.slot, pa = pos.par;
+          pos.advance();
+          const uint32_t sb = pos.slot, pb = pos.par;
+          pos.advance();
+          const double ax = coef[c], bx = coef[c + 1];
+          mbar_wait(&rg.full[sa], pa);
+          mbar_wait(&rg.full[sb], pb);
+          const double2 *A = reinterpret_cast<const double2 *>(rg.buf + (size_t)sa * R);
+          const double2 *B = reinterpret_cast<const double2 *>(rg.buf + (size_t)sb * R);
+#pragma unroll
+          for (int j = 0; j < EPT / 2; ++j) {
+            double2 a = A[j * B2O_NCONS + tid], b = B[j * B2O_NCONS + tid];
+            q[2 * j] = q[2 * j] + (bx * b.x - ax * a.x);
+            q[2 * j + 1] = q[2 * j + 1] + (bx * b.y - ax * a.y);
+          }
+          consumer_release(rg, sa);
+          consumer_release(rg, sb);
+        }
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) q[j] = (beta != 0.0) ? alpha * q[j] + beta * rold[j] : alpha * q[j];  // :197-201
+      } else {
+        for (int c = 0; c < ncols; ++c) {
+          // ax = α * dot(a[k], x) / as[k];  q[j] += ax * a[k][j]          src/lsr1.jl:101-104
+          const double ax = (alpha * coef[c]) / p.cdiv[c];
+          mbar_wait(&rg.full[pos.slot], pos.par);
+          const double2 *A = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R);
+#pragma unroll
+          for (int j = 0; j < EPT / 2; ++j) {
+            double2 a = A[j * B2O_NCONS + tid];
+            q[2 * j] = q[2 * j] + ax * a.x;
+            q[2 * j + 1] = q[2 * j + 1] + ax * a.y;
+          }
+          consumer_release(rg, pos.slot);
+          pos.advance();
+        }
+      }
+      store_user_tile<R>(p.res, t * R, p.n, p.res_al16, q);
+    }
+  }
+}
+
+// =====================================================================================================
+// Inverse L-BFGS two-loop recursion, src/lbfgs.jl:117-154
+// =====================================================================================================
+constexpr int B2O_MAX_MEM = 64;
+
+struct TwoLoopArgs {
+  const double *s[B2O_MAX_MEM];  // active slots ordered newest -> oldest (loop-1 order)
+  const double *y[B2O_MAX_MEM];
+  double ys[B2O_MAX_MEM];
+  int nact;
+  const double *x;
+  double *res;
+  double *q;                     // library-owned work vector (data.Ax), padded pitch
+  double *alpha_out;             // device copy of data.α in loop-1 order (may be null)
+  int64_t n, ntiles;
+  double alpha, beta, gamma;
+  int scaling;
+  int x_al16, res_al16;
+  double *partials;              // [grid]
+  double *dots;                  // step mode: dots[0] carries the reduced dot between launches, dots[1+i] the α_i
+  unsigned long long *bar;
+  unsigned long long bar_target;
+  unsigned long long *arrive;
+  int stages;
+  int sweep_begin, sweep_end;    // sweeps [begin,end) of 0..2A run in this launch (fused: 0..2A+1)
+  uint32_t coef_off, bar_off;
+};
+
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+template <int R>
+__global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_kernel(const __grid_constant__ TwoLoopArgs p) {
+  constexpr int EPT = R / B2O_NCONS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Ring rg;
+  rg.buf = reinterpret_cast<double *>(smem_raw);
+  double *sred = reinterpret_cast<double *>(smem_raw + p.coef_off);  // [8] warp partials + [8..8+64) α_i
+  double *alphas = sred + 8;
+  rg.full = reinterpret_cast<uint64_t *>(smem_raw + p.bar_off);
+  rg.empty = rg.full + p.stages;
+  rg.stages = p.stages;
+  __shared__ double s_dot;
+  __shared__ bool s_is_last;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool is_producer = warp == B2O_CONS_WARPS;
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&rg.full[s], 1);
+      mbar_init(&rg.empty[s], B2O_CONS_WARPS);
+    }
+    mbar_fence_init();
+  }
+  const int A = p.nact;
+  const bool fused = (p.sweep_end - p.sweep_begin) > 1 || (p.sweep_begin == 0 && p.sweep_end == 2 * A + 1);
+  if (p.sweep_begin > 0) {
+    // step mode: pick up the reduced dot and the α's of earlier launches
+    if (tid == 0) s_dot = __ldcg(&p.dots[0]);
+    for (int i = tid; i < A; i += B2O_NTHREADS) alphas[i] = __ldcg(&p.dots[1 + i]);
+  }
+  __syncthreads();
+
+  RingPos pos(p.stages);
+  const int64_t grid = gridDim.x;
+  const int64_t my_tiles = (p.ntiles > (int64_t)blockIdx.x) ? (p.ntiles - 1 - blockIdx.x) / grid + 1 : 0;
+  unsigned long long bar_target = p.bar_target;
+
+  for (int w = p.sweep_begin; w < p.sweep_end; ++w) {
+    // ---- describe sweep w (all threads compute the same thing)
+    // w = 0          : d = s[0]·x
+    // w = 1..A       : loop 1 step i=w  : q = qin - α_i y[i-1];  (i==A: q *= γ);  d = (i<A ? s[i] : y[A-1])·q
+    // w = A+1..2A    : loop 2 step i=w-A: slot o = A-i;  β' = α_o - d/ys_o;  q = q + β' s[o];  (i<A: d = y[o-1]·q) else res
+    const bool dot_only = (w == 0);
+    const bool loop1 = (w >= 1 && w <= A);
+    const bool last = (w == 2 * A);
+    const double *v1 = nullptr, *v2 = nullptr;
+    double c1 = 0.0;
+    bool qin_is_x = false;
+    bool apply_gamma = false;
+    if (dot_only) {
+      v2 = p.s[0];
+      qin_is_x = true;
+    } else if (loop1) {
+      const int i = w;
+      const double ak = s_dot / p.ys[i - 1];                      // αk = dot(s[k], q) / ys[k]      :133
+      if (tid == 0) alphas[i - 1] = ak;
+      c1 = ak;
+      v1 = p.y[i - 1];
+      qin_is_x = (i == 1);
+      apply_gamma = (i == A) && p.scaling;
+      v2 = (i < A) ? p.s[i] : p.y[A - 1];
+    } else {
+      const int i = w - A, o = A - i;
+      c1 = alphas[o] - s_dot / p.ys[o];                           // β = αk - dot(y[k], q) / ys[k]  :144-145
+      v1 = p.s[o];
+      v2 = last ? nullptr : p.y[o - 1];
+    }
+    __syncthreads();  // alphas[] write above vs reads in later sweeps; s_dot reads vs next write
+
+    if (is_producer) {
+      if (lane == 0) {
+        fence_proxy_async();
+        for (int64_t i = 0; i < my_tiles; ++i) {
+          const int64_t t = blockIdx.x + i * grid;
+          if (!qin_is_x) producer_push<R>(rg, pos, p.q + t * R);
+          if (v1) producer_push<R>(rg, pos, v1 + t * R);
+          if (v2) producer_push<R>(rg, pos, v2 + t * R);
+        }
+      }
+      __syncwarp();
+    } else {
+      double acc = 0.0;
+      double q[EPT], xn[EPT], rold[EPT];
+      if (qin_is_x && my_tiles > 0) load_user_tile<R>(p.x, (int64_t)blockIdx.x * R, p.n, p.x_al16, xn);
+      for (int64_t i = 0; i < my_tiles; ++i) {
+        const int64_t t = blockIdx.x + i * grid;
+        if (qin_is_x) {
+#pragma unroll
+          for (int j = 0; j < EPT; ++j) q[j] = xn[j];                                  // q .= x   :127-128
+          if (i + 1 < my_tiles) load_user_tile<R>(p.x, (t + grid) * R, p.n, p.x_al16, xn);
+        } else {
+          mbar_wait(&rg.full[pos.slot], pos.par);
+          const double2 *Q = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R);
+#pragma unroll
+          for (int j = 0; j < EPT / 2; ++j) {
+            double2 v = Q[j * B2O_NCONS + tid];
+            q[2 * j] = v.x;
+            q[2 * j + 1] = v.y;
+          }
+          consumer_release(rg, pos.slot);
+          pos.advance();
+        }
+        if (last && p.beta != 0.0) load_user_tile<R>(p.res, t * R, p.n, p.res_al16, rold);
+        if (v1) {
+          mbar_wait(&rg.full[pos.slot], pos.par);
+          const double2 *V = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R);
+#pragma unroll
+          for (int j = 0; j < EPT / 2; ++j) {
+            double2 v = V[j * B2O_NCONS + tid];
+            if (loop1) {
+              q[2 * j] = q[2 * j] - c1 * v.x;                                          // q .-= αk .* y[k]   :135
+              q[2 * j + 1] = q[2 * j + 1] - c1 * v.y;
+            } else {
+              q[2 * j] = q[2 * j] + c1 * v.x;                                          // q .+= β .* s[k]    :146
+              q[2 * j + 1] = q[2 * j + 1] + c1 * v.y;
+            }
+          }
+          consumer_release(rg, pos.slot);
+          pos.advance();
+          if (apply_gamma) {
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) q[j] = q[j] * p.gamma;                       // q .*= γ            :139
+          }
+          if (last) {
+#pragma unroll
+            for (int j = 0; j < EPT; ++j)
+              q[j] = (p.beta != 0.0) ? p.alpha * q[j] + p.beta * rold[j] : p.alpha * q[j];  // :149-153
+            store_user_tile<R>(p.res, t * R, p.n, p.res_al16, q);
+          } else {
+            // q is library-owned: pitch is padded, rows >= n hold zeros and stay zero (x loads 0 there)
+            double2 *Qg = reinterpret_cast<double2 *>(p.q + t * R);
+#pragma unroll
+            for (int j = 0; j < EPT / 2; ++j) Qg[j * B2O_NCONS + tid] = make_double2(q[2 * j], q[2 * j + 1]);
+          }
+        }
+        if (v2) {
+          mbar_wait(&rg.full[pos.slot], pos.par);
+          const double2 *V = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R);
+          double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+          for (int j = 0; j < EPT / 2; ++j) {
+            double2 v = V[j * B2O_NCONS + tid];
+            s0 = fma(v.x, q[2 * j], s0);
+            s1 = fma(v.y, q[2 * j + 1], s1);
+          }
+          acc += s0 + s1;
+          consumer_release(rg, pos.slot);
+          pos.advance();
+        }
+      }
+      if (v2) {
+        double s = warp_sum(acc);
+        if (lane == 0) sred[warp] = s;
+      }
+      fence_proxy_async();  // our generic-proxy stores to q precede next sweep's TMA reads of q
+    }
+    if (!v2) break;  // last sweep wrote res
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int wv = 0; wv < B2O_CONS_WARPS; ++wv) s += sred[wv];
+      p.partials[blockIdx.x] = s;
+    }
+    if (fused) {
+      grid_barrier(p.bar, bar_target);
+      bar_target += gridDim.x;
+      if (warp == 0) {
+        double s = 0.0;
+        for (int b = lane; b < (int)grid; b += 32) s += __ldcg(&p.partials[b]);
+        s = warp_sum(s);
+        if (lane == 0) s_dot = s;
+      }
+      __syncthreads();
+    } else {
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        unsigned long long tk = atomicAdd(p.arrive, 1ULL);
+        s_is_last = (tk == gridDim.x - 1);
+      }
+      __syncthreads();
+      if (s_is_last) {
+        __threadfence();
+        if (warp == 0) {
+          double s = 0.0;
+          for (int b = lane; b < (int)grid; b += 32) s += __ldcg(&p.partials[b]);
+          s = warp_sum(s);
+          if (lane == 0) {
+            p.dots[0] = s;
+            *p.arrive = 0ULL;
+          }
+        }
+        for (int i = tid; i < A; i += B2O_NTHREADS) p.dots[1 + i] = alphas[i];
+      }
+    }
+  }
+  if (p.alpha_out && blockIdx.x == 0 && p.sweep_end == 2 * A + 1)
+    for (int i = tid; i < A; i += B2O_NTHREADS) p.alpha_out[i] = alphas[i];
+}

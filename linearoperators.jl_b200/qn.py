@@ -1,0 +1,172 @@
+"""LBFGSOperator / InverseLBFGSOperator / LSR1Operator -- mirror of src/lbfgs.jl and src/lsr1.jl.
+
+State (the {s,y,a,b} columns, ring index, scaling factor) lives in HBM inside a libb2o handle; the apply is
+ONE persistent sm_100a kernel (TMA-staged columns, all dots and axpys in a single launch)."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import ErrorException, LinearOperatorException
+from .abstract import AbstractLinearOperator, Storage
+from .context import default_context
+from .special_operators import _vp
+
+F64 = _lib.B2O_F64
+
+
+class _QNData:
+    """read-only view of op.data (LBFGSData src/lbfgs.jl:4-24 / LSR1Data src/lsr1.jl:4-17)."""
+
+    def __init__(self, op):
+        self._op = op
+
+    def _scalars(self):
+        op = self._op
+        ins, g, ub = ctypes.c_int(), ctypes.c_double(), ctypes.c_double()
+        ys = (ctypes.c_double * op.mem)()
+        aux = (ctypes.c_double * op.mem)()
+        _lib.check(op.ctx.lib.b2o_qn_get_scalars(op.handle, ctypes.byref(ins), ctypes.byref(g), ctypes.byref(ub), ys, aux))
+        return ins.value, g.value, ub.value, np.array(ys[:]), np.array(aux[:])
+
+    mem = property(lambda self: self._op.mem)
+    scaling = property(lambda self: self._op.scaling)
+    damped = property(lambda self: self._op.damped)
+    insert = property(lambda self: self._scalars()[0])
+    scaling_factor = property(lambda self: self._scalars()[1])
+    opnorm_upper_bound = property(lambda self: self._scalars()[2])
+    ys = property(lambda self: self._scalars()[3])
+    aux = property(lambda self: self._scalars()[4])
+
+    def col(self, which, k0):
+        """device copy of column `which` ('s','y','a','b') in 0-based ring slot k0"""
+        op = self._op
+        out = op.ctx.empty(op.nrow)
+        _lib.check(op.ctx.lib.b2o_qn_get_col(op.handle, "syab".index(which), int(k0), _vp(out)))
+        return out
+
+    def set_col(self, which, k0, src):
+        op = self._op
+        _lib.check(op.ctx.lib.b2o_qn_set_col(op.handle, "syab".index(which), int(k0), _vp(src)))
+
+    def set_scalars(self, insert, scaling_factor, opnorm_upper_bound, ys, aux):
+        op = self._op
+        ysb = (ctypes.c_double * op.mem)(*[float(v) for v in ys])
+        axb = (ctypes.c_double * op.mem)(*[float(v) for v in aux])
+        _lib.check(op.ctx.lib.b2o_qn_set_scalars(op.handle, int(insert), float(scaling_factor),
+                                                 float(opnorm_upper_bound), ysb, axb))
+
+
+class AbstractQuasiNewtonOperator(AbstractLinearOperator):
+    """AbstractQuasiNewtonOperator{T} (src/qn.jl)."""
+    always_allocated5 = True          # has_args5 / isallocated5 are hard-wired true (src/lbfgs.jl:101-102)
+
+    def _common(self, ctx, n, mem):
+        import torch
+        self.ctx = ctx
+        self.eltype = torch.float64
+        self.nrow = self.ncol = int(n)
+        self.symmetric = self.hermitian = True
+        self.nprod = self.ntprod = self.nctprod = 0
+        self.mem = max(int(mem), 1)
+        self.S = Storage("cuda", ctx.device)
+        self.Mv = self.Mtu = None
+        self.data = _QNData(self)
+        lib, op = ctx.lib, self
+
+        def prod_(res, x, a, b):
+            _lib.check(lib.b2o_qn_apply(op.handle, _vp(res), res.shape[0], _vp(x), x.shape[0], float(a), float(b)))
+
+        self.prod_ = prod_
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and self.ctx.handle:
+                self.ctx.lib.b2o_qn_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def apply_host(self, res_host, x_host, alpha=1.0, beta=0.0):
+        """end-to-end apply with HOST buffers (numpy / pinned torch CPU tensors): H2D, apply, D2H inside."""
+        def hp(t):
+            return ctypes.c_void_p(t.data_ptr() if hasattr(t, "data_ptr") else t.ctypes.data)
+        _lib.check(self.ctx.lib.b2o_qn_apply_host(self.handle, hp(res_host), hp(x_host), int(x_host.shape[0]),
+                                                  float(alpha), float(beta)))
+        self.nprod += 1
+        return res_host
+
+    def apply_bytes(self, beta=0.0):
+        out = ctypes.c_double()
+        _lib.check(self.ctx.lib.b2o_qn_apply_bytes(self.handle, float(beta), ctypes.byref(out)))
+        return out.value
+
+    def _reset_state(self):
+        _lib.check(self.ctx.lib.b2o_qn_reset(self.handle))
+
+
+class LBFGSOperator(AbstractQuasiNewtonOperator):
+    """LBFGSOperator(n; mem=5, scaling=true, damped=false, σ₂=0.99, σ₃=10.0) -- forward form, src/lbfgs.jl:168-208.
+    InverseLBFGSOperator builds the same type with inverse=True (:112-160)."""
+
+    def __init__(self, n, mem=5, scaling=True, damped=False, sigma2=0.99, sigma3=10.0, inverse=False, ctx=None):
+        ctx = ctx or default_context()
+        self._common(ctx, n, mem)
+        self.scaling, self.damped, self.inverse = bool(scaling), bool(damped), bool(inverse)
+        self.handle = ctypes.c_void_p()
+        _lib.check(ctx.lib.b2o_lbfgs_create(ctx.handle, F64, int(n), int(mem), int(scaling), int(damped), float(sigma2),
+                                            float(sigma3), int(inverse), ctypes.byref(self.handle)))
+        self.tprod_ = self.prod_
+        self.ctprod_ = self.prod_
+
+
+def InverseLBFGSOperator(n, **kw):
+    kw.pop("inverse", None)
+    return LBFGSOperator(n, inverse=True, **kw)
+
+
+class LSR1Operator(AbstractQuasiNewtonOperator):
+    """LSR1Operator(n; mem=5, scaling=true) -- src/lsr1.jl:86-113 (tprod!/ctprod! are `nothing`: inferred)."""
+
+    def __init__(self, n, mem=5, scaling=True, ctx=None):
+        ctx = ctx or default_context()
+        self._common(ctx, n, mem)
+        self.scaling, self.damped, self.inverse = bool(scaling), False, False
+        self.handle = ctypes.c_void_p()
+        _lib.check(ctx.lib.b2o_lsr1_create(ctx.handle, F64, int(n), int(mem), int(scaling), ctypes.byref(self.handle)))
+        self.tprod_ = None
+        self.ctprod_ = None
+
+
+def push_(op, s, y, *rest):
+    """push!(op, s, y) | push!(op, s, y, Bs) | push!(op, s, y, α, g) | push!(op, s, y, α, g, Bs)
+    (src/lbfgs.jl:269-367, src/lsr1.jl:119-184).  Returns op; a rejected pair leaves the state unchanged."""
+    lib = op.ctx.lib
+    acc = ctypes.c_int(0)
+    n = s.shape[0]
+    if isinstance(op, LSR1Operator) or len(rest) == 0:
+        if len(rest) != 0:
+            raise TypeError("no such push! method for LSR1Operator")
+        _lib.check(lib.b2o_qn_push(op.handle, _vp(s), _vp(y), n, ctypes.byref(acc)))
+    elif len(rest) == 1:
+        (Bs,) = rest
+        _lib.check(lib.b2o_lbfgs_push_damped_fwd(op.handle, _vp(s), _vp(y), _vp(Bs), n, ctypes.byref(acc)))
+    elif len(rest) in (2, 3):
+        alpha, g = rest[0], rest[1]
+        Bs = rest[2] if len(rest) == 3 else op.ctx.empty(n)      # similar(g)  src/lbfgs.jl:366
+        _lib.check(lib.b2o_lbfgs_push_damped_inv(op.handle, _vp(s), _vp(y), float(alpha), _vp(g), _vp(Bs), n,
+                                                 ctypes.byref(acc)))
+    else:
+        raise TypeError("no such push! method")
+    op.last_push_accepted = bool(acc.value)
+    return op
+
+
+def diag_(op, d):
+    """diag!(op, d) (src/lbfgs.jl:379-395, src/lsr1.jl:196-211)"""
+    _lib.check(op.ctx.lib.b2o_qn_diag(op.handle, _vp(d), d.shape[0]))
+    return d
+
+
+def diag(op):
+    return diag_(op, op.ctx.empty(op.nrow))

@@ -1,0 +1,98 @@
+/*
+ * b2o_oracle.h -- CPU ORACLE (test infrastructure, NOT the product).
+ *
+ * A plain-C restatement of the closure bodies on the `mul!(res, op, v, α, β)`
+ * hot path of JuliaSmoothOptimizers/LinearOperators.jl v2.14.2.  Only `tests/`,
+ * `__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs of
+ * `bench.py` may load this library; the product (libb2o.so) never does.
+ *
+ * PARITY PINNING: the reference is Julia and cannot be executed in this image.
+ * The oracle is pinned (tests/test_oracle_pinning.py) against every literal
+ * known answer and every test predicate the reference's own suite holds for this
+ * path (exact index equality test/test_linop.jl:437-467; H*B≈I, dense-BFGS /
+ * dense-SR1 recurrences test/test_lbfgs.jl:13-159, test/test_lsr1.jl:7-72; dense
+ * kron test/test_kron.jl:3-39).  Bit-level parity of *reductions* (dot/norm/sum
+ * go to OpenBLAS in the reference, summation order unspecified) is UNPINNED by
+ * construction; the oracle takes them in long double so it is the accurate side.
+ *
+ * Each function cites the reference file:line it follows (paths relative to the
+ * reference checkout).
+ */
+#ifndef B2O_ORACLE_H
+#define B2O_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* mode: accurate=1 -> long-double reductions (parity checker);
+ *       accurate=0 -> plain double loops, `threads` OpenMP threads (timing twin). */
+void orc_set_mode(int accurate, int threads);
+int orc_max_threads(void);
+
+/* deterministic counter-based U[lo,hi) generator shared bit-for-bit with the CUDA side */
+void orc_fill_uniform(double *x, int64_t n, uint64_t seed, double lo, double hi);
+void orc_fill_uniform_f32(float *x, int64_t n, uint64_t seed, float lo, float hi);
+
+double orc_dot(const double *a, const double *b, int64_t n);
+double orc_sum(const double *a, int64_t n);
+double orc_nrm2(const double *a, int64_t n);
+
+/* leaf closures -- src/special-operators.jl, src/linalg.jl */
+void orc_eye(double *res, int64_t nres, const double *v, int64_t nv, double alpha, double beta, int64_t n_min);
+void orc_ones(double *res, int64_t nres, const double *v, int64_t nv, double alpha, double beta);
+void orc_zeros(double *res, int64_t nres, double alpha, double beta);
+void orc_diag_square(double *res, const double *d, const double *v, int64_t n, double alpha, double beta);
+void orc_diag_rect(double *res, int64_t nres, const double *d, const double *v, double alpha, double beta, int64_t n_min);
+void orc_householder(double *res, const double *h, const double *v, int64_t n, double alpha, double beta);
+void orc_restrict(double *res, const int64_t *idx1, int64_t k, const double *v);
+void orc_extend(double *res, int64_t ncol, const int64_t *idx1, int64_t k, const double *u);
+
+/* quasi-Newton operators -- src/lbfgs.jl, src/lsr1.jl */
+typedef struct orc_lbfgs orc_lbfgs;
+orc_lbfgs *orc_lbfgs_create(int64_t n, int mem, int scaling, int damped, double sigma2, double sigma3, int inverse);
+void orc_lbfgs_destroy(orc_lbfgs *);
+void orc_lbfgs_apply(orc_lbfgs *, double *res, const double *x, double alpha, double beta);
+int orc_lbfgs_push(orc_lbfgs *, const double *s, const double *y);                    /* 1 accepted, 0 rejected, <0 error */
+int orc_lbfgs_push_damped_fwd(orc_lbfgs *, const double *s, const double *y, double *Bs);
+int orc_lbfgs_push_damped_inv(orc_lbfgs *, const double *s, double *y, double alpha, const double *g, double *Bs);
+int orc_lbfgs_diag(orc_lbfgs *, double *d);
+void orc_lbfgs_reset(orc_lbfgs *);
+/* state access: which = 0:s 1:y 2:a 3:b (n-vectors, slot k0 0-based); scalars below */
+double *orc_lbfgs_col(orc_lbfgs *, int which, int k0);
+double *orc_lbfgs_ys(orc_lbfgs *);
+double orc_lbfgs_gamma(orc_lbfgs *);
+void orc_lbfgs_set_gamma(orc_lbfgs *, double);
+int orc_lbfgs_insert(orc_lbfgs *);                 /* 1-based, as data.insert */
+void orc_lbfgs_set_insert(orc_lbfgs *, int insert1);
+double orc_lbfgs_opnorm_upper_bound(orc_lbfgs *);
+
+typedef struct orc_lsr1 orc_lsr1;
+orc_lsr1 *orc_lsr1_create(int64_t n, int mem, int scaling);
+void orc_lsr1_destroy(orc_lsr1 *);
+void orc_lsr1_apply(orc_lsr1 *, double *res, const double *x, double alpha, double beta);
+int orc_lsr1_push(orc_lsr1 *, const double *s, const double *y);
+void orc_lsr1_diag(orc_lsr1 *, double *d);
+void orc_lsr1_reset(orc_lsr1 *);
+double *orc_lsr1_col(orc_lsr1 *, int which, int k0); /* 0:s 1:y 2:a */
+double *orc_lsr1_ys(orc_lsr1 *);
+double *orc_lsr1_as(orc_lsr1 *);
+double orc_lsr1_gamma(orc_lsr1 *);
+void orc_lsr1_set_gamma(orc_lsr1 *, double);
+int orc_lsr1_insert(orc_lsr1 *);
+void orc_lsr1_set_insert(orc_lsr1 *, int insert1);
+double orc_lsr1_opnorm_upper_bound(orc_lsr1 *);
+
+/* kron(A,B)*x = alpha*vec(B X A^T)+beta*res -- src/kron.jl:14-22; A m×n, B p×q, col-major;
+ * trans: 0 prod, 1 tprod (B^T X A), 2 ctprod (same for real) */
+void orc_kron(double *res, const double *A, int64_t m, int64_t n, const double *B, int64_t p, int64_t q,
+              const double *x, double alpha, double beta, int trans);
+
+/* bf16 helpers used by the kron parity test (round-to-nearest-even) */
+uint16_t orc_f32_to_bf16(float f);
+float orc_bf16_to_f32(uint16_t h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

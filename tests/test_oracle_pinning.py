@@ -1,0 +1,309 @@
+"""Pin the CPU oracle (oracle/b2o_oracle.c + oracle/oracle.py) against the reference's OWN test predicates
+and literal known answers for the apply path.  The reference is Julia and cannot run here, so
+these are transcriptions of what its test-suite asserts:
+
+  test/test_linop.jl:437-461   Restriction/Extension, exact ==
+  test/test_linop.jl:229-344   Eye / Ones / Zeros / Diagonal / rectangular Diagonal
+  test/test_linop.jl:511-518   Householder
+  test/test_lbfgs.jl:13-159    identity at start, rejection, H*B≈I, diag, reset!, dense BFGS, damped, norm bound
+  test/test_lsr1.jl:7-72       same for L-SR1 against dense SR1
+  test/test_kron.jl:3-39       kron operator against dense kron
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+EPS = np.finfo(np.float64).eps
+RTOL = np.sqrt(EPS)
+
+
+def simple_vector(n):
+    """test/test_aux.jl:35  T[-(-one(T))^i for i = 1:n] = [1, -1, 1, ...]"""
+    return np.array([-((-1.0) ** i) for i in range(1, n + 1)])
+
+
+# ---------------------------------------------------------------- index operators: exact equality
+@pytest.mark.parametrize("idx", [[1, 2, 4, 7], list(range(3, 7)), list(range(1, 8, 2)), [4]])
+def test_restriction_extension_exact(orc, idx):
+    n = 10
+    v = simple_vector(n)
+    idx = np.array(idx)
+    P, Z = orc.opRestriction(idx, n), orc.opExtension(idx, n)
+    w = v[idx - 1]
+    vz = np.zeros(n)
+    vz[idx - 1] = v[idx - 1]
+    assert np.array_equal(P(v), w)
+    assert np.array_equal(P.T(w), vz)
+    assert np.array_equal(Z(w), vz)
+    assert np.array_equal(Z.T(v), w)
+    assert np.array_equal((P * Z)(w), w)
+    assert np.array_equal((Z * P)(v), vz)
+
+
+def test_extension_duplicates_last_wins(orc):
+    # Q4: res[I] = u with duplicate I keeps the last occurrence (src/special-operators.jl:173)
+    res = np.full(5, 7.0)
+    orc.extend_(res, [2, 4, 2, 2], np.array([1.0, 2.0, 3.0, 4.0]))
+    assert np.array_equal(res, [0, 4.0, 0, 2.0, 0])
+
+
+def test_restriction_ignores_alpha_beta(orc):
+    # Q1 (src/special-operators.jl:167-169)
+    P = orc.opRestriction([2, 3], 4)
+    res = np.array([9.0, 9.0])
+    P.mul(res, np.array([1.0, 2.0, 3.0, 4.0]), 5.0, 3.0)
+    assert np.array_equal(res, [2.0, 3.0])
+
+
+# ---------------------------------------------------------------- leaf operators
+def test_eye_and_rect_eye_quirk(orc):
+    v = simple_vector(5)
+    assert np.array_equal(orc.opEye(5)(v), v)
+    E = orc.opEye(7, 5)
+    res = np.full(7, 3.0)
+    E.mul(res, v, 2.0, 0.0)
+    assert np.array_equal(res, np.r_[2 * v, 0, 0])
+    res = np.full(7, 3.0)
+    E.mul(res, v, 2.0, 0.5)                     # Q2: tail becomes β, not β*res
+    assert np.array_equal(res, np.r_[2 * v + 1.5, 0.5, 0.5])
+
+
+def test_ones_zeros(orc):
+    u = simple_vector(6) * 1.5
+    assert np.allclose(orc.opOnes(4, 6)(u), np.sum(u) * np.ones(4), rtol=0, atol=RTOL * np.linalg.norm(u))
+    assert np.linalg.norm(orc.opZeros(4, 6)(u)) <= EPS
+    res = np.full(4, 2.0)
+    orc.opZeros(4, 6).mul(res, u, 1.0, 3.0)
+    assert np.array_equal(res, np.full(4, 6.0))
+
+
+def test_diagonal_known_answers(orc):
+    # test/test_linop.jl:308-319 (real restriction of the complex test) + the literal `[2;1]` check (:565,:594)
+    v, u = simple_vector(8) * 2, simple_vector(8) + 0.5
+    D = orc.opDiagonal(v)
+    assert np.linalg.norm(D(u) - v * u) <= EPS * np.linalg.norm(u)
+    res = simple_vector(8).copy()
+    res2 = v * u * 2.0 + 2.0 * res
+    D.mul(res, u, 2.0, 2.0)
+    assert np.linalg.norm(res - res2) <= EPS * np.linalg.norm(u)
+    assert np.array_equal(orc.opDiagonal(np.array([2.0, 1.0]))(np.ones(2)), [2.0, 1.0])
+
+
+def test_rect_diagonal(orc):
+    # test/test_linop.jl:321-344; Q3: tail rows are zeroed even when β != 0
+    nmin, nmax = 4, 7
+    v, u = simple_vector(nmin) * 3, simple_vector(nmin)
+    A = np.zeros((nmax, nmin))
+    A[np.arange(nmin), np.arange(nmin)] = v
+    D = orc.opDiagonal(v, nmax, nmin)
+    assert np.linalg.norm(A @ u - D(u)) <= EPS * np.linalg.norm(u)
+    w = simple_vector(nmax)
+    assert np.linalg.norm(A.T @ w - D.T(w)) <= EPS * np.linalg.norm(w)
+    res = np.full(nmax, 5.0)
+    D.mul(res, u, 1.0, 1.0)
+    assert np.array_equal(res[nmin:], np.zeros(nmax - nmin))
+
+
+def test_householder(orc):
+    # test/test_linop.jl:511-518
+    n = 9
+    h = simple_vector(n) / 3.0
+    u = np.arange(1.0, n + 1)
+    H = orc.opHouseholder(h)
+    assert np.linalg.norm(H(u) - (u - 2 * np.dot(h, u) * h)) <= RTOL * np.linalg.norm(u)
+    assert np.linalg.norm(H.T(u) - H(u)) == 0
+
+
+def test_composition_against_dense(orc):
+    # test/test_linop.jl:139-226: (A+B), (A*B), scalar, unary minus against dense algebra
+    rng = np.random.default_rng(0)
+    d1, d2, h = rng.random(6), rng.random(6) + 0.5, rng.random(6)
+    h /= np.linalg.norm(h)
+    D1, D2, H = orc.opDiagonal(d1), orc.opDiagonal(d2), orc.opHouseholder(h)
+    Hm = np.eye(6) - 2 * np.outer(h, h)
+    for op, M in [(D1 + D2, np.diag(d1 + d2)), (H * D1, Hm @ np.diag(d1)), (2.5 * H, 2.5 * Hm), (-(H * D2), -Hm @ np.diag(d2)),
+                  (H * D1 + 0.1 * orc.opEye(6), Hm @ np.diag(d1) + 0.1 * np.eye(6)), ((H * D1).T, np.diag(d1) @ Hm)]:
+        assert np.linalg.norm(op.matrix() - M) <= RTOL * np.linalg.norm(M)
+
+
+# ---------------------------------------------------------------- L-BFGS (test/test_lbfgs.jl)
+def bfgs_dense(B, s, y, damped=False):
+    ys = y @ s
+    Bs = B @ s
+    tol = 0.2 * (s @ Bs) if damped else 1e-20
+    if ys > tol:
+        B = B - np.outer(Bs, Bs) / (s @ Bs) + np.outer(y, y) / ys
+    return B
+
+
+def test_lbfgs_reference_predicates(orc):
+    n, mem = 10, 5
+    B = orc.LBFGS(n, mem=mem, scaling=False)
+    H = orc.LBFGS(n, mem=mem, scaling=False, inverse=True)
+    for _ in range(2):                                                # "Run again after reset!"
+        assert np.linalg.norm(B.diag() - np.diag(B.matrix())) <= RTOL
+        assert B.insert == 1 and H.insert == 1
+        assert np.linalg.norm(B.matrix() - np.eye(n)) <= EPS
+        assert np.linalg.norm(H.matrix() - np.eye(n)) <= EPS
+        s, z = simple_vector(n), np.zeros(n)
+        for op in (B, H):                                             # nonpositive curvature is rejected
+            assert not op.push(s, -s) and op.insert == 1
+            assert not op.push(s, z) and op.insert == 1
+        insert = 0
+        for i in range(1, mem + 3):
+            s = np.ones(n) * i
+            y = np.r_[i, np.ones(n - 1)]
+            if s @ y > 1e-20:
+                insert += 1
+                B.push(s, y)
+                H.push(s, y)
+        assert B.insert == insert % mem + 1 and H.insert == insert % mem + 1
+        Bm, Hm = B.matrix(), H.matrix()
+        assert np.all(np.linalg.eigvalsh((Bm + Bm.T) / 2) > 0) and np.all(np.linalg.eigvalsh((Hm + Hm.T) / 2) > 0)
+        assert np.linalg.norm(Bm - Bm.T) <= RTOL * np.linalg.norm(Bm)
+        assert np.linalg.norm(B.diag() - np.diag(Bm)) <= RTOL
+        assert np.linalg.norm(Hm @ Bm - np.eye(n)) <= RTOL            # Matrix(H*B) ≈ I
+        v = simple_vector(n)
+        assert np.linalg.norm(B.apply(v) - v) > RTOL
+        assert np.linalg.norm(np.linalg.norm(Bm, 2)) <= B.opnorm_upper_bound
+        B.reset()
+        H.reset()
+        assert B.scaling_factor == 1.0 and H.scaling_factor == 1.0
+        assert np.linalg.norm(B.apply(v) - v) < RTOL and np.linalg.norm(H.apply(v) - v) < RTOL
+
+
+@pytest.mark.parametrize("damped", [False, True])
+def test_lbfgs_equals_dense_bfgs(orc, damped):
+    n = mem = 10
+    LB = orc.LBFGS(n, mem=mem, scaling=False, damped=damped)
+    B = np.eye(n)
+    rng = np.random.default_rng(3)
+    assert np.linalg.norm(LB.matrix() - B) < RTOL * np.linalg.norm(B)
+    for k in range(mem):
+        s = simple_vector(n) if k == 0 else rng.random(n)
+        y = simple_vector(n) if k == 0 else s + 0.1 * rng.random(n)
+        B = bfgs_dense(B, s, y, damped)
+        LB.push(s, y)
+        assert np.linalg.norm(LB.matrix() - B) < RTOL * np.linalg.norm(B)
+        assert np.linalg.norm(LB.diag() - np.diag(B)) < RTOL * np.linalg.norm(np.diag(B))
+    assert np.linalg.norm(B, 2) <= LB.opnorm_upper_bound * (1 + 1e-12)
+
+
+def test_lbfgs_damped_pair(orc):
+    # test/test_lbfgs.jl:104-137
+    n, mem = 10, 5
+    B = orc.LBFGS(n, mem=mem, damped=True, scaling=False, sigma2=0.8, sigma3=np.inf)
+    H = orc.LBFGS(n, mem=mem, damped=True, scaling=False, sigma2=0.8, sigma3=np.inf, inverse=True)
+    ins = 0
+    for i in range(1, mem + 3):
+        y = simple_vector(n)
+        g = simple_vector(n)
+        d = -H.apply(g)
+        a = i / mem
+        s = a * d
+        if y @ simple_vector(n) > 0.2 * (s @ B.apply(s)):
+            ins += 1
+            B.push(s, y)
+            H.push_damped_inv(s, y.copy(), a, g)
+    assert B.insert == ins % mem + 1 and H.insert == ins % mem + 1
+    Bm, Hm = B.matrix(), H.matrix()
+    assert np.linalg.norm(Hm @ Bm - np.eye(n)) <= RTOL
+    assert np.linalg.norm(B.diag() - np.diag(Bm)) <= RTOL
+    assert np.linalg.norm(Bm, 2) <= B.opnorm_upper_bound
+
+
+def test_lbfgs_scaling_and_5arg(orc):
+    n, mem = 12, 4
+    rng = np.random.default_rng(5)
+    for inverse in (False, True):
+        op = orc.LBFGS(n, mem=mem, scaling=True, inverse=inverse)
+        for _ in range(6):
+            s = rng.random(n)
+            op.push(s, s + 0.1 * rng.random(n))
+        M = op.matrix()
+        x, r0 = rng.random(n), rng.random(n)
+        res = r0.copy()
+        op.apply(x, 2.0, -0.5, res=res)
+        assert np.linalg.norm(res - (2.0 * M @ x - 0.5 * r0)) <= 1e-13 * np.linalg.norm(res)
+
+
+# ---------------------------------------------------------------- L-SR1 (test/test_lsr1.jl)
+def sr1_dense(B, s, y):
+    r = y - B @ s
+    den = r @ s
+    if abs(den) >= 1e-8 + 1e-8 * np.linalg.norm(s) * np.linalg.norm(r):
+        B = B + np.outer(r, r) / den
+    return B
+
+
+def test_lsr1_reference_predicates(orc):
+    n, mem = 10, 5
+    B = orc.LSR1(n, mem=mem, scaling=False)
+    for _ in range(2):
+        assert np.linalg.norm(B.diag() - np.diag(B.matrix())) <= RTOL
+        assert B.insert == 1
+        assert np.linalg.norm(B.matrix() - np.eye(n)) <= EPS
+        s = simple_vector(n)
+        assert not B.push(s, B.apply(s)) and B.insert == 1            # y = B s is rejected
+        for i in range(1, mem + 3):
+            B.push(np.ones(n) * i, np.r_[i, np.ones(n - 1)])
+        Bm = B.matrix()
+        assert np.linalg.norm(Bm - Bm.T) <= RTOL * np.linalg.norm(Bm)
+        assert np.linalg.norm(B.diag() - np.diag(Bm)) <= RTOL
+        v = simple_vector(n)
+        assert np.linalg.norm(B.apply(v) - v) > RTOL
+        B.reset()
+        assert B.scaling_factor == 1.0
+        assert np.linalg.norm(B.apply(v) - v) < RTOL
+        assert np.linalg.norm(B.matrix(), 2) <= B.opnorm_upper_bound
+
+
+def test_lsr1_equals_dense_sr1(orc):
+    n = mem = 10
+    LB = orc.LSR1(n, mem=mem, scaling=False)
+    B = np.eye(n)
+    rng = np.random.default_rng(11)
+    for k in range(mem):
+        s = simple_vector(n) if k == 0 else rng.random(n) - 0.5
+        y = simple_vector(n) if k == 0 else rng.random(n) - 0.5
+        B = sr1_dense(B, s, y)
+        LB.push(s, y)
+        assert np.linalg.norm(LB.matrix() - B) < RTOL * np.linalg.norm(B)
+        assert np.linalg.norm(LB.diag() - np.diag(B)) < RTOL * np.linalg.norm(np.diag(B))
+    assert np.linalg.norm(B, 2) <= LB.opnorm_upper_bound * (1 + 1e-12)
+
+
+# ---------------------------------------------------------------- kron (test/test_kron.jl:3-39)
+@pytest.mark.parametrize("shapeA,shapeB", [((2, 3), (2, 3)), ((4, 4), (3, 5))])
+def test_kron_against_dense(orc, shapeA, shapeB):
+    rng = np.random.default_rng(7)
+    A, B = rng.random(shapeA), rng.random(shapeB)
+    K = np.kron(A, B)
+    normK = np.abs(K).sum(axis=0).max()
+    x = simple_vector(K.shape[1])
+    res = np.empty(K.shape[0])
+    orc.kron_(res, A, B, x)
+    assert np.abs(K @ x - res).sum() < 1e-12 * normK
+    xt = simple_vector(K.shape[0])
+    rt = np.empty(K.shape[1])
+    orc.kron_(rt, A, B, xt, trans=1)
+    assert np.abs(K.T @ xt - rt).sum() < 1e-12 * normK
+    r2 = np.ones(K.shape[0])
+    orc.kron_(r2, A, B, x, alpha=2.0, beta=-1.0)
+    assert np.abs(2 * K @ x - 1 - r2).sum() < 1e-12 * normK
+
+
+# ---------------------------------------------------------------- frozen golden vectors
+def test_golden_vectors(orc):
+    """tests/golden/golden_v1.json was produced by tests/golden/make_golden.py from this oracle after it passed
+    every predicate above; it freezes seeded inputs -> outputs so that later edits cannot drift silently."""
+    path = os.path.join(os.path.dirname(__file__), "golden", "golden_v1.json")
+    G = json.load(open(path))
+    from golden.make_golden import compute_cases
+    fresh = compute_cases(orc)
+    assert set(fresh) == set(G["cases"])
+    for name, val in fresh.items():
+        ref = np.array(G["cases"][name])
+        assert np.allclose(val, ref, rtol=1e-14, atol=0), name
