@@ -1,0 +1,250 @@
+#!/usr/bin/env python
+"""bench.py -- the BASELINE.json headline: LBFGSOperator(n=1e8, mem=10) Float64 `op*v` on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--n ROWS] [--mem M] [--workload fwd|inv]
+
+A "step" is ONE apply `mul!(res, B, x, 1, 0)` (one persistent kernel launch) on synthetic state: `mem` accepted
+pushes of s_i ~ U[0,1)^n (seed 100+i), y_i = s_i + 0.1 U[0,1)^n (seed 200+i), x ~ U[0,1) seed 7.
+`value` is whole-job algorithmic GB/s = (4m+3)*8*n bytes * applies/s summed over ranks (weak scaling: every rank
+holds n rows; the 2m dots are all-reduced over NCCL).  Inputs are 16 GB >> the 126 MB L2, so no L2 flush is needed
+between iterations.  `e2e` runs the same apply through the host-buffer C-ABI entry (pinned host x -> H2D -> kernel
+-> D2H res) inside the timed region.  `cpu_baseline` / `--impl reference` time the CPU restatement of the reference
+(oracle/, "port": Julia is not installed anywhere) on a bounded sample with all host threads."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+METRIC = "LBFGS(m=10,n=1e8) op*v algorithmic GB/s"
+NOMINAL_HBM_GBS = 8000.0
+FALLBACK_HBM_GBS = 6650.0
+
+
+def alg_bytes(n, m, inverse=False):
+    """forward (4m+3)*8*n, inverse two-loop (8m+2)*8*n (beta = 0)."""
+    return ((8 * m + 2) if inverse else (4 * m + 3)) * 8.0 * n
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+def cpu_reference(n_cpu, mem, steps, warmup, inverse=False):
+    """Reference arm: the CPU restatement of lbfgs_multiply (src/lbfgs.jl:173-202), one pass per reference statement,
+    all host threads, on a bounded sample of n_cpu rows (state columns filled directly -- apply cost is data-independent)."""
+    import numpy as np
+    import oracle
+    oracle.build()
+    threads = oracle.max_threads()
+    oracle.set_mode(False, threads)
+    op = oracle.LBFGS(n_cpu, mem=mem, inverse=inverse)
+    for k in range(mem):
+        for which in (("s", "y") if inverse else ("a", "b")):
+            oracle.lib().orc_fill_uniform(op.col(which, k).ctypes.data, n_cpu, 1000 + 10 * k + ord(which[0]), 0.0, 1.0e-3)
+        op.ys[k] = 1.0
+    op.set_state(1, 0.5)
+    x = oracle.uniform(n_cpu, 7)
+    res = np.empty(n_cpu)
+    for _ in range(warmup):
+        op.apply(x, res=res)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        op.apply(x, res=res)
+    dt = (time.perf_counter() - t0) / steps
+    oracle.set_mode(True, 1)
+    return {"value": alg_bytes(n_cpu, mem, inverse) / dt / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
+            "sample": "%s apply at n=%d rows (1/%d of the workload), mem=%d, %d timed applies, %.3f s/apply" %
+                      ("inverse" if inverse else "forward", n_cpu, max(1, round(1e8 / n_cpu)), mem, steps, dt),
+            "applies_per_s": 1.0 / dt, "ms_per_apply": dt * 1e3}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=10**8, help="rows per GPU")
+    ap.add_argument("--mem", type=int, default=10)
+    ap.add_argument("--workload", default="fwd", choices=["fwd", "inv"])
+    ap.add_argument("--cpu-n", type=int, default=10**7)
+    ap.add_argument("--tile-rows", type=int, default=0)
+    ap.add_argument("--stages", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    inverse = args.workload == "inv"
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    args.warmup = max(args.warmup, 3)
+    config = {"workload": "%sLBFGSOperator(n=%d, mem=%d) Float64 apply, alpha=1 beta=0" % ("Inverse" if inverse else "", args.n, args.mem),
+              "rows_per_gpu": args.n, "mem": args.mem, "parallelism": "row-partition x%d" % world if world > 1 else "single GPU",
+              "l2": "inputs (%.1f GB of columns) >> 126 MB L2, no flush needed" % (2 * args.mem * args.n * 8 / 1e9)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb = cpu_reference(args.cpu_n, args.mem, max(1, min(args.steps, 5)), 1, inverse)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "GB/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_apply"],
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": config, "cpu_baseline": cb,
+                          "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return
+
+    import torch
+    import linearoperators_jl_b200 as lo
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = lo.default_context(local_rank)
+    if world > 1:
+        ctx.init_comm_from_torch()
+    if args.tile_rows:
+        ctx.set_option("tile_rows", args.tile_rows)
+    if args.stages:
+        ctx.set_option("stages", args.stages)
+
+    n, m = args.n, args.mem
+    B = lo.LBFGSOperator(n, mem=m, inverse=inverse, ctx=ctx)
+    for i in range(m):
+        s = ctx.uniform(n, 1000 * rank + 100 + i)
+        y = s + 0.1 * ctx.uniform(n, 1000 * rank + 200 + i)
+        lo.push_(B, s, y)
+        assert B.last_push_accepted
+    del s, y
+    x = ctx.uniform(n, 1000 * rank + 7)
+    res = ctx.empty(n)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        lo.mul_(res, B, x)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        lo.mul_(res, B, x)
+    e1.record()
+    barrier()
+    launches = ctx.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_step = ms / args.steps
+    bytes_step = alg_bytes(n, m, inverse)
+    value = world * bytes_step / (ms_step * 1e-3) / 1e9
+
+    # ---- end to end through the host-buffer C-ABI entry: pinned host x -> H2D -> apply -> D2H res, every step
+    xh = x.cpu().pin_memory()
+    rh = torch.empty(n, dtype=torch.float64).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    B.apply_host(rh, xh)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        B.apply_host(rh, xh)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": world * bytes_step / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8,
+           "ms_per_step": e2e_s * 1e3, "applies_per_s": world / e2e_s}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_kind = measured_peak()
+    per_gpu = bytes_step / (ms_step * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("inv" if inverse else "fwd")
+        except Exception:
+            traffic = None
+    out = {
+        "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config, "applies_per_s": world / (ms_step * 1e-3),
+        "frac_of_nominal_8TBs_per_gpu": per_gpu / NOMINAL_HBM_GBS,
+        "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak,
+                     "traffic": traffic, "peak_source": "of " + peak_kind,
+                     "kernel": "qn_twoloop_kernel" if inverse else "qn_compact_kernel<2048,LBFGS_FWD>",
+                     "algorithmic_bytes_per_launch": bytes_step},
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+    }
+    if not args.no_cpu:
+        out["cpu_baseline"] = cpu_reference(args.cpu_n, m, 3, 1, inverse)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,529 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI, via the host mirror) against the CPU oracle on the
+same seeded inputs.  Bars: bit-exact for index work and for purely elementwise operators; norm-wise relative
+<= 1e-12 (Float64) wherever a reduction is involved (north_star)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    d = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / (d if d > 0 else 1.0)
+
+
+def dev(ctx, a):
+    import torch
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to("cuda:%d" % ctx.device)
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def simple_vector(n):
+    return np.array([-((-1.0) ** i) for i in range(1, n + 1)])
+
+
+# ---------------------------------------------------------------- plumbing
+@pytest.mark.parametrize("n", [1, 7, 1000, 65537])
+def test_fill_uniform_bit_exact(ctx, orc, n):
+    x = ctx.uniform(n, 42, -1.0, 2.5)
+    assert np.array_equal(host(x), orc.uniform(n, 42, -1.0, 2.5))
+
+
+def test_device_dot(ctx, orc):
+    n = 100003
+    a, b = ctx.uniform(n, 1), ctx.uniform(n, 2)
+    assert abs(ctx.dot(a, b) - orc.dot(host(a), host(b))) <= 1e-13 * abs(orc.dot(host(a), host(b)))
+
+
+# ---------------------------------------------------------------- cfg1: opDiagonal (bit-exact, elementwise)
+@pytest.mark.parametrize("n", [1, 2, 5, 1000, 1000003])
+@pytest.mark.parametrize("ab", [(1.0, 0.0), (2.0, 2.0), (-0.5, 1.0)])
+def test_diag_bit_exact(lo, ctx, orc, n, ab):
+    alpha, beta = ab
+    d, v, r0 = ctx.uniform(n, 1), ctx.uniform(n, 2), ctx.uniform(n, 9)
+    D = lo.opDiagonal(d)
+    res = r0.clone() if beta != 0 else ctx.empty(n).fill_(float("nan"))     # beta == 0 must not read res
+    lo.mul_(res, D, v, alpha, beta)
+    ref = host(r0).copy()
+    orc.diag_(ref, host(d), host(v), alpha, beta)
+    assert np.array_equal(host(res), ref)
+    assert np.array_equal(host(lo.transpose(D) * v), host(D * v))
+    assert np.array_equal(host(lo.adjoint(D) * v), host(D * v))
+
+
+def test_cfg1_diag_1e6(lo, ctx, orc):
+    """BASELINE config 1: opDiagonal(n=1e6) * v, Float64 -- GPU result identical to the CPU oracle."""
+    n = 10**6
+    d, v = ctx.uniform(n, 1), ctx.uniform(n, 2)
+    res = lo.opDiagonal(d) * v
+    ref = np.empty(n)
+    orc.diag_(ref, orc.uniform(n, 1), orc.uniform(n, 2), 1.0, 0.0)
+    assert np.array_equal(host(res), ref)
+
+
+def test_diag_misaligned_views_and_aliasing(lo, ctx, orc):
+    n = 1001
+    base_d, base_v, base_r = ctx.uniform(n + 1, 1), ctx.uniform(n + 1, 2), ctx.uniform(n + 1, 3)
+    d, v, res = base_d[1:], base_v[1:], base_r[1:]                           # 8-byte-aligned only
+    D = lo.opDiagonal(d)
+    r0 = host(res).copy()
+    lo.mul_(res, D, v, 1.5, -2.0)
+    orc.diag_(r0, host(d), host(v), 1.5, -2.0)
+    assert np.array_equal(host(res), r0)
+    d.mul_(2.0)                                                              # the operator aliases d (special-operators.jl:139)
+    out = host(D * v)
+    ref = np.empty(n)
+    orc.diag_(ref, host(d), host(v), 1.0, 0.0)
+    assert np.array_equal(out, ref)
+
+
+def test_rect_diag_and_eye_quirks(lo, ctx, orc):
+    for nrow, ncol in [(7, 4), (4, 7), (1025, 513)]:
+        nmin = min(nrow, ncol)
+        d, v, r0 = ctx.uniform(nmin, 1), ctx.uniform(ncol, 2), ctx.uniform(nrow, 3)
+        for alpha, beta in [(1.0, 0.0), (2.0, 0.5)]:
+            D = lo.opDiagonal(nrow, ncol, d)
+            res = r0.clone()
+            lo.mul_(res, D, v, alpha, beta)
+            ref = host(r0).copy()
+            orc.diag_(ref, host(d), host(v), alpha, beta, nmin)
+            assert np.array_equal(host(res), ref)                            # Q3 tail zero
+            E = lo.opEye(nrow, ncol)
+            res = r0.clone()
+            lo.mul_(res, E, v, alpha, beta)
+            ref = host(r0).copy()
+            orc.eye_(ref, host(v), alpha, beta, nmin)
+            assert np.array_equal(host(res), ref)                            # Q2 tail == beta
+            w = ctx.uniform(nrow, 5)
+            res = lo.transpose(E) * w
+            ref = np.empty(ncol)
+            orc.eye_(ref, host(w), 1.0, 0.0, nmin)
+            assert np.array_equal(host(res), ref)
+    v = ctx.uniform(10, 1)
+    assert lo.opEye() * v is v
+    assert np.array_equal(host(lo.opEye(10) * v), host(v))
+
+
+def test_ones_zeros(lo, ctx, orc):
+    nrow, ncol = 1003, 2049
+    v, r0 = ctx.uniform(ncol, 1, -1, 1), ctx.uniform(nrow, 2)
+    for alpha, beta in [(1.0, 0.0), (2.0, -1.5)]:
+        res = r0.clone()
+        lo.mul_(res, lo.opOnes(nrow, ncol), v, alpha, beta)
+        ref = host(r0).copy()
+        orc.ones_(ref, host(v), alpha, beta)
+        assert rel(host(res), ref) <= TOL
+        res = r0.clone() if beta != 0 else ctx.empty(nrow).fill_(float("nan"))
+        lo.mul_(res, lo.opZeros(nrow, ncol), v, alpha, beta)
+        ref = host(r0).copy()
+        orc.zeros_(ref, host(v), alpha, beta)
+        assert np.array_equal(host(res), ref)
+    u = ctx.uniform(nrow, 3)
+    assert rel(host(lo.transpose(lo.opOnes(nrow, ncol)) * u), np.full(ncol, host(u).sum())) <= TOL
+
+
+@pytest.mark.parametrize("n", [9, 1000, 100001, 2**21 + 3])
+def test_householder(lo, ctx, orc, n):
+    h = ctx.uniform(n, 3)
+    h /= float(np.sqrt(ctx.dot(h, h)))
+    v, r0 = ctx.uniform(n, 5), ctx.uniform(n, 6)
+    H = lo.opHouseholder(h)
+    for alpha, beta in [(1.0, 0.0), (-2.0, 0.5)]:
+        res = r0.clone() if beta != 0 else ctx.empty(n).fill_(float("nan"))
+        lo.mul_(res, H, v, alpha, beta)
+        ref = host(r0).copy()
+        orc.householder_(ref, host(h), host(v), alpha, beta)
+        assert rel(host(res), ref) <= TOL
+    # tprod! is None: transpose is inferred through symmetric, adjoint through hermitian (linalg.jl:91-95)
+    assert np.array_equal(host(lo.transpose(H) * v), host(H * v))
+    assert np.array_equal(host(lo.adjoint(H) * v), host(H * v))
+
+
+# ---------------------------------------------------------------- index operators: bit-exact
+@pytest.mark.parametrize("idx", [[1, 2, 4, 7], slice(3, 6), slice(1, 7, 2), slice(None), 4])
+def test_restriction_extension_reference_cases(lo, ctx, idx):
+    """test/test_linop.jl:437-461"""
+    n = 10
+    v_h = simple_vector(n)
+    v = dev(ctx, v_h)
+    P, Z = lo.opRestriction(idx, n), lo.opExtension(idx, n)
+    if isinstance(idx, slice):
+        sel = np.arange(n)[slice(None if idx.start is None else idx.start - 1, idx.stop, idx.step)]
+    elif isinstance(idx, int):
+        sel = np.array([idx - 1])
+    else:
+        sel = np.array(idx) - 1
+    w_h = v_h[sel]
+    vz_h = np.zeros(n)
+    vz_h[sel] = v_h[sel]
+    w = dev(ctx, w_h)
+    assert np.array_equal(host(P * v), w_h)
+    assert np.array_equal(host(lo.adjoint(P) * w), vz_h)
+    assert np.array_equal(host(Z * w), vz_h)
+    assert np.array_equal(host(lo.adjoint(Z) * v), w_h)
+    assert np.array_equal(host((P * Z) * w), w_h)
+    assert np.array_equal(host((Z * P) * v), vz_h)
+
+
+def test_gather_scatter_large_and_duplicates(lo, ctx, orc):
+    ncol, k = 1000003, 300007
+    rng = np.random.default_rng(0)
+    idx = rng.integers(1, ncol + 1, size=k)                                   # duplicates are legal
+    idx[-5:] = idx[:5]
+    v, u = ctx.uniform(ncol, 1), ctx.uniform(k, 2)
+    P = lo.opRestriction(idx, ncol)
+    res = ctx.empty(k).fill_(float("nan"))
+    lo.mul_(res, P, v, 3.0, 7.0)                                              # Q1: alpha/beta ignored
+    ref = np.empty(k)
+    orc.restrict_(ref, idx, host(v))
+    assert np.array_equal(host(res), ref)
+    out = lo.transpose(P) * u
+    ref = np.empty(ncol)
+    orc.extend_(ref, idx, host(u))                                            # Q4: last occurrence wins
+    assert np.array_equal(host(out), ref)
+    with pytest.raises(lo.LinearOperatorException, match="indices should be between 1 and 10"):
+        lo.opRestriction([0, 3], 10)
+    with pytest.raises(lo.LinearOperatorException, match="indices should be between 1 and 10"):
+        lo.opRestriction([11], 10)
+
+
+# ---------------------------------------------------------------- quasi-Newton operators
+def build_pair(lo, ctx, orc, kind, n, mem, npush, **kw):
+    """same seeded pushes into the CUDA operator and the oracle"""
+    if kind == "lsr1":
+        g, o = lo.LSR1Operator(n, mem=mem, ctx=ctx, **kw), orc.LSR1(n, mem=mem, **kw)
+    else:
+        inv = kind == "inv"
+        g, o = lo.LBFGSOperator(n, mem=mem, inverse=inv, ctx=ctx, **kw), orc.LBFGS(n, mem=mem, inverse=inv, **kw)
+    for i in range(npush):
+        if kind == "lsr1":
+            s = ctx.uniform(n, 300 + i, -1.0, 1.0)
+            y = 2.0 * s + 0.3 * ctx.uniform(n, 400 + i, -1.0, 1.0)
+        else:
+            s = ctx.uniform(n, 100 + i)
+            y = s + 0.1 * ctx.uniform(n, 200 + i)
+        lo.push_(g, s, y)
+        acc = o.push(host(s), host(y))
+        assert g.last_push_accepted == acc
+    return g, o
+
+
+@pytest.mark.parametrize("kind", ["fwd", "inv", "lsr1"])
+@pytest.mark.parametrize("n,mem,npush", [(10, 5, 3), (1000, 5, 7), (4097, 3, 3), (100003, 10, 12), (2048 * 37, 4, 4)])
+def test_qn_pipeline_vs_oracle(lo, ctx, orc, kind, n, mem, npush):
+    g, o = build_pair(lo, ctx, orc, kind, n, mem, npush)
+    d = g.data
+    assert d.insert == o.insert
+    assert abs(d.scaling_factor - o.scaling_factor) <= 1e-13 * abs(o.scaling_factor)
+    assert np.allclose(d.ys, o.ys, rtol=1e-13, atol=0)
+    for k0 in range(mem):
+        if o.ys[k0] != 0:
+            for which in ("a", "b") if kind == "fwd" else (("a",) if kind == "lsr1" else ()):
+                assert rel(host(d.col(which, k0)), o.col(which, k0)) <= TOL, (which, k0)
+    x, r0 = ctx.uniform(n, 7), ctx.uniform(n, 8)
+    for alpha, beta in [(1.0, 0.0), (1.5, -0.25)]:
+        res = r0.clone() if beta != 0 else ctx.empty(n).fill_(float("nan"))
+        lo.mul_(res, g, x, alpha, beta)
+        ref = host(r0).copy()
+        o.apply(host(x), alpha, beta, res=ref)
+        assert rel(host(res), ref) <= TOL, (alpha, beta)
+    # symmetric + hermitian => transpose/adjoint route to prod! (adjtrans.jl:100-102,168-170)
+    assert np.array_equal(host(lo.transpose(g) * x), host(g * x))
+    assert np.array_equal(host(lo.adjoint(g) * x), host(g * x))
+    if kind != "inv":
+        assert rel(host(lo.diag(g)), o.diag()) <= TOL
+    assert abs(d.opnorm_upper_bound - o.opnorm_upper_bound) <= 1e-10 * abs(o.opnorm_upper_bound)
+
+
+@pytest.mark.parametrize("tile_rows", [1024, 2048, 4096])
+def test_qn_tile_configs(lo, ctx, orc, tile_rows):
+    ctx.set_option("tile_rows", tile_rows)
+    try:
+        n = 3 * 148 * 1024 + 517
+        for kind in ("fwd", "inv", "lsr1"):
+            g, o = build_pair(lo, ctx, orc, kind, n, 3, 3)
+            x = ctx.uniform(n, 7)
+            assert rel(host(g * x), o.apply(host(x))) <= TOL
+    finally:
+        ctx.set_option("tile_rows", 2048)
+
+
+def test_qn_unaligned_x_and_res(lo, ctx, orc):
+    n = 50001
+    for kind in ("fwd", "inv", "lsr1"):
+        g, o = build_pair(lo, ctx, orc, kind, n, 4, 4)
+        xb, rb = ctx.uniform(n + 1, 7), ctx.uniform(n + 1, 8)
+        x, res = xb[1:], rb[1:]
+        r0 = host(res).copy()
+        lo.mul_(res, g, x, 2.0, 1.0)
+        o.apply(host(x), 2.0, 1.0, res=r0)
+        assert rel(host(res), r0) <= TOL
+
+
+def test_lbfgs_reference_predicates_on_gpu(lo, ctx):
+    """test/test_lbfgs.jl:13-71 against the CUDA path"""
+    n, mem = 10, 5
+    rtol = np.sqrt(np.finfo(float).eps)
+    B = lo.LBFGSOperator(n, mem=mem, scaling=False, ctx=ctx)
+    H = lo.InverseLBFGSOperator(n, mem=mem, scaling=False, ctx=ctx)
+    assert lo.isallocated5(B) and lo.isallocated5(H)
+    for _ in range(2):
+        Bm = host(lo.Matrix(B))
+        assert np.linalg.norm(host(lo.diag(B)) - np.diag(Bm)) <= rtol
+        assert B.data.insert == 1 and H.data.insert == 1
+        assert np.linalg.norm(Bm - np.eye(n)) <= np.finfo(float).eps
+        assert np.linalg.norm(host(lo.Matrix(H)) - np.eye(n)) <= np.finfo(float).eps
+        s, z = dev(ctx, simple_vector(n)), dev(ctx, np.zeros(n))
+        for op in (B, H):
+            lo.push_(op, s, -s)
+            assert op.data.insert == 1
+            lo.push_(op, s, z)
+            assert op.data.insert == 1
+        ins = 0
+        for i in range(1, mem + 3):
+            s = dev(ctx, np.ones(n) * i)
+            y = dev(ctx, np.r_[i, np.ones(n - 1)])
+            ins += 1
+            lo.push_(B, s, y)
+            lo.push_(H, s, y)
+        assert B.data.insert == ins % mem + 1 and H.data.insert == ins % mem + 1
+        Bm, Hm = host(lo.Matrix(B)), host(lo.Matrix(H))
+        assert np.all(np.linalg.eigvalsh((Bm + Bm.T) / 2) > 0) and np.all(np.linalg.eigvalsh((Hm + Hm.T) / 2) > 0)
+        assert np.linalg.norm(Bm - Bm.T) <= rtol * np.linalg.norm(Bm)
+        assert np.linalg.norm(host(lo.diag(B)) - np.diag(Bm)) <= rtol
+        assert np.linalg.norm(host(lo.Matrix(H * B)) - np.eye(n)) <= rtol        # Matrix(H * B) ≈ I
+        v = dev(ctx, simple_vector(n))
+        assert np.linalg.norm(host(B * v) - host(v)) > rtol
+        assert np.linalg.norm(Bm, 2) <= B.data.opnorm_upper_bound
+        lo.reset_(B)
+        lo.reset_(H)
+        assert B.data.scaling_factor == 1.0 and H.data.scaling_factor == 1.0 and lo.nprod(B) == 0
+        assert np.linalg.norm(host(B * v) - host(v)) < rtol and np.linalg.norm(host(H * v) - host(v)) < rtol
+
+
+@pytest.mark.parametrize("damped", [False, True])
+def test_lbfgs_equals_dense_bfgs_on_gpu(lo, ctx, damped):
+    """test/test_lbfgs.jl:73-99,139-156"""
+    n = mem = 10
+    rtol = np.sqrt(np.finfo(float).eps)
+    LB = lo.LBFGSOperator(n, mem=mem, scaling=False, damped=damped, ctx=ctx)
+    Bd = np.eye(n)
+    rng = np.random.default_rng(3)
+    for k in range(mem):
+        s = simple_vector(n) if k == 0 else rng.random(n)
+        y = simple_vector(n) if k == 0 else s + 0.1 * rng.random(n)
+        ys, Bs = y @ s, Bd @ s
+        if ys > (0.2 * (s @ Bs) if damped else 1e-20):
+            Bd = Bd - np.outer(Bs, Bs) / (s @ Bs) + np.outer(y, y) / ys
+        lo.push_(LB, dev(ctx, s), dev(ctx, y))
+        assert np.linalg.norm(host(lo.Matrix(LB)) - Bd) < rtol * np.linalg.norm(Bd)
+        assert np.linalg.norm(host(lo.diag(LB)) - np.diag(Bd)) < rtol * np.linalg.norm(np.diag(Bd))
+    assert np.linalg.norm(Bd, 2) <= LB.data.opnorm_upper_bound * (1 + 1e-12)
+
+
+def test_lbfgs_damped_vs_oracle(lo, ctx, orc):
+    """test/test_lbfgs.jl:104-137 with both damped variants compared against the oracle"""
+    n, mem = 1000, 5
+    kw = dict(damped=True, scaling=True, sigma2=0.8, sigma3=10.0)
+    B, H = lo.LBFGSOperator(n, mem=mem, ctx=ctx, **kw), lo.InverseLBFGSOperator(n, mem=mem, ctx=ctx, **kw)
+    Bo, Ho = orc.LBFGS(n, mem=mem, **kw), orc.LBFGS(n, mem=mem, inverse=True, **kw)
+    for i in range(1, mem + 3):
+        y = ctx.uniform(n, 500 + i, -0.2, 1.0)
+        g = ctx.uniform(n, 600 + i, -1.0, 1.0)
+        a = i / mem
+        s = -a * (H * g)
+        Bs = ctx.empty(n)
+        lo.push_(B, s, y, Bs)
+        Bo.push_damped_fwd(host(s), host(y))
+        y2, y2h = y.clone(), host(y).copy()
+        lo.push_(H, s, y2, a, g)
+        Ho.push_damped_inv(host(s), y2h, a, host(g))
+        assert rel(host(y2), y2h) <= TOL                                         # damped y written back in place
+    x = ctx.uniform(n, 7)
+    assert B.data.insert == Bo.insert and H.data.insert == Ho.insert
+    assert rel(host(B * x), Bo.apply(host(x))) <= 1e-10
+    assert rel(host(H * x), Ho.apply(host(x))) <= 1e-10
+
+
+def test_push_error_variants(lo, ctx):
+    """test/test_lbfgs.jl:220-240"""
+    n, mem = 100, 20
+    B, H = lo.LBFGSOperator(n, mem=mem, ctx=ctx), lo.InverseLBFGSOperator(n, mem=mem, ctx=ctx)
+    BD = lo.LBFGSOperator(n, mem=mem, damped=True, ctx=ctx)
+    HD = lo.InverseLBFGSOperator(n, mem=mem, damped=True, ctx=ctx)
+    s, y, g, Bs = (dev(ctx, np.ones(n)) for _ in range(4))
+    for op, args in [(B, (Bs,)), (H, (Bs,)), (HD, (Bs,)), (B, (1.0, g)), (BD, (1.0, g)), (H, (1.0, g)), (B, (1.0, g, Bs)),
+                     (BD, (1.0, g, Bs)), (H, (1.0, g, Bs))]:
+        with pytest.raises(lo.ErrorException):
+            lo.push_(op, s, y, *args)
+    with pytest.raises(lo.LinearOperatorException, match="only the diagonal of a forward"):
+        lo.diag(H)
+    with pytest.raises(lo.LinearOperatorException, match="shape mismatch"):
+        B * dev(ctx, np.ones(n + 1))
+    with pytest.raises(lo.LinearOperatorException, match="shape mismatch"):
+        lo.push_(B, dev(ctx, np.ones(n - 1)), y)
+
+
+def test_lsr1_reference_predicates_on_gpu(lo, ctx):
+    """test/test_lsr1.jl:7-72"""
+    n, mem = 10, 5
+    rtol = np.sqrt(np.finfo(float).eps)
+    B = lo.LSR1Operator(n, mem=mem, scaling=False, ctx=ctx)
+    for _ in range(2):
+        assert np.linalg.norm(host(lo.Matrix(B)) - np.eye(n)) <= np.finfo(float).eps
+        s = dev(ctx, simple_vector(n))
+        lo.push_(B, s, B * s)
+        assert B.data.insert == 1
+        for i in range(1, mem + 3):
+            lo.push_(B, dev(ctx, np.ones(n) * i), dev(ctx, np.r_[i, np.ones(n - 1)]))
+        Bm = host(lo.Matrix(B))
+        assert np.linalg.norm(Bm - Bm.T) <= rtol * np.linalg.norm(Bm)
+        assert np.linalg.norm(host(lo.diag(B)) - np.diag(Bm)) <= rtol
+        assert np.linalg.norm(Bm, 2) <= B.data.opnorm_upper_bound
+        lo.reset_(B)
+        assert B.data.scaling_factor == 1.0
+    LB = lo.LSR1Operator(n, mem=n, scaling=False, ctx=ctx)
+    Bd = np.eye(n)
+    rng = np.random.default_rng(11)
+    for k in range(n):
+        s = simple_vector(n) if k == 0 else rng.random(n) - 0.5
+        y = simple_vector(n) if k == 0 else rng.random(n) - 0.5
+        r = y - Bd @ s
+        den = r @ s
+        if abs(den) >= 1e-8 + 1e-8 * np.linalg.norm(s) * np.linalg.norm(r):
+            Bd = Bd + np.outer(r, r) / den
+        lo.push_(LB, dev(ctx, s), dev(ctx, y))
+        assert np.linalg.norm(host(lo.Matrix(LB)) - Bd) < rtol * np.linalg.norm(Bd)
+
+
+def test_apply_host_end_to_end(lo, ctx, orc):
+    import torch
+    n = 30011
+    for kind in ("fwd", "inv"):
+        g, o = build_pair(lo, ctx, orc, kind, n, 4, 5)
+        xh = torch.from_numpy(orc.uniform(n, 7)).pin_memory()
+        rh = torch.empty(n, dtype=torch.float64).pin_memory()
+        g.apply_host(rh, xh)
+        assert rel(rh.numpy(), o.apply(xh.numpy())) <= TOL
+
+
+# ---------------------------------------------------------------- composed chains (closure tree over CUDA leaves)
+def test_cfg3_chain_small(lo, ctx, orc):
+    """(opHouseholder(h)*opDiagonal(d) + 0.1*opEye(n)) * v  -- BASELINE config 3 at a size the oracle finishes quickly"""
+    n = 1000003
+    h = ctx.uniform(n, 3)
+    h /= float(np.sqrt(ctx.dot(h, h)))
+    d, v = ctx.uniform(n, 4, 0.5, 1.5), ctx.uniform(n, 5)
+    op = lo.opHouseholder(h) * lo.opDiagonal(d) + 0.1 * lo.opEye(n)
+    ref_op = orc.opHouseholder(host(h)) * orc.opDiagonal(host(d)) + 0.1 * orc.opEye(n)
+    assert rel(host(op * v), ref_op(host(v))) <= TOL
+    r0 = ctx.uniform(n, 6)
+    res, ref = r0.clone(), host(r0).copy()
+    lo.mul_(res, op, v, -1.5, 0.75)
+    ref_op.mul(ref, host(v), -1.5, 0.75)
+    assert rel(host(res), ref) <= TOL
+    assert rel(host(lo.transpose(op) * v), ref_op.T(host(v))) <= TOL
+    assert lo.nprod(op) == 2
+
+
+def test_block_diagonal_and_cat_on_gpu(lo, ctx, orc):
+    n1, n2 = 1001, 2050
+    d1, d2 = ctx.uniform(n1, 1), ctx.uniform(n2, 2)
+    g, o = build_pair(lo, ctx, orc, "fwd", n2, 3, 3)
+    bd = lo.BlockDiagonalOperator(lo.opDiagonal(d1), g)
+    bd_ref = orc.block_diagonal(orc.opDiagonal(host(d1)), orc.wrap_qn(o))
+    x = ctx.uniform(n1 + n2, 7)
+    assert rel(host(bd * x), bd_ref(host(x))) <= TOL                          # second block starts at an odd offset
+    assert rel(host(lo.transpose(bd) * x), bd_ref.T(host(x))) <= TOL
+    A, Bop = lo.opDiagonal(d2), g
+    hc = lo.hcat(A, Bop)
+    hc_ref = orc.hcat(orc.opDiagonal(host(d2)), orc.wrap_qn(o))
+    v = ctx.uniform(2 * n2, 8)
+    assert rel(host(hc * v), hc_ref(host(v))) <= TOL
+    u = ctx.uniform(n2, 9)
+    assert rel(host(lo.transpose(hc) * u), hc_ref.T(host(u))) <= TOL
+    vc = lo.vcat(A, Bop)
+    vc_ref = orc.vcat(orc.opDiagonal(host(d2)), orc.wrap_qn(o))
+    assert rel(host(vc * u), vc_ref(host(u))) <= TOL
+    assert rel(host(lo.adjoint(vc) * v), vc_ref.T(host(v))) <= TOL
+    sub = g[[3, 4, 10], slice(5, 9)]                                          # getindex = R * op * E
+    w = ctx.uniform(5, 10)
+    full = np.zeros(n2)
+    full[4:9] = host(w)
+    assert rel(host(sub * w), o.apply(full)[[2, 3, 9]]) <= TOL
+
+
+def test_op_plus_scalar(lo, ctx, orc):
+    n = 1000
+    d, v = ctx.uniform(n, 1), ctx.uniform(n, 2)
+    op = lo.opDiagonal(d) + 2.5                                               # op + x*opOnes (operations.jl:222)
+    ref = host(d) * host(v) + 2.5 * host(v).sum()
+    assert rel(host(op * v), ref) <= TOL
+
+
+# ---------------------------------------------------------------- frozen golden vectors
+def test_golden_vectors_on_gpu(lo, ctx, orc):
+    G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_v1.json")))["cases"]
+    n = 1000
+    x, r0, d, v = ctx.uniform(n, 7), ctx.uniform(n, 8), ctx.uniform(n, 1), ctx.uniform(n, 2)
+    res = r0.clone()
+    lo.mul_(res, lo.opDiagonal(d), v, 2.0, 2.0)
+    assert np.array_equal(host(res)[:16], np.array(G["diag_a2_b2"]))
+    h = ctx.uniform(n, 3)
+    h = dev(ctx, host(h) / np.linalg.norm(host(h)))
+    assert rel(host(lo.opHouseholder(h) * v)[:16], G["householder"]) <= TOL
+    dd, vv = ctx.uniform(n, 4, 0.5, 1.5), ctx.uniform(n, 5)
+    chain = lo.opHouseholder(h) * lo.opDiagonal(dd) + 0.1 * lo.opEye(n)
+    assert rel(host(chain * vv)[:16], G["cfg3_chain"]) <= TOL
+    for inverse in (False, True):
+        g, _ = build_pair(lo, ctx, orc, "inv" if inverse else "fwd", n, 5, 7)
+        assert rel(host(g * x)[:16], G["lbfgs_inv%d_apply" % inverse]) <= TOL
+        res = r0.clone()
+        lo.mul_(res, g, x, 1.5, -0.25)
+        assert rel(host(res)[:16], G["lbfgs_inv%d_apply_ab" % inverse]) <= TOL
+        if not inverse:
+            assert rel(host(lo.diag(g))[:16], G["lbfgs_diag"]) <= TOL
+    g, _ = build_pair(lo, ctx, orc, "lsr1", n, 5, 7)
+    assert rel(host(g * x)[:16], G["lsr1_apply"]) <= TOL
+    assert rel(host(lo.diag(g))[:16], G["lsr1_diag"]) <= TOL
+
+
+# ---------------------------------------------------------------- full BASELINE size: size-independent properties
+def test_cfg2_full_size_properties(lo, ctx):
+    """LBFGSOperator(n=1e8, mem=10): the oracle cannot hold this in seconds, so check properties that do not depend
+    on size: linearity, symmetry, H*(B*x) == x for the inverse built from the same pairs, determinism."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    n, mem = 10**8, 10
+    if free < 60 * 2**30:
+        pytest.skip("needs ~45 GB of HBM")
+    B = lo.LBFGSOperator(n, mem=mem, ctx=ctx)
+    H = lo.InverseLBFGSOperator(n, mem=mem, ctx=ctx)
+    for i in range(mem):
+        s = ctx.uniform(n, 100 + i)
+        y = s + 0.1 * ctx.uniform(n, 200 + i)
+        lo.push_(B, s, y)
+        lo.push_(H, s, y)
+        assert B.last_push_accepted and H.last_push_accepted
+    del s, y
+    x, z = ctx.uniform(n, 7), ctx.uniform(n, 8)
+    Bx, Bz = B * x, B * z
+    nb = np.sqrt(ctx.dot(Bx, Bx))
+    assert abs(ctx.dot(z, Bx) - ctx.dot(x, Bz)) <= 1e-12 * np.sqrt(ctx.dot(z, z)) * nb          # symmetry
+    lin = B * (2.0 * x - 3.0 * z)
+    lin -= 2.0 * Bx - 3.0 * Bz
+    assert np.sqrt(ctx.dot(lin, lin)) <= 1e-12 * (2 * nb + 3 * np.sqrt(ctx.dot(Bz, Bz)))        # linearity
+    del lin, Bz
+    back = H * Bx
+    back -= x
+    assert np.sqrt(ctx.dot(back, back)) <= 1e-9 * np.sqrt(ctx.dot(x, x))                        # H * B ≈ I
+    again = B * x
+    assert torch.equal(again, Bx)                                                               # deterministic reductions

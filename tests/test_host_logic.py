@@ -1,0 +1,201 @@
+"""Host-side dispatch layer (linearoperators.jl_b200/abstract.py, cat.py) driven on CPU with user closures over
+numpy arrays -- the same way the reference tests its own dispatch with Julia closures:
+  test/test_linop.jl:634-673 (counters), :768-891 (3-arg closures / prod3!), test/test_adjtrans.jl:10-37,
+  test/test_cat.jl:4-50, test/test_linop.jl:25-26,201-202 (shape errors)."""
+import numpy as np
+import pytest
+
+
+def dense_op(lo, M, args5=True, with_t=True):
+    M = np.asarray(M, dtype=float)
+    S = lo.Storage("numpy")
+    if args5:
+        def prod(res, v, a, b):
+            res[:] = a * (M @ v) + (b * res if b != 0 else 0)
+
+        def tprod(res, u, a, b):
+            res[:] = a * (M.T @ u) + (b * res if b != 0 else 0)
+    else:
+        def prod(res, v):
+            res[:] = M @ v
+
+        def tprod(res, u):
+            res[:] = M.T @ u
+    return lo.LinearOperator(np.float64, M.shape[0], M.shape[1], False, False, prod, tprod if with_t else None,
+                             tprod if with_t else None, S=S)
+
+
+def test_mul_shape_and_counters(lo):
+    rng = np.random.default_rng(0)
+    A = rng.random((5, 3))
+    op = dense_op(lo, A)
+    v, u = rng.random(3), rng.random(5)
+    assert np.allclose(op * v, A @ v)
+    assert lo.nprod(op) == 1 and lo.ntprod(op) == 0 and lo.nctprod(op) == 0
+    assert np.allclose(lo.transpose(op) * u, A.T @ u)
+    assert lo.ntprod(op) == 1
+    assert np.allclose(lo.adjoint(op) * u, A.T @ u)
+    assert lo.nctprod(op) == 1
+    # wrappers remap counters (src/adjtrans.jl:46-58)
+    assert lo.nprod(lo.adjoint(op)) == lo.nctprod(op)
+    assert lo.nprod(lo.transpose(op)) == lo.ntprod(op)
+    lo.reset_(op)
+    assert (lo.nprod(op), lo.ntprod(op), lo.nctprod(op)) == (0, 0, 0)
+    with pytest.raises(lo.LinearOperatorException, match="shape mismatch"):
+        op * u
+    with pytest.raises(lo.LinearOperatorException, match="shape mismatch"):
+        lo.mul_(np.empty(4), op, v)
+    with pytest.raises(lo.LinearOperatorException, match="shape mismatch"):
+        lo.adjoint(op) * v
+    assert lo.size(op) == (5, 3) and lo.size(lo.adjoint(op)) == (3, 5) and lo.size(op, 2) == 3
+    with pytest.raises(lo.LinearOperatorException):
+        lo.size(op, 3)
+
+
+def test_five_arg_mul(lo):
+    rng = np.random.default_rng(1)
+    A = rng.random((4, 4))
+    op = dense_op(lo, A)
+    v, r0 = rng.random(4), rng.random(4)
+    res = r0.copy()
+    lo.mul_(res, op, v, 2.0, -3.0)
+    assert np.allclose(res, 2 * A @ v - 3 * r0)
+    res = np.full(4, np.nan)
+    lo.mul_(res, op, v, 2.0, 0.0)                 # beta == 0: res is never read
+    assert np.allclose(res, 2 * A @ v)
+
+
+def test_three_arg_closures_prod3(lo):
+    # src/operations.jl:10-20: Mv is allocated lazily only when beta != 0
+    rng = np.random.default_rng(2)
+    A = rng.random((4, 6))
+    op = dense_op(lo, A, args5=False)
+    assert not lo.has_args5(op) and not lo.isallocated5(op)
+    v, r0 = rng.random(6), rng.random(4)
+    res = np.empty(4)
+    lo.mul_(res, op, v)
+    assert np.allclose(res, A @ v) and not lo.isallocated5(op)
+    lo.mul_(res, op, v, 3.0, 0.0)
+    assert np.allclose(res, 3 * A @ v) and not lo.isallocated5(op)
+    res = r0.copy()
+    lo.mul_(res, op, v, 3.0, 0.5)
+    assert np.allclose(res, 3 * A @ v + 0.5 * r0) and lo.isallocated5(op)
+    u, t0 = rng.random(4), rng.random(6)
+    res = t0.copy()
+    lo.mul_(res, lo.transpose(op), u, 2.0, 2.0)
+    assert np.allclose(res, 2 * A.T @ u + 2 * t0)
+
+
+def test_adjoint_algebra(lo):
+    # test/test_adjtrans.jl:10-37
+    op = dense_op(lo, np.arange(6.0).reshape(2, 3))
+    A, T, C = lo.adjoint(op), lo.transpose(op), lo.conj(op)
+    assert lo.adjoint(A) is op and lo.transpose(T) is op and lo.conj(C) is op
+    assert isinstance(lo.adjoint(T), lo.ConjugateLinearOperator) and lo.adjoint(T).parent is op
+    assert isinstance(lo.transpose(A), lo.ConjugateLinearOperator)
+    assert isinstance(lo.conj(A), lo.TransposeLinearOperator)
+    assert isinstance(lo.conj(T), lo.AdjointLinearOperator)
+    assert isinstance(lo.adjoint(C), lo.TransposeLinearOperator)
+    assert isinstance(lo.transpose(C), lo.AdjointLinearOperator)
+    v = np.array([1.0, -1.0, 2.0])
+    assert np.allclose(C * v, op * v)
+
+
+def test_adjoint_inference(lo):
+    M = np.array([[2.0, 1.0], [1.0, 3.0]])
+    S = lo.Storage("numpy")
+    prod = lambda res, v, a, b: res.__setitem__(slice(None), a * (M @ v) + (b * res if b != 0 else 0))
+    sym = lo.LinearOperator(np.float64, 2, 2, True, False, prod, None, None, S=S)
+    v = np.array([1.0, -2.0])
+    assert np.allclose(lo.transpose(sym) * v, M @ v)       # symmetric shortcut
+    assert np.allclose(lo.adjoint(sym) * v, M @ v)         # inferred through prod! (conj sandwich is a no-op for real)
+    assert lo.nprod(sym) == 2
+    nosym = lo.LinearOperator(np.float64, 2, 2, False, False, prod, None, None, S=S)
+    with pytest.raises(lo.LinearOperatorException, match="unable to infer conjugate transpose"):
+        lo.adjoint(nosym) * v
+    with pytest.raises(lo.LinearOperatorException, match="unable to infer transpose"):
+        lo.transpose(nosym) * v
+    herm = lo.LinearOperator(np.float64, 2, 2, False, True, prod, None, None, S=S)
+    assert np.allclose(lo.adjoint(herm) * v, M @ v)
+    assert np.allclose(lo.transpose(herm) * v, M @ v)      # ctprod inferred from hermitian
+
+
+def test_operator_algebra_against_dense(lo):
+    rng = np.random.default_rng(3)
+    A, B, C = rng.random((4, 5)), rng.random((4, 5)), rng.random((5, 3))
+    a, b, c = dense_op(lo, A), dense_op(lo, B), dense_op(lo, C)
+    v5, v3, u4 = rng.random(5), rng.random(3), rng.random(4)
+    for op, M, v in [(a + b, A + B, v5), (a - b, A - B, v5), (a * c, A @ C, v3), (2.5 * a, 2.5 * A, v5), (a * 2.5, 2.5 * A, v5),
+                     (-a, -A, v5), (a / 4, A / 4, v5), ((a + b) * c, (A + B) @ C, v3), (+a, A, v5)]:
+        assert np.allclose(op * v, M @ v)
+        assert np.allclose(lo.Matrix(op, like=v), M)
+    for op, M in [(lo.transpose(a * c), (A @ C).T), (lo.adjoint(a + b), (A + B).T), (lo.transpose(-a), -A.T),
+                  (lo.transpose(3 * a), 3 * A.T), (lo.adjoint(a) * 2, 2 * A.T)]:
+        assert np.allclose(op * u4, M @ u4)
+    with pytest.raises(lo.LinearOperatorException, match="shape mismatch"):
+        a * b
+    with pytest.raises(lo.LinearOperatorException, match="shape mismatch"):
+        a + c
+    sq = dense_op(lo, rng.random((4, 4)))
+    Hs = lo.Hermitian(sq)
+    assert np.allclose(lo.Matrix(Hs, like=u4), lo.Matrix(Hs, like=u4).T)
+    with pytest.raises(lo.LinearOperatorException, match="not square"):
+        lo.Symmetric(a)
+    assert lo.opEye() * v5 is v5 and (lo.opEye() * a) is a
+
+
+def test_nested_counters(lo):
+    # every node of the closure tree counts its own applies
+    rng = np.random.default_rng(4)
+    a, b = dense_op(lo, rng.random((3, 3))), dense_op(lo, rng.random((3, 3)))
+    s = a * b + a
+    s * rng.random(3)
+    assert lo.nprod(s) == 1 and lo.nprod(a) == 2 and lo.nprod(b) == 1
+
+
+def test_cat(lo):
+    # test/test_cat.jl:4-50
+    rng = np.random.default_rng(5)
+    A, B, C = rng.random((4, 3)), rng.random((4, 2)), rng.random((6, 3))
+    a, b, c = dense_op(lo, A), dense_op(lo, B), dense_op(lo, C)
+    H = lo.hcat(a, b)
+    V = lo.vcat(a, c)
+    v5, v3, u4, u10 = rng.random(5), rng.random(3), rng.random(4), rng.random(10)
+    assert np.allclose(H * v5, np.hstack([A, B]) @ v5)
+    assert np.allclose(lo.transpose(H) * u4, np.hstack([A, B]).T @ u4)
+    assert np.allclose(V * v3, np.vstack([A, C]) @ v3)
+    assert np.allclose(lo.adjoint(V) * u10, np.vstack([A, C]).T @ u10)
+    r0 = rng.random(4)
+    res = r0.copy()
+    lo.mul_(res, H, v5, 2.0, 3.0)
+    assert np.allclose(res, 2 * np.hstack([A, B]) @ v5 + 3 * r0)
+    with pytest.raises(lo.LinearOperatorException, match="hcat: inconsistent row sizes"):
+        lo.hcat(a, c)
+    with pytest.raises(lo.LinearOperatorException, match="vcat: inconsistent column sizes"):
+        lo.vcat(a, b)
+    D = rng.random((6, 2))
+    HV = lo.hvcat((2, 2), a, b, c, dense_op(lo, D))
+    assert np.allclose(HV * v5, np.block([[A, B], [C, D]]) @ v5)
+
+
+def test_block_diagonal_host(lo):
+    # test/test_linop.jl:718-756
+    rng = np.random.default_rng(6)
+    A, B = rng.random((3, 2)), rng.random((2, 4))
+    bd = lo.BlockDiagonalOperator(dense_op(lo, A), dense_op(lo, B))
+    M = np.block([[A, np.zeros((3, 4))], [np.zeros((2, 2)), B]])
+    v, u = rng.random(6), rng.random(5)
+    assert lo.size(bd) == (5, 6)
+    assert np.allclose(bd * v, M @ v)
+    assert np.allclose(lo.transpose(bd) * u, M.T @ u)
+    assert np.allclose(lo.adjoint(bd) * u, M.T @ u)
+
+
+def test_storage_promotion(lo):
+    a = dense_op(lo, np.eye(2))
+    b = dense_op(lo, np.eye(2))
+    b.S = lo.Storage("cuda", 0)
+    with pytest.raises(lo.LinearOperatorException, match="cannot be promoted"):
+        a * b
+    with pytest.raises(lo.LinearOperatorException, match="cannot be promoted"):
+        a + b
