@@ -55,7 +55,7 @@ typedef struct b2o_index_s b2o_index; /* opRestriction / opExtension index set *
 /* ---- library / context ------------------------------------------------------------------ */
 int b2o_version(void);
 const char *b2o_last_error(void);
-/* device: CUDA ordinal; stream: cudaStream_t to enqueue on (NULL -> the context creates its own). */
+/* device: CUDA ordinal; stream: cudaStream_t to enqueue on (NULL = the legacy default stream). */
 int b2o_ctx_create(int device, void *stream, b2o_ctx **out);
 int b2o_ctx_destroy(b2o_ctx *ctx);
 int b2o_ctx_sync(b2o_ctx *ctx);

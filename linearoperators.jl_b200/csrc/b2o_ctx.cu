@@ -29,12 +29,9 @@ extern "C" int b2o_ctx_create(int device, void *stream, b2o_ctx **out) {
   b2o_ctx *c = new b2o_ctx_s();
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
-  if (stream) {
-    c->stream = (cudaStream_t)stream;
-  } else {
-    B2O_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    c->own_stream = true;
-  }
+  // stream == NULL is CUDA's legacy default stream (what torch / CUDA.jl use unless told otherwise)
+  c->stream = (cudaStream_t)stream;
+  c->own_stream = false;
   B2O_CUDA(cudaMalloc(&c->d_partials, sizeof(double) * B2O_MAX_GRID * B2O_MAX_COLS));
   B2O_CUDA(cudaMalloc(&c->d_dots, sizeof(double) * B2O_WS_DOTS));
   B2O_CUDA(cudaMalloc(&c->d_bar, sizeof(unsigned long long) * 8));

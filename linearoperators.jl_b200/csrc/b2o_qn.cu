@@ -5,7 +5,9 @@
 #include <math.h>
 #include <algorithm>
 
-constexpr int64_t B2O_PITCH_ALIGN = 4096;  // rows; every supported tile size divides it
+constexpr int64_t B2O_PITCH_ALIGN = 4096;
+// 227 KB opt-in limit per CTA minus the kernels' static shared memory (flags, a few doubles)
+constexpr size_t B2O_MAX_DYN_SMEM = 227 * 1024 - 1024;  // rows; every supported tile size divides it
 
 struct b2o_qn_s {
   b2o_ctx *ctx = nullptr;
@@ -252,7 +254,7 @@ struct LaunchCfg {
 static int plan_launch(b2o_ctx *c, int64_t ntiles, int ncols, bool need_accs, LaunchCfg *cfg) {
   cfg->R = c->tile_rows;
   cfg->group = need_accs ? std::max(1, std::min(ncols, 40)) : 0;
-  const size_t max_smem = 227 * 1024;
+  const size_t max_smem = B2O_MAX_DYN_SMEM;
   int stages = 32;
   for (;; --stages) {
     cfg->L = smem_layout(cfg->R, stages, cfg->group);
@@ -275,7 +277,7 @@ static int launch_persistent(b2o_ctx *c, K kern, const LaunchCfg &cfg, Args &arg
   bool seen = false;
   for (int i = 0; i < nconfigured; ++i) seen |= (configured[i] == (const void *)kern);
   if (!seen) {
-    B2O_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2O_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2O_MAX_DYN_SMEM));
     if (nconfigured < 64) configured[nconfigured++] = (const void *)kern;
   }
   if (c->time_kernels) B2O_CUDA(cudaEventRecord(c->ev0, c->stream));
