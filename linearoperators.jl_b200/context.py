@@ -75,16 +75,12 @@ class Context:
     # -- row-partitioned multi-GPU: torch.distributed is only the rendezvous for the NCCL unique id
     def init_comm_from_torch(self, group=None):
         import torch.distributed as dist
-        torch = _torch()
+        from .partition import broadcast_bytes
         rank, world = dist.get_rank(group), dist.get_world_size(group)
         buf = (ctypes.c_ubyte * 128)()
         if rank == 0:
             _lib.check(self.lib.b2o_comm_unique_id(buf))
-        t = torch.tensor(list(buf), dtype=torch.uint8)
-        if dist.get_backend(group) == "nccl":
-            t = t.cuda(self.device)
-        dist.broadcast(t, src=0, group=group)
-        raw = bytes(t.cpu().tolist())
+        raw = broadcast_bytes(bytes(buf), 128, group, self.device)
         idbuf = (ctypes.c_ubyte * 128).from_buffer_copy(raw)
         _lib.check(self.lib.b2o_comm_init(self.handle, idbuf, world, rank))
         self.nranks, self.rank = world, rank

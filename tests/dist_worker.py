@@ -1,0 +1,123 @@
+"""Worker for the world_size>1 tests (launched by tests/test_dist.py through torch.distributed.run).
+
+  backend=gloo : CPU.  Checks the row-partition algebra the multi-GPU path relies on: slab-local arithmetic + all-reduced
+                 inner products reproduce the global oracle result (forward L-BFGS compact form and the inverse two-loop).
+  backend=nccl : GPU.  Runs the real library row-partitioned (b2o_comm_init, NCCL all-reduce per inner product) and
+                 compares the gathered result with the global CPU oracle."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def pairs(orc, n, npush):
+    out = []
+    for i in range(npush):
+        s = orc.uniform(n, 100 + i)
+        out.append((s, s + 0.1 * orc.uniform(n, 200 + i)))
+    return out
+
+
+def main():
+    backend = sys.argv[1]
+    import torch
+    import torch.distributed as dist
+    import oracle as orc
+    import linearoperators_jl_b200 as lo
+    from linearoperators_jl_b200.partition import allreduce_sum, broadcast_bytes, row_slab
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    if backend == "nccl":
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    else:
+        dist.init_process_group("gloo")
+    orc.set_mode(True, 1)
+    n, mem, npush = 100003, 4, 6
+    lo_, hi_ = row_slab(n, rank, world)
+    assert sum(row_slab(n, r, world)[1] - row_slab(n, r, world)[0] for r in range(world)) == n
+    got = broadcast_bytes(bytes(range(128)), 128)
+    assert got == bytes(range(128))
+    P = pairs(orc, n, npush)
+    x = orc.uniform(n, 7)
+
+    if backend == "gloo":
+        # forward compact form on slabs: dots all-reduced, combine local (src/lbfgs.jl:188-196)
+        B = orc.LBFGS(n, mem=mem)
+        H = orc.LBFGS(n, mem=mem, inverse=True)
+        for s, y in P:
+            B.push(s, y)
+            H.push(s, y)
+        ref_f, ref_i = B.apply(x), H.apply(x)
+        order = [(B.insert - 1 + i) % mem for i in range(mem)]
+        order = [k for k in order if B.ys[k] != 0]
+        xs = x[lo_:hi_]
+        local = []
+        for k in order:
+            local += [float(B.col("a", k)[lo_:hi_] @ xs), float(B.col("b", k)[lo_:hi_] @ xs)]
+        red = allreduce_sum(local)
+        q = xs / B.scaling_factor
+        for j, k in enumerate(order):
+            q = q + (red[2 * j + 1] * B.col("b", k)[lo_:hi_] - red[2 * j] * B.col("a", k)[lo_:hi_])
+        assert np.linalg.norm(q - ref_f[lo_:hi_]) <= 1e-12 * np.linalg.norm(ref_f[lo_:hi_])
+        # inverse two-loop on slabs: one all-reduce per inner product (src/lbfgs.jl:130-147)
+        q = xs.copy()
+        alphas = {}
+        for k in reversed(order):
+            a = allreduce_sum([float(H.col("s", k)[lo_:hi_] @ q)])[0] / H.ys[k]
+            alphas[k] = a
+            q = q - a * H.col("y", k)[lo_:hi_]
+        q = q * H.scaling_factor
+        for k in order:
+            b = alphas[k] - allreduce_sum([float(H.col("y", k)[lo_:hi_] @ q)])[0] / H.ys[k]
+            q = q + b * H.col("s", k)[lo_:hi_]
+        assert np.linalg.norm(q - ref_i[lo_:hi_]) <= 1e-12 * np.linalg.norm(ref_i[lo_:hi_])
+    else:
+        dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+        ctx = lo.default_context(dev.index)
+        ctx.init_comm_from_torch()
+        assert ctx.nranks == world and ctx.rank == rank
+        t = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(dev)
+        xs = t(x[lo_:hi_])
+        ns = hi_ - lo_
+        for kind in ("fwd", "inv", "lsr1"):
+            if kind == "lsr1":
+                g, o = lo.LSR1Operator(ns, mem=mem, ctx=ctx), orc.LSR1(n, mem=mem)
+            else:
+                g = lo.LBFGSOperator(ns, mem=mem, inverse=kind == "inv", ctx=ctx)
+                o = orc.LBFGS(n, mem=mem, inverse=kind == "inv")
+            for s, y in P:
+                if kind == "lsr1":
+                    y = 2.0 * s + 3.0 * (y - s)
+                lo.push_(g, t(s[lo_:hi_]), t(y[lo_:hi_]))
+                assert g.last_push_accepted == o.push(s, y)
+            assert g.data.insert == o.insert
+            assert abs(g.data.scaling_factor - o.scaling_factor) <= 1e-13 * abs(o.scaling_factor)
+            for alpha, beta in ((1.0, 0.0), (1.5, -0.5)):
+                r0 = orc.uniform(n, 8)
+                res = t(r0[lo_:hi_])
+                lo.mul_(res, g, xs, alpha, beta)
+                ref = r0.copy()
+                o.apply(x, alpha, beta, res=ref)
+                err = np.linalg.norm(res.cpu().numpy() - ref[lo_:hi_]) / np.linalg.norm(ref[lo_:hi_])
+                assert err <= 1e-12, (kind, alpha, beta, err)
+        # leaf operators with reductions
+        h = orc.uniform(n, 3)
+        h /= np.linalg.norm(h)
+        res = lo.opHouseholder(t(h[lo_:hi_]), ctx=ctx) * xs
+        ref = np.empty(n)
+        orc.householder_(ref, h, x, 1.0, 0.0)
+        assert np.linalg.norm(res.cpu().numpy() - ref[lo_:hi_]) <= 1e-12 * np.linalg.norm(ref[lo_:hi_])
+        res = lo.opOnes(ns, ns, ctx=ctx) * xs
+        assert np.allclose(res.cpu().numpy(), x.sum(), rtol=1e-13)
+    dist.barrier()
+    if rank == 0:
+        print("DIST_OK", backend, world)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
