@@ -51,6 +51,7 @@ typedef enum { B2O_F64 = 0, B2O_F32 = 1, B2O_BF16 = 2 } b2o_dtype;
 typedef struct b2o_ctx_s b2o_ctx;
 typedef struct b2o_qn_s b2o_qn;       /* LBFGSOperator / InverseLBFGSOperator / LSR1Operator state */
 typedef struct b2o_index_s b2o_index; /* opRestriction / opExtension index set */
+typedef struct b2o_graph_s b2o_graph; /* static operator tree lowered to one fused launch */
 
 /* ---- library / context ------------------------------------------------------------------ */
 int b2o_version(void);
@@ -140,6 +141,24 @@ int b2o_qn_get_scalars(b2o_qn *op, int *insert1, double *gamma, double *opnorm_u
 int b2o_qn_set_scalars(b2o_qn *op, int insert1, double gamma, double opnorm_ub, const double *ys, const double *aux);
 /* algorithmic DRAM bytes of one apply (SURVEY §8d / DESIGN.md), for the roofline */
 int b2o_qn_apply_bytes(b2o_qn *op, double beta, double *bytes);
+
+/* ---- fused static operator trees (src/operations.jl:100-234 closure trees collapsed into one launch) ---- */
+/* Build the tree bottom-up, compile once, apply many times.  All nodes are n x n.  Leaf vectors are aliased.
+ * leaf kinds : 0 opDiagonal(d)  1 opEye  2 opZeros  3 opOnes  4 opHouseholder(h)
+ * unary kinds: 12 op*x (scalar x)  13 -op  14 transpose(op)        binary kinds: 10 op1+op2  11 op1*op2
+ * The lowering follows mul!'s own recursion (prod_op! :117-128, sum_prod! :187-197, x*α folding :163-177), so the
+ * result equals the closure tree's, with every dot/sum taken once and no temporaries in HBM. */
+int b2o_graph_create(b2o_ctx *ctx, int64_t n, b2o_graph **out);
+int b2o_graph_destroy(b2o_graph *g);
+int b2o_graph_leaf(b2o_graph *g, int kind, const void *vec, int *node);
+int b2o_graph_unary(b2o_graph *g, int kind, int child, double x, int *node);
+int b2o_graph_binary(b2o_graph *g, int kind, int a, int b, int *node);
+int b2o_graph_compile(b2o_graph *g, int root);
+/* mul!(res, op, v, alpha, beta) (transposed != 0: transpose(op)) in ONE cooperative launch */
+int b2o_graph_apply(b2o_graph *g, int transposed, void *res, int64_t res_len, const void *v, int64_t v_len,
+                    double alpha, double beta);
+/* passes, reductions and algorithmic DRAM bytes of one apply */
+int b2o_graph_info(b2o_graph *g, int transposed, double beta, int *npasses, int *nreductions, double *alg_bytes);
 
 /* ---- row-partitioned multi-GPU (one process per GPU) ------------------------------------- */
 /* id: 128-byte ncclUniqueId produced on rank 0 by b2o_comm_unique_id and broadcast by the host

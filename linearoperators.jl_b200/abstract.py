@@ -509,8 +509,10 @@ def neg(op):
     prod_ = lambda res, v, a, b: mul_(res, op, v, -a, b)
     tprod_ = lambda res, u, a, b: mul_(res, transpose(op), u, -a, b)
     ctprod_ = lambda res, w, a, b: mul_(res, adjoint(op), w, -a, b)
-    return LinearOperator(eltype(op), op.nrow, op.ncol, op.symmetric, op.hermitian, prod_, tprod_, ctprod_,
-                          S=storage_type(op))
+    out = LinearOperator(eltype(op), op.nrow, op.ncol, op.symmetric, op.hermitian, prod_, tprod_, ctprod_,
+                         S=storage_type(op))
+    out._expr = ("neg", op)
+    return out
 
 
 def prod_op_(res, op1, op2, vtmp, v, alpha, beta):
@@ -536,7 +538,9 @@ def op_times_op(op1, op2):
     prod_ = lambda res, v, a, b: prod_op_(res, op1, op2, vtmp, v, a, b)
     tprod_ = lambda res, u, a, b: prod_op_(res, transpose(op2), transpose(op1), utmp, u, a, b)
     ctprod_ = lambda res, w, a, b: prod_op_(res, adjoint(op2), adjoint(op1), wtmp, w, a, b)
-    return LinearOperator(_promote_eltype(eltype(op1), eltype(op2)), m1, n2, False, False, prod_, tprod_, ctprod_, S=S)
+    out = LinearOperator(_promote_eltype(eltype(op1), eltype(op2)), m1, n2, False, False, prod_, tprod_, ctprod_, S=S)
+    out._expr = ("prod", op1, op2)
+    return out
 
 
 def op_times_scalar(op, x):
@@ -551,8 +555,10 @@ def op_times_scalar(op, x):
     tprod_ = lambda res, u, a, b: mul_(res, transpose(op), u, x * a, b)
     ctprod_ = lambda res, w, a, b: mul_(res, adjoint(op), w, _conj_scalar(x) * a, b)
     isreal = not isinstance(x, complex) or x.imag == 0
-    return LinearOperator(eltype(op), op.nrow, op.ncol, op.symmetric, op.hermitian and isreal, prod_, tprod_,
-                          ctprod_, S=storage_type(op))
+    out = LinearOperator(eltype(op), op.nrow, op.ncol, op.symmetric, op.hermitian and isreal, prod_, tprod_,
+                         ctprod_, S=storage_type(op))
+    out._expr = ("scale", op, x)
+    return out
 
 
 def sum_prod_(res, op1, op2, v, alpha, beta):
@@ -573,7 +579,9 @@ def op_plus_op(op1, op2):
     symm = issymmetric(op1) and issymmetric(op2)
     herm = ishermitian(op1) and ishermitian(op2)
     S = promote_storage(storage_type(op1), storage_type(op2))
-    return LinearOperator(_promote_eltype(eltype(op1), eltype(op2)), m1, n1, symm, herm, prod_, tprod_, ctprod_, S=S)
+    out = LinearOperator(_promote_eltype(eltype(op1), eltype(op2)), m1, n1, symm, herm, prod_, tprod_, ctprod_, S=S)
+    out._expr = ("sum", op1, op2)
+    return out
 
 
 def Hermitian(op):

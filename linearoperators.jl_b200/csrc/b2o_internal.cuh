@@ -57,6 +57,7 @@ struct b2o_ctx_s {
   int tile_rows = 2048;
   int stages = 0;        // 0 -> as many as shared memory allows
   int grid = 0;          // 0 -> one CTA per SM
+  int graph_blocks = 1;  // CTAs per SM of the fused-graph kernel (1: no spills, 2: more warps)
   // accounting
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

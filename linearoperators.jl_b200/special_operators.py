@@ -86,7 +86,9 @@ def opEye(*args, T=None, ctx=None, like=None):
                                      float(a), float(b)))
 
     if nrow == ncol:
-        return _Leaf(ctx, T, nrow, ncol, True, True, prod_, prod_, prod_)
+        op = _Leaf(ctx, T, nrow, ncol, True, True, prod_, prod_, prod_)
+        op._expr = ("eye",)
+        return op
     return _Leaf(ctx, T, nrow, ncol, False, False, prod_, prod_, prod_)
 
 
@@ -100,7 +102,10 @@ def opOnes(nrow, ncol, T=None, ctx=None, like=None):
         _lib.check(lib.b2o_ones_apply(h, F64, res.shape[0], v.shape[0], _vp(res), res.shape[0], _vp(v), v.shape[0],
                                       float(a), float(b)))
 
-    return _Leaf(ctx, T or _float_type(), nrow, ncol, nrow == ncol, nrow == ncol, prod_, prod_, prod_)
+    op = _Leaf(ctx, T or _float_type(), nrow, ncol, nrow == ncol, nrow == ncol, prod_, prod_, prod_)
+    if nrow == ncol:
+        op._expr = ("ones",)
+    return op
 
 
 def opZeros(nrow, ncol, T=None, ctx=None, like=None):
@@ -113,7 +118,10 @@ def opZeros(nrow, ncol, T=None, ctx=None, like=None):
         _lib.check(lib.b2o_zeros_apply(h, F64, res.shape[0], v.shape[0], _vp(res), res.shape[0], v.shape[0],
                                        float(a), float(b)))
 
-    return _Leaf(ctx, T or _float_type(), nrow, ncol, nrow == ncol, nrow == ncol, prod_, prod_, prod_)
+    op = _Leaf(ctx, T or _float_type(), nrow, ncol, nrow == ncol, nrow == ncol, prod_, prod_, prod_)
+    if nrow == ncol:
+        op._expr = ("zeros",)
+    return op
 
 
 def opDiagonal(*args, ctx=None):
@@ -137,7 +145,9 @@ def opDiagonal(*args, ctx=None):
 
     del dp
     if nrow == ncol:
-        return _Leaf(ctx, d.dtype, nrow, ncol, True, True, prod_, prod_, prod_)
+        op = _Leaf(ctx, d.dtype, nrow, ncol, True, True, prod_, prod_, prod_)
+        op._expr = ("diag", d)
+        return op
     return _Leaf(ctx, d.dtype, nrow, ncol, False, False, prod_, prod_, prod_)
 
 
@@ -152,7 +162,9 @@ def opHouseholder(h, ctx=None):
         _lib.check(lib.b2o_householder_apply(hd, F64, n, _vp(h, "h"), _vp(res), res.shape[0], _vp(v), v.shape[0],
                                              float(a), float(b)))
 
-    return _Leaf(ctx, h.dtype, n, n, True, True, prod_, None, prod_)
+    op = _Leaf(ctx, h.dtype, n, n, True, True, prod_, None, prod_)
+    op._expr = ("house", h)
+    return op
 
 
 def _expand_index(idx, ncol):

@@ -527,3 +527,86 @@ def test_cfg2_full_size_properties(lo, ctx):
     assert np.sqrt(ctx.dot(back, back)) <= 1e-9 * np.sqrt(ctx.dot(x, x))                        # H * B ≈ I
     again = B * x
     assert torch.equal(again, Bx)                                                               # deterministic reductions
+
+
+# ---------------------------------------------------------------- fused static trees (csrc/b2o_graph.cu)
+def _mk_vecs(ctx, n):
+    h1 = ctx.uniform(n, 3)
+    h1 /= float(np.sqrt(ctx.dot(h1, h1)))
+    h2 = ctx.uniform(n, 13)
+    h2 /= float(np.sqrt(ctx.dot(h2, h2)))
+    return h1, h2, ctx.uniform(n, 4, 0.5, 1.5), ctx.uniform(n, 14, -1.0, 1.0), ctx.uniform(n, 5), ctx.uniform(n, 6)
+
+
+@pytest.mark.parametrize("n", [7, 1000, 1024 * 148 * 2 + 13])
+def test_fused_cfg3_chain(lo, ctx, orc, n):
+    """(opHouseholder(h)*opDiagonal(d) + 0.1*opEye(n)) * v in ONE launch == closure tree == oracle"""
+    h1, _, d, _, v, r0 = _mk_vecs(ctx, n)
+    tree = lo.opHouseholder(h1) * lo.opDiagonal(d) + 0.1 * lo.opEye(n)
+    fused = lo.fuse(tree)
+    info = fused.info()
+    assert info["passes"] == 2 and info["reductions"] == 1 and info["alg_bytes"] == 7 * 8 * n     # SURVEY Appendix A
+    ref_op = orc.opHouseholder(host(h1)) * orc.opDiagonal(host(d)) + 0.1 * orc.opEye(n)
+    l0 = ctx.launch_count()
+    out = fused * v
+    assert ctx.launch_count() - l0 == 1
+    assert rel(host(out), ref_op(host(v))) <= TOL
+    assert rel(host(out), host(tree * v)) <= TOL
+    for alpha, beta in [(-1.5, 0.75), (2.0, 1.0)]:
+        res, ref = r0.clone(), host(r0).copy()
+        lo.mul_(res, fused, v, alpha, beta)
+        ref_op.mul(ref, host(v), alpha, beta)
+        assert rel(host(res), ref) <= TOL
+    assert rel(host(lo.transpose(fused) * v), ref_op.T(host(v))) <= TOL
+    res = ctx.empty(n).fill_(float("nan"))
+    lo.mul_(res, fused, v, 1.0, 0.0)                                             # beta == 0 never reads res
+    assert np.isfinite(host(res)).all()
+
+
+def test_fused_trees_vs_oracle(lo, ctx, orc):
+    n = 50001
+    h1, h2, d1, d2, v, r0 = _mk_vecs(ctx, n)
+    H1, H2, D1, D2, E, O, Z = (lo.opHouseholder(h1), lo.opHouseholder(h2), lo.opDiagonal(d1), lo.opDiagonal(d2), lo.opEye(n),
+                               lo.opOnes(n, n), lo.opZeros(n, n))
+    oH1, oH2, oD1, oD2, oE, oO, oZ = (orc.opHouseholder(host(h1)), orc.opHouseholder(host(h2)), orc.opDiagonal(host(d1)),
+                                      orc.opDiagonal(host(d2)), orc.opEye(n), orc.opOnes(n, n), orc.opZeros(n, n))
+    cases = [
+        (D1 + D2, oD1 + oD2, True),                       # no reduction: bit-exact
+        (D1 * D2 - 2.5 * E, oD1 * oD2 - 2.5 * oE, True),
+        (-(D1 * 0.5) + Z, -(oD1 * 0.5) + oZ, True),
+        (H1 * H2, oH1 * oH2, False),                      # dependent reductions: 3 passes
+        (H1 * D1 * H2 + D2, oH1 * oD1 * oH2 + oD2, False),
+        (lo.transpose(H1 * D1) + 3.0 * D2, (oH1 * oD1).T + 3.0 * oD2, False),
+        (D1 + 1e-3 * O, oD1 + 1e-3 * oO, False),          # opOnes: sum reduction
+        (H1 - H2, oH1 - oH2, False),                      # two independent reductions in one pass
+    ]
+    for tree, ref_op, exact in cases:
+        fused = lo.fuse(tree)
+        for alpha, beta in [(1.0, 0.0), (0.75, -1.25)]:
+            res, ref = r0.clone(), host(r0).copy()
+            lo.mul_(res, fused, v, alpha, beta)
+            ref_op.mul(ref, host(v), alpha, beta)
+            if exact:
+                assert np.array_equal(host(res), ref)
+            else:
+                assert rel(host(res), ref) <= TOL
+            rt, reft = r0.clone(), host(r0).copy()
+            lo.mul_(rt, lo.transpose(fused), v, alpha, beta)
+            ref_op.tmul(reft, host(v), alpha, beta)
+            assert rel(host(rt), reft) <= TOL
+    assert lo.fuse(H1 * H2).info()["passes"] == 3
+    assert lo.fuse(H1 - H2).info()["passes"] == 2
+
+
+def test_fuse_rejects_non_static_trees(lo, ctx):
+    n = 100
+    g = lo.LBFGSOperator(n, ctx=ctx)
+    with pytest.raises(lo.LinearOperatorException):
+        lo.fuse(g + lo.opEye(n))
+    with pytest.raises(lo.LinearOperatorException):
+        lo.fuse(lo.opEye(5, 7))
+    with pytest.raises(lo.LinearOperatorException):
+        lo.fuse(lo.opRestriction([1, 2], n))
+    f = lo.fuse(lo.opEye(n) * 2.0)
+    with pytest.raises(lo.LinearOperatorException, match="shape mismatch"):
+        f * ctx.uniform(n + 1, 1)

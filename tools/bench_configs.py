@@ -1,0 +1,126 @@
+#!/usr/bin/env python
+"""Measures the BASELINE.json configs other than the bench.py headline, plus the remaining kernels, on ONE B200:
+one JSON line per case with the algorithmic-bytes roofline.  Output is copied to profiles/."""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import linearoperators_jl_b200 as lo  # noqa: E402
+
+PEAK = 6570.0
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timeit(fn, steps, warmup=3, flush=None):
+    for _ in range(warmup):
+        if flush is not None:
+            flush.zero_()
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(steps):
+        if flush is not None:
+            flush.zero_()          # > L2: evicts the working set between iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / steps
+
+
+def line(name, ms, alg_bytes, **kw):
+    gbs = alg_bytes / (ms * 1e-3) / 1e9
+    d = {"case": name, "ms": round(ms, 5), "alg_bytes": alg_bytes, "GBps": round(gbs, 1), "frac_of_measured_peak": round(gbs / PEAK, 3),
+         "frac_of_nominal_8TBs": round(gbs / 8000.0, 3)}
+    d.update(kw)
+    print(json.dumps(d), flush=True)
+
+
+def main():
+    ctx = lo.default_context(0)
+    big = "--small" not in sys.argv
+    n = 10**8 if big else 10**6
+    flush = torch.empty(256 * 2**20 // 8, dtype=torch.float64, device="cuda")
+    # cfg1: opDiagonal(n=1e6) * v  (24 MB: L2 resident unless flushed)
+    n1 = 10**6
+    d, v, res = ctx.uniform(n1, 1), ctx.uniform(n1, 2), ctx.empty(n1)
+    D = lo.opDiagonal(d)
+    line("cfg1 opDiagonal(n=1e6)*v, L2 flushed between iterations", timeit(lambda: lo.mul_(res, D, v), 50, flush=flush), 24.0 * n1)
+    line("cfg1 opDiagonal(n=1e6)*v, L2 warm", timeit(lambda: lo.mul_(res, D, v), 200), 24.0 * n1)
+    # elementwise leaves at n=1e8
+    d, v, res = ctx.uniform(n, 1), ctx.uniform(n, 2), ctx.empty(n)
+    D, E, Z, O = lo.opDiagonal(d), lo.opEye(n), lo.opZeros(n, n), lo.opOnes(n, n)
+    line("opDiagonal(n=%g)*v" % n, timeit(lambda: lo.mul_(res, D, v), 30), 24.0 * n)
+    line("opDiagonal 5-arg (alpha=2,beta=2)", timeit(lambda: lo.mul_(res, D, v, 2.0, 2.0), 30), 32.0 * n)
+    line("opEye(n)*v", timeit(lambda: lo.mul_(res, E, v), 30), 16.0 * n)
+    line("opZeros(n)*v", timeit(lambda: lo.mul_(res, Z, v), 30), 8.0 * n)
+    line("opOnes(n,n)*v (sum + fill: 2 launches)", timeit(lambda: lo.mul_(res, O, v), 30), 16.0 * n)
+    h = ctx.uniform(n, 3)
+    h /= float(np.sqrt(ctx.dot(h, h)))
+    H = lo.opHouseholder(h)
+    line("opHouseholder(h)*v (one cooperative launch)", timeit(lambda: lo.mul_(res, H, v), 30), 40.0 * n)
+    # cfg3
+    dd = ctx.uniform(n, 4, 0.5, 1.5)
+    tree = lo.opHouseholder(h) * lo.opDiagonal(dd) + 0.1 * lo.opEye(n)
+    fused = lo.fuse(tree)
+    l0 = ctx.launch_count()
+    lo.mul_(res, tree, v)
+    tree_launches = ctx.launch_count() - l0
+    line("cfg3 (opHouseholder*opDiagonal + 0.1*opEye)*v, closure tree", timeit(lambda: lo.mul_(res, tree, v), 30), 56.0 * n,
+         launches_per_apply=tree_launches, reference_traffic_bytes=88.0 * n)
+    for gb in (1, 2):
+        ctx.set_option("graph_blocks", gb)
+        line("cfg3 fused, ONE launch (graph_blocks=%d)" % gb, timeit(lambda: lo.mul_(res, fused, v), 30), 56.0 * n, launches_per_apply=1)
+    ctx.set_option("graph_blocks", 1)
+    del tree, fused, H, dd, h
+    # gather / scatter
+    k = n // 4
+    idx = torch.randint(1, n + 1, (k,), device="cuda", dtype=torch.int64).cpu().numpy()
+    P = lo.opRestriction(idx, n)
+    rk, uk = ctx.empty(k), ctx.uniform(k, 9)
+    line("opRestriction random k=n/4 (gather)", timeit(lambda: lo.mul_(rk, P, v), 20), 24.0 * k, note="random 8-byte gathers are sector (32 B) granular")
+    line("opExtension random k=n/4 (memset + scatter)", timeit(lambda: lo.mul_(res, lo.transpose(P), uk), 20), 8.0 * n + 24.0 * k)
+    idx = np.arange(1, n + 1, 4, dtype=np.int64)
+    P = lo.opRestriction(idx, n)
+    rk = ctx.empty(idx.shape[0])
+    line("opRestriction 1:4:n (strided gather)", timeit(lambda: lo.mul_(rk, P, v), 20), 24.0 * idx.shape[0])
+    del P, rk, uk, idx, d, D
+    torch.cuda.empty_cache()
+    # quasi-Newton applies
+    for name, mk, m, npr in (("LSR1Operator(n, mem=10)", lambda: lo.LSR1Operator(n, mem=10, ctx=ctx), 10, 2 * 10 + 3),
+                             ("cfg5 per-GPU slab: InverseLBFGSOperator(n, mem=20)", lambda: lo.InverseLBFGSOperator(n, mem=20, ctx=ctx), 20, 8 * 20 + 2),
+                             ("cfg2 LBFGSOperator(n, mem=10)", lambda: lo.LBFGSOperator(n, mem=10, ctx=ctx), 10, 4 * 10 + 3)):
+        op = mk()
+        t0 = time.perf_counter()
+        for i in range(m):
+            if "LSR1" in name:
+                s = ctx.uniform(n, 300 + i, -1.0, 1.0)
+                y = 2.0 * s + 0.3 * ctx.uniform(n, 400 + i, -1.0, 1.0)
+            else:
+                s = ctx.uniform(n, 100 + i)
+                y = s + 0.1 * ctx.uniform(n, 200 + i)
+            lo.push_(op, s, y)
+            assert op.last_push_accepted
+        torch.cuda.synchronize()
+        push_s = (time.perf_counter() - t0) / m
+        del s, y
+        line(name + " apply", timeit(lambda: lo.mul_(res, op, v), 20), npr * 8.0 * n, push_seconds_avg=round(push_s, 4))
+        line(name + " apply 5-arg beta=0.5", timeit(lambda: lo.mul_(res, op, v, 2.0, 0.5), 10), (npr + 1) * 8.0 * n)
+        del op
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
