@@ -157,6 +157,13 @@ int b2o_graph_compile(b2o_graph *g, int root);
 /* mul!(res, op, v, alpha, beta) (transposed != 0: transpose(op)) in ONE cooperative launch */
 int b2o_graph_apply(b2o_graph *g, int transposed, void *res, int64_t res_len, const void *v, int64_t v_len,
                     double alpha, double beta);
+/* The compiled passes run either as an NVRTC-specialised instantiation of the pass template (straight-line code,
+ * default when libnvrtc + the driver are present) or through the built-in interpreter kernel (ctx option
+ * "graph_jit"=0).  b2o_graph_create accepts ctx == NULL for a dry graph that can be lowered and NVRTC-compiled on
+ * a CPU-only box (b2o_graph_jit_check) but not applied. */
+int b2o_graph_jit_source(b2o_graph *g, int transposed, double beta, char *buf, int64_t cap, int64_t *len);
+int b2o_graph_jit_check(b2o_graph *g, int64_t *cubin_bytes);
+int b2o_graph_uses_jit(b2o_graph *g, int transposed, double beta, int *out);
 /* passes, reductions and algorithmic DRAM bytes of one apply */
 int b2o_graph_info(b2o_graph *g, int transposed, double beta, int *npasses, int *nreductions, double *alg_bytes);
 

@@ -79,8 +79,10 @@ extern "C" int b2o_ctx_set_option(b2o_ctx *c, const char *key, int64_t value) {
   } else if (!strcmp(key, "grid")) {
     if (value < 0 || value > B2O_MAX_GRID) B2O_FAIL(B2O_EARG, "grid out of range");
     c->grid = (int)value;
+  } else if (!strcmp(key, "graph_jit")) {
+    c->graph_jit = value != 0;
   } else if (!strcmp(key, "graph_blocks")) {
-    if (value < 1 || value > 2) B2O_FAIL(B2O_EARG, "graph_blocks must be 1 or 2");
+    if (value < 1 || value > 4) B2O_FAIL(B2O_EARG, "graph_blocks must be 1..4");
     c->graph_blocks = (int)value;
   } else if (!strcmp(key, "time_kernels")) {
     c->time_kernels = value != 0;

@@ -17,8 +17,11 @@
 #include <memory>
 
 constexpr int G_MAX_PROG = 96, G_MAX_PASS = 4, G_MAX_ARR = 12, G_MAX_SCAL = 48, G_MAX_RED = 8;
-constexpr int G_DEPTH = 6, G_SLOTS = 6, G_EPT = 4, G_NT = 256, G_RED_PER_PASS = 4, G_MAX_SOP = 8;
-enum { I_PUSH_ARR = 0, I_PUSH_SCAL = 1, I_ADD = 2, I_SUB = 3, I_MUL = 4, I_RED = 5, I_STORE = 6 };
+constexpr int G_DEPTH = 6, G_SLOTS = 6, G_EPT = 2, G_NT = 256, G_RED_PER_PASS = 4, G_MAX_SOP = 8;
+// abstract ops used by the host code generator; the device sees FLAT opcodes (op, stack depth and array slot folded
+// into one number so that one jump-table dispatch reaches code with static register indices)
+enum { I_PUSH_ARR = 0, I_PUSH_SCAL = 1, I_ADD = 2, I_SUB = 3, I_MUL = 4, I_RED = 5, I_STORE = 6, I_BINA = 7, I_BINS = 8 };
+enum { F_PUSHA = 0, F_PUSHS = 48, F_BIN = 56, F_BINA = 80, F_BINS = 224, F_RED = 248, F_STORE = 256 };
 enum { GK_DIAG = 0, GK_EYE = 1, GK_ZEROS = 2, GK_ONES = 3, GK_HOUSE = 4, GK_SUM = 10, GK_PROD = 11, GK_SCALE = 12, GK_NEG = 13,
        GK_TRANS = 14 };
 
@@ -30,7 +33,7 @@ struct GraphArgs {
   int64_t n;
   int npass;
   int prog_len[G_MAX_PASS];
-  uint32_t prog[G_MAX_PASS][G_MAX_PROG];        // op | sp<<8 | arg<<16
+  uint32_t prog[G_MAX_PASS][G_MAX_PROG];        // flat opcode | arg<<16
   int narr_pass[G_MAX_PASS];
   unsigned char arr_of_pass[G_MAX_PASS][G_SLOTS];
   double scal[G_MAX_SCAL];
@@ -47,13 +50,15 @@ struct GraphArgs {
 };
 
 #define G_FOR_J _Pragma("unroll") for (int j = 0; j < G_EPT; ++j)
+#define G_ROW6(M, A) M(A, 0) M(A, 1) M(A, 2) M(A, 3) M(A, 4) M(A, 5)
+#define G_ROW6S(M, A) M(A, 1) M(A, 2) M(A, 3) M(A, 4) M(A, 5) M(A, 6)
 
 template <int MINB>
 __global__ void __launch_bounds__(G_NT, MINB) graph_kernel(const __grid_constant__ GraphArgs p) {
   __shared__ double s_scal[G_MAX_SCAL];
   __shared__ double s_red[G_MAX_RED];
   __shared__ double s_w[G_NT / 32][G_RED_PER_PASS];
-  __shared__ uint32_t s_prog[G_MAX_PROG];
+  __shared__ uint32_t s_prog[G_MAX_PROG + 1];
   __shared__ bool s_is_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < G_MAX_SCAL; i += G_NT) s_scal[i] = p.scal[i];
@@ -72,7 +77,7 @@ __global__ void __launch_bounds__(G_NT, MINB) graph_kernel(const __grid_constant
     if (tid == 0)
       for (int i = 0; i < p.nsop[pass]; ++i) s_scal[p.sop[pass][i][0]] = s_scal[p.sop[pass][i][1]] * s_red[p.sop[pass][i][2]];
     const int len = p.prog_len[pass];
-    for (int i = tid; i < len; i += G_NT) s_prog[i] = p.prog[pass][i];
+    for (int i = tid; i <= len; i += G_NT) s_prog[i] = i < len ? p.prog[pass][i] : 0u;
     __syncthreads();
     const int narr = p.narr_pass[pass];
     double racc[G_RED_PER_PASS];
@@ -82,128 +87,77 @@ __global__ void __launch_bounds__(G_NT, MINB) graph_kernel(const __grid_constant
 
     for (int64_t tt = blockIdx.x; tt < ntiles; tt += gridDim.x) {
       const int64_t t = reverse ? (ntiles - 1 - tt) : tt;
-      // rows of this thread: pairs e = jj*G_NT + tid  (jj < G_EPT/2) -> rows 2e, 2e+1 of the tile
-      const int64_t row0 = t * tile_rows;
+      const int64_t r0 = t * tile_rows + 2 * (int64_t)tid;      // this thread's two rows
+      const bool in0 = r0 < p.n, in1 = r0 + 1 < p.n;
       double av[G_SLOTS][G_EPT];
 #pragma unroll
       for (int s = 0; s < G_SLOTS; ++s) {
+        av[s][0] = av[s][1] = 0.0;
         if (s < narr) {
           const int a = p.arr_of_pass[pass][s];
           const double *base = p.arr[a];
-          const bool al = p.arr_al16[a];
-#pragma unroll
-          for (int jj = 0; jj < G_EPT / 2; ++jj) {
-            const int64_t r = row0 + 2 * ((int64_t)jj * G_NT + tid);
-            if (al && r + 1 < p.n) {
-              double2 v = *reinterpret_cast<const double2 *>(base + r);
-              av[s][2 * jj] = v.x;
-              av[s][2 * jj + 1] = v.y;
-            } else {
-              av[s][2 * jj] = r < p.n ? base[r] : 0.0;
-              av[s][2 * jj + 1] = r + 1 < p.n ? base[r + 1] : 0.0;
-            }
+          if (p.arr_al16[a] && in1) {
+            double2 v = *reinterpret_cast<const double2 *>(base + r0);
+            av[s][0] = v.x;
+            av[s][1] = v.y;
+          } else {
+            if (in0) av[s][0] = base[r0];
+            if (in1) av[s][1] = base[r0 + 1];
           }
-        } else {
-          G_FOR_J av[s][j] = 0.0;
         }
       }
       double st[G_DEPTH][G_EPT];
 #pragma unroll
       for (int d = 0; d < G_DEPTH; ++d) G_FOR_J st[d][j] = 0.0;
 
+      uint32_t ins = s_prog[0];
       for (int pc = 0; pc < len; ++pc) {
-        const uint32_t ins = s_prog[pc];
-        const int op = ins & 0xff, sp = (ins >> 8) & 0xff, arg = ins >> 16;
-        switch (op) {
-          case I_PUSH_ARR: {
-            double tmp[G_EPT];
-            switch (arg) {
-#define G_CASE_SLOT(S) case S: G_FOR_J tmp[j] = av[S][j]; break;
-              G_CASE_SLOT(0) G_CASE_SLOT(1) G_CASE_SLOT(2) G_CASE_SLOT(3) G_CASE_SLOT(4) G_CASE_SLOT(5)
-#undef G_CASE_SLOT
-              default: G_FOR_J tmp[j] = 0.0;
-            }
-            switch (sp) {
-#define G_CASE_SP(S) case S: G_FOR_J st[S][j] = tmp[j]; break;
-              G_CASE_SP(0) G_CASE_SP(1) G_CASE_SP(2) G_CASE_SP(3) G_CASE_SP(4) G_CASE_SP(5)
-#undef G_CASE_SP
-            }
-            break;
-          }
-          case I_PUSH_SCAL: {
-            const double c = s_scal[arg];
-            switch (sp) {
-#define G_CASE_SP(S) case S: G_FOR_J st[S][j] = c; break;
-              G_CASE_SP(0) G_CASE_SP(1) G_CASE_SP(2) G_CASE_SP(3) G_CASE_SP(4) G_CASE_SP(5)
-#undef G_CASE_SP
-            }
-            break;
-          }
-          case I_ADD:
-            switch (sp) {
-#define G_CASE_SP(S) case S: G_FOR_J st[S - 2][j] = st[S - 2][j] + st[S - 1][j]; break;
-              G_CASE_SP(2) G_CASE_SP(3) G_CASE_SP(4) G_CASE_SP(5) G_CASE_SP(6)
-#undef G_CASE_SP
-            }
-            break;
-          case I_SUB:
-            switch (sp) {
-#define G_CASE_SP(S) case S: G_FOR_J st[S - 2][j] = st[S - 2][j] - st[S - 1][j]; break;
-              G_CASE_SP(2) G_CASE_SP(3) G_CASE_SP(4) G_CASE_SP(5) G_CASE_SP(6)
-#undef G_CASE_SP
-            }
-            break;
-          case I_MUL:
-            switch (sp) {
-#define G_CASE_SP(S) case S: G_FOR_J st[S - 2][j] = st[S - 2][j] * st[S - 1][j]; break;
-              G_CASE_SP(2) G_CASE_SP(3) G_CASE_SP(4) G_CASE_SP(5) G_CASE_SP(6)
-#undef G_CASE_SP
-            }
-            break;
-          case I_RED: {
-            // masked sum of the top of stack into local reduction `arg` (rows >= n contribute nothing)
-            double tmp[G_EPT];
-            switch (sp) {
-#define G_CASE_SP(S) case S: G_FOR_J tmp[j] = st[S - 1][j]; break;
-              G_CASE_SP(1) G_CASE_SP(2) G_CASE_SP(3) G_CASE_SP(4) G_CASE_SP(5) G_CASE_SP(6)
-#undef G_CASE_SP
-              default: G_FOR_J tmp[j] = 0.0;
-            }
-            double s = 0.0;
-#pragma unroll
-            for (int jj = 0; jj < G_EPT / 2; ++jj) {
-              const int64_t r = row0 + 2 * ((int64_t)jj * G_NT + tid);
-              if (r < p.n) s += tmp[2 * jj];
-              if (r + 1 < p.n) s += tmp[2 * jj + 1];
-            }
-            switch (arg) {
-              case 0: racc[0] += s; break;
-              case 1: racc[1] += s; break;
-              case 2: racc[2] += s; break;
-              case 3: racc[3] += s; break;
-            }
-            break;
-          }
-          case I_STORE: {
-            double tmp[G_EPT];
-            switch (sp) {
-#define G_CASE_SP(S) case S: G_FOR_J tmp[j] = st[S - 1][j]; break;
-              G_CASE_SP(1) G_CASE_SP(2) G_CASE_SP(3) G_CASE_SP(4) G_CASE_SP(5) G_CASE_SP(6)
-#undef G_CASE_SP
-              default: G_FOR_J tmp[j] = 0.0;
-            }
-#pragma unroll
-            for (int jj = 0; jj < G_EPT / 2; ++jj) {
-              const int64_t r = row0 + 2 * ((int64_t)jj * G_NT + tid);
-              if (p.out_al16 && r + 1 < p.n) {
-                stg_stream2(p.out + r, make_double2(tmp[2 * jj], tmp[2 * jj + 1]));
-              } else {
-                if (r < p.n) p.out[r] = tmp[2 * jj];
-                if (r + 1 < p.n) p.out[r + 1] = tmp[2 * jj + 1];
-              }
-            }
-            break;
-          }
+        const uint32_t cur = ins;
+        ins = s_prog[pc + 1];                       // prefetch the next instruction
+        const int arg = cur >> 16;
+        switch (cur & 0xffffu) {
+#define C_PUSHA(SL, SP) case F_PUSHA + SL * 8 + SP: G_FOR_J st[SP][j] = av[SL][j]; break;
+          G_ROW6(C_PUSHA, 0) G_ROW6(C_PUSHA, 1) G_ROW6(C_PUSHA, 2) G_ROW6(C_PUSHA, 3) G_ROW6(C_PUSHA, 4) G_ROW6(C_PUSHA, 5)
+#define C_PUSHS(U, SP) case F_PUSHS + SP: { const double c = s_scal[arg]; G_FOR_J st[SP][j] = c; } break;
+          G_ROW6(C_PUSHS, 0)
+#define C_ADD(U, SP) case F_BIN + 0 * 8 + SP: G_FOR_J st[SP - 2][j] = st[SP - 2][j] + st[SP - 1][j]; break;
+#define C_SUB(U, SP) case F_BIN + 1 * 8 + SP: G_FOR_J st[SP - 2][j] = st[SP - 2][j] - st[SP - 1][j]; break;
+#define C_MUL(U, SP) case F_BIN + 2 * 8 + SP: G_FOR_J st[SP - 2][j] = st[SP - 2][j] * st[SP - 1][j]; break;
+          C_ADD(0, 2) C_ADD(0, 3) C_ADD(0, 4) C_ADD(0, 5) C_ADD(0, 6)
+          C_SUB(0, 2) C_SUB(0, 3) C_SUB(0, 4) C_SUB(0, 5) C_SUB(0, 6)
+          C_MUL(0, 2) C_MUL(0, 3) C_MUL(0, 4) C_MUL(0, 5) C_MUL(0, 6)
+          // top (op)= array slot
+#define C_ADDA(SL, SP) case F_BINA + (0 * 6 + SL) * 8 + SP: G_FOR_J st[SP - 1][j] = st[SP - 1][j] + av[SL][j]; break;
+#define C_SUBA(SL, SP) case F_BINA + (1 * 6 + SL) * 8 + SP: G_FOR_J st[SP - 1][j] = st[SP - 1][j] - av[SL][j]; break;
+#define C_MULA(SL, SP) case F_BINA + (2 * 6 + SL) * 8 + SP: G_FOR_J st[SP - 1][j] = st[SP - 1][j] * av[SL][j]; break;
+          G_ROW6S(C_ADDA, 0) G_ROW6S(C_ADDA, 1) G_ROW6S(C_ADDA, 2) G_ROW6S(C_ADDA, 3) G_ROW6S(C_ADDA, 4) G_ROW6S(C_ADDA, 5)
+          G_ROW6S(C_SUBA, 0) G_ROW6S(C_SUBA, 1) G_ROW6S(C_SUBA, 2) G_ROW6S(C_SUBA, 3) G_ROW6S(C_SUBA, 4) G_ROW6S(C_SUBA, 5)
+          G_ROW6S(C_MULA, 0) G_ROW6S(C_MULA, 1) G_ROW6S(C_MULA, 2) G_ROW6S(C_MULA, 3) G_ROW6S(C_MULA, 4) G_ROW6S(C_MULA, 5)
+          // top (op)= scalar
+#define C_ADDS(U, SP) case F_BINS + 0 * 8 + SP: { const double c = s_scal[arg]; G_FOR_J st[SP - 1][j] = st[SP - 1][j] + c; } break;
+#define C_SUBS(U, SP) case F_BINS + 1 * 8 + SP: { const double c = s_scal[arg]; G_FOR_J st[SP - 1][j] = st[SP - 1][j] - c; } break;
+#define C_MULS(U, SP) case F_BINS + 2 * 8 + SP: { const double c = s_scal[arg]; G_FOR_J st[SP - 1][j] = st[SP - 1][j] * c; } break;
+          G_ROW6S(C_ADDS, 0) G_ROW6S(C_SUBS, 0) G_ROW6S(C_MULS, 0)
+          // masked sum of the top of stack into local reduction `arg` (rows >= n contribute nothing)
+#define C_RED(U, SP)                                                   \
+  case F_RED + SP: {                                                   \
+    double s = (in0 ? st[SP - 1][0] : 0.0) + (in1 ? st[SP - 1][1] : 0.0); \
+    if (arg == 0) racc[0] += s;                                        \
+    else if (arg == 1) racc[1] += s;                                   \
+    else if (arg == 2) racc[2] += s;                                   \
+    else racc[3] += s;                                                 \
+  } break;
+          G_ROW6S(C_RED, 0)
+#define C_STORE(U, SP)                                                                       \
+  case F_STORE + SP: {                                                                       \
+    if (p.out_al16 && in1) stg_stream2(p.out + r0, make_double2(st[SP - 1][0], st[SP - 1][1])); \
+    else {                                                                                   \
+      if (in0) p.out[r0] = st[SP - 1][0];                                                    \
+      if (in1) p.out[r0 + 1] = st[SP - 1][1];                                                \
+    }                                                                                        \
+  } break;
+          G_ROW6S(C_STORE, 0)
+          default: break;
         }
       }
     }
@@ -383,6 +337,12 @@ struct Compiled {
   GraphArgs args;
   std::vector<SExpr> S;                 // scalar expressions; slot i of args.scal
   int alg_arrays_read = 0;
+  // specialised instantiation (NVRTC): the same passes as straight-line code
+  std::string jit_src;
+  void *jit_module = nullptr;           // CUmodule
+  void *jit_func = nullptr;             // CUfunction
+  int jit_state = 0;                    // 0 not tried, 1 ready, -1 unavailable (interpreter is used)
+  int jit_blocks_per_sm = 0;
 };
 
 }  // namespace
@@ -396,34 +356,332 @@ struct b2o_graph_s {
   std::string err;
 };
 
+static int slot_of(std::vector<int> &slots, int id, std::string &err) {
+  for (size_t i = 0; i < slots.size(); ++i)
+    if (slots[i] == id) return (int)i;
+  if ((int)slots.size() >= G_SLOTS) { err = "too many distinct vectors in one pass"; return -1; }
+  slots.push_back(id);
+  return (int)slots.size() - 1;
+}
+static inline int op3(int op) { return op == I_ADD ? 0 : op == I_SUB ? 1 : 2; }
+
+// post-order code generation; binary ops whose right (or, if commutative, left) operand is a leaf fold the operand
+// into the instruction (st op= array / scalar): same arithmetic, fewer dispatches.
 static bool gen_code(Lowering &L, int v, std::vector<uint32_t> &code, int &sp, int &maxsp, std::vector<int> &slots,
                      std::string &err) {
   const VExpr &e = L.V[v];
   if (e.kind == VExpr::BIN) {
-    if (!gen_code(L, e.l, code, sp, maxsp, slots, err)) return false;
-    if (!gen_code(L, e.r, code, sp, maxsp, slots, err)) return false;
-    code.push_back((uint32_t)e.op | ((uint32_t)sp << 8));
+    int lhs = e.l, rhs = e.r;
+    const bool commut = e.op != I_SUB;
+    if (L.V[rhs].kind == VExpr::BIN && L.V[lhs].kind != VExpr::BIN && commut) std::swap(lhs, rhs);  // a+b == b+a, a*b == b*a bitwise
+    if (L.V[rhs].kind != VExpr::BIN) {
+      if (!gen_code(L, lhs, code, sp, maxsp, slots, err)) return false;
+      if (L.V[rhs].kind == VExpr::ARR) {
+        int sl = slot_of(slots, L.V[rhs].id, err);
+        if (sl < 0) return false;
+        code.push_back((uint32_t)(F_BINA + (op3(e.op) * 6 + sl) * 8 + sp));
+      } else {
+        code.push_back((uint32_t)(F_BINS + op3(e.op) * 8 + sp) | ((uint32_t)L.V[rhs].id << 16));
+      }
+      return true;
+    }
+    if (!gen_code(L, lhs, code, sp, maxsp, slots, err)) return false;
+    if (!gen_code(L, rhs, code, sp, maxsp, slots, err)) return false;
+    code.push_back((uint32_t)(F_BIN + op3(e.op) * 8 + sp));
     sp -= 1;
     return true;
   }
   if (sp >= G_DEPTH) { err = "expression too deep for the fused evaluator"; return false; }
   if (e.kind == VExpr::ARR) {
-    int slot = -1;
-    for (size_t i = 0; i < slots.size(); ++i)
-      if (slots[i] == e.id) slot = (int)i;
-    if (slot < 0) {
-      if ((int)slots.size() >= G_SLOTS) { err = "too many distinct vectors in one pass"; return false; }
-      slots.push_back(e.id);
-      slot = (int)slots.size() - 1;
-    }
-    code.push_back((uint32_t)I_PUSH_ARR | ((uint32_t)sp << 8) | ((uint32_t)slot << 16));
+    int sl = slot_of(slots, e.id, err);
+    if (sl < 0) return false;
+    code.push_back((uint32_t)(F_PUSHA + sl * 8 + sp));
   } else {
-    code.push_back((uint32_t)I_PUSH_SCAL | ((uint32_t)sp << 8) | ((uint32_t)e.id << 16));
+    code.push_back((uint32_t)(F_PUSHS + sp) | ((uint32_t)e.id << 16));
   }
   sp += 1;
   maxsp = std::max(maxsp, sp);
   return true;
 }
+
+
+// ====================================================================================== specialised instantiation via NVRTC
+// The interpreter above pays one dispatch per op per tile.  For a STATIC tree the passes are known when the graph is
+// compiled, so the same hand-written pass template (vector loads, masked reductions, deterministic grid barrier) is
+// instantiated with the per-row expressions written out as straight-line __dmul_rn/__dadd_rn/__dsub_rn calls and
+// compiled for sm_100a with NVRTC.  No NVRTC / driver -> the interpreter kernel remains the (all-CUDA) path.
+#include <dlfcn.h>
+#include <sstream>
+namespace {
+
+struct JitRT {          // must match `struct RT` in the generated source
+  const double *arr[G_MAX_ARR];
+  double *out;
+  long long n;
+  double scal[G_MAX_SCAL];
+  double *partials;
+  double *dots;
+  unsigned long long *bar;
+  unsigned long long bar_target;
+  unsigned long long *arrive;
+  int pass_begin, pass_end, fused, vec;
+};
+
+struct JitApi {
+  bool tried = false, ok = false;
+  // nvrtc
+  int (*CreateProgram)(void **, const char *, const char *, int, const char *const *, const char *const *) = nullptr;
+  int (*CompileProgram)(void *, int, const char *const *) = nullptr;
+  int (*GetCUBINSize)(void *, size_t *) = nullptr;
+  int (*GetCUBIN)(void *, char *) = nullptr;
+  int (*GetProgramLogSize)(void *, size_t *) = nullptr;
+  int (*GetProgramLog)(void *, char *) = nullptr;
+  int (*DestroyProgram)(void **) = nullptr;
+  // driver
+  int (*ModuleLoadData)(void **, const void *) = nullptr;
+  int (*ModuleGetFunction)(void **, void *, const char *) = nullptr;
+  int (*ModuleUnload)(void *) = nullptr;
+  int (*LaunchCooperativeKernel)(void *, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void *, void **) = nullptr;
+  int (*LaunchKernel)(void *, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void *, void **, void **) = nullptr;
+  int (*OccupancyMaxActiveBlocksPerMultiprocessor)(int *, void *, int, size_t) = nullptr;
+  bool have_nvrtc = false, have_driver = false;
+};
+static JitApi g_jit;
+
+static void jit_load_api() {
+  if (g_jit.tried) return;
+  g_jit.tried = true;
+  void *n = dlopen("libnvrtc.so.12", RTLD_NOW);
+  if (!n) n = dlopen("libnvrtc.so", RTLD_NOW);
+  if (n) {
+    *(void **)&g_jit.CreateProgram = dlsym(n, "nvrtcCreateProgram");
+    *(void **)&g_jit.CompileProgram = dlsym(n, "nvrtcCompileProgram");
+    *(void **)&g_jit.GetCUBINSize = dlsym(n, "nvrtcGetCUBINSize");
+    *(void **)&g_jit.GetCUBIN = dlsym(n, "nvrtcGetCUBIN");
+    *(void **)&g_jit.GetProgramLogSize = dlsym(n, "nvrtcGetProgramLogSize");
+    *(void **)&g_jit.GetProgramLog = dlsym(n, "nvrtcGetProgramLog");
+    *(void **)&g_jit.DestroyProgram = dlsym(n, "nvrtcDestroyProgram");
+    g_jit.have_nvrtc = g_jit.CreateProgram && g_jit.CompileProgram && g_jit.GetCUBINSize && g_jit.GetCUBIN && g_jit.DestroyProgram;
+  }
+  void *d = dlopen("libcuda.so.1", RTLD_NOW);
+  if (d) {
+    *(void **)&g_jit.ModuleLoadData = dlsym(d, "cuModuleLoadData");
+    *(void **)&g_jit.ModuleGetFunction = dlsym(d, "cuModuleGetFunction");
+    *(void **)&g_jit.ModuleUnload = dlsym(d, "cuModuleUnload");
+    *(void **)&g_jit.LaunchCooperativeKernel = dlsym(d, "cuLaunchCooperativeKernel");
+    *(void **)&g_jit.LaunchKernel = dlsym(d, "cuLaunchKernel");
+    *(void **)&g_jit.OccupancyMaxActiveBlocksPerMultiprocessor = dlsym(d, "cuOccupancyMaxActiveBlocksPerMultiprocessor");
+    g_jit.have_driver = g_jit.ModuleLoadData && g_jit.ModuleGetFunction && g_jit.LaunchCooperativeKernel && g_jit.LaunchKernel &&
+                        g_jit.OccupancyMaxActiveBlocksPerMultiprocessor;
+  }
+  g_jit.ok = g_jit.have_nvrtc && g_jit.have_driver;
+}
+
+static void emit_expr(const Lowering &L, int v, const std::vector<int> &slots, std::ostringstream &o) {
+  const VExpr &e = L.V[v];
+  if (e.kind == VExpr::ARR) {
+    int sl = 0;
+    for (size_t i = 0; i < slots.size(); ++i)
+      if (slots[i] == e.id) sl = (int)i;
+    o << "a" << sl;
+  } else if (e.kind == VExpr::SCAL) {
+    o << "S[" << e.id << "]";
+  } else {
+    o << (e.op == I_ADD ? "__dadd_rn(" : e.op == I_SUB ? "__dsub_rn(" : "__dmul_rn(");
+    emit_expr(L, e.l, slots, o);
+    o << ", ";
+    emit_expr(L, e.r, slots, o);
+    o << ")";
+  }
+}
+static void collect_slots(const Lowering &L, int v, std::vector<int> &slots) {
+  const VExpr &e = L.V[v];
+  if (e.kind == VExpr::ARR) {
+    for (int s : slots)
+      if (s == e.id) return;
+    slots.push_back(e.id);
+  } else if (e.kind == VExpr::BIN) {
+    collect_slots(L, e.l, slots);
+    collect_slots(L, e.r, slots);
+  }
+}
+
+static const char *kJitPrologue = R"SRC(
+typedef unsigned long long u64;
+struct RT {
+  const double *arr[12]; double *out; long long n; double scal[48];
+  double *partials; double *dots; u64 *bar; u64 bar_target; u64 *arrive;
+  int pass_begin, pass_end, fused, vec;
+};
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ u64 ldacq(const u64 *p) { u64 v; asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void gbar(u64 *ctr, u64 target) {
+  __syncthreads();
+  if (threadIdx.x == 0) { __threadfence(); atomicAdd(ctr, 1ULL); while (ldacq(ctr) < target) { __nanosleep(32); } __threadfence(); }
+  __syncthreads();
+}
+__device__ __forceinline__ void st2(double *p, double x, double y) { asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" :: "l"(p), "d"(x), "d"(y) : "memory"); }
+)SRC";
+
+// emits the CUDA source of the specialised kernel for one compiled variant
+static std::string jit_source(const Lowering &L, const GraphArgs &A, int out_expr) {
+  std::ostringstream o;
+  o << kJitPrologue;
+  const int npass = A.npass;
+  std::vector<std::vector<int>> pass_slots(npass);
+  std::vector<std::vector<int>> pass_reds(npass);
+  for (int p = 0; p < npass; ++p) {
+    for (size_t r = 0; r < L.R.size(); ++r)
+      if (L.R[r].level == p + 1) {
+        pass_reds[p].push_back((int)r);
+        collect_slots(L, L.R[r].expr, pass_slots[p]);
+      }
+    if (p == npass - 1) collect_slots(L, out_expr, pass_slots[p]);
+  }
+  auto params = [&](int p) {
+    std::ostringstream q;
+    for (size_t i = 0; i < pass_slots[p].size(); ++i) q << "double a" << i << ", ";
+    q << "const double *S";
+    return q.str();
+  };
+  auto argsj = [&](int p, const char *suffix) {
+    std::ostringstream q;
+    for (size_t i = 0; i < pass_slots[p].size(); ++i) q << "x" << i << suffix << ", ";
+    q << "S";
+    return q.str();
+  };
+  for (int p = 0; p < npass; ++p) {
+    for (size_t k = 0; k < pass_reds[p].size(); ++k) {
+      o << "__device__ __forceinline__ double f_p" << p << "_r" << k << "(" << params(p) << ") { return ";
+      emit_expr(L, L.R[pass_reds[p][k]].expr, pass_slots[p], o);
+      o << "; }\n";
+    }
+    if (p == npass - 1) {
+      o << "__device__ __forceinline__ double f_out(" << params(p) << ") { return ";
+      emit_expr(L, out_expr, pass_slots[p], o);
+      o << "; }\n";
+    }
+  }
+  o << "extern \"C\" __global__ void __launch_bounds__(256) b2o_fused(const __grid_constant__ RT p) {\n"
+       "  __shared__ double S[48]; __shared__ double R[8]; __shared__ double W[8][4]; __shared__ bool s_last;\n"
+       "  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;\n"
+       "  for (int i = tid; i < 48; i += 256) S[i] = p.scal[i];\n"
+       "  if (p.pass_begin > 0) for (int i = tid; i < 8; i += 256) R[i] = __ldcg(&p.dots[i]);\n"
+       "  __syncthreads();\n"
+       "  u64 bt = p.bar_target;\n"
+       "  const long long npair = p.n >> 1;\n"
+       "  const long long stride = (long long)gridDim.x * 256;\n"
+       "  const long long nit = (npair + stride - 1) / stride;   // grid-stride iterations over 16-byte pairs\n";
+  for (int p = 0; p < npass; ++p) {
+    const int ns = (int)pass_slots[p].size(), nr = (int)pass_reds[p].size();
+    const bool last = p == npass - 1;
+    // scalars that depend on reductions finished before this pass (recomputed when a launch starts at a later pass)
+    o << "  if (tid == 0 && " << p << " < p.pass_end) {\n";
+    for (int i = 0; i < A.nsop[p]; ++i)
+      o << "    S[" << (int)A.sop[p][i][0] << "] = __dmul_rn(S[" << (int)A.sop[p][i][1] << "], R[" << (int)A.sop[p][i][2] << "]);\n";
+    o << "  }\n  __syncthreads();\n";
+    o << "  if (p.pass_begin <= " << p << " && " << p << " < p.pass_end) {\n";
+    for (int i = 0; i < ns; ++i) o << "    const double *A" << i << " = p.arr[" << pass_slots[p][i] << "];\n";
+    for (int k = 0; k < nr; ++k) o << "    double acc" << k << " = 0.0;\n";
+    const bool rev = p & 1;
+    o << "    if (p.vec) {\n"
+         "      for (long long it0 = 0; it0 < nit; it0 += 2) {\n"
+         "        const long long ita = " << (rev ? "nit - 1 - it0" : "it0") << ", itb = " << (rev ? "nit - 2 - it0" : "it0 + 1") << ";\n"
+         "        const long long ea = ita * stride + (long long)blockIdx.x * 256 + tid;\n"
+         "        const long long eb = itb * stride + (long long)blockIdx.x * 256 + tid;\n"
+         "        const bool va = ea < npair, vb = " << (rev ? "itb >= 0" : "itb < nit") << " && eb < npair;\n";
+    for (int i = 0; i < ns; ++i)
+      o << "        double2 u" << i << "a = make_double2(0.0, 0.0), u" << i << "b = make_double2(0.0, 0.0);\n";
+    for (int i = 0; i < ns; ++i) o << "        if (va) u" << i << "a = *reinterpret_cast<const double2 *>(A" << i << " + 2 * ea);\n";
+    for (int i = 0; i < ns; ++i) o << "        if (vb) u" << i << "b = *reinterpret_cast<const double2 *>(A" << i << " + 2 * eb);\n";
+    for (const char *h : {"a", "b"}) {
+      o << "        if (v" << h << ") {\n";
+      for (int i = 0; i < ns; ++i) o << "          const double x" << i << "0 = u" << i << h << ".x, x" << i << "1 = u" << i << h << ".y;\n";
+      for (int k = 0; k < nr; ++k)
+        o << "          acc" << k << " += f_p" << p << "_r" << k << "(" << argsj(p, "0") << ") + f_p" << p << "_r" << k << "(" << argsj(p, "1") << ");\n";
+      if (last) o << "          st2(p.out + 2 * e" << h << ", f_out(" << argsj(p, "0") << "), f_out(" << argsj(p, "1") << "));\n";
+      o << "        }\n";
+    }
+    o << "      }\n"
+         "      if ((p.n & 1) && blockIdx.x == 0 && tid == 0) {\n"
+         "        const long long r = p.n - 1;\n";
+    for (int i = 0; i < ns; ++i) o << "        const double x" << i << "0 = A" << i << "[r];\n";
+    for (int k = 0; k < nr; ++k) o << "        acc" << k << " += f_p" << p << "_r" << k << "(" << argsj(p, "0") << ");\n";
+    if (last) o << "        p.out[r] = f_out(" << argsj(p, "0") << ");\n";
+    o << "      }\n"
+         "    } else {\n"
+         "      for (long long r = (long long)blockIdx.x * 256 + tid; r < p.n; r += stride) {\n";
+    for (int i = 0; i < ns; ++i) o << "        const double x" << i << "0 = A" << i << "[r];\n";
+    for (int k = 0; k < nr; ++k) o << "        acc" << k << " += f_p" << p << "_r" << k << "(" << argsj(p, "0") << ");\n";
+    if (last) o << "        p.out[r] = f_out(" << argsj(p, "0") << ");\n";
+    o << "      }\n    }\n";
+    if (nr > 0) {
+      for (int k = 0; k < nr; ++k) o << "    { double s = wsum(acc" << k << "); if (lane == 0) W[warp][" << k << "] = s; }\n";
+      o << "    __syncthreads();\n"
+           "    if (tid < " << nr << ") { double s = 0.0; for (int w = 0; w < 8; ++w) s += W[w][tid]; p.partials[(size_t)blockIdx.x * 4 + tid] = s; }\n"
+           "    if (p.fused) {\n"
+           "      gbar(p.bar, bt); bt += gridDim.x;\n"
+           "      if (warp < " << nr << ") {\n"
+           "        double s = 0.0; for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(&p.partials[(size_t)b * 4 + warp]);\n"
+           "        s = wsum(s);\n"
+           "        if (lane == 0) { const int ids[4] = {";
+      for (int k = 0; k < 4; ++k) o << (k < nr ? pass_reds[p][k] : 0) << (k < 3 ? ", " : "");
+      o << "}; R[ids[warp]] = s; }\n"
+           "      }\n"
+           "      __syncthreads();\n"
+           "    } else {\n"
+           "      __threadfence(); __syncthreads();\n"
+           "      if (tid == 0) { u64 tk = atomicAdd(p.arrive, 1ULL); s_last = (tk == gridDim.x - 1); }\n"
+           "      __syncthreads();\n"
+           "      if (s_last) {\n"
+           "        __threadfence();\n"
+           "        if (warp < " << nr << ") {\n"
+           "          double s = 0.0; for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(&p.partials[(size_t)b * 4 + warp]);\n"
+           "          s = wsum(s);\n"
+           "          if (lane == 0) { const int ids[4] = {";
+      for (int k = 0; k < 4; ++k) o << (k < nr ? pass_reds[p][k] : 0) << (k < 3 ? ", " : "");
+      o << "}; p.dots[ids[warp]] = s; }\n"
+           "        }\n"
+           "        if (tid == 0) *p.arrive = 0ULL;\n"
+           "      }\n"
+           "    }\n";
+    }
+    o << "  }\n";
+  }
+  o << "}\n";
+  return o.str();
+}
+
+// NVRTC: source -> sm_100a cubin.  Usable on a CPU-only box (this is what tests/test_abi.py checks).
+static int jit_compile_cubin(const std::string &src, std::vector<char> &cubin, std::string &log) {
+  jit_load_api();
+  if (!g_jit.have_nvrtc) { log = "libnvrtc not available"; return -1; }
+  void *prog = nullptr;
+  if (g_jit.CreateProgram(&prog, src.c_str(), "b2o_fused.cu", 0, nullptr, nullptr) != 0) { log = "nvrtcCreateProgram failed"; return -1; }
+  const char *opts[] = {"--gpu-architecture=sm_100a", "--fmad=false", "-lineinfo", "--std=c++17"};
+  int rc = g_jit.CompileProgram(prog, 4, opts);
+  if (rc != 0) {
+    size_t ls = 0;
+    if (g_jit.GetProgramLogSize && g_jit.GetProgramLogSize(prog, &ls) == 0 && ls > 1) {
+      log.resize(ls);
+      g_jit.GetProgramLog(prog, &log[0]);
+    }
+    g_jit.DestroyProgram(&prog);
+    return -1;
+  }
+  size_t cs = 0;
+  g_jit.GetCUBINSize(prog, &cs);
+  cubin.resize(cs);
+  g_jit.GetCUBIN(prog, cubin.data());
+  g_jit.DestroyProgram(&prog);
+  return 0;
+}
+
+}  // namespace
 
 static int compile_variant(b2o_graph *g, bool tr, bool beta_nz, Compiled &C) {
   Lowering L;
@@ -456,14 +714,14 @@ static int compile_variant(b2o_graph *g, bool tr, bool beta_nz, Compiled &C) {
       if (nlocal >= G_RED_PER_PASS) B2O_FAIL(B2O_EUNSUPPORTED, "graph: too many reductions in one pass");
       int sp = 0, maxsp = 0;
       if (!gen_code(L, L.R[r].expr, code, sp, maxsp, slots, err)) B2O_FAIL(B2O_EUNSUPPORTED, "graph: %s", err.c_str());
-      code.push_back((uint32_t)I_RED | (1u << 8) | ((uint32_t)nlocal << 16));
+      code.push_back((uint32_t)(F_RED + 1) | ((uint32_t)nlocal << 16));
       A.red_of_pass[pass][nlocal++] = (unsigned char)r;
     }
     A.nred_pass[pass] = nlocal;
     if (pass == npass - 1) {
       int sp = 0, maxsp = 0;
       if (!gen_code(L, out, code, sp, maxsp, slots, err)) B2O_FAIL(B2O_EUNSUPPORTED, "graph: %s", err.c_str());
-      code.push_back((uint32_t)I_STORE | (1u << 8));
+      code.push_back((uint32_t)(F_STORE + 1));
     }
     if ((int)code.size() > G_MAX_PROG) B2O_FAIL(B2O_EUNSUPPORTED, "graph: program too long (%zu)", code.size());
     A.prog_len[pass] = (int)code.size();
@@ -493,12 +751,15 @@ static int compile_variant(b2o_graph *g, bool tr, bool beta_nz, Compiled &C) {
     A.arr_al16[i] = ((uintptr_t)L.arrays[i] % 16) == 0;
   }
   C.S = L.S;
+  C.jit_src = jit_source(L, A, out);
+  C.jit_state = 0;
   C.valid = true;
   return B2O_OK;
 }
 
 extern "C" int b2o_graph_create(b2o_ctx *ctx, int64_t n, b2o_graph **out) {
-  if (!ctx || !out) B2O_FAIL(B2O_EARG, "null argument");
+  // ctx may be NULL: a "dry" graph can be built, lowered and NVRTC-compiled on a CPU-only box, but not applied
+  if (!out) B2O_FAIL(B2O_EARG, "null argument");
   if (n < 0) B2O_FAIL(B2O_EARG, "negative size");
   b2o_graph *g = new b2o_graph_s();
   g->ctx = ctx;
@@ -507,7 +768,70 @@ extern "C" int b2o_graph_create(b2o_ctx *ctx, int64_t n, b2o_graph **out) {
   return B2O_OK;
 }
 extern "C" int b2o_graph_destroy(b2o_graph *g) {
+  if (!g) return B2O_OK;
+  for (int tr = 0; tr < 2; ++tr)
+    for (int bz = 0; bz < 2; ++bz)
+      if (g->prog[tr][bz].jit_module && g_jit.ModuleUnload) g_jit.ModuleUnload(g->prog[tr][bz].jit_module);
   delete g;
+  return B2O_OK;
+}
+
+// generated CUDA source of one variant (for inspection / tests); returns the length, copies at most cap-1 bytes
+extern "C" int b2o_graph_jit_source(b2o_graph *g, int transposed, double beta, char *buf, int64_t cap, int64_t *len) {
+  if (!g || g->root < 0) B2O_FAIL(B2O_EARG, "graph not compiled");
+  const Compiled &C = g->prog[transposed ? 1 : 0][beta != 0.0];
+  if (len) *len = (int64_t)C.jit_src.size();
+  if (buf && cap > 0) {
+    size_t k = std::min<size_t>((size_t)cap - 1, C.jit_src.size());
+    memcpy(buf, C.jit_src.data(), k);
+    buf[k] = 0;
+  }
+  return B2O_OK;
+}
+// NVRTC-compile every variant for sm_100a (works without a GPU); B2O_EUNSUPPORTED when NVRTC is absent
+extern "C" int b2o_graph_jit_check(b2o_graph *g, int64_t *cubin_bytes) {
+  if (!g || g->root < 0) B2O_FAIL(B2O_EARG, "graph not compiled");
+  int64_t total = 0;
+  for (int tr = 0; tr < 2; ++tr)
+    for (int bz = 0; bz < 2; ++bz) {
+      std::vector<char> cubin;
+      std::string log;
+      if (jit_compile_cubin(g->prog[tr][bz].jit_src, cubin, log) != 0) {
+        if (!g_jit.have_nvrtc) B2O_FAIL(B2O_EUNSUPPORTED, "NVRTC not available");
+        B2O_FAIL(B2O_ECUDA, "NVRTC compilation failed: %s", log.c_str());
+      }
+      total += (int64_t)cubin.size();
+    }
+  if (cubin_bytes) *cubin_bytes = total;
+  return B2O_OK;
+}
+
+static int ensure_jit(b2o_ctx *c, Compiled &C) {
+  if (C.jit_state != 0) return C.jit_state;
+  C.jit_state = -1;
+  jit_load_api();
+  if (!g_jit.ok) return -1;
+  std::vector<char> cubin;
+  std::string log;
+  if (jit_compile_cubin(C.jit_src, cubin, log) != 0) return -1;
+  cudaFree(0);  // make sure the runtime's primary context is current for the driver calls
+  void *mod = nullptr, *fn = nullptr;
+  if (g_jit.ModuleLoadData(&mod, cubin.data()) != 0) return -1;
+  if (g_jit.ModuleGetFunction(&fn, mod, "b2o_fused") != 0) return -1;
+  int nb = 0;
+  if (g_jit.OccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, 256, 0) != 0 || nb < 1) return -1;
+  C.jit_module = mod;
+  C.jit_func = fn;
+  C.jit_blocks_per_sm = nb;
+  (void)c;
+  C.jit_state = 1;
+  return 1;
+}
+
+// 1 when the last apply of this variant ran the NVRTC-specialised kernel, 0 for the interpreter
+extern "C" int b2o_graph_uses_jit(b2o_graph *g, int transposed, double beta, int *out) {
+  if (!g || g->root < 0 || !out) B2O_FAIL(B2O_EARG, "graph not compiled");
+  *out = g->prog[transposed ? 1 : 0][beta != 0.0].jit_state == 1;
   return B2O_OK;
 }
 extern "C" int b2o_graph_leaf(b2o_graph *g, int kind, const void *ptr, int *node) {
@@ -575,8 +899,63 @@ extern "C" int b2o_graph_apply(b2o_graph *g, int transposed, void *res, int64_t 
   if (!res || !v) B2O_FAIL(B2O_EARG, "null vector");
   if (((uintptr_t)res | (uintptr_t)v) % 8) B2O_FAIL(B2O_EARG, "vectors must be 8-byte aligned");
   b2o_ctx *c = g->ctx;
+  if (!c) B2O_FAIL(B2O_EARG, "graph was created without a context (dry graph)");
   B2O_CUDA(cudaSetDevice(c->device));
   Compiled &C = g->prog[transposed ? 1 : 0][beta != 0.0];
+  if (c->graph_jit && ensure_jit(c, C) == 1) {
+    JitRT R;
+    memset(&R, 0, sizeof(R));
+    for (int i = 2; i < G_MAX_ARR; ++i) R.arr[i] = C.args.arr[i];
+    R.arr[0] = (const double *)v;
+    R.arr[1] = (const double *)res;
+    R.out = (double *)res;
+    R.n = g->n;
+    for (size_t sidx = 0; sidx < C.S.size(); ++sidx) R.scal[sidx] = eval_scalar(C.S, (int)sidx, alpha, beta);
+    R.partials = c->d_partials;
+    R.dots = c->d_dots + 400;
+    R.bar = c->d_bar;
+    R.arrive = c->d_bar + 1;
+    bool vec = (((uintptr_t)v | (uintptr_t)res) % 16) == 0;
+    for (int i = 2; i < G_MAX_ARR; ++i) vec = vec && (((uintptr_t)C.args.arr[i]) % 16 == 0);
+    R.vec = vec ? 1 : 0;
+    const int64_t units = (vec ? (g->n >> 1) : g->n);
+    const int64_t want = (units + 2 * 256 - 1) / (2 * 256);
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->num_sms * C.jit_blocks_per_sm));
+    grid = std::min(grid, B2O_MAX_GRID);
+    int nbar = 0;
+    for (int p = 0; p < C.args.npass; ++p) nbar += C.args.nred_pass[p] > 0;
+    void *params[] = {(void *)&R};
+    if (c->time_kernels) B2O_CUDA(cudaEventRecord(c->ev0, c->stream));
+    if (c->nranks <= 1) {
+      R.pass_begin = 0;
+      R.pass_end = C.args.npass;
+      R.fused = 1;
+      R.bar_target = c->bar_base + (unsigned long long)grid;
+      int rc = g_jit.LaunchCooperativeKernel(C.jit_func, grid, 1, 1, 256, 1, 1, 0, (void *)c->stream, params);
+      if (rc != 0) B2O_FAIL(B2O_ECUDA, "cuLaunchCooperativeKernel failed (%d)", rc);
+      c->bar_base += (unsigned long long)grid * nbar;
+      c->launches++;
+    } else {
+      for (int p = 0; p < C.args.npass; ++p) {
+        R.pass_begin = p;
+        R.pass_end = p + 1;
+        R.fused = 0;
+        int rc = g_jit.LaunchKernel(C.jit_func, grid, 1, 1, 256, 1, 1, 0, (void *)c->stream, params, nullptr);
+        if (rc != 0) B2O_FAIL(B2O_ECUDA, "cuLaunchKernel failed (%d)", rc);
+        c->launches++;
+        for (int r = 0; r < C.args.nred_pass[p]; ++r) B2O_TRY(b2o_allreduce_sum_f64(c, R.dots + C.args.red_of_pass[p][r], 1));
+      }
+    }
+    if (c->time_kernels) {
+      B2O_CUDA(cudaEventRecord(c->ev1, c->stream));
+      B2O_CUDA(cudaEventSynchronize(c->ev1));
+      float ms = 0.f;
+      B2O_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+      c->kern_ms += ms;
+      c->kern_n++;
+    }
+    return B2O_OK;
+  }
   GraphArgs A = C.args;
   A.arr[0] = (const double *)v;
   A.arr_al16[0] = ((uintptr_t)v % 16) == 0;
@@ -590,8 +969,8 @@ extern "C" int b2o_graph_apply(b2o_graph *g, int transposed, void *res, int64_t 
   A.dots = c->d_dots + 400;
   A.bar = c->d_bar;
   A.arrive = c->d_bar + 1;
-  const bool two = c->graph_blocks == 2;
-  const void *kern = two ? (const void *)graph_kernel<2> : (const void *)graph_kernel<1>;
+  const void *kern = c->graph_blocks >= 4 ? (const void *)graph_kernel<4> : c->graph_blocks == 3 ? (const void *)graph_kernel<3> :
+                     c->graph_blocks == 2 ? (const void *)graph_kernel<2> : (const void *)graph_kernel<1>;
   int blocks_per_sm = 0;
   B2O_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, G_NT, 0));
   if (blocks_per_sm < 1) blocks_per_sm = 1;

@@ -57,7 +57,8 @@ struct b2o_ctx_s {
   int tile_rows = 2048;
   int stages = 0;        // 0 -> as many as shared memory allows
   int grid = 0;          // 0 -> one CTA per SM
-  int graph_blocks = 1;  // CTAs per SM of the fused-graph kernel (1: no spills, 2: more warps)
+  int graph_jit = 1;     // fused trees: use the NVRTC-specialised kernel when NVRTC + driver are present (else the interpreter)
+  int graph_blocks = 3;  // resident CTAs per SM the fused-graph kernel is compiled for (occupancy hides the dispatch latency)
   // accounting
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

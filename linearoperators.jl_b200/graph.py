@@ -72,7 +72,16 @@ class FusedOperator(LinearOperator):
         np_, nr, by = ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
         _lib.check(self.ctx.lib.b2o_graph_info(self._graph.h, int(transposed), float(beta), ctypes.byref(np_), ctypes.byref(nr),
                                                ctypes.byref(by)))
-        return {"passes": np_.value, "reductions": nr.value, "alg_bytes": by.value}
+        j = ctypes.c_int()
+        _lib.check(self.ctx.lib.b2o_graph_uses_jit(self._graph.h, int(transposed), float(beta), ctypes.byref(j)))
+        return {"passes": np_.value, "reductions": nr.value, "alg_bytes": by.value, "jit": bool(j.value)}
+
+    def source(self, transposed=False, beta=0.0):
+        """CUDA source of the NVRTC-specialised kernel for this variant"""
+        n = ctypes.c_int64()
+        buf = ctypes.create_string_buffer(1 << 18)
+        _lib.check(self.ctx.lib.b2o_graph_jit_source(self._graph.h, int(transposed), float(beta), buf, 1 << 18, ctypes.byref(n)))
+        return buf.value.decode()
 
 
 def fuse(op, ctx=None):

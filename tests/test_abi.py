@@ -55,3 +55,41 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "b2o_oracle" not in txt, f
+
+
+def test_fused_graph_lowering_and_nvrtc_on_cpu(lo):
+    """A dry graph (no context) can be lowered and its specialised kernel NVRTC-compiled for sm_100a without a GPU."""
+    from linearoperators_jl_b200 import _lib
+    lib = _lib.load()
+    g, node = ctypes.c_void_p(), ctypes.c_int()
+    _lib.check(lib.b2o_graph_create(None, 12345, ctypes.byref(g)))
+
+    def leaf(kind, ptr=None):
+        _lib.check(lib.b2o_graph_leaf(g, kind, ptr, ctypes.byref(node)))
+        return node.value
+
+    H, D, E = leaf(4, ctypes.c_void_p(0x1000)), leaf(0, ctypes.c_void_p(0x2000)), leaf(1)
+    _lib.check(lib.b2o_graph_binary(g, 11, H, D, ctypes.byref(node)))
+    P = node.value
+    _lib.check(lib.b2o_graph_unary(g, 12, E, 0.1, ctypes.byref(node)))
+    S = node.value
+    _lib.check(lib.b2o_graph_binary(g, 10, P, S, ctypes.byref(node)))
+    _lib.check(lib.b2o_graph_compile(g, node.value))
+    npass, nred, nbytes = ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
+    _lib.check(lib.b2o_graph_info(g, 0, 0.0, ctypes.byref(npass), ctypes.byref(nred), ctypes.byref(nbytes)))
+    assert (npass.value, nred.value, nbytes.value) == (2, 1, 7 * 8 * 12345)          # cfg3: 2 passes, 7n*8 bytes
+    _lib.check(lib.b2o_graph_info(g, 1, 0.5, ctypes.byref(npass), ctypes.byref(nred), ctypes.byref(nbytes)))
+    assert (npass.value, nred.value, nbytes.value) == (2, 1, 8 * 8 * 12345)          # + res read when beta != 0
+    buf, n = ctypes.create_string_buffer(1 << 16), ctypes.c_int64()
+    _lib.check(lib.b2o_graph_jit_source(g, 0, 0.0, buf, 1 << 16, ctypes.byref(n)))
+    src = buf.value.decode()
+    assert "__dmul_rn(a0, __dmul_rn(a1, a2))" in src and "b2o_fused" in src          # dot(h, d .* v), no fma contraction
+    cb = ctypes.c_int64()
+    st = lib.b2o_graph_jit_check(g, ctypes.byref(cb))
+    if st == _lib.B2O_EUNSUPPORTED:
+        pytest.skip("NVRTC not installed")
+    assert st == 0, lib.b2o_last_error()
+    assert cb.value > 1000
+    res = ctypes.c_void_p(0x3000)
+    assert lib.b2o_graph_apply(g, 0, res, 12345, res, 12345, 1.0, 0.0) == _lib.B2O_EARG   # dry graphs cannot be applied
+    lib.b2o_graph_destroy(g)

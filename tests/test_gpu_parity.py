@@ -538,8 +538,15 @@ def _mk_vecs(ctx, n):
     return h1, h2, ctx.uniform(n, 4, 0.5, 1.5), ctx.uniform(n, 14, -1.0, 1.0), ctx.uniform(n, 5), ctx.uniform(n, 6)
 
 
+@pytest.fixture(params=["jit", "interpreter"])
+def graph_mode(request, ctx):
+    ctx.set_option("graph_jit", 1 if request.param == "jit" else 0)
+    yield request.param
+    ctx.set_option("graph_jit", 1)
+
+
 @pytest.mark.parametrize("n", [7, 1000, 1024 * 148 * 2 + 13])
-def test_fused_cfg3_chain(lo, ctx, orc, n):
+def test_fused_cfg3_chain(lo, ctx, orc, n, graph_mode):
     """(opHouseholder(h)*opDiagonal(d) + 0.1*opEye(n)) * v in ONE launch == closure tree == oracle"""
     h1, _, d, _, v, r0 = _mk_vecs(ctx, n)
     tree = lo.opHouseholder(h1) * lo.opDiagonal(d) + 0.1 * lo.opEye(n)
@@ -552,6 +559,7 @@ def test_fused_cfg3_chain(lo, ctx, orc, n):
     assert ctx.launch_count() - l0 == 1
     assert rel(host(out), ref_op(host(v))) <= TOL
     assert rel(host(out), host(tree * v)) <= TOL
+    assert fused.info()["jit"] == (graph_mode == "jit")      # the NVRTC-specialised kernel is the one that ran
     for alpha, beta in [(-1.5, 0.75), (2.0, 1.0)]:
         res, ref = r0.clone(), host(r0).copy()
         lo.mul_(res, fused, v, alpha, beta)
@@ -563,7 +571,7 @@ def test_fused_cfg3_chain(lo, ctx, orc, n):
     assert np.isfinite(host(res)).all()
 
 
-def test_fused_trees_vs_oracle(lo, ctx, orc):
+def test_fused_trees_vs_oracle(lo, ctx, orc, graph_mode):
     n = 50001
     h1, h2, d1, d2, v, r0 = _mk_vecs(ctx, n)
     H1, H2, D1, D2, E, O, Z = (lo.opHouseholder(h1), lo.opHouseholder(h2), lo.opDiagonal(d1), lo.opDiagonal(d2), lo.opEye(n),
@@ -594,6 +602,12 @@ def test_fused_trees_vs_oracle(lo, ctx, orc):
             lo.mul_(rt, lo.transpose(fused), v, alpha, beta)
             ref_op.tmul(reft, host(v), alpha, beta)
             assert rel(host(rt), reft) <= TOL
+    xb, rb = ctx.uniform(n + 1, 21), ctx.uniform(n + 1, 22)                     # 8-byte-aligned views: scalar path
+    fused = lo.fuse(H1 * D1 + D2)
+    res, ref = rb[1:], host(rb[1:]).copy()
+    lo.mul_(res, fused, xb[1:], 1.25, -0.5)
+    (oH1 * oD1 + oD2).mul(ref, host(xb[1:]), 1.25, -0.5)
+    assert rel(host(res), ref) <= TOL
     assert lo.fuse(H1 * H2).info()["passes"] == 3
     assert lo.fuse(H1 - H2).info()["passes"] == 2
 

@@ -50,9 +50,27 @@ def line(name, ms, alg_bytes, **kw):
 
 def main():
     ctx = lo.default_context(0)
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]
     big = "--small" not in sys.argv
     n = 10**8 if big else 10**6
     flush = torch.empty(256 * 2**20 // 8, dtype=torch.float64, device="cuda")
+    if only == ["cfg3"]:
+        v, res = ctx.uniform(n, 2), ctx.empty(n)
+        h = ctx.uniform(n, 3)
+        h /= float(np.sqrt(ctx.dot(h, h)))
+        dd = ctx.uniform(n, 4, 0.5, 1.5)
+        tree = lo.opHouseholder(h) * lo.opDiagonal(dd) + 0.1 * lo.opEye(n)
+        fused = lo.fuse(tree)
+        line("cfg3 closure tree", timeit(lambda: lo.mul_(res, tree, v), 30), 56.0 * n)
+        line("cfg3 fused, ONE launch, NVRTC-specialised", timeit(lambda: lo.mul_(res, fused, v), 50), 56.0 * n, jit=fused.info()["jit"])
+        line("cfg3 fused 5-arg beta=0.5, NVRTC-specialised", timeit(lambda: lo.mul_(res, fused, v, 2.0, 0.5), 50), 64.0 * n)
+        line("cfg3 fused transpose, NVRTC-specialised", timeit(lambda: lo.mul_(res, lo.transpose(fused), v), 50), 56.0 * n)
+        ctx.set_option("graph_jit", 0)
+        for gb in (2, 3):
+            ctx.set_option("graph_blocks", gb)
+            line("cfg3 fused, ONE launch (graph_blocks=%d)" % gb, timeit(lambda: lo.mul_(res, fused, v), 30), 56.0 * n)
+            line("cfg3 fused 5-arg beta=0.5 (graph_blocks=%d)" % gb, timeit(lambda: lo.mul_(res, fused, v, 2.0, 0.5), 30), 64.0 * n)
+        return
     # cfg1: opDiagonal(n=1e6) * v  (24 MB: L2 resident unless flushed)
     n1 = 10**6
     d, v, res = ctx.uniform(n1, 1), ctx.uniform(n1, 2), ctx.empty(n1)
@@ -80,10 +98,11 @@ def main():
     tree_launches = ctx.launch_count() - l0
     line("cfg3 (opHouseholder*opDiagonal + 0.1*opEye)*v, closure tree", timeit(lambda: lo.mul_(res, tree, v), 30), 56.0 * n,
          launches_per_apply=tree_launches, reference_traffic_bytes=88.0 * n)
-    for gb in (1, 2):
-        ctx.set_option("graph_blocks", gb)
-        line("cfg3 fused, ONE launch (graph_blocks=%d)" % gb, timeit(lambda: lo.mul_(res, fused, v), 30), 56.0 * n, launches_per_apply=1)
-    ctx.set_option("graph_blocks", 1)
+    line("cfg3 fused, ONE launch, NVRTC-specialised", timeit(lambda: lo.mul_(res, fused, v), 30), 56.0 * n, launches_per_apply=1,
+         jit=fused.info()["jit"])
+    ctx.set_option("graph_jit", 0)
+    line("cfg3 fused, ONE launch, interpreter kernel", timeit(lambda: lo.mul_(res, fused, v), 30), 56.0 * n, launches_per_apply=1)
+    ctx.set_option("graph_jit", 1)
     del tree, fused, H, dd, h
     # gather / scatter
     k = n // 4
