@@ -78,8 +78,10 @@ def test_fused_graph_lowering_and_nvrtc_on_cpu(lo):
     npass, nred, nbytes = ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
     _lib.check(lib.b2o_graph_info(g, 0, 0.0, ctypes.byref(npass), ctypes.byref(nred), ctypes.byref(nbytes)))
     assert (npass.value, nred.value, nbytes.value) == (2, 1, 7 * 8 * 12345)          # cfg3: 2 passes, 7n*8 bytes
-    _lib.check(lib.b2o_graph_info(g, 1, 0.5, ctypes.byref(npass), ctypes.byref(nred), ctypes.byref(nbytes)))
+    _lib.check(lib.b2o_graph_info(g, 0, 0.5, ctypes.byref(npass), ctypes.byref(nred), ctypes.byref(nbytes)))
     assert (npass.value, nred.value, nbytes.value) == (2, 1, 8 * 8 * 12345)          # + res read when beta != 0
+    _lib.check(lib.b2o_graph_info(g, 1, 0.0, ctypes.byref(npass), ctypes.byref(nred), ctypes.byref(nbytes)))
+    assert (npass.value, nred.value, nbytes.value) == (2, 1, 6 * 8 * 12345)          # transpose = D*H: the dot reads h, v only
     buf, n = ctypes.create_string_buffer(1 << 16), ctypes.c_int64()
     _lib.check(lib.b2o_graph_jit_source(g, 0, 0.0, buf, 1 << 16, ctypes.byref(n)))
     src = buf.value.decode()
