@@ -51,6 +51,7 @@ typedef enum { B2O_F64 = 0, B2O_F32 = 1, B2O_BF16 = 2 } b2o_dtype;
 typedef struct b2o_ctx_s b2o_ctx;
 typedef struct b2o_qn_s b2o_qn;       /* LBFGSOperator / InverseLBFGSOperator / LSR1Operator state */
 typedef struct b2o_index_s b2o_index; /* opRestriction / opExtension index set */
+typedef struct b2o_kron_s b2o_kron;   /* kron(A,B) operator (tcgen05 GEMM pair) */
 typedef struct b2o_graph_s b2o_graph; /* static operator tree lowered to one fused launch */
 
 /* ---- library / context ------------------------------------------------------------------ */
@@ -166,6 +167,21 @@ int b2o_graph_jit_check(b2o_graph *g, int64_t *cubin_bytes);
 int b2o_graph_uses_jit(b2o_graph *g, int transposed, double beta, int *out);
 /* passes, reductions and algorithmic DRAM bytes of one apply */
 int b2o_graph_info(b2o_graph *g, int transposed, double beta, int *npasses, int *nreductions, double *alg_bytes);
+
+/* ---- kron(A, B) (src/kron.jl:10-49): the tensor-core path ----------------------------------- */
+/* A: m x n, B: p x q, COLUMN-major (Julia layout), bf16, 16-byte aligned, every dimension a multiple of 8.  The
+ * matrices are borrowed (aliased) for the lifetime of the handle; row-major copies for the K-major operands are
+ * made once here.  max_batch = most right-hand sides one apply may carry (sizes the L2-resident intermediate). */
+int b2o_kron_create(b2o_ctx *ctx, int dtype, const void *A, int64_t m, int64_t n, const void *B, int64_t p, int64_t q,
+                    int max_batch, b2o_kron **out);
+int b2o_kron_destroy(b2o_kron *k);
+/* trans = 0: prod!  res = alpha*vec(B X A^T) + beta*res, X = reshape(x, q, n)   (src/kron.jl:14-22)
+ * trans = 1: tprod!/ctprod!  res = alpha*vec(B^T X A) + beta*res, X = reshape(x, p, m)   (:23-40)
+ * x / res hold nb vectors back to back (nb = 1 is the reference call); *_len are the per-vector lengths.
+ * One cooperative launch: TMA -> tcgen05.mma (fp32 accumulate in TMEM) -> bf16 hi/lo intermediate in L2 -> tcgen05.mma. */
+int b2o_kron_apply(b2o_kron *k, int trans, void *res, int64_t res_len, const void *x, int64_t x_len, int nb,
+                   double alpha, double beta);
+int b2o_kron_flops(b2o_kron *k, int nb, double *flops);
 
 /* ---- row-partitioned multi-GPU (one process per GPU) ------------------------------------- */
 /* id: 128-byte ncclUniqueId produced on rank 0 by b2o_comm_unique_id and broadcast by the host

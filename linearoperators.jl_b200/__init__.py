@@ -12,6 +12,7 @@ from .abstract import (AbstractLinearOperator, AdjointLinearOperator, ConjugateL
 from .cat import hcat, hvcat, vcat  # noqa: F401
 from .context import Context, default_context  # noqa: F401
 from .graph import FusedOperator, fuse  # noqa: F401
+from .kron import KronOperator, kron  # noqa: F401
 from .qn import (InverseLBFGSOperator, LBFGSOperator, LSR1Operator, diag, diag_, push_)  # noqa: F401
 from .special_operators import (BlockDiagonalOperator, getindex, opDiagonal, opExtension, opEye, opHouseholder,  # noqa: F401
                                 opOnes, opRestriction, opZeros)

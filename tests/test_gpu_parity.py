@@ -624,3 +624,64 @@ def test_fuse_rejects_non_static_trees(lo, ctx):
     f = lo.fuse(lo.opEye(n) * 2.0)
     with pytest.raises(lo.LinearOperatorException, match="shape mismatch"):
         f * ctx.uniform(n + 1, 1)
+
+
+# ---------------------------------------------------------------- kron(A,B): tcgen05 GEMM pair (bf16, 1e-3)
+def _bf16_mats(ctx, orc, shapes, seeds):
+    import torch
+    out_t, out_np = [], []
+    for shp, seed in zip(shapes, seeds):
+        n = int(np.prod(shp))
+        a = orc.bf16_round(orc.uniform(n, seed, -1.0, 1.0)).reshape(shp)          # values exactly representable in bf16
+        out_np.append(a)
+        out_t.append(torch.as_tensor(a, dtype=torch.float64).to("cuda:%d" % ctx.device).to(torch.bfloat16).contiguous())
+    return out_t, out_np
+
+
+@pytest.mark.parametrize("dims", [(512, 512, 512, 512), (24, 40, 72, 56), (128, 64, 256, 192), (8, 8, 8, 8)])
+def test_kron_tcgen05_vs_oracle(lo, ctx, orc, dims):
+    """BASELINE config 4 (512x512 bf16) and ragged shapes; norm-wise rel <= 1e-3 against the Float64 oracle on the
+    same bf16-rounded inputs (src/kron.jl:14-40; test/test_kron.jl:3-39 predicate for the small case)."""
+    import torch
+    m, n, p, q = dims
+    (A, B, x, xt, r0), (An, Bn, xn, xtn, r0n) = _bf16_mats(ctx, orc, [(m, n), (p, q), (n * q,), (m * p,), (m * p,)], [11, 12, 13, 14, 15])
+    K = lo.kron(A, B, ctx=ctx)
+    assert lo.size(K) == (m * p, n * q)
+    res = (K * x).to(torch.float64).cpu().numpy()
+    ref = np.empty(m * p)
+    orc.kron_(ref, An, Bn, xn)
+    assert rel(res, ref) <= 1e-3, rel(res, ref)
+    if m * p * n * q <= 1 << 22:                                                     # dense Kronecker product for small cases
+        assert rel(res, np.kron(An, Bn) @ xn) <= 1e-3
+    rt = (lo.transpose(K) * xt).to(torch.float64).cpu().numpy()
+    reft = np.empty(n * q)
+    orc.kron_(reft, An, Bn, xtn, trans=1)
+    assert rel(rt, reft) <= 1e-3
+    assert rel((lo.adjoint(K) * xt).to(torch.float64).cpu().numpy(), reft) <= 1e-3
+    out = r0.clone()
+    lo.mul_(out, K, x, 2.0, -0.5)                                                    # 5-arg form
+    ref5 = r0n.copy()
+    orc.kron_(ref5, An, Bn, xn, alpha=2.0, beta=-0.5)
+    assert rel(out.to(torch.float64).cpu().numpy(), ref5) <= 2e-3
+    with pytest.raises(lo.LinearOperatorException, match="shape mismatch"):
+        K * xt[:-8] if xt.shape[0] != x.shape[0] else K * x[:-8]
+
+
+def test_kron_batch_and_launch_count(lo, ctx, orc):
+    import torch
+    m = n = p = q = 128
+    (A, B), (An, Bn) = _bf16_mats(ctx, orc, [(m, n), (p, q)], [21, 22])
+    nb = 5
+    Xn = orc.bf16_round(orc.uniform(nb * n * q, 23, -1.0, 1.0)).reshape(nb, n * q)
+    X = torch.as_tensor(Xn).to("cuda:%d" % ctx.device).to(torch.bfloat16).contiguous()
+    K = lo.kron(A, B, max_batch=8, ctx=ctx)
+    l0 = ctx.launch_count()
+    R = K.apply_batch(X)
+    assert ctx.launch_count() - l0 == 1                                              # the GEMM pair is ONE launch
+    for b in range(nb):
+        ref = np.empty(m * p)
+        orc.kron_(ref, An, Bn, Xn[b])
+        assert rel(R[b].to(torch.float64).cpu().numpy(), ref) <= 1e-3
+    assert K.flops() == 2.0 * p * q * n + 2.0 * p * n * m
+    with pytest.raises(lo.B2OError):
+        lo.kron(A[:, :-1].contiguous(), B, ctx=ctx)                                  # dims must be multiples of 8

@@ -54,6 +54,30 @@ def main():
     big = "--small" not in sys.argv
     n = 10**8 if big else 10**6
     flush = torch.empty(256 * 2**20 // 8, dtype=torch.float64, device="cuda")
+    if only == ["kron"]:
+        import oracle as orc
+        orc.set_mode(True, 1)
+        m = 512
+        mk = lambda seed, shape: torch.as_tensor(orc.bf16_round(orc.uniform(int(np.prod(shape)), seed, -1.0, 1.0)).reshape(shape)).cuda().to(torch.bfloat16).contiguous()
+        A, B, x = mk(11, (m, m)), mk(12, (m, m)), mk(13, (m * m,))
+        K = lo.kron(A, B, max_batch=64, ctx=ctx)
+        res = torch.empty(m * m, dtype=torch.bfloat16, device="cuda")
+        fl = K.flops()
+        for name, fn, f in (("cfg4 kron(A,B)*x 512x512 bf16, one launch (tcgen05 GEMM pair)", lambda: lo.mul_(res, K, x), fl),
+                            ("cfg4 transpose(kron)*x", lambda: lo.mul_(res, lo.transpose(K), x), fl)):
+            ms = timeit(fn, 200, warmup=10)
+            print(json.dumps({"case": name, "ms": round(ms, 5), "flops": f, "TFLOPs": round(f / (ms * 1e-3) / 1e12, 2),
+                              "frac_of_measured_bf16_peak": round(f / (ms * 1e-3) / 1e12 / 1686.8, 4)}), flush=True)
+        X = mk(14, (64, m * m))
+        R = torch.empty((64, m * m), dtype=torch.bfloat16, device="cuda")
+        ms = timeit(lambda: K.apply_batch(X, res=R), 100, warmup=5)
+        f = K.flops(64)
+        print(json.dumps({"case": "EXTRA (not a reference feature): 64 right-hand sides in one launch", "ms": round(ms, 5), "flops": f,
+                          "TFLOPs": round(f / (ms * 1e-3) / 1e12, 2), "frac_of_measured_bf16_peak": round(f / (ms * 1e-3) / 1e12 / 1686.8, 4)}), flush=True)
+        Af, Bf, Xf = A.float(), B.float(), x.float().reshape(m, m).t()   # X = reshape(x, q, n) column-major
+        ms = timeit(lambda: (Bf @ Xf) @ Af.t(), 100, warmup=5)
+        print(json.dumps({"case": "for scale: torch fp32 (B@X)@A.T via cuBLAS, 2 launches", "ms": round(ms, 5)}), flush=True)
+        return
     if only == ["cfg3"]:
         v, res = ctx.uniform(n, 2), ctx.empty(n)
         h = ctx.uniform(n, 3)
