@@ -178,8 +178,9 @@ int b2o_kron_destroy(b2o_kron *k);
 /* trans = 0: prod!  res = alpha*vec(B X A^T) + beta*res, X = reshape(x, q, n)   (src/kron.jl:14-22)
  * trans = 1: tprod!/ctprod!  res = alpha*vec(B^T X A) + beta*res, X = reshape(x, p, m)   (:23-40)
  * x / res hold nb vectors back to back (nb = 1 is the reference call); *_len are the per-vector lengths.
+ * res_dtype: B2O_BF16 (the reference's promoted element type; the final rounding alone is 2^-9 relative) or B2O_F32.
  * One cooperative launch: TMA -> tcgen05.mma (fp32 accumulate in TMEM) -> bf16 hi/lo intermediate in L2 -> tcgen05.mma. */
-int b2o_kron_apply(b2o_kron *k, int trans, void *res, int64_t res_len, const void *x, int64_t x_len, int nb,
+int b2o_kron_apply(b2o_kron *k, int trans, void *res, int res_dtype, int64_t res_len, const void *x, int64_t x_len, int nb,
                    double alpha, double beta);
 int b2o_kron_flops(b2o_kron *k, int nb, double *flops);
 

@@ -26,7 +26,8 @@ struct KronArgs {
   int M, K1, N1, N2, nb;        // see header comment; phase-1 K = N1
   int ldy;                      // N1 rounded up to 64; a Y row holds [hi: ldy | lo: ldy] elements
   __nv_bfloat16 *Y;             // [(nb*M) × 2*ldy], padding columns stay zero
-  __nv_bfloat16 *res;           // nb × (M*N2), each column-major M×N2
+  void *res;                    // nb × (M*N2), each column-major M×N2; bf16 or (out_f32) fp32
+  int out_f32;
   float alpha, beta;
   unsigned long long *bar;
   unsigned long long bar_target;
@@ -212,15 +213,21 @@ kron_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_con
             } else {
               // res_b[j*M + i] = α·Z (+ β·res), rows r = b*M + i; lanes of a warp write consecutive i: coalesced
               const int b = r / p.M, i = r - b * p.M;
-              __nv_bfloat16 *base = p.res + (size_t)b * p.M * p.N2 + i;
+              const size_t off = (size_t)b * p.M * p.N2 + i;
 #pragma unroll
               for (int e = 0; e < 32; ++e) {
                 const int j = n0 + c0 + e;
                 if (j < Ncols) {
                   float z = p.alpha * __uint_as_float(v[e]);
-                  __nv_bfloat16 *dst = base + (size_t)j * p.M;
-                  if (p.beta != 0.f) z += p.beta * __bfloat162float(*dst);
-                  *dst = __float2bfloat16_rn(z);
+                  if (p.out_f32) {
+                    float *dst = reinterpret_cast<float *>(p.res) + off + (size_t)j * p.M;
+                    if (p.beta != 0.f) z += p.beta * *dst;
+                    *dst = z;
+                  } else {
+                    __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(p.res) + off + (size_t)j * p.M;
+                    if (p.beta != 0.f) z += p.beta * __bfloat162float(*dst);
+                    *dst = __float2bfloat16_rn(z);
+                  }
                 }
               }
             }
@@ -294,7 +301,11 @@ struct b2o_kron_s {
   int ldArm, ldBrm;
   __nv_bfloat16 *Y[2] = {nullptr, nullptr};   // [0] prod, [1] tprod workspaces ([hi|lo] rows, zero padded)
   size_t y_elems[2] = {0, 0};
-  CUtensorMap tmA1[2], tmB2[2];        // [0] prod, [1] tprod
+  CUtensorMap tmA1[2], tmB2[2][2], tmY[2][2];   // [direction][BN==64]; fixed operands are encoded once at create
+  int y_rows[2] = {0, 0};              // rows (nb*M) the cached Y map was encoded for
+  CUtensorMap tmX[2];                  // last x map per direction (re-encoded only when x / nb / BN change)
+  const void *x_last[2] = {nullptr, nullptr};
+  int x_nb[2] = {0, 0}, x_bn[2] = {0, 0};
 };
 
 static inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
@@ -337,6 +348,16 @@ extern "C" int b2o_kron_create(b2o_ctx *ctx, int dtype, const void *A, int64_t m
   // prod : A1 = B row-major [p × q], B2 = A row-major [m × n];   tprod: A1 = Bᵀ = [q × p] (B as stored), B2 = Aᵀ = [n × m]
   int st = make_tmap(&k->tmA1[0], k->Brm, p, q, k->ldBrm, KR_BM);
   if (st == B2O_OK) st = make_tmap(&k->tmA1[1], k->B, q, p, p, KR_BM);
+  for (int w = 0; w < 2 && st == B2O_OK; ++w) {
+    const int bn = w ? 64 : 128;
+    st = make_tmap(&k->tmB2[0][w], k->Arm, m, n, k->ldArm, bn);                       // prod : B2 = A row-major [m × n]
+    if (st == B2O_OK) st = make_tmap(&k->tmB2[1][w], k->A, n, m, m, bn);              // tprod: B2 = Aᵀ = [n × m], A as stored
+  }
+  if (st == B2O_OK) {                                                                 // Y maps for the full batch capacity
+    const int ldy0 = round_up((int)n, 64), ldy1 = round_up((int)m, 64);
+    st = make_tmap(&k->tmY[0][0], k->Y[0], (uint64_t)max_batch * p, 2 * (uint64_t)ldy0, 2 * (uint64_t)ldy0, KR_BM);
+    if (st == B2O_OK) st = make_tmap(&k->tmY[1][0], k->Y[1], (uint64_t)max_batch * q, 2 * (uint64_t)ldy1, 2 * (uint64_t)ldy1, KR_BM);
+  }
   if (st != B2O_OK) {
     b2o_kron_destroy(k);
     return st;
@@ -382,21 +403,23 @@ static int kron_launch(b2o_ctx *c, const CUtensorMap &tA1, const CUtensorMap &tX
 }
 
 // trans: 0 prod!, 1 tprod! (== ctprod! for real element types).  x: nb vectors back to back, res likewise.
-extern "C" int b2o_kron_apply(b2o_kron *k, int trans, void *res, int64_t res_len, const void *x, int64_t x_len, int nb,
-                              double alpha, double beta) {
+extern "C" int b2o_kron_apply(b2o_kron *k, int trans, void *res, int res_dtype, int64_t res_len, const void *x, int64_t x_len,
+                              int nb, double alpha, double beta) {
   if (!k) B2O_FAIL(B2O_EARG, "null operator");
   if (nb < 1 || nb > k->max_batch) B2O_FAIL(B2O_EARG, "batch %d outside [1, %d]", nb, k->max_batch);
   const int M = trans ? k->q : k->p, K1 = trans ? k->p : k->q, N1 = trans ? k->m : k->n, N2 = trans ? k->n : k->m;
   if (x_len != (int64_t)K1 * N1 || res_len != (int64_t)M * N2) B2O_FAIL(B2O_ESHAPE, "shape mismatch");
   if (!res || !x) B2O_FAIL(B2O_EARG, "null vector");
-  if (((uintptr_t)x % 16) || ((uintptr_t)res % 2)) B2O_FAIL(B2O_EARG, "kron: x must be 16-byte aligned");
+  if (res_dtype != B2O_BF16 && res_dtype != B2O_F32) B2O_FAIL(B2O_EUNSUPPORTED, "kron: result dtype must be bf16 or f32");
+  if (((uintptr_t)x % 16) || ((uintptr_t)res % 4)) B2O_FAIL(B2O_EARG, "kron: x must be 16-byte aligned");
   b2o_ctx *c = k->ctx;
   B2O_CUDA(cudaSetDevice(c->device));
   KronArgs a;
   a.M = M; a.K1 = K1; a.N1 = N1; a.N2 = N2; a.nb = nb;
   a.ldy = round_up(N1, 64);
   a.Y = k->Y[trans ? 1 : 0];
-  a.res = (__nv_bfloat16 *)res;
+  a.res = res;
+  a.out_f32 = res_dtype == B2O_F32;
   a.alpha = (float)alpha;
   a.beta = (float)beta;
   a.bar = c->d_bar;
@@ -407,13 +430,17 @@ extern "C" int b2o_kron_apply(b2o_kron *k, int trans, void *res, int64_t res_len
   const int tiles0 = t0 * ((nb * N1 + BN - 1) / BN), tiles1 = t1rows * ((N2 + BN - 1) / BN);
   int grid = std::max(1, std::min(c->num_sms, std::max(tiles0, tiles1)));
   a.bar_target = c->bar_base + (unsigned long long)grid;
-  CUtensorMap tX, tY, tB2;
-  B2O_TRY(make_tmap(&tX, x, (uint64_t)nb * N1, K1, K1, BN));
-  B2O_TRY(make_tmap(&tY, a.Y, (uint64_t)nb * M, 2 * (uint64_t)a.ldy, 2 * (uint64_t)a.ldy, KR_BM));
-  if (trans) B2O_TRY(make_tmap(&tB2, k->A, N2, N1, N1 /* = m */, BN));
-  else B2O_TRY(make_tmap(&tB2, k->Arm, N2, N1, k->ldArm, BN));
-  int st = bn64 ? kron_launch<64>(c, k->tmA1[trans ? 1 : 0], tX, tY, tB2, a, grid)
-                : kron_launch<128>(c, k->tmA1[trans ? 1 : 0], tX, tY, tB2, a, grid);
+  const int d = trans ? 1 : 0;
+  if (k->x_last[d] != x || k->x_nb[d] != nb || k->x_bn[d] != BN) {   // the only per-call descriptor: x (host-side encode, ~1 us)
+    B2O_TRY(make_tmap(&k->tmX[d], x, (uint64_t)nb * N1, K1, K1, BN));
+    k->x_last[d] = x;
+    k->x_nb[d] = nb;
+    k->x_bn[d] = BN;
+  }
+  // Y rows beyond nb*M hold stale (finite) data from larger batches; phase 1 masks its rows with Mrows = nb*M
+  const CUtensorMap &tY = k->tmY[d][0], &tB2 = k->tmB2[d][bn64 ? 1 : 0];
+  int st = bn64 ? kron_launch<64>(c, k->tmA1[d], k->tmX[d], tY, tB2, a, grid)
+                : kron_launch<128>(c, k->tmA1[d], k->tmX[d], tY, tB2, a, grid);
   if (st == B2O_OK) c->bar_base += (unsigned long long)grid;
   return st;
 }

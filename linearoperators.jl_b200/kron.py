@@ -15,6 +15,14 @@ def _bf16_ptr(t, what):
     return ctypes.c_void_p(t.data_ptr())
 
 
+def _res_ptr(t):
+    """result vector: bfloat16 (the reference's promoted eltype) or float32"""
+    import torch
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype not in (torch.bfloat16, torch.float32) or not t.is_contiguous():
+        raise _lib.B2OError("res must be a contiguous torch CUDA bfloat16 or float32 tensor")
+    return ctypes.c_void_p(t.data_ptr()), (_lib.B2O_BF16 if t.dtype == torch.bfloat16 else _lib.B2O_F32)
+
+
 class KronOperator(LinearOperator):
     def apply_batch(self, X, alpha=1.0, beta=0.0, res=None, trans=False):
         """nb right-hand sides at once: X is (nb, ncol) row-major (each row one vec), result (nb, nrow)."""
@@ -23,7 +31,8 @@ class KronOperator(LinearOperator):
         ncol, nrow = (self.nrow, self.ncol) if trans else (self.ncol, self.nrow)
         if res is None:
             res = torch.empty((nb, nrow), dtype=torch.bfloat16, device=X.device)
-        _lib.check(self.ctx.lib.b2o_kron_apply(self._h, int(trans), _bf16_ptr(res, "res"), nrow, _bf16_ptr(X, "x"), ncol, nb,
+        rp, rd = _res_ptr(res)
+        _lib.check(self.ctx.lib.b2o_kron_apply(self._h, int(trans), rp, rd, nrow, _bf16_ptr(X, "x"), ncol, nb,
                                                float(alpha), float(beta)))
         return res
 
@@ -57,10 +66,12 @@ def kron(A, B, max_batch=1, ctx=None):
     lib = ctx.lib
 
     def prod_(res, x, a, b):
-        _lib.check(lib.b2o_kron_apply(h, 0, _bf16_ptr(res, "res"), res.shape[0], _bf16_ptr(x, "x"), x.shape[0], 1, float(a), float(b)))
+        rp, rd = _res_ptr(res)
+        _lib.check(lib.b2o_kron_apply(h, 0, rp, rd, res.shape[0], _bf16_ptr(x, "x"), x.shape[0], 1, float(a), float(b)))
 
     def tprod_(res, x, a, b):
-        _lib.check(lib.b2o_kron_apply(h, 1, _bf16_ptr(res, "res"), res.shape[0], _bf16_ptr(x, "x"), x.shape[0], 1, float(a), float(b)))
+        rp, rd = _res_ptr(res)
+        _lib.check(lib.b2o_kron_apply(h, 1, rp, rd, res.shape[0], _bf16_ptr(x, "x"), x.shape[0], 1, float(a), float(b)))
 
     op = KronOperator(torch.bfloat16, m * p, n * q, False, False, prod_, tprod_, tprod_,
                       S=Storage("cuda", ctx.device, dtype=torch.bfloat16))

@@ -647,24 +647,36 @@ def test_kron_tcgen05_vs_oracle(lo, ctx, orc, dims):
     (A, B, x, xt, r0), (An, Bn, xn, xtn, r0n) = _bf16_mats(ctx, orc, [(m, n), (p, q), (n * q,), (m * p,), (m * p,)], [11, 12, 13, 14, 15])
     K = lo.kron(A, B, ctx=ctx)
     assert lo.size(K) == (m * p, n * q)
-    res = (K * x).to(torch.float64).cpu().numpy()
-    ref = np.empty(m * p)
+    ref, reft = np.empty(m * p), np.empty(n * q)
     orc.kron_(ref, An, Bn, xn)
-    assert rel(res, ref) <= 1e-3, rel(res, ref)
-    if m * p * n * q <= 1 << 22:                                                     # dense Kronecker product for small cases
-        assert rel(res, np.kron(An, Bn) @ xn) <= 1e-3
-    rt = (lo.transpose(K) * xt).to(torch.float64).cpu().numpy()
-    reft = np.empty(n * q)
     orc.kron_(reft, An, Bn, xtn, trans=1)
-    assert rel(rt, reft) <= 1e-3
-    assert rel((lo.adjoint(K) * xt).to(torch.float64).cpu().numpy(), reft) <= 1e-3
+    dev_ = "cuda:%d" % ctx.device
+    # (1) fp32 result: the computation itself (fp32 TMEM accumulation, hi/lo intermediate) against the Float64 oracle
+    r32 = torch.empty(m * p, dtype=torch.float32, device=dev_)
+    lo.mul_(r32, K, x)
+    assert rel(r32.double().cpu().numpy(), ref) <= 1e-5, rel(r32.double().cpu().numpy(), ref)
+    t32 = torch.empty(n * q, dtype=torch.float32, device=dev_)
+    lo.mul_(t32, lo.transpose(K), xt)
+    assert rel(t32.double().cpu().numpy(), reft) <= 1e-5
+    lo.mul_(t32, lo.adjoint(K), xt)
+    assert rel(t32.double().cpu().numpy(), reft) <= 1e-5
+    if m * p * n * q <= 1 << 22:                                                     # dense Kronecker product (test_kron.jl:15-17)
+        assert rel(r32.double().cpu().numpy(), np.kron(An, Bn) @ xn) <= 1e-5
+    # (2) bf16 result (the reference's promoted eltype): equals the oracle rounded to bf16 up to rare 1-ulp flips, and is
+    #     within the 2^-8 relative rounding of bf16 of the unrounded oracle elementwise
+    res = (K * x).to(torch.float64).cpu().numpy()
+    assert rel(res, orc.bf16_round(ref)) <= 1e-3
+    assert np.all(np.abs(res - ref) <= 2.0**-8 * np.abs(ref) + 1e-5 * np.abs(ref).max())
     out = r0.clone()
     lo.mul_(out, K, x, 2.0, -0.5)                                                    # 5-arg form
     ref5 = r0n.copy()
     orc.kron_(ref5, An, Bn, xn, alpha=2.0, beta=-0.5)
-    assert rel(out.to(torch.float64).cpu().numpy(), ref5) <= 2e-3
+    assert rel(out.to(torch.float64).cpu().numpy(), orc.bf16_round(ref5)) <= 1e-3
+    o32 = torch.as_tensor(r0n, dtype=torch.float32).to(dev_)
+    lo.mul_(o32, K, x, 2.0, -0.5)
+    assert rel(o32.double().cpu().numpy(), ref5) <= 1e-5
     with pytest.raises(lo.LinearOperatorException, match="shape mismatch"):
-        K * xt[:-8] if xt.shape[0] != x.shape[0] else K * x[:-8]
+        K * x[:-8]
 
 
 def test_kron_batch_and_launch_count(lo, ctx, orc):
@@ -681,7 +693,12 @@ def test_kron_batch_and_launch_count(lo, ctx, orc):
     for b in range(nb):
         ref = np.empty(m * p)
         orc.kron_(ref, An, Bn, Xn[b])
-        assert rel(R[b].to(torch.float64).cpu().numpy(), ref) <= 1e-3
+        assert rel(R[b].to(torch.float64).cpu().numpy(), orc.bf16_round(ref)) <= 1e-3
+    R32 = K.apply_batch(X, res=torch.empty((nb, m * p), dtype=torch.float32, device=X.device))
+    for b in range(nb):
+        ref = np.empty(m * p)
+        orc.kron_(ref, An, Bn, Xn[b])
+        assert rel(R32[b].double().cpu().numpy(), ref) <= 1e-5
     assert K.flops() == 2.0 * p * q * n + 2.0 * p * n * m
     with pytest.raises(lo.B2OError):
         lo.kron(A[:, :-1].contiguous(), B, ctx=ctx)                                  # dims must be multiples of 8
