@@ -55,6 +55,13 @@ extern "C" int b2o_ctx_destroy(b2o_ctx *c) {
   cudaFreeHost(c->h_scal);
   if (c->stage_x) cudaFree(c->stage_x);
   if (c->stage_res) cudaFree(c->stage_res);
+  if (c->s_in) cudaStreamDestroy(c->s_in);
+  if (c->s_out) cudaStreamDestroy(c->s_out);
+  for (int i = 0; i < 16; ++i) {
+    if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+    if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
+  }
+  if (c->ev_start) cudaEventDestroy(c->ev_start);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -79,6 +86,9 @@ extern "C" int b2o_ctx_set_option(b2o_ctx *c, const char *key, int64_t value) {
   } else if (!strcmp(key, "grid")) {
     if (value < 0 || value > B2O_MAX_GRID) B2O_FAIL(B2O_EARG, "grid out of range");
     c->grid = (int)value;
+  } else if (!strcmp(key, "host_chunks")) {
+    if (value < 1 || value > 16) B2O_FAIL(B2O_EARG, "host_chunks must be 1..16");
+    c->host_chunks = (int)value;
   } else if (!strcmp(key, "graph_jit")) {
     c->graph_jit = value != 0;
   } else if (!strcmp(key, "graph_blocks")) {

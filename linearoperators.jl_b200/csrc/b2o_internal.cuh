@@ -53,6 +53,10 @@ struct b2o_ctx_s {
   // staging for *_host entry points (grown on first use, then reused)
   void *stage_x = nullptr, *stage_res = nullptr;
   size_t stage_bytes = 0;
+  // host-buffer pipeline: copy-in / copy-out streams and per-chunk events (created on first use)
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[16] = {}, ev_k[16] = {}, ev_start = nullptr;
+  int host_chunks = 8;
   // tuning
   int tile_rows = 2048;
   int stages = 0;        // 0 -> as many as shared memory allows

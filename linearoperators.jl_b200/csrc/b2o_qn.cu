@@ -330,11 +330,10 @@ static int active_old_to_new(const b2o_qn *q, int *slots) {
 }
 
 // ------------------------------------------------------------------ apply
-static int qn_apply_compact(b2o_qn *q, double *res, const double *x, double alpha, double beta) {
-  b2o_ctx *c = q->ctx;
+// fills the column table (reference order) and scalars; row range / launch geometry are set by the launcher
+static void compact_columns(const b2o_qn *q, CompactArgs &a, double alpha, double beta) {
   int slots[B2O_MAX_MEM];
   const int na = active_old_to_new(q, slots);
-  CompactArgs a;
   memset(&a, 0, sizeof(a));
   if (q->kind == 0) {
     for (int i = 0; i < na; ++i) {
@@ -350,19 +349,27 @@ static int qn_apply_compact(b2o_qn *q, double *res, const double *x, double alph
     }
     a.ncols = na;
   }
-  a.x = x;
-  a.res = res;
-  a.n = q->n;
-  LaunchCfg cfg;
-  cfg.R = c->tile_rows;
-  a.ntiles = (q->n + cfg.R - 1) / cfg.R;
-  B2O_TRY(plan_launch(c, a.ntiles, a.ncols, true, &cfg));
   a.alpha = alpha;
   a.beta = beta;
   a.gamma = q->gamma;
   a.scaling = q->scaling ? 1 : 0;
-  a.x_al16 = ((uintptr_t)x % 16) == 0;
-  a.res_al16 = ((uintptr_t)res % 16) == 0;
+}
+
+// one launch of the compact kernel over rows [r0, r1) (r0 a multiple of the pitch alignment)
+static int compact_launch_rows(b2o_qn *q, const CompactArgs &base, double *res, const double *x, int64_t r0, int64_t r1, int mode,
+                               int accumulate, cudaStream_t stream_override = nullptr, bool use_override = false) {
+  b2o_ctx *c = q->ctx;
+  CompactArgs a = base;
+  for (int i = 0; i < a.ncols; ++i) a.cols[i] += r0;
+  a.x = x + r0;
+  a.res = res + r0;
+  a.n = r1 - r0;
+  LaunchCfg cfg;
+  cfg.R = c->tile_rows;
+  a.ntiles = (a.n + cfg.R - 1) / cfg.R;
+  B2O_TRY(plan_launch(c, a.ntiles, a.ncols, true, &cfg));
+  a.x_al16 = ((uintptr_t)a.x % 16) == 0;
+  a.res_al16 = ((uintptr_t)a.res % 16) == 0;
   a.partials = c->d_partials;
   a.dots = c->d_dots;
   a.bar = c->d_bar;
@@ -372,25 +379,29 @@ static int qn_apply_compact(b2o_qn *q, double *res, const double *x, double alph
   a.accs_off = (uint32_t)cfg.L.accs_off;
   a.coef_off = (uint32_t)cfg.L.coef_off;
   a.bar_off = (uint32_t)cfg.L.bar_off;
+  a.mode = mode;
+  a.accumulate = accumulate;
+  if (a.n <= 0) return B2O_OK;
+  const bool coop = mode == MODE_FUSED;
+  if (coop) a.bar_target = c->bar_base + (unsigned long long)cfg.grid;
+  (void)stream_override;
+  (void)use_override;
+  int st = q->kind == 0 ? launch_compact_R<OP_LBFGS_FWD>(c, cfg, a, coop) : launch_compact_R<OP_LSR1>(c, cfg, a, coop);
+  if (st == B2O_OK && coop) c->bar_base += (unsigned long long)cfg.grid;
+  return st;
+}
+
+static int qn_apply_compact(b2o_qn *q, double *res, const double *x, double alpha, double beta) {
+  b2o_ctx *c = q->ctx;
   if (q->n == 0) return B2O_OK;
-  const bool split = c->nranks > 1 && a.ncols > 0;
-  auto launch = [&](bool coop) -> int {
-    return q->kind == 0 ? launch_compact_R<OP_LBFGS_FWD>(c, cfg, a, coop) : launch_compact_R<OP_LSR1>(c, cfg, a, coop);
-  };
-  if (!split) {
-    a.mode = a.ncols > 0 ? MODE_FUSED : MODE_PHASE2;
-    a.bar_target = c->bar_base + (unsigned long long)cfg.grid;
-    B2O_TRY(launch(a.ncols > 0));
-    if (a.ncols > 0) c->bar_base += (unsigned long long)cfg.grid;
-  } else {
-    // row-partitioned: local dots -> one all-reduce of ncols scalars -> combine
-    a.mode = MODE_PHASE1;
-    B2O_TRY(launch(false));
-    B2O_TRY(b2o_allreduce_sum_f64(c, c->d_dots, a.ncols));
-    a.mode = MODE_PHASE2;
-    B2O_TRY(launch(false));
-  }
-  return B2O_OK;
+  CompactArgs a;
+  compact_columns(q, a, alpha, beta);
+  if (a.ncols == 0) return compact_launch_rows(q, a, res, x, 0, q->n, MODE_PHASE2, 0);
+  if (c->nranks <= 1) return compact_launch_rows(q, a, res, x, 0, q->n, MODE_FUSED, 0);
+  // row-partitioned: local dots -> one all-reduce of ncols scalars -> combine
+  B2O_TRY(compact_launch_rows(q, a, res, x, 0, q->n, MODE_PHASE1, 0));
+  B2O_TRY(b2o_allreduce_sum_f64(c, c->d_dots, a.ncols));
+  return compact_launch_rows(q, a, res, x, 0, q->n, MODE_PHASE2, 0);
 }
 
 // A == 0 (fresh / reset operator): q = x; scaling && q *= γ; res = α q (+ β res)
@@ -496,6 +507,22 @@ static int ensure_stage(b2o_ctx *c, size_t bytes) {
   return B2O_OK;
 }
 
+static int ensure_pipeline(b2o_ctx *c) {
+  if (c->s_in) return B2O_OK;
+  B2O_CUDA(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+  B2O_CUDA(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < 16; ++i) {
+    B2O_CUDA(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+    B2O_CUDA(cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
+  }
+  B2O_CUDA(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
+  return B2O_OK;
+}
+
+// Host-buffer apply.  For the two-phase operators (forward L-BFGS, L-SR1) the transfers are pipelined with the kernels in
+// row chunks: chunk c's dots run while chunk c+1 is still crossing PCIe, and res chunks stream back while later chunks combine
+// (phase 2 needs all dots, so the H2D and D2H halves cannot overlap each other).  Chunk results are bit-identical to a single
+// launch's only per chunk order: the dots are accumulated chunk by chunk in a fixed order (deterministic).
 extern "C" int b2o_qn_apply_host(b2o_qn *q, void *res_host, const void *x_host, int64_t len, double alpha, double beta) {
   if (!q) B2O_FAIL(B2O_EARG, "null operator");
   if (len != q->n) B2O_FAIL(B2O_ESHAPE, "shape mismatch");
@@ -503,10 +530,55 @@ extern "C" int b2o_qn_apply_host(b2o_qn *q, void *res_host, const void *x_host, 
   B2O_CUDA(cudaSetDevice(c->device));
   const size_t bytes = (size_t)q->n * sizeof(double);
   B2O_TRY(ensure_stage(c, std::max<size_t>(bytes, 16)));
-  B2O_CUDA(cudaMemcpyAsync(c->stage_x, x_host, bytes, cudaMemcpyHostToDevice, c->stream));
-  if (beta != 0.0) B2O_CUDA(cudaMemcpyAsync(c->stage_res, res_host, bytes, cudaMemcpyHostToDevice, c->stream));
-  B2O_TRY(qn_apply_dev(q, (double *)c->stage_res, (const double *)c->stage_x, alpha, beta));
-  B2O_CUDA(cudaMemcpyAsync(res_host, c->stage_res, bytes, cudaMemcpyDeviceToHost, c->stream));
+  double *dx = (double *)c->stage_x, *dres = (double *)c->stage_res;
+  const bool two_phase = !(q->kind == 0 && q->inverse);
+  const int64_t align = B2O_PITCH_ALIGN;
+  int nch = c->host_chunks;
+  if (!two_phase || q->n < 4 * align * nch) nch = 1;
+  if (nch == 1) {
+    B2O_CUDA(cudaMemcpyAsync(dx, x_host, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (beta != 0.0) B2O_CUDA(cudaMemcpyAsync(dres, res_host, bytes, cudaMemcpyHostToDevice, c->stream));
+    B2O_TRY(qn_apply_dev(q, dres, dx, alpha, beta));
+    B2O_CUDA(cudaMemcpyAsync(res_host, dres, bytes, cudaMemcpyDeviceToHost, c->stream));
+    B2O_CUDA(cudaStreamSynchronize(c->stream));
+    return B2O_OK;
+  }
+  B2O_TRY(ensure_pipeline(c));
+  CompactArgs a;
+  compact_columns(q, a, alpha, beta);
+  const int64_t rows_per = ((q->n + nch - 1) / nch + align - 1) / align * align;
+  auto lo = [&](int ch) { return std::min<int64_t>(q->n, (int64_t)ch * rows_per); };
+  // copy-in stream starts after whatever is already queued on the compute stream (previous users of the staging buffers)
+  B2O_CUDA(cudaEventRecord(c->ev_start, c->stream));
+  B2O_CUDA(cudaStreamWaitEvent(c->s_in, c->ev_start, 0));
+  B2O_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_start, 0));
+  for (int ch = 0; ch < nch; ++ch) {
+    const int64_t r0 = lo(ch), r1 = lo(ch + 1);
+    if (r1 > r0) {
+      B2O_CUDA(cudaMemcpyAsync(dx + r0, (const double *)x_host + r0, (size_t)(r1 - r0) * 8, cudaMemcpyHostToDevice, c->s_in));
+      if (beta != 0.0)
+        B2O_CUDA(cudaMemcpyAsync(dres + r0, (const double *)res_host + r0, (size_t)(r1 - r0) * 8, cudaMemcpyHostToDevice, c->s_in));
+    }
+    B2O_CUDA(cudaEventRecord(c->ev_in[ch], c->s_in));
+  }
+  if (a.ncols > 0) {
+    for (int ch = 0; ch < nch; ++ch) {
+      B2O_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in[ch], 0));
+      B2O_TRY(compact_launch_rows(q, a, dres, dx, lo(ch), lo(ch + 1), MODE_PHASE1, ch > 0));
+    }
+    B2O_TRY(b2o_allreduce_sum_f64(c, c->d_dots, a.ncols));
+  } else {
+    B2O_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in[nch - 1], 0));
+  }
+  for (int ch = 0; ch < nch; ++ch) {
+    const int64_t r0 = lo(ch), r1 = lo(ch + 1);
+    B2O_TRY(compact_launch_rows(q, a, dres, dx, r0, r1, MODE_PHASE2, 0));
+    B2O_CUDA(cudaEventRecord(c->ev_k[ch], c->stream));
+    B2O_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_k[ch], 0));
+    if (r1 > r0)
+      B2O_CUDA(cudaMemcpyAsync((double *)res_host + r0, dres + r0, (size_t)(r1 - r0) * 8, cudaMemcpyDeviceToHost, c->s_out));
+  }
+  B2O_CUDA(cudaStreamSynchronize(c->s_out));
   B2O_CUDA(cudaStreamSynchronize(c->stream));
   return B2O_OK;
 }

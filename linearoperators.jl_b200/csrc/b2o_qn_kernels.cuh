@@ -29,6 +29,7 @@ struct CompactArgs {
   unsigned long long bar_target;
   unsigned long long *arrive;        // last-block counter (split mode)
   int mode, stages, group;
+  int accumulate;                    // split mode: dots[c] += this launch's partial (row-chunked host pipeline)
   uint32_t accs_off, coef_off, bar_off;
 };
 
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
             double s = 0.0;
             for (int b = lane; b < (int)grid; b += 32) s += __ldcg(&p.partials[(size_t)b * ncols + c]);
             s = warp_sum(s);
-            if (lane == 0) p.dots[c] = s;
+            if (lane == 0) p.dots[c] = p.accumulate ? __ldcg(&p.dots[c]) + s : s;
           }
         }
         if (tid == 0) *p.arrive = 0ULL;

@@ -404,15 +404,28 @@ def test_lsr1_reference_predicates_on_gpu(lo, ctx):
         assert np.linalg.norm(host(lo.Matrix(LB)) - Bd) < rtol * np.linalg.norm(Bd)
 
 
-def test_apply_host_end_to_end(lo, ctx, orc):
+@pytest.mark.parametrize("n", [30011, 8 * 4096 * 8 + 4096 * 3 + 17])
+def test_apply_host_end_to_end(lo, ctx, orc, n):
+    """host-buffer C-ABI entry (H2D + apply + D2H inside); the larger size takes the row-chunked transfer/compute pipeline"""
     import torch
-    n = 30011
-    for kind in ("fwd", "inv"):
+    for kind in ("fwd", "inv", "lsr1"):
         g, o = build_pair(lo, ctx, orc, kind, n, 4, 5)
         xh = torch.from_numpy(orc.uniform(n, 7)).pin_memory()
         rh = torch.empty(n, dtype=torch.float64).pin_memory()
         g.apply_host(rh, xh)
         assert rel(rh.numpy(), o.apply(xh.numpy())) <= TOL
+        r0 = orc.uniform(n, 8)
+        rh.copy_(torch.from_numpy(r0))
+        g.apply_host(rh, xh, 1.5, -0.25)
+        ref = r0.copy()
+        o.apply(xh.numpy(), 1.5, -0.25, res=ref)
+        assert rel(rh.numpy(), ref) <= TOL
+        ctx.set_option("host_chunks", 3)
+        g.apply_host(rh, xh)
+        ctx.set_option("host_chunks", 8)
+        assert rel(rh.numpy(), o.apply(xh.numpy())) <= TOL
+        dres = g * ctx.uniform(n, 7)                                            # device path still agrees afterwards
+        assert rel(host(dres), o.apply(xh.numpy())) <= TOL
 
 
 # ---------------------------------------------------------------- composed chains (closure tree over CUDA leaves)
