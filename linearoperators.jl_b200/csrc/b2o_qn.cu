@@ -261,7 +261,10 @@ static int plan_launch(b2o_ctx *c, int64_t ntiles, int ncols, bool need_accs, La
     if (cfg->L.total <= max_smem) break;
     if (stages <= 2) B2O_FAIL(B2O_ECUDA, "shared memory plan does not fit");
   }
-  if (c->stages > 0) stages = std::min(stages, std::max(2, c->stages));
+  // measured on B200 (tools/sweep_stream.py, profiles/r1_sweep.jsonl): ~112-128 KB of column data in flight per SM is the
+  // sweet spot (2048x7, 4096x4, 1024x16); deeper rings lose 3-4%.
+  const int auto_stages = std::max(3, (int)((114688 + cfg->R * 4) / (cfg->R * 8)));
+  stages = std::min(stages, c->stages > 0 ? std::max(2, c->stages) : auto_stages);
   cfg->stages = stages;
   cfg->L = smem_layout(cfg->R, stages, cfg->group);
   int g = c->grid > 0 ? c->grid : c->num_sms;
