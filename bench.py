@@ -120,6 +120,7 @@ def main():
     ap.add_argument("--tile-rows", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-mailbox", action="store_true", help="multi-GPU: NCCL all-reduce per inner product instead of the NVLink mailbox")
     args = ap.parse_args()
     inverse = args.workload == "inv"
     rank = int(os.environ.get("RANK", "0"))
@@ -127,7 +128,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     args.warmup = max(args.warmup, 3)
     config = {"workload": "%sLBFGSOperator(n=%d, mem=%d) Float64 apply, alpha=1 beta=0" % ("Inverse" if inverse else "", args.n, args.mem),
-              "rows_per_gpu": args.n, "mem": args.mem, "parallelism": "row-partition x%d" % world if world > 1 else "single GPU",
+              "rows_per_gpu": args.n, "mem": args.mem, "parallelism": ("row-partition x%d, dots all-reduced %s" % (world, "over NCCL" if args.no_mailbox else "in-kernel over the NVLink peer mailbox")) if world > 1 else "single GPU",
               "l2": "inputs (%.1f GB of columns) >> 126 MB L2, no flush needed" % (2 * args.mem * args.n * 8 / 1e9)}
 
     if args.impl == "reference":
@@ -151,6 +152,12 @@ def main():
     ctx = lo.default_context(local_rank)
     if world > 1:
         ctx.init_comm_from_torch()
+        if not args.no_mailbox:
+            try:
+                ctx.connect_mailbox()          # in-kernel all-reduce over NVLink peer memory; NCCL stays for push!
+            except Exception as e:              # e.g. IPC not permitted: the NCCL path (kernel + all-reduce per dot) is used
+                if rank == 0:
+                    print("mailbox unavailable, using NCCL per inner product: %s" % e, file=sys.stderr)
     if args.tile_rows:
         ctx.set_option("tile_rows", args.tile_rows)
     if args.stages:

@@ -190,6 +190,13 @@ int b2o_kron_flops(b2o_kron *k, int nb, double *flops);
 int b2o_comm_unique_id(void *id128);
 int b2o_comm_init(b2o_ctx *ctx, const void *id128, int nranks, int rank);
 int b2o_comm_destroy(b2o_ctx *ctx);
+/* NVLink peer mailbox: with it the quasi-Newton applies stay ONE persistent launch per GPU -- the dots are all-reduced
+ * inside the kernel through peer-mapped memory (stores over NVLink + system-scope flags) instead of a kernel/NCCL pair per
+ * inner product.  Each rank exports a 64-byte CUDA-IPC handle of its mailbox, the host all-gathers them (rank order),
+ * every rank connects.  NCCL (b2o_comm_init) stays in use for the reductions inside push!. */
+int b2o_mbox_local_handle(b2o_ctx *ctx, void *handle64);
+int b2o_mbox_connect(b2o_ctx *ctx, const void *handles, int nranks, int rank);
+int b2o_mbox_disconnect(b2o_ctx *ctx);
 
 #ifdef __cplusplus
 }

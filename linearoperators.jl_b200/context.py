@@ -29,6 +29,7 @@ class Context:
         _lib.check(self.lib.b2o_ctx_create(self.device, ctypes.c_void_p(stream.cuda_stream), ctypes.byref(h)))
         self.handle = h
         self.nranks, self.rank = 1, 0
+        self.mailbox = False
 
     # -- plumbing
     def sync(self):
@@ -84,6 +85,24 @@ class Context:
         idbuf = (ctypes.c_ubyte * 128).from_buffer_copy(raw)
         _lib.check(self.lib.b2o_comm_init(self.handle, idbuf, world, rank))
         self.nranks, self.rank = world, rank
+
+    def connect_mailbox(self, group=None):
+        """NVLink peer mailbox: exchange CUDA-IPC handles of the per-GPU mailboxes so that the quasi-Newton applies all-reduce
+        their dots inside ONE persistent launch per GPU (stores over NVLink) instead of a kernel + NCCL call per inner product."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        mine = (ctypes.c_ubyte * 64)()
+        _lib.check(self.lib.b2o_mbox_local_handle(self.handle, mine))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, bytes(mine), group=group)
+        allh = (ctypes.c_ubyte * (64 * world)).from_buffer_copy(b"".join(gathered))
+        _lib.check(self.lib.b2o_mbox_connect(self.handle, allh, world, rank))
+        dist.barrier(group)
+        self.mailbox = True
+
+    def disconnect_mailbox(self):
+        _lib.check(self.lib.b2o_mbox_disconnect(self.handle))
+        self.mailbox = False
 
     def close(self):
         if self.handle:

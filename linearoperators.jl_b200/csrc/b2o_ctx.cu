@@ -49,6 +49,8 @@ extern "C" int b2o_ctx_destroy(b2o_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   b2o_comm_destroy(c);
+  b2o_mbox_disconnect(c);
+  if (c->mbox) cudaFree(c->mbox);
   cudaFree(c->d_partials);
   cudaFree(c->d_dots);
   cudaFree(c->d_bar);
@@ -367,6 +369,71 @@ extern "C" int b2o_comm_destroy(b2o_ctx *c) {
   c->rank = 0;
   return B2O_OK;
 }
+// ------------------------------------------------------------------ NVLink peer mailbox (CUDA IPC between the per-GPU processes)
+extern "C" int b2o_mbox_local_handle(b2o_ctx *c, void *handle64) {
+  if (!c || !handle64) B2O_FAIL(B2O_EARG, "null argument");
+  B2O_CUDA(cudaSetDevice(c->device));
+  if (!c->mbox) {
+    B2O_CUDA(cudaMalloc(&c->mbox, MBOX_BYTES));
+    B2O_CUDA(cudaMemset(c->mbox, 0, MBOX_BYTES));
+  }
+  cudaIpcMemHandle_t h;
+  B2O_CUDA(cudaIpcGetMemHandle(&h, c->mbox));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  return B2O_OK;
+}
+// handles: nranks x 64 bytes in rank order (this rank's own entry is ignored)
+extern "C" int b2o_mbox_connect(b2o_ctx *c, const void *handles, int nranks, int rank) {
+  if (!c || !handles) B2O_FAIL(B2O_EARG, "null argument");
+  if (nranks < 1 || nranks > MBOX_MAXR || rank < 0 || rank >= nranks) B2O_FAIL(B2O_EARG, "mailbox supports up to %d ranks", MBOX_MAXR);
+  if (!c->mbox) B2O_FAIL(B2O_EARG, "call b2o_mbox_local_handle first");
+  B2O_CUDA(cudaSetDevice(c->device));
+  for (int r = 0; r < nranks; ++r) {
+    if (r == rank) {
+      c->mbox_peers[r] = c->mbox;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)handles + 64 * r, 64);
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      B2O_FAIL(B2O_ECUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+    }
+    c->mbox_peers[r] = p;
+  }
+  c->nranks = nranks;
+  c->rank = rank;
+  c->mbox_epoch = 0;
+  c->mbox_ready = 1;
+  return B2O_OK;
+}
+extern "C" int b2o_mbox_disconnect(b2o_ctx *c) {
+  if (!c) B2O_FAIL(B2O_EARG, "null context");
+  if (c->mbox_ready) {
+    cudaStreamSynchronize(c->stream);
+    for (int r = 0; r < c->nranks; ++r)
+      if (r != c->rank && c->mbox_peers[r]) cudaIpcCloseMemHandle(c->mbox_peers[r]);
+  }
+  c->mbox_ready = 0;
+  return B2O_OK;
+}
+void b2o_mbox_fill(b2o_ctx *c, MboxDev *m) {
+  memset(m, 0, sizeof(*m));
+  m->nranks = 1;
+  m->ready = c->d_bar + 2;
+  if (!c->mbox_ready || c->nranks <= 1) return;
+  m->nranks = c->nranks;
+  m->rank = c->rank;
+  for (int r = 0; r < c->nranks; ++r) {
+    m->vals[r] = (double *)c->mbox_peers[r];
+    m->flags[r] = (unsigned long long *)((char *)c->mbox_peers[r] + MBOX_FLAGS_OFF);
+  }
+  m->epoch_base = c->mbox_epoch;
+}
+
 int b2o_allreduce_sum_f64(b2o_ctx *c, double *dptr, int count) {
   if (c->nranks <= 1 || !c->nccl_comm) return B2O_OK;
   // ncclFloat64 = 8, ncclSum = 0

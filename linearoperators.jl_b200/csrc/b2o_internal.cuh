@@ -72,7 +72,25 @@ struct b2o_ctx_s {
   // multi-GPU (row partition); comm is an ncclComm_t, resolved lazily through dlopen
   void *nccl_comm = nullptr;
   int nranks = 1, rank = 0;
+  // NVLink peer mailbox (in-kernel all-reduce of the small dot vectors): local buffer + IPC-mapped peers
+  void *mbox = nullptr;
+  void *mbox_peers[8] = {};
+  int mbox_ready = 0;
+  unsigned long long mbox_epoch = 0;
 };
+
+// ---- peer mailbox layout (one per GPU): vals[2][8][128] doubles, then flags[8] u64
+constexpr int MBOX_MAXV = 128, MBOX_MAXR = 8;
+constexpr size_t MBOX_FLAGS_OFF = sizeof(double) * 2 * MBOX_MAXR * MBOX_MAXV;
+constexpr size_t MBOX_BYTES = MBOX_FLAGS_OFF + sizeof(unsigned long long) * MBOX_MAXR;
+struct MboxDev {
+  double *vals[MBOX_MAXR];                 // vals region of every rank's mailbox (own entry = local memory)
+  unsigned long long *flags[MBOX_MAXR];
+  unsigned long long *ready;               // local "dots are published" flag for the other CTAs of this GPU
+  int nranks, rank;
+  unsigned long long epoch_base;           // epoch of the first all-reduce of this launch is epoch_base + 1
+};
+void b2o_mbox_fill(b2o_ctx *ctx, MboxDev *m);   // nranks = 1 when the mailbox is not connected
 
 int b2o_allreduce_sum_f64(b2o_ctx *ctx, double *dptr, int count);  // no-op when nranks == 1
 
@@ -159,6 +177,47 @@ __device__ __forceinline__ void grid_barrier(unsigned long long *ctr, unsigned l
     __threadfence();
   }
   __syncthreads();
+}
+
+// ---- NVLink peer mailbox: all-reduce (sum) of nv <= 128 doubles held in shared memory, executed by ONE warp per GPU.
+// Every rank stores its values into its slot of every peer's mailbox (plain stores over NVLink), publishes them with a
+// system-scope release of the epoch number, waits for the peers' epochs, and sums the slots in rank order -- the same order
+// on every GPU, so all ranks obtain bit-identical results.  Slots are double-buffered by epoch parity: a rank can be at most
+// one all-reduce ahead of the slowest peer.
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double *p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void mbox_allreduce_warp(const MboxDev &mb, unsigned long long epoch, double *vals, int nv) {
+  const int lane = threadIdx.x & 31;
+  const size_t slot = ((size_t)(epoch & 1ULL) * MBOX_MAXR + mb.rank) * MBOX_MAXV;
+  for (int r = 0; r < mb.nranks; ++r)
+    for (int v = lane; v < nv; v += 32) mb.vals[r][slot + v] = vals[v];
+  __threadfence_system();
+  __syncwarp();
+  if (lane < mb.nranks) st_release_sys_u64(mb.flags[lane] + mb.rank, epoch);
+  if (lane < mb.nranks)
+    while (ld_acquire_sys_u64(mb.flags[mb.rank] + lane) < epoch) { __nanosleep(20); }
+  __syncwarp();
+  const double *mine = mb.vals[mb.rank] + (size_t)(epoch & 1ULL) * MBOX_MAXR * MBOX_MAXV;
+  for (int v = lane; v < nv; v += 32) {
+    double s = 0.0;
+    for (int r = 0; r < mb.nranks; ++r) s += ld_relaxed_sys_f64(mine + (size_t)r * MBOX_MAXV + v);
+    vals[v] = s;
+  }
+  __syncwarp();
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -387,10 +387,15 @@ static int compact_launch_rows(b2o_qn *q, const CompactArgs &base, double *res, 
   if (a.n <= 0) return B2O_OK;
   const bool coop = mode == MODE_FUSED;
   if (coop) a.bar_target = c->bar_base + (unsigned long long)cfg.grid;
+  b2o_mbox_fill(c, &a.mbox);
+  if (!coop) a.mbox.nranks = 1;
   (void)stream_override;
   (void)use_override;
   int st = q->kind == 0 ? launch_compact_R<OP_LBFGS_FWD>(c, cfg, a, coop) : launch_compact_R<OP_LSR1>(c, cfg, a, coop);
-  if (st == B2O_OK && coop) c->bar_base += (unsigned long long)cfg.grid;
+  if (st == B2O_OK && coop) {
+    c->bar_base += (unsigned long long)cfg.grid;
+    if (a.mbox.nranks > 1) c->mbox_epoch += 1;
+  }
   return st;
 }
 
@@ -400,8 +405,8 @@ static int qn_apply_compact(b2o_qn *q, double *res, const double *x, double alph
   CompactArgs a;
   compact_columns(q, a, alpha, beta);
   if (a.ncols == 0) return compact_launch_rows(q, a, res, x, 0, q->n, MODE_PHASE2, 0);
-  if (c->nranks <= 1) return compact_launch_rows(q, a, res, x, 0, q->n, MODE_FUSED, 0);
-  // row-partitioned: local dots -> one all-reduce of ncols scalars -> combine
+  if (c->nranks <= 1 || c->mbox_ready) return compact_launch_rows(q, a, res, x, 0, q->n, MODE_FUSED, 0);   // mailbox: still ONE launch
+  // row-partitioned without the mailbox: local dots -> one NCCL all-reduce of ncols scalars -> combine
   B2O_TRY(compact_launch_rows(q, a, res, x, 0, q->n, MODE_PHASE1, 0));
   B2O_TRY(b2o_allreduce_sum_f64(c, c->d_dots, a.ncols));
   return compact_launch_rows(q, a, res, x, 0, q->n, MODE_PHASE2, 0);
@@ -462,13 +467,17 @@ static int qn_apply_twoloop(b2o_qn *q, double *res, const double *x, double alph
   a.coef_off = (uint32_t)cfg.L.coef_off;
   a.bar_off = (uint32_t)cfg.L.bar_off;
   const int nsweeps = 2 * na + 1;
-  if (c->nranks <= 1) {
+  b2o_mbox_fill(c, &a.mbox);
+  if (c->nranks <= 1 || c->mbox_ready) {
+    // single GPU, or row-partitioned with the NVLink mailbox: all 2A+1 sweeps and all 2A all-reduces in ONE launch
     a.sweep_begin = 0;
     a.sweep_end = nsweeps;
     a.bar_target = c->bar_base + (unsigned long long)cfg.grid;
     B2O_TRY(launch_twoloop_R(c, cfg, a, true));
     c->bar_base += (unsigned long long)cfg.grid * (unsigned long long)(2 * na);
+    if (a.mbox.nranks > 1) c->mbox_epoch += (unsigned long long)(2 * na);
   } else {
+    a.mbox.nranks = 1;
     // row-partitioned: one launch + one NCCL all-reduce per inner product (north_star / SURVEY §8e)
     for (int w = 0; w < nsweeps; ++w) {
       a.sweep_begin = w;

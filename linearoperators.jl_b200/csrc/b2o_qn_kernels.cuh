@@ -31,6 +31,7 @@ struct CompactArgs {
   int mode, stages, group;
   int accumulate;                    // split mode: dots[c] += this launch's partial (row-chunked host pipeline)
   uint32_t accs_off, coef_off, bar_off;
+  MboxDev mbox;                      // nranks > 1: the dots are all-reduced in-kernel through the NVLink peer mailbox
 };
 
 template <int R, int OP>
@@ -114,7 +115,45 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
   // ------------------------------------------------------------------ reduce the dots
   unsigned long long bar_target = p.bar_target;
   if (ncols > 0) {
-    if (p.mode == MODE_FUSED) {
+    if (p.mode == MODE_FUSED && p.mbox.nranks > 1) {
+      // row-partitioned, one launch per GPU: CTA 0 gathers the local partials, all-reduces them with the peers through the
+      // NVLink mailbox and publishes the global dots; the other CTAs wait for the publication instead of a second barrier.
+      const unsigned long long epoch = p.mbox.epoch_base + 1;
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        atomicAdd(p.bar, 1ULL);
+      }
+      if (blockIdx.x == 0) {
+        if (tid == 0) {
+          while (ld_acquire_u64(p.bar) < bar_target) { __nanosleep(32); }
+          __threadfence();
+        }
+        __syncthreads();
+        if (!is_producer) {
+          for (int c = warp; c < ncols; c += B2O_CONS_WARPS) {
+            double s = 0.0;
+            for (int b = lane; b < (int)grid; b += 32) s += __ldcg(&p.partials[(size_t)b * ncols + c]);
+            s = warp_sum(s);
+            if (lane == 0) coef[c] = s;
+          }
+        }
+        __syncthreads();
+        if (warp == 0) mbox_allreduce_warp(p.mbox, epoch, coef, ncols);
+        __syncthreads();
+        for (int c = tid; c < ncols; c += B2O_NTHREADS) p.dots[c] = coef[c];
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) st_release_gpu_u64(p.mbox.ready, epoch);
+      } else {
+        if (tid == 0)
+          while (ld_acquire_u64(p.mbox.ready) < epoch) { __nanosleep(32); }
+        __syncthreads();
+        for (int c = tid; c < ncols; c += B2O_NTHREADS) coef[c] = __ldcg(&p.dots[c]);
+        __syncthreads();
+      }
+      bar_target += gridDim.x;
+    } else if (p.mode == MODE_FUSED) {
       grid_barrier(p.bar, bar_target);
       bar_target += gridDim.x;
       if (!is_producer) {
@@ -254,6 +293,7 @@ struct TwoLoopArgs {
   int stages;
   int sweep_begin, sweep_end;    // sweeps [begin,end) of 0..2A run in this launch (fused: 0..2A+1)
   uint32_t coef_off, bar_off;
+  MboxDev mbox;                  // nranks > 1: each inner product is all-reduced in-kernel through the NVLink peer mailbox
 };
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -270,6 +310,7 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_kernel(const __gri
   rg.empty = rg.full + p.stages;
   rg.stages = p.stages;
   __shared__ double s_dot;
+  __shared__ double s_mb[2];
   __shared__ bool s_is_last;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -281,6 +322,7 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_kernel(const __gri
     }
     mbar_fence_init();
   }
+  unsigned long long mb_epoch = p.mbox.epoch_base;
   const int A = p.nact;
   const bool fused = (p.sweep_end - p.sweep_begin) > 1 || (p.sweep_begin == 0 && p.sweep_end == 2 * A + 1);
   if (p.sweep_begin > 0) {
@@ -421,7 +463,43 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_kernel(const __gri
       for (int wv = 0; wv < B2O_CONS_WARPS; ++wv) s += sred[wv];
       p.partials[blockIdx.x] = s;
     }
-    if (fused) {
+    if (fused && p.mbox.nranks > 1) {
+      // one inner product, all-reduced across GPUs without leaving the kernel (NVLink peer mailbox)
+      const unsigned long long epoch = ++mb_epoch;
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        atomicAdd(p.bar, 1ULL);
+      }
+      if (blockIdx.x == 0) {
+        if (tid == 0) {
+          while (ld_acquire_u64(p.bar) < bar_target) { __nanosleep(32); }
+          __threadfence();
+        }
+        __syncthreads();
+        if (warp == 0) {
+          double s = 0.0;
+          for (int b = lane; b < (int)grid; b += 32) s += __ldcg(&p.partials[b]);
+          s = warp_sum(s);
+          if (lane == 0) s_mb[0] = s;
+          __syncwarp();
+          mbox_allreduce_warp(p.mbox, epoch, s_mb, 1);
+          if (lane == 0) {
+            s_dot = s_mb[0];
+            p.dots[0] = s_mb[0];
+            __threadfence();
+            st_release_gpu_u64(p.mbox.ready, epoch);
+          }
+        }
+      } else {
+        if (tid == 0) {
+          while (ld_acquire_u64(p.mbox.ready) < epoch) { __nanosleep(32); }
+          s_dot = __ldcg(&p.dots[0]);
+        }
+      }
+      bar_target += gridDim.x;
+      __syncthreads();
+    } else if (fused) {
       grid_barrier(p.bar, bar_target);
       bar_target += gridDim.x;
       if (warp == 0) {
