@@ -14,7 +14,7 @@ from .context import Context, default_context  # noqa: F401
 from .graph import FusedOperator, fuse  # noqa: F401
 from .kron import KronOperator, kron  # noqa: F401
 from .qn import (InverseLBFGSOperator, LBFGSOperator, LSR1Operator, diag, diag_, push_)  # noqa: F401
-from .special_operators import (BlockDiagonalOperator, getindex, opDiagonal, opExtension, opEye, opHouseholder,  # noqa: F401
+from .special_operators import (BlockDiagonalOperator, LocalBlockOfDiagonal, getindex, opDiagonal, opExtension, opEye, opHouseholder,  # noqa: F401
                                 opOnes, opRestriction, opZeros)
 
 __version__ = "0.1.0"

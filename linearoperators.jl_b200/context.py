@@ -96,7 +96,14 @@ class Context:
         gathered = [None] * world
         dist.all_gather_object(gathered, bytes(mine), group=group)
         allh = (ctypes.c_ubyte * (64 * world)).from_buffer_copy(b"".join(gathered))
-        _lib.check(self.lib.b2o_mbox_connect(self.handle, allh, world, rank))
+        st = self.lib.b2o_mbox_connect(self.handle, allh, world, rank)
+        err = None if st == 0 else _lib.last_error()
+        # all-or-nothing: a rank that could not map its peers would otherwise wait on NCCL while the others spin on the mailbox
+        oks = [None] * world
+        dist.all_gather_object(oks, err, group=group)
+        if any(e is not None for e in oks):
+            self.lib.b2o_mbox_disconnect(self.handle)
+            raise _lib.B2OError("NVLink mailbox unavailable on some rank: %s" % [e for e in oks if e][0])
         dist.barrier(group)
         self.mailbox = True
 

@@ -277,3 +277,15 @@ def BlockDiagonalOperator(*ops, S=None):
     out = LinearOperator(eltype(ops[0]), nrow, ncol, symm, herm, prod_, tprod_, ctprod_, S=S)
     out.ctx = _ctx_of(ops[0]) if S.kind == "cuda" else None
     return out
+
+
+def LocalBlockOfDiagonal(op, rank, world):
+    """BlockDiagonalOperator with ONE BLOCK PER GPU (one process per GPU): rank r owns block r and the r-th slab of x and y,
+    so `mul!` of the global block-diagonal operator is just the local block applied to the local slab -- no collective
+    (src/special-operators.jl:258-267 evaluates the blocks one after the other on one device).  The block must live on a
+    context WITHOUT a communicator (its inner products are local to the block); this helper checks that and returns it."""
+    ctx = _ctx_of(op)
+    if ctx is not None and getattr(ctx, "nranks", 1) != 1:
+        raise LinearOperatorException("a block of a block-diagonal operator must use a local (non row-partitioned) context")
+    op.block_rank, op.block_world = int(rank), int(world)
+    return op

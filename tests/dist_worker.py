@@ -119,6 +119,38 @@ def main():
         check_qn(expect_one_launch=True)               # NVLink peer mailbox: ONE persistent launch per GPU
         ctx.disconnect_mailbox()
         check_qn(expect_one_launch=False)
+        # BlockDiagonalOperator, one block per GPU: a LOCAL context (no communicator), block r on rank r, no collective at all
+        lctx = lo.Context(dev.index)
+        nb_ = 1000 + 37 * rank
+        blk = lo.LocalBlockOfDiagonal(lo.LBFGSOperator(nb_, mem=3, ctx=lctx), rank, world)
+        oblk = orc.LBFGS(nb_, mem=3)
+        for i in range(4):
+            s = orc.uniform(nb_, 900 + 10 * rank + i)
+            y = s + 0.1 * orc.uniform(nb_, 950 + 10 * rank + i)
+            lo.push_(blk, t(s), t(y))
+            oblk.push(s, y)
+        xb = orc.uniform(nb_, 77 + rank)
+        yb = (blk * t(xb)).cpu().numpy()
+        assert np.linalg.norm(yb - oblk.apply(xb)) <= 1e-12 * np.linalg.norm(yb)
+        parts = [None] * world
+        dist.all_gather_object(parts, (xb, yb))
+        if rank == 0:       # the gathered slabs are the global block-diagonal product
+            blocks = []
+            for r in range(world):
+                nbr = 1000 + 37 * r
+                ob = orc.LBFGS(nbr, mem=3)
+                for i in range(4):
+                    s = orc.uniform(nbr, 900 + 10 * r + i)
+                    ob.push(s, s + 0.1 * orc.uniform(nbr, 950 + 10 * r + i))
+                blocks.append(orc.wrap_qn(ob))
+            bd = orc.block_diagonal(*blocks)
+            xg, yg = np.concatenate([pp[0] for pp in parts]), np.concatenate([pp[1] for pp in parts])
+            assert np.linalg.norm(yg - bd(xg)) <= 1e-12 * np.linalg.norm(yg)
+        try:
+            lo.LocalBlockOfDiagonal(lo.LBFGSOperator(10, ctx=ctx), rank, world)
+            raise AssertionError("row-partitioned context must be rejected")
+        except lo.LinearOperatorException:
+            pass
         # leaf operators with reductions
         h = orc.uniform(n, 3)
         h /= np.linalg.norm(h)
