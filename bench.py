@@ -84,8 +84,7 @@ def cpu_reference(n_cpu, mem, steps, warmup, inverse=False):
     import numpy as np
     import oracle
     oracle.build()
-    threads = oracle.max_threads()
-    oracle.set_mode(False, threads)
+    avail = oracle.max_threads()
     op = oracle.LBFGS(n_cpu, mem=mem, inverse=inverse)
     for k in range(mem):
         for which in (("s", "y") if inverse else ("a", "b")):
@@ -94,6 +93,25 @@ def cpu_reference(n_cpu, mem, steps, warmup, inverse=False):
     op.set_state(1, 0.5)
     x = oracle.uniform(n_cpu, 7)
     res = np.empty(n_cpu)
+    # "all the host threads it can use": calibrate the thread count (all / half / quarter of the usable CPUs -- SMT siblings and
+    # container quotas make "all" slower on some hosts) with one apply each, then time the best
+    best_t, best_dt = avail, None
+    cands = sorted({t for t in (avail, avail // 2, avail // 4, 16, 8, 1) if 1 <= t <= avail}, reverse=True)
+    for t in cands:
+        oracle.set_mode(False, t)
+        dts = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            op.apply(x, res=res)
+            dts.append(time.perf_counter() - t0)
+            if dts[-1] > 10.0:
+                break
+        if best_dt is None or min(dts) < best_dt:
+            best_t, best_dt = t, min(dts)
+    threads = best_t
+    oracle.set_mode(False, threads)
+    if best_dt * (steps + warmup) > 60.0:
+        steps, warmup = max(1, int(30.0 / best_dt)), 0
     for _ in range(warmup):
         op.apply(x, res=res)
     t0 = time.perf_counter()
@@ -102,8 +120,8 @@ def cpu_reference(n_cpu, mem, steps, warmup, inverse=False):
     dt = (time.perf_counter() - t0) / steps
     oracle.set_mode(True, 1)
     return {"value": alg_bytes(n_cpu, mem, inverse) / dt / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
-            "sample": "%s apply at n=%d rows (1/%d of the workload), mem=%d, %d timed applies, %.3f s/apply" %
-                      ("inverse" if inverse else "forward", n_cpu, max(1, round(1e8 / n_cpu)), mem, steps, dt),
+            "sample": "%s apply at n=%d rows (1/%d of the workload), mem=%d, %d timed applies, %.3f s/apply, %d threads of %d usable CPUs (fastest of a thread-count sweep)" %
+                      ("inverse" if inverse else "forward", n_cpu, max(1, round(1e8 / n_cpu)), mem, steps, dt, threads, avail),
             "applies_per_s": 1.0 / dt, "ms_per_apply": dt * 1e3}
 
 

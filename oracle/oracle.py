@@ -25,6 +25,21 @@ _lib = None
 c_dp = ctypes.POINTER(ctypes.c_double)
 
 
+def usable_cpus():
+    """CPUs this process may really use: affinity mask capped by the cgroup CPU quota (containers)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = max(1, min(n, int(-(-int(q) // int(per)))))
+    except Exception:
+        pass
+    return n
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -76,7 +91,7 @@ def set_mode(accurate=True, threads=1):
 
 
 def max_threads():
-    return lib().orc_max_threads()
+    return max(1, min(lib().orc_max_threads(), usable_cpus()))
 
 
 def uniform(n, seed, lo=0.0, hi=1.0):
