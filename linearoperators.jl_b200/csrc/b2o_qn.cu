@@ -21,6 +21,11 @@ struct b2o_qn_s {
   double *d_alpha = nullptr;                                      // [mem] device copy of data.α (inverse)
   std::vector<double> ys, aux;  // aux: inverse L-BFGS α (host mirror, lazily), forward norm_b, L-SR1 as
   int ins0 = 0;
+  // optional compact-representation inverse apply: Gram matrices by ring slot, device middle matrix
+  bool inv_compact = false, w_dirty = true;
+  std::vector<double> SY, YY;   // [mem*mem]: SY[i*mem+j] = s_i·y_j, YY[i*mem+j] = y_i·y_j
+  double *d_W = nullptr;        // [(2*mem)^2]
+  double *h_W = nullptr;        // pinned staging
   double *col(double *base, int k0) const { return base + (size_t)k0 * (size_t)pitch; }
 };
 
@@ -194,6 +199,8 @@ extern "C" int b2o_qn_destroy(b2o_qn *q) {
   cudaFree(q->q);
   cudaFree(q->tmp);
   cudaFree(q->d_alpha);
+  if (q->d_W) cudaFree(q->d_W);
+  if (q->h_W) cudaFreeHost(q->h_W);
   delete q;
   return B2O_OK;
 }
@@ -338,7 +345,16 @@ static void compact_columns(const b2o_qn *q, CompactArgs &a, double alpha, doubl
   int slots[B2O_MAX_MEM];
   const int na = active_old_to_new(q, slots);
   memset(&a, 0, sizeof(a));
-  if (q->kind == 0) {
+  if (q->kind == 0 && q->inverse) {
+    // compact inverse: columns [s_old..s_new, y_old..y_new]
+    for (int i = 0; i < na; ++i) {
+      a.cols[i] = q->col(q->S, slots[i]);
+      a.cols[na + i] = q->col(q->Y, slots[i]);
+      a.cdiv[i] = a.cdiv[na + i] = 1.0;
+    }
+    a.ncols = 2 * na;
+    a.W = q->d_W;
+  } else if (q->kind == 0) {
     for (int i = 0; i < na; ++i) {
       a.cols[2 * i] = q->col(q->A, slots[i]);
       a.cols[2 * i + 1] = q->col(q->B, slots[i]);
@@ -391,7 +407,9 @@ static int compact_launch_rows(b2o_qn *q, const CompactArgs &base, double *res, 
   if (!coop) a.mbox.nranks = 1;
   (void)stream_override;
   (void)use_override;
-  int st = q->kind == 0 ? launch_compact_R<OP_LBFGS_FWD>(c, cfg, a, coop) : launch_compact_R<OP_LSR1>(c, cfg, a, coop);
+  int st = (q->kind == 0 && q->inverse) ? launch_compact_R<OP_INV_COMPACT>(c, cfg, a, coop)
+           : q->kind == 0             ? launch_compact_R<OP_LBFGS_FWD>(c, cfg, a, coop)
+                                      : launch_compact_R<OP_LSR1>(c, cfg, a, coop);
   if (st == B2O_OK && coop) {
     c->bar_base += (unsigned long long)cfg.grid;
     if (a.mbox.nranks > 1) c->mbox_epoch += 1;
@@ -489,9 +507,114 @@ static int qn_apply_twoloop(b2o_qn *q, double *res, const double *x, double alph
   return B2O_OK;
 }
 
+// W' = diag(I, γI) · [[R^{-T}(D + γ YᵀY) R^{-1}, -R^{-T}], [-R^{-1}, 0]] · diag(I, γI) for the active pairs, oldest -> newest
+// (Byrd, Nocedal, Schnabel 1994, eq. 4.x: H = γI + [S γY] W [Sᵀ; γYᵀ]); small (2A x 2A), computed on the host in long double.
+static int build_inverse_W(b2o_qn *q) {
+  b2o_ctx *c = q->ctx;
+  int sl[B2O_MAX_MEM];
+  const int A = active_old_to_new(q, sl), m = q->mem, N = 2 * A;
+  if (A == 0) {
+    q->w_dirty = false;
+    return B2O_OK;
+  }
+  const long double g = q->scaling ? (long double)q->gamma : 1.0L;
+  std::vector<long double> R((size_t)A * A, 0.0L), Ri((size_t)A * A, 0.0L), M((size_t)A * A, 0.0L), T((size_t)A * A, 0.0L);
+  for (int i = 0; i < A; ++i)
+    for (int j = i; j < A; ++j) R[(size_t)i * A + j] = q->SY[(size_t)sl[i] * m + sl[j]];
+  for (int j = 0; j < A; ++j) {       // Ri = R^{-1} (upper triangular), column by column
+    for (int i = A - 1; i >= 0; --i) {
+      long double s = (i == j) ? 1.0L : 0.0L;
+      for (int k = i + 1; k < A; ++k) s -= R[(size_t)i * A + k] * Ri[(size_t)k * A + j];
+      Ri[(size_t)i * A + j] = s / R[(size_t)i * A + i];
+    }
+  }
+  for (int i = 0; i < A; ++i)
+    for (int j = 0; j < A; ++j)
+      M[(size_t)i * A + j] = g * (long double)q->YY[(size_t)sl[i] * m + sl[j]] + (i == j ? (long double)q->SY[(size_t)sl[i] * m + sl[i]] : 0.0L);
+  for (int i = 0; i < A; ++i)         // T = M * Ri
+    for (int j = 0; j < A; ++j) {
+      long double s = 0.0L;
+      for (int k = 0; k < A; ++k) s += M[(size_t)i * A + k] * Ri[(size_t)k * A + j];
+      T[(size_t)i * A + j] = s;
+    }
+  double *W = q->h_W;
+  for (int i = 0; i < A; ++i)
+    for (int j = 0; j < A; ++j) {
+      long double s = 0.0L;           // (Ri^T * T)[i][j]
+      for (int k = 0; k < A; ++k) s += Ri[(size_t)k * A + i] * T[(size_t)k * A + j];
+      W[(size_t)i * N + j] = (double)s;                                    // S-S block
+      W[(size_t)i * N + A + j] = (double)(-g * Ri[(size_t)j * A + i]);     // S-Y block: -R^{-T} (times γ on the Y side)
+      W[(size_t)(A + i) * N + j] = (double)(-g * Ri[(size_t)i * A + j]);   // Y-S block: -R^{-1}
+      W[(size_t)(A + i) * N + A + j] = 0.0;
+    }
+  B2O_CUDA(cudaMemcpyAsync(q->d_W, W, sizeof(double) * N * N, cudaMemcpyHostToDevice, c->stream));
+  B2O_CUDA(cudaStreamSynchronize(c->stream));   // h_W is reused by the next rebuild
+  q->w_dirty = false;
+  return B2O_OK;
+}
+
 static int qn_apply_dev(b2o_qn *q, double *res, const double *x, double alpha, double beta) {
-  if (q->kind == 0 && q->inverse) return qn_apply_twoloop(q, res, x, alpha, beta);
+  if (q->kind == 0 && q->inverse) {
+    if (!q->inv_compact) return qn_apply_twoloop(q, res, x, alpha, beta);
+    if (q->w_dirty) B2O_TRY(build_inverse_W(q));
+  }
   return qn_apply_compact(q, res, x, alpha, beta);
+}
+
+// Gram entries involving ring slot `k` (after s_k, y_k were stored): s_k·y_j, s_j·y_k, y_k·y_j for every slot j
+static int update_gram(b2o_qn *q, int k) {
+  b2o_ctx *c = q->ctx;
+  const int m = q->mem;
+  const double *sk = q->col(q->S, k), *yk = q->col(q->Y, k);
+  for (int j0 = 0; j0 < m; j0 += 2) {
+    const double *u[8], *v[8];
+    int np = 0, idx[8][2];
+    for (int j = j0; j < std::min(m, j0 + 2); ++j) {
+      u[np] = sk; v[np] = q->col(q->Y, j); idx[np][0] = 0; idx[np][1] = j; np++;   // s_k·y_j
+      u[np] = q->col(q->S, j); v[np] = yk; idx[np][0] = 1; idx[np][1] = j; np++;   // s_j·y_k
+      u[np] = yk; v[np] = q->col(q->Y, j); idx[np][0] = 2; idx[np][1] = j; np++;   // y_k·y_j
+    }
+    double h[8];
+    B2O_TRY(b2o_pair_dots(c, np, u, v, q->n, c->d_dots + 300));
+    B2O_TRY(b2o_read_scalars(c, c->d_dots + 300, np, h));
+    for (int p = 0; p < np; ++p) {
+      const int j = idx[p][1];
+      if (idx[p][0] == 0) q->SY[(size_t)k * m + j] = h[p];
+      else if (idx[p][0] == 1) q->SY[(size_t)j * m + k] = h[p];
+      else q->YY[(size_t)k * m + j] = q->YY[(size_t)j * m + k] = h[p];
+    }
+  }
+  q->w_dirty = true;
+  return B2O_OK;
+}
+
+// "inverse_mode": 0 = two-loop recursion (reference algorithm, default), 1 = compact representation (half the DRAM traffic,
+// ONE all-reduce instead of 2m dependent ones; different rounding, same operator)
+extern "C" int b2o_qn_set_option(b2o_qn *q, const char *key, int64_t value) {
+  if (!q || !key) B2O_FAIL(B2O_EARG, "null argument");
+  if (!strcmp(key, "inverse_mode")) {
+    if (!(q->kind == 0 && q->inverse)) B2O_FAIL(B2O_EARG, "inverse_mode applies to InverseLBFGSOperator");
+    if (value != 0 && value != 1) B2O_FAIL(B2O_EARG, "inverse_mode must be 0 (two-loop) or 1 (compact)");
+    b2o_ctx *c = q->ctx;
+    B2O_CUDA(cudaSetDevice(c->device));
+    if (value == 1 && !q->inv_compact) {
+      const int m = q->mem;
+      if (!q->d_W) {
+        B2O_CUDA(cudaMalloc(&q->d_W, sizeof(double) * 4 * m * m));
+        B2O_CUDA(cudaMallocHost(&q->h_W, sizeof(double) * 4 * m * m));
+      }
+      q->SY.assign((size_t)m * m, 0.0);
+      q->YY.assign((size_t)m * m, 0.0);
+      q->inv_compact = true;
+      for (int k = 0; k < m; ++k)
+        if (q->ys[k] != 0) B2O_TRY(update_gram(q, k));   // pairs pushed before the mode was enabled
+      q->w_dirty = true;
+    } else if (value == 0) {
+      q->inv_compact = false;
+    }
+    return B2O_OK;
+  }
+  B2O_FAIL(B2O_EARG, "unknown option '%s'", key);
 }
 
 extern "C" int b2o_qn_apply(b2o_qn *q, void *res, int64_t res_len, const void *x, int64_t x_len, double alpha,
@@ -600,7 +723,8 @@ extern "C" int b2o_qn_apply_bytes(b2o_qn *q, double beta, double *bytes) {
   int slots[B2O_MAX_MEM];
   const int na = active_old_to_new(q, slots);
   double per_row;
-  if (q->kind == 0 && q->inverse) per_row = na > 0 ? 8.0 * na + 2.0 : 2.0;   // (8m+2) n E   SURVEY App. A
+  if (q->kind == 0 && q->inverse && q->inv_compact) per_row = na > 0 ? 4.0 * na + 3.0 : 2.0;   // compact: (4m+3) n E
+  else if (q->kind == 0 && q->inverse) per_row = na > 0 ? 8.0 * na + 2.0 : 2.0;   // (8m+2) n E   SURVEY App. A
   else if (q->kind == 0) per_row = na > 0 ? 4.0 * na + 3.0 : 2.0;            // (4m+3) n E
   else per_row = na > 0 ? 2.0 * na + 3.0 : 2.0;                              // (2m+3) n E
   if (beta != 0.0) per_row += 1.0;
@@ -703,6 +827,8 @@ static int lbfgs_push_common(b2o_qn *q, const double *s, const double *y, double
     }
     B2O_CUDA(cudaGetLastError());
   }
+  if (q->inverse && q->inv_compact) B2O_TRY(update_gram(q, ins));
+  q->w_dirty = true;
   q->ins0 = pmod(ins + 1, mem);                                                                 // :253
   return B2O_OK;
 }
@@ -965,6 +1091,11 @@ extern "C" int b2o_qn_reset(b2o_qn *q) {
   if (q->kind == 1 || q->inverse) std::fill(q->aux.begin(), q->aux.end(), 0.0);
   q->gamma = 1.0;
   q->ins0 = 0;
+  q->w_dirty = true;
+  if (q->inv_compact) {
+    std::fill(q->SY.begin(), q->SY.end(), 0.0);
+    std::fill(q->YY.begin(), q->YY.end(), 0.0);
+  }
   return B2O_OK;
 }
 

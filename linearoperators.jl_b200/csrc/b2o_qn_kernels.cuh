@@ -10,7 +10,7 @@
 #pragma once
 #include "b2o_stream.cuh"
 
-enum { OP_LBFGS_FWD = 0, OP_LSR1 = 1 };
+enum { OP_LBFGS_FWD = 0, OP_LSR1 = 1, OP_INV_COMPACT = 2 };
 enum { MODE_FUSED = 0, MODE_PHASE1 = 1, MODE_PHASE2 = 2 };
 
 struct CompactArgs {
@@ -32,6 +32,7 @@ struct CompactArgs {
   int accumulate;                    // split mode: dots[c] += this launch's partial (row-chunked host pipeline)
   uint32_t accs_off, coef_off, bar_off;
   MboxDev mbox;                      // nranks > 1: the dots are all-reduced in-kernel through the NVLink peer mailbox
+  const double *W;                   // OP_INV_COMPACT: ncols x ncols middle matrix (row-major), coefficients = W * dots
 };
 
 template <int R, int OP>
@@ -194,6 +195,19 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
     return;
   }
 
+  if (OP == OP_INV_COMPACT && ncols > 0) {
+    // compact representation (Byrd-Nocedal-Schnabel): coefficients = W * [Sᵀx; Yᵀx]; every CTA does the tiny matvec
+    // redundantly in the same order -> identical coefficients everywhere
+    for (int j = tid; j < ncols; j += B2O_NTHREADS) {
+      double s = 0.0;
+      for (int k = 0; k < ncols; ++k) s = fma(__ldcg(&p.W[(size_t)j * ncols + k]), coef[k], s);
+      accs[j] = s;
+    }
+    __syncthreads();
+    for (int j = tid; j < ncols; j += B2O_NTHREADS) coef[j] = accs[j];
+    __syncthreads();
+  }
+
   // ------------------------------------------------------------------ phase 2: combine and write res
   if (is_producer) {
     if (lane == 0) {
@@ -214,6 +228,10 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
         // q .= x ; scaling && (q ./= γ)                                   src/lbfgs.jl:183-186
 #pragma unroll
         for (int j = 0; j < EPT; ++j) q[j] = p.scaling ? xn[j] / gamma : xn[j];
+      } else if (OP == OP_INV_COMPACT) {
+        // H0 x = γ x (γ = 1 without scaling)
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) q[j] = p.scaling ? xn[j] * gamma : xn[j];
       } else {
         // q .= α .* x ./ γ (.+ β .* q)                                    src/lsr1.jl:92-96
 #pragma unroll
@@ -248,8 +266,9 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
         for (int j = 0; j < EPT; ++j) q[j] = (beta != 0.0) ? alpha * q[j] + beta * rold[j] : alpha * q[j];  // :197-201
       } else {
         for (int c = 0; c < ncols; ++c) {
-          // ax = α * dot(a[k], x) / as[k];  q[j] += ax * a[k][j]          src/lsr1.jl:101-104
-          const double ax = (alpha * coef[c]) / p.cdiv[c];
+          // LSR1: ax = α * dot(a[k], x) / as[k];  q[j] += ax * a[k][j]    src/lsr1.jl:101-104
+          // compact inverse: q += c_j * col_j
+          const double ax = (OP == OP_INV_COMPACT) ? coef[c] : (alpha * coef[c]) / p.cdiv[c];
           mbar_wait(&rg.full[pos.slot], pos.par);
           const double2 *A = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R);
 #pragma unroll
@@ -260,6 +279,10 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
           }
           consumer_release(rg, pos.slot);
           pos.advance();
+        }
+        if (OP == OP_INV_COMPACT) {
+#pragma unroll
+          for (int j = 0; j < EPT; ++j) q[j] = (beta != 0.0) ? alpha * q[j] + beta * rold[j] : alpha * q[j];
         }
       }
       store_user_tile<R>(p.res, t * R, p.n, p.res_al16, q);

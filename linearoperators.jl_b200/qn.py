@@ -101,6 +101,11 @@ class AbstractQuasiNewtonOperator(AbstractLinearOperator):
         _lib.check(self.ctx.lib.b2o_qn_apply_bytes(self.handle, float(beta), ctypes.byref(out)))
         return out.value
 
+    def set_option(self, key, value):
+        """e.g. set_option("inverse_mode", 1): compact-representation apply for InverseLBFGSOperator"""
+        _lib.check(self.ctx.lib.b2o_qn_set_option(self.handle, key.encode(), int(value)))
+        return self
+
     def _reset_state(self):
         _lib.check(self.ctx.lib.b2o_qn_reset(self.handle))
 
@@ -120,9 +125,15 @@ class LBFGSOperator(AbstractQuasiNewtonOperator):
         self.ctprod_ = self.prod_
 
 
-def InverseLBFGSOperator(n, **kw):
+def InverseLBFGSOperator(n, compact=False, **kw):
+    """InverseLBFGSOperator(n; mem, scaling, damped, σ₂, σ₃) (src/lbfgs.jl:112-160).  compact=True switches the apply from the
+    reference's two-loop recursion to the mathematically identical compact representation (half the DRAM traffic, one
+    all-reduce instead of 2m): an extension, not the reference algorithm -- rounding differs."""
     kw.pop("inverse", None)
-    return LBFGSOperator(n, inverse=True, **kw)
+    op = LBFGSOperator(n, inverse=True, **kw)
+    if compact:
+        op.set_option("inverse_mode", 1)
+    return op
 
 
 class LSR1Operator(AbstractQuasiNewtonOperator):

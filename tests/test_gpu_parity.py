@@ -715,3 +715,37 @@ def test_kron_batch_and_launch_count(lo, ctx, orc):
     assert K.flops() == 2.0 * p * q * n + 2.0 * p * n * m
     with pytest.raises(lo.B2OError):
         lo.kron(A[:, :-1].contiguous(), B, ctx=ctx)                                  # dims must be multiples of 8
+
+
+# ---------------------------------------------------------------- §8f.1: compact-representation inverse apply (extension)
+@pytest.mark.parametrize("n,mem,npush,scaling", [(10, 5, 3, False), (1000, 5, 7, True), (100003, 10, 12, True), (75776, 20, 20, True)])
+def test_inverse_compact_representation(lo, ctx, orc, n, mem, npush, scaling):
+    """same operator as the two-loop recursion (src/lbfgs.jl:117-154), different algorithm: agreement to ~1e-10 on these
+    (correlated, hence ill-conditioned SᵀY) pairs, H*B ≈ I, and switching modes back and forth on one handle"""
+    H = lo.InverseLBFGSOperator(n, mem=mem, scaling=scaling, compact=True, ctx=ctx)
+    B = lo.LBFGSOperator(n, mem=mem, scaling=scaling, ctx=ctx)
+    o = orc.LBFGS(n, mem=mem, scaling=scaling, inverse=True)
+    for i in range(npush):
+        s = ctx.uniform(n, 100 + i)
+        y = s + 0.1 * ctx.uniform(n, 200 + i)
+        lo.push_(H, s, y)
+        lo.push_(B, s, y)
+        o.push(host(s), host(y))
+    x, r0 = ctx.uniform(n, 7), ctx.uniform(n, 8)
+    for alpha, beta in [(1.0, 0.0), (1.5, -0.25)]:
+        res, ref = r0.clone(), host(r0).copy()
+        l0 = ctx.launch_count()
+        lo.mul_(res, H, x, alpha, beta)
+        assert ctx.launch_count() - l0 == 1
+        o.apply(host(x), alpha, beta, res=ref)
+        assert rel(host(res), ref) <= 1e-9, rel(host(res), ref)
+    back = H * (B * x)
+    assert rel(host(back), host(x)) <= 1e-8
+    H.set_option("inverse_mode", 0)
+    two = host(H * x)
+    assert rel(two, o.apply(host(x))) <= TOL
+    H.set_option("inverse_mode", 1)                                          # Gram matrices are rebuilt from the stored pairs
+    assert rel(host(H * x), two) <= 1e-9
+    assert H.apply_bytes() == (4 * min(mem, npush) + 3) * 8 * n
+    lo.reset_(H)
+    assert np.array_equal(host(H * x), host(x))

@@ -54,6 +54,30 @@ def main():
     big = "--small" not in sys.argv
     n = 10**8 if big else 10**6
     flush = torch.empty(256 * 2**20 // 8, dtype=torch.float64, device="cuda")
+    if only == ["invc"]:
+        v, res = ctx.uniform(n, 7), ctx.empty(n)
+        for m in (10, 20):
+            H = lo.InverseLBFGSOperator(n, mem=m, ctx=ctx)
+            t0 = time.perf_counter()
+            for i in range(m):
+                s = ctx.uniform(n, 100 + i)
+                y = s + 0.1 * ctx.uniform(n, 200 + i)
+                lo.push_(H, s, y)
+            del s, y
+            line("InverseLBFGS(mem=%d) two-loop (reference algorithm)" % m, timeit(lambda: lo.mul_(res, H, v), 10), (8 * m + 2) * 8.0 * n)
+            two = res.clone()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            H.set_option("inverse_mode", 1)
+            torch.cuda.synchronize()
+            t_gram = time.perf_counter() - t0
+            ms = timeit(lambda: lo.mul_(res, H, v), 10)
+            diff = float(torch.linalg.norm(res - two) / torch.linalg.norm(two))
+            line("InverseLBFGS(mem=%d) compact representation (extension)" % m, ms, (4 * m + 3) * 8.0 * n,
+                 two_loop_equivalent_GBps=round((8 * m + 2) * 8.0 * n / ms / 1e6, 1), rel_diff_vs_two_loop=diff, gram_rebuild_s=round(t_gram, 3))
+            del H, two
+            torch.cuda.empty_cache()
+        return
     if only == ["kron"]:
         import oracle as orc
         orc.set_mode(True, 1)
