@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Small invocation of every kernel family, meant to run under compute-sanitizer (memcheck / synccheck / initcheck)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import linearoperators_jl_b200 as lo  # noqa: E402
+
+
+def main():
+    ctx = lo.default_context(0)
+    n = 2 * 4096 + 333
+    x, r = ctx.uniform(n, 7), ctx.uniform(n, 8)
+    d = ctx.uniform(n, 1)
+    h = ctx.uniform(n, 3)
+    h /= float(np.sqrt(ctx.dot(h, h)))
+    for op in (lo.opDiagonal(d), lo.opEye(n), lo.opZeros(n, n), lo.opOnes(n, n), lo.opHouseholder(h), lo.opEye(n + 5, n),
+               lo.opDiagonal(n + 3, n, d)):
+        res = ctx.uniform(lo.size(op, 1), 9)
+        lo.mul_(res, op, x, 1.5, 0.5)
+        lo.mul_(res, op, x)
+    P = lo.opRestriction(np.random.default_rng(0).integers(1, n + 1, size=1000), n)
+    lo.transpose(P) * (P * x)
+    for kind in ("fwd", "inv", "lsr1", "invc"):
+        if kind == "lsr1":
+            g = lo.LSR1Operator(n, mem=3, ctx=ctx)
+        else:
+            g = lo.LBFGSOperator(n, mem=3, inverse=kind in ("inv", "invc"), ctx=ctx)
+        if kind == "invc":
+            g.set_option("inverse_mode", 1)
+        for i in range(4):
+            s = ctx.uniform(n, 100 + i, -1.0, 1.0) if kind == "lsr1" else ctx.uniform(n, 100 + i)
+            y = (2.0 * s + 0.3 * ctx.uniform(n, 200 + i, -1.0, 1.0)) if kind == "lsr1" else s + 0.1 * ctx.uniform(n, 200 + i)
+            lo.push_(g, s, y)
+        lo.mul_(r, g, x, 1.5, -0.5)
+        lo.mul_(r, g, x[:n].clone())
+        if kind in ("fwd", "lsr1"):
+            lo.diag(g)
+        xh, rh = x.cpu().pin_memory(), torch.empty(n, dtype=torch.float64).pin_memory()
+        g.apply_host(rh, xh)
+    f = lo.fuse(lo.opHouseholder(h) * lo.opDiagonal(d) + 0.1 * lo.opEye(n))
+    for jit in (1, 0):
+        ctx.set_option("graph_jit", jit)
+        lo.mul_(r, f, x, 2.0, 0.5)
+        lo.mul_(r, lo.transpose(f), x)
+    ctx.set_option("graph_jit", 1)
+    A = torch.randn(64, 72, device="cuda").to(torch.bfloat16)
+    B = torch.randn(136, 40, device="cuda").to(torch.bfloat16)
+    K = lo.kron(A, B, max_batch=2, ctx=ctx)
+    xk = torch.randn(72 * 40, device="cuda").to(torch.bfloat16)
+    K * xk
+    lo.transpose(K) * (K * xk)
+    K.apply_batch(torch.stack([xk, xk]).contiguous())
+    torch.cuda.synchronize()
+    print("SANITIZE_OK launches=%d" % ctx.launch_count())
+
+
+if __name__ == "__main__":
+    main()
