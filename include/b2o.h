@@ -110,6 +110,11 @@ int b2o_restrict_apply(b2o_index *ix, int dtype, void *res, int64_t res_len, con
 /* multRestrict! :171-174  res .= 0; res[I] = u  (duplicates: last occurrence wins) */
 int b2o_extend_apply(b2o_index *ix, int dtype, void *res, int64_t res_len, const void *u, int64_t u_len);
 
+/* diagonal quasi-Newton updates (src/DiagonalHessianApproximation.jl; their apply is b2o_diag_apply on `d`):
+ * push!(B,s,y) for kind 0 DiagonalPSB :45-64, 1 DiagonalAndrei :120-141, 2 DiagonalBFGS :234-248,
+ * 3 SpectralGradient :186-196 (d = 1-element device vector holding σ).  s == 0 -> B2O_ESTATE like the reference's error(). */
+int b2o_diagqn_push(b2o_ctx *ctx, int kind, void *d, int64_t d_len, const void *s, const void *y, int64_t n);
+
 /* ---- quasi-Newton operators (src/lbfgs.jl, src/lsr1.jl) ---------------------------------- */
 /* LBFGSOperator(T,n;mem,scaling,damped,σ₂,σ₃) :168-208 (inverse=0) / InverseLBFGSOperator :112-160 (inverse=1) */
 int b2o_lbfgs_create(b2o_ctx *ctx, int dtype, int64_t n, int mem, int scaling, int damped, double sigma2,

@@ -11,6 +11,8 @@ from .abstract import (AbstractLinearOperator, AdjointLinearOperator, ConjugateL
                        storage_type, transpose)
 from .cat import hcat, hvcat, vcat  # noqa: F401
 from .context import Context, default_context  # noqa: F401
+from .diagqn import (AbstractDiagonalQuasiNewtonOperator, DiagonalAndrei, DiagonalBFGS, DiagonalPSB, ShiftedOperator,  # noqa: F401
+                     SpectralGradient)
 from .graph import FusedOperator, fuse  # noqa: F401
 from .kron import KronOperator, kron  # noqa: F401
 from .qn import (InverseLBFGSOperator, LBFGSOperator, LSR1Operator, diag, diag_, push_)  # noqa: F401

@@ -89,6 +89,8 @@ def check(status):
     if status == B2O_ESTATE:
         if msg.startswith("only the diagonal"):
             raise LinearOperatorException(msg)
+        if msg.startswith("Cannot"):
+            raise ErrorException(msg)
         raise ErrorException(msg)
     if status == B2O_EARG and msg.startswith("indices should be between"):
         raise LinearOperatorException(msg)

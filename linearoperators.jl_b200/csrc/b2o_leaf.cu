@@ -459,3 +459,120 @@ extern "C" int b2o_extend_apply(b2o_index *ix, int dtype, void *res, int64_t res
   }
   return B2O_OK;
 }
+
+// ------------------------------------------------------------------ diagonal quasi-Newton updates (src/DiagonalHessianApproximation.jl)
+// One pass computes every reduction the four push! variants need: Σs², Σs⁴, Σs·y, Σs²·d, Σ|y|, count(s != 0).
+struct DiagQnRedArgs {
+  const double *s, *y, *d;
+  int64_t n;
+  int d_is_scalar;
+  double *partials;            // [grid][6]
+  double *out;                 // [6]
+  unsigned long long *arrive;
+};
+__global__ void __launch_bounds__(256) diagqn_reduce_kernel(const __grid_constant__ DiagQnRedArgs a) {
+  __shared__ double sred[6][8];
+  __shared__ bool is_last;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+    const double s = a.s[i], y = a.y[i], s2 = s * s;
+    acc[0] += s2;
+    acc[1] = fma(s2, s2, acc[1]);
+    acc[2] = fma(s, y, acc[2]);
+    if (!a.d_is_scalar) acc[3] = fma(s2, a.d[i], acc[3]);
+    acc[4] += fabs(y);
+    acc[5] += (s != 0.0) ? 1.0 : 0.0;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int p = 0; p < 6; ++p) {
+    double v = warp_sum(acc[p]);
+    if (lane == 0) sred[p][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double v = 0.0;
+    for (int w = 0; w < 8; ++w) v += sred[threadIdx.x][w];
+    a.partials[(size_t)blockIdx.x * 6 + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(a.arrive, 1ULL) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (warp < 6) {
+      double v = 0.0;
+      for (int b = lane; b < (int)gridDim.x; b += 32) v += __ldcg(&a.partials[(size_t)b * 6 + warp]);
+      v = warp_sum(v);
+      if (lane == 0) a.out[warp] = v;
+    }
+    if (threadIdx.x == 0) *a.arrive = 0ULL;
+  }
+}
+// kind 0 PSB: d += c*s² ; 1 Andrei: d += (c*s² - 1) ; 2 BFGS: d = |y| * c
+__global__ void diagqn_update_kernel(double *d, const double *s, const double *y, double c, int kind, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (kind == 0) d[i] = d[i] + c * (s[i] * s[i]);
+    else if (kind == 1) d[i] = d[i] + (c * (s[i] * s[i]) - 1.0);
+    else d[i] = fabs(y[i]) * c;
+  }
+}
+
+// push!(B, s, y) for DiagonalPSB (kind 0, :45-64), DiagonalAndrei (1, :120-141), DiagonalBFGS (2, :234-248) and
+// SpectralGradient (3, :186-196; d is the 1-element device vector holding σ).  s == 0 -> B2O_ESTATE (the reference errors).
+extern "C" int b2o_diagqn_push(b2o_ctx *c, int kind, void *d_, int64_t d_len, const void *s_, const void *y_, int64_t n) {
+  if (!c) B2O_FAIL(B2O_EARG, "null context");
+  if (kind < 0 || kind > 3) B2O_FAIL(B2O_EARG, "bad diagonal quasi-Newton kind %d", kind);
+  if ((kind == 3 && d_len != 1) || (kind != 3 && d_len != n)) B2O_FAIL(B2O_ESHAPE, "shape mismatch");
+  if (n > 0 && (!d_ || !s_ || !y_)) B2O_FAIL(B2O_EARG, "null vector");
+  B2O_TRY(check_ptrs8(d_, s_, y_));
+  B2O_CUDA(cudaSetDevice(c->device));
+  double *d = (double *)d_;
+  const double *s = (const double *)s_, *y = (const double *)y_;
+  DiagQnRedArgs a;
+  a.s = s; a.y = y; a.d = d; a.n = n;
+  a.d_is_scalar = kind == 3;
+  a.partials = c->d_partials;
+  a.out = c->d_dots + 330;
+  a.arrive = c->d_bar + 1;
+  const int64_t want = (n + 255) / 256;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->num_sms * 4));
+  diagqn_reduce_kernel<<<grid, 256, 0, c->stream>>>(a);
+  c->launches++;
+  B2O_CUDA(cudaGetLastError());
+  B2O_TRY(b2o_allreduce_sum_f64(c, c->d_dots + 330, 6));
+  double h[6];
+  B2O_TRY(b2o_read_scalars(c, c->d_dots + 330, 6, h));
+  const double ss = h[0], s4 = h[1], sy = h[2], s2d = h[3], sumabsy = h[4], nnz = h[5];
+  if (kind == 3) {
+    if (nnz == 0) B2O_FAIL(B2O_ESTATE, "Cannot divide by zero and s .= 0");
+    const double sigma = sy / ss;                                             // B.d[1] = dot(s,y)/dot(s,s)
+    B2O_CUDA(cudaMemcpyAsync(d, &sigma, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    B2O_CUDA(cudaStreamSynchronize(c->stream));
+    return B2O_OK;
+  }
+  const double sNorm = sqrt(ss);
+  if (sNorm == 0) B2O_FAIL(B2O_ESTATE, "Cannot update DiagonalQN operator with s=0");
+  const double sNorm2 = sNorm * sNorm;
+  double coef;
+  if (kind == 2) {
+    const double sT_y = sy / sNorm2;
+    coef = sumabsy / sT_y;                                                    // d .= abs.(y); d .*= sum(d)/sT_y
+  } else {
+    const double trA2 = s4 / (sNorm2 * sNorm2);
+    const double sT_y = sy / sNorm2, sT_B_s = s2d / sNorm2;
+    double q = sT_y - sT_B_s;
+    if (kind == 1) q += ss / sNorm2;                                          // sT_s = dot(s,s)/sNorm2
+    q /= trA2;
+    coef = q / sNorm2;
+  }
+  if (n > 0) {
+    diagqn_update_kernel<<<grid, 256, 0, c->stream>>>(d, s, y, coef, kind, n);
+    c->launches++;
+    B2O_CUDA(cudaGetLastError());
+  }
+  return B2O_OK;
+}

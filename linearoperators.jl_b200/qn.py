@@ -152,6 +152,11 @@ class LSR1Operator(AbstractQuasiNewtonOperator):
 def push_(op, s, y, *rest):
     """push!(op, s, y) | push!(op, s, y, Bs) | push!(op, s, y, α, g) | push!(op, s, y, α, g, Bs)
     (src/lbfgs.jl:269-367, src/lsr1.jl:119-184).  Returns op; a rejected pair leaves the state unchanged."""
+    from .diagqn import AbstractDiagonalQuasiNewtonOperator
+    if isinstance(op, AbstractDiagonalQuasiNewtonOperator):
+        if rest:
+            raise TypeError("no such push! method for diagonal quasi-Newton operators")
+        return op._push(s, y)
     lib = op.ctx.lib
     acc = ctypes.c_int(0)
     n = s.shape[0]

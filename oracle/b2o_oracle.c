@@ -530,6 +530,44 @@ void orc_lsr1_reset(orc_lsr1 *o) {
   o->ins0 = 0;
 }
 
+/* ================= diagonal quasi-Newton push!  src/DiagonalHessianApproximation.jl ================= */
+int orc_diagqn_push(int kind, double *d, const double *s, const double *y, int64_t n) {
+  if (kind == 3) {                                                              /* SpectralGradient :186-196 */
+    int allzero = 1;
+    for (int64_t i = 0; i < n; ++i) if (s[i] != 0) allzero = 0;
+    if (allzero) return -1;
+    d[0] = orc_dot(s, y, n) / orc_dot(s, s, n);
+    return 0;
+  }
+  double sNorm = orc_nrm2(s, n);
+  if (sNorm == 0) return -1;
+  double sNorm2 = sNorm * sNorm;
+  if (kind == 2) {                                                              /* DiagonalBFGS :234-248 */
+    double sT_y = orc_dot(s, y, n) / sNorm2;
+    long double sum = 0;
+    for (int64_t i = 0; i < n; ++i) { d[i] = fabs(y[i]); sum += d[i]; }
+    double c = (double)sum / sT_y;
+    for (int64_t i = 0; i < n; ++i) d[i] *= c;
+    return 0;
+  }
+  long double s4 = 0, s2d = 0;                                                  /* PSB :45-64, Andrei :120-141 */
+  for (int64_t i = 0; i < n; ++i) {
+    long double s2 = (long double)s[i] * s[i];
+    s4 += s2 * s2;
+    s2d += s2 * d[i];
+  }
+  double trA2 = (double)s4 / (sNorm2 * sNorm2);
+  double sT_y = orc_dot(s, y, n) / sNorm2;
+  double sT_B_s = (double)s2d / sNorm2;
+  double q = sT_y - sT_B_s;
+  if (kind == 1) q += orc_dot(s, s, n) / sNorm2;
+  q /= trA2;
+  double c = q / sNorm2;
+  if (kind == 0) for (int64_t i = 0; i < n; ++i) d[i] = d[i] + c * (s[i] * s[i]);
+  else for (int64_t i = 0; i < n; ++i) d[i] = d[i] + (c * (s[i] * s[i]) - 1.0);
+  return 0;
+}
+
 /* ================= kron  src/kron.jl:14-40 =================
  * prod : X = reshape(x,q,n);  res = α vec(B X Aᵀ) + β res      (A m×n, B p×q)  -> p×m
  * tprod: X = reshape(x,p,m);  res = α vec(Bᵀ X A) + β res                      -> q×n

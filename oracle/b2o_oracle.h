@@ -83,6 +83,10 @@ int orc_lsr1_insert(orc_lsr1 *);
 void orc_lsr1_set_insert(orc_lsr1 *, int insert1);
 double orc_lsr1_opnorm_upper_bound(orc_lsr1 *);
 
+/* diagonal quasi-Newton push! -- src/DiagonalHessianApproximation.jl:45-64,120-141,186-196,234-248; kind 0 PSB 1 Andrei 2 BFGS 3 Spectral
+ * returns 0, or -1 when s == 0 (the reference errors) */
+int orc_diagqn_push(int kind, double *d, const double *s, const double *y, int64_t n);
+
 /* kron(A,B)*x = alpha*vec(B X A^T)+beta*res -- src/kron.jl:14-22; A m×n, B p×q, col-major;
  * trans: 0 prod, 1 tprod (B^T X A), 2 ctprod (same for real) */
 void orc_kron(double *res, const double *A, int64_t m, int64_t n, const double *B, int64_t p, int64_t q,

@@ -67,6 +67,7 @@ def lib():
             "orc_lsr1_ys": (c_dp, [vp]), "orc_lsr1_as": (c_dp, [vp]), "orc_lsr1_gamma": (d, [vp]),
             "orc_lsr1_set_gamma": (None, [vp, d]), "orc_lsr1_insert": (i32, [vp]),
             "orc_lsr1_set_insert": (None, [vp, i32]), "orc_lsr1_opnorm_upper_bound": (d, [vp]),
+            "orc_diagqn_push": (i32, [i32, vp, vp, vp, i64]),
             "orc_kron": (None, [vp, vp, i64, i64, vp, i64, i64, vp, d, d, i32]),
             "orc_f32_to_bf16": (ctypes.c_uint16, [ctypes.c_float]), "orc_bf16_to_f32": (ctypes.c_float, [ctypes.c_uint16]),
         }
@@ -136,6 +137,14 @@ def restrict_(res, idx1, v):
 def extend_(res, idx1, u):
     idx1 = np.ascontiguousarray(idx1, dtype=np.int64)
     lib().orc_extend(_p(res), res.shape[0], _p(idx1), idx1.shape[0], _p(u))
+
+
+def diagqn_push(kind, d, s, y):
+    """push! of DiagonalPSB (0) / DiagonalAndrei (1) / DiagonalBFGS (2) / SpectralGradient (3); d is updated in place"""
+    s, y = _f64(s), _f64(y)
+    if lib().orc_diagqn_push(int(kind), _p(d), _p(s), _p(y), s.shape[0]) != 0:
+        raise ZeroDivisionError("Cannot update DiagonalQN operator with s=0")
+    return d
 
 
 def kron_(res, A, B, x, alpha=1.0, beta=0.0, trans=0):

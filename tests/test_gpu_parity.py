@@ -749,3 +749,74 @@ def test_inverse_compact_representation(lo, ctx, orc, n, mem, npush, scaling):
     assert H.apply_bytes() == (4 * min(mem, npush) + 3) * 8 * n
     lo.reset_(H)
     assert np.array_equal(host(H * x), host(x))
+
+
+# ---------------------------------------------------------------- §8f.3: diagonal quasi-Newton family + ShiftedOperator
+def test_diagonal_qn_reference_values_on_gpu(lo, ctx):
+    """test/test_diag.jl:37-106 (hard-coded Bref / weak secant equation) on the CUDA path"""
+    from test_oracle_pinning import BREF, BREF_SPG, GRADS, X0, X1
+    for fun in ("f", "g", "h"):
+        s_h, y_h = X1 - X0, GRADS[fun](X1) - GRADS[fun](X0)
+        s, y = dev(ctx, s_h), dev(ctx, y_h)
+        for kind, cls in ((0, lo.DiagonalPSB), (1, lo.DiagonalAndrei)):
+            B = cls(dev(ctx, [1.0, -1.0, 1.0]), ctx=ctx)
+            lo.push_(B, s, y)
+            assert np.linalg.norm(host(B.d) - np.array(BREF[(fun, kind)], dtype=float)) <= 1e-10
+            assert abs(s_h @ host(B * s) - s_h @ y_h) <= 1e-10
+        S = lo.SpectralGradient(1.0, 3, ctx=ctx)
+        lo.push_(S, s, y)
+        assert abs(float(S.d.item()) - BREF_SPG[fun]) <= 1e-10
+        assert np.allclose(host(S * s), BREF_SPG[fun] * s_h, rtol=1e-15)
+    with pytest.raises(lo.ErrorException, match="Cannot update DiagonalQN operator with s=0"):
+        lo.push_(lo.DiagonalPSB(dev(ctx, np.ones(3)), ctx=ctx), dev(ctx, np.zeros(3)), y)
+    with pytest.raises(lo.ErrorException, match="Cannot divide by zero"):
+        lo.push_(lo.SpectralGradient(1.0, 3, ctx=ctx), dev(ctx, np.zeros(3)), y)
+
+
+@pytest.mark.parametrize("n", [1001, 300007])
+def test_diagonal_qn_vs_oracle(lo, ctx, orc, n):
+    s, y = ctx.uniform(n, 31, -1.0, 1.0), ctx.uniform(n, 32, -1.0, 1.0)
+    x = ctx.uniform(n, 7)
+    for kind, cls in ((0, lo.DiagonalPSB), (1, lo.DiagonalAndrei), (2, lo.DiagonalBFGS)):
+        d = ctx.uniform(n, 33, 0.5, 1.5)
+        d_ref = host(d).copy()
+        B = cls(d, ctx=ctx)
+        for _ in range(2):
+            lo.push_(B, s, y)
+            orc.diagqn_push(kind, d_ref, host(s), host(y))
+        assert rel(host(B.d), d_ref) <= TOL
+        ref = np.empty(n)
+        orc.diag_(ref, d_ref, host(x), 1.0, 0.0)
+        assert rel(host(B * x), ref) <= TOL
+        assert lo.isallocated5(B) and lo.issymmetric(B)
+        lo.reset_(B)
+        assert np.array_equal(host(B.d), np.ones(n)) and lo.nprod(B) == 0
+    S = lo.SpectralGradient(2.0, n, ctx=ctx)
+    sig = np.array([2.0])
+    lo.push_(S, s, y)
+    orc.diagqn_push(3, sig, host(s), host(y))
+    assert abs(float(S.d.item()) - sig[0]) <= 1e-12 * abs(sig[0])
+    r0 = ctx.uniform(n, 8)
+    res = r0.clone()
+    lo.mul_(res, S, x, 1.5, -0.5)
+    assert rel(host(res), (1.5 * float(S.d.item())) * host(x) - 0.5 * host(r0)) <= 1e-15
+
+
+def test_shifted_operator(lo, ctx, orc):
+    """src/shifted_operators.jl: (H + σI) x with a mutable σ; test/test_shifted_operator.jl basics"""
+    n = 20011
+    g, o = build_pair(lo, ctx, orc, "fwd", n, 4, 5)
+    x, r0 = ctx.uniform(n, 7), ctx.uniform(n, 8)
+    Sop = lo.ShiftedOperator(g, 0.75)
+    assert lo.issymmetric(Sop) and lo.ishermitian(Sop) and lo.size(Sop) == (n, n)
+    assert rel(host(Sop * x), o.apply(host(x)) + 0.75 * host(x)) <= TOL
+    res, ref = r0.clone(), host(r0).copy()
+    lo.mul_(res, Sop, x, 2.0, -0.5)
+    o.apply(host(x), 2.0, -0.5, res=ref)
+    assert rel(host(res), ref + 2.0 * 0.75 * host(x)) <= TOL
+    Sop.sigma = -1.25                                                            # σ is mutable (shifted_operators.jl:6)
+    assert rel(host(lo.transpose(Sop) * x), o.apply(host(x)) - 1.25 * host(x)) <= TOL
+    Sop.sigma = 0.0
+    assert np.array_equal(host(Sop * x), host(g * x))
+    with pytest.raises(ValueError):
+        lo.ShiftedOperator(lo.opEye(3, 4), 1.0)

@@ -275,6 +275,39 @@ def test_lsr1_equals_dense_sr1(orc):
     assert np.linalg.norm(B, 2) <= LB.opnorm_upper_bound * (1 + 1e-12)
 
 
+# ---------------------------------------------------------------- diagonal quasi-Newton (test/test_diag.jl:37-106): LITERAL known answers
+X0 = np.array([-1.0, 1.0, -1.0])
+X1 = X0 + np.array([1.0, 0.0, 1.0])
+GRADS = {
+    "f": lambda x: 2 * np.array([x[0], x[1], x[2]]),
+    "g": lambda x: np.array([np.exp(x[0]), 1.0, -np.sin(x[2])]),
+    "h": lambda x: np.array([2 * x[0] * x[1] * x[2]**3, x[0]**2 * x[2]**3, 3 * x[0]**2 * x[1] * x[2]**2]),
+}
+# Bref of test/test_diag.jl:76-88 (kind 0 = DiagonalPSB, 1 = DiagonalAndrei) and Bref_spg (:85-88)
+BREF = {
+    ("f", 0): [2, -1, 2], ("f", 1): [2, -2, 2],
+    ("g", 0): [1 + (np.sin(-1) - np.exp(-1) - 1) / 2, -1, 1 + (np.sin(-1) - np.exp(-1) - 1) / 2],
+    ("g", 1): [(1 + np.sin(-1) - np.exp(-1)) / 2, -2, (1 + np.sin(-1) - np.exp(-1)) / 2],
+    ("h", 0): [-5 / 2, -1, -5 / 2], ("h", 1): [-5 / 2, -2, -5 / 2],
+}
+BREF_SPG = {"f": 2.0, "g": (1 - np.exp(-1) + np.sin(-1)) / 2, "h": -5 / 2}
+
+
+@pytest.mark.parametrize("fun", ["f", "g", "h"])
+def test_diagonal_qn_hard_coded_reference_values(orc, fun):
+    s, y = X1 - X0, GRADS[fun](X1) - GRADS[fun](X0)
+    for kind in (0, 1):
+        d = np.array([1.0, -1.0, 1.0])
+        orc.diagqn_push(kind, d, s, y)
+        assert np.linalg.norm(d - np.array(BREF[(fun, kind)], dtype=float)) <= 1e-10
+        assert abs(s @ (d * s) - s @ y) <= 1e-10                                # weak secant equation (:50-72)
+    sig = np.array([1.0])
+    orc.diagqn_push(3, sig, s, y)
+    assert abs(sig[0] - BREF_SPG[fun]) <= 1e-10
+    with pytest.raises(ZeroDivisionError):
+        orc.diagqn_push(0, np.ones(3), np.zeros(3), y)
+
+
 # ---------------------------------------------------------------- kron (test/test_kron.jl:3-39)
 @pytest.mark.parametrize("shapeA,shapeB", [((2, 3), (2, 3)), ((4, 4), (3, 5))])
 def test_kron_against_dense(orc, shapeA, shapeB):
