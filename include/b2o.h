@@ -138,6 +138,10 @@ int b2o_lbfgs_push_damped_inv(b2o_qn *op, const void *s, void *y, double alpha, 
 int b2o_qn_diag(b2o_qn *op, void *d, int64_t d_len);
 /* reset! src/lbfgs.jl:401-427, src/lsr1.jl:217-240 */
 int b2o_qn_reset(b2o_qn *op);
+/* solve_shifted_system!(x, B, b, σ) src/utilities.jl:207-248 and ldiv!(x, B, b) :281-289 (σ = 0): (B + σI) x = b for a FORWARD
+ * L-BFGS operator; σ < 0 -> B2O_EARG ("σ must be nonnegative", the reference's ArgumentError).  The n x 2mem work matrix
+ * (data.shifted_p, src/lbfgs.jl:53) is allocated on first use. */
+int b2o_lbfgs_solve_shifted(b2o_qn *op, void *x, int64_t x_len, const void *b, int64_t b_len, double sigma);
 /* state access (checkpoint/resume and parity tests).  which: 0=s 1=y 2=a 3=b; k0 = 0-based ring slot.
  * scalars: insert1 (1-based data.insert), gamma (scaling_factor), opnorm_upper_bound,
  * ys[mem], aux[mem] (LBFGS inverse: α scratch; LBFGS forward: norm_b; LSR1: as). */

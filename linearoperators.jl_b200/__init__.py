@@ -15,7 +15,7 @@ from .diagqn import (AbstractDiagonalQuasiNewtonOperator, DiagonalAndrei, Diagon
                      SpectralGradient)
 from .graph import FusedOperator, fuse  # noqa: F401
 from .kron import KronOperator, kron  # noqa: F401
-from .qn import (InverseLBFGSOperator, LBFGSOperator, LSR1Operator, diag, diag_, push_)  # noqa: F401
+from .qn import (InverseLBFGSOperator, LBFGSOperator, LSR1Operator, diag, diag_, ldiv_, push_, solve_shifted_system_)  # noqa: F401
 from .special_operators import (BlockDiagonalOperator, LocalBlockOfDiagonal, getindex, opDiagonal, opExtension, opEye, opHouseholder,  # noqa: F401
                                 opOnes, opRestriction, opZeros)
 

@@ -18,6 +18,7 @@ struct b2o_qn_s {
   double gamma = 1.0, sigma2 = 0.99, sigma3 = 10.0, opnorm_ub = 1.0;
   double *S = nullptr, *Y = nullptr, *A = nullptr, *B = nullptr;  // [mem][pitch], zero padded
   double *q = nullptr, *tmp = nullptr;                            // [pitch]
+  double *shifted_p = nullptr;                                    // [2*mem][pitch] work matrix of solve_shifted_system! (lazy)
   double *d_alpha = nullptr;                                      // [mem] device copy of data.α (inverse)
   std::vector<double> ys, aux;  // aux: inverse L-BFGS α (host mirror, lazily), forward norm_b, L-SR1 as
   int ins0 = 0;
@@ -54,7 +55,8 @@ __global__ void div_sqrt_dev_kernel(double *out, const double *x, const double *
 }
 
 // out[j] = base(j), then sequentially out[j] (+|-)= coef_t * col_t[j];  coef_t = dots[t] / cdiv[t].
-// base: mode 0: P1[j]/g ; mode 1: P0[j] - P1[j]/g.   Fused reductions: red[0] = out·u0 ; red[1] = out·out.
+// base: mode 0: P1[j]/g ; mode 1: P0[j] - P1[j]/g ; mode 2: g*P1[j].   coef_t = dots[t]/cdiv[t] (or dots[t]*cdiv[t] if cmul).
+// Fused reductions: red[0] = out·u0 ; red[1] = out·out (or out·u1 when u1 is given).
 struct LincombArgs {
   const double *cols[B2O_MAX_COLS];
   double cdiv[B2O_MAX_COLS];
@@ -65,6 +67,8 @@ struct LincombArgs {
   double g;
   const double *dots;  // device coefficients
   const double *u0;    // may be null
+  const double *u1;    // may be null: red[1] = out·u1 instead of out·out
+  int cmul;            // coef_t = dots[t] * cdiv[t]
   double *out;
   int64_t n;
   double *partials;    // [grid][2]
@@ -75,19 +79,19 @@ __global__ void __launch_bounds__(256) lincomb_kernel(const __grid_constant__ Li
   __shared__ double scoef[B2O_MAX_COLS];
   __shared__ double sred[2][8];
   __shared__ bool is_last;
-  for (int t = threadIdx.x; t < a.nterms; t += blockDim.x) scoef[t] = a.dots[t] / a.cdiv[t];
+  for (int t = threadIdx.x; t < a.nterms; t += blockDim.x) scoef[t] = a.cmul ? a.cdiv[t] * a.dots[t] : a.dots[t] / a.cdiv[t];
   __syncthreads();
   double r0 = 0.0, r1 = 0.0;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
-    double v = a.base_mode == 0 ? a.P1[i] / a.g : a.P0[i] - a.P1[i] / a.g;
+    double v = a.base_mode == 0 ? a.P1[i] / a.g : a.base_mode == 1 ? a.P0[i] - a.P1[i] / a.g : a.g * a.P1[i];
     for (int t = 0; t < a.nterms; ++t) {
       double c = scoef[t] * a.cols[t][i];
       v = a.sign[t] > 0 ? v + c : v - c;
     }
     a.out[i] = v;
     if (a.u0) r0 = fma(v, a.u0[i], r0);
-    r1 = fma(v, v, r1);
+    r1 = fma(v, a.u1 ? a.u1[i] : v, r1);
   }
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   r0 = warp_sum(r0);
@@ -199,6 +203,7 @@ extern "C" int b2o_qn_destroy(b2o_qn *q) {
   cudaFree(q->q);
   cudaFree(q->tmp);
   cudaFree(q->d_alpha);
+  if (q->shifted_p) cudaFree(q->shifted_p);
   if (q->d_W) cudaFree(q->d_W);
   if (q->h_W) cudaFreeHost(q->h_W);
   delete q;
@@ -1044,6 +1049,95 @@ static int lsr1_push(b2o_qn *q, const double *s, const double *y, int *accepted)
     prev[nprev++] = k;
   }
   if (accepted) *accepted = 1;
+  return B2O_OK;
+}
+
+// ------------------------------------------------------------------ solve_shifted_system! / ldiv!  (src/utilities.jl:207-289)
+// (B + σI) x = b for a forward L-BFGS operator: 2*mem Sherman-Morrison steps over the rank-one terms a_k a_kᵀ / b_k b_kᵀ
+// (Erway, Jain, Marcia 2014).  Per step: all dots p_t·u in multi-dot passes, one combine pass that forms p_i with the two
+// dots u·p_i and b·p_i fused in; x is assembled at the end in one pass with the reference's statement order.
+extern "C" int b2o_lbfgs_solve_shifted(b2o_qn *q, void *x_, int64_t x_len, const void *b_, int64_t b_len, double sigma) {
+  if (!q) B2O_FAIL(B2O_EARG, "null operator");
+  if (q->kind != 0 || q->inverse) B2O_FAIL(B2O_EARG, "solve_shifted_system! needs a forward LBFGSOperator");
+  if (sigma < 0) B2O_FAIL(B2O_EARG, "σ must be nonnegative");                                   // ArgumentError :213-215
+  B2O_TRY(check_vec(q, x_, x_len));
+  B2O_TRY(check_vec(q, b_, b_len));
+  b2o_ctx *c = q->ctx;
+  B2O_CUDA(cudaSetDevice(c->device));
+  const int64_t n = q->n;
+  const int mem = q->mem, max_i = 2 * mem;
+  if (n == 0) return B2O_OK;
+  if (2 * mem + 1 > B2O_MAX_COLS) B2O_FAIL(B2O_EUNSUPPORTED, "mem too large for solve_shifted_system!");
+  if (!q->shifted_p) {
+    cudaError_t e = cudaMalloc(&q->shifted_p, sizeof(double) * (size_t)q->pitch * max_i);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      B2O_FAIL(B2O_ENOMEM, "solve_shifted_system!: work matrix of %zu bytes: %s", sizeof(double) * (size_t)q->pitch * max_i, cudaGetErrorString(e));
+    }
+  }
+  double *x = (double *)x_;
+  const double *b = (const double *)b_;
+  const double gamma_inv = 1 / q->gamma;                                                        // :219
+  const double x_0 = 1 / (gamma_inv + sigma);
+  std::vector<double> v(max_i, 0.0), cx(max_i, 0.0);
+  int sign_i = 1;
+  for (int i = 1; i <= max_i; ++i) {                                                            // :226
+    const int jj = (i + 1) / 2;
+    const int k = pmod(q->ins0 + jj, mem);                                                      // k = mod(insert + j - 1, mem) + 1
+    const double *u = (sign_i == -1) ? q->col(q->B, k) : q->col(q->A, k);                       // :229
+    double *pi = q->shifted_p + (size_t)(i - 1) * q->pitch;
+    LincombArgs a;
+    memset(&a, 0, sizeof(a));
+    const double *dcols[B2O_MAX_COLS];
+    int sign_t = 1;
+    for (int t = 1; t <= i - 1; ++t) {                                                          // c2 = (sign_t * v[t]) * dot(p_t, u)
+      a.cols[t - 1] = q->shifted_p + (size_t)(t - 1) * q->pitch;
+      a.sign[t - 1] = +1;
+      a.cdiv[t - 1] = sign_t * v[t - 1];
+      dcols[t - 1] = a.cols[t - 1];
+      sign_t = -sign_t;
+    }
+    a.nterms = i - 1;
+    a.cmul = 1;
+    B2O_TRY(multi_dots(c, a.nterms, dcols, u, n, c->d_dots));
+    a.base_mode = 2;                                                                            // p_i = x_0 .* u   :231
+    a.P1 = u;
+    a.g = x_0;
+    a.dots = c->d_dots;
+    a.u0 = u;                                                                                   // red[0] = u·p_i
+    a.u1 = b;                                                                                   // red[1] = p_i·b
+    a.out = pi;
+    a.n = n;
+    a.red = c->d_dots + 256;
+    double r[2];
+    B2O_TRY(lincomb_launch(c, a));
+    B2O_TRY(b2o_allreduce_sum_f64(c, c->d_dots + 256, 2));
+    B2O_TRY(b2o_read_scalars(c, c->d_dots + 256, 2, r));
+    v[i - 1] = 1 / (1 - sign_i * r[0]);                                                         // :242
+    cx[i - 1] = sign_i * v[i - 1] * r[1];                                                       // :243
+    sign_i = -sign_i;
+  }
+  // x = x_0 .* b ; x .+= cx_i .* p_i  (i = 1..2mem in order)                                    :221, :243-244
+  LincombArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int i = 0; i < max_i; ++i) {
+    a.cols[i] = q->shifted_p + (size_t)i * q->pitch;
+    a.sign[i] = +1;
+    a.cdiv[i] = 1.0;
+    c->h_scal[i] = cx[i];
+  }
+  B2O_CUDA(cudaMemcpyAsync(c->d_dots, c->h_scal, sizeof(double) * max_i, cudaMemcpyHostToDevice, c->stream));
+  a.nterms = max_i;
+  a.cmul = 1;
+  a.base_mode = 2;
+  a.P1 = b;
+  a.g = x_0;
+  a.dots = c->d_dots;
+  a.out = x;
+  a.n = n;
+  a.red = c->d_dots + 256;
+  B2O_TRY(lincomb_launch(c, a));
+  B2O_CUDA(cudaStreamSynchronize(c->stream));   // h_scal is reused by later calls
   return B2O_OK;
 }
 

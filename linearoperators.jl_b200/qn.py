@@ -186,3 +186,16 @@ def diag_(op, d):
 
 def diag(op):
     return diag_(op, op.ctx.empty(op.nrow))
+
+
+def solve_shifted_system_(x, B, b, sigma):
+    """solve_shifted_system!(x, B, b, σ): solve (B + σI) x = b for a forward LBFGSOperator (src/utilities.jl:207-248)."""
+    if sigma < 0:
+        raise ValueError("σ must be nonnegative")                      # ArgumentError
+    _lib.check(B.ctx.lib.b2o_lbfgs_solve_shifted(B.handle, _vp(x), x.shape[0], _vp(b), b.shape[0], float(sigma)))
+    return x
+
+
+def ldiv_(x, B, b):
+    """ldiv!(x, B, b): solve B x = b (src/utilities.jl:281-289)"""
+    return solve_shifted_system_(x, B, b, 0.0)

@@ -389,6 +389,42 @@ void orc_lbfgs_reset(orc_lbfgs *o) {
   o->ins0 = 0;
 }
 
+/* solve_shifted_system!  src/utilities.jl:207-248 (Erway, Jain, Marcia 2014): 2*mem rank-one Sherman-Morrison steps */
+int orc_lbfgs_solve_shifted(orc_lbfgs *o, double *x, const double *b, double sigma) {
+  if (sigma < 0 || o->inverse) return -1;                                       /* :213-215 */
+  const int64_t n = o->n;
+  const int mem = o->mem, max_i = 2 * mem;
+  double *P = (double *)calloc((size_t)n * max_i, sizeof(double));               /* data.shifted_p  n x 2mem */
+  double *v = (double *)calloc(max_i, sizeof(double));                           /* data.shifted_v */
+  const double gamma_inv = 1 / o->gamma;                                         /* :219 */
+  const double x_0 = 1 / (gamma_inv + sigma);
+  for (int64_t j = 0; j < n; ++j) x[j] = x_0 * b[j];                             /* :221 */
+  int sign_i = 1;
+  for (int i = 1; i <= max_i; ++i) {                                             /* :226 */
+    const int jj = (i + 1) / 2;
+    const int k = pmod(o->ins0 + jj, mem);                                       /* k = mod(insert + j - 1, mem) + 1 */
+    const double *u = (sign_i == -1) ? o->b + (size_t)k * n : o->a + (size_t)k * n;   /* :229 */
+    double *pi = P + (size_t)(i - 1) * n;
+    for (int64_t j = 0; j < n; ++j) pi[j] = x_0 * u[j];                          /* :231 */
+    int sign_t = 1;
+    for (int t = 1; t <= i - 1; ++t) {                                           /* :234 */
+      const double *pt = P + (size_t)(t - 1) * n;
+      const double c0 = orc_dot(pt, u, n);
+      const double c1 = sign_t * v[t - 1];
+      const double c2 = c1 * c0;
+      for (int64_t j = 0; j < n; ++j) pi[j] += c2 * pt[j];                       /* :238 */
+      sign_t = -sign_t;
+    }
+    v[i - 1] = 1 / (1 - sign_i * orc_dot(u, pi, n));                             /* :242 */
+    const double cx = sign_i * v[i - 1] * orc_dot(pi, b, n);                     /* :243-244 */
+    for (int64_t j = 0; j < n; ++j) x[j] += cx * pi[j];
+    sign_i = -sign_i;
+  }
+  free(P);
+  free(v);
+  return 0;
+}
+
 /* ================= L-SR1  src/lsr1.jl ================= */
 struct orc_lsr1 {
   int64_t n;

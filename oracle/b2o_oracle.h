@@ -66,6 +66,8 @@ void orc_lbfgs_set_gamma(orc_lbfgs *, double);
 int orc_lbfgs_insert(orc_lbfgs *);                 /* 1-based, as data.insert */
 void orc_lbfgs_set_insert(orc_lbfgs *, int insert1);
 double orc_lbfgs_opnorm_upper_bound(orc_lbfgs *);
+/* solve_shifted_system!(x, B, b, σ): (B + σI) x = b for a forward operator -- src/utilities.jl:207-248; -1 if σ < 0 or inverse */
+int orc_lbfgs_solve_shifted(orc_lbfgs *, double *x, const double *b, double sigma);
 
 typedef struct orc_lsr1 orc_lsr1;
 orc_lsr1 *orc_lsr1_create(int64_t n, int mem, int scaling);

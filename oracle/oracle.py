@@ -61,6 +61,7 @@ def lib():
             "orc_lbfgs_reset": (None, [vp]), "orc_lbfgs_col": (c_dp, [vp, i32, i32]), "orc_lbfgs_ys": (c_dp, [vp]),
             "orc_lbfgs_gamma": (d, [vp]), "orc_lbfgs_set_gamma": (None, [vp, d]), "orc_lbfgs_insert": (i32, [vp]),
             "orc_lbfgs_set_insert": (None, [vp, i32]), "orc_lbfgs_opnorm_upper_bound": (d, [vp]),
+            "orc_lbfgs_solve_shifted": (i32, [vp, vp, vp, d]),
             "orc_lsr1_create": (vp, [i64, i32, i32]), "orc_lsr1_destroy": (None, [vp]),
             "orc_lsr1_apply": (None, [vp, vp, vp, d, d]), "orc_lsr1_push": (i32, [vp, vp, vp]),
             "orc_lsr1_diag": (None, [vp, vp]), "orc_lsr1_reset": (None, [vp]), "orc_lsr1_col": (c_dp, [vp, i32, i32]),
@@ -209,6 +210,14 @@ class LBFGS:
         if lib().orc_lbfgs_diag(self.h, _p(d)) < 0:
             raise RuntimeError("only the diagonal of a forward L-BFGS approximation is available")
         return d
+
+    def solve_shifted(self, b, sigma=0.0, x=None):
+        """solve_shifted_system!(x, B, b, σ)  (src/utilities.jl:207-248)"""
+        b = _f64(b)
+        x = np.empty(self.n) if x is None else x
+        if lib().orc_lbfgs_solve_shifted(self.h, _p(x), _p(b), float(sigma)) != 0:
+            raise ValueError("σ must be nonnegative")
+        return x
 
     def reset(self):
         lib().orc_lbfgs_reset(self.h)

@@ -820,3 +820,26 @@ def test_shifted_operator(lo, ctx, orc):
     assert np.array_equal(host(Sop * x), host(g * x))
     with pytest.raises(ValueError):
         lo.ShiftedOperator(lo.opEye(3, 4), 1.0)
+
+
+# ---------------------------------------------------------------- §8f.2: solve_shifted_system! / ldiv!
+@pytest.mark.parametrize("n,mem,npush,sigma", [(100, 5, 10, 0.1), (20011, 4, 3, 0.0), (300007, 6, 9, 2.5)])
+def test_solve_shifted_system(lo, ctx, orc, n, mem, npush, sigma):
+    """(B + σI) x = b on the CUDA path: against the oracle restatement and the reference's own predicates
+    (test/test_solve_shifted_system.jl:22-63)"""
+    g, o = build_pair(lo, ctx, orc, "fwd", n, mem, npush)
+    xt = ctx.uniform(n, 41, -1.0, 1.0)
+    b = g * xt + sigma * xt
+    x = ctx.zeros(n)
+    out = lo.solve_shifted_system_(x, g, b, sigma)
+    assert out is x and np.isfinite(host(x)).all()
+    assert rel(host(x), o.solve_shifted(host(b), sigma)) <= 1e-9
+    assert np.allclose(host(x), host(xt), atol=1e-6, rtol=1e-6)
+    resid = g * x + sigma * x - b
+    assert np.sqrt(ctx.dot(resid, resid) / ctx.dot(b, b)) < 1e-8
+    if sigma == 0.0:
+        H, _ = build_pair(lo, ctx, orc, "inv", n, mem, npush)
+        x2 = lo.ldiv_(ctx.zeros(n), g, b)
+        assert np.allclose(host(x2), host(H * b), atol=1e-6, rtol=1e-6)
+    with pytest.raises(ValueError):
+        lo.solve_shifted_system_(x, g, b, -0.1)

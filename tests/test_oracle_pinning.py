@@ -229,6 +229,29 @@ def test_lbfgs_scaling_and_5arg(orc):
         assert np.linalg.norm(res - (2.0 * M @ x - 0.5 * r0)) <= 1e-13 * np.linalg.norm(res)
 
 
+def test_solve_shifted_system_reference_predicates(orc):
+    """test/test_solve_shifted_system.jl:5-63 and the docstring check of src/utilities.jl:191"""
+    rng = np.random.default_rng(9)
+    for scaling, sigma in [(False, 0.1), (True, 0.1), (True, 0.0)]:
+        n, M = 100, 5
+        B = orc.LBFGS(n, mem=M, scaling=scaling)
+        H = orc.LBFGS(n, mem=M, scaling=scaling, inverse=True)
+        for _ in range(10):
+            s, y = rng.random(n), rng.random(n)
+            B.push(s, y)
+            H.push(s, y)
+        x_true = rng.standard_normal(n)
+        b = B.apply(x_true) + sigma * x_true
+        x = B.solve_shifted(b, sigma)
+        assert np.all(np.isfinite(x))
+        assert np.allclose(x, x_true, atol=1e-6, rtol=1e-6)
+        assert np.linalg.norm(B.apply(x) + sigma * x - b) / np.linalg.norm(b) < 1e-8
+        if sigma == 0.0:
+            assert np.allclose(x, H.apply(b), atol=1e-6, rtol=1e-6)            # ldiv! agrees with the inverse operator
+    with pytest.raises(ValueError):
+        B.solve_shifted(b, -0.1)
+
+
 # ---------------------------------------------------------------- L-SR1 (test/test_lsr1.jl)
 def sr1_dense(B, s, y):
     r = y - B @ s
