@@ -94,7 +94,7 @@ class ShiftedOperator(AbstractLinearOperator):
     def __init__(self, H, sigma=0.0):
         if size(H, 1) != size(H, 2):
             raise ValueError("Operator H must be square.")            # DimensionMismatch
-        self.H, self.sigma = H, float(sigma)
+        self.base, self.sigma = H, float(sigma)      # data.H, data.σ (`.H` is the adjoint shortcut of the mirror)
         self.ctx = _ctx_of(H)
         self.eltype = eltype(H)
         self.nrow = self.ncol = size(H, 1)
@@ -110,15 +110,15 @@ class ShiftedOperator(AbstractLinearOperator):
                                              float(a) * self.sigma, 1.0))
 
         def prod_(y, x, a, b):
-            mul_(y, self.H, x, a, b)
+            mul_(y, self.base, x, a, b)
             axpy(y, x, a)
 
         def tprod_(y, x, a, b):
-            mul_(y, transpose(self.H), x, a, b)
+            mul_(y, transpose(self.base), x, a, b)
             axpy(y, x, a)
 
         def ctprod_(y, x, a, b):
-            mul_(y, adjoint(self.H), x, a, b)
+            mul_(y, adjoint(self.base), x, a, b)
             axpy(y, x, a)
 
         self.prod_, self.tprod_, self.ctprod_ = prod_, tprod_, ctprod_
