@@ -63,6 +63,8 @@ int b2o_ctx_destroy(b2o_ctx *ctx);
 int b2o_ctx_sync(b2o_ctx *ctx);
 /* tuning knobs of the streaming kernels: "tile_rows" (1024|2048|4096), "stages", "grid", "threads" */
 int b2o_ctx_set_option(b2o_ctx *ctx, const char *key, int64_t value);
+/* debug: raw read of workspace scalars (e.g. the kron kernel's %globaltimer timeline with option "kron_debug") */
+int b2o_ctx_debug_read(b2o_ctx *ctx, int offset, int count, double *out);
 /* number of libb2o kernels launched through this context since creation */
 int b2o_ctx_launch_count(b2o_ctx *ctx, int64_t *out);
 /* average device time (ms) of the dominant streaming kernel over the launches since the last reset,

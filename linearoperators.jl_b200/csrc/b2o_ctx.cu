@@ -88,6 +88,8 @@ extern "C" int b2o_ctx_set_option(b2o_ctx *c, const char *key, int64_t value) {
   } else if (!strcmp(key, "grid")) {
     if (value < 0 || value > B2O_MAX_GRID) B2O_FAIL(B2O_EARG, "grid out of range");
     c->grid = (int)value;
+  } else if (!strcmp(key, "kron_debug")) {
+    c->kron_debug = value != 0;
   } else if (!strcmp(key, "host_chunks")) {
     if (value < 1 || value > 16) B2O_FAIL(B2O_EARG, "host_chunks must be 1..16");
     c->host_chunks = (int)value;
@@ -102,6 +104,12 @@ extern "C" int b2o_ctx_set_option(b2o_ctx *c, const char *key, int64_t value) {
     B2O_FAIL(B2O_EARG, "unknown option '%s'", key);
   }
   return B2O_OK;
+}
+
+// raw read of `count` workspace doubles starting at `offset` (debug timelines)
+extern "C" int b2o_ctx_debug_read(b2o_ctx *c, int offset, int count, double *out) {
+  if (!c || !out || offset < 0 || count < 1 || offset + count > B2O_WS_DOTS) B2O_FAIL(B2O_EARG, "bad argument");
+  return b2o_read_scalars(c, c->d_dots + offset, count, out);
 }
 
 extern "C" int b2o_ctx_launch_count(b2o_ctx *c, int64_t *out) {

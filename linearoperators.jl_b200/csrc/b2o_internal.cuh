@@ -61,6 +61,7 @@ struct b2o_ctx_s {
   int tile_rows = 2048;
   int stages = 0;        // 0 -> as many as shared memory allows
   int grid = 0;          // 0 -> one CTA per SM
+  int kron_debug = 0;    // record a %globaltimer timeline of CTA 0 of the kron kernel into d_dots[448..464)
   int graph_jit = 1;     // fused trees: use the NVRTC-specialised kernel when NVRTC + driver are present (else the interpreter)
   int graph_blocks = 3;  // resident CTAs per SM the fused-graph kernel is compiled for (occupancy hides the dispatch latency)
   // accounting

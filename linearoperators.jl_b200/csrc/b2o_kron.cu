@@ -31,7 +31,19 @@ struct KronArgs {
   float alpha, beta;
   unsigned long long *bar;
   unsigned long long bar_target;
+  unsigned long long *dbg;      // optional timeline of CTA 0 (%globaltimer, ns): [0] start [1] setup done [2+4*ph] first stage landed
+                                // [3+4*ph] accumulator complete [4+4*ph] epilogue done [5+4*ph] phase end/barrier passed [10] exit
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define KR_STAMP(idx)                                                     \
+  do {                                                                   \
+    if (p.dbg && blockIdx.x == 0) p.dbg[idx] = gtimer();                  \
+  } while (0)
 
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tm, int c0, int c1, uint64_t *bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
@@ -75,6 +87,53 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(const void *smem) {
   return d;
 }
 
+// the kron launch is latency-bound (tens of CTAs): poll the barrier without sleeping
+__device__ __forceinline__ void grid_barrier_tight(unsigned long long *ctr, unsigned long long target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1ULL);
+    while (ld_acquire_u64(ctr) < target) {}
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// epilogue helpers: the per-element branches (result type, beta, bounds) are hoisted out of the 32-column loops
+template <bool F32, bool BETA>
+__device__ __forceinline__ void kron_store_cols(void *res, size_t off, int M, float alpha, float beta, const uint32_t (&v)[32], int nvalid) {
+  if (nvalid >= 32) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      float z = alpha * __uint_as_float(v[e]);
+      if (F32) {
+        float *dst = reinterpret_cast<float *>(res) + off + (size_t)e * M;
+        if (BETA) z += beta * *dst;
+        *dst = z;
+      } else {
+        __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(res) + off + (size_t)e * M;
+        if (BETA) z += beta * __bfloat162float(*dst);
+        *dst = __float2bfloat16_rn(z);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      if (e >= nvalid) continue;   // static register indices: v[] must stay in registers
+      float z = alpha * __uint_as_float(v[e]);
+      if (F32) {
+        float *dst = reinterpret_cast<float *>(res) + off + (size_t)e * M;
+        if (BETA) z += beta * *dst;
+        *dst = z;
+      } else {
+        __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(res) + off + (size_t)e * M;
+        if (BETA) z += beta * __bfloat162float(*dst);
+        *dst = __float2bfloat16_rn(z);
+      }
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(KR_THREADS, 1)
 kron_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmX,
@@ -88,6 +147,13 @@ kron_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_con
   __shared__ __align__(8) uint64_t full[KR_STAGES], empty[KR_STAGES], tmem_full, tmem_empty;
   __shared__ uint32_t s_tmem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) KR_STAMP(0);
+  if (threadIdx.x == 32) {   // hide the descriptor fetches behind the setup
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB2) : "memory");
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < KR_STAGES; ++s) {
@@ -106,6 +172,7 @@ kron_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
+  if (threadIdx.x == 0) KR_STAMP(1);
 
   uint32_t stage = 0, sphase = 0;   // smem ring position (producer and MMA warp each keep their own copy)
   uint32_t tphase = 0;              // accumulator hand-over parity (MMA warp and epilogue warps)
@@ -148,6 +215,7 @@ kron_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_con
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full[stage], sphase);
           tc_fence_after();
+          if (lane == 0 && kb == 0 && t == (int)blockIdx.x) KR_STAMP(2 + 4 * ph);
           if (lane == 0) {
             unsigned char *sa = smem + (size_t)stage * STAGE_BYTES;
             const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + A_BYTES);
@@ -169,65 +237,61 @@ kron_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_con
         const int m0 = (t / nt) * KR_BM, n0 = (t % nt) * BN;
         mbar_wait(&tmem_full, tphase);
         tc_fence_after();
+        if (warp == 2 && lane == 0 && t == (int)blockIdx.x) KR_STAMP(3 + 4 * ph);
         const int r = m0 + quarter * 32 + lane;    // global row of this thread
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t v[32];
           tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+          if (ph == 1 && warp == 2 && lane == 0 && t == (int)blockIdx.x) KR_STAMP(11 + 2 * (c0 / 32));
           if (r < Mrows) {
             if (ph == 0) {
-              // Y[(b*M + r) * ldy + j] with global column jj = b*N1 + j
+              // Y[(b*M + r) * 2*ldy + j] (hi) / + ldy (lo), global column jj = b*N1 + j
+              const int jj0 = n0 + c0;
+              const int b0 = jj0 / p.N1, j0 = jj0 - b0 * p.N1;
+              if (jj0 + 32 <= Ncols && j0 + 32 <= p.N1) {
+                // fast path: the 32 columns belong to one right-hand side; 16-byte stores (j0 is a multiple of 8, ldy of 64)
+                __nv_bfloat16 *dst = p.Y + ((size_t)b0 * p.M + r) * (2 * (size_t)p.ldy) + j0;
 #pragma unroll
-              for (int g = 0; g < 32; g += 8) {
-                const int jj = n0 + c0 + g;
-                if (jj < Ncols) {
-                  const int b = jj / p.N1, j = jj - b * p.N1;
-                  __nv_bfloat16 *dst = p.Y + ((size_t)b * p.M + r) * (2 * (size_t)p.ldy) + j;
-                  if (j + 8 <= p.N1 && ((uintptr_t)dst & 15) == 0) {
-                    uint32_t hi[4], lo[4];
+                for (int g = 0; g < 32; g += 8) {
+                  uint32_t hi[4], lo[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                      const float y0 = __uint_as_float(v[g + 2 * e]), y1 = __uint_as_float(v[g + 2 * e + 1]);
-                      const __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
-                      const __nv_bfloat162 l = __floats2bfloat162_rn(y0 - __low2float(h), y1 - __high2float(h));
-                      hi[e] = *reinterpret_cast<const uint32_t *>(&h);
-                      lo[e] = *reinterpret_cast<const uint32_t *>(&l);
-                    }
-                    *reinterpret_cast<uint4 *>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4 *>(dst + p.ldy) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                  } else {
-                    for (int e = 0; e < 8; ++e) {
-                      const int jje = jj + e;
-                      if (jje < Ncols) {
-                        const int be = jje / p.N1, je = jje - be * p.N1;
-                        const float y = __uint_as_float(v[g + e]);
-                        const __nv_bfloat16 h = __float2bfloat16_rn(y);
-                        __nv_bfloat16 *d1 = p.Y + ((size_t)be * p.M + r) * (2 * (size_t)p.ldy) + je;
-                        d1[0] = h;
-                        d1[p.ldy] = __float2bfloat16_rn(y - __bfloat162float(h));
-                      }
-                    }
+                  for (int e = 0; e < 4; ++e) {
+                    const float y0 = __uint_as_float(v[g + 2 * e]), y1 = __uint_as_float(v[g + 2 * e + 1]);
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
+                    const __nv_bfloat162 l = __floats2bfloat162_rn(y0 - __low2float(h), y1 - __high2float(h));
+                    hi[e] = *reinterpret_cast<const uint32_t *>(&h);
+                    lo[e] = *reinterpret_cast<const uint32_t *>(&l);
+                  }
+                  *reinterpret_cast<uint4 *>(dst + g) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                  *reinterpret_cast<uint4 *>(dst + g + p.ldy) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                  const int jje = jj0 + e;
+                  if (jje < Ncols) {
+                    const int be = jje / p.N1, je = jje - be * p.N1;
+                    const float y = __uint_as_float(v[e]);
+                    const __nv_bfloat16 h = __float2bfloat16_rn(y);
+                    __nv_bfloat16 *d1 = p.Y + ((size_t)be * p.M + r) * (2 * (size_t)p.ldy) + je;
+                    d1[0] = h;
+                    d1[p.ldy] = __float2bfloat16_rn(y - __bfloat162float(h));
                   }
                 }
               }
             } else {
               // res_b[j*M + i] = α·Z (+ β·res), rows r = b*M + i; lanes of a warp write consecutive i: coalesced
               const int b = r / p.M, i = r - b * p.M;
-              const size_t off = (size_t)b * p.M * p.N2 + i;
-#pragma unroll
-              for (int e = 0; e < 32; ++e) {
-                const int j = n0 + c0 + e;
-                if (j < Ncols) {
-                  float z = p.alpha * __uint_as_float(v[e]);
-                  if (p.out_f32) {
-                    float *dst = reinterpret_cast<float *>(p.res) + off + (size_t)j * p.M;
-                    if (p.beta != 0.f) z += p.beta * *dst;
-                    *dst = z;
-                  } else {
-                    __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(p.res) + off + (size_t)j * p.M;
-                    if (p.beta != 0.f) z += p.beta * __bfloat162float(*dst);
-                    *dst = __float2bfloat16_rn(z);
-                  }
+              const size_t off = (size_t)b * p.M * p.N2 + i + (size_t)(n0 + c0) * p.M;
+              const int nvalid = Ncols - (n0 + c0);
+              if (nvalid > 0) {
+                if (p.out_f32) {
+                  if (p.beta != 0.f) kron_store_cols<true, true>(p.res, off, p.M, p.alpha, p.beta, v, nvalid);
+                  else kron_store_cols<true, false>(p.res, off, p.M, p.alpha, p.beta, v, nvalid);
+                } else {
+                  if (p.beta != 0.f) kron_store_cols<false, true>(p.res, off, p.M, p.alpha, p.beta, v, nvalid);
+                  else kron_store_cols<false, false>(p.res, off, p.M, p.alpha, p.beta, v, nvalid);
                 }
               }
             }
@@ -235,18 +299,22 @@ kron_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_con
         }
         tc_fence_before();
         __syncwarp();
+        if (ph == 1 && warp == 2 && lane == 0 && t == (int)blockIdx.x) KR_STAMP(15);
         if (lane == 0) mbar_arrive(&tmem_empty);
+        if (warp == 2 && lane == 0 && t == (int)blockIdx.x) KR_STAMP(4 + 4 * ph);
         tphase ^= 1u;
       }
       if (ph == 0) asm volatile("fence.proxy.async;" ::: "memory");
     }
     if (ph == 0) {
-      grid_barrier(p.bar, bar_target);   // all of Y is written before any CTA starts streaming it
+      grid_barrier_tight(p.bar, bar_target);   // all of Y is written before any CTA starts streaming it
       bar_target += gridDim.x;
+      if (threadIdx.x == 0) KR_STAMP(5);
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) KR_STAMP(10);
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
 }
 
@@ -301,7 +369,7 @@ struct b2o_kron_s {
   int ldArm, ldBrm;
   __nv_bfloat16 *Y[2] = {nullptr, nullptr};   // [0] prod, [1] tprod workspaces ([hi|lo] rows, zero padded)
   size_t y_elems[2] = {0, 0};
-  CUtensorMap tmA1[2], tmB2[2][2], tmY[2][2];   // [direction][BN==64]; fixed operands are encoded once at create
+  CUtensorMap tmA1[2], tmB2[2][3], tmY[2][2];   // [direction][BN index: 128, 64, 32]; fixed operands are encoded once at create
   int y_rows[2] = {0, 0};              // rows (nb*M) the cached Y map was encoded for
   CUtensorMap tmX[2];                  // last x map per direction (re-encoded only when x / nb / BN change)
   const void *x_last[2] = {nullptr, nullptr};
@@ -348,8 +416,8 @@ extern "C" int b2o_kron_create(b2o_ctx *ctx, int dtype, const void *A, int64_t m
   // prod : A1 = B row-major [p × q], B2 = A row-major [m × n];   tprod: A1 = Bᵀ = [q × p] (B as stored), B2 = Aᵀ = [n × m]
   int st = make_tmap(&k->tmA1[0], k->Brm, p, q, k->ldBrm, KR_BM);
   if (st == B2O_OK) st = make_tmap(&k->tmA1[1], k->B, q, p, p, KR_BM);
-  for (int w = 0; w < 2 && st == B2O_OK; ++w) {
-    const int bn = w ? 64 : 128;
+  for (int w = 0; w < 3 && st == B2O_OK; ++w) {
+    const int bn = 128 >> w;
     st = make_tmap(&k->tmB2[0][w], k->Arm, m, n, k->ldArm, bn);                       // prod : B2 = A row-major [m × n]
     if (st == B2O_OK) st = make_tmap(&k->tmB2[1][w], k->A, n, m, m, bn);              // tprod: B2 = Aᵀ = [n × m], A as stored
   }
@@ -423,10 +491,12 @@ extern "C" int b2o_kron_apply(b2o_kron *k, int trans, void *res, int res_dtype, 
   a.alpha = (float)alpha;
   a.beta = (float)beta;
   a.bar = c->d_bar;
+  a.dbg = c->kron_debug ? (unsigned long long *)(c->d_dots + 448) : nullptr;
   const int t0 = ((M + KR_BM - 1) / KR_BM), t1rows = ((nb * M + KR_BM - 1) / KR_BM);
-  // narrower N tiles when the problem has few tiles (latency-bound sizes like 512^3)
-  const bool bn64 = (int64_t)t0 * ((int64_t)nb * N1 + 127) / 128 < c->num_sms / 2;
-  const int BN = bn64 ? 64 : 128;
+  // narrower N tiles when the problem has few tiles (latency-bound sizes like 512^3): more CTAs, fewer bytes per CTA
+  int w = 0;
+  while (w < 2 && (int64_t)t0 * (((int64_t)nb * N1 + (128 >> w) - 1) / (128 >> w)) < c->num_sms / 2) ++w;
+  const int BN = 128 >> w;
   const int tiles0 = t0 * ((nb * N1 + BN - 1) / BN), tiles1 = t1rows * ((N2 + BN - 1) / BN);
   int grid = std::max(1, std::min(c->num_sms, std::max(tiles0, tiles1)));
   a.bar_target = c->bar_base + (unsigned long long)grid;
@@ -438,9 +508,10 @@ extern "C" int b2o_kron_apply(b2o_kron *k, int trans, void *res, int res_dtype, 
     k->x_bn[d] = BN;
   }
   // Y rows beyond nb*M hold stale (finite) data from larger batches; phase 1 masks its rows with Mrows = nb*M
-  const CUtensorMap &tY = k->tmY[d][0], &tB2 = k->tmB2[d][bn64 ? 1 : 0];
-  int st = bn64 ? kron_launch<64>(c, k->tmA1[d], k->tmX[d], tY, tB2, a, grid)
-                : kron_launch<128>(c, k->tmA1[d], k->tmX[d], tY, tB2, a, grid);
+  const CUtensorMap &tY = k->tmY[d][0], &tB2 = k->tmB2[d][w];
+  int st = w == 2   ? kron_launch<32>(c, k->tmA1[d], k->tmX[d], tY, tB2, a, grid)
+           : w == 1 ? kron_launch<64>(c, k->tmA1[d], k->tmX[d], tY, tB2, a, grid)
+                    : kron_launch<128>(c, k->tmA1[d], k->tmX[d], tY, tB2, a, grid);
   if (st == B2O_OK) c->bar_base += (unsigned long long)grid;
   return st;
 }
