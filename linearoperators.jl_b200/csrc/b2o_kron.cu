@@ -20,7 +20,9 @@
 #include <dlfcn.h>
 #include <algorithm>
 
-constexpr int KR_BM = 128, KR_BK = 64, KR_STAGES = 4, KR_THREADS = 192;
+constexpr int KR_BM = 128, KR_BK = 64, KR_MAX_STAGES = 12, KR_THREADS = 192;
+// ring depth: the per-SM stream is latency-bound (Little: bytes in flight / L2 latency), so use what shared memory allows
+__host__ __device__ constexpr int kr_stages(int BN) { return (200 * 1024) / (KR_BM * KR_BK * 2 + BN * KR_BK * 2) > KR_MAX_STAGES ? KR_MAX_STAGES : (200 * 1024) / (KR_BM * KR_BK * 2 + BN * KR_BK * 2); }
 
 struct KronArgs {
   int M, K1, N1, N2, nb;        // see header comment; phase-1 K = N1
@@ -140,6 +142,7 @@ kron_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_con
                       const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmB2,
                       const __grid_constant__ KronArgs p) {
   constexpr uint32_t A_BYTES = KR_BM * KR_BK * 2, B_BYTES = BN * KR_BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int KR_STAGES = kr_stages(BN);
   // instruction descriptor: D=F32, A=B=BF16, both K-major, N=BN, M=128
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(KR_BM >> 4) << 24);
   extern __shared__ unsigned char smem_raw[];
@@ -449,7 +452,7 @@ extern "C" int b2o_kron_destroy(b2o_kron *k) {
 template <int BN>
 static int kron_launch(b2o_ctx *c, const CUtensorMap &tA1, const CUtensorMap &tX, const CUtensorMap &tY, const CUtensorMap &tB2,
                        KronArgs &a, int grid) {
-  const size_t smem = (size_t)KR_STAGES * (KR_BM * KR_BK * 2 + BN * KR_BK * 2) + 1024;
+  const size_t smem = (size_t)kr_stages(BN) * (KR_BM * KR_BK * 2 + BN * KR_BK * 2) + 1024;
   static thread_local bool configured = false;
   if (!configured) {
     B2O_CUDA(cudaFuncSetAttribute(kron_gemm_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
