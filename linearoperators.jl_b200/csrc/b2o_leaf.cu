@@ -176,6 +176,96 @@ extern "C" int b2o_zeros_apply(b2o_ctx *c, int dtype, int64_t nrow, int64_t ncol
   return ew_launch<EW_ZEROS>(c, p);
 }
 
+// ------------------------------------------------------------------ opOnes: sum pass + fill pass in one cooperative launch
+struct OnesArgs {
+  const double *v;
+  double *res;
+  int64_t ncol, nrow;
+  double alpha, beta;
+  double *partials;
+  unsigned long long *bar;
+  unsigned long long bar_target;
+  int vvec, rvec;
+};
+__global__ void __launch_bounds__(512) ones_kernel(const __grid_constant__ OnesArgs p) {
+  __shared__ double sred[16];
+  __shared__ double s_c;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  double a0 = 0.0, a1 = 0.0;
+  if (p.vvec) {
+    const int64_t nvec = p.ncol >> 1;
+    for (int64_t i = tid; i < nvec; i += nth) {
+      double2 x = ldg_stream2(p.v + 2 * i);
+      a0 += x.x;
+      a1 += x.y;
+    }
+    if ((p.ncol & 1) && tid == 0) a0 += p.v[p.ncol - 1];
+  } else {
+    for (int64_t i = tid; i < p.ncol; i += nth) a0 += p.v[i];
+  }
+  double s = warp_sum(a0 + a1);
+  if (lane == 0) sred[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sred[w];
+    p.partials[blockIdx.x] = t;
+  }
+  grid_barrier(p.bar, p.bar_target);
+  if (warp == 0) {
+    double t = 0.0;
+    for (int b = lane; b < (int)gridDim.x; b += 32) t += __ldcg(&p.partials[b]);
+    t = warp_sum(t);
+    if (lane == 0) s_c = p.alpha * t;                 // α * sum(v)                 special-operators.jl:81
+  }
+  __syncthreads();
+  const double cst = s_c;
+  const bool need_r = p.beta != 0.0;
+  if (p.rvec) {
+    const int64_t nvec = p.nrow >> 1;
+    for (int64_t i = tid; i < nvec; i += nth) {
+      double2 o = make_double2(cst, cst);
+      if (need_r) {
+        double2 r = *reinterpret_cast<const double2 *>(p.res + 2 * i);
+        o.x = cst + p.beta * r.x;
+        o.y = cst + p.beta * r.y;
+      }
+      stg_stream2(p.res + 2 * i, o);
+    }
+    if ((p.nrow & 1) && tid == 0) p.res[p.nrow - 1] = need_r ? cst + p.beta * p.res[p.nrow - 1] : cst;
+  } else {
+    for (int64_t i = tid; i < p.nrow; i += nth) p.res[i] = need_r ? cst + p.beta * p.res[i] : cst;
+  }
+}
+static int ones_fused(b2o_ctx *c, double *res, int64_t nrow, const double *v, int64_t ncol, double alpha, double beta) {
+  static thread_local int blocks_per_sm = 0;
+  if (!blocks_per_sm) {
+    B2O_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, ones_kernel, 512, 0));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+  }
+  OnesArgs p;
+  p.v = v;
+  p.res = res;
+  p.ncol = ncol;
+  p.nrow = nrow;
+  p.alpha = alpha;
+  p.beta = beta;
+  p.partials = c->d_partials;
+  p.bar = c->d_bar;
+  p.vvec = ((uintptr_t)v % 16) == 0;
+  p.rvec = ((uintptr_t)res % 16) == 0;
+  const int64_t want = (std::max(nrow, ncol) / 2 + 511) / 512;
+  int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->num_sms * std::min(blocks_per_sm, 4)));
+  grid = std::min(grid, B2O_MAX_GRID);
+  p.bar_target = c->bar_base + (unsigned long long)grid;
+  void *kargs[] = {(void *)&p};
+  B2O_CUDA(cudaLaunchCooperativeKernel((const void *)ones_kernel, dim3(grid), dim3(512), kargs, 0, c->stream));
+  c->bar_base += (unsigned long long)grid;
+  c->launches++;
+  return B2O_OK;
+}
+
 // ------------------------------------------------------------------ sums (opOnes) -- pair_dots with v = null means "times one"
 extern "C" int b2o_ones_apply(b2o_ctx *c, int dtype, int64_t nrow, int64_t ncol, void *res, int64_t res_len, const void *v,
                               int64_t v_len, double alpha, double beta) {
@@ -185,6 +275,7 @@ extern "C" int b2o_ones_apply(b2o_ctx *c, int dtype, int64_t nrow, int64_t ncol,
   if ((nrow > 0 && !res) || (ncol > 0 && !v)) B2O_FAIL(B2O_EARG, "null vector");
   B2O_TRY(check_ptrs8(nullptr, v, res));
   B2O_CUDA(cudaSetDevice(c->device));
+  if (c->nranks <= 1 && nrow > 0) return ones_fused(c, (double *)res, nrow, (const double *)v, ncol, alpha, beta);
   const double *u[1] = {(const double *)v}, *w[1] = {nullptr};
   B2O_TRY(b2o_pair_dots(c, 1, u, w, ncol, c->d_dots + 320));   // sum(v), all-reduced when row-partitioned
   EwArgs p;

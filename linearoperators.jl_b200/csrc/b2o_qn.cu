@@ -381,7 +381,7 @@ static void compact_columns(const b2o_qn *q, CompactArgs &a, double alpha, doubl
 
 // one launch of the compact kernel over rows [r0, r1) (r0 a multiple of the pitch alignment)
 static int compact_launch_rows(b2o_qn *q, const CompactArgs &base, double *res, const double *x, int64_t r0, int64_t r1, int mode,
-                               int accumulate, cudaStream_t stream_override = nullptr, bool use_override = false) {
+                               int accumulate) {
   b2o_ctx *c = q->ctx;
   CompactArgs a = base;
   for (int i = 0; i < a.ncols; ++i) a.cols[i] += r0;
@@ -410,8 +410,6 @@ static int compact_launch_rows(b2o_qn *q, const CompactArgs &base, double *res, 
   if (coop) a.bar_target = c->bar_base + (unsigned long long)cfg.grid;
   b2o_mbox_fill(c, &a.mbox);
   if (!coop) a.mbox.nranks = 1;
-  (void)stream_override;
-  (void)use_override;
   int st = (q->kind == 0 && q->inverse) ? launch_compact_R<OP_INV_COMPACT>(c, cfg, a, coop)
            : q->kind == 0             ? launch_compact_R<OP_LBFGS_FWD>(c, cfg, a, coop)
                                       : launch_compact_R<OP_LSR1>(c, cfg, a, coop);
@@ -1214,6 +1212,8 @@ extern "C" int b2o_qn_set_col(b2o_qn *q, int which, int k0, const void *src) {
   double *base = qn_base(q, which);
   if (!base || k0 < 0 || k0 >= q->mem) B2O_FAIL(B2O_EARG, "no such column (which=%d, k0=%d)", which, k0);
   B2O_CUDA(cudaMemcpyAsync(q->col(base, k0), src, (size_t)q->n * sizeof(double), cudaMemcpyDeviceToDevice, q->ctx->stream));
+  if (q->inv_compact && (which == 0 || which == 1)) B2O_TRY(update_gram(q, k0));   // imported pair: refresh its Gram row/column
+  q->w_dirty = true;
   return B2O_OK;
 }
 extern "C" int b2o_qn_get_scalars(b2o_qn *q, int *insert1, double *gamma, double *opnorm_ub, double *ys, double *aux) {
@@ -1244,5 +1244,6 @@ extern "C" int b2o_qn_set_scalars(b2o_qn *q, int insert1, double gamma, double o
   q->opnorm_ub = opnorm_ub;
   if (ys) q->ys.assign(ys, ys + q->mem);
   if (aux) q->aux.assign(aux, aux + q->mem);
+  q->w_dirty = true;
   return B2O_OK;
 }
