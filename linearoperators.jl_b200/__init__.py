@@ -20,3 +20,4 @@ from .special_operators import (BlockDiagonalOperator, LocalBlockOfDiagonal, get
                                 opOnes, opRestriction, opZeros)
 
 __version__ = "0.1.0"
+from .utilities import check_ctranspose, check_hermitian, check_positive_definite, normest  # noqa: F401,E402

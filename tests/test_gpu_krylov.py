@@ -63,3 +63,32 @@ def test_cg_on_fused_spd_chain(lo, ctx):
     res = tree * x - b
     assert np.sqrt(ctx.dot(res, res) / ctx.dot(b, b)) <= 1e-9
     assert lo.nprod(A) == its
+
+
+def test_reference_check_predicates_and_normest(lo, ctx):
+    """check_hermitian / check_positive_definite / check_ctranspose / normest (src/utilities.jl:20-149) -- the predicates the
+    reference's own test-suite applies to its operators (test/test_lbfgs.jl:48-52) -- on the CUDA operators"""
+    n = 50001
+    B = lo.LBFGSOperator(n, mem=5, ctx=ctx)
+    H = lo.InverseLBFGSOperator(n, mem=5, ctx=ctx)
+    for i in range(7):
+        s = ctx.uniform(n, 100 + i)
+        y = s + 0.1 * ctx.uniform(n, 200 + i)
+        lo.push_(B, s, y)
+        lo.push_(H, s, y)
+    d = ctx.uniform(n, 1, 0.5, 2.0)
+    D = lo.opDiagonal(d)
+    h = ctx.uniform(n, 3)
+    h /= float(np.sqrt(ctx.dot(h, h)))
+    P = lo.opRestriction(np.arange(1, n + 1, 3), n)
+    for op in (B, H, D, lo.opHouseholder(h) * D * lo.opHouseholder(h)):
+        assert lo.check_hermitian(op) and lo.check_ctranspose(op)
+    assert lo.check_positive_definite(B) and lo.check_positive_definite(H) and lo.check_positive_definite(D)
+    assert lo.check_ctranspose(P) and lo.check_ctranspose(lo.opHouseholder(h) * D)
+    assert not lo.check_positive_definite(-D)
+    e, cnt = lo.normest(D)
+    assert abs(e - float(d.max())) <= 1e-6 * float(d.max()) or cnt > 100
+    e, _ = lo.normest(lo.opHouseholder(h))
+    assert abs(e - 1.0) <= 1e-8
+    with pytest.raises(lo.LinearOperatorException):
+        lo.check_hermitian(P)
