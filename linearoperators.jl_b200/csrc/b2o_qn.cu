@@ -24,7 +24,8 @@ struct b2o_qn_s {
   int ins0 = 0;
   // optional compact-representation inverse apply: Gram matrices by ring slot, device middle matrix
   bool inv_compact = false, w_dirty = true;
-  std::vector<double> SY, YY;   // [mem*mem]: SY[i*mem+j] = s_i·y_j, YY[i*mem+j] = y_i·y_j
+  bool fwd_compact = false;     // forward operator in compact form: state = S, Y + Gram matrices; push! is O(m) dots, not O(m^2) passes
+  std::vector<double> SY, YY, SS;   // [mem*mem]: SY[i*mem+j] = s_i·y_j, YY[i*mem+j] = y_i·y_j, SS[i*mem+j] = s_i·s_j
   double *d_W = nullptr;        // [(2*mem)^2]
   double *h_W = nullptr;        // pinned staging
   double *col(double *base, int k0) const { return base + (size_t)k0 * (size_t)pitch; }
@@ -350,8 +351,8 @@ static void compact_columns(const b2o_qn *q, CompactArgs &a, double alpha, doubl
   int slots[B2O_MAX_MEM];
   const int na = active_old_to_new(q, slots);
   memset(&a, 0, sizeof(a));
-  if (q->kind == 0 && q->inverse) {
-    // compact inverse: columns [s_old..s_new, y_old..y_new]
+  if (q->kind == 0 && (q->inverse || q->fwd_compact)) {
+    // compact forms: columns [s_old..s_new, y_old..y_new]
     for (int i = 0; i < na; ++i) {
       a.cols[i] = q->col(q->S, slots[i]);
       a.cols[na + i] = q->col(q->Y, slots[i]);
@@ -359,6 +360,7 @@ static void compact_columns(const b2o_qn *q, CompactArgs &a, double alpha, doubl
     }
     a.ncols = 2 * na;
     a.W = q->d_W;
+    a.base_div = q->inverse ? 0 : 1;
   } else if (q->kind == 0) {
     for (int i = 0; i < na; ++i) {
       a.cols[2 * i] = q->col(q->A, slots[i]);
@@ -410,7 +412,7 @@ static int compact_launch_rows(b2o_qn *q, const CompactArgs &base, double *res, 
   if (coop) a.bar_target = c->bar_base + (unsigned long long)cfg.grid;
   b2o_mbox_fill(c, &a.mbox);
   if (!coop) a.mbox.nranks = 1;
-  int st = (q->kind == 0 && q->inverse) ? launch_compact_R<OP_INV_COMPACT>(c, cfg, a, coop)
+  int st = (q->kind == 0 && (q->inverse || q->fwd_compact)) ? launch_compact_R<OP_INV_COMPACT>(c, cfg, a, coop)
            : q->kind == 0             ? launch_compact_R<OP_LBFGS_FWD>(c, cfg, a, coop)
                                       : launch_compact_R<OP_LSR1>(c, cfg, a, coop);
   if (st == B2O_OK && coop) {
@@ -556,7 +558,70 @@ static int build_inverse_W(b2o_qn *q) {
   return B2O_OK;
 }
 
+// Compact FORWARD form (Byrd, Nocedal, Schnabel 1994, Thm 2.3) with B0 = I/γ:
+//   B = B0 - [B0 S  Y] [[SᵀB0S, L], [Lᵀ, -D]]^{-1} [SᵀB0; Yᵀ],   L_ij = s_i·y_j (i > j), D = diag(s_i·y_i)
+// so  B x = x/γ + [S Y] W' [Sᵀx; Yᵀx]  with  W' = -diag(1/γ, 1) M^{-1} diag(1/γ, 1).  M is 2A x 2A, inverted on the host
+// (Gauss-Jordan with partial pivoting, long double).
+static int build_forward_W(b2o_qn *q) {
+  b2o_ctx *c = q->ctx;
+  int sl[B2O_MAX_MEM];
+  const int A = active_old_to_new(q, sl), m = q->mem, N = 2 * A;
+  if (A == 0) {
+    q->w_dirty = false;
+    return B2O_OK;
+  }
+  const long double g = q->scaling ? (long double)q->gamma : 1.0L;
+  std::vector<long double> M((size_t)N * N, 0.0L), Inv((size_t)N * N, 0.0L);
+  for (int i = 0; i < A; ++i)
+    for (int j = 0; j < A; ++j) {
+      M[(size_t)i * N + j] = (long double)q->SS[(size_t)sl[i] * m + sl[j]] / g;
+      const long double Lij = (i > j) ? (long double)q->SY[(size_t)sl[i] * m + sl[j]] : 0.0L;
+      M[(size_t)i * N + A + j] = Lij;
+      M[(size_t)(A + j) * N + i] = Lij;
+      M[(size_t)(A + i) * N + A + j] = (i == j) ? -(long double)q->SY[(size_t)sl[i] * m + sl[i]] : 0.0L;
+    }
+  for (int i = 0; i < N; ++i) Inv[(size_t)i * N + i] = 1.0L;
+  for (int col = 0; col < N; ++col) {
+    int piv = col;
+    for (int r = col + 1; r < N; ++r)
+      if (fabsl(M[(size_t)r * N + col]) > fabsl(M[(size_t)piv * N + col])) piv = r;
+    if (M[(size_t)piv * N + col] == 0.0L) B2O_FAIL(B2O_ESTATE, "compact forward L-BFGS: singular middle matrix");
+    if (piv != col)
+      for (int k = 0; k < N; ++k) {
+        std::swap(M[(size_t)piv * N + k], M[(size_t)col * N + k]);
+        std::swap(Inv[(size_t)piv * N + k], Inv[(size_t)col * N + k]);
+      }
+    const long double d = M[(size_t)col * N + col];
+    for (int k = 0; k < N; ++k) {
+      M[(size_t)col * N + k] /= d;
+      Inv[(size_t)col * N + k] /= d;
+    }
+    for (int r = 0; r < N; ++r) {
+      if (r == col) continue;
+      const long double f = M[(size_t)r * N + col];
+      if (f == 0.0L) continue;
+      for (int k = 0; k < N; ++k) {
+        M[(size_t)r * N + k] -= f * M[(size_t)col * N + k];
+        Inv[(size_t)r * N + k] -= f * Inv[(size_t)col * N + k];
+      }
+    }
+  }
+  double *W = q->h_W;
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < N; ++j) {
+      long double v = -Inv[(size_t)i * N + j];
+      if (i < A) v /= g;
+      if (j < A) v /= g;
+      W[(size_t)i * N + j] = (double)v;
+    }
+  B2O_CUDA(cudaMemcpyAsync(q->d_W, W, sizeof(double) * N * N, cudaMemcpyHostToDevice, c->stream));
+  B2O_CUDA(cudaStreamSynchronize(c->stream));
+  q->w_dirty = false;
+  return B2O_OK;
+}
+
 static int qn_apply_dev(b2o_qn *q, double *res, const double *x, double alpha, double beta) {
+  if (q->kind == 0 && !q->inverse && q->fwd_compact && q->w_dirty) B2O_TRY(build_forward_W(q));
   if (q->kind == 0 && q->inverse) {
     if (!q->inv_compact) return qn_apply_twoloop(q, res, x, alpha, beta);
     if (q->w_dirty) B2O_TRY(build_inverse_W(q));
@@ -564,7 +629,7 @@ static int qn_apply_dev(b2o_qn *q, double *res, const double *x, double alpha, d
   return qn_apply_compact(q, res, x, alpha, beta);
 }
 
-// Gram entries involving ring slot `k` (after s_k, y_k were stored): s_k·y_j, s_j·y_k, y_k·y_j for every slot j
+// Gram entries involving ring slot `k` (after s_k, y_k were stored): s_k·y_j, s_j·y_k, y_k·y_j (and s_k·s_j) for every slot j
 static int update_gram(b2o_qn *q, int k) {
   b2o_ctx *c = q->ctx;
   const int m = q->mem;
@@ -576,6 +641,7 @@ static int update_gram(b2o_qn *q, int k) {
       u[np] = sk; v[np] = q->col(q->Y, j); idx[np][0] = 0; idx[np][1] = j; np++;   // s_k·y_j
       u[np] = q->col(q->S, j); v[np] = yk; idx[np][0] = 1; idx[np][1] = j; np++;   // s_j·y_k
       u[np] = yk; v[np] = q->col(q->Y, j); idx[np][0] = 2; idx[np][1] = j; np++;   // y_k·y_j
+      if (q->fwd_compact) { u[np] = sk; v[np] = q->col(q->S, j); idx[np][0] = 3; idx[np][1] = j; np++; }   // s_k·s_j
     }
     double h[8];
     B2O_TRY(b2o_pair_dots(c, np, u, v, q->n, c->d_dots + 300));
@@ -584,7 +650,8 @@ static int update_gram(b2o_qn *q, int k) {
       const int j = idx[p][1];
       if (idx[p][0] == 0) q->SY[(size_t)k * m + j] = h[p];
       else if (idx[p][0] == 1) q->SY[(size_t)j * m + k] = h[p];
-      else q->YY[(size_t)k * m + j] = q->YY[(size_t)j * m + k] = h[p];
+      else if (idx[p][0] == 2) q->YY[(size_t)k * m + j] = q->YY[(size_t)j * m + k] = h[p];
+      else q->SS[(size_t)k * m + j] = q->SS[(size_t)j * m + k] = h[p];
     }
   }
   q->w_dirty = true;
@@ -614,6 +681,32 @@ extern "C" int b2o_qn_set_option(b2o_qn *q, const char *key, int64_t value) {
       q->w_dirty = true;
     } else if (value == 0) {
       q->inv_compact = false;
+    }
+    return B2O_OK;
+  }
+  if (!strcmp(key, "forward_mode")) {
+    // 0 = the reference's a_k/b_k form (default); 1 = compact form: push! costs O(m) dots instead of O(m^2) vector passes
+    if (!(q->kind == 0 && !q->inverse)) B2O_FAIL(B2O_EARG, "forward_mode applies to the forward LBFGSOperator");
+    if (value != 0 && value != 1) B2O_FAIL(B2O_EARG, "forward_mode must be 0 or 1");
+    b2o_ctx *c = q->ctx;
+    B2O_CUDA(cudaSetDevice(c->device));
+    if (value == 1 && !q->fwd_compact) {
+      const int m = q->mem;
+      if (!q->d_W) {
+        B2O_CUDA(cudaMalloc(&q->d_W, sizeof(double) * 4 * m * m));
+        B2O_CUDA(cudaMallocHost(&q->h_W, sizeof(double) * 4 * m * m));
+      }
+      q->SY.assign((size_t)m * m, 0.0);
+      q->YY.assign((size_t)m * m, 0.0);
+      q->SS.assign((size_t)m * m, 0.0);
+      q->fwd_compact = true;
+      for (int k = 0; k < m; ++k)
+        if (q->ys[k] != 0) B2O_TRY(update_gram(q, k));
+      q->w_dirty = true;
+    } else if (value == 0 && q->fwd_compact) {
+      for (int k = 0; k < q->mem; ++k)
+        if (q->ys[k] != 0) B2O_FAIL(B2O_EUNSUPPORTED, "cannot leave the compact forward mode once pairs were pushed (a_k, b_k were not built); reset! first");
+      q->fwd_compact = false;
     }
     return B2O_OK;
   }
@@ -774,7 +867,13 @@ static int lbfgs_push_common(b2o_qn *q, const double *s, const double *y, double
     q->gamma = ys / yy;
     if (q->gamma != 0) q->opnorm_ub += 1 / q->gamma;
   }
-  if (!q->inverse) {
+  if (!q->inverse && q->fwd_compact) {
+    // compact forward form: no a_k / b_k vectors.  ‖b‖² = y·y / ys keeps opnorm_upper_bound exact (src/lbfgs.jl:231-234).
+    q->opnorm_ub -= q->aux[ins] * q->aux[ins];
+    q->aux[ins] = sqrt(yy / ys);
+    q->opnorm_ub += q->aux[ins] * q->aux[ins];
+    B2O_TRY(update_gram(q, ins));
+  } else if (!q->inverse) {
     double *bi = q->col(q->B, ins);
     q->opnorm_ub -= q->aux[ins] * q->aux[ins];                                                  // :231
     if (n > 0) {
@@ -1058,6 +1157,7 @@ extern "C" int b2o_lbfgs_solve_shifted(b2o_qn *q, void *x_, int64_t x_len, const
   if (!q) B2O_FAIL(B2O_EARG, "null operator");
   if (q->kind != 0 || q->inverse) B2O_FAIL(B2O_EARG, "solve_shifted_system! needs a forward LBFGSOperator");
   if (sigma < 0) B2O_FAIL(B2O_EARG, "σ must be nonnegative");                                   // ArgumentError :213-215
+  if (q->fwd_compact) B2O_FAIL(B2O_EUNSUPPORTED, "solve_shifted_system! needs the a_k/b_k form (forward_mode 0)");
   B2O_TRY(check_vec(q, x_, x_len));
   B2O_TRY(check_vec(q, b_, b_len));
   b2o_ctx *c = q->ctx;
@@ -1144,6 +1244,7 @@ extern "C" int b2o_qn_diag(b2o_qn *q, void *d, int64_t d_len) {
   if (!q) B2O_FAIL(B2O_EARG, "null operator");
   if (q->kind == 0 && q->inverse)
     B2O_FAIL(B2O_ESTATE, "only the diagonal of a forward L-BFGS approximation is available");  // src/lbfgs.jl:380-382
+  if (q->fwd_compact) B2O_FAIL(B2O_EUNSUPPORTED, "diag! needs the a_k/b_k form (forward_mode 0)");
   B2O_TRY(check_vec(q, d, d_len));
   b2o_ctx *c = q->ctx;
   B2O_CUDA(cudaSetDevice(c->device));
@@ -1184,9 +1285,10 @@ extern "C" int b2o_qn_reset(b2o_qn *q) {
   q->gamma = 1.0;
   q->ins0 = 0;
   q->w_dirty = true;
-  if (q->inv_compact) {
+  if (q->inv_compact || q->fwd_compact) {
     std::fill(q->SY.begin(), q->SY.end(), 0.0);
     std::fill(q->YY.begin(), q->YY.end(), 0.0);
+    std::fill(q->SS.begin(), q->SS.end(), 0.0);
   }
   return B2O_OK;
 }
@@ -1212,7 +1314,7 @@ extern "C" int b2o_qn_set_col(b2o_qn *q, int which, int k0, const void *src) {
   double *base = qn_base(q, which);
   if (!base || k0 < 0 || k0 >= q->mem) B2O_FAIL(B2O_EARG, "no such column (which=%d, k0=%d)", which, k0);
   B2O_CUDA(cudaMemcpyAsync(q->col(base, k0), src, (size_t)q->n * sizeof(double), cudaMemcpyDeviceToDevice, q->ctx->stream));
-  if (q->inv_compact && (which == 0 || which == 1)) B2O_TRY(update_gram(q, k0));   // imported pair: refresh its Gram row/column
+  if ((q->inv_compact || q->fwd_compact) && (which == 0 || which == 1)) B2O_TRY(update_gram(q, k0));   // imported pair: refresh its Gram row/column
   q->w_dirty = true;
   return B2O_OK;
 }

@@ -33,6 +33,7 @@ struct CompactArgs {
   uint32_t accs_off, coef_off, bar_off;
   MboxDev mbox;                      // nranks > 1: the dots are all-reduced in-kernel through the NVLink peer mailbox
   const double *W;                   // OP_INV_COMPACT: ncols x ncols middle matrix (row-major), coefficients = W * dots
+  int base_div;                      // OP_INV_COMPACT: base term x/γ (compact FORWARD form) instead of γx (compact inverse)
 };
 
 template <int R, int OP>
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
       } else if (OP == OP_INV_COMPACT) {
         // H0 x = γ x (γ = 1 without scaling)
 #pragma unroll
-        for (int j = 0; j < EPT; ++j) q[j] = p.scaling ? xn[j] * gamma : xn[j];
+        for (int j = 0; j < EPT; ++j) q[j] = !p.scaling ? xn[j] : (p.base_div ? xn[j] / gamma : xn[j] * gamma);
       } else {
         // q .= α .* x ./ γ (.+ β .* q)                                    src/lsr1.jl:92-96
 #pragma unroll

@@ -114,7 +114,7 @@ class LBFGSOperator(AbstractQuasiNewtonOperator):
     """LBFGSOperator(n; mem=5, scaling=true, damped=false, σ₂=0.99, σ₃=10.0) -- forward form, src/lbfgs.jl:168-208.
     InverseLBFGSOperator builds the same type with inverse=True (:112-160)."""
 
-    def __init__(self, n, mem=5, scaling=True, damped=False, sigma2=0.99, sigma3=10.0, inverse=False, ctx=None):
+    def __init__(self, n, mem=5, scaling=True, damped=False, sigma2=0.99, sigma3=10.0, inverse=False, compact=False, ctx=None):
         ctx = ctx or default_context()
         self._common(ctx, n, mem)
         self.scaling, self.damped, self.inverse = bool(scaling), bool(damped), bool(inverse)
@@ -123,6 +123,10 @@ class LBFGSOperator(AbstractQuasiNewtonOperator):
                                             float(sigma3), int(inverse), ctypes.byref(self.handle)))
         self.tprod_ = self.prod_
         self.ctprod_ = self.prod_
+        if compact:
+            # extension (not the reference algorithm): compact representation -- same operator; for the forward form push! then
+            # costs O(m) dots instead of O(m²) vector passes, for the inverse form the apply moves half the bytes
+            self.set_option("inverse_mode" if inverse else "forward_mode", 1)
 
 
 def InverseLBFGSOperator(n, compact=False, **kw):
@@ -130,10 +134,7 @@ def InverseLBFGSOperator(n, compact=False, **kw):
     reference's two-loop recursion to the mathematically identical compact representation (half the DRAM traffic, one
     all-reduce instead of 2m): an extension, not the reference algorithm -- rounding differs."""
     kw.pop("inverse", None)
-    op = LBFGSOperator(n, inverse=True, **kw)
-    if compact:
-        op.set_option("inverse_mode", 1)
-    return op
+    return LBFGSOperator(n, inverse=True, compact=compact, **kw)
 
 
 class LSR1Operator(AbstractQuasiNewtonOperator):

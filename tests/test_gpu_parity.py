@@ -845,3 +845,40 @@ def test_solve_shifted_system(lo, ctx, orc, n, mem, npush, sigma):
         assert np.allclose(host(x2), host(H * b), atol=1e-6, rtol=1e-6)
     with pytest.raises(ValueError):
         lo.solve_shifted_system_(x, g, b, -0.1)
+
+
+@pytest.mark.parametrize("n,mem,npush,scaling,damped", [(10, 5, 3, False, False), (1000, 5, 7, True, False), (100003, 10, 14, True, False),
+                                                         (75776, 20, 20, True, False), (20011, 5, 8, True, True)])
+def test_forward_compact_representation(lo, ctx, orc, n, mem, npush, scaling, damped):
+    """compact FORWARD form (extension): B x = x/γ + [S Y] W [Sᵀx; Yᵀx] -- same operator as the reference's a_k/b_k form
+    (src/lbfgs.jl:173-202), push! without the O(m²) rebuild of the a_k (src/lbfgs.jl:236-250)"""
+    kw = dict(mem=mem, scaling=scaling, damped=damped)
+    Bc = lo.LBFGSOperator(n, compact=True, ctx=ctx, **kw)
+    H = lo.InverseLBFGSOperator(n, mem=mem, scaling=scaling, ctx=ctx)
+    o = orc.LBFGS(n, **kw)
+    for i in range(npush):
+        s = ctx.uniform(n, 100 + i)
+        y = s + 0.1 * ctx.uniform(n, 200 + i) if not damped else ctx.uniform(n, 200 + i, -0.2, 1.0)
+        l0 = ctx.launch_count()
+        lo.push_(Bc, s, y)
+        assert ctx.launch_count() - l0 <= 3 * mem + 8                       # O(m) dots, no O(m²) rebuild
+        acc = o.push(host(s), host(y))
+        assert Bc.last_push_accepted == acc
+        if not damped:
+            lo.push_(H, s, y)
+    assert Bc.data.insert == o.insert
+    assert abs(Bc.data.opnorm_upper_bound - o.opnorm_upper_bound) <= 1e-10 * abs(o.opnorm_upper_bound)
+    x, r0 = ctx.uniform(n, 7), ctx.uniform(n, 8)
+    for alpha, beta in [(1.0, 0.0), (1.5, -0.25)]:
+        res, ref = r0.clone(), host(r0).copy()
+        l0 = ctx.launch_count()
+        lo.mul_(res, Bc, x, alpha, beta)
+        assert ctx.launch_count() - l0 == 1
+        o.apply(host(x), alpha, beta, res=ref)
+        assert rel(host(res), ref) <= 1e-9, rel(host(res), ref)
+    if not damped:
+        assert rel(host(H * (Bc * x)), host(x)) <= 1e-8                      # H·B ≈ I across the two representations
+    with pytest.raises(lo.B2OError):
+        lo.diag(Bc)
+    lo.reset_(Bc)
+    assert np.array_equal(host(Bc * x), host(x))

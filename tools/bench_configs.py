@@ -54,6 +54,37 @@ def main():
     big = "--small" not in sys.argv
     n = 10**8 if big else 10**6
     flush = torch.empty(256 * 2**20 // 8, dtype=torch.float64, device="cuda")
+    if only == ["fwdc"]:
+        v, res = ctx.uniform(n, 7), ctx.empty(n)
+        m = 10
+        for compact in (False, True):
+            B = lo.LBFGSOperator(n, mem=m, compact=compact, ctx=ctx)
+            for i in range(m):                      # fill the memory
+                s = ctx.uniform(n, 100 + i)
+                y = s + 0.1 * ctx.uniform(n, 200 + i)
+                lo.push_(B, s, y)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(5):                      # steady state: memory full, every push evicts
+                s = ctx.uniform(n, 500 + i)
+                y = s + 0.1 * ctx.uniform(n, 600 + i)
+                torch.cuda.synchronize()
+                t1 = time.perf_counter()
+                lo.push_(B, s, y)
+                torch.cuda.synchronize()
+                t0 += time.perf_counter() - t1 - (time.perf_counter() - time.perf_counter())
+                if i == 0:
+                    tp = 0.0
+                tp += time.perf_counter() - t1
+            ms = timeit(lambda: lo.mul_(res, B, v), 20)
+            if not compact:
+                ref = res.clone()
+            line("LBFGSOperator(mem=10) %s" % ("compact form (extension)" if compact else "a_k/b_k form (reference algorithm)"), ms,
+                 (4 * m + 3) * 8.0 * n, push_ms_steady_state=round(tp / 5 * 1e3, 2),
+                 rel_diff_vs_reference_form=(float(torch.linalg.norm(res - ref) / torch.linalg.norm(ref)) if compact else 0.0))
+            del B
+            torch.cuda.empty_cache()
+        return
     if only == ["invc"]:
         v, res = ctx.uniform(n, 7), ctx.empty(n)
         for m in (10, 20):
