@@ -558,34 +558,15 @@ static int build_inverse_W(b2o_qn *q) {
   return B2O_OK;
 }
 
-// Compact FORWARD form (Byrd, Nocedal, Schnabel 1994, Thm 2.3) with B0 = I/γ:
-//   B = B0 - [B0 S  Y] [[SᵀB0S, L], [Lᵀ, -D]]^{-1} [SᵀB0; Yᵀ],   L_ij = s_i·y_j (i > j), D = diag(s_i·y_i)
-// so  B x = x/γ + [S Y] W' [Sᵀx; Yᵀx]  with  W' = -diag(1/γ, 1) M^{-1} diag(1/γ, 1).  M is 2A x 2A, inverted on the host
-// (Gauss-Jordan with partial pivoting, long double).
-static int build_forward_W(b2o_qn *q) {
-  b2o_ctx *c = q->ctx;
-  int sl[B2O_MAX_MEM];
-  const int A = active_old_to_new(q, sl), m = q->mem, N = 2 * A;
-  if (A == 0) {
-    q->w_dirty = false;
-    return B2O_OK;
-  }
-  const long double g = q->scaling ? (long double)q->gamma : 1.0L;
-  std::vector<long double> M((size_t)N * N, 0.0L), Inv((size_t)N * N, 0.0L);
-  for (int i = 0; i < A; ++i)
-    for (int j = 0; j < A; ++j) {
-      M[(size_t)i * N + j] = (long double)q->SS[(size_t)sl[i] * m + sl[j]] / g;
-      const long double Lij = (i > j) ? (long double)q->SY[(size_t)sl[i] * m + sl[j]] : 0.0L;
-      M[(size_t)i * N + A + j] = Lij;
-      M[(size_t)(A + j) * N + i] = Lij;
-      M[(size_t)(A + i) * N + A + j] = (i == j) ? -(long double)q->SY[(size_t)sl[i] * m + sl[i]] : 0.0L;
-    }
+// in-place Gauss-Jordan inverse with partial pivoting (long double); false if singular
+static bool invert_ld(std::vector<long double> &M, std::vector<long double> &Inv, int N) {
+  Inv.assign((size_t)N * N, 0.0L);
   for (int i = 0; i < N; ++i) Inv[(size_t)i * N + i] = 1.0L;
   for (int col = 0; col < N; ++col) {
     int piv = col;
     for (int r = col + 1; r < N; ++r)
       if (fabsl(M[(size_t)r * N + col]) > fabsl(M[(size_t)piv * N + col])) piv = r;
-    if (M[(size_t)piv * N + col] == 0.0L) B2O_FAIL(B2O_ESTATE, "compact forward L-BFGS: singular middle matrix");
+    if (M[(size_t)piv * N + col] == 0.0L) return false;
     if (piv != col)
       for (int k = 0; k < N; ++k) {
         std::swap(M[(size_t)piv * N + k], M[(size_t)col * N + k]);
@@ -606,6 +587,39 @@ static int build_forward_W(b2o_qn *q) {
       }
     }
   }
+  return true;
+}
+
+// middle matrix of the compact forward form for the active pairs (age order): M = [[SᵀS/γ, L], [Lᵀ, -D]]
+static void forward_middle(const b2o_qn *q, const int *sl, int A, long double g, std::vector<long double> &M) {
+  const int m = q->mem, N = 2 * A;
+  M.assign((size_t)N * N, 0.0L);
+  for (int i = 0; i < A; ++i)
+    for (int j = 0; j < A; ++j) {
+      M[(size_t)i * N + j] = (long double)q->SS[(size_t)sl[i] * m + sl[j]] / g;
+      const long double Lij = (i > j) ? (long double)q->SY[(size_t)sl[i] * m + sl[j]] : 0.0L;
+      M[(size_t)i * N + A + j] = Lij;
+      M[(size_t)(A + j) * N + i] = Lij;
+      M[(size_t)(A + i) * N + A + j] = (i == j) ? -(long double)q->SY[(size_t)sl[i] * m + sl[i]] : 0.0L;
+    }
+}
+
+// Compact FORWARD form (Byrd, Nocedal, Schnabel 1994, Thm 2.3) with B0 = I/γ:
+//   B = B0 - [B0 S  Y] [[SᵀB0S, L], [Lᵀ, -D]]^{-1} [SᵀB0; Yᵀ],   L_ij = s_i·y_j (i > j), D = diag(s_i·y_i)
+// so  B x = x/γ + [S Y] W' [Sᵀx; Yᵀx]  with  W' = -diag(1/γ, 1) M^{-1} diag(1/γ, 1).  M is 2A x 2A, inverted on the host
+// (Gauss-Jordan with partial pivoting, long double).
+static int build_forward_W(b2o_qn *q) {
+  b2o_ctx *c = q->ctx;
+  int sl[B2O_MAX_MEM];
+  const int A = active_old_to_new(q, sl), m = q->mem, N = 2 * A;
+  if (A == 0) {
+    q->w_dirty = false;
+    return B2O_OK;
+  }
+  const long double g = q->scaling ? (long double)q->gamma : 1.0L;
+  std::vector<long double> M, Inv;
+  forward_middle(q, sl, A, g, M);
+  if (!invert_ld(M, Inv, N)) B2O_FAIL(B2O_ESTATE, "compact forward L-BFGS: singular middle matrix");
   double *W = q->h_W;
   for (int i = 0; i < N; ++i)
     for (int j = 0; j < N; ++j) {
@@ -1157,7 +1171,58 @@ extern "C" int b2o_lbfgs_solve_shifted(b2o_qn *q, void *x_, int64_t x_len, const
   if (!q) B2O_FAIL(B2O_EARG, "null operator");
   if (q->kind != 0 || q->inverse) B2O_FAIL(B2O_EARG, "solve_shifted_system! needs a forward LBFGSOperator");
   if (sigma < 0) B2O_FAIL(B2O_EARG, "σ must be nonnegative");                                   // ArgumentError :213-215
-  if (q->fwd_compact) B2O_FAIL(B2O_EUNSUPPORTED, "solve_shifted_system! needs the a_k/b_k form (forward_mode 0)");
+  if (q->fwd_compact) {
+    // Woodbury on the compact form: B + σI = τI - Ψ M⁻¹ Ψᵀ, τ = 1/γ + σ, Ψ = [S/γ  Y]  =>
+    //   x = b/τ + [S Y] W'' [Sᵀb; Yᵀb],  W'' = diag(1/γ,1) (τ²M - τG)⁻¹ diag(1/γ,1),  G = ΨᵀΨ from the Gram matrices:
+    // ONE launch of the compact kernel (two passes over S, Y) instead of 2·mem Sherman-Morrison steps.
+    B2O_TRY(check_vec(q, x_, x_len));
+    B2O_TRY(check_vec(q, b_, b_len));
+    b2o_ctx *c = q->ctx;
+    B2O_CUDA(cudaSetDevice(c->device));
+    if (q->n == 0) return B2O_OK;
+    int sl[B2O_MAX_MEM];
+    const int A = active_old_to_new(q, sl), m = q->mem, N = 2 * A;
+    const long double g = (long double)q->gamma;            // B0 = I/γ (γ = 1 without scaling or after reset!)
+    const long double tau = 1.0L / g + (long double)sigma;
+    if (A > 0) {
+      std::vector<long double> M, K((size_t)N * N), Inv;
+      forward_middle(q, sl, A, g, M);
+      for (int i = 0; i < A; ++i)
+        for (int j = 0; j < A; ++j) {
+          const long double ss = q->SS[(size_t)sl[i] * m + sl[j]], sy = q->SY[(size_t)sl[i] * m + sl[j]],
+                            ys_ = q->SY[(size_t)sl[j] * m + sl[i]], yy = q->YY[(size_t)sl[i] * m + sl[j]];
+          K[(size_t)i * N + j] = tau * tau * M[(size_t)i * N + j] - tau * ss / (g * g);
+          K[(size_t)i * N + A + j] = tau * tau * M[(size_t)i * N + A + j] - tau * sy / g;
+          K[(size_t)(A + i) * N + j] = tau * tau * M[(size_t)(A + i) * N + j] - tau * ys_ / g;
+          K[(size_t)(A + i) * N + A + j] = tau * tau * M[(size_t)(A + i) * N + A + j] - tau * yy;
+        }
+      if (!invert_ld(K, Inv, N)) B2O_FAIL(B2O_ESTATE, "solve_shifted_system!: singular system");
+      for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) {
+          long double v = Inv[(size_t)i * N + j];
+          if (i < A) v /= g;
+          if (j < A) v /= g;
+          q->h_W[(size_t)i * N + j] = (double)v;
+        }
+      B2O_CUDA(cudaMemcpyAsync(q->d_W, q->h_W, sizeof(double) * N * N, cudaMemcpyHostToDevice, c->stream));
+      q->w_dirty = true;     // d_W now holds the solve matrix; the apply matrix is rebuilt on the next apply
+    }
+    CompactArgs a;
+    compact_columns(q, a, 1.0, 0.0);
+    a.gamma = (double)tau;
+    a.scaling = 1;
+    a.base_div = 1;
+    const int mode = (a.ncols == 0) ? MODE_PHASE2 : MODE_FUSED;
+    if (c->nranks > 1 && !c->mbox_ready && a.ncols > 0) {
+      B2O_TRY(compact_launch_rows(q, a, (double *)x_, (const double *)b_, 0, q->n, MODE_PHASE1, 0));
+      B2O_TRY(b2o_allreduce_sum_f64(c, c->d_dots, a.ncols));
+      B2O_TRY(compact_launch_rows(q, a, (double *)x_, (const double *)b_, 0, q->n, MODE_PHASE2, 0));
+    } else {
+      B2O_TRY(compact_launch_rows(q, a, (double *)x_, (const double *)b_, 0, q->n, mode, 0));
+    }
+    B2O_CUDA(cudaStreamSynchronize(c->stream));   // h_W is reused
+    return B2O_OK;
+  }
   B2O_TRY(check_vec(q, x_, x_len));
   B2O_TRY(check_vec(q, b_, b_len));
   b2o_ctx *c = q->ctx;

@@ -845,6 +845,17 @@ def test_solve_shifted_system(lo, ctx, orc, n, mem, npush, sigma):
         assert np.allclose(host(x2), host(H * b), atol=1e-6, rtol=1e-6)
     with pytest.raises(ValueError):
         lo.solve_shifted_system_(x, g, b, -0.1)
+    # compact forward form: the same solve is ONE launch (Woodbury on the Gram matrices)
+    gc = lo.LBFGSOperator(n, mem=mem, compact=True, ctx=ctx)
+    for i in range(npush):
+        s = ctx.uniform(n, 100 + i)
+        lo.push_(gc, s, s + 0.1 * ctx.uniform(n, 200 + i))
+    xc = ctx.zeros(n)
+    l0 = ctx.launch_count()
+    lo.solve_shifted_system_(xc, gc, b, sigma)
+    assert ctx.launch_count() - l0 == 1
+    assert rel(host(xc), host(xt)) <= 1e-8
+    assert rel(host(gc * x), host(g * x)) <= 1e-9                                # apply matrix is rebuilt after the solve
 
 
 @pytest.mark.parametrize("n,mem,npush,scaling,damped", [(10, 5, 3, False, False), (1000, 5, 7, True, False), (100003, 10, 14, True, False),

@@ -77,10 +77,12 @@ def main():
                     tp = 0.0
                 tp += time.perf_counter() - t1
             ms = timeit(lambda: lo.mul_(res, B, v), 20)
+            xs = ctx.zeros(n)
+            ms_solve = timeit(lambda: lo.solve_shifted_system_(xs, B, v, 0.5), 3, warmup=1)
             if not compact:
                 ref = res.clone()
             line("LBFGSOperator(mem=10) %s" % ("compact form (extension)" if compact else "a_k/b_k form (reference algorithm)"), ms,
-                 (4 * m + 3) * 8.0 * n, push_ms_steady_state=round(tp / 5 * 1e3, 2),
+                 (4 * m + 3) * 8.0 * n, push_ms_steady_state=round(tp / 5 * 1e3, 2), solve_shifted_system_ms=round(ms_solve, 2),
                  rel_diff_vs_reference_form=(float(torch.linalg.norm(res - ref) / torch.linalg.norm(ref)) if compact else 0.0))
             del B
             torch.cuda.empty_cache()
