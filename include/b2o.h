@@ -128,6 +128,13 @@ int b2o_qn_destroy(b2o_qn *op);
 int b2o_qn_apply(b2o_qn *op, void *res, int64_t res_len, const void *x, int64_t x_len, double alpha, double beta);
 /* same, HOST buffers: H2D copy of x, apply, D2H copy of res, stream sync (the end-to-end path). */
 int b2o_qn_apply_host(b2o_qn *op, void *res_host, const void *x_host, int64_t len, double alpha, double beta);
+/* mul!(Res::Matrix, op, X::Matrix, α, β) (src/operations.jl:34-36): Res, X are column-major n x nrhs
+ * device matrices with leading dimensions ldr, ldx (>= n).  Extension: every column of Res equals b2o_qn_apply of the matching
+ * column of X (to reduction-order rounding), but each state column is streamed once per 8 right-hand sides:
+ * (2*ncols + 3*nrhs)*8*n algorithmic bytes per pass.  Two-loop inverse handles and NCCL (non-mailbox) partitions run column by
+ * column. */
+int b2o_qn_apply_multi(b2o_qn *op, void *res, int64_t ldr, const void *x, int64_t ldx, int64_t len, int nrhs, double alpha,
+                       double beta);
 /* push!(op,s,y) src/lbfgs.jl:269-287, src/lsr1.jl:119-184.  *accepted = 0 when the pair is rejected
  * (not an error, the reference returns op silently).  Synchronises (host-side acceptance tests). */
 int b2o_qn_push(b2o_qn *op, const void *s, const void *y, int64_t len, int *accepted);

@@ -400,6 +400,9 @@ def _mul_matrix(res, op, m, alpha, beta):
     matrix to the closure; the library's closures are vector kernels, so the mirror loops)."""
     if not (m.shape[0] == size(op, 2) and res.shape[0] == size(op, 1) and m.shape[1] == res.shape[1]):
         raise LinearOperatorException("shape mismatch")
+    block = getattr(op, "_mul_block", None)
+    if block is not None and block(res, m, alpha, beta):
+        return res
     for j in range(m.shape[1]):
         mul_(res[:, j], op, m[:, j], alpha, beta)
     return res

@@ -1,6 +1,6 @@
 // b2o_qn.cu -- LBFGSOperator / InverseLBFGSOperator / LSR1Operator handles (src/lbfgs.jl, src/lsr1.jl):
 // state, apply (persistent kernels in b2o_qn_kernels.cuh), push!, diag!, reset!, state access.
-#include "b2o_qn_kernels.cuh"
+#include "b2o_qn_multi.cuh"
 #include <float.h>
 #include <math.h>
 #include <algorithm>
@@ -641,6 +641,114 @@ static int qn_apply_dev(b2o_qn *q, double *res, const double *x, double alpha, d
     if (q->w_dirty) B2O_TRY(build_inverse_W(q));
   }
   return qn_apply_compact(q, res, x, alpha, beta);
+}
+
+// ------------------------------------------------------------------ block apply: NR right-hand sides per column pass
+template <int NR>
+static int multi_launch(b2o_qn *q, const CompactArgs &base, double *res, int64_t ldr, const double *x, int64_t ldx, int nrhs) {
+  b2o_ctx *c = q->ctx;
+  constexpr int R = MultiTile<NR>::R;
+  MultiArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int i = 0; i < base.ncols; ++i) {
+    a.cols[i] = base.cols[i];
+    a.cdiv[i] = base.cdiv[i];
+  }
+  a.ncols = base.ncols;
+  a.x = x;
+  a.res = res;
+  a.ldx = ldx;
+  a.ldr = ldr;
+  a.nrhs = nrhs;
+  a.n = q->n;
+  a.ntiles = (a.n + R - 1) / R;
+  a.alpha = base.alpha;
+  a.beta = base.beta;
+  a.gamma = base.gamma;
+  a.scaling = base.scaling;
+  a.W = base.W;
+  a.base_div = base.base_div;
+  a.x_al16 = ((uintptr_t)x % 16) == 0 && (nrhs == 1 || ldx % 2 == 0);
+  a.res_al16 = ((uintptr_t)res % 16) == 0 && (nrhs == 1 || ldr % 2 == 0);
+  const int nv = a.ncols * NR;
+  LaunchCfg cfg;
+  cfg.R = R;
+  cfg.group = 0;
+  const size_t fixed = ((size_t)B2O_CONS_WARPS * a.ncols * 32 + nv) * sizeof(double) + B2O_NCONS * sizeof(unsigned);
+  int stages = c->stages > 0 ? std::max(2, c->stages) : std::max(3, (114688 + R * 4) / (R * 8));
+  while (stages > 2 && (size_t)stages * R * sizeof(double) + fixed + 2 * stages * sizeof(uint64_t) + 16 > B2O_MAX_DYN_SMEM) --stages;
+  cfg.stages = stages;
+  cfg.L.ring_off = 0;
+  cfg.L.accs_off = (size_t)stages * R * sizeof(double);
+  cfg.L.coef_off = cfg.L.accs_off + (size_t)B2O_CONS_WARPS * a.ncols * 32 * sizeof(double);
+  cfg.L.bar_off = cfg.L.coef_off + (size_t)nv * sizeof(double);
+  a.landed_off = (uint32_t)(cfg.L.bar_off + (size_t)2 * stages * sizeof(uint64_t));
+  cfg.L.total = a.landed_off + B2O_NCONS * sizeof(unsigned);
+  if (cfg.L.total > B2O_MAX_DYN_SMEM) B2O_FAIL(B2O_ECUDA, "shared memory plan does not fit");
+  int g = c->grid > 0 ? c->grid : c->num_sms;
+  g = std::min(g, c->num_sms);
+  cfg.grid = (int)std::max<int64_t>(1, std::min<int64_t>(g, a.ntiles));
+  if ((size_t)cfg.grid * nv > (size_t)B2O_MAX_GRID * B2O_MAX_COLS) B2O_FAIL(B2O_EUNSUPPORTED, "too many columns for the block apply");
+  a.partials = c->d_partials;
+  a.dots = c->d_dots;
+  a.bar = c->d_bar;
+  a.stages = stages;
+  a.wacc_off = (uint32_t)cfg.L.accs_off;
+  a.coef_off = (uint32_t)cfg.L.coef_off;
+  a.bar_off = (uint32_t)cfg.L.bar_off;
+  a.bar_target = c->bar_base + (unsigned long long)cfg.grid;
+  b2o_mbox_fill(c, &a.mbox);
+  int st = (q->kind == 0 && (q->inverse || q->fwd_compact)) ? launch_persistent(c, qn_multi_kernel<NR, OP_INV_COMPACT>, cfg, a, true)
+           : q->kind == 0             ? launch_persistent(c, qn_multi_kernel<NR, OP_LBFGS_FWD>, cfg, a, true)
+                                      : launch_persistent(c, qn_multi_kernel<NR, OP_LSR1>, cfg, a, true);
+  if (st == B2O_OK) {
+    c->bar_base += (unsigned long long)cfg.grid;
+    if (a.mbox.nranks > 1) c->mbox_epoch += (unsigned long long)((nv + MBOX_MAXV - 1) / MBOX_MAXV);
+  }
+  return st;
+}
+
+// mul!(Res, op, X, α, β) with n x nrhs column-major matrices (leading dimensions ldr, ldx)
+extern "C" int b2o_qn_apply_multi(b2o_qn *q, void *res_, int64_t ldr, const void *x_, int64_t ldx, int64_t len, int nrhs,
+                                  double alpha, double beta) {
+  if (!q) B2O_FAIL(B2O_EARG, "null operator");
+  if (len != q->n) B2O_FAIL(B2O_ESHAPE, "shape mismatch");
+  if (nrhs < 0) B2O_FAIL(B2O_EARG, "nrhs must be >= 0");
+  if (nrhs == 0 || q->n == 0) return B2O_OK;
+  if (!res_ || !x_) B2O_FAIL(B2O_EARG, "null matrix");
+  if (nrhs > 1 && (ldr < q->n || ldx < q->n)) B2O_FAIL(B2O_EARG, "leading dimension smaller than n");
+  if (((uintptr_t)res_ | (uintptr_t)x_) % 8) B2O_FAIL(B2O_EARG, "matrices must be 8-byte aligned");
+  b2o_ctx *c = q->ctx;
+  B2O_CUDA(cudaSetDevice(c->device));
+  double *res = (double *)res_;
+  const double *x = (const double *)x_;
+  const bool twoloop = q->kind == 0 && q->inverse && !q->inv_compact;
+  const bool split_ranks = c->nranks > 1 && !c->mbox_ready;
+  CompactArgs base;
+  if (!twoloop) {
+    if (q->kind == 0 && !q->inverse && q->fwd_compact && q->w_dirty) B2O_TRY(build_forward_W(q));
+    if (q->kind == 0 && q->inverse && q->w_dirty) B2O_TRY(build_inverse_W(q));
+    compact_columns(q, base, alpha, beta);
+  }
+  if (nrhs == 1 || twoloop || split_ranks || base.ncols == 0 || base.ncols * 4 > B2O_MULTI_MAXV) {
+    // the two-loop recursion is a chain of dependent sweeps and NCCL mode splits the launch: column by column
+    for (int r = 0; r < nrhs; ++r) B2O_TRY(qn_apply_dev(q, res + (int64_t)r * ldr, x + (int64_t)r * ldx, alpha, beta));
+    return B2O_OK;
+  }
+  const bool can8 = base.ncols * 8 <= B2O_MULTI_MAXV;
+  for (int r0 = 0; r0 < nrhs;) {
+    const int left = nrhs - r0;
+    if (can8 && left > 4) {
+      const int k = std::min(left, 8);
+      B2O_TRY(multi_launch<8>(q, base, res + (int64_t)r0 * ldr, ldr, x + (int64_t)r0 * ldx, ldx, k));
+      r0 += k;
+    } else {
+      const int k = std::min(left, 4);
+      B2O_TRY(multi_launch<4>(q, base, res + (int64_t)r0 * ldr, ldr, x + (int64_t)r0 * ldx, ldx, k));
+      r0 += k;
+    }
+  }
+  return B2O_OK;
 }
 
 // Gram entries involving ring slot `k` (after s_k, y_k were stored): s_k·y_j, s_j·y_k, y_k·y_j (and s_k·s_j) for every slot j

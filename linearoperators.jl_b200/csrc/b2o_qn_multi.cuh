@@ -1,0 +1,425 @@
+// b2o_qn_multi.cuh -- block (multi right-hand-side) variant of qn_compact_kernel: mul!(Res::Matrix, op, X::Matrix, α, β)
+// for the forward LBFGSOperator, LSR1Operator and the compact forms (the reference hands the matrices to
+// the closure, src/operations.jl:34-36 -- its quasi-Newton closures are vector code, so this is an extension with the
+// per-column semantics of src/lbfgs.jl:173-202 / src/lsr1.jl:89-107).
+//
+// Same two streaming phases as the vector kernel, but every TMA-staged column tile is used for NR right-hand sides while it
+// is in shared memory:  algorithmic DRAM bytes per launch (2*ncols + 3*nrhs)*8*n  instead of nrhs*(2*ncols+3)*8*n.
+//   phase 1: G[c][r] = col_c · x_r.  The thread's x rows stay in registers (NR x EPT doubles, one tile prefetched ahead);
+//            per column tile the NR thread partials are folded to one value per lane by a transposing butterfly
+//            (NR/2 + NR/4 + ... exchange shuffles) and accumulated in the lane's shared-memory cell [warp][c][lane]
+//            -> fixed order, deterministic.  With 8 right-hand sides the kernel sits near the FP64 pipe's balance point
+//            (64 DFMA/clk/SM against 25 B/clk/SM of HBM), so the arithmetic is contracted to FMAs here (the vector kernel
+//            keeps the reference's unfused statement rounding); per-column results differ from it by a few ulp.
+//   phase 2: res_r = α (x_r/γ + Σ_c coef[c][r] col_c) + β res_r with NR x EPT accumulators in registers.
+#pragma once
+#include "b2o_qn_kernels.cuh"
+
+constexpr int B2O_MULTI_MAXV = 256;   // ncols * NR values reduced per launch (fits d_dots and two mailbox epochs)
+
+struct MultiArgs {
+  const double *cols[B2O_MAX_COLS];
+  double cdiv[B2O_MAX_COLS];
+  int ncols;
+  const double *x;   // column-major n x nrhs, leading dimension ldx
+  double *res;       // column-major n x nrhs, leading dimension ldr
+  int64_t ldx, ldr;
+  int nrhs;          // <= NR
+  int64_t n, ntiles;
+  double alpha, beta, gamma;
+  int scaling;
+  int x_al16, res_al16;
+  double *partials;                  // [grid][ncols*NR]
+  double *dots;                      // [ncols*NR] (mailbox publication)
+  unsigned long long *bar;
+  unsigned long long bar_target;
+  int stages;
+  uint32_t wacc_off, coef_off, bar_off, landed_off;
+  MboxDev mbox;
+  const double *W;
+  int base_div;
+};
+
+// Transposing butterfly: log2(NR) exchange stages fold the NR per-thread partials into ONE value per lane -- the sum over the
+// NR lanes that differ in the top log2(NR) lane bits -- for right-hand side r = lane / (32/NR).  The remaining 32/NR lanes of a
+// group are NOT folded here: each lane accumulates its value over all tiles in its own shared-memory cell and the group is
+// summed once at the end (keeps the dependent shuffle chain per column tile short).  Fixed pattern -> deterministic.
+template <int NR>
+__device__ __forceinline__ double transpose_fold(double (&s)[NR], int lane);
+
+template <>
+__device__ __forceinline__ double transpose_fold<8>(double (&s)[8], int lane) {
+  const unsigned F = 0xffffffffu;
+  double t[4], u[2];
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double send = h16 ? s[i] : s[i + 4];
+    const double keep = h16 ? s[i + 4] : s[i];
+    t[i] = keep + __shfl_xor_sync(F, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double send = h8 ? t[i] : t[i + 2];
+    const double keep = h8 ? t[i + 2] : t[i];
+    u[i] = keep + __shfl_xor_sync(F, send, 8);
+  }
+  const double send = h4 ? u[0] : u[1];
+  const double keep = h4 ? u[1] : u[0];
+  return keep + __shfl_xor_sync(F, send, 4);   // r = lane >> 2 (bit4 -> 4, bit3 -> 2, bit2 -> 1)
+}
+
+template <>
+__device__ __forceinline__ double transpose_fold<4>(double (&s)[4], int lane) {
+  const unsigned F = 0xffffffffu;
+  double t[2];
+  const bool h16 = lane & 16, h8 = lane & 8;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double send = h16 ? s[i] : s[i + 2];
+    const double keep = h16 ? s[i + 2] : s[i];
+    t[i] = keep + __shfl_xor_sync(F, send, 16);
+  }
+  const double send = h8 ? t[0] : t[1];
+  const double keep = h8 ? t[1] : t[0];
+  return keep + __shfl_xor_sync(F, send, 8);   // r = lane >> 3
+}
+
+// A ring slot is handed back to the TMA producer right after its tile was copied to registers, BEFORE the arithmetic (the
+// shuffle chain is long).  ptxas then schedules the mbarrier arrive a few instructions behind LDS that are still in flight, and
+// with that schedule the block apply showed intermittent 1e-8 errors at n = 1e8 (a tile refilled under the read).  The
+// hand-back is therefore made data-dependent on every LDS of the tile: one 4-byte shared-memory store whose operand is
+// folded from a register of each LDS.128 -- it cannot issue before the loads have returned, and the arrive is ordered after it.
+template <int EPT>
+__device__ __forceinline__ unsigned fold_loaded(const double (&a)[EPT]) {
+  unsigned v = 0;
+#pragma unroll
+  for (int j = 0; j < EPT; j += 2) v ^= (unsigned)__double2hiint(a[j]);
+  return v;
+}
+__device__ __forceinline__ void smem_reads_landed(unsigned *cell, unsigned v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(smem_u32(cell)), "r"(v) : "memory");
+}
+
+template <int NR>
+struct MultiTile {
+  static constexpr int R = (NR == 8) ? 1024 : 2048;
+};
+
+template <int NR, int OP>
+__global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_multi_kernel(const __grid_constant__ MultiArgs p) {
+  constexpr int R = MultiTile<NR>::R;
+  constexpr int EPT = R / B2O_NCONS;
+  constexpr int LPG = 32 / NR;   // lanes per right-hand-side group after the transposing reduce
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Ring rg;
+  rg.buf = reinterpret_cast<double *>(smem_raw);
+  double *wacc = reinterpret_cast<double *>(smem_raw + p.wacc_off);   // [8 warps][ncols][32 lanes]
+  double *coef = reinterpret_cast<double *>(smem_raw + p.coef_off);   // [ncols*NR]
+  rg.full = reinterpret_cast<uint64_t *>(smem_raw + p.bar_off);
+  rg.empty = rg.full + p.stages;
+  rg.stages = p.stages;
+  unsigned *s_landed = reinterpret_cast<unsigned *>(smem_raw + p.landed_off);   // [256] one cell per consumer thread
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool is_producer = warp == B2O_CONS_WARPS;
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&rg.full[s], 1);
+      mbar_init(&rg.empty[s], B2O_CONS_WARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  RingPos pos(p.stages);
+  const int64_t grid = gridDim.x;
+  const int64_t my_tiles = (p.ntiles > (int64_t)blockIdx.x) ? (p.ntiles - 1 - blockIdx.x) / grid + 1 : 0;
+  const int ncols = p.ncols, nrhs = p.nrhs;
+  const int nv = ncols * NR;
+
+  // ------------------------------------------------------------------ phase 1: G = colsᵀ X
+  if (is_producer) {
+    if (lane == 0) {
+      for (int64_t i = 0; i < my_tiles; ++i) {
+        const int64_t t = blockIdx.x + i * grid;
+        for (int c = 0; c < ncols; ++c) producer_push<R>(rg, pos, p.cols[c] + t * R);
+      }
+    }
+    __syncwarp();
+  } else {
+    for (int i = tid; i < B2O_CONS_WARPS * ncols * 32; i += B2O_NCONS) wacc[i] = 0.0;
+    consumers_sync();
+    double xr[NR][EPT], xn[NR][EPT];
+    if (my_tiles > 0) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        if (r < nrhs) load_user_tile<R>(p.x + (int64_t)r * p.ldx, (int64_t)blockIdx.x * R, p.n, p.x_al16, xn[r]);
+        else {
+#pragma unroll
+          for (int j = 0; j < EPT; ++j) xn[r][j] = 0.0;
+        }
+      }
+    }
+    double *my_acc = wacc + (size_t)warp * ncols * 32 + lane;    // cell [warp][c][lane]
+    auto take = [&](uint32_t slot, double (&a)[EPT]) {
+      const double2 *b = reinterpret_cast<const double2 *>(rg.buf + (size_t)slot * R);
+#pragma unroll
+      for (int j = 0; j < EPT / 2; ++j) {
+        double2 v = b[j * B2O_NCONS + tid];
+        a[2 * j] = v.x;
+        a[2 * j + 1] = v.y;
+      }
+    };
+    auto dots = [&](const double (&a)[EPT], double (&sv)[NR]) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        double acc = a[0] * xr[r][0];
+#pragma unroll
+        for (int j = 1; j < EPT; ++j) acc = fma(a[j], xr[r][j], acc);
+        sv[r] = acc;
+      }
+    };
+    for (int64_t i = 0; i < my_tiles; ++i) {
+      const int64_t t = blockIdx.x + i * grid;
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) xr[r][j] = xn[r][j];
+      if (i + 1 < my_tiles) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+          if (r < nrhs) load_user_tile<R>(p.x + (int64_t)r * p.ldx, (t + grid) * R, p.n, p.x_al16, xn[r]);
+      }
+      int c = 0;
+      for (; c + 1 < ncols; c += 2) {     // two columns per iteration: two independent shuffle chains in flight
+        const uint32_t s0 = pos.slot, p0 = pos.par;
+        pos.advance();
+        const uint32_t s1 = pos.slot, p1 = pos.par;
+        pos.advance();
+        double a0[EPT], a1[EPT], v0[NR], v1[NR];
+        mbar_wait(&rg.full[s0], p0);
+        take(s0, a0);
+        mbar_wait(&rg.full[s1], p1);
+        take(s1, a1);
+        smem_reads_landed(&s_landed[tid], fold_loaded(a0) ^ fold_loaded(a1));
+        consumer_release(rg, s0);         // the tiles are in registers: hand the slots back before the arithmetic
+        consumer_release(rg, s1);
+        dots(a0, v0);
+        dots(a1, v1);
+        const double f0 = transpose_fold<NR>(v0, lane), f1 = transpose_fold<NR>(v1, lane);
+        my_acc[c * 32] += f0;
+        my_acc[(c + 1) * 32] += f1;
+      }
+      if (c < ncols) {
+        double a0[EPT], v0[NR];
+        mbar_wait(&rg.full[pos.slot], pos.par);
+        take(pos.slot, a0);
+        smem_reads_landed(&s_landed[tid], fold_loaded(a0));
+        consumer_release(rg, pos.slot);
+        pos.advance();
+        dots(a0, v0);
+        my_acc[c * 32] += transpose_fold<NR>(v0, lane);
+      }
+    }
+    consumers_sync();
+    // G[c][r] of this CTA: the LPG lanes of group r, then the 8 warps, in a fixed order
+    for (int i = tid; i < nv; i += B2O_NCONS) {
+      const int c = i / NR, r = i % NR;
+      double sum = 0.0;
+#pragma unroll
+      for (int w = 0; w < B2O_CONS_WARPS; ++w) {
+        double sw = 0.0;
+#pragma unroll
+        for (int l = 0; l < LPG; ++l) sw += wacc[((size_t)w * ncols + c) * 32 + r * LPG + l];
+        sum += sw;
+      }
+      p.partials[(size_t)blockIdx.x * nv + i] = sum;
+    }
+  }
+
+  // ------------------------------------------------------------------ reduce G over the grid (and over the ranks)
+  unsigned long long bar_target = p.bar_target;
+  if (p.mbox.nranks > 1) {
+    const int nep = (nv + MBOX_MAXV - 1) / MBOX_MAXV;
+    const unsigned long long epoch_last = p.mbox.epoch_base + nep;
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(p.bar, 1ULL);
+    }
+    if (blockIdx.x == 0) {
+      if (tid == 0) {
+        while (ld_acquire_u64(p.bar) < bar_target) { __nanosleep(32); }
+        __threadfence();
+      }
+      __syncthreads();
+      if (!is_producer) {
+        for (int c = warp; c < nv; c += B2O_CONS_WARPS) {
+          double s = 0.0;
+          for (int b = lane; b < (int)grid; b += 32) s += __ldcg(&p.partials[(size_t)b * nv + c]);
+          s = warp_sum(s);
+          if (lane == 0) coef[c] = s;
+        }
+      }
+      __syncthreads();
+      if (warp == 0)
+        for (int e = 0; e < nep; ++e)
+          mbox_allreduce_warp(p.mbox, p.mbox.epoch_base + 1 + e, coef + e * MBOX_MAXV, min(MBOX_MAXV, nv - e * MBOX_MAXV));
+      __syncthreads();
+      for (int c = tid; c < nv; c += B2O_NTHREADS) p.dots[c] = coef[c];
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) st_release_gpu_u64(p.mbox.ready, epoch_last);
+    } else {
+      if (tid == 0)
+        while (ld_acquire_u64(p.mbox.ready) < epoch_last) { __nanosleep(32); }
+      __syncthreads();
+      for (int c = tid; c < nv; c += B2O_NTHREADS) coef[c] = __ldcg(&p.dots[c]);
+      __syncthreads();
+    }
+  } else {
+    grid_barrier(p.bar, bar_target);
+    if (!is_producer) {
+      for (int c = warp; c < nv; c += B2O_CONS_WARPS) {
+        double s = 0.0;
+        for (int b = lane; b < (int)grid; b += 32) s += __ldcg(&p.partials[(size_t)b * nv + c]);
+        s = warp_sum(s);
+        if (lane == 0) coef[c] = s;
+      }
+    }
+    __syncthreads();
+  }
+
+  if (OP == OP_INV_COMPACT) {
+    // coefficients(:, r) = W * G(:, r); every CTA repeats the tiny product in the same order
+    for (int idx = tid; idx < nv; idx += B2O_NTHREADS) {
+      const int j = idx / NR, r = idx % NR;
+      double s = 0.0;
+      for (int k = 0; k < ncols; ++k) s = fma(__ldcg(&p.W[(size_t)j * ncols + k]), coef[k * NR + r], s);
+      wacc[idx] = s;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nv; idx += B2O_NTHREADS) coef[idx] = wacc[idx];
+    __syncthreads();
+  }
+
+  // ------------------------------------------------------------------ phase 2: combine and write Res
+  if (is_producer) {
+    if (lane == 0) {
+      for (int64_t i = my_tiles - 1; i >= 0; --i) {
+        const int64_t t = blockIdx.x + i * grid;
+        for (int c = 0; c < ncols; ++c) producer_push<R>(rg, pos, p.cols[c] + t * R);
+      }
+    }
+    __syncwarp();
+  } else {
+    const double alpha = p.alpha, beta = p.beta, gamma = p.gamma;
+    double xn[NR][EPT], q[NR][EPT];
+    if (my_tiles > 0) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        if (r < nrhs) load_user_tile<R>(p.x + (int64_t)r * p.ldx, (blockIdx.x + (my_tiles - 1) * grid) * R, p.n, p.x_al16, xn[r]);
+        else {
+#pragma unroll
+          for (int j = 0; j < EPT; ++j) xn[r][j] = 0.0;
+        }
+      }
+    }
+    for (int64_t i = my_tiles - 1; i >= 0; --i) {
+      const int64_t t = blockIdx.x + i * grid;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        if (OP == OP_LBFGS_FWD) {
+#pragma unroll
+          for (int j = 0; j < EPT; ++j) q[r][j] = p.scaling ? xn[r][j] / gamma : xn[r][j];          // src/lbfgs.jl:183-186
+        } else if (OP == OP_INV_COMPACT) {
+#pragma unroll
+          for (int j = 0; j < EPT; ++j) q[r][j] = !p.scaling ? xn[r][j] : (p.base_div ? xn[r][j] / gamma : xn[r][j] * gamma);
+        } else {
+          double rold[EPT];
+          if (beta != 0.0 && r < nrhs) load_user_tile<R>(p.res + (int64_t)r * p.ldr, t * R, p.n, p.res_al16, rold);
+#pragma unroll
+          for (int j = 0; j < EPT; ++j) {                                                           // src/lsr1.jl:92-96
+            const double v = (alpha * xn[r][j]) / gamma;
+            q[r][j] = (beta != 0.0 && r < nrhs) ? v + beta * rold[j] : v;
+          }
+        }
+      }
+      if (i > 0) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+          if (r < nrhs) load_user_tile<R>(p.x + (int64_t)r * p.ldx, (t - grid) * R, p.n, p.x_al16, xn[r]);
+      }
+      if (OP == OP_LBFGS_FWD) {
+        for (int c = 0; c < ncols; c += 2) {
+          const uint32_t sa = pos.slot, pa = pos.par;
+          pos.advance();
+          const uint32_t sb = pos.slot, pb = pos.par;
+          pos.advance();
+          mbar_wait(&rg.full[sa], pa);
+          mbar_wait(&rg.full[sb], pb);
+          const double2 *A = reinterpret_cast<const double2 *>(rg.buf + (size_t)sa * R);
+          const double2 *B = reinterpret_cast<const double2 *>(rg.buf + (size_t)sb * R);
+          double a[EPT], b[EPT];
+#pragma unroll
+          for (int j = 0; j < EPT / 2; ++j) {
+            double2 va = A[j * B2O_NCONS + tid], vb = B[j * B2O_NCONS + tid];
+            a[2 * j] = va.x;
+            a[2 * j + 1] = va.y;
+            b[2 * j] = vb.x;
+            b[2 * j + 1] = vb.y;
+          }
+          smem_reads_landed(&s_landed[tid], fold_loaded(a) ^ fold_loaded(b));
+          consumer_release(rg, sa);
+          consumer_release(rg, sb);
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            const double ax = coef[c * NR + r], bx = coef[(c + 1) * NR + r];
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) q[r][j] = fma(bx, b[j], fma(-ax, a[j], q[r][j]));          // src/lbfgs.jl:194, contracted
+          }
+        }
+      } else {
+        for (int c = 0; c < ncols; ++c) {
+          mbar_wait(&rg.full[pos.slot], pos.par);
+          const double2 *A = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R);
+          double a[EPT];
+#pragma unroll
+          for (int j = 0; j < EPT / 2; ++j) {
+            double2 va = A[j * B2O_NCONS + tid];
+            a[2 * j] = va.x;
+            a[2 * j + 1] = va.y;
+          }
+          smem_reads_landed(&s_landed[tid], fold_loaded(a));
+          consumer_release(rg, pos.slot);
+          pos.advance();
+          const double cd = p.cdiv[c];
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            const double ax = (OP == OP_INV_COMPACT) ? coef[c * NR + r] : (alpha * coef[c * NR + r]) / cd;   // src/lsr1.jl:101
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) q[r][j] = fma(ax, a[j], q[r][j]);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        if (r < nrhs) {
+          if (OP != OP_LSR1) {
+            if (beta != 0.0) {
+              double rold[EPT];
+              load_user_tile<R>(p.res + (int64_t)r * p.ldr, t * R, p.n, p.res_al16, rold);
+#pragma unroll
+              for (int j = 0; j < EPT; ++j) q[r][j] = alpha * q[r][j] + beta * rold[j];             // src/lbfgs.jl:197-201
+            } else {
+#pragma unroll
+              for (int j = 0; j < EPT; ++j) q[r][j] = alpha * q[r][j];
+            }
+          }
+          store_user_tile<R>(p.res + (int64_t)r * p.ldr, t * R, p.n, p.res_al16, q[r]);
+        }
+      }
+    }
+  }
+}

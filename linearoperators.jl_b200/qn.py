@@ -96,6 +96,23 @@ class AbstractQuasiNewtonOperator(AbstractLinearOperator):
         self.nprod += 1
         return res_host
 
+    def _mul_block(self, res, X, alpha, beta):
+        """mul!(Res::Matrix, op, X::Matrix, α, β) (src/operations.jl:34-36) in one launch per 8 right-hand sides; returns False
+        (caller falls back to the column loop) unless both matrices are column-major float64 CUDA tensors."""
+        import torch
+        for t in (res, X):
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.dim() == 2):
+                return False
+            if t.shape[0] > 1 and t.stride(0) != 1:
+                return False
+            if t.shape[1] > 1 and t.stride(1) < t.shape[0]:
+                return False
+        k = X.shape[1]
+        _lib.check(self.ctx.lib.b2o_qn_apply_multi(self.handle, ctypes.c_void_p(res.data_ptr()), int(res.stride(1)) if k > 1 else self.nrow,
+                                                   ctypes.c_void_p(X.data_ptr()), int(X.stride(1)) if k > 1 else self.nrow,
+                                                   int(X.shape[0]), int(k), float(alpha), float(beta)))
+        return True
+
     def apply_bytes(self, beta=0.0):
         out = ctypes.c_double()
         _lib.check(self.ctx.lib.b2o_qn_apply_bytes(self.handle, float(beta), ctypes.byref(out)))

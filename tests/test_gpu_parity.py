@@ -893,3 +893,57 @@ def test_forward_compact_representation(lo, ctx, orc, n, mem, npush, scaling, da
         lo.diag(Bc)
     lo.reset_(Bc)
     assert np.array_equal(host(Bc * x), host(x))
+
+
+# ---------------------------------------------------------------- §8f rank 4: matrix right-hand sides in one pass
+def _colmajor(ctx, n, k, seed, pad=0):
+    """column-major n x k device matrix (leading dimension n + pad), columns = uniform(seed + j)"""
+    import torch
+    buf = torch.empty((k, n + pad), dtype=torch.float64, device="cuda:%d" % ctx.device)
+    for j in range(k):
+        buf[j, :n] = ctx.uniform(n, seed + j)
+    return buf[:, :n].T
+
+
+@pytest.mark.parametrize("kind", ["lbfgs", "lbfgs_compact", "inverse_compact", "lsr1", "inverse_twoloop"])
+@pytest.mark.parametrize("n,mem,npush,nrhs,pad", [(10, 3, 2, 3, 0), (4099, 5, 7, 8, 1), (100003, 10, 12, 13, 0), (30011, 4, 4, 5, 2)])
+def test_block_apply_matches_vector_apply(lo, ctx, orc, kind, n, mem, npush, nrhs, pad):
+    """mul!(Res, op, X, α, β) with matrices (src/operations.jl:34-36): every column equals the vector apply; the state columns
+    are streamed once per 8 right-hand sides (one launch per 8)"""
+    if kind == "lbfgs":
+        op, o = lo.LBFGSOperator(n, mem=mem, ctx=ctx), orc.LBFGS(n, mem=mem)
+    elif kind == "lbfgs_compact":
+        op, o = lo.LBFGSOperator(n, mem=mem, compact=True, ctx=ctx), orc.LBFGS(n, mem=mem)
+    elif kind == "inverse_compact":
+        op, o = lo.InverseLBFGSOperator(n, mem=mem, compact=True, ctx=ctx), orc.LBFGS(n, mem=mem, inverse=True)
+    elif kind == "inverse_twoloop":
+        op, o = lo.InverseLBFGSOperator(n, mem=mem, ctx=ctx), orc.LBFGS(n, mem=mem, inverse=True)
+    else:
+        op, o = lo.LSR1Operator(n, mem=mem, ctx=ctx), orc.LSR1(n, mem=mem)
+    for i in range(npush):
+        s = ctx.uniform(n, 100 + i)
+        y = s + 0.1 * ctx.uniform(n, 200 + i) if kind != "lsr1" else ctx.uniform(n, 200 + i, -0.5, 1.0)
+        lo.push_(op, s, y)
+        o.push(host(s), host(y))
+    X = _colmajor(ctx, n, nrhs, 300, pad)
+    R0 = _colmajor(ctx, n, nrhs, 400, pad)
+    tol = 1e-12 if kind in ("lbfgs", "lsr1", "inverse_twoloop") else 1e-9      # compact forms: extension, conditioning of W
+    for alpha, beta in [(1.0, 0.0), (-0.75, 0.5)]:
+        Res = _colmajor(ctx, n, nrhs, 400, pad)
+        assert Res.stride(0) == 1 and (nrhs == 1 or Res.stride(1) == n + pad)
+        if beta == 0:
+            Res.fill_(float("nan"))
+        l0 = ctx.launch_count()
+        lo.mul_(Res, op, X, alpha, beta)
+        nl = ctx.launch_count() - l0
+        if kind != "inverse_twoloop":
+            assert nl == (1 if nrhs <= 8 else 2), nl
+        for j in range(nrhs):
+            ref = host(R0[:, j]).copy()
+            o.apply(host(X[:, j]), alpha, beta, res=ref)
+            assert rel(host(Res[:, j]), ref) <= tol, (j, rel(host(Res[:, j]), ref))
+            v = ctx.empty(n).copy_(R0[:, j])
+            lo.mul_(v, op, X[:, j].contiguous(), alpha, beta)
+            assert rel(host(Res[:, j]), host(v)) <= (1e-13 if tol == 1e-12 else 1e-10)
+    with pytest.raises(lo.LinearOperatorException):
+        lo.mul_(Res, op, _colmajor(ctx, n + 1, nrhs, 1))

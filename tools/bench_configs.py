@@ -87,6 +87,34 @@ def main():
             del B
             torch.cuda.empty_cache()
         return
+    if only == ["multi"]:
+        # §8f rank 4: mul!(Res, B, X) with nrhs right-hand sides; the state columns are streamed once per 8 of them
+        m = 10
+        B = lo.LBFGSOperator(n, mem=m, ctx=ctx)
+        for i in range(m):
+            s = ctx.uniform(n, 100 + i)
+            lo.push_(B, s, s + 0.1 * ctx.uniform(n, 200 + i))
+        del s
+        for k in (1, 2, 4, 8, 16):
+            Xb = torch.empty((k, n), dtype=torch.float64, device="cuda")
+            for j in range(k):
+                Xb[j] = ctx.uniform(n, 300 + j)
+            X, Res = Xb.T, torch.empty((k, n), dtype=torch.float64, device="cuda").T
+            ms = timeit(lambda: lo.mul_(Res, B, X), 10)
+            v, r = ctx.empty(n), ctx.empty(n)
+            def loop():
+                for j in range(k):
+                    lo.mul_(r, B, Xb[j])
+            ms_loop = timeit(loop, 5) if k > 1 else ms
+            lo.mul_(r, B, Xb[k - 1])
+            diff = float(torch.linalg.norm(Res[:, k - 1] - r) / torch.linalg.norm(r))
+            passes = (k + 7) // 8
+            line("LBFGSOperator(mem=10) block apply, %d right-hand sides" % k, ms, (4 * m * passes + 3 * k) * 8.0 * n,
+                 ms_column_by_column=round(ms_loop, 3), speedup=round(ms_loop / ms, 2), vector_equivalent_GBps=round(k * (4 * m + 3) * 8.0 * n / ms / 1e6, 1),
+                 rel_diff_vs_vector_apply=diff)
+            del Xb, X, Res
+            torch.cuda.empty_cache()
+        return
     if only == ["invc"]:
         v, res = ctx.uniform(n, 7), ctx.empty(n)
         for m in (10, 20):
