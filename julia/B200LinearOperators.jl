@@ -112,6 +112,23 @@ function push!(op::B200LBFGSOperator, s::CuVector{Float64}, y::CuVector{Float64}
               op.handle, s, y, α, g, Bs, length(s), acc))
   return op
 end
+# mul!(Res, op, X, α, β) with matrices (src/operations.jl:34-36): the reference hands the matrices to prod!; here the block
+# kernel streams every state column once per 8 right-hand sides (b2o_qn_apply_multi)
+function LinearAlgebra.mul!(res::CuMatrix{Float64}, op::B200LBFGSOperator, X::CuMatrix{Float64}, α, β)
+  (size(X, 1) == op.ncol && size(res, 1) == op.nrow && size(X, 2) == size(res, 2)) || throw(LinearOperatorException("shape mismatch"))
+  check(ccall((:b2o_qn_apply_multi, libb2o), Cint,
+              (Ptr{Cvoid}, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, Int64, Int64, Cint, Cdouble, Cdouble),
+              op.handle, res, stride(res, 2), X, stride(X, 2), size(X, 1), size(X, 2), α, β))
+  return res
+end
+# solve_shifted_system!(x, B, b, σ) / ldiv!(x, B, b) (src/utilities.jl:207-289) on the device state
+function LinearOperators.solve_shifted_system!(x::CuVector{Float64}, op::B200LBFGSOperator, b::CuVector{Float64}, σ::Float64)
+  σ >= 0 || throw(ArgumentError("σ must be nonnegative"))
+  check(ccall((:b2o_lbfgs_solve_shifted, libb2o), Cint, (Ptr{Cvoid}, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, Int64, Cdouble),
+              op.handle, x, length(x), b, length(b), σ))
+  return x
+end
+LinearAlgebra.ldiv!(x::CuVector{Float64}, op::B200LBFGSOperator, b::CuVector{Float64}) = LinearOperators.solve_shifted_system!(x, op, b, 0.0)
 function reset!(op::B200LBFGSOperator)
   check(ccall((:b2o_qn_reset, libb2o), Cint, (Ptr{Cvoid},), op.handle))
   op.nprod = op.ntprod = op.nctprod = 0
