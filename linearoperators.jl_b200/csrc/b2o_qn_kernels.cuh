@@ -410,6 +410,7 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_kernel(const __gri
       if (qin_is_x && my_tiles > 0) load_user_tile<R>(p.x, (int64_t)blockIdx.x * R, p.n, p.x_al16, xn);
       for (int64_t i = 0; i < my_tiles; ++i) {
         const int64_t t = blockIdx.x + i * grid;
+        uint32_t q_slot = 0xffffffffu;
         if (qin_is_x) {
 #pragma unroll
           for (int j = 0; j < EPT; ++j) q[j] = xn[j];                                  // q .= x   :127-128
@@ -423,7 +424,9 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_kernel(const __gri
             q[2 * j] = v.x;
             q[2 * j + 1] = v.y;
           }
-          consumer_release(rg, pos.slot);
+          // the slot goes back only after the arithmetic below has consumed the loaded registers: an mbarrier arrive
+          // issued behind still-in-flight LDS can let the TMA refill race the read (tests/test_sass_invariants.py)
+          q_slot = pos.slot;
           pos.advance();
         }
         if (last && p.beta != 0.0) load_user_tile<R>(p.res, t * R, p.n, p.res_al16, rold);
@@ -441,6 +444,7 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_kernel(const __gri
               q[2 * j + 1] = q[2 * j + 1] + c1 * v.y;
             }
           }
+          if (q_slot != 0xffffffffu) consumer_release(rg, q_slot);
           consumer_release(rg, pos.slot);
           pos.advance();
           if (apply_gamma) {
@@ -459,6 +463,7 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_kernel(const __gri
             for (int j = 0; j < EPT / 2; ++j) Qg[j * B2O_NCONS + tid] = make_double2(q[2 * j], q[2 * j + 1]);
           }
         }
+        else if (q_slot != 0xffffffffu) consumer_release(rg, q_slot);   // (no sweep reads q without an update vector)
         if (v2) {
           mbar_wait(&rg.full[pos.slot], pos.par);
           const double2 *V = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R);
