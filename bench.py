@@ -250,7 +250,10 @@ def main():
     tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("inv" if inverse else "fwd")
+            tj = json.load(open(tp))
+            key = "inv" if inverse else "fwd"
+            # the ncu capture is for the default shapes (n=1e8; fwd mem=10, inv mem=20): report it only for that workload
+            traffic = tj.get(key) if abs(tj.get("algorithmic", {}).get(key, -1.0) - bytes_step) < 1.0 else None
         except Exception:
             traffic = None
     out = {

@@ -160,7 +160,10 @@ int b2o_qn_get_scalars(b2o_qn *op, int *insert1, double *gamma, double *opnorm_u
 int b2o_qn_set_scalars(b2o_qn *op, int insert1, double gamma, double opnorm_ub, const double *ys, const double *aux);
 /* options: "inverse_mode" (InverseLBFGSOperator only): 0 = the reference's two-loop recursion (default),
  * 1 = compact representation H = γI + [S γY] W [Sᵀ; γYᵀ] (Byrd-Nocedal-Schnabel): same operator, (4m+3)n instead of (8m+2)n
- * words of DRAM traffic and ONE all-reduce instead of 2m dependent ones; rounding differs from the two-loop. */
+ * words of DRAM traffic and ONE all-reduce instead of 2m dependent ones; rounding differs from the two-loop.
+ * "forward_mode" (forward LBFGSOperator): 1 = compact form (push! = O(m) dots).  "push_mode" (forward LBFGSOperator, reference
+ * form): 1 (default) = each a_k of the rebuild in push! (src/lbfgs.jl:236-250) is one launch of the streaming apply kernel,
+ * 0 = generic multi-dot + linear-combination passes (same statements, same rounding of the elementwise part). */
 int b2o_qn_set_option(b2o_qn *op, const char *key, int64_t value);
 /* algorithmic DRAM bytes of one apply (SURVEY §8d / DESIGN.md), for the roofline */
 int b2o_qn_apply_bytes(b2o_qn *op, double beta, double *bytes);

@@ -24,6 +24,7 @@ struct b2o_qn_s {
   int ins0 = 0;
   // optional compact-representation inverse apply: Gram matrices by ring slot, device middle matrix
   bool inv_compact = false, w_dirty = true;
+  bool push_streamed = true;    // push!: rebuild the a_k with the streaming apply kernel (false: generic multi-dot + lincomb passes)
   bool fwd_compact = false;     // forward operator in compact form: state = S, Y + Gram matrices; push! is O(m) dots, not O(m^2) passes
   std::vector<double> SY, YY, SS;   // [mem*mem]: SY[i*mem+j] = s_i·y_j, YY[i*mem+j] = y_i·y_j, SS[i*mem+j] = s_i·s_j
   double *d_W = nullptr;        // [(2*mem)^2]
@@ -53,6 +54,14 @@ __global__ void div_sqrt_dev_kernel(double *out, const double *x, const double *
   const double d = sqrt(*dscal);
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = x[i] / d;
+}
+
+// *out = partials[0] + ... + partials[count-1] in index order (one warp)
+__global__ void sum_partials_kernel(const double *partials, int count, double *out) {
+  double s = 0.0;
+  for (int b = threadIdx.x; b < count; b += 32) s += partials[b];
+  s = warp_sum(s);
+  if (threadIdx.x == 0) *out = s;
 }
 
 // out[j] = base(j), then sequentially out[j] (+|-)= coef_t * col_t[j];  coef_t = dots[t] / cdiv[t].
@@ -383,7 +392,7 @@ static void compact_columns(const b2o_qn *q, CompactArgs &a, double alpha, doubl
 
 // one launch of the compact kernel over rows [r0, r1) (r0 a multiple of the pitch alignment)
 static int compact_launch_rows(b2o_qn *q, const CompactArgs &base, double *res, const double *x, int64_t r0, int64_t r1, int mode,
-                               int accumulate) {
+                               int accumulate, bool push_a = false, int *grid_out = nullptr) {
   b2o_ctx *c = q->ctx;
   CompactArgs a = base;
   for (int i = 0; i < a.ncols; ++i) a.cols[i] += r0;
@@ -412,7 +421,9 @@ static int compact_launch_rows(b2o_qn *q, const CompactArgs &base, double *res, 
   if (coop) a.bar_target = c->bar_base + (unsigned long long)cfg.grid;
   b2o_mbox_fill(c, &a.mbox);
   if (!coop) a.mbox.nranks = 1;
-  int st = (q->kind == 0 && (q->inverse || q->fwd_compact)) ? launch_compact_R<OP_INV_COMPACT>(c, cfg, a, coop)
+  if (grid_out) *grid_out = cfg.grid;
+  int st = push_a                                                   ? launch_compact_R<OP_PUSH_A>(c, cfg, a, coop)
+           : (q->kind == 0 && (q->inverse || q->fwd_compact)) ? launch_compact_R<OP_INV_COMPACT>(c, cfg, a, coop)
            : q->kind == 0             ? launch_compact_R<OP_LBFGS_FWD>(c, cfg, a, coop)
                                       : launch_compact_R<OP_LSR1>(c, cfg, a, coop);
   if (st == B2O_OK && coop) {
@@ -806,6 +817,12 @@ extern "C" int b2o_qn_set_option(b2o_qn *q, const char *key, int64_t value) {
     }
     return B2O_OK;
   }
+  if (!strcmp(key, "push_mode")) {
+    // 1 (default) = the a_k rebuild of push! runs on the streaming apply kernel; 0 = generic multi-dot + linear-combination passes
+    if (value != 0 && value != 1) B2O_FAIL(B2O_EARG, "push_mode must be 0 or 1");
+    q->push_streamed = value == 1;
+    return B2O_OK;
+  }
   if (!strcmp(key, "forward_mode")) {
     // 0 = the reference's a_k/b_k form (default); 1 = compact form: push! costs O(m) dots instead of O(m^2) vector passes
     if (!(q->kind == 0 && !q->inverse)) B2O_FAIL(B2O_EARG, "forward_mode applies to the forward LBFGSOperator");
@@ -1032,6 +1049,39 @@ static int lbfgs_push_common(b2o_qn *q, const double *s, const double *y, double
         dcols[2 * j + 1] = a.cols[2 * j + 1];
       }
       a.nterms = 2 * nprev;
+      if (n > 0 && 2 * nprev <= B2O_MAX_COLS && q->push_streamed) {
+        // a_k = (operator truncated to the pairs older than k) * s_k: ONE launch of the streaming apply kernel (TMA ring, all
+        // 2(k-1) dots + combine + the dot s_k·a_k), then the scaling pass                          :239-248
+        CompactArgs ca;
+        memset(&ca, 0, sizeof(ca));
+        for (int j = 0; j < nprev; ++j) {
+          ca.cols[2 * j] = q->col(q->A, prev[j]);
+          ca.cols[2 * j + 1] = q->col(q->B, prev[j]);
+          ca.cdiv[2 * j] = ca.cdiv[2 * j + 1] = 1.0;
+        }
+        ca.ncols = 2 * nprev;
+        ca.alpha = 1.0;
+        ca.beta = 0.0;
+        ca.gamma = q->gamma;
+        ca.scaling = 1;
+        int grid = 0;
+        if (ca.ncols == 0) {
+          B2O_TRY(compact_launch_rows(q, ca, ak, sk, 0, n, MODE_PHASE2, 0, true, &grid));
+        } else if (c->nranks <= 1 || c->mbox_ready) {
+          B2O_TRY(compact_launch_rows(q, ca, ak, sk, 0, n, MODE_FUSED, 0, true, &grid));
+        } else {
+          B2O_TRY(compact_launch_rows(q, ca, ak, sk, 0, n, MODE_PHASE1, 0, true, &grid));
+          B2O_TRY(b2o_allreduce_sum_f64(c, c->d_dots, ca.ncols));
+          B2O_TRY(compact_launch_rows(q, ca, ak, sk, 0, n, MODE_PHASE2, 0, true, &grid));
+        }
+        sum_partials_kernel<<<1, 32, 0, c->stream>>>(c->d_partials + (size_t)grid * ca.ncols, grid, c->d_dots + 256);
+        c->launches++;
+        B2O_TRY(b2o_allreduce_sum_f64(c, c->d_dots + 256, 1));
+        div_sqrt_dev_kernel<<<ew_grid(c, n), 256, 0, c->stream>>>(ak, ak, c->d_dots + 256, n);     // :248
+        c->launches++;
+        prev[nprev++] = k;
+        continue;
+      }
       B2O_TRY(multi_dots(c, a.nterms, dcols, sk, n, c->d_dots));
       a.base_mode = 0;  // a[k] .= s[k] ./ γ                                                     :239
       a.P1 = sk;

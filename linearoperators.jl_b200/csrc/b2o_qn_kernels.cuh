@@ -10,7 +10,11 @@
 #pragma once
 #include "b2o_stream.cuh"
 
-enum { OP_LBFGS_FWD = 0, OP_LSR1 = 1, OP_INV_COMPACT = 2 };
+enum { OP_LBFGS_FWD = 0, OP_LSR1 = 1, OP_INV_COMPACT = 2, OP_PUSH_A = 3 };
+// OP_PUSH_A: one step of the a_k rebuild inside push! (src/lbfgs.jl:236-250): a_k = s_k/γ + Σ_{l<k} [(b_l·s_k) b_l − (a_l·s_k) a_l]
+// is the forward apply of the operator truncated to the pairs older than k, taken at x = s_k -- same two streaming phases; the
+// combine keeps the reference's TWO statements per pair (.+= then .-=) and the dot s_k·a_k (:248) is taken on the way out
+// (per-CTA partials at partials[grid*ncols + cta]).
 enum { MODE_FUSED = 0, MODE_PHASE1 = 1, MODE_PHASE2 = 2 };
 
 struct CompactArgs {
@@ -221,6 +225,8 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
   } else {
     const double alpha = p.alpha, beta = p.beta, gamma = p.gamma;
     double xn[EPT], q[EPT], rold[EPT];
+    double xc[OP == OP_PUSH_A ? EPT : 1];
+    double racc = 0.0;
     if (my_tiles > 0) load_user_tile<R>(p.x, (blockIdx.x + (my_tiles - 1) * grid) * R, p.n, p.x_al16, xn);
     for (int64_t i = my_tiles - 1; i >= 0; --i) {
       const int64_t t = blockIdx.x + i * grid;
@@ -229,6 +235,13 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
         // q .= x ; scaling && (q ./= γ)                                   src/lbfgs.jl:183-186
 #pragma unroll
         for (int j = 0; j < EPT; ++j) q[j] = p.scaling ? xn[j] / gamma : xn[j];
+      } else if (OP == OP_PUSH_A) {
+        // a[k] .= s[k] ./ γ                                               src/lbfgs.jl:239
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+          xc[j] = xn[j];
+          q[j] = xn[j] / gamma;
+        }
       } else if (OP == OP_INV_COMPACT) {
         // H0 x = γ x (γ = 1 without scaling)
 #pragma unroll
@@ -242,7 +255,7 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
         }
       }
       if (i > 0) load_user_tile<R>(p.x, (t - grid) * R, p.n, p.x_al16, xn);
-      if (OP == OP_LBFGS_FWD) {
+      if (OP == OP_LBFGS_FWD || OP == OP_PUSH_A) {
         for (int c = 0; c < ncols; c += 2) {
           // q .+= bx .* b[k] .- ax .* a[k]                                src/lbfgs.jl:194
           const uint32_t sa = pos.slot, pa = pos.par;
@@ -257,14 +270,25 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
 #pragma unroll
           for (int j = 0; j < EPT / 2; ++j) {
             double2 a = A[j * B2O_NCONS + tid], b = B[j * B2O_NCONS + tid];
-            q[2 * j] = q[2 * j] + (bx * b.x - ax * a.x);
-            q[2 * j + 1] = q[2 * j + 1] + (bx * b.y - ax * a.y);
+            if (OP == OP_PUSH_A) {
+              // a[k] .+= dot(b[l], s[k]) .* b[l] ; a[k] .-= dot(a[l], s[k]) .* a[l]      src/lbfgs.jl:244-245
+              q[2 * j] = (q[2 * j] + bx * b.x) - ax * a.x;
+              q[2 * j + 1] = (q[2 * j + 1] + bx * b.y) - ax * a.y;
+            } else {
+              q[2 * j] = q[2 * j] + (bx * b.x - ax * a.x);
+              q[2 * j + 1] = q[2 * j + 1] + (bx * b.y - ax * a.y);
+            }
           }
           consumer_release(rg, sa);
           consumer_release(rg, sb);
         }
+        if (OP == OP_PUSH_A) {
 #pragma unroll
-        for (int j = 0; j < EPT; ++j) q[j] = (beta != 0.0) ? alpha * q[j] + beta * rold[j] : alpha * q[j];  // :197-201
+          for (int j = 0; j < EPT; ++j) racc = fma(q[j], xc[j], racc);                           // dot(s[k], a[k])   :248
+        } else {
+#pragma unroll
+          for (int j = 0; j < EPT; ++j) q[j] = (beta != 0.0) ? alpha * q[j] + beta * rold[j] : alpha * q[j];  // :197-201
+        }
       } else {
         for (int c = 0; c < ncols; ++c) {
           // LSR1: ax = α * dot(a[k], x) / as[k];  q[j] += ax * a[k][j]    src/lsr1.jl:101-104
@@ -287,6 +311,17 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
         }
       }
       store_user_tile<R>(p.res, t * R, p.n, p.res_al16, q);
+    }
+    if (OP == OP_PUSH_A) {
+      // per-CTA partial of dot(s[k], a[k]) in a fixed order (accs is free after phase 1)
+      racc = warp_sum(racc);
+      if (lane == 0) accs[warp] = racc;
+      consumers_sync();
+      if (tid == 0) {
+        double sum = 0.0;
+        for (int w = 0; w < B2O_CONS_WARPS; ++w) sum += accs[w];
+        p.partials[(size_t)gridDim.x * ncols + blockIdx.x] = sum;
+      }
     }
   }
 }

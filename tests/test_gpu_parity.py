@@ -947,3 +947,26 @@ def test_block_apply_matches_vector_apply(lo, ctx, orc, kind, n, mem, npush, nrh
             assert rel(host(Res[:, j]), host(v)) <= (1e-13 if tol == 1e-12 else 1e-10)
     with pytest.raises(lo.LinearOperatorException):
         lo.mul_(Res, op, _colmajor(ctx, n + 1, nrhs, 1))
+
+
+@pytest.mark.parametrize("n,mem,npush", [(1000, 5, 7), (100003, 10, 13), (75776, 3, 3)])
+def test_push_streamed_rebuild_equals_generic_passes(lo, ctx, orc, n, mem, npush):
+    """push! rebuilds every a_k (src/lbfgs.jl:236-250): the streaming-kernel path (default) and the generic multi-dot +
+    linear-combination passes are the same statements -- states agree to reduction-order rounding, both match the oracle"""
+    Bs, Bg, o = lo.LBFGSOperator(n, mem=mem, ctx=ctx), lo.LBFGSOperator(n, mem=mem, ctx=ctx), orc.LBFGS(n, mem=mem)
+    Bg.set_option("push_mode", 0)
+    for i in range(npush):
+        s = ctx.uniform(n, 100 + i)
+        y = s + 0.1 * ctx.uniform(n, 200 + i)
+        l0 = ctx.launch_count()
+        lo.push_(Bs, s, y)
+        nl = ctx.launch_count() - l0
+        assert nl <= 3 * min(i + 1, mem) + 8, nl                   # one streaming launch + reduce + scale per a_k
+        lo.push_(Bg, s, y)
+        o.push(host(s), host(y))
+    for k in range(mem):
+        for w in "ab":
+            assert rel(host(Bs.data.col(w, k)), host(Bg.data.col(w, k))) <= 1e-13
+            assert rel(host(Bs.data.col(w, k)), o.col(w, k)) <= TOL
+    x = ctx.uniform(n, 7)
+    assert rel(host(Bs * x), o.apply(host(x))) <= TOL

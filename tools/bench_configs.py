@@ -76,13 +76,29 @@ def main():
                 if i == 0:
                     tp = 0.0
                 tp += time.perf_counter() - t1
+            # three more pushes (same pairs for both representations); the reference form takes them through the generic
+            # multi-dot + linear-combination passes (push_mode 0) for comparison with the streaming rebuild above
+            if not compact:
+                B.set_option("push_mode", 0)
+            t_g = 0.0
+            for i in range(3):
+                s = ctx.uniform(n, 700 + i)
+                y = s + 0.1 * ctx.uniform(n, 800 + i)
+                torch.cuda.synchronize()
+                t1 = time.perf_counter()
+                lo.push_(B, s, y)
+                torch.cuda.synchronize()
+                t_g += time.perf_counter() - t1
+            tp_generic = None if compact else round(t_g / 3 * 1e3, 2)
+            if not compact:
+                B.set_option("push_mode", 1)
             ms = timeit(lambda: lo.mul_(res, B, v), 20)
             xs = ctx.zeros(n)
             ms_solve = timeit(lambda: lo.solve_shifted_system_(xs, B, v, 0.5), 3, warmup=1)
             if not compact:
                 ref = res.clone()
             line("LBFGSOperator(mem=10) %s" % ("compact form (extension)" if compact else "a_k/b_k form (reference algorithm)"), ms,
-                 (4 * m + 3) * 8.0 * n, push_ms_steady_state=round(tp / 5 * 1e3, 2), solve_shifted_system_ms=round(ms_solve, 2),
+                 (4 * m + 3) * 8.0 * n, push_ms_steady_state=round(tp / 5 * 1e3, 2), push_ms_generic_passes=tp_generic, solve_shifted_system_ms=round(ms_solve, 2),
                  rel_diff_vs_reference_form=(float(torch.linalg.norm(res - ref) / torch.linalg.norm(ref)) if compact else 0.0))
             del B
             torch.cuda.empty_cache()
