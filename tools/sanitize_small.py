@@ -40,6 +40,23 @@ def main():
         lo.mul_(r, g, x[:n].clone())
         if kind in ("fwd", "lsr1"):
             lo.diag(g)
+        if kind != "inv":
+            # block apply (NR = 4 and NR = 8 kernels) and, for the forward form, the streamed a_k rebuild ran in push_ above
+            for k in (3, 8):
+                Xb = torch.empty((k, n + 2), dtype=torch.float64, device="cuda")
+                for j in range(k):
+                    Xb[j, :n] = ctx.uniform(n, 300 + j)
+                Rb = torch.zeros((k, n + 2), dtype=torch.float64, device="cuda")
+                lo.mul_(Rb[:, :n].T, g, Xb[:, :n].T, 1.5, 0.5)
+        if kind == "fwd":
+            xs = ctx.zeros(n)
+            lo.solve_shifted_system_(xs, g, x, 0.5)
+            gc = lo.LBFGSOperator(n, mem=3, compact=True, ctx=ctx)
+            for i in range(4):
+                s = ctx.uniform(n, 100 + i)
+                lo.push_(gc, s, s + 0.1 * ctx.uniform(n, 200 + i))
+            lo.mul_(r, gc, x, 1.5, -0.5)
+            lo.solve_shifted_system_(xs, gc, x, 0.5)
         xh, rh = x.cpu().pin_memory(), torch.empty(n, dtype=torch.float64).pin_memory()
         g.apply_host(rh, xh)
     f = lo.fuse(lo.opHouseholder(h) * lo.opDiagonal(d) + 0.1 * lo.opEye(n))
