@@ -818,7 +818,8 @@ extern "C" int b2o_qn_set_option(b2o_qn *q, const char *key, int64_t value) {
     return B2O_OK;
   }
   if (!strcmp(key, "push_mode")) {
-    // 1 (default) = the a_k rebuild of push! runs on the streaming apply kernel; 0 = generic multi-dot + linear-combination passes
+    // 1 (default) = the a_k rebuild of push! (L-BFGS forward form and L-SR1) runs on the streaming apply kernel;
+    // 0 = generic multi-dot + linear-combination passes
     if (value != 0 && value != 1) B2O_FAIL(B2O_EARG, "push_mode must be 0 or 1");
     q->push_streamed = value == 1;
     return B2O_OK;
@@ -1297,6 +1298,40 @@ static int lsr1_push(b2o_qn *q, const double *s, const double *y, int *accepted)
       dcols[j] = a.cols[j];
     }
     a.nterms = nprev;
+    if (n > 0 && q->push_streamed && nprev <= B2O_MAX_COLS) {
+      // a_k = y_k - (operator truncated to the terms older than k) * s_k: the streaming apply kernel with res preloaded with
+      // y_k, α = -1, β = 1 evaluates exactly the reference's statements ((-x)/γ + y == y - x/γ, q + (-(d/as))·a == q - (d/as)·a
+      // in IEEE arithmetic); one pass then takes as[k] = a_k·s_k and ‖a_k‖²                      :169-179
+      B2O_CUDA(cudaMemcpyAsync(ak, yk, bytes, cudaMemcpyDeviceToDevice, c->stream));
+      CompactArgs ca;
+      memset(&ca, 0, sizeof(ca));
+      for (int j = 0; j < nprev; ++j) {
+        ca.cols[j] = q->col(q->A, prev[j]);
+        ca.cdiv[j] = q->aux[prev[j]];
+      }
+      ca.ncols = nprev;
+      ca.alpha = -1.0;
+      ca.beta = 1.0;
+      ca.gamma = q->gamma;
+      ca.scaling = 1;
+      if (ca.ncols == 0) {
+        B2O_TRY(compact_launch_rows(q, ca, ak, sk, 0, n, MODE_PHASE2, 0));
+      } else if (c->nranks <= 1 || c->mbox_ready) {
+        B2O_TRY(compact_launch_rows(q, ca, ak, sk, 0, n, MODE_FUSED, 0));
+      } else {
+        B2O_TRY(compact_launch_rows(q, ca, ak, sk, 0, n, MODE_PHASE1, 0));
+        B2O_TRY(b2o_allreduce_sum_f64(c, c->d_dots, ca.ncols));
+        B2O_TRY(compact_launch_rows(q, ca, ak, sk, 0, n, MODE_PHASE2, 0));
+      }
+      const double *u2[2] = {ak, ak}, *v2[2] = {sk, ak};
+      double r2[2] = {0, 0};
+      B2O_TRY(b2o_pair_dots(c, 2, u2, v2, n, c->d_dots + 256));
+      B2O_TRY(b2o_read_scalars(c, c->d_dots + 256, 2, r2));
+      q->aux[k] = r2[0];                                                                          // :177
+      if (q->aux[k] != 0) q->opnorm_ub += r2[1] / fabs(q->aux[k]);                                // :179
+      prev[nprev++] = k;
+      continue;
+    }
     B2O_TRY(multi_dots(c, a.nterms, dcols, sk, n, c->d_dots));
     a.base_mode = 1;  // a[k] .= y[k] .- s[k] ./ γ                                               :169
     a.P0 = yk;

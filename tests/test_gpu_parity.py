@@ -970,3 +970,23 @@ def test_push_streamed_rebuild_equals_generic_passes(lo, ctx, orc, n, mem, npush
             assert rel(host(Bs.data.col(w, k)), o.col(w, k)) <= TOL
     x = ctx.uniform(n, 7)
     assert rel(host(Bs * x), o.apply(host(x))) <= TOL
+
+
+@pytest.mark.parametrize("n,mem,npush", [(1000, 5, 7), (100003, 10, 13)])
+def test_lsr1_push_streamed_rebuild_equals_generic_passes(lo, ctx, orc, n, mem, npush):
+    """L-SR1 push! (src/lsr1.jl:166-181): streaming-kernel rebuild (default) vs generic passes vs oracle"""
+    Ls, Lg, o = lo.LSR1Operator(n, mem=mem, ctx=ctx), lo.LSR1Operator(n, mem=mem, ctx=ctx), orc.LSR1(n, mem=mem)
+    Lg.set_option("push_mode", 0)
+    for i in range(npush):
+        s = ctx.uniform(n, 100 + i, -1.0, 1.0)
+        y = 2.0 * s + 0.3 * ctx.uniform(n, 200 + i, -1.0, 1.0)
+        lo.push_(Ls, s, y)
+        lo.push_(Lg, s, y)
+        assert Ls.last_push_accepted == Lg.last_push_accepted == o.push(host(s), host(y))
+    for k in range(mem):
+        assert rel(host(Ls.data.col("a", k)), host(Lg.data.col("a", k))) <= 1e-13
+        assert rel(host(Ls.data.col("a", k)), o.col("a", k)) <= TOL
+    assert np.allclose(Ls.data.aux, Lg.data.aux, rtol=1e-12, atol=0)
+    assert abs(Ls.data.opnorm_upper_bound - o.opnorm_upper_bound) <= 1e-10 * abs(o.opnorm_upper_bound)
+    x = ctx.uniform(n, 7)
+    assert rel(host(Ls * x), o.apply(host(x))) <= TOL

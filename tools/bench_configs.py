@@ -103,6 +103,28 @@ def main():
             del B
             torch.cuda.empty_cache()
         return
+    if only == ["lsr1push"]:
+        m = 10
+        for mode in (1, 0):
+            L = lo.LSR1Operator(n, mem=m, ctx=ctx)
+            L.set_option("push_mode", mode)
+            for i in range(m):
+                s = ctx.uniform(n, 300 + i, -1.0, 1.0)
+                lo.push_(L, s, 2.0 * s + 0.3 * ctx.uniform(n, 400 + i, -1.0, 1.0))
+            tp = 0.0
+            for i in range(4):
+                s = ctx.uniform(n, 500 + i, -1.0, 1.0)
+                y = 2.0 * s + 0.3 * ctx.uniform(n, 600 + i, -1.0, 1.0)
+                torch.cuda.synchronize()
+                t1 = time.perf_counter()
+                lo.push_(L, s, y)
+                torch.cuda.synchronize()
+                tp += time.perf_counter() - t1
+            print(json.dumps({"case": "LSR1Operator(mem=10) push!, steady state, %s" % ("streaming rebuild" if mode else "generic passes"),
+                              "ms": round(tp / 4 * 1e3, 2), "accepted": bool(L.last_push_accepted)}), flush=True)
+            del L
+            torch.cuda.empty_cache()
+        return
     if only == ["multi"]:
         # §8f rank 4: mul!(Res, B, X) with nrhs right-hand sides; the state columns are streamed once per 8 of them
         m = 10
