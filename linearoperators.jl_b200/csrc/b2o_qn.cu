@@ -57,11 +57,13 @@ __global__ void div_sqrt_dev_kernel(double *out, const double *x, const double *
 }
 
 // *out = partials[0] + ... + partials[count-1] in index order (one warp)
+// out[o] = partials[o] + partials[2+o] + ... (count pairs, index order), o = warp index (launch with 32*nout threads)
 __global__ void sum_partials_kernel(const double *partials, int count, double *out) {
+  const int o = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double s = 0.0;
-  for (int b = threadIdx.x; b < count; b += 32) s += partials[b];
+  for (int b = lane; b < count; b += 32) s += partials[2 * b + o];
   s = warp_sum(s);
-  if (threadIdx.x == 0) *out = s;
+  if (lane == 0) out[o] = s;
 }
 
 // out[j] = base(j), then sequentially out[j] (+|-)= coef_t * col_t[j];  coef_t = dots[t] / cdiv[t].
@@ -392,12 +394,13 @@ static void compact_columns(const b2o_qn *q, CompactArgs &a, double alpha, doubl
 
 // one launch of the compact kernel over rows [r0, r1) (r0 a multiple of the pitch alignment)
 static int compact_launch_rows(b2o_qn *q, const CompactArgs &base, double *res, const double *x, int64_t r0, int64_t r1, int mode,
-                               int accumulate, bool push_a = false, int *grid_out = nullptr) {
+                               int accumulate, int push_op = -1, int *grid_out = nullptr) {
   b2o_ctx *c = q->ctx;
   CompactArgs a = base;
   for (int i = 0; i < a.ncols; ++i) a.cols[i] += r0;
   a.x = x + r0;
   a.res = res + r0;
+  if (a.y2) a.y2 += r0;
   a.n = r1 - r0;
   LaunchCfg cfg;
   cfg.R = c->tile_rows;
@@ -422,7 +425,8 @@ static int compact_launch_rows(b2o_qn *q, const CompactArgs &base, double *res, 
   b2o_mbox_fill(c, &a.mbox);
   if (!coop) a.mbox.nranks = 1;
   if (grid_out) *grid_out = cfg.grid;
-  int st = push_a                                                   ? launch_compact_R<OP_PUSH_A>(c, cfg, a, coop)
+  int st = push_op == OP_PUSH_A                                     ? launch_compact_R<OP_PUSH_A>(c, cfg, a, coop)
+           : push_op == OP_PUSH_L                                   ? launch_compact_R<OP_PUSH_L>(c, cfg, a, coop)
            : (q->kind == 0 && (q->inverse || q->fwd_compact)) ? launch_compact_R<OP_INV_COMPACT>(c, cfg, a, coop)
            : q->kind == 0             ? launch_compact_R<OP_LBFGS_FWD>(c, cfg, a, coop)
                                       : launch_compact_R<OP_LSR1>(c, cfg, a, coop);
@@ -1067,13 +1071,13 @@ static int lbfgs_push_common(b2o_qn *q, const double *s, const double *y, double
         ca.scaling = 1;
         int grid = 0;
         if (ca.ncols == 0) {
-          B2O_TRY(compact_launch_rows(q, ca, ak, sk, 0, n, MODE_PHASE2, 0, true, &grid));
+          B2O_TRY(compact_launch_rows(q, ca, ak, sk, 0, n, MODE_PHASE2, 0, OP_PUSH_A, &grid));
         } else if (c->nranks <= 1 || c->mbox_ready) {
-          B2O_TRY(compact_launch_rows(q, ca, ak, sk, 0, n, MODE_FUSED, 0, true, &grid));
+          B2O_TRY(compact_launch_rows(q, ca, ak, sk, 0, n, MODE_FUSED, 0, OP_PUSH_A, &grid));
         } else {
-          B2O_TRY(compact_launch_rows(q, ca, ak, sk, 0, n, MODE_PHASE1, 0, true, &grid));
+          B2O_TRY(compact_launch_rows(q, ca, ak, sk, 0, n, MODE_PHASE1, 0, OP_PUSH_A, &grid));
           B2O_TRY(b2o_allreduce_sum_f64(c, c->d_dots, ca.ncols));
-          B2O_TRY(compact_launch_rows(q, ca, ak, sk, 0, n, MODE_PHASE2, 0, true, &grid));
+          B2O_TRY(compact_launch_rows(q, ca, ak, sk, 0, n, MODE_PHASE2, 0, OP_PUSH_A, &grid));
         }
         sum_partials_kernel<<<1, 32, 0, c->stream>>>(c->d_partials + (size_t)grid * ca.ncols, grid, c->d_dots + 256);
         c->launches++;
@@ -1299,10 +1303,8 @@ static int lsr1_push(b2o_qn *q, const double *s, const double *y, int *accepted)
     }
     a.nterms = nprev;
     if (n > 0 && q->push_streamed && nprev <= B2O_MAX_COLS) {
-      // a_k = y_k - (operator truncated to the terms older than k) * s_k: the streaming apply kernel with res preloaded with
-      // y_k, α = -1, β = 1 evaluates exactly the reference's statements ((-x)/γ + y == y - x/γ, q + (-(d/as))·a == q - (d/as)·a
-      // in IEEE arithmetic); one pass then takes as[k] = a_k·s_k and ‖a_k‖²                      :169-179
-      B2O_CUDA(cudaMemcpyAsync(ak, yk, bytes, cudaMemcpyDeviceToDevice, c->stream));
+      // a_k = (y_k - s_k/γ) - Σ_{l<k} ((a_l·s_k)/as_l) a_l: ONE launch of the streaming kernel (all dots, the combine with the
+      // reference's statements, as[k] = a_k·s_k and ‖a_k‖² on the way out)                      :169-179
       CompactArgs ca;
       memset(&ca, 0, sizeof(ca));
       for (int j = 0; j < nprev; ++j) {
@@ -1310,22 +1312,25 @@ static int lsr1_push(b2o_qn *q, const double *s, const double *y, int *accepted)
         ca.cdiv[j] = q->aux[prev[j]];
       }
       ca.ncols = nprev;
-      ca.alpha = -1.0;
-      ca.beta = 1.0;
+      ca.alpha = 1.0;
+      ca.beta = 0.0;
       ca.gamma = q->gamma;
       ca.scaling = 1;
+      ca.y2 = yk;
+      int grid = 0;
       if (ca.ncols == 0) {
-        B2O_TRY(compact_launch_rows(q, ca, ak, sk, 0, n, MODE_PHASE2, 0));
+        B2O_TRY(compact_launch_rows(q, ca, ak, sk, 0, n, MODE_PHASE2, 0, OP_PUSH_L, &grid));
       } else if (c->nranks <= 1 || c->mbox_ready) {
-        B2O_TRY(compact_launch_rows(q, ca, ak, sk, 0, n, MODE_FUSED, 0));
+        B2O_TRY(compact_launch_rows(q, ca, ak, sk, 0, n, MODE_FUSED, 0, OP_PUSH_L, &grid));
       } else {
-        B2O_TRY(compact_launch_rows(q, ca, ak, sk, 0, n, MODE_PHASE1, 0));
+        B2O_TRY(compact_launch_rows(q, ca, ak, sk, 0, n, MODE_PHASE1, 0, OP_PUSH_L, &grid));
         B2O_TRY(b2o_allreduce_sum_f64(c, c->d_dots, ca.ncols));
-        B2O_TRY(compact_launch_rows(q, ca, ak, sk, 0, n, MODE_PHASE2, 0));
+        B2O_TRY(compact_launch_rows(q, ca, ak, sk, 0, n, MODE_PHASE2, 0, OP_PUSH_L, &grid));
       }
-      const double *u2[2] = {ak, ak}, *v2[2] = {sk, ak};
+      sum_partials_kernel<<<1, 64, 0, c->stream>>>(c->d_partials + (size_t)grid * ca.ncols, grid, c->d_dots + 256);
+      c->launches++;
+      B2O_TRY(b2o_allreduce_sum_f64(c, c->d_dots + 256, 2));
       double r2[2] = {0, 0};
-      B2O_TRY(b2o_pair_dots(c, 2, u2, v2, n, c->d_dots + 256));
       B2O_TRY(b2o_read_scalars(c, c->d_dots + 256, 2, r2));
       q->aux[k] = r2[0];                                                                          // :177
       if (q->aux[k] != 0) q->opnorm_ub += r2[1] / fabs(q->aux[k]);                                // :179

@@ -10,11 +10,13 @@
 #pragma once
 #include "b2o_stream.cuh"
 
-enum { OP_LBFGS_FWD = 0, OP_LSR1 = 1, OP_INV_COMPACT = 2, OP_PUSH_A = 3 };
+enum { OP_LBFGS_FWD = 0, OP_LSR1 = 1, OP_INV_COMPACT = 2, OP_PUSH_A = 3, OP_PUSH_L = 4 };
 // OP_PUSH_A: one step of the a_k rebuild inside push! (src/lbfgs.jl:236-250): a_k = s_k/γ + Σ_{l<k} [(b_l·s_k) b_l − (a_l·s_k) a_l]
 // is the forward apply of the operator truncated to the pairs older than k, taken at x = s_k -- same two streaming phases; the
 // combine keeps the reference's TWO statements per pair (.+= then .-=) and the dot s_k·a_k (:248) is taken on the way out
-// (per-CTA partials at partials[grid*ncols + cta]).
+// (per-CTA partials at partials[grid*ncols + 2*cta]).
+// OP_PUSH_L: the same for L-SR1 (src/lsr1.jl:169-179): a_k = (y_k − s_k/γ) − Σ_{l<k} ((a_l·s_k)/as_l) a_l with x = s_k, y2 = y_k;
+// takes as_k = a_k·s_k and ‖a_k‖² on the way out (partials[grid*ncols + 2*cta + {0,1}]).
 enum { MODE_FUSED = 0, MODE_PHASE1 = 1, MODE_PHASE2 = 2 };
 
 struct CompactArgs {
@@ -36,6 +38,7 @@ struct CompactArgs {
   int accumulate;                    // split mode: dots[c] += this launch's partial (row-chunked host pipeline)
   uint32_t accs_off, coef_off, bar_off;
   MboxDev mbox;                      // nranks > 1: the dots are all-reduced in-kernel through the NVLink peer mailbox
+  const double *y2;                  // OP_PUSH_L: y_k (library-owned column)
   const double *W;                   // OP_INV_COMPACT: ncols x ncols middle matrix (row-major), coefficients = W * dots
   int base_div;                      // OP_INV_COMPACT: base term x/γ (compact FORWARD form) instead of γx (compact inverse)
 };
@@ -225,8 +228,8 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
   } else {
     const double alpha = p.alpha, beta = p.beta, gamma = p.gamma;
     double xn[EPT], q[EPT], rold[EPT];
-    double xc[OP == OP_PUSH_A ? EPT : 1];
-    double racc = 0.0;
+    double xc[(OP == OP_PUSH_A || OP == OP_PUSH_L) ? EPT : 1];
+    double racc = 0.0, racc2 = 0.0;
     if (my_tiles > 0) load_user_tile<R>(p.x, (blockIdx.x + (my_tiles - 1) * grid) * R, p.n, p.x_al16, xn);
     for (int64_t i = my_tiles - 1; i >= 0; --i) {
       const int64_t t = blockIdx.x + i * grid;
@@ -241,6 +244,14 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
         for (int j = 0; j < EPT; ++j) {
           xc[j] = xn[j];
           q[j] = xn[j] / gamma;
+        }
+      } else if (OP == OP_PUSH_L) {
+        // a[k] .= y[k] .- s[k] ./ γ                                       src/lsr1.jl:169
+        load_user_tile<R>(p.y2, t * R, p.n, true, rold);
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+          xc[j] = xn[j];
+          q[j] = rold[j] - xn[j] / gamma;
         }
       } else if (OP == OP_INV_COMPACT) {
         // H0 x = γ x (γ = 1 without scaling)
@@ -293,14 +304,20 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
         for (int c = 0; c < ncols; ++c) {
           // LSR1: ax = α * dot(a[k], x) / as[k];  q[j] += ax * a[k][j]    src/lsr1.jl:101-104
           // compact inverse: q += c_j * col_j
-          const double ax = (OP == OP_INV_COMPACT) ? coef[c] : (alpha * coef[c]) / p.cdiv[c];
+          // push! of L-SR1: as = dot(a[l], s[k]) / as[l];  a[k] .-= as .* a[l]              src/lsr1.jl:173-174
+          const double ax = (OP == OP_INV_COMPACT) ? coef[c] : (OP == OP_PUSH_L) ? coef[c] / p.cdiv[c] : (alpha * coef[c]) / p.cdiv[c];
           mbar_wait(&rg.full[pos.slot], pos.par);
           const double2 *A = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R);
 #pragma unroll
           for (int j = 0; j < EPT / 2; ++j) {
             double2 a = A[j * B2O_NCONS + tid];
-            q[2 * j] = q[2 * j] + ax * a.x;
-            q[2 * j + 1] = q[2 * j + 1] + ax * a.y;
+            if (OP == OP_PUSH_L) {
+              q[2 * j] = q[2 * j] - ax * a.x;
+              q[2 * j + 1] = q[2 * j + 1] - ax * a.y;
+            } else {
+              q[2 * j] = q[2 * j] + ax * a.x;
+              q[2 * j + 1] = q[2 * j + 1] + ax * a.y;
+            }
           }
           consumer_release(rg, pos.slot);
           pos.advance();
@@ -309,18 +326,29 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
 #pragma unroll
           for (int j = 0; j < EPT; ++j) q[j] = (beta != 0.0) ? alpha * q[j] + beta * rold[j] : alpha * q[j];
         }
+        if (OP == OP_PUSH_L) {
+#pragma unroll
+          for (int j = 0; j < EPT; ++j) {
+            racc = fma(q[j], xc[j], racc);                                                        // as[k] = dot(a[k], s[k])   :177
+            racc2 = fma(q[j], q[j], racc2);                                                       // norm(a[k])^2              :179
+          }
+        }
       }
       store_user_tile<R>(p.res, t * R, p.n, p.res_al16, q);
     }
-    if (OP == OP_PUSH_A) {
-      // per-CTA partial of dot(s[k], a[k]) in a fixed order (accs is free after phase 1)
+    if (OP == OP_PUSH_A || OP == OP_PUSH_L) {
+      // per-CTA partials of the outgoing dots in a fixed order (accs is free after phase 1)
       racc = warp_sum(racc);
-      if (lane == 0) accs[warp] = racc;
+      racc2 = warp_sum(racc2);
+      if (lane == 0) {
+        accs[warp] = racc;
+        accs[B2O_CONS_WARPS + warp] = racc2;
+      }
       consumers_sync();
-      if (tid == 0) {
+      if (tid < 2) {
         double sum = 0.0;
-        for (int w = 0; w < B2O_CONS_WARPS; ++w) sum += accs[w];
-        p.partials[(size_t)gridDim.x * ncols + blockIdx.x] = sum;
+        for (int w = 0; w < B2O_CONS_WARPS; ++w) sum += accs[tid * B2O_CONS_WARPS + w];
+        p.partials[(size_t)gridDim.x * ncols + 2 * blockIdx.x + tid] = sum;
       }
     }
   }
