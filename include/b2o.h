@@ -53,6 +53,7 @@ typedef struct b2o_qn_s b2o_qn;       /* LBFGSOperator / InverseLBFGSOperator / 
 typedef struct b2o_index_s b2o_index; /* opRestriction / opExtension index set */
 typedef struct b2o_kron_s b2o_kron;   /* kron(A,B) operator (tcgen05 GEMM pair) */
 typedef struct b2o_graph_s b2o_graph; /* static operator tree lowered to one fused launch */
+typedef struct b2o_dense_s b2o_dense; /* LinearOperator(M) for a dense device matrix */
 
 /* ---- library / context ------------------------------------------------------------------ */
 int b2o_version(void);
@@ -208,6 +209,19 @@ int b2o_kron_destroy(b2o_kron *k);
 int b2o_kron_apply(b2o_kron *k, int trans, void *res, int res_dtype, int64_t res_len, const void *x, int64_t x_len, int nb,
                    double alpha, double beta);
 int b2o_kron_flops(b2o_kron *k, int nb, double *flops);
+
+/* ---- LinearOperator(M), dense matrix leaf (src/constructors.jl:15-29) --------------------------- */
+/* M: COLUMN-major (Julia layout) m x n device matrix, leading dimension lda >= max(1,m), dtype B2O_F64 or B2O_F32, aligned to
+ * its element size (16-byte alignment + lda a multiple of 16/sizeof(T) selects the vectorised kernels).  The matrix is borrowed
+ * (aliased) for the lifetime of the handle, like the reference's closures capture M; the handle owns only the partial-sum
+ * workspace of split products.  This is what BlockDiagonalOperator(A, B, C) of CUDA matrices runs (test/gpu/nvidia.jl:8-15). */
+int b2o_dense_create(b2o_ctx *ctx, int dtype, const void *M, int64_t m, int64_t n, int64_t lda, b2o_dense **out);
+int b2o_dense_destroy(b2o_dense *d);
+/* trans = 0: prod!  mul!(res, M, v, α, β) :25;  trans = 1: tprod!/ctprod!  mul!(res, transpose(M), u, α, β) :26-27 (real element
+ * types: adjoint(M) == transpose(M)).  res = α (M v) + β res, res never read when β == 0; vectors have the matrix's dtype. */
+int b2o_dense_apply(b2o_dense *d, int trans, void *res, int64_t res_len, const void *v, int64_t v_len, double alpha, double beta);
+/* algorithmic DRAM bytes of one product (matrix once + vectors), for the roofline */
+int b2o_dense_apply_bytes(b2o_dense *d, int trans, double beta, double *bytes);
 
 /* ---- row-partitioned multi-GPU (one process per GPU) ------------------------------------- */
 /* id: 128-byte ncclUniqueId produced on rank 0 by b2o_comm_unique_id and broadcast by the host

@@ -87,13 +87,35 @@ class Storage:
         return "Storage(%s)" % (self.kind if self.kind != "cuda" else "cuda:%d" % self.device)
 
 
+def _dtype_rank(dt):
+    """(bits, dtype) with None standing for the default Float64"""
+    name = "float64" if dt is None else str(dt).replace("torch.", "")
+    return {"bfloat16": 16, "float16": 16, "float32": 32, "float64": 64}.get(name, 64), dt
+
+
 def promote_storage(a, b):
-    """promote_type(storage_type(op1), storage_type(op2)) must be concrete (src/operations.jl:138-147)."""
+    """promote_type(storage_type(op1), storage_type(op2)) must be concrete (src/operations.jl:138-147); the element type
+    promotes to the wider one (promote_type(Vector{Float32}, Vector{Float64}) == Vector{Float64})."""
     if a == b:
-        return a
+        ra, rb = _dtype_rank(a.dtype), _dtype_rank(b.dtype)
+        if ra[0] == rb[0]:
+            return a
+        return a if ra[0] > rb[0] else b
     raise LinearOperatorException(
         "storage types %r and %r cannot be promoted to a concrete type. "
         "Ensure both operators use compatible storage types (e.g., both GPU or both CPU)." % (a, b))
+
+
+def _is_matrix(x):
+    """AbstractMatrix arguments of the reference's methods (promoted with LinearOperator(M)): a 2-D torch tensor"""
+    return _is_torch(x) and hasattr(x, "dim") and x.dim() == 2
+
+
+def _as_op(x):
+    if _is_matrix(x):
+        from .constructors import DenseMatrixOperator
+        return DenseMatrixOperator(x)
+    return x
 
 
 # ------------------------------------------------------------------ types
@@ -119,6 +141,8 @@ class AbstractLinearOperator:
     def __mul__(self, other):
         if isinstance(other, AbstractLinearOperator):
             return op_times_op(self, other)
+        if _is_matrix(other):
+            return op_times_op(self, _as_op(other))              # op * M = op * LinearOperator(M)   operations.jl:160
         if isinstance(other, (int, float, complex, np.number)):
             return op_times_scalar(self, other)
         if hasattr(other, "shape") and len(other.shape) == 1:
@@ -128,7 +152,12 @@ class AbstractLinearOperator:
     def __rmul__(self, other):
         if isinstance(other, (int, float, complex, np.number)):
             return op_times_scalar(self, other)
+        if _is_matrix(other):
+            return op_times_op(_as_op(other), self)              # M * op = LinearOperator(M) * op   operations.jl:159
         return NotImplemented
+
+    def __rmatmul__(self, other):
+        return self.__rmul__(other)
 
     def __truediv__(self, x):
         return op_times_scalar(self, 1.0 / x)                 # op * (one(T) / x)      operations.jl:183
@@ -136,12 +165,16 @@ class AbstractLinearOperator:
     def __add__(self, other):
         if isinstance(other, AbstractLinearOperator):
             return op_plus_op(self, other)
+        if _is_matrix(other):
+            return op_plus_op(self, _as_op(other))               # op + M                            operations.jl:219
         if isinstance(other, (int, float, complex, np.number)):
             from .special_operators import opOnes
             return op_plus_op(self, op_times_scalar(opOnes(self.nrow, self.ncol, like=self), other))  # :222
         return NotImplemented
 
     def __radd__(self, other):
+        if _is_matrix(other):
+            return op_plus_op(_as_op(other), self)               # M + op                            operations.jl:218
         if isinstance(other, (int, float, complex, np.number)):
             from .special_operators import opOnes
             return op_plus_op(op_times_scalar(opOnes(self.nrow, self.ncol, like=self), other), self)  # :223
@@ -150,11 +183,15 @@ class AbstractLinearOperator:
     def __sub__(self, other):
         if isinstance(other, AbstractLinearOperator):
             return op_plus_op(self, neg(other))                                                     # :226
+        if _is_matrix(other):
+            return op_plus_op(self, neg(_as_op(other)))                                             # :230
         if isinstance(other, (int, float, complex, np.number)):
             return self + (-other)                                                                   # :233
         return NotImplemented
 
     def __rsub__(self, other):
+        if _is_matrix(other):
+            return op_plus_op(_as_op(other), neg(self))                                             # :229
         if isinstance(other, (int, float, complex, np.number)):
             return other + neg(self)                                                                 # :234
         return NotImplemented
@@ -184,7 +221,15 @@ class AbstractLinearOperator:
 
 class LinearOperator(AbstractLinearOperator):
     """LinearOperator{T,S}(nrow, ncol, symmetric, hermitian, prod!, tprod!, ctprod!) -- src/abstract.jl:46-143,
-    src/constructors.jl:99-111.  Closures are `(res, v, α, β)`; `(res, v)` closures are emulated (prod3!)."""
+    src/constructors.jl:99-111.  Closures are `(res, v, α, β)`; `(res, v)` closures are emulated (prod3!).
+    `LinearOperator(M; symmetric, hermitian)` with a matrix M (src/constructors.jl:15-29) builds the dense-matrix leaf
+    (constructors.DenseMatrixOperator)."""
+
+    def __new__(cls, *args, **kw):
+        if cls is LinearOperator and args and _is_matrix(args[0]):
+            from .constructors import DenseMatrixOperator
+            return object.__new__(DenseMatrixOperator)
+        return object.__new__(cls)
 
     def __init__(self, T, nrow, ncol, symmetric, hermitian, prod_, tprod_=None, ctprod_=None, S=None):
         self.eltype = T

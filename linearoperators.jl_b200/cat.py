@@ -1,6 +1,6 @@
 """hcat / vcat / hvcat of operators -- mirror of src/cat.jl.  Blocks work on views of the caller's vectors."""
 from ._lib import LinearOperatorException
-from .abstract import (LinearOperator, adjoint, eltype, mul_, promote_storage, size, storage_type, transpose)
+from .abstract import (LinearOperator, _as_op, adjoint, eltype, mul_, promote_storage, size, storage_type, transpose)
 
 
 def _hcat_prod_(res, A, B, Ancol, nV, v, alpha, beta):
@@ -30,10 +30,10 @@ def _hcat2(A, B):
 
 
 def hcat(*ops):
-    """[A B ...]  (src/cat.jl:53-59)"""
-    op = ops[0]
+    """[A B ...]  (src/cat.jl:53-59); matrices are promoted with LinearOperator(M) (:3-5)"""
+    op = _as_op(ops[0])
     for o in ops[1:]:
-        op = _hcat2(op, o)
+        op = _hcat2(op, _as_op(o))
     return op
 
 
@@ -64,10 +64,10 @@ def _vcat2(A, B):
 
 
 def vcat(*ops):
-    """[A; B; ...]  (src/cat.jl:111-117)"""
-    op = ops[0]
+    """[A; B; ...]  (src/cat.jl:111-117); matrices are promoted with LinearOperator(M) (:61-63)"""
+    op = _as_op(ops[0])
     for o in ops[1:]:
-        op = _vcat2(op, o)
+        op = _vcat2(op, _as_op(o))
     return op
 
 

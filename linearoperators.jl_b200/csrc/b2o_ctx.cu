@@ -95,6 +95,8 @@ extern "C" int b2o_ctx_set_option(b2o_ctx *c, const char *key, int64_t value) {
     c->host_chunks = (int)value;
   } else if (!strcmp(key, "graph_jit")) {
     c->graph_jit = value != 0;
+  } else if (!strcmp(key, "dense_scalar")) {
+    c->dense_scalar = value != 0;
   } else if (!strcmp(key, "graph_blocks")) {
     if (value < 1 || value > 4) B2O_FAIL(B2O_EARG, "graph_blocks must be 1..4");
     c->graph_blocks = (int)value;

@@ -34,6 +34,10 @@ void b2o_set_error(const char *fmt, ...);
     if (_s != B2O_OK) return _s; \
   } while (0)
 
+// kernel launch spelled as a macro so that tests/emu can run the same launch logic under the host SIMT emulator
+#define B2O_STREAM_T cudaStream_t
+#define B2O_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+
 // ------------------------------------------------------------------ context
 constexpr int B2O_MAX_COLS = 128;      // column streams one launch can address
 constexpr int B2O_MAX_GRID = 1024;     // upper bound on persistent grid
@@ -64,6 +68,7 @@ struct b2o_ctx_s {
   int kron_debug = 0;    // record a %globaltimer timeline of CTA 0 of the kron kernel into d_dots[448..464)
   int graph_jit = 1;     // fused trees: use the NVRTC-specialised kernel when NVRTC + driver are present (else the interpreter)
   int graph_blocks = 3;  // resident CTAs per SM the fused-graph kernel is compiled for (occupancy hides the dispatch latency)
+  int dense_scalar = 0;  // dense-matrix leaf: force the scalar (unvectorised) kernels (testing)
   // accounting
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -236,7 +236,10 @@ def getindex(op, rows, cols):
 
 def BlockDiagonalOperator(*ops, S=None):
     """BlockDiagonalOperator(M1, ..., Mn) (src/special-operators.jl:249-294): block k maps the k-th slab of x
-    to the k-th slab of y; slabs are views, no copies."""
+    to the k-th slab of y; slabs are views, no copies.  Blocks may be matrices (the reference calls `mul!` on them
+    directly, :258-267; here they become LinearOperator(M) leaves) -- test/gpu/nvidia.jl:8-15."""
+    from .abstract import _as_op
+    ops = tuple(_as_op(op) for op in ops)
     nrow = ncol = 0
     for op in ops:
         m, n = size(op)

@@ -639,6 +639,39 @@ void orc_kron(double *res, const double *A, int64_t m, int64_t n, const double *
   free(Y);
 }
 
+/* ---- LinearOperator(M) for a dense matrix: src/constructors.jl:25-27 ----
+ * prod!   = mul!(res, M, v, α, β)              trans = 0   res[m] = α M v + β res
+ * tprod!  = mul!(res, transpose(M), u, α, β)   trans = 1   res[n] = α Mᵀ u + β res   (ctprod! ≡ tprod! for real T)
+ * M is column-major m×n with leading dimension lda.  BLAS gemv in the reference (summation order unspecified): the inner
+ * product is taken in long double here; `res` is not read when β == 0 (BLAS semantics). */
+void orc_gemv(double *res, const double *M, int64_t m, int64_t n, int64_t lda, const double *v, double alpha, double beta,
+              int trans) {
+  int64_t nout = trans ? n : m, nin = trans ? m : n;
+  for (int64_t i = 0; i < nout; ++i) {
+    long double acc = 0.0L;
+    for (int64_t j = 0; j < nin; ++j) {
+      double mij = trans ? M[j + i * lda] : M[i + j * lda];
+      acc += (long double)mij * (long double)v[j];
+    }
+    double t = alpha * (double)acc;
+    res[i] = (beta == 0.0) ? t : t + beta * res[i];
+  }
+}
+/* Float32 storage (test/gpu/nvidia.jl:8-15 uses CUDA.rand -> Float32): same, the result rounded to Float32 once */
+void orc_gemv_f32(float *res, const float *M, int64_t m, int64_t n, int64_t lda, const float *v, float alpha, float beta,
+                  int trans) {
+  int64_t nout = trans ? n : m, nin = trans ? m : n;
+  for (int64_t i = 0; i < nout; ++i) {
+    long double acc = 0.0L;
+    for (int64_t j = 0; j < nin; ++j) {
+      float mij = trans ? M[j + i * lda] : M[i + j * lda];
+      acc += (long double)mij * (long double)v[j];
+    }
+    double t = (double)alpha * (double)acc;
+    res[i] = (float)((beta == 0.0f) ? t : t + (double)beta * (double)res[i]);
+  }
+}
+
 uint16_t orc_f32_to_bf16(float f) {
   uint32_t u;
   memcpy(&u, &f, 4);

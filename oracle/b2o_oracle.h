@@ -94,6 +94,13 @@ int orc_diagqn_push(int kind, double *d, const double *s, const double *y, int64
 void orc_kron(double *res, const double *A, int64_t m, int64_t n, const double *B, int64_t p, int64_t q,
               const double *x, double alpha, double beta, int trans);
 
+/* LinearOperator(M), dense column-major M (m×n, leading dimension lda): mul!(res, M, v, α, β) / transpose(M) --
+ * src/constructors.jl:25-27.  trans: 0 prod!, 1 tprod!/ctprod! */
+void orc_gemv(double *res, const double *M, int64_t m, int64_t n, int64_t lda, const double *v, double alpha, double beta,
+              int trans);
+void orc_gemv_f32(float *res, const float *M, int64_t m, int64_t n, int64_t lda, const float *v, float alpha, float beta,
+                  int trans);
+
 /* bf16 helpers used by the kron parity test (round-to-nearest-even) */
 uint16_t orc_f32_to_bf16(float f);
 float orc_bf16_to_f32(uint16_t h);

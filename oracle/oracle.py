@@ -70,6 +70,8 @@ def lib():
             "orc_lsr1_set_insert": (None, [vp, i32]), "orc_lsr1_opnorm_upper_bound": (d, [vp]),
             "orc_diagqn_push": (i32, [i32, vp, vp, vp, i64]),
             "orc_kron": (None, [vp, vp, i64, i64, vp, i64, i64, vp, d, d, i32]),
+            "orc_gemv": (None, [vp, vp, i64, i64, i64, vp, d, d, i32]),
+            "orc_gemv_f32": (None, [vp, vp, i64, i64, i64, vp, ctypes.c_float, ctypes.c_float, i32]),
             "orc_f32_to_bf16": (ctypes.c_uint16, [ctypes.c_float]), "orc_bf16_to_f32": (ctypes.c_float, [ctypes.c_uint16]),
         }
         for name, (res, args) in sig.items():
@@ -152,6 +154,18 @@ def kron_(res, A, B, x, alpha=1.0, beta=0.0, trans=0):
     A = np.asfortranarray(A, dtype=np.float64)
     B = np.asfortranarray(B, dtype=np.float64)
     lib().orc_kron(_p(res), _p(A), A.shape[0], A.shape[1], _p(B), B.shape[0], B.shape[1], _p(x), alpha, beta, trans)
+
+
+def gemv_(res, M, v, alpha=1.0, beta=0.0, trans=0):
+    """LinearOperator(M) closures (src/constructors.jl:25-27): res = α M v + β res (trans=0) or α Mᵀ v + β res (trans=1).
+    M: 2-D float64 or float32 array (any layout; passed column-major); res, v of the same dtype, res updated in place."""
+    dt = np.float32 if M.dtype == np.float32 else np.float64
+    Mf = np.asfortranarray(M, dtype=dt)
+    v = np.ascontiguousarray(v, dtype=dt)
+    assert res.dtype == dt and res.flags.c_contiguous
+    f = lib().orc_gemv_f32 if dt == np.float32 else lib().orc_gemv
+    f(_p(res), _p(Mf), Mf.shape[0], Mf.shape[1], max(1, Mf.shape[0]), _p(v), alpha, beta, int(trans))
+    return res
 
 
 def bf16_round(a):

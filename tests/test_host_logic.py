@@ -199,3 +199,30 @@ def test_storage_promotion(lo):
         a * b
     with pytest.raises(lo.LinearOperatorException, match="cannot be promoted"):
         a + b
+
+
+def test_dense_matrix_layout_mapping(lo):
+    """LinearOperator(M): how a strided 2-D tensor maps onto the column-major matrix of the C ABI (constructors.colmajor_view);
+    checked by addressing: element (i, j) of M must be element (i, j) [or (j, i) when swapped] of the column-major view."""
+    import torch
+    from linearoperators_jl_b200.constructors import colmajor_view
+    base = torch.arange(40 * 30, dtype=torch.float64).reshape(40, 30)
+    views = [base, base.t(), base[3:20, 5:9], base.t()[2:7, 1:30], base[:, 4:5], base[7:8, :], base.t()[:, 3:4],
+             base[:1, :1], base[5:5, :], base[:, 2:2], base.t().contiguous().t()]
+    for M in views:
+        m, n = M.shape
+        flat = torch.as_strided(M, (M.untyped_storage().nbytes() // 8,), (1,), 0)     # the tensor's whole storage
+        (rows, cols, lda), swap = colmajor_view(m, n, *M.stride())
+        assert (rows, cols) == ((n, m) if swap else (m, n)) and lda >= max(1, rows)
+        off = M.storage_offset()
+        for i in range(m):
+            for j in range(n):
+                r, c = (j, i) if swap else (i, j)
+                assert flat[off + r + c * lda] == M[i, j]
+    with pytest.raises(lo.B2OError):
+        colmajor_view(20, 15, 2, 60)
+    with pytest.raises(lo.B2OError):
+        lo.LinearOperator(base)                      # CPU tensor: no CPU fallback
+    # the closure-based constructor is untouched by the matrix overload
+    op = lo.LinearOperator(np.float64, 2, 2, True, True, lambda res, v, a, b: None)
+    assert type(op) is lo.LinearOperator and lo.size(op) == (2, 2)
