@@ -22,7 +22,8 @@ def emu():
     src.append(os.path.join(HERE, "..", "linearoperators.jl_b200", "csrc", "b2o_dense_kernels.cuh"))
     if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in src):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
-        subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-o", SO, src[0]],
+        subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-fvisibility=hidden",
+                        "-Wl,-Bsymbolic", "-o", SO, src[0]],
                        check=True)
     L = ctypes.CDLL(SO)
     vp, i64, i32, d = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double
