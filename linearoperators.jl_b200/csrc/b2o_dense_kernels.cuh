@@ -19,6 +19,7 @@ struct DenseArgs {
   int nsplit;
   double alpha, beta;
   double *part;    // [nsplit][len(res)] when nsplit > 1
+  int tx_log2;     // narrow kernels: log2 of the threads laid along the rows
 };
 
 // 16-byte read-only load that does not allocate in L1 (the matrix is streamed; L2 keeps it when it fits)
@@ -243,6 +244,191 @@ __global__ void __launch_bounds__(DN_THREADS, 2) dense_t_kernel(const __grid_con
   }
 }
 
+// ------------------------------------------------------------------ matrices with few rows (nrow <= 128 quads)
+// With a short leading dimension the one-thread-per-row-quad layout above leaves most of a CTA idle.  The narrow kernels lay
+// the 256 threads out as TX x TY: TX = 2^tx_log2 threads cover the row quads of one column, TY = 256/TX columns are worked
+// on at the same time (for a contiguous matrix a warp then reads one contiguous 512-byte run).
+//
+// res[m] = α M v + β res: the CTA owns the columns [j0, j1) of its split; thread (tx, ty) accumulates its row quad over the
+// columns j0+ty, j0+ty+TY, ...; the TY partial sums per row are added in ty order through shared memory.
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(DN_THREADS, 2) dense_n_narrow_kernel(const __grid_constant__ DenseArgs p) {
+  constexpr int W = VEC ? (int)(16 / sizeof(T)) : 1;
+  __shared__ double red[DN_THREADS * W];                     // [ty][TX * W]
+  const T *__restrict__ M = (const T *)p.M;
+  const T *__restrict__ v = (const T *)p.v;
+  const int TX = 1 << p.tx_log2, TY = DN_THREADS >> p.tx_log2;
+  const int tx = threadIdx.x & (TX - 1), ty = threadIdx.x >> p.tx_log2;
+  const int64_t row0 = (int64_t)tx * W;
+  const int nrows = row0 < p.m ? (int)min((int64_t)W, p.m - row0) : 0;
+  const int64_t j0 = (int64_t)blockIdx.x * p.chunk;
+  const int64_t j1 = min(p.n, j0 + p.chunk);
+  const int64_t mine = (j0 + ty < j1) ? (j1 - j0 - ty + TY - 1) / TY : 0;   // columns of this thread
+  double acc[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) acc[w] = 0.0;
+  if (nrows == W) {
+    const int64_t cstride = (int64_t)TY * p.lda;
+    const T *col = M + row0 + (j0 + ty) * p.lda;
+    const T *vj = v + j0 + ty;
+    const int64_t ngroups = mine / DN_UNROLL;
+    Raw<T, W> cur[DN_UNROLL], nxt[DN_UNROLL];
+    T xc[DN_UNROLL], xn[DN_UNROLL];
+    if (ngroups > 0) {
+#pragma unroll
+      for (int u = 0; u < DN_UNROLL; ++u) nxt[u] = load_raw<T, W>(col + (int64_t)u * cstride);
+#pragma unroll
+      for (int u = 0; u < DN_UNROLL; ++u) xn[u] = __ldg(vj + (int64_t)u * TY);
+    }
+    int64_t k = 0;
+    for (int64_t g = 0; g < ngroups; ++g) {
+#pragma unroll
+      for (int u = 0; u < DN_UNROLL; ++u) {
+        cur[u] = nxt[u];
+        xc[u] = xn[u];
+      }
+      col += (int64_t)DN_UNROLL * cstride;
+      vj += (int64_t)DN_UNROLL * TY;
+      k += DN_UNROLL;
+      if (g + 1 < ngroups) {
+#pragma unroll
+        for (int u = 0; u < DN_UNROLL; ++u) nxt[u] = load_raw<T, W>(col + (int64_t)u * cstride);
+#pragma unroll
+        for (int u = 0; u < DN_UNROLL; ++u) xn[u] = __ldg(vj + (int64_t)u * TY);
+      }
+#pragma unroll
+      for (int u = 0; u < DN_UNROLL; ++u) {
+        double e[W];
+        unpack<T, W>(cur[u], e);
+        const double x = (double)xc[u];
+#pragma unroll
+        for (int w = 0; w < W; ++w) acc[w] = fma(e[w], x, acc[w]);
+      }
+    }
+    for (; k < mine; ++k, col += cstride, vj += TY) {
+      double e[W];
+      unpack<T, W>(load_raw<T, W>(col), e);
+      const double x = (double)__ldg(vj);
+#pragma unroll
+      for (int w = 0; w < W; ++w) acc[w] = fma(e[w], x, acc[w]);
+    }
+  } else if (nrows > 0) {
+    // ragged last row quad (m not a multiple of W)
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      if (w < nrows) {
+        double s = 0.0;
+        for (int64_t j = j0 + ty; j < j1; j += TY) s = fma((double)__ldg(M + row0 + w + j * p.lda), (double)__ldg(v + j), s);
+        acc[w] = s;
+      }
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < W; ++w) red[(ty * TX + tx) * W + w] = acc[w];
+  __syncthreads();
+  for (int64_t r = threadIdx.x; r < p.m; r += DN_THREADS) {
+    double s = 0.0;
+    for (int y = 0; y < TY; ++y) s += red[(int64_t)y * TX * W + r];
+    if (p.nsplit > 1)
+      p.part[(int64_t)blockIdx.x * p.m + r] = s;
+    else
+      dense_epilogue<T>(p, (T *)p.res, r, s);
+  }
+}
+
+// res[n] = α Mᵀ u + β res with at most 32 row quads: the u quad of a thread stays in registers for the whole kernel, thread
+// (tx, ty) forms its part of the dot for the columns c0+ty, c0+ty+TY, ..., the TX parts are added with a shuffle butterfly
+// (TX <= 32 consecutive lanes) and lane tx == 0 writes the result.  No split: the CTA owns the columns [c0, c1).
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(DN_THREADS, 2) dense_t_narrow_kernel(const __grid_constant__ DenseArgs p) {
+  constexpr int W = VEC ? (int)(16 / sizeof(T)) : 1;
+  const T *__restrict__ M = (const T *)p.M;
+  const T *__restrict__ u = (const T *)p.v;
+  const int TX = 1 << p.tx_log2, TY = DN_THREADS >> p.tx_log2;
+  const int tx = threadIdx.x & (TX - 1), ty = threadIdx.x >> p.tx_log2;
+  const int64_t row0 = (int64_t)tx * W;
+  const int nrows = row0 < p.m ? (int)min((int64_t)W, p.m - row0) : 0;
+  const bool full = nrows == W;
+  double x[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) x[w] = 0.0;
+  if (full) {
+    unpack<T, W>(load_raw<T, W>(u + row0), x);
+  } else {
+#pragma unroll
+    for (int w = 0; w < W; ++w)
+      if (w < nrows) x[w] = (double)__ldg(u + row0 + w);
+  }
+  const int64_t c0 = (int64_t)blockIdx.x * p.chunk;
+  const int64_t c1 = min(p.n, c0 + p.chunk);
+  const int64_t blockcols = (int64_t)TY * DN_UNROLL;          // columns one iteration of the CTA covers
+  const int64_t nfull = (c1 - c0) / blockcols;
+  const int64_t cstride = (int64_t)TY * p.lda;
+  const T *col = M + row0 + (c0 + ty) * p.lda;
+  Raw<T, W> cur[DN_UNROLL], nxt[DN_UNROLL];
+  if (full && nfull > 0) {
+#pragma unroll
+    for (int k = 0; k < DN_UNROLL; ++k) nxt[k] = load_raw<T, W>(col + (int64_t)k * cstride);
+  }
+  int64_t j = c0 + ty;
+  for (int64_t b = 0; b < nfull; ++b) {
+    double s[DN_UNROLL];
+    if (full) {
+#pragma unroll
+      for (int k = 0; k < DN_UNROLL; ++k) cur[k] = nxt[k];
+      col += (int64_t)DN_UNROLL * cstride;
+      if (b + 1 < nfull) {
+#pragma unroll
+        for (int k = 0; k < DN_UNROLL; ++k) nxt[k] = load_raw<T, W>(col + (int64_t)k * cstride);
+      }
+#pragma unroll
+      for (int k = 0; k < DN_UNROLL; ++k) {
+        double e[W];
+        unpack<T, W>(cur[k], e);
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) t = fma(e[w], x[w], t);
+        s[k] = t;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < DN_UNROLL; ++k) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < W; ++w)
+          if (w < nrows) t = fma((double)__ldg(M + row0 + w + (j + (int64_t)k * TY) * p.lda), x[w], t);
+        s[k] = t;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < DN_UNROLL; ++k) {
+      double t = s[k];
+      for (int o = TX >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (tx == 0) dense_epilogue<T>(p, (T *)p.res, j + (int64_t)k * TY, t);
+    }
+    j += blockcols;
+  }
+  // remaining (< TY * DN_UNROLL) columns, TY at a time; the trip count is uniform across the CTA (shuffles stay convergent)
+  for (int64_t jb = c0 + nfull * blockcols; jb < c1; jb += TY) {
+    const int64_t jj = jb + ty;
+    double t = 0.0;
+    if (jj < c1) {
+      if (full) {
+        double e[W];
+        unpack<T, W>(load_raw<T, W>(M + row0 + jj * p.lda), e);
+#pragma unroll
+        for (int w = 0; w < W; ++w) t = fma(e[w], x[w], t);
+      } else {
+#pragma unroll
+        for (int w = 0; w < W; ++w)
+          if (w < nrows) t = fma((double)__ldg(M + row0 + w + jj * p.lda), x[w], t);
+      }
+    }
+    for (int o = TX >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (tx == 0 && jj < c1) dense_epilogue<T>(p, (T *)p.res, jj, t);
+  }
+}
+
 // ------------------------------------------------------------------ fixed-order sum of the splits + epilogue
 template <typename T>
 __global__ void __launch_bounds__(256) dense_finish_kernel(const __grid_constant__ DenseArgs p, int64_t len) {
@@ -259,12 +445,29 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 struct DensePlan {
   int64_t gx = 0, chunk = 0;
   int nsplit = 1;
+  int narrow = 0;    // 1: the narrow kernels (few row quads)
+  int tx_log2 = 0;
 };
+constexpr int64_t DENSE_NARROW_N_QUADS = 128;   // narrow N kernel: at least 2 columns in flight per CTA sweep
+constexpr int64_t DENSE_NARROW_T_QUADS = 32;    // narrow T kernel: the row reduction stays inside one warp
+
 // Split so that ~4 CTAs per SM exist whenever the matrix is big enough; never below DENSE_MIN_COLS columns /
 // DENSE_MIN_ROWITERS row sweeps per split (keeps the partial-sum traffic under a few % of the matrix bytes).
 static DensePlan dense_plan(int num_sms, int trans, int64_t m, int64_t n, int W) {
   DensePlan pl;
   const int64_t target = 4 * (int64_t)num_sms;
+  const int64_t quads = ceil_div64(m, W);
+  if (quads <= (trans ? DENSE_NARROW_T_QUADS : DENSE_NARROW_N_QUADS)) {
+    pl.narrow = 1;
+    while (((int64_t)1 << pl.tx_log2) < quads) ++pl.tx_log2;
+    const int64_t blockcols = (int64_t)(DN_THREADS >> pl.tx_log2) * DN_UNROLL;   // columns per CTA iteration
+    // whole iterations per CTA, at least two of them, ~target CTAs when there are enough columns
+    pl.chunk = std::max<int64_t>(2 * blockcols, ceil_div64(ceil_div64(n, target), blockcols) * blockcols);
+    if (!trans && ceil_div64(n, pl.chunk) > 1024) pl.chunk = ceil_div64(ceil_div64(n, 1024), blockcols) * blockcols;
+    pl.gx = std::max<int64_t>(1, ceil_div64(n, pl.chunk));
+    pl.nsplit = trans ? 1 : (int)pl.gx;           // N: every CTA is a column split; T: no reduction across CTAs
+    return pl;
+  }
   if (!trans) {
     pl.gx = std::max<int64_t>(1, ceil_div64(m, (int64_t)DN_THREADS * W));
     int64_t s = std::max<int64_t>(1, std::min<int64_t>(ceil_div64(target, pl.gx), n / DENSE_MIN_COLS));
@@ -281,7 +484,6 @@ static DensePlan dense_plan(int num_sms, int trans, int64_t m, int64_t n, int W)
   }
   return pl;
 }
-
 
 // partial-sum workspace (doubles) for the worst case over {N, T} x {vectorised, scalar} products of an m x n matrix
 static inline size_t dense_workspace_elems(int num_sms, int Wv, int64_t m, int64_t n) {
@@ -321,9 +523,15 @@ static int dense_run_impl(int num_sms, B2O_STREAM_T stream, int64_t *launches, c
   a.alpha = alpha;
   a.beta = beta;
   a.part = part;
-  const dim3 grid((unsigned)pl.gx, (unsigned)pl.nsplit);
-  void (*kern)(const DenseArgs) = !trans ? (vec ? dense_n_kernel<T, true> : dense_n_kernel<T, false>)
-                                         : (vec ? dense_t_kernel<T, true> : dense_t_kernel<T, false>);
+  a.tx_log2 = pl.tx_log2;
+  const dim3 grid = pl.narrow ? dim3((unsigned)pl.gx) : dim3((unsigned)pl.gx, (unsigned)pl.nsplit);
+  void (*kern)(const DenseArgs);
+  if (pl.narrow)
+    kern = !trans ? (vec ? dense_n_narrow_kernel<T, true> : dense_n_narrow_kernel<T, false>)
+                  : (vec ? dense_t_narrow_kernel<T, true> : dense_t_narrow_kernel<T, false>);
+  else
+    kern = !trans ? (vec ? dense_n_kernel<T, true> : dense_n_kernel<T, false>)
+                  : (vec ? dense_t_kernel<T, true> : dense_t_kernel<T, false>);
   B2O_LAUNCH(kern, grid, dim3(DN_THREADS), 0, stream, a);
   ++*launches;
   B2O_CUDA(cudaGetLastError());

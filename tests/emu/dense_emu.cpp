@@ -27,10 +27,13 @@ EMU_API int emu_dense_apply(int dtype, int trans, int64_t m, int64_t n, int64_t 
                                force_scalar);
 }
 
-EMU_API void emu_dense_plan(int num_sms, int trans, int64_t m, int64_t n, int W, int64_t *gx, int64_t *chunk, int *nsplit) {
+EMU_API void emu_dense_plan(int num_sms, int trans, int64_t m, int64_t n, int W, int64_t *gx, int64_t *chunk, int *nsplit,
+                            int *narrow, int *tx_log2) {
   const DensePlan pl = dense_plan(num_sms, trans, m, n, W);
   *gx = pl.gx;
   *chunk = pl.chunk;
   *nsplit = pl.nsplit;
+  *narrow = pl.narrow;
+  *tx_log2 = pl.tx_log2;
 }
 }

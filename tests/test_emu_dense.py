@@ -22,7 +22,7 @@ def emu():
     src.append(os.path.join(HERE, "..", "linearoperators.jl_b200", "csrc", "b2o_dense_kernels.cuh"))
     if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in src):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
-        subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-fvisibility=hidden",
+        subprocess.run(["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-fvisibility=hidden",
                         "-Wl,-Bsymbolic", "-o", SO, src[0]],
                        check=True)
     L = ctypes.CDLL(SO)
@@ -30,7 +30,8 @@ def emu():
     L.emu_dense_apply.restype = i32
     L.emu_dense_apply.argtypes = [i32, i32, i64, i64, i64, vp, vp, vp, d, d, i32, i32, ctypes.POINTER(i64)]
     L.emu_dense_plan.restype = None
-    L.emu_dense_plan.argtypes = [i32, i32, i64, i64, i32, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i32)]
+    L.emu_dense_plan.argtypes = [i32, i32, i64, i64, i32, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i32),
+                                 ctypes.POINTER(i32), ctypes.POINTER(i32)]
     L.emu_last_error.restype = ctypes.c_char_p
     return L
 
@@ -69,7 +70,7 @@ def _run(emu, orc, dtype, trans, m, n, lda=None, alpha=1.0, beta=0.0, moff=0, vo
 
 SHAPES = [(5, 5), (10, 10), (20, 20),                 # the reference's GPU test blocks (test/gpu/nvidia.jl:8-10)
           (1, 1), (1, 9), (9, 1), (10, 6),            # test/test_linop.jl:2 (nrow, ncol) = (10, 6)
-          (515, 70), (70, 1101), (2051, 13), (3, 2500), (1030, 24), (1283, 67)]
+          (515, 70), (70, 601), (2051, 13), (3, 900), (1030, 24), (1283, 67)]
 
 
 @pytest.mark.parametrize("dtype", [F64, F32])
@@ -93,6 +94,16 @@ def test_dense_kernels_layout_variants(emu, orc, dtype, trans):
     _run(emu, orc, dtype, trans, 4 * W * 256 + W - 1, 9, seed=6)              # ragged last rows of a vectorised launch
     _run(emu, orc, dtype, trans, 300, 8 * 5, seed=7)                          # only full 8-column groups
     _run(emu, orc, dtype, trans, 300, 8 * 5 + 3, seed=8)                      # + one partial column group
+    # narrow kernels (few rows): ragged last row quad, sub-matrix views, scalar variants, many CTA iterations
+    # (every emulated shuffle is two barriers of 32 OS threads, so the T cases are kept smaller)
+    shapes = ((7, 700), (33, 1300), (2 * W * 16 - 1, 517), (W * 32, 64), (W * 128 - 1, 130), (1, 3000))
+    for k, (mm, nn) in enumerate(shapes):
+        nn = nn if not trans else max(40, nn // 6)
+        _run(emu, orc, dtype, trans, mm, nn, num_sms=1, seed=20 + k)
+        _run(emu, orc, dtype, trans, mm, nn, lda=mm + 3 * W, alpha=1.5, beta=-2.0, num_sms=2, seed=30 + k)
+        _run(emu, orc, dtype, trans, mm, nn, lda=mm + 1, moff=1, num_sms=1, seed=40 + k)
+        if k % 2 == 0:
+            _run(emu, orc, dtype, trans, mm, nn, force_scalar=1, num_sms=1, seed=50 + k)
 
 
 @pytest.mark.parametrize("dtype", [F64, F32])
@@ -116,10 +127,12 @@ def test_dense_kernels_empty_shapes(emu, orc, dtype):
 
 
 def test_dense_plan_invariants(emu):
-    """the split plan covers every column/row exactly once, keeps T-splits on 16-byte boundaries and fits the CUDA grid limits"""
+    """the split plan covers every column/row exactly once, keeps T-splits on 16-byte boundaries, fits the CUDA grid limits,
+    and matrices with few rows go to the narrow kernels with enough row threads"""
     gx, chunk, ns = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int()
-    rng = np.random.default_rng(0)
-    dims = [0, 1, 2, 7, 8, 9, 63, 64, 65, 255, 256, 257, 1000, 4096, 10**5, 10**6, 10**8]
+    narrow, txl = ctypes.c_int(), ctypes.c_int()
+    dims = [0, 1, 2, 7, 8, 9, 63, 64, 65, 127, 128, 129, 255, 256, 257, 511, 512, 513, 1000, 4096, 10**5, 10**6, 10**8]
+    seen = set()
     for sms in (1, 4, 148):
         for W in (1, 2, 4):
             for trans in (0, 1):
@@ -127,15 +140,27 @@ def test_dense_plan_invariants(emu):
                     for n in dims:
                         if m * n > 10**13:
                             continue
-                        emu.emu_dense_plan(sms, trans, m, n, W, ctypes.byref(gx), ctypes.byref(chunk), ctypes.byref(ns))
+                        emu.emu_dense_plan(sms, trans, m, n, W, ctypes.byref(gx), ctypes.byref(chunk), ctypes.byref(ns),
+                                           ctypes.byref(narrow), ctypes.byref(txl))
+                        key = (sms, W, trans, m, n)
+                        assert ns.value >= 1 and chunk.value >= 1 and gx.value >= 1, key
+                        assert ns.value <= 1024 and gx.value < 2**31, key
+                        seen.add((trans, narrow.value))
+                        if narrow.value:
+                            TX = 1 << txl.value
+                            assert TX * W >= m and TX <= (32 if trans else 128), key      # every row has a thread
+                            assert (m + W - 1) // W <= (32 if trans else 128), key
+                            assert gx.value * chunk.value >= n, key                      # the CTAs cover the columns
+                            assert (gx.value - 1) * chunk.value < max(n, 1), key         # no empty CTA
+                            assert chunk.value % ((256 // TX) * 8) == 0, key             # whole CTA iterations
+                            assert ns.value == (1 if trans else gx.value), key
+                            continue
                         length = m if trans else n                     # the dimension that is split
-                        assert ns.value >= 1 and chunk.value >= 1 and gx.value >= 1
-                        assert ns.value * chunk.value >= length, (sms, W, trans, m, n)
-                        assert (ns.value - 1) * chunk.value < max(length, 1), (sms, W, trans, m, n)   # no empty split
-                        assert ns.value <= 1024
+                        assert ns.value * chunk.value >= length, key
+                        assert (ns.value - 1) * chunk.value < max(length, 1), key   # no empty split
                         if trans:
-                            assert chunk.value % (256 * W) == 0
-                            assert gx.value * 8 >= n
+                            assert chunk.value % (256 * W) == 0, key
+                            assert gx.value * 8 >= n, key
                         else:
-                            assert gx.value * 256 * W >= m
-    assert rng is not None
+                            assert gx.value * 256 * W >= m, key
+    assert seen == {(0, 0), (0, 1), (1, 0), (1, 1)}

@@ -54,6 +54,36 @@ def main():
     big = "--small" not in sys.argv
     n = 10**8 if big else 10**6
     flush = torch.empty(256 * 2**20 // 8, dtype=torch.float64, device="cuda")
+    if only == ["dense"]:
+        # LinearOperator(M) (src/constructors.jl:15-29): matrix-vector kernels, matrix >> L2 so no flush is needed for the
+        # large cases; the small ones (test/gpu/nvidia.jl block sizes) are launch-latency bound and flushed
+        for dtype in (torch.float64, torch.float32):
+            E = 8 if dtype == torch.float64 else 4
+            for (m, k) in ((32768, 32768), (8192, 131072), (1 << 22, 32), (32, 1 << 22), (20, 20)):
+                A = (torch.rand((k, m), dtype=dtype, device="cuda") * 2 - 1).t()           # column-major m x k
+                op = lo.LinearOperator(A)
+                v = torch.rand(k, dtype=dtype, device="cuda")
+                u = torch.rand(m, dtype=dtype, device="cuda")
+                r, rt = torch.empty(m, dtype=dtype, device="cuda"), torch.empty(k, dtype=dtype, device="cuda")
+                fl = flush if m * k * E < 2**28 else None
+                l0 = ctx.launch_count()
+                lo.mul_(r, op, v)
+                nl = ctx.launch_count() - l0
+                ms = timeit(lambda: lo.mul_(r, op, v), 20, flush=fl)
+                line("dense N %dx%d %s" % (m, k, str(dtype).replace("torch.", "")), ms, op.apply_bytes(False), launches=nl)
+                l0 = ctx.launch_count()
+                lo.mul_(rt, lo.transpose(op), u)
+                nl = ctx.launch_count() - l0
+                ms = timeit(lambda: lo.mul_(rt, lo.transpose(op), u), 20, flush=fl)
+                line("dense T %dx%d %s" % (m, k, str(dtype).replace("torch.", "")), ms, op.apply_bytes(True), launches=nl)
+                if m * k * E >= 2**30:                                                   # library GEMV beside it (cuBLAS via torch.mv)
+                    ms = timeit(lambda: torch.mv(A, v, out=r), 20)
+                    line("cublas gemv N %dx%d %s (torch.mv, for comparison)" % (m, k, str(dtype).replace("torch.", "")), ms, op.apply_bytes(False))
+                    ms = timeit(lambda: torch.mv(A.t(), u, out=rt), 20)
+                    line("cublas gemv T %dx%d %s (torch.mv, for comparison)" % (m, k, str(dtype).replace("torch.", "")), ms, op.apply_bytes(True))
+                del A, op, v, u, r, rt
+                torch.cuda.empty_cache()
+        return
     if only == ["fwdc"]:
         v, res = ctx.uniform(n, 7), ctx.empty(n)
         m = 10
