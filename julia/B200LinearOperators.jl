@@ -56,6 +56,26 @@ end
 # opEye / opOnes / opZeros / opRestriction / opExtension follow the same pattern with
 # b2o_eye_apply / b2o_ones_apply / b2o_zeros_apply / b2o_index_create + b2o_restrict_apply / b2o_extend_apply.
 
+# ---- LinearOperator(M) for a dense CuMatrix (src/constructors.jl:15-29): Float64 and Float32 ------------------
+# The closures alias M like the reference's; the handle only owns the partial-sum workspace of split products.
+const B2O_DTYPE = Dict(Float64 => Cint(0), Float32 => Cint(1))
+function B200DenseOperator(M::CuMatrix{T}; symmetric = false, hermitian = false, c = ctx()) where {T <: Union{Float64, Float32}}
+  nrow, ncol = size(M)
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:b2o_dense_create, libb2o), Cint, (Ptr{Cvoid}, Cint, CuPtr{Cvoid}, Int64, Int64, Int64, Ptr{Ptr{Cvoid}}),
+    c.handle, B2O_DTYPE[T], M, nrow, ncol, max(1, stride(M, 2)), h))
+  handle = h[]
+  run(trans) = (res, v, α, β) -> check(ccall((:b2o_dense_apply, libb2o), Cint,
+    (Ptr{Cvoid}, Cint, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, Int64, Cdouble, Cdouble),
+    handle, trans, res, length(res), v, length(v), α, β))
+  op = LinearOperator{T, CuVector{T}}(nrow, ncol, symmetric, hermitian, run(Cint(0)), run(Cint(1)), run(Cint(1)))
+  finalizer(_ -> ccall((:b2o_dense_destroy, libb2o), Cint, (Ptr{Cvoid},), handle), op)
+  return op
+end
+# BlockDiagonalOperator(A, B, C) of CuMatrix blocks (test/gpu/nvidia.jl:8-15): wrap the blocks first, the reference's
+# own block loop (src/special-operators.jl:258-267) then calls the closures above on the slab views.
+B200BlockDiagonalOperator(Ms::CuMatrix...; kw...) = BlockDiagonalOperator((B200DenseOperator(M; kw...) for M in Ms)...)
+
 # ---- quasi-Newton operators ----------------------------------------------------------------------------------
 mutable struct B200LBFGSOperator{T, F} <: AbstractQuasiNewtonOperator{T}
   const nrow::Int

@@ -363,3 +363,44 @@ def test_golden_vectors(orc):
     for name, val in fresh.items():
         ref = np.array(G["cases"][name])
         assert np.allclose(val, ref, rtol=1e-14, atol=0), name
+
+
+# ---------------------------------------------------------------- LinearOperator(Matrix) -- test/test_linop.jl:41-75, :101-124
+def test_dense_matrix_operator_predicates(orc):
+    """oracle gemv (the closures of LinearOperator(M), src/constructors.jl:25-27) against dense algebra: A*v, transpose(A)*u,
+    A'*u, Matrix(op) == A (column by column with unit vectors, src/abstract.jl:282-292), matrix right-hand sides hcat(v, -2v),
+    5-arg α/β form, β = 0 never reads res; Float32 storage as in test/gpu/nvidia.jl:8-15."""
+    nrow, ncol = 10, 6                                                # test/test_linop.jl:2
+    rng = np.random.default_rng(11)
+    for dt, rtol in ((np.float64, 1e-15), (np.float32, 1e-6)):
+        A = np.asfortranarray(rng.uniform(-1, 1, (nrow, ncol)).astype(dt))
+        v, u = rng.uniform(-1, 1, ncol).astype(dt), rng.uniform(-1, 1, nrow).astype(dt)
+        res = np.full(nrow, np.nan, dtype=dt)
+        orc.gemv_(res, A, v)
+        assert np.linalg.norm(res - A @ v) <= 10 * rtol * np.linalg.norm(v) * np.sqrt(ncol)
+        rt = np.full(ncol, np.nan, dtype=dt)
+        orc.gemv_(rt, A, u, trans=1)
+        assert np.linalg.norm(rt - A.T @ u) <= 10 * rtol * np.linalg.norm(u) * np.sqrt(nrow)
+        full = np.empty((nrow, ncol), dtype=dt)                       # Matrix(op): op * e_i
+        for i in range(ncol):
+            e = np.zeros(ncol, dtype=dt)
+            e[i] = 1
+            col = np.empty(nrow, dtype=dt)
+            orc.gemv_(col, A, e)
+            full[:, i] = col
+        assert np.array_equal(full, A)                                # norm(A - Matrix(op)) <= ϵ * norm(A), exactly 0 here
+        mv = np.stack([v, -2 * v], axis=1)                            # mul!(res_mat, op, hcat(v, -2v))
+        out = np.empty((nrow, 2), dtype=dt)
+        for j in range(2):
+            c = np.empty(nrow, dtype=dt)
+            orc.gemv_(c, A, np.ascontiguousarray(mv[:, j]))
+            out[:, j] = c
+        assert np.linalg.norm(out - A @ mv) <= 10 * rtol * np.linalg.norm(mv) * np.sqrt(ncol)
+        r0 = rng.uniform(-1, 1, nrow).astype(dt)
+        r5 = r0.copy()
+        orc.gemv_(r5, A, v, 2.0, -0.5)
+        assert np.linalg.norm(r5 - (2 * (A @ v) - 0.5 * r0)) <= 20 * rtol * (np.linalg.norm(v) * np.sqrt(ncol) + np.linalg.norm(r0))
+        sub = A[2:9, 1:5]                                             # a view with leading dimension > nrow is passed column-major
+        rs = np.empty(7, dtype=dt)
+        orc.gemv_(rs, sub, v[1:5])
+        assert np.linalg.norm(rs - sub @ v[1:5]) <= 10 * rtol * np.linalg.norm(v) * 2
