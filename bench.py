@@ -109,6 +109,11 @@ def cpu_reference(n_cpu, mem, steps, warmup, inverse=False):
         if best_dt is None or min(dts) < best_dt:
             best_t, best_dt = t, min(dts)
     threads = best_t
+    # SURVEY §8d figure (i): reference-faithful single thread (Julia broadcasts and the default `dot` of one BLAS thread), one apply
+    oracle.set_mode(False, 1)
+    t0 = time.perf_counter()
+    op.apply(x, res=res)
+    dt1 = time.perf_counter() - t0
     oracle.set_mode(False, threads)
     if best_dt * (steps + warmup) > 60.0:
         steps, warmup = max(1, int(30.0 / best_dt)), 0
@@ -122,7 +127,9 @@ def cpu_reference(n_cpu, mem, steps, warmup, inverse=False):
     return {"value": alg_bytes(n_cpu, mem, inverse) / dt / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
             "sample": "%s apply at n=%d rows (1/%d of the workload), mem=%d, %d timed applies, %.3f s/apply, %d threads of %d usable CPUs (fastest of a thread-count sweep)" %
                       ("inverse" if inverse else "forward", n_cpu, max(1, round(1e8 / n_cpu)), mem, steps, dt, threads, avail),
-            "applies_per_s": 1.0 / dt, "ms_per_apply": dt * 1e3}
+            "applies_per_s": 1.0 / dt, "ms_per_apply": dt * 1e3,
+            "single_thread": {"value": alg_bytes(n_cpu, mem, inverse) / dt1 / 1e9, "unit": "GB/s", "cores": 1, "ms_per_apply": dt1 * 1e3,
+                              "note": "same restatement on one thread (the reference's broadcasts are single-threaded)"}}
 
 
 def main():
