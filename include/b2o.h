@@ -54,6 +54,7 @@ typedef struct b2o_index_s b2o_index; /* opRestriction / opExtension index set *
 typedef struct b2o_kron_s b2o_kron;   /* kron(A,B) operator (tcgen05 GEMM pair) */
 typedef struct b2o_graph_s b2o_graph; /* static operator tree lowered to one fused launch */
 typedef struct b2o_dense_s b2o_dense; /* LinearOperator(M) for a dense device matrix */
+typedef struct b2o_sparse_s b2o_sparse; /* LinearOperator(M) for a sparse matrix (CSC / CSR) */
 
 /* ---- library / context ------------------------------------------------------------------ */
 int b2o_version(void);
@@ -222,6 +223,22 @@ int b2o_dense_destroy(b2o_dense *d);
 int b2o_dense_apply(b2o_dense *d, int trans, void *res, int64_t res_len, const void *v, int64_t v_len, double alpha, double beta);
 /* algorithmic DRAM bytes of one product (matrix once + vectors), for the roofline */
 int b2o_dense_apply_bytes(b2o_dense *d, int trans, double beta, double *bytes);
+
+/* ---- LinearOperator(M), sparse matrix leaf (src/constructors.jl:15-29 with M::SparseMatrixCSC) --------------- */
+/* fmt 0: CSC, Julia's SparseMatrixCSC fields colptr[n+1], rowval[nnz], nzval[nnz]; fmt 1: CSR (rowptr[m+1], colval[nnz]).
+ * ptr1 / idx1: HOST arrays holding the reference's 1-based values (validated: B2O_EARG when out of range / not monotone);
+ * vals: DEVICE array, B2O_F64 or B2O_F32, borrowed (aliased) for the lifetime of the handle.  The structure is transposed once
+ * here (host, stable counting sort) so that both products are gather-form, atomics-free and bit-reproducible. */
+int b2o_sparse_create(b2o_ctx *ctx, int dtype, int fmt, int64_t m, int64_t n, int64_t nnz, const int64_t *ptr1,
+                      const int64_t *idx1, const void *vals, b2o_sparse **out);
+int b2o_sparse_destroy(b2o_sparse *s);
+/* trans = 0: prod!  mul!(res, M, v, α, β);  trans = 1: tprod!/ctprod!  mul!(res, transpose(M), u, α, β) (real element types).
+ * res is never read when β == 0. */
+int b2o_sparse_apply(b2o_sparse *s, int trans, void *res, int64_t res_len, const void *v, int64_t v_len, double alpha, double beta);
+/* after nzval was changed in place: re-gather the values of the transposed copy (the given orientation is aliased) */
+int b2o_sparse_refresh(b2o_sparse *s);
+/* algorithmic DRAM bytes of one product: nnz*(sizeof(T)+4) + 8*(rows+1) + the vectors */
+int b2o_sparse_apply_bytes(b2o_sparse *s, int trans, double beta, double *bytes);
 
 /* ---- row-partitioned multi-GPU (one process per GPU) ------------------------------------- */
 /* id: 128-byte ncclUniqueId produced on rank 0 by b2o_comm_unique_id and broadcast by the host

@@ -10,7 +10,7 @@ from .abstract import (AbstractLinearOperator, AdjointLinearOperator, ConjugateL
                        has_args5, isallocated5, ishermitian, issymmetric, mul_, nctprod, nprod, ntprod, reset_, size,
                        storage_type, transpose)
 from .cat import hcat, hvcat, vcat  # noqa: F401
-from .constructors import DenseMatrixOperator  # noqa: F401
+from .constructors import DenseMatrixOperator, SparseMatrixOperator  # noqa: F401
 from .context import Context, default_context  # noqa: F401
 from .diagqn import (AbstractDiagonalQuasiNewtonOperator, DiagonalAndrei, DiagonalBFGS, DiagonalPSB, ShiftedOperator,  # noqa: F401
                      SpectralGradient)

@@ -113,8 +113,8 @@ def _is_matrix(x):
 
 def _as_op(x):
     if _is_matrix(x):
-        from .constructors import DenseMatrixOperator
-        return DenseMatrixOperator(x)
+        from .constructors import matrix_operator
+        return matrix_operator(x)
     return x
 
 
@@ -227,8 +227,9 @@ class LinearOperator(AbstractLinearOperator):
 
     def __new__(cls, *args, **kw):
         if cls is LinearOperator and args and _is_matrix(args[0]):
-            from .constructors import DenseMatrixOperator
-            return object.__new__(DenseMatrixOperator)
+            from .constructors import DenseMatrixOperator, SparseMatrixOperator
+            import torch
+            return object.__new__(DenseMatrixOperator if args[0].layout == torch.strided else SparseMatrixOperator)
         return object.__new__(cls)
 
     def __init__(self, T, nrow, ncol, symmetric, hermitian, prod_, tprod_=None, ctprod_=None, S=None):

@@ -104,6 +104,97 @@ class DenseMatrixOperator(LinearOperator):
             pass
 
 
+def _is_sparse(M):
+    import torch
+    return isinstance(M, torch.Tensor) and M.layout in (torch.sparse_csc, torch.sparse_csr)
+
+
+class SparseMatrixOperator(LinearOperator):
+    """LinearOperator(M; symmetric, hermitian) for a sparse matrix -- src/constructors.jl:15-29 with M::SparseMatrixCSC (the
+    docstring :3-5 says "dense or sparse"; test/test_linop.jl:41-75 runs every predicate on both).  M: a torch CUDA tensor
+    with layout sparse_csc (Julia's SparseMatrixCSC: colptr, rowval, nzval) or sparse_csr, float64 or float32.  The index
+    arrays are copied to the host once (the C ABI takes the reference's 1-based arrays and transposes the structure there);
+    the values are ALIASED -- after changing them in place call `refresh()` so the transposed copy follows."""
+
+    def __init__(self, M, symmetric=False, hermitian=False, ctx=None):
+        import torch
+        if not _is_sparse(M):
+            raise _lib.B2OError("LinearOperator(M): sparse matrices must use torch's sparse_csc or sparse_csr layout "
+                                "(got %s); use M.to_sparse_csc()" % getattr(M, "layout", type(M)))
+        if not M.is_cuda:
+            raise _lib.B2OError("LinearOperator(M): M must be a torch CUDA tensor (no CPU fallback)")
+        if M.dim() != 2:
+            raise LinearOperatorException("LinearOperator(M) needs a matrix")
+        self.ctx = ctx or default_context(M.device.index)
+        if self.ctx.device != M.device.index:
+            raise _lib.B2OError("LinearOperator(M): matrix lives on cuda:%d, context on cuda:%d" % (M.device.index, self.ctx.device))
+        nrow, ncol = int(M.shape[0]), int(M.shape[1])
+        if M.layout == torch.sparse_csc:
+            fmt, ptr, idx = 0, M.ccol_indices(), M.row_indices()
+        else:
+            fmt, ptr, idx = 1, M.crow_indices(), M.col_indices()
+        vals = M.values()
+        if not vals.is_contiguous():
+            raise _lib.B2OError("LinearOperator(M): the value array must be contiguous")
+        self.M, self._vals = M, vals                     # aliased, and kept alive for the handle
+        self._code = _dtype_code(vals)
+        ptr1 = (ptr.to("cpu", torch.int64) + 1).contiguous()      # the reference's 1-based arrays
+        idx1 = (idx.to("cpu", torch.int64) + 1).contiguous()
+        nnz = int(vals.numel())
+        self._h = ctypes.c_void_p()
+        _lib.check(self.ctx.lib.b2o_sparse_create(self.ctx.handle, self._code, fmt, nrow, ncol, nnz, ctypes.c_void_p(ptr1.data_ptr()),
+                                                  ctypes.c_void_p(idx1.data_ptr()), ctypes.c_void_p(vals.data_ptr() if nnz else 0),
+                                                  ctypes.byref(self._h)))
+
+        def prod_(res, v, a, b):         # mul!(res, M, v, α, β)                              constructors.jl:25
+            self._run(0, res, v, a, b)
+
+        def tprod_(res, u, a, b):        # mul!(res, transpose(M), u, α, β) (≡ adjoint, real T) constructors.jl:26-27
+            self._run(1, res, u, a, b)
+
+        super().__init__(vals.dtype, nrow, ncol, symmetric, hermitian, prod_, tprod_, tprod_,
+                         S=Storage("cuda", self.ctx.device, dtype=vals.dtype))
+
+    def _vec(self, t, what):
+        import torch
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise _lib.B2OError("%s must be a torch CUDA tensor (no CPU fallback)" % what)
+        if t.dtype != self._vals.dtype:
+            raise _lib.B2OError("%s must be %s like the matrix (got %s)" % (what, self._vals.dtype, t.dtype))
+        if t.dim() != 1 or (t.numel() > 1 and t.stride(0) != 1):
+            raise _lib.B2OError("%s must be a unit-stride 1-D tensor" % what)
+        return ctypes.c_void_p(t.data_ptr())
+
+    def _run(self, trans, res, v, alpha, beta):
+        _lib.check(self.ctx.lib.b2o_sparse_apply(self._h, int(trans), self._vec(res, "res"), res.shape[0], self._vec(v, "v"),
+                                                 v.shape[0], float(alpha), float(beta)))
+
+    def refresh(self):
+        """the values were changed in place: re-gather the transposed copy"""
+        _lib.check(self.ctx.lib.b2o_sparse_refresh(self._h))
+
+    def apply_bytes(self, trans=False, beta=0.0):
+        out = ctypes.c_double()
+        _lib.check(self.ctx.lib.b2o_sparse_apply_bytes(self._h, int(bool(trans)), float(beta), ctypes.byref(out)))
+        return out.value
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self.ctx.handle:
+                self.ctx.lib.b2o_sparse_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def matrix_operator(M, **kw):
+    """LinearOperator(M): dense (strided) or sparse (CSC / CSR) matrix leaf"""
+    import torch
+    if isinstance(M, torch.Tensor) and M.layout != torch.strided:
+        return SparseMatrixOperator(M, **kw)
+    return DenseMatrixOperator(M, **kw)
+
+
 def as_operator(x):
     """the reference's `LinearOperator(M)` promotion of a matrix argument (operations.jl:159-160, cat.jl:3-5)"""
-    return DenseMatrixOperator(x) if is_matrix(x) else x
+    return matrix_operator(x) if is_matrix(x) else x

@@ -672,6 +672,51 @@ void orc_gemv_f32(float *res, const float *M, int64_t m, int64_t n, int64_t lda,
   }
 }
 
+/* ---- LinearOperator(M) for M::SparseMatrixCSC: src/constructors.jl:25-27 -> SparseArrays' mul! ----
+ * SparseArrays is a standard-library dependency (Project.toml:9, compat "1.10", Project.toml:44) and is NOT vendored under
+ * /root/reference; its published algorithm (SparseArrays/src/linalg.jl, `_spmatmul!` and `_At_or_Ac_mul_B!`) is restated:
+ *   prod!  (trans = 0): C = β C (or 0 when β == 0); for col = 1:n, αxj = v[col]*α; for k in nzrange(A, col): C[rowval[k]] += nzval[k]*αxj
+ *   tprod! (trans = 1): for col = 1:n, tmp = Σ_{k in nzrange(A, col)} nzval[k]*u[rowval[k]]; C[col] = α*tmp + β*C[col]
+ * colptr1 / rowval1 hold Julia's 1-based values.  Accurate side: the per-output sums are taken in long double (the
+ * reference's summation order over a row is the storage order; nothing in its tests pins more than √eps). */
+void orc_spmv_csc(double *res, int64_t m, int64_t n, const int64_t *colptr1, const int64_t *rowval1, const double *nzval,
+                  const double *v, double alpha, double beta, int trans) {
+  if (trans) {
+    for (int64_t col = 0; col < n; ++col) {
+      long double tmp = 0.0L;
+      for (int64_t k = colptr1[col] - 1; k < colptr1[col + 1] - 1; ++k) tmp += (long double)nzval[k] * (long double)v[rowval1[k] - 1];
+      double t = alpha * (double)tmp;
+      res[col] = (beta == 0.0) ? t : t + beta * res[col];
+    }
+    return;
+  }
+  long double *acc = (long double *)calloc((size_t)(m > 0 ? m : 1), sizeof(long double));
+  for (int64_t col = 0; col < n; ++col)
+    for (int64_t k = colptr1[col] - 1; k < colptr1[col + 1] - 1; ++k)
+      acc[rowval1[k] - 1] += (long double)nzval[k] * (long double)v[col];
+  for (int64_t i = 0; i < m; ++i) {
+    double t = alpha * (double)acc[i];
+    res[i] = (beta == 0.0) ? t : t + beta * res[i];
+  }
+  free(acc);
+}
+void orc_spmv_csc_f32(float *res, int64_t m, int64_t n, const int64_t *colptr1, const int64_t *rowval1, const float *nzval,
+                      const float *v, float alpha, float beta, int trans) {
+  int64_t nout = trans ? n : m;
+  long double *acc = (long double *)calloc((size_t)(nout > 0 ? nout : 1), sizeof(long double));
+  for (int64_t col = 0; col < n; ++col)
+    for (int64_t k = colptr1[col] - 1; k < colptr1[col + 1] - 1; ++k) {
+      int64_t row = rowval1[k] - 1;
+      if (trans) acc[col] += (long double)nzval[k] * (long double)v[row];
+      else acc[row] += (long double)nzval[k] * (long double)v[col];
+    }
+  for (int64_t i = 0; i < nout; ++i) {
+    double t = (double)alpha * (double)acc[i];
+    res[i] = (float)((beta == 0.0f) ? t : t + (double)beta * (double)res[i]);
+  }
+  free(acc);
+}
+
 uint16_t orc_f32_to_bf16(float f) {
   uint32_t u;
   memcpy(&u, &f, 4);

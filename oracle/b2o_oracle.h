@@ -101,6 +101,13 @@ void orc_gemv(double *res, const double *M, int64_t m, int64_t n, int64_t lda, c
 void orc_gemv_f32(float *res, const float *M, int64_t m, int64_t n, int64_t lda, const float *v, float alpha, float beta,
                   int trans);
 
+/* LinearOperator(M::SparseMatrixCSC): SparseArrays' mul!(res, M, v, α, β) / transpose(M) restated (stdlib dependency,
+ * Project.toml:9,44; not vendored).  1-based colptr / rowval as in Julia.  trans: 0 prod!, 1 tprod!/ctprod! */
+void orc_spmv_csc(double *res, int64_t m, int64_t n, const int64_t *colptr1, const int64_t *rowval1, const double *nzval,
+                  const double *v, double alpha, double beta, int trans);
+void orc_spmv_csc_f32(float *res, int64_t m, int64_t n, const int64_t *colptr1, const int64_t *rowval1, const float *nzval,
+                      const float *v, float alpha, float beta, int trans);
+
 /* bf16 helpers used by the kron parity test (round-to-nearest-even) */
 uint16_t orc_f32_to_bf16(float f);
 float orc_bf16_to_f32(uint16_t h);

@@ -72,6 +72,8 @@ def lib():
             "orc_kron": (None, [vp, vp, i64, i64, vp, i64, i64, vp, d, d, i32]),
             "orc_gemv": (None, [vp, vp, i64, i64, i64, vp, d, d, i32]),
             "orc_gemv_f32": (None, [vp, vp, i64, i64, i64, vp, ctypes.c_float, ctypes.c_float, i32]),
+            "orc_spmv_csc": (None, [vp, i64, i64, vp, vp, vp, vp, d, d, i32]),
+            "orc_spmv_csc_f32": (None, [vp, i64, i64, vp, vp, vp, vp, ctypes.c_float, ctypes.c_float, i32]),
             "orc_f32_to_bf16": (ctypes.c_uint16, [ctypes.c_float]), "orc_bf16_to_f32": (ctypes.c_float, [ctypes.c_uint16]),
         }
         for name, (res, args) in sig.items():
@@ -165,6 +167,20 @@ def gemv_(res, M, v, alpha=1.0, beta=0.0, trans=0):
     assert res.dtype == dt and res.flags.c_contiguous
     f = lib().orc_gemv_f32 if dt == np.float32 else lib().orc_gemv
     f(_p(res), _p(Mf), Mf.shape[0], Mf.shape[1], max(1, Mf.shape[0]), _p(v), alpha, beta, int(trans))
+    return res
+
+
+def spmv_csc_(res, m, n, colptr1, rowval1, nzval, v, alpha=1.0, beta=0.0, trans=0):
+    """LinearOperator(M::SparseMatrixCSC) closures: res = α M v + β res (trans=0) / α Mᵀ v + β res (trans=1).
+    colptr1, rowval1: Julia's 1-based int64 arrays; nzval float64 or float32; res updated in place."""
+    dt = np.float32 if nzval.dtype == np.float32 else np.float64
+    colptr1 = np.ascontiguousarray(colptr1, dtype=np.int64)
+    rowval1 = np.ascontiguousarray(rowval1, dtype=np.int64)
+    nzval = np.ascontiguousarray(nzval, dtype=dt)
+    v = np.ascontiguousarray(v, dtype=dt)
+    assert res.dtype == dt and res.flags.c_contiguous and colptr1.shape[0] == n + 1
+    f = lib().orc_spmv_csc_f32 if dt == np.float32 else lib().orc_spmv_csc
+    f(_p(res), int(m), int(n), _p(colptr1), _p(rowval1), _p(nzval), _p(v), alpha, beta, int(trans))
     return res
 
 

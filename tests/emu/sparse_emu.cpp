@@ -1,0 +1,56 @@
+// sparse_emu.cpp -- host build of csrc/b2o_sparse_kernels.cuh under the SIMT emulator (TEST INFRASTRUCTURE).
+// Mirrors b2o_sparse_create (structure transposition by a stable counting sort) + b2o_sparse_apply of csrc/b2o_sparse.cu:
+// the row kernel, lane-group sizing and launch logic are the product's own code; the transposition is restated here because
+// the product's sits next to its cudaMalloc/cudaMemcpy calls.  Built with hidden visibility + -Bsymbolic (see dense_emu.cpp).
+#include "simt_emu.h"
+namespace emu_sparse {
+#include "../../linearoperators.jl_b200/csrc/b2o_sparse_kernels.cuh"
+}
+using namespace emu_sparse;
+#define EMU_API __attribute__((visibility("default")))
+
+extern "C" {
+EMU_API const char *emu_sparse_last_error() { return emu::last_error.c_str(); }
+
+// fmt 0 CSC / 1 CSR with 1-based host arrays, exactly the arguments of b2o_sparse_create; one product like b2o_sparse_apply
+EMU_API int emu_sparse_apply(int dtype, int fmt, int64_t m, int64_t n, int64_t nnz, const int64_t *ptr1, const int64_t *idx1,
+                             const void *vals, int trans, void *res, const void *v, double alpha, double beta, int num_sms,
+                             int64_t *launches, int *lanes_log2) {
+  const int64_t np = fmt == 0 ? n : m, nd = fmt == 0 ? m : n;
+  std::vector<int64_t> gptr(np + 1), tptr(nd + 1, 0), perm(std::max<int64_t>(nnz, 1));
+  std::vector<int32_t> gidx(std::max<int64_t>(nnz, 1)), tidx(std::max<int64_t>(nnz, 1));
+  for (int64_t j = 0; j <= np; ++j) gptr[j] = ptr1[j] - 1;
+  for (int64_t k = 0; k < nnz; ++k) {
+    gidx[k] = (int32_t)(idx1[k] - 1);
+    tptr[gidx[k] + 1]++;
+  }
+  for (int64_t i = 0; i < nd; ++i) tptr[i + 1] += tptr[i];
+  std::vector<int64_t> fill(tptr.begin(), tptr.end() - 1);
+  for (int64_t j = 0; j < np; ++j)
+    for (int64_t k = gptr[j]; k < gptr[j + 1]; ++k) {
+      const int64_t dst = fill[gidx[k]]++;
+      tidx[dst] = (int32_t)j;
+      perm[dst] = k;
+    }
+  const size_t E = dtype == B2O_F64 ? 8 : 4;
+  std::vector<unsigned char> tval(std::max<int64_t>(nnz, 1) * E);
+  *launches = 0;
+  if (nnz > 0) {   // the product's gather kernel
+    if (dtype == B2O_F64) {
+      void (*k)(double *, const double *, const int64_t *, int64_t) = perm_gather_kernel<double>;
+      B2O_LAUNCH(k, dim3(2), dim3(SP_THREADS), 0, nullptr, (double *)tval.data(), (const double *)vals, perm.data(), nnz);
+    } else {
+      void (*k)(float *, const float *, const int64_t *, int64_t) = perm_gather_kernel<float>;
+      B2O_LAUNCH(k, dim3(2), dim3(SP_THREADS), 0, nullptr, (float *)tval.data(), (const float *)vals, perm.data(), nnz);
+    }
+  }
+  const int given = fmt == 0 ? 1 : 0, o = trans ? 1 : 0;
+  const int64_t *ptr = o == given ? gptr.data() : tptr.data();
+  const int32_t *idx = o == given ? gidx.data() : tidx.data();
+  const void *val = o == given ? vals : (const void *)tval.data();
+  const int64_t out_len = trans ? n : m;
+  *lanes_log2 = spmv_lanes_log2(out_len, nnz);
+  if (dtype == B2O_F64) return spmv_run_impl<double>(num_sms, nullptr, launches, ptr, idx, val, out_len, nnz, res, v, alpha, beta);
+  return spmv_run_impl<float>(num_sms, nullptr, launches, ptr, idx, val, out_len, nnz, res, v, alpha, beta);
+}
+}

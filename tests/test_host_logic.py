@@ -226,3 +226,17 @@ def test_dense_matrix_layout_mapping(lo):
     # the closure-based constructor is untouched by the matrix overload
     op = lo.LinearOperator(np.float64, 2, 2, True, True, lambda res, v, a, b: None)
     assert type(op) is lo.LinearOperator and lo.size(op) == (2, 2)
+
+
+def test_sparse_matrix_leaf_refuses_cpu_and_coo(lo):
+    """LinearOperator(M) with a sparse M dispatches to the sparse leaf (constructors.jl:3-5 "dense or sparse"); there is no CPU
+    fallback and only the compressed layouts (Julia's SparseMatrixCSC, or CSR) are accepted"""
+    import torch
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        S = torch.sparse_csc_tensor(torch.tensor([0, 1, 2]), torch.tensor([0, 1]), torch.tensor([1.0, 2.0]), size=(2, 2))
+        with pytest.raises(lo.B2OError, match="CUDA"):
+            lo.LinearOperator(S)
+        with pytest.raises(lo.B2OError, match="sparse_csc or sparse_csr"):
+            lo.SparseMatrixOperator(S.to_sparse_coo())

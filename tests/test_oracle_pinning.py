@@ -404,3 +404,51 @@ def test_dense_matrix_operator_predicates(orc):
         rs = np.empty(7, dtype=dt)
         orc.gemv_(rs, sub, v[1:5])
         assert np.linalg.norm(rs - sub @ v[1:5]) <= 10 * rtol * np.linalg.norm(v) * 2
+
+
+# ---------------------------------------------------------------- LinearOperator(SparseMatrixCSC) -- test/test_linop.jl:740-766
+def test_sparse_matrix_operator_predicates(orc):
+    """oracle spmv (SparseArrays' mul! restated: the closures of LinearOperator(M::SparseMatrixCSC), src/constructors.jl:25-27)
+    against dense algebra and scipy.sparse (independent): `opA * b == A * b`, transpose, adjoint (test_linop.jl:759-766, exact
+    on integer-valued data), Matrix(op) == A column by column, 5-arg α/β form, β = 0 never reads res, empty columns/rows,
+    the block-diagonal predicate of :740-755 with a sprand(2, 4, 0.5) block."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(21)
+    for dt, rtol in ((np.float64, 1e-15), (np.float32, 1e-6)):
+        for (m, n, dens) in ((10, 10, 0.2), (2, 4, 0.5), (40, 25, 0.1), (7, 300, 0.3), (300, 7, 0.3), (5, 5, 0.0)):
+            A = sp.random(m, n, density=dens, random_state=rng, format="csc").astype(dt)
+            A.sort_indices()
+            cp, rv, nz = A.indptr.astype(np.int64) + 1, A.indices.astype(np.int64) + 1, A.data
+            Ad = A.toarray().astype(np.float64)
+            v, u = rng.uniform(-1, 1, n).astype(dt), rng.uniform(-1, 1, m).astype(dt)
+            res = np.full(m, np.nan, dtype=dt)
+            orc.spmv_csc_(res, m, n, cp, rv, nz, v)
+            assert np.linalg.norm(res - Ad @ v) <= 10 * rtol * max(np.linalg.norm(Ad), 1.0) * np.linalg.norm(v)
+            assert np.linalg.norm(res - A.astype(np.float64) @ v.astype(np.float64)) <= 10 * rtol * max(np.linalg.norm(Ad), 1.0) * np.linalg.norm(v)
+            rt = np.full(n, np.nan, dtype=dt)
+            orc.spmv_csc_(rt, m, n, cp, rv, nz, u, trans=1)
+            assert np.linalg.norm(rt - Ad.T @ u) <= 10 * rtol * max(np.linalg.norm(Ad), 1.0) * np.linalg.norm(u)
+            full = np.empty((m, n), dtype=dt)                      # Matrix(op): op * e_i, exact
+            for i in range(n):
+                e = np.zeros(n, dtype=dt)
+                e[i] = 1
+                col = np.empty(m, dtype=dt)
+                orc.spmv_csc_(col, m, n, cp, rv, nz, e)
+                full[:, i] = col
+            assert np.array_equal(full, A.toarray())
+            r0 = rng.uniform(-1, 1, m).astype(dt)
+            r5 = r0.copy()
+            orc.spmv_csc_(r5, m, n, cp, rv, nz, v, 2.0, -0.5)
+            assert np.linalg.norm(r5 - (2 * (Ad @ v) - 0.5 * r0)) <= 20 * rtol * (max(np.linalg.norm(Ad), 1.0) * np.linalg.norm(v) + np.linalg.norm(r0))
+            t0 = rng.uniform(-1, 1, n).astype(dt)
+            t5 = t0.copy()
+            orc.spmv_csc_(t5, m, n, cp, rv, nz, u, 2.0, -0.5, trans=1)
+            assert np.linalg.norm(t5 - (2 * (Ad.T @ u) - 0.5 * t0)) <= 20 * rtol * (max(np.linalg.norm(Ad), 1.0) * np.linalg.norm(u) + np.linalg.norm(t0))
+    # issue #139 (test_linop.jl:759-766) asserts ==; with integer-valued entries every sum is exact in any order
+    A = sp.random(10, 10, density=0.2, random_state=rng, format="csc", data_rvs=lambda k: rng.integers(-8, 9, k).astype(np.float64))
+    b = np.where(rng.uniform(size=10) < 0.2, rng.integers(-8, 9, 10), 0).astype(np.float64)     # sprand(10, 0.2) as a dense vector
+    cp, rv = A.indptr.astype(np.int64) + 1, A.indices.astype(np.int64) + 1
+    for trans, ref in ((0, A @ b), (1, A.T @ b)):
+        out = np.empty(10)
+        orc.spmv_csc_(out, 10, 10, cp, rv, A.data, b, trans=trans)
+        assert np.array_equal(out, ref)

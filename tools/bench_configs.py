@@ -84,6 +84,58 @@ def main():
                 del A, op, v, u, r, rt
                 torch.cuda.empty_cache()
         return
+    if only == ["sparse"]:
+        # LinearOperator(M::SparseMatrixCSC) (src/constructors.jl:15-29): compressed-row kernels.  Two patterns far above L2:
+        # (a) 2^21 rows x 24 entries (12 banded + 12 uniformly random columns: the gathers from x are sector-granular),
+        # (b) the 5-point Laplacian of a 2048 x 2048 grid (local gathers).  cuSPARSE (torch.sparse.mm) beside it.
+        dev = "cuda"
+        for dtype in (torch.float64, torch.float32):
+            tn = str(dtype).replace("torch.", "")
+            for pat in ("band12+rand12", "laplace2d"):
+                if pat == "laplace2d":
+                    g = 2048
+                    nr = g * g
+                    ii = torch.arange(nr, device=dev, dtype=torch.int64)
+                    gx, gy = ii % g, ii // g
+                    cand = torch.stack([ii - g, ii - 1, ii, ii + 1, ii + g], dim=1)
+                    ok = torch.stack([gy > 0, gx > 0, gx >= 0, gx < g - 1, gy < g - 1], dim=1)
+                    vals_full = torch.tensor([-1.0, -1.0, 4.0, -1.0, -1.0], device=dev, dtype=dtype).repeat(nr, 1)
+                    crow = torch.zeros(nr + 1, device=dev, dtype=torch.int64)
+                    crow[1:] = torch.cumsum(ok.sum(dim=1), 0)
+                    cols, vals = cand[ok], vals_full[ok]
+                    del ii, gx, gy, cand, ok, vals_full
+                else:
+                    nr, per_row = 1 << 21, 24
+                    gen = torch.Generator(device=dev).manual_seed(11)
+                    rows = torch.arange(nr, device=dev, dtype=torch.int64)
+                    band = (rows[:, None] + torch.arange(-6, 6, device=dev)[None, :]) % nr
+                    rnd = torch.randint(0, nr, (nr, per_row - 12), generator=gen, device=dev, dtype=torch.int64)
+                    cols = torch.sort(torch.cat([band, rnd], dim=1), dim=1).values.reshape(-1)
+                    vals = (torch.rand(nr * per_row, generator=gen, device=dev, dtype=torch.float64) * 2 - 1).to(dtype)
+                    crow = torch.arange(0, nr * per_row + 1, per_row, device=dev, dtype=torch.int64)
+                    del rows, band, rnd
+                M = torch.sparse_csr_tensor(crow, cols, vals, size=(nr, nr), device=dev)
+                t0 = time.perf_counter()
+                op = lo.LinearOperator(M)
+                torch.cuda.synchronize()
+                t_create = time.perf_counter() - t0
+                v = torch.rand(nr, dtype=dtype, device=dev)
+                r = torch.empty(nr, dtype=dtype, device=dev)
+                nnz = int(vals.numel())
+                for trans, tag in ((False, "N"), (True, "T")):
+                    o = lo.transpose(op) if trans else op
+                    l0 = ctx.launch_count()
+                    lo.mul_(r, o, v)
+                    nl = ctx.launch_count() - l0
+                    ms = timeit(lambda: lo.mul_(r, o, v), 20)
+                    line("sparse %s %s rows=%d nnz=%d %s" % (tag, pat, nr, nnz, tn), ms, op.apply_bytes(trans), launches=nl,
+                         create_s=round(t_create, 2), nnz_per_s=round(nnz / (ms * 1e-3), 0))
+                v2 = v[:, None].contiguous()
+                ms = timeit(lambda: torch.sparse.mm(M, v2), 20)
+                line("cusparse N %s %s (torch.sparse.mm, for comparison)" % (pat, tn), ms, op.apply_bytes(False))
+                del M, op, v, r, v2, cols, vals, crow
+                torch.cuda.empty_cache()
+        return
     if only == ["fwdc"]:
         v, res = ctx.uniform(n, 7), ctx.empty(n)
         m = 10

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""One profiled launch of each dense-matrix kernel (N / T, Float64 / Float32) on a 32768 x 32768 matrix
-(ncu --profile-from-start off; the cudaProfilerStart/Stop window below)."""
+"""One profiled launch of each matrix-leaf kernel (ncu --profile-from-start off; the cudaProfilerStart/Stop window below):
+dense N / T, Float64 / Float32, on a 32768 x 32768 matrix; sparse N / T on 2^21 rows x 24 entries (12 banded + 12 random)."""
 import os
 import sys
 
@@ -21,6 +21,20 @@ def main():
         v, u = torch.rand(k, dtype=dtype, device="cuda"), torch.rand(m, dtype=dtype, device="cuda")
         r, rt = torch.empty(m, dtype=dtype, device="cuda"), torch.empty(k, dtype=dtype, device="cuda")
         todo.append((op, v, u, r, rt))
+    dev = "cuda"
+    for dtype in (torch.float64, torch.float32):
+        nr, per_row = 1 << 21, 24
+        gen = torch.Generator(device=dev).manual_seed(11)
+        rows = torch.arange(nr, device=dev, dtype=torch.int64)
+        band = (rows[:, None] + torch.arange(-6, 6, device=dev)[None, :]) % nr
+        rnd = torch.randint(0, nr, (nr, per_row - 12), generator=gen, device=dev, dtype=torch.int64)
+        cols = torch.sort(torch.cat([band, rnd], dim=1), dim=1).values.reshape(-1)
+        vals = (torch.rand(nr * per_row, generator=gen, device=dev, dtype=torch.float64) * 2 - 1).to(dtype)
+        crow = torch.arange(0, nr * per_row + 1, per_row, device=dev, dtype=torch.int64)
+        op = lo.LinearOperator(torch.sparse_csr_tensor(crow, cols, vals, size=(nr, nr), device=dev))
+        v, u = torch.rand(nr, dtype=dtype, device=dev), torch.rand(nr, dtype=dtype, device=dev)
+        todo.append((op, v, u, torch.empty(nr, dtype=dtype, device=dev), torch.empty(nr, dtype=dtype, device=dev)))
+        del rows, band, rnd
     for op, v, u, r, rt in todo:       # warm-up
         lo.mul_(r, op, v)
         lo.mul_(rt, lo.transpose(op), u)
