@@ -69,6 +69,7 @@ struct b2o_ctx_s {
   int graph_jit = 1;     // fused trees: use the NVRTC-specialised kernel when NVRTC + driver are present (else the interpreter)
   int graph_blocks = 3;  // resident CTAs per SM the fused-graph kernel is compiled for (occupancy hides the dispatch latency)
   int dense_scalar = 0;  // dense-matrix leaf: force the scalar (unvectorised) kernels (testing)
+  int sparse_kernel = 0; // sparse-matrix leaf: 0 auto, 1 row kernel, 2 TMA-staged tile kernel
   // accounting
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -123,6 +124,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// orders this thread's generic-proxy shared-memory accesses before later async-proxy (bulk copy) accesses to the same bytes
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
       "{\n"

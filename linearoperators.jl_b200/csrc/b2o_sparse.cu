@@ -27,6 +27,8 @@ struct b2o_sparse_s {
   int given = 0;                 // which orientation aliases the caller's values (CSR: 0, CSC: 1)
   void *tval = nullptr;          // gathered values of the other orientation (owned)
   int64_t *perm = nullptr;       // tval[k] = vals[perm[k]]
+  SpTile *tiles[2] = {nullptr, nullptr};   // tile descriptors of the TMA-staged kernel, per orientation (ntiles + 1 entries)
+  int64_t ntiles[2] = {0, 0};
 };
 
 static inline size_t sparse_elem(int dtype) { return dtype == B2O_F64 ? 8 : 4; }
@@ -48,6 +50,7 @@ static void sparse_free(b2o_sparse *s) {
   for (int o = 0; o < 2; ++o) {
     cudaFree(s->ptr[o]);
     cudaFree(s->idx[o]);
+    cudaFree(s->tiles[o]);
   }
   cudaFree(s->tval);
   cudaFree(s->perm);
@@ -93,6 +96,11 @@ extern "C" int b2o_sparse_create(b2o_ctx *ctx, int dtype, int fmt, int64_t m, in
       }
   }
 
+  // tiles of the TMA-staged kernel for both orientations (index work, host)
+  std::vector<SpTile> gtiles, ttiles;
+  const int64_t ngt = spmv_build_tiles(gptr.data(), np, nnz, gtiles);
+  const int64_t ntt = spmv_build_tiles(tptr.data(), nd, nnz, ttiles);
+
   b2o_sparse *s = new b2o_sparse_s();
   s->ctx = ctx;
   s->dtype = dtype;
@@ -103,9 +111,12 @@ extern "C" int b2o_sparse_create(b2o_ctx *ctx, int dtype, int fmt, int64_t m, in
   s->given = fmt == 0 ? 1 : 0;               // CSC arrays are the compressed rows of Mᵀ
   const int g = s->given, t = 1 - g;
   const size_t nz = (size_t)std::max<int64_t>(nnz, 1);
-  bool ok = cudaMalloc(&s->ptr[g], sizeof(int64_t) * (np + 1)) == cudaSuccess &&
+  // offset arrays carry 3 spare (zeroed) entries: the bulk copies of the tile kernel read an even number of offsets
+  bool ok = cudaMalloc(&s->ptr[g], sizeof(int64_t) * (np + 4)) == cudaSuccess &&
             cudaMalloc(&s->idx[g], sizeof(int32_t) * nz) == cudaSuccess &&
-            cudaMalloc(&s->ptr[t], sizeof(int64_t) * (nd + 1)) == cudaSuccess &&
+            cudaMalloc(&s->ptr[t], sizeof(int64_t) * (nd + 4)) == cudaSuccess &&
+            cudaMalloc(&s->tiles[g], sizeof(SpTile) * gtiles.size()) == cudaSuccess &&
+            cudaMalloc(&s->tiles[t], sizeof(SpTile) * ttiles.size()) == cudaSuccess &&
             cudaMalloc(&s->idx[t], sizeof(int32_t) * nz) == cudaSuccess &&
             cudaMalloc(&s->tval, sparse_elem(dtype) * nz) == cudaSuccess && cudaMalloc(&s->perm, sizeof(int64_t) * nz) == cudaSuccess;
   if (!ok) {
@@ -115,7 +126,13 @@ extern "C" int b2o_sparse_create(b2o_ctx *ctx, int dtype, int fmt, int64_t m, in
   }
   s->val[g] = vals;
   s->val[t] = s->tval;
-  cudaError_t e = cudaMemcpyAsync(s->ptr[g], gptr.data(), sizeof(int64_t) * (np + 1), cudaMemcpyHostToDevice, ctx->stream);
+  s->ntiles[g] = ngt;
+  s->ntiles[t] = ntt;
+  cudaError_t e = cudaMemsetAsync(s->ptr[g], 0, sizeof(int64_t) * (np + 4), ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(s->ptr[t], 0, sizeof(int64_t) * (nd + 4), ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s->tiles[g], gtiles.data(), sizeof(SpTile) * gtiles.size(), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s->tiles[t], ttiles.data(), sizeof(SpTile) * ttiles.size(), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s->ptr[g], gptr.data(), sizeof(int64_t) * (np + 1), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(s->idx[g], gidx.data(), sizeof(int32_t) * nz, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(s->ptr[t], tptr.data(), sizeof(int64_t) * (nd + 1), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(s->idx[t], tidx.data(), sizeof(int32_t) * nz, cudaMemcpyHostToDevice, ctx->stream);
@@ -160,6 +177,17 @@ extern "C" int b2o_sparse_apply(b2o_sparse *s, int trans, void *res, int64_t res
   b2o_ctx *c = s->ctx;
   B2O_CUDA(cudaSetDevice(c->device));
   const int o = trans ? 1 : 0;
+  // sparse_kernel option: 0 picks the TMA-staged tile kernel when it pays off, 1 forces the row kernel, 2 the tile kernel
+  // (still needs 16-byte aligned values)
+  const bool tiles = c->sparse_kernel != 1 && s->ntiles[o] > 0 && ((uintptr_t)s->val[o] & 15) == 0 &&
+                     (c->sparse_kernel == 2 || spmv_tiles_eligible(c->num_sms, s->ntiles[o], s->val[o]));
+  if (tiles) {
+    if (s->dtype == B2O_F64)
+      return spmv_tiles_run_impl<double>(c->num_sms, c->stream, &c->launches, s->tiles[o], s->ntiles[o], s->ptr[o], s->idx[o],
+                                         s->val[o], out_len, s->nnz, res, v, alpha, beta);
+    return spmv_tiles_run_impl<float>(c->num_sms, c->stream, &c->launches, s->tiles[o], s->ntiles[o], s->ptr[o], s->idx[o],
+                                      s->val[o], out_len, s->nnz, res, v, alpha, beta);
+  }
   if (s->dtype == B2O_F64)
     return spmv_run_impl<double>(c->num_sms, c->stream, &c->launches, s->ptr[o], s->idx[o], s->val[o], out_len, s->nnz, res, v, alpha, beta);
   return spmv_run_impl<float>(c->num_sms, c->stream, &c->launches, s->ptr[o], s->idx[o], s->val[o], out_len, s->nnz, res, v, alpha, beta);

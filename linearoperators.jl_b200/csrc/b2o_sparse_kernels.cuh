@@ -85,6 +85,261 @@ __global__ void __launch_bounds__(SP_THREADS, SP_CTAS_PER_SM) spmv_rows_kernel(c
   }
 }
 
+// ================================================================== TMA-staged tile kernel
+// The row kernel above is bound by its dependent load chain (ptr -> idx/val -> x: three DRAM/L2 latencies per row, measured
+// 47 % DRAM utilisation with the same duration for Float32 and Float64).  The tile kernel takes the two streaming legs off
+// that chain: the structure is cut ONCE, on the host at create time, into tiles of consecutive rows holding <= ST_C entries
+// and <= ST_RT rows; a producer warp stages each tile's idx / val / row-offset slices global -> shared with 1-D TMA bulk
+// copies (cp.async.bulk + mbarrier complete_tx) into a ring, several tiles ahead; 8 consumer warps
+//   (1) gather: thread t takes entries t, t+256, ... of the tile -- eight independent x[idx] gathers in flight per thread --
+//       and writes the products (double) in place over the staged values,
+//   (2) reduce: 2^LL lanes per row sum the row's products from shared memory in a fixed order (same butterfly as above),
+//       apply α / β and store y.
+// No atomics, fixed order -> bit-reproducible.  Bulk copies need 16-byte aligned sources: a tile's copy starts at its first
+// entry rounded down to a multiple of 4 and is clamped to the last whole quad of the array (entries beyond it, at most 3, are
+// read straight from global memory); row-offset slices start at an even row.  A row longer than ST_C is a "direct" tile:
+// the 256 consumer threads sum it straight from global memory (fixed-order block reduction).
+constexpr int ST_C = 2048;                     // entries per tile (including <= 3 leading alignment entries)
+constexpr int ST_RT = 1024;                    // rows per tile
+constexpr int ST_NCONS = 256;                  // consumer threads
+constexpr int ST_CONS_WARPS = ST_NCONS / 32;
+constexpr int ST_NTHREADS = ST_NCONS + 32;     // + producer warp
+constexpr int ST_STAGES = 3;
+constexpr int ST_CTAS_PER_SM = 2;
+constexpr int ST_EPT = ST_C / ST_NCONS;        // entries per consumer thread and tile
+// one ring stage: idx[ST_C] int32 | val / products [ST_C] 8 bytes each | row offsets [ST_RT + 2] int64
+constexpr size_t ST_IDX_OFF = 0;
+constexpr size_t ST_VAL_OFF = ST_IDX_OFF + sizeof(int32_t) * ST_C;
+constexpr size_t ST_PTR_OFF = ST_VAL_OFF + sizeof(double) * ST_C;
+constexpr size_t ST_STAGE_BYTES = ST_PTR_OFF + sizeof(int64_t) * (ST_RT + 2);
+constexpr size_t ST_BAR_OFF = ST_STAGE_BYTES * ST_STAGES;
+constexpr size_t ST_SMEM_BYTES = ST_BAR_OFF + sizeof(uint64_t) * 2 * ST_STAGES;
+static_assert(ST_STAGE_BYTES % 16 == 0 && ST_C % 4 == 0 && ST_C % ST_NCONS == 0, "tile layout");
+
+struct SpTile {      // 16 bytes; tiles[ntiles] is a sentinel {nnz, nrows, 0}
+  int64_t e0;        // first entry staged (multiple of 4, <= ptr[r0]); direct tile: ptr[r0]
+  int32_t r0;        // first row; the tile ends where the next one starts
+  int32_t ne;        // entries staged (multiple of 4, e0 + ne >= ptr[r1]); -1: direct tile (one row longer than ST_C)
+};
+
+struct SpTileArgs {
+  const SpTile *tiles;
+  int64_t ntiles;
+  const int64_t *ptr;   // [nrows + 1], 16-byte aligned, readable up to index nrows + 2
+  const int32_t *idx;   // 16-byte aligned
+  const void *val;      // 16-byte aligned
+  const void *x;
+  void *y;
+  int64_t nrows;
+  int64_t q_tail;       // nnz rounded down to a multiple of 4: no bulk copy reaches beyond it
+  double alpha, beta;
+};
+
+#ifdef B2O_SIMT_EMU
+inline void st_consumers_sync() { emu::named_barrier_sync(1, ST_NCONS); }
+#else
+__device__ __forceinline__ void st_consumers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(ST_NCONS) : "memory"); }
+#endif
+
+template <typename T, int LL>
+__global__ void __launch_bounds__(ST_NTHREADS, ST_CTAS_PER_SM) spmv_tiles_kernel(const __grid_constant__ SpTileArgs p) {
+  constexpr int L = 1 << LL;
+  constexpr int GROUPS_PER_WARP = 32 >> LL;
+#ifdef B2O_SIMT_EMU
+  unsigned char *smem_raw = emu::dyn_smem();
+#else
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+#endif
+  __shared__ double s_red[ST_CONS_WARPS];
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + ST_BAR_OFF);
+  uint64_t *empty = full + ST_STAGES;
+  const int tid = threadIdx.x, lane32 = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < ST_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], ST_CONS_WARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // contiguous tile range of this CTA
+  const int64_t tb = p.ntiles * (int64_t)blockIdx.x / (int64_t)gridDim.x;
+  const int64_t te = p.ntiles * ((int64_t)blockIdx.x + 1) / (int64_t)gridDim.x;
+  const T *__restrict__ val = (const T *)p.val;
+  uint32_t slot = 0, par = 0;
+
+  if (warp == ST_CONS_WARPS) {
+    // ---------------------------------------------------------------- producer: one elected lane issues the bulk copies
+    if (lane32 == 0 && tb < te) {
+      SpTile cur = p.tiles[tb], nxt = p.tiles[tb + 1];           // descriptors are fetched two tiles ahead (sentinel at ntiles)
+      for (int64_t t = tb; t < te; ++t) {
+        const SpTile nn = p.tiles[t + 2 <= p.ntiles ? t + 2 : p.ntiles];
+        if (cur.ne >= 0) {
+          const int64_t r1 = nxt.r0;
+          const int64_t rbase = (int64_t)cur.r0 & ~(int64_t)1;
+          const uint32_t nptr = (uint32_t)(((r1 - rbase + 1) + 1) & ~(int64_t)1);      // offsets rbase .. r1, even count
+          int64_t ncopy = cur.ne;
+          if (cur.e0 + ncopy > p.q_tail) ncopy = p.q_tail > cur.e0 ? p.q_tail - cur.e0 : 0;
+          unsigned char *stage = smem_raw + (size_t)slot * ST_STAGE_BYTES;
+          mbar_wait(&empty[slot], par ^ 1u);
+          mbar_expect_tx(&full[slot], (uint32_t)(ncopy * (sizeof(int32_t) + sizeof(T)) + nptr * sizeof(int64_t)));
+          bulk_g2s(stage + ST_PTR_OFF, p.ptr + rbase, (uint32_t)(nptr * sizeof(int64_t)), &full[slot]);
+          if (ncopy > 0) {
+            bulk_g2s(stage + ST_IDX_OFF, p.idx + cur.e0, (uint32_t)(ncopy * sizeof(int32_t)), &full[slot]);
+            bulk_g2s(stage + ST_VAL_OFF, val + cur.e0, (uint32_t)(ncopy * sizeof(T)), &full[slot]);
+          }
+          if (++slot == ST_STAGES) {
+            slot = 0;
+            par ^= 1u;
+          }
+        }
+        cur = nxt;
+        nxt = nn;
+      }
+    }
+    __syncwarp();
+    return;
+  }
+
+  // ------------------------------------------------------------------ consumers
+  const T *__restrict__ x = (const T *)p.x;
+  T *y = (T *)p.y;
+  const int lane = tid & (L - 1);
+  const int group_in_warp = lane32 >> LL;
+  if (tb >= te) return;
+  SpTile cur = p.tiles[tb], nxt = p.tiles[tb + 1];
+  for (int64_t t = tb; t < te; ++t) {
+    const SpTile nn = p.tiles[t + 2 <= p.ntiles ? t + 2 : p.ntiles];
+    const int64_t r0 = cur.r0, r1 = nxt.r0;
+    if (cur.ne < 0) {
+      // ---- direct tile: one long row summed from global memory by all consumers, fixed-order block reduction
+      const int64_t start = __ldg(p.ptr + r0), end = __ldg(p.ptr + r0 + 1);
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      for (int64_t k = start + tid; k < end; k += 4 * ST_NCONS) {
+        const int64_t k1 = k + ST_NCONS, k2 = k + 2 * ST_NCONS, k3 = k + 3 * ST_NCONS;
+        const bool p1 = k1 < end, p2 = k2 < end, p3 = k3 < end;
+        const int32_t i0 = __ldg(p.idx + k);
+        const int32_t i1 = p1 ? __ldg(p.idx + k1) : 0;
+        const int32_t i2 = p2 ? __ldg(p.idx + k2) : 0;
+        const int32_t i3 = p3 ? __ldg(p.idx + k3) : 0;
+        const T a0 = __ldg(val + k);
+        const T a1 = p1 ? __ldg(val + k1) : (T)0;
+        const T a2 = p2 ? __ldg(val + k2) : (T)0;
+        const T a3 = p3 ? __ldg(val + k3) : (T)0;
+        const T x0 = __ldg(x + i0);
+        const T x1 = p1 ? __ldg(x + i1) : (T)0;
+        const T x2 = p2 ? __ldg(x + i2) : (T)0;
+        const T x3 = p3 ? __ldg(x + i3) : (T)0;
+        s0 = fma((double)a0, (double)x0, s0);
+        s1 = fma((double)a1, (double)x1, s1);
+        s2 = fma((double)a2, (double)x2, s2);
+        s3 = fma((double)a3, (double)x3, s3);
+      }
+      double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane32 == 0) s_red[warp] = s;
+      st_consumers_sync();
+      if (tid == 0) {
+        double tot = 0.0;
+#pragma unroll
+        for (int w = 0; w < ST_CONS_WARPS; ++w) tot += s_red[w];
+        double r = p.alpha * tot;
+        if (p.beta != 0.0) r += p.beta * (double)y[r0];
+        y[r0] = (T)r;
+      }
+      st_consumers_sync();                                        // s_red is reused by the next direct tile
+      cur = nxt;
+      nxt = nn;
+      continue;
+    }
+
+    unsigned char *stage = smem_raw + (size_t)slot * ST_STAGE_BYTES;
+    const int32_t *sidx = reinterpret_cast<const int32_t *>(stage + ST_IDX_OFF);
+    const T *sval = reinterpret_cast<const T *>(stage + ST_VAL_OFF);
+    double *sprod = reinterpret_cast<double *>(stage + ST_VAL_OFF);
+    const int64_t *sptr = reinterpret_cast<const int64_t *>(stage + ST_PTR_OFF) + (r0 & 1);      // sptr[i] = ptr[r0 + i]
+    mbar_wait(&full[slot], par);
+    const int64_t e0 = cur.e0;
+    const int lead = (int)(sptr[0] - e0);                          // 0..3 alignment entries in front of the first row
+    const int used = (int)(sptr[r1 - r0] - e0);                    // one past the last entry of the tile's rows
+    int64_t avail = p.q_tail - e0;                                 // entries of this tile the bulk copies may cover
+    avail = avail < 0 ? 0 : avail;
+    const int staged = (int)(avail < (int64_t)cur.ne ? avail : (int64_t)cur.ne);
+    // ---- (1) gather: ST_EPT products per thread, all x loads issued before the first multiply
+    int32_t ci[ST_EPT];
+    T ca[ST_EPT], cx[ST_EPT];
+#pragma unroll
+    for (int u = 0; u < ST_EPT; ++u) {
+      const int j = u * ST_NCONS + tid;
+      const bool ok = j >= lead && j < used;
+      ci[u] = 0;
+      ca[u] = (T)0;
+      if (ok) {
+        if (j < staged) {
+          ci[u] = sidx[j];
+          ca[u] = sval[j];
+        } else {                                                   // the <= 3 entries beyond the last whole quad of the arrays
+          ci[u] = __ldg(p.idx + e0 + j);
+          ca[u] = __ldg(val + e0 + j);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < ST_EPT; ++u) {
+      const int j = u * ST_NCONS + tid;
+      cx[u] = (j >= lead && j < used) ? __ldg(x + ci[u]) : (T)0;
+    }
+    if (sizeof(T) < sizeof(double)) st_consumers_sync();           // Float32: products (8 bytes) overlay two staged values
+#pragma unroll
+    for (int u = 0; u < ST_EPT; ++u) {
+      const int j = u * ST_NCONS + tid;
+      if (j < used) sprod[j] = (double)ca[u] * (double)cx[u];
+    }
+    st_consumers_sync();
+    // ---- (2) reduce: L lanes per row, fixed order
+    const int nr = (int)(r1 - r0);
+    for (int rr0 = warp * GROUPS_PER_WARP; rr0 < nr; rr0 += ST_CONS_WARPS * GROUPS_PER_WARP) {
+      const int rr = rr0 + group_in_warp;
+      const bool valid = rr < nr;
+      int start = 0, end = 0;
+      if (valid) {
+        start = (int)(sptr[rr] - e0);
+        end = (int)(sptr[rr + 1] - e0);
+      }
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      for (int k = start + lane; k < end; k += 4 * L) {
+        const int k1 = k + L, k2 = k + 2 * L, k3 = k + 3 * L;
+        s0 += sprod[k];
+        s1 += k1 < end ? sprod[k1] : 0.0;
+        s2 += k2 < end ? sprod[k2] : 0.0;
+        s3 += k3 < end ? sprod[k3] : 0.0;
+      }
+      double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+      for (int o = L >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (valid && lane == 0) {
+        const int64_t r = r0 + rr;
+        double tv = p.alpha * s;
+        if (p.beta != 0.0) tv += p.beta * (double)y[r];
+        y[r] = (T)tv;
+      }
+    }
+    // hand the slot back: all reads of this warp are done; its product stores (generic proxy) are ordered before the bulk copy
+    // (async proxy) that refills the slot
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane32 == 0) mbar_arrive(&empty[slot]);
+    if (++slot == ST_STAGES) {
+      slot = 0;
+      par ^= 1u;
+    }
+    cur = nxt;
+    nxt = nn;
+  }
+}
+
 // dst[k] = src[perm[k]]: refreshes the values of the transposed copy (structure transposition happens once, on the host)
 template <typename T>
 __global__ void __launch_bounds__(SP_THREADS) perm_gather_kernel(T *dst, const T *src, const int64_t *perm, int64_t nnz) {
@@ -131,6 +386,88 @@ static int spmv_run_impl(int num_sms, B2O_STREAM_T stream, int64_t *launches, co
     default: kern = spmv_rows_kernel<T, 5>; break;
   }
   B2O_LAUNCH(kern, dim3((unsigned)spmv_grid(num_sms, nrows, a.lanes_log2)), dim3(SP_THREADS), 0, stream, a);
+  ++*launches;
+  B2O_CUDA(cudaGetLastError());
+  return B2O_OK;
+}
+
+// ---- tile kernel, host side ----------------------------------------------------------------------------------------
+#ifndef B2O_SIMT_EMU
+#define B2O_FUNC_SMEM(kern, bytes) \
+  B2O_CUDA(cudaFuncSetAttribute((const void *)(kern), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)))
+#else
+#define B2O_FUNC_SMEM(kern, bytes) \
+  do {                             \
+  } while (0)
+#endif
+
+// cut a compressed-row structure (0-based host offsets) into tiles; returns ntiles, `out` holds ntiles + 1 descriptors
+template <typename Vec>
+static inline int64_t spmv_build_tiles(const int64_t *ptr, int64_t nrows, int64_t nnz, Vec &out) {
+  out.clear();
+  int64_t r = 0;
+  while (r < nrows) {
+    SpTile t;
+    const int64_t e0 = ptr[r] & ~(int64_t)3;
+    if (ptr[r + 1] - e0 > ST_C) {                      // a row that does not fit a tile: summed straight from global memory
+      t.e0 = ptr[r];
+      t.r0 = (int32_t)r;
+      t.ne = -1;
+      out.push_back(t);
+      ++r;
+      continue;
+    }
+    int64_t r1 = r + 1;
+    while (r1 < nrows && r1 - r < ST_RT && ptr[r1 + 1] - e0 <= ST_C) ++r1;
+    t.e0 = e0;
+    t.r0 = (int32_t)r;
+    t.ne = (int32_t)(((ptr[r1] - e0) + 3) & ~(int64_t)3);
+    out.push_back(t);
+    r = r1;
+  }
+  const int64_t ntiles = (int64_t)out.size();
+  SpTile sentinel;
+  sentinel.e0 = nnz;
+  sentinel.r0 = (int32_t)nrows;
+  sentinel.ne = 0;
+  out.push_back(sentinel);
+  return ntiles;
+}
+
+// the tile kernel pays off when every SM gets several tiles and the arrays can be bulk-copied (16-byte aligned values)
+static inline bool spmv_tiles_eligible(int num_sms, int64_t ntiles, const void *val) {
+  return ntiles >= 4 * (int64_t)num_sms * ST_CTAS_PER_SM && ((uintptr_t)val & 15) == 0;
+}
+
+template <typename T>
+static int spmv_tiles_run_impl(int num_sms, B2O_STREAM_T stream, int64_t *launches, const SpTile *tiles, int64_t ntiles,
+                               const int64_t *ptr, const int32_t *idx, const void *val, int64_t nrows, int64_t nnz, void *y,
+                               const void *x, double alpha, double beta) {
+  if (nrows == 0 || ntiles == 0) return B2O_OK;
+  SpTileArgs a;
+  a.tiles = tiles;
+  a.ntiles = ntiles;
+  a.ptr = ptr;
+  a.idx = idx;
+  a.val = val;
+  a.x = x;
+  a.y = y;
+  a.nrows = nrows;
+  a.q_tail = nnz & ~(int64_t)3;
+  a.alpha = alpha;
+  a.beta = beta;
+  void (*kern)(const SpTileArgs) = nullptr;
+  switch (spmv_lanes_log2(nrows, nnz)) {
+    case 0: kern = spmv_tiles_kernel<T, 0>; break;
+    case 1: kern = spmv_tiles_kernel<T, 1>; break;
+    case 2: kern = spmv_tiles_kernel<T, 2>; break;
+    case 3: kern = spmv_tiles_kernel<T, 3>; break;
+    case 4: kern = spmv_tiles_kernel<T, 4>; break;
+    default: kern = spmv_tiles_kernel<T, 5>; break;
+  }
+  B2O_FUNC_SMEM(kern, ST_SMEM_BYTES);
+  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)num_sms * ST_CTAS_PER_SM));
+  B2O_LAUNCH(kern, dim3((unsigned)grid), dim3(ST_NTHREADS), ST_SMEM_BYTES, stream, a);
   ++*launches;
   B2O_CUDA(cudaGetLastError());
   return B2O_OK;

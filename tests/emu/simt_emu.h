@@ -14,7 +14,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -48,7 +50,10 @@ struct Block {
   std::barrier<> bar;
   std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
   std::vector<double> xchg;  // [nthreads]
-  explicit Block(unsigned n) : nthreads(n), bar(n), xchg(n) {
+  std::vector<unsigned char> dyn;                                  // dynamic shared memory (+ slack for 128-byte alignment)
+  std::mutex named_mu;
+  std::map<int, std::unique_ptr<std::barrier<>>> named;           // bar.sync id, count
+  explicit Block(unsigned n, size_t smem = 0) : nthreads(n), bar(n), xchg(n), dyn(smem + 128) {
     for (unsigned w = 0; w < (n + 31) / 32; ++w) warp_bar.emplace_back(new std::barrier<>(std::min(32u, n - 32 * w)));
   }
 };
@@ -57,6 +62,82 @@ inline std::string last_error;
 }  // namespace emu
 inline thread_local dim3 threadIdx, blockIdx;
 inline dim3 gridDim, blockDim;
+
+namespace emu {
+inline unsigned char *dyn_smem() {
+  unsigned char *p = cur_block->dyn.data();
+  return p + ((128 - ((uintptr_t)p & 127)) & 127);
+}
+// bar.sync id, count: the first `count` arrivals form the barrier (all callers pass the same count for an id)
+inline void named_barrier_sync(int id, int count) {
+  Block *b = cur_block;
+  std::barrier<> *bar;
+  {
+    std::lock_guard<std::mutex> g(b->named_mu);
+    auto &slot = b->named[id];
+    if (!slot) slot.reset(new std::barrier<>(count));
+    bar = slot.get();
+  }
+  bar->arrive_and_wait();
+}
+// ---- mbarrier + 1-D bulk copy (cp.async.bulk ... mbarrier::complete_tx) restated for the host: the 8-byte barrier word
+// packs pending arrivals [0,16), arrival count [16,32), outstanding transaction bytes [32,63) and the phase bit [63].
+// A phase completes when the pending arrivals AND the outstanding bytes reach zero; waiting on parity P returns once the
+// phase of parity P is over.  Checks the alignment rules of the real instruction (16-byte addresses and sizes).
+inline std::mutex mbar_mu;
+inline void mbar_check(uint64_t *b) {
+  const uint64_t pend = *b & 0xffffu, init = (*b >> 16) & 0xffffu, tx = (*b >> 32) & 0x7fffffffu, ph = *b >> 63;
+  if (pend == 0 && tx == 0) *b = ((ph ^ 1u) << 63) | (init << 16) | init;
+}
+}  // namespace emu
+inline void mbar_init(uint64_t *b, uint32_t count) {
+  std::lock_guard<std::mutex> g(emu::mbar_mu);
+  *b = ((uint64_t)count << 16) | count;
+}
+inline void mbar_fence_init() {}
+inline void fence_proxy_async_smem() {}
+inline void mbar_expect_tx(uint64_t *b, uint32_t bytes) {      // mbarrier.arrive.expect_tx
+  std::lock_guard<std::mutex> g(emu::mbar_mu);
+  if ((*b & 0xffffu) == 0) {
+    fprintf(stderr, "emu: mbarrier arrive with no pending arrivals\n");
+    abort();
+  }
+  *b += ((uint64_t)bytes << 32);
+  *b -= 1;
+  emu::mbar_check(b);
+}
+inline void mbar_arrive(uint64_t *b) {
+  std::lock_guard<std::mutex> g(emu::mbar_mu);
+  if ((*b & 0xffffu) == 0) {
+    fprintf(stderr, "emu: mbarrier arrive with no pending arrivals\n");
+    abort();
+  }
+  *b -= 1;
+  emu::mbar_check(b);
+}
+inline void mbar_wait(uint64_t *b, uint32_t parity) {
+  for (;;) {
+    {
+      std::lock_guard<std::mutex> g(emu::mbar_mu);
+      if ((uint32_t)(*b >> 63) != (parity & 1u)) return;
+    }
+    std::this_thread::yield();
+  }
+}
+inline void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *b) {
+  if (((uintptr_t)dst & 15) || ((uintptr_t)src & 15) || (bytes & 15) || bytes == 0) {
+    fprintf(stderr, "emu: bulk copy breaks the 16-byte rules (dst %p src %p bytes %u)\n", dst, src, bytes);
+    abort();
+  }
+  memcpy(dst, src, bytes);
+  std::lock_guard<std::mutex> g(emu::mbar_mu);
+  if (((*b >> 32) & 0x7fffffffu) < bytes) {
+    fprintf(stderr, "emu: bulk copy completes more bytes than expected\n");
+    abort();
+  }
+  *b -= ((uint64_t)bytes << 32);
+  emu::mbar_check(b);
+}
 
 inline void __syncthreads() { emu::cur_block->bar.arrive_and_wait(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::cur_block->warp_bar[threadIdx.x >> 5]->arrive_and_wait(); }
@@ -116,7 +197,7 @@ namespace emu {
 // run `fn` for every thread of every block of the grid: blocks one after the other (a `__shared__` static belongs to one
 // block at a time), the threads of a block concurrently.  One pool of OS threads per launch walks over the blocks.
 template <typename F>
-inline void launch(dim3 grid, dim3 block, F fn) {
+inline void launch(dim3 grid, dim3 block, size_t smem, F fn) {
   gridDim = grid;
   blockDim = block;
   const unsigned nthreads = block.x * block.y * block.z;
@@ -130,7 +211,7 @@ inline void launch(dim3 grid, dim3 block, F fn) {
       threadIdx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
       for (size_t b = 0; b < nblocks; ++b) {
         static Block *shared_blk = nullptr;           // published by thread 0, read by all after the barrier
-        if (t == 0) shared_blk = new Block(nthreads);
+        if (t == 0) shared_blk = new Block(nthreads, smem);
         between_blocks.arrive_and_wait();
         Block *blk = shared_blk;
         cur_block = blk;
@@ -146,4 +227,4 @@ inline void launch(dim3 grid, dim3 block, F fn) {
   for (auto &th : ts) th.join();
 }
 }  // namespace emu
-#define B2O_LAUNCH(kern, grid, block, smem, stream, ...) emu::launch((grid), (block), [&] { kern(__VA_ARGS__); })
+#define B2O_LAUNCH(kern, grid, block, smem, stream, ...) emu::launch((grid), (block), (size_t)(smem), [&] { kern(__VA_ARGS__); })

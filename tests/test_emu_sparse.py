@@ -29,7 +29,9 @@ def emu():
     vp, i64, i32, d = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double
     L.emu_sparse_apply.restype = i32
     L.emu_sparse_apply.argtypes = [i32, i32, i64, i64, i64, vp, vp, vp, i32, vp, vp, d, d, i32, ctypes.POINTER(i64),
-                                   ctypes.POINTER(i32)]
+                                   ctypes.POINTER(i32), i32, ctypes.POINTER(i64)]
+    L.emu_sparse_tiles.restype = i64
+    L.emu_sparse_tiles.argtypes = [vp, i64, i64, vp, i64, ctypes.POINTER(i32), ctypes.POINTER(i32)]
     return L
 
 
@@ -63,8 +65,9 @@ def test_spmv_kernel_matches_oracle(emu, orc, dtype, fmt):
     assert {0, 1, 2, 3, 4, 5} <= seen          # every lane-group width 1..32 was exercised
 
 
-def run_checked(emu, orc, A, dtype, fmt, trans, alpha, beta, num_sms=2, seed=0):
-    """run() + independent scipy check, with the starting res regenerated for β != 0"""
+def run_checked(emu, orc, A, dtype, fmt, trans, alpha, beta, num_sms=2, seed=0, kernel=1, want_tiles=None):
+    """one product through the emulated row kernel (kernel=1) or TMA-staged tile kernel (kernel=2), checked against the
+    oracle and, independently, scipy; the starting res is regenerated for β != 0"""
     dt = np.float64 if dtype == F64 else np.float32
     m, n = A.shape
     csc = A.tocsc()
@@ -82,10 +85,13 @@ def run_checked(emu, orc, A, dtype, fmt, trans, alpha, beta, num_sms=2, seed=0):
     ref = res.copy()
     orc.spmv_csc_(ref, m, n, csc.indptr.astype(np.int64) + 1, csc.indices.astype(np.int64) + 1, csc.data.astype(dt), v, alpha, beta,
                   trans)
-    launches, lanes = ctypes.c_int64(), ctypes.c_int()
+    launches, lanes, ntiles = ctypes.c_int64(), ctypes.c_int(), ctypes.c_int64()
     rc = emu.emu_sparse_apply(dtype, fmt, m, n, S.nnz, ptr1.ctypes.data, idx1.ctypes.data, vals.ctypes.data, trans,
-                              res.ctypes.data, v.ctypes.data, alpha, beta, num_sms, ctypes.byref(launches), ctypes.byref(lanes))
+                              res.ctypes.data, v.ctypes.data, alpha, beta, num_sms, ctypes.byref(launches), ctypes.byref(lanes),
+                              kernel, ctypes.byref(ntiles))
     assert rc == 0
+    if want_tiles is not None:
+        assert ntiles.value >= want_tiles, (ntiles.value, want_tiles)
     tol = 1e-13 if dtype == F64 else 2e-6
     if nout:
         B = (A.T if trans else A).astype(np.float64)
@@ -110,3 +116,92 @@ def test_spmv_kernel_edge_cases(emu, orc, dtype):
             assert run_checked(emu, orc, D, dtype, fmt, trans, 1.0, 0.0, num_sms=1) == 0
             R = sp.csc_matrix(np.ones((3, 4000), dtype=dt))              # three dense rows / 4000 tiny columns
             run_checked(emu, orc, R, dtype, fmt, trans, 1.0, 0.0, num_sms=1)
+
+
+# ---------------------------------------------------------------- the TMA-staged tile kernel (spmv_tiles_kernel)
+def tile_cut(emu, ptr0, nnz):
+    ptr0 = np.ascontiguousarray(ptr0, dtype=np.int64)
+    nrows = len(ptr0) - 1
+    out = np.zeros(3 * (nrows + 2), dtype=np.int64)
+    c, rt = ctypes.c_int(), ctypes.c_int()
+    nt = emu.emu_sparse_tiles(ptr0.ctypes.data, nrows, nnz, out.ctypes.data, nrows + 2, ctypes.byref(c), ctypes.byref(rt))
+    return out[:3 * (nt + 1)].reshape(nt + 1, 3), c.value, rt.value
+
+
+def test_tile_cut_invariants(emu):
+    """spmv_build_tiles: tiles cover the rows once and in order; staged ranges start on a quad at or before the first entry,
+    cover the tile's entries, fit the stage; rows that cannot fit become direct tiles of one row; sentinel at the end"""
+    rng = np.random.default_rng(0)
+    for trial in range(30):
+        nrows = int(rng.integers(1, 4000))
+        kind = trial % 5
+        if kind == 0:
+            lens = rng.integers(0, 6, nrows)
+        elif kind == 1:
+            lens = np.where(rng.uniform(size=nrows) < 0.01, rng.integers(2000, 9000, nrows), rng.integers(0, 40, nrows))
+        elif kind == 2:
+            lens = np.zeros(nrows, dtype=np.int64)
+            lens[rng.integers(0, nrows, 3)] = rng.integers(1, 5000, 3)
+        elif kind == 3:
+            lens = rng.integers(500, 1100, nrows % 50 + 1)
+        else:
+            lens = np.full(nrows, 1)
+        ptr0 = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        nrows, nnz = len(lens), int(ptr0[-1])
+        tiles, C, RT = tile_cut(emu, ptr0, nnz)
+        assert tuple(tiles[-1]) == (nnz, nrows, 0) and tiles[0, 1] == 0
+        for (e0, r0, ne), (_, r1, _) in zip(tiles[:-1], tiles[1:]):
+            assert r1 > r0 and r1 - r0 <= RT
+            if ne < 0:
+                assert r1 == r0 + 1 and e0 == ptr0[r0] and ptr0[r1] - (ptr0[r0] & ~3) > C      # a row that cannot fit
+            else:
+                assert e0 % 4 == 0 and ne % 4 == 0 and 0 <= ptr0[r0] - e0 <= 3
+                assert e0 + ne >= ptr0[r1] and ne <= C and e0 + ne - ptr0[r1] <= 3
+                # greedy: the next row would not have fitted (or the row limit / end was hit)
+                assert r1 == nrows or r1 - r0 == RT or ptr0[r1 + 1] - e0 > C
+
+
+@pytest.mark.parametrize("dtype", [F64, F32])
+def test_tile_kernel_matches_oracle(emu, orc, dtype):
+    """the tile kernel on structures that exercise: several tiles per CTA and more CTAs than tiles, nnz not a multiple of 4
+    (entries past the last whole quad come from global memory), odd first rows (offset slice starts one row early), long rows
+    (direct tiles), long runs of empty rows (row limit per tile), every lane-group width"""
+    dt = np.float64 if dtype == F64 else np.float32
+    rng = np.random.default_rng(7)
+    seen = set()
+    cases = []
+    A = random_sparse(700, 900, 0.02, 1, dt)                                   # ~18 entries per row, ~6 tiles
+    cases.append((A, 3))
+    B = random_sparse(300, 5000, 0.004, 2, dt, dense_row=150)                  # one 5000-entry row -> direct tile
+    cases.append((B, 3))
+    Cm = sp.identity(5000, dtype=dt, format="csc") * 1.5                       # 1 entry per row -> row limit binds (5 tiles)
+    cases.append((Cm, 4))
+    Dm = sp.lil_matrix((3000, 40), dtype=dt)                                   # long runs of empty rows, entries in rows 1000-1020
+    Dm[1000:1021, :] = rng.uniform(-1, 1, (21, 40))
+    cases.append((Dm.tocsc(), 2))
+    Em = random_sparse(37, 2500, 0.5, 3, dt)                                   # ~1250 per row: one row per tile, 32 lanes
+    cases.append((Em, 30))
+    for k, (M, want) in enumerate(cases):
+        M = sp.csc_matrix(M)
+        M.eliminate_zeros()
+        for trans in (0, 1):
+            for fmt in (0, 1):
+                seen.add(run_checked(emu, orc, M, dtype, fmt, trans, 1.0, 0.0, seed=k, kernel=2,
+                                     want_tiles=want if (trans == 0) else None))
+            run_checked(emu, orc, M, dtype, 0, trans, 2.0, -0.5, seed=60 + k, kernel=2, num_sms=1)
+    assert {0, 3, 5} <= seen
+    # nnz % 4 in {1, 2, 3}: drop entries from the end of the storage
+    base = random_sparse(400, 300, 0.06, 9, dt).tocsr()
+    for cut in (1, 2, 3):
+        M = base.copy()
+        M.data[-cut:] = 0
+        M.eliminate_zeros()
+        assert M.nnz % 4 != base.nnz % 4 or cut == 0
+        for trans in (0, 1):
+            run_checked(emu, orc, sp.csc_matrix(M), dtype, 1, trans, 1.0, 0.0, seed=cut, kernel=2)
+    # edge: empty matrix / no rows -> nothing staged
+    for shape in ((0, 5), (5, 0), (9, 9)):
+        Z = sp.csc_matrix(shape, dtype=dt)
+        for trans in (0, 1):
+            run_checked(emu, orc, Z, dtype, 0, trans, 1.0, 0.0, kernel=2)
+            run_checked(emu, orc, Z, dtype, 0, trans, 3.0, 2.0, seed=3, kernel=2)

@@ -73,13 +73,23 @@ def oracle_product(orc, A, v, alpha, beta, trans, res0):
 
 
 CASES = [(10, 6, 0.5), (6, 10, 0.5), (200, 300, 0.004), (300, 200, 0.02), (150, 150, 0.05), (64, 500, 0.12), (40, 700, 0.3),
-         (33, 900, 0.9), (1, 50, 0.5), (50, 1, 0.5), (257, 129, 0.03), (20011, 30011, 0.0004), (70001, 517, 0.01)]
+         (33, 900, 0.9), (1, 50, 0.5), (50, 1, 0.5), (257, 129, 0.03), (20011, 30011, 0.0004), (70001, 517, 0.01),
+         (64, 3000, 0.01), (129, 2600, 0.5), (300, 5000, 0.004)]     # the last one gets a 5000-entry row: a direct tile
+
+
+@pytest.fixture(params=[1, 2], ids=["rowkernel", "tilekernel"])
+def kernel(request, ctx):
+    """force the row kernel / the TMA-staged tile kernel (the default picks by size: small matrices never reach the tiles)"""
+    ctx.set_option("sparse_kernel", request.param)
+    yield request.param
+    ctx.set_option("sparse_kernel", 0)
 
 
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
 @pytest.mark.parametrize("fmt", ["csc", "csr"])
-def test_sparse_apply_matches_oracle(lo, ctx, orc, dtype, fmt):
-    """prod!/tprod!/ctprod! of LinearOperator(M) for every lane-group width (mean row length 1 ... >= 32), empty and dense rows"""
+def test_sparse_apply_matches_oracle(lo, ctx, orc, dtype, fmt, kernel):
+    """prod!/tprod!/ctprod! of LinearOperator(M) for every lane-group width (mean row length 1 ... >= 32), empty and dense rows,
+    through both kernels"""
     import torch
     dt = tdtype(dtype)
     ndt = np.dtype(dtype)
@@ -106,12 +116,12 @@ def test_sparse_apply_matches_oracle(lo, ctx, orc, dtype, fmt):
 
 
 @pytest.mark.parametrize("fmt", ["csc", "csr"])
-def test_sparse_index_work_is_exact(lo, ctx, fmt):
+def test_sparse_index_work_is_exact(lo, ctx, fmt, kernel):
     """0/1 patterns and small-integer values: every product is exactly representable, so == must hold (structure
     transposition, pointer arithmetic, duplicate-free gather).  Includes Matrix(op) == A and Matrix(op') == A'."""
     import torch
     rng = np.random.default_rng(5)
-    for m, n, dens in ((10, 10, 0.2), (37, 91, 0.1), (1000, 333, 0.02), (5, 4000, 0.5)):
+    for m, n, dens in ((10, 10, 0.2), (37, 91, 0.1), (1000, 333, 0.02), (5, 4000, 0.5), (4001, 4003, 0.003)):
         A = sp.random(m, n, density=dens, random_state=rng, format="csc", data_rvs=lambda k: rng.integers(-8, 9, k).astype(np.float64))
         A.eliminate_zeros()
         M = to_torch(ctx, A, fmt)
@@ -127,7 +137,7 @@ def test_sparse_index_work_is_exact(lo, ctx, fmt):
 
 
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
-def test_sparse_edge_cases_and_errors(lo, ctx, orc, dtype):
+def test_sparse_edge_cases_and_errors(lo, ctx, orc, dtype, kernel):
     """nnz == 0, empty dimensions, β == 0 never reads res; malformed structure, CPU / COO matrices, shape and dtype mismatch"""
     import ctypes
     import torch
@@ -282,4 +292,19 @@ def test_sparse_large_matrix_properties(lo, ctx, orc, dtype):
     rhs = float(torch.dot(z.double(), v.double()))
     assert abs(lhs - rhs) <= tol * max(abs(lhs), 1.0) * 10
     assert torch.equal(op * v, y) and torch.equal(lo.transpose(op) * u, z)
+    # the default picked the TMA-staged tile kernel (25 K tiles); the row kernel must agree to rounding, and both are
+    # deterministic; values whose storage is off a 16-byte boundary fall back to the row kernel
+    ctx.set_option("sparse_kernel", 1)
+    try:
+        yr, zr = op * v, lo.transpose(op) * u
+        assert torch.equal(op * v, yr)
+    finally:
+        ctx.set_option("sparse_kernel", 0)
+    assert rel(host(yr), host(y)) <= (1e-14 if dtype == "float64" else 1e-6)
+    assert rel(host(zr), host(z)) <= (1e-14 if dtype == "float64" else 1e-6)
+    off = torch.empty(n * per_row + 1, dtype=dt, device=dev)[1:]
+    off.copy_(vals.reshape(-1))
+    Moff = torch.sparse_csr_tensor(crow, cols.reshape(-1), off, size=(n, n), device=dev)
+    if Moff.values().data_ptr() % 16 != 0:                                            # torch kept the view: unaligned storage
+        assert rel(host(lo.LinearOperator(Moff) * v), host(y)) <= (1e-14 if dtype == "float64" else 1e-6)
     assert op.apply_bytes() == n * per_row * (vals.element_size() + 4) + 8 * (n + 1) + 2 * n * vals.element_size()

@@ -122,14 +122,17 @@ def main():
                 v = torch.rand(nr, dtype=dtype, device=dev)
                 r = torch.empty(nr, dtype=dtype, device=dev)
                 nnz = int(vals.numel())
-                for trans, tag in ((False, "N"), (True, "T")):
-                    o = lo.transpose(op) if trans else op
-                    l0 = ctx.launch_count()
-                    lo.mul_(r, o, v)
-                    nl = ctx.launch_count() - l0
-                    ms = timeit(lambda: lo.mul_(r, o, v), 20)
-                    line("sparse %s %s rows=%d nnz=%d %s" % (tag, pat, nr, nnz, tn), ms, op.apply_bytes(trans), launches=nl,
-                         create_s=round(t_create, 2), nnz_per_s=round(nnz / (ms * 1e-3), 0))
+                for kern, kname in ((2, "tile kernel (TMA-staged)"), (1, "row kernel")):
+                    ctx.set_option("sparse_kernel", kern)
+                    for trans, tag in ((False, "N"), (True, "T")):
+                        o = lo.transpose(op) if trans else op
+                        l0 = ctx.launch_count()
+                        lo.mul_(r, o, v)
+                        nl = ctx.launch_count() - l0
+                        ms = timeit(lambda: lo.mul_(r, o, v), 20)
+                        line("sparse %s %s rows=%d nnz=%d %s, %s" % (tag, pat, nr, nnz, tn, kname), ms, op.apply_bytes(trans),
+                             launches=nl, create_s=round(t_create, 2), nnz_per_s=round(nnz / (ms * 1e-3), 0))
+                ctx.set_option("sparse_kernel", 0)
                 v2 = v[:, None].contiguous()
                 ms = timeit(lambda: torch.sparse.mm(M, v2), 20)
                 line("cusparse N %s %s (torch.sparse.mm, for comparison)" % (pat, tn), ms, op.apply_bytes(False))

@@ -43,6 +43,11 @@ def main():
     for op, v, u, r, rt in todo:
         lo.mul_(r, op, v)
         lo.mul_(rt, lo.transpose(op), u)
+    ctx = lo.default_context(0)
+    ctx.set_option("sparse_kernel", 1)          # the sparse row kernel beside the (default) tile kernel
+    for op, v, u, r, rt in todo[2:]:
+        lo.mul_(r, op, v)
+    ctx.set_option("sparse_kernel", 0)
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
     print("NCU_DENSE_DONE")
