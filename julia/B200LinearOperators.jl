@@ -7,7 +7,7 @@
 # adjoint/transpose) work unchanged.
 module B200LinearOperators
 
-using LinearOperators, CUDA, LinearAlgebra
+using LinearOperators, CUDA, LinearAlgebra, SparseArrays
 import LinearOperators: AbstractQuasiNewtonOperator, LinearOperatorException, storage_type, has_args5, isallocated5, reset!
 import Base: push!
 import LinearAlgebra: diag
@@ -72,6 +72,26 @@ function B200DenseOperator(M::CuMatrix{T}; symmetric = false, hermitian = false,
   finalizer(_ -> ccall((:b2o_dense_destroy, libb2o), Cint, (Ptr{Cvoid},), handle), op)
   return op
 end
+# ---- LinearOperator(M) for a sparse matrix (src/constructors.jl:3-5,15-29): colptr / rowval stay on the host (1-based, as
+# SparseMatrixCSC stores them), nzval lives on the device and is aliased; call refresh!(op) after changing nzval in place.
+function B200SparseOperator(M::SparseMatrixCSC{T, Int64}, nzval::CuVector{T}; symmetric = false, hermitian = false,
+                            c = ctx()) where {T <: Union{Float64, Float32}}
+  nrow, ncol = size(M)
+  length(nzval) == nnz(M) || throw(LinearOperatorException("nzval must hold nnz(M) device values"))
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:b2o_sparse_create, libb2o), Cint,
+    (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64}, CuPtr{Cvoid}, Ptr{Ptr{Cvoid}}),
+    c.handle, B2O_DTYPE[T], Cint(0), nrow, ncol, nnz(M), M.colptr, M.rowval, nzval, h))
+  handle = h[]
+  run(trans) = (res, v, α, β) -> check(ccall((:b2o_sparse_apply, libb2o), Cint,
+    (Ptr{Cvoid}, Cint, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, Int64, Cdouble, Cdouble),
+    handle, trans, res, length(res), v, length(v), α, β))
+  op = LinearOperator{T, CuVector{T}}(nrow, ncol, symmetric, hermitian, run(Cint(0)), run(Cint(1)), run(Cint(1)))
+  finalizer(_ -> ccall((:b2o_sparse_destroy, libb2o), Cint, (Ptr{Cvoid},), handle), op)
+  return op, () -> check(ccall((:b2o_sparse_refresh, libb2o), Cint, (Ptr{Cvoid},), handle))
+end
+B200SparseOperator(M::SparseMatrixCSC{T, Int64}; kw...) where {T} = B200SparseOperator(M, CuVector{T}(M.nzval); kw...)
+
 # BlockDiagonalOperator(A, B, C) of CuMatrix blocks (test/gpu/nvidia.jl:8-15): wrap the blocks first, the reference's
 # own block loop (src/special-operators.jl:258-267) then calls the closures above on the slab views.
 B200BlockDiagonalOperator(Ms::CuMatrix...; kw...) = BlockDiagonalOperator((B200DenseOperator(M; kw...) for M in Ms)...)

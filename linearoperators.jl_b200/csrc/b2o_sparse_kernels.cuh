@@ -86,35 +86,36 @@ __global__ void __launch_bounds__(SP_THREADS, SP_CTAS_PER_SM) spmv_rows_kernel(c
 }
 
 // ================================================================== TMA-staged tile kernel
-// The row kernel above is bound by its dependent load chain (ptr -> idx/val -> x: three DRAM/L2 latencies per row, measured
-// 47 % DRAM utilisation with the same duration for Float32 and Float64).  The tile kernel takes the two streaming legs off
-// that chain: the structure is cut ONCE, on the host at create time, into tiles of consecutive rows holding <= ST_C entries
-// and <= ST_RT rows; a producer warp stages each tile's idx / val / row-offset slices global -> shared with 1-D TMA bulk
-// copies (cp.async.bulk + mbarrier complete_tx) into a ring, several tiles ahead; 8 consumer warps
-//   (1) gather: thread t takes entries t, t+256, ... of the tile -- eight independent x[idx] gathers in flight per thread --
-//       and writes the products (double) in place over the staged values,
-//   (2) reduce: 2^LL lanes per row sum the row's products from shared memory in a fixed order (same butterfly as above),
-//       apply α / β and store y.
+// The row kernel above is bound by its dependent load chain (ptr -> idx/val -> x: two DRAM latencies and one L2 latency per
+// row batch; measured 47 % DRAM utilisation with the same duration for Float32 and Float64, about 2 us per warp pass).  The
+// tile kernel takes the two streaming legs off that chain: the structure is cut ONCE, on the host at create time, into
+// tiles of consecutive rows holding <= ST_C entries and <= ST_RT rows; a producer warp stages each tile's idx / val /
+// row-offset slices global -> shared with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx) into a ring, tiles
+// ahead of their use.  The consumer warps then run the row kernel's inner step against SHARED memory: 2^LL lanes per row,
+// four predicated (idx, val) pairs per lane from the staged slices, their four gathers from x in flight together, fixed-
+// order butterfly, α / β, store.  Row batches are dealt round-robin to the warps across tiles and the warps only meet at the
+// slot's "empty" barrier, so nobody waits inside a tile.  (A first version gathered tile-wide into shared products with a
+// CTA barrier between gather and row sums: 0.28 ms against the row kernel's 0.19 ms -- the barrier exposes the slowest of
+// 2048 gathers per tile; profiles/r1_sparse_tilekernel_v1.jsonl.)
 // No atomics, fixed order -> bit-reproducible.  Bulk copies need 16-byte aligned sources: a tile's copy starts at its first
 // entry rounded down to a multiple of 4 and is clamped to the last whole quad of the array (entries beyond it, at most 3, are
 // read straight from global memory); row-offset slices start at an even row.  A row longer than ST_C is a "direct" tile:
-// the 256 consumer threads sum it straight from global memory (fixed-order block reduction).
+// all consumer threads sum it straight from global memory (fixed-order block reduction).
 constexpr int ST_C = 2048;                     // entries per tile (including <= 3 leading alignment entries)
 constexpr int ST_RT = 1024;                    // rows per tile
-constexpr int ST_NCONS = 256;                  // consumer threads
+constexpr int ST_NCONS = 384;                  // consumer threads (12 warps; 2 CTAs per SM)
 constexpr int ST_CONS_WARPS = ST_NCONS / 32;
 constexpr int ST_NTHREADS = ST_NCONS + 32;     // + producer warp
 constexpr int ST_STAGES = 3;
 constexpr int ST_CTAS_PER_SM = 2;
-constexpr int ST_EPT = ST_C / ST_NCONS;        // entries per consumer thread and tile
-// one ring stage: idx[ST_C] int32 | val / products [ST_C] 8 bytes each | row offsets [ST_RT + 2] int64
+// one ring stage: idx[ST_C] int32 | val[ST_C] (8 bytes reserved per entry) | row offsets [ST_RT + 2] int64
 constexpr size_t ST_IDX_OFF = 0;
 constexpr size_t ST_VAL_OFF = ST_IDX_OFF + sizeof(int32_t) * ST_C;
 constexpr size_t ST_PTR_OFF = ST_VAL_OFF + sizeof(double) * ST_C;
 constexpr size_t ST_STAGE_BYTES = ST_PTR_OFF + sizeof(int64_t) * (ST_RT + 2);
 constexpr size_t ST_BAR_OFF = ST_STAGE_BYTES * ST_STAGES;
 constexpr size_t ST_SMEM_BYTES = ST_BAR_OFF + sizeof(uint64_t) * 2 * ST_STAGES;
-static_assert(ST_STAGE_BYTES % 16 == 0 && ST_C % 4 == 0 && ST_C % ST_NCONS == 0, "tile layout");
+static_assert(ST_STAGE_BYTES % 16 == 0 && ST_C % 4 == 0, "tile layout");
 
 struct SpTile {      // 16 bytes; tiles[ntiles] is a sentinel {nnz, nrows, 0}
   int64_t e0;        // first entry staged (multiple of 4, <= ptr[r0]); direct tile: ptr[r0]
@@ -209,6 +210,7 @@ __global__ void __launch_bounds__(ST_NTHREADS, ST_CTAS_PER_SM) spmv_tiles_kernel
   const int group_in_warp = lane32 >> LL;
   if (tb >= te) return;
   SpTile cur = p.tiles[tb], nxt = p.tiles[tb + 1];
+  int batch_base = 0;
   for (int64_t t = tb; t < te; ++t) {
     const SpTile nn = p.tiles[t + 2 <= p.ntiles ? t + 2 : p.ntiles];
     const int64_t r0 = cur.r0, r1 = nxt.r0;
@@ -258,50 +260,21 @@ __global__ void __launch_bounds__(ST_NTHREADS, ST_CTAS_PER_SM) spmv_tiles_kernel
     unsigned char *stage = smem_raw + (size_t)slot * ST_STAGE_BYTES;
     const int32_t *sidx = reinterpret_cast<const int32_t *>(stage + ST_IDX_OFF);
     const T *sval = reinterpret_cast<const T *>(stage + ST_VAL_OFF);
-    double *sprod = reinterpret_cast<double *>(stage + ST_VAL_OFF);
     const int64_t *sptr = reinterpret_cast<const int64_t *>(stage + ST_PTR_OFF) + (r0 & 1);      // sptr[i] = ptr[r0 + i]
     mbar_wait(&full[slot], par);
     const int64_t e0 = cur.e0;
-    const int lead = (int)(sptr[0] - e0);                          // 0..3 alignment entries in front of the first row
-    const int used = (int)(sptr[r1 - r0] - e0);                    // one past the last entry of the tile's rows
     int64_t avail = p.q_tail - e0;                                 // entries of this tile the bulk copies may cover
     avail = avail < 0 ? 0 : avail;
     const int staged = (int)(avail < (int64_t)cur.ne ? avail : (int64_t)cur.ne);
-    // ---- (1) gather: ST_EPT products per thread, all x loads issued before the first multiply
-    int32_t ci[ST_EPT];
-    T ca[ST_EPT], cx[ST_EPT];
-#pragma unroll
-    for (int u = 0; u < ST_EPT; ++u) {
-      const int j = u * ST_NCONS + tid;
-      const bool ok = j >= lead && j < used;
-      ci[u] = 0;
-      ca[u] = (T)0;
-      if (ok) {
-        if (j < staged) {
-          ci[u] = sidx[j];
-          ca[u] = sval[j];
-        } else {                                                   // the <= 3 entries beyond the last whole quad of the arrays
-          ci[u] = __ldg(p.idx + e0 + j);
-          ca[u] = __ldg(val + e0 + j);
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < ST_EPT; ++u) {
-      const int j = u * ST_NCONS + tid;
-      cx[u] = (j >= lead && j < used) ? __ldg(x + ci[u]) : (T)0;
-    }
-    if (sizeof(T) < sizeof(double)) st_consumers_sync();           // Float32: products (8 bytes) overlay two staged values
-#pragma unroll
-    for (int u = 0; u < ST_EPT; ++u) {
-      const int j = u * ST_NCONS + tid;
-      if (j < used) sprod[j] = (double)ca[u] * (double)cx[u];
-    }
-    st_consumers_sync();
-    // ---- (2) reduce: L lanes per row, fixed order
     const int nr = (int)(r1 - r0);
-    for (int rr0 = warp * GROUPS_PER_WARP; rr0 < nr; rr0 += ST_CONS_WARPS * GROUPS_PER_WARP) {
-      const int rr = rr0 + group_in_warp;
+    const int nb = (nr + GROUPS_PER_WARP - 1) / GROUPS_PER_WARP;   // row batches of this tile (one batch = one warp pass)
+    // batches are dealt round-robin to the consumer warps ACROSS tiles (batch_base counts them modulo the warp count), so
+    // the warps stay balanced although a tile rarely holds a multiple of ST_CONS_WARPS batches; warps never wait for each
+    // other inside a tile -- a fast warp moves on to the next staged tile
+    int b = warp - batch_base;
+    b += b < 0 ? ST_CONS_WARPS : 0;
+    for (; b < nb; b += ST_CONS_WARPS) {
+      const int rr = b * GROUPS_PER_WARP + group_in_warp;
       const bool valid = rr < nr;
       int start = 0, end = 0;
       if (valid) {
@@ -310,11 +283,29 @@ __global__ void __launch_bounds__(ST_NTHREADS, ST_CTAS_PER_SM) spmv_tiles_kernel
       }
       double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
       for (int k = start + lane; k < end; k += 4 * L) {
-        const int k1 = k + L, k2 = k + 2 * L, k3 = k + 3 * L;
-        s0 += sprod[k];
-        s1 += k1 < end ? sprod[k1] : 0.0;
-        s2 += k2 < end ? sprod[k2] : 0.0;
-        s3 += k3 < end ? sprod[k3] : 0.0;
+        int32_t ci[4];
+        T ca[4], cx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int jj = k + u * L;
+          ci[u] = 0;
+          ca[u] = (T)0;
+          if (jj < end) {
+            if (jj < staged) {
+              ci[u] = sidx[jj];
+              ca[u] = sval[jj];
+            } else {                                               // the <= 3 entries beyond the last whole quad of the arrays
+              ci[u] = __ldg(p.idx + e0 + jj);
+              ca[u] = __ldg(val + e0 + jj);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cx[u] = (k + u * L < end) ? __ldg(x + ci[u]) : (T)0;
+        s0 = fma((double)ca[0], (double)cx[0], s0);
+        s1 = fma((double)ca[1], (double)cx[1], s1);
+        s2 = fma((double)ca[2], (double)cx[2], s2);
+        s3 = fma((double)ca[3], (double)cx[3], s3);
       }
       double s = (s0 + s1) + (s2 + s3);
 #pragma unroll
@@ -326,9 +317,8 @@ __global__ void __launch_bounds__(ST_NTHREADS, ST_CTAS_PER_SM) spmv_tiles_kernel
         y[r] = (T)tv;
       }
     }
-    // hand the slot back: all reads of this warp are done; its product stores (generic proxy) are ordered before the bulk copy
-    // (async proxy) that refills the slot
-    fence_proxy_async_smem();
+    batch_base = (batch_base + nb) % ST_CONS_WARPS;
+    // hand the slot back: all shared-memory reads of this warp are done
     __syncwarp();
     if (lane32 == 0) mbar_arrive(&empty[slot]);
     if (++slot == ST_STAGES) {
@@ -432,11 +422,6 @@ static inline int64_t spmv_build_tiles(const int64_t *ptr, int64_t nrows, int64_
   sentinel.ne = 0;
   out.push_back(sentinel);
   return ntiles;
-}
-
-// the tile kernel pays off when every SM gets several tiles and the arrays can be bulk-copied (16-byte aligned values)
-static inline bool spmv_tiles_eligible(int num_sms, int64_t ntiles, const void *val) {
-  return ntiles >= 4 * (int64_t)num_sms * ST_CTAS_PER_SM && ((uintptr_t)val & 15) == 0;
 }
 
 template <typename T>
