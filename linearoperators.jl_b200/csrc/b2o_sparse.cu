@@ -184,13 +184,16 @@ extern "C" int b2o_sparse_apply(b2o_sparse *s, int trans, void *res, int64_t res
   if (tiles) {
     if (s->dtype == B2O_F64)
       return spmv_tiles_run_impl<double>(c->num_sms, c->stream, &c->launches, s->tiles[o], s->ntiles[o], s->ptr[o], s->idx[o],
-                                         s->val[o], out_len, s->nnz, res, v, alpha, beta);
+                                         s->val[o], out_len, s->nnz, res, v, alpha, beta, c->sparse_lanes);
     return spmv_tiles_run_impl<float>(c->num_sms, c->stream, &c->launches, s->tiles[o], s->ntiles[o], s->ptr[o], s->idx[o],
-                                      s->val[o], out_len, s->nnz, res, v, alpha, beta);
+                                      s->val[o], out_len, s->nnz, res, v, alpha, beta, c->sparse_lanes);
   }
+  const bool pipe = c->sparse_kernel == 3;
   if (s->dtype == B2O_F64)
-    return spmv_run_impl<double>(c->num_sms, c->stream, &c->launches, s->ptr[o], s->idx[o], s->val[o], out_len, s->nnz, res, v, alpha, beta);
-  return spmv_run_impl<float>(c->num_sms, c->stream, &c->launches, s->ptr[o], s->idx[o], s->val[o], out_len, s->nnz, res, v, alpha, beta);
+    return spmv_run_impl<double>(c->num_sms, c->stream, &c->launches, s->ptr[o], s->idx[o], s->val[o], out_len, s->nnz, res, v, alpha, beta,
+                                 pipe, c->sparse_lanes);
+  return spmv_run_impl<float>(c->num_sms, c->stream, &c->launches, s->ptr[o], s->idx[o], s->val[o], out_len, s->nnz, res, v, alpha, beta,
+                              pipe, c->sparse_lanes);
 }
 
 extern "C" int b2o_sparse_apply_bytes(b2o_sparse *s, int trans, double beta, double *bytes) {

@@ -85,6 +85,116 @@ __global__ void __launch_bounds__(SP_THREADS, SP_CTAS_PER_SM) spmv_rows_kernel(c
   }
 }
 
+// Software-pipelined variant of the row kernel (sparse_kernel = 3): the first four (idx, val) pairs of a lane's NEXT row are
+// loaded into registers while the gathers of the CURRENT row are in flight, so a pass waits for one memory latency (x)
+// instead of two in a row (idx -> x).  Costs registers (one resident CTA fewer per SM); pays off when the gathers from x are
+// local (L1 / L2 hits) and the pass is latency-bound.  Same lane layout, same summation order as spmv_rows_kernel: the two
+// produce identical bits.
+constexpr int SP_PIPE_CTAS_PER_SM = 4;
+template <typename T, int LL>
+__global__ void __launch_bounds__(SP_THREADS, SP_PIPE_CTAS_PER_SM) spmv_rows_pipe_kernel(const __grid_constant__ SpmvArgs p) {
+  constexpr int L = 1 << LL;
+  constexpr int GROUPS_PER_WARP = 32 >> LL;
+  const T *__restrict__ val = (const T *)p.val;
+  const T *__restrict__ x = (const T *)p.x;
+  const int32_t *__restrict__ idx = p.idx;
+  T *y = (T *)p.y;
+  const int lane = threadIdx.x & (L - 1);
+  const int64_t warp_id = ((int64_t)blockIdx.x * SP_THREADS + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * SP_THREADS) >> 5;
+  const int group_in_warp = (threadIdx.x & 31) >> LL;
+  const int64_t step = nwarps * GROUPS_PER_WARP;
+  int64_t r0 = warp_id * GROUPS_PER_WARP;
+  // pipeline registers: offsets two rows ahead, first-trip entries one row ahead
+  int64_t start = 0, end = 0, nstart = 0, nend = 0;
+  int32_t ci[4] = {0, 0, 0, 0};
+  T ca[4] = {(T)0, (T)0, (T)0, (T)0};
+  {
+    const int64_t r = r0 + group_in_warp;
+    if (r < p.nrows) {
+      start = __ldg(p.ptr + r);
+      end = __ldg(p.ptr + r + 1);
+    }
+    if (r + step < p.nrows) {
+      nstart = __ldg(p.ptr + r + step);
+      nend = __ldg(p.ptr + r + step + 1);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t k = start + lane + u * L;
+      if (k < end) {
+        ci[u] = __ldg(idx + k);
+        ca[u] = __ldg(val + k);
+      }
+    }
+  }
+  for (; r0 < p.nrows; r0 += step) {
+    const int64_t r = r0 + group_in_warp;
+    const bool valid = r < p.nrows;
+    // offsets two rows ahead, entries of the next row
+    int64_t n2start = 0, n2end = 0;
+    if (r + 2 * step < p.nrows) {
+      n2start = __ldg(p.ptr + r + 2 * step);
+      n2end = __ldg(p.ptr + r + 2 * step + 1);
+    }
+    int32_t ni[4] = {0, 0, 0, 0};
+    T na[4] = {(T)0, (T)0, (T)0, (T)0};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t k = nstart + lane + u * L;
+      if (k < nend) {
+        ni[u] = __ldg(idx + k);
+        na[u] = __ldg(val + k);
+      }
+    }
+    // current row: first trip from the pipeline registers
+    T cx[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) cx[u] = (start + lane + u * L < end) ? __ldg(x + ci[u]) : (T)0;
+    double s0 = fma((double)ca[0], (double)cx[0], 0.0);
+    double s1 = fma((double)ca[1], (double)cx[1], 0.0);
+    double s2 = fma((double)ca[2], (double)cx[2], 0.0);
+    double s3 = fma((double)ca[3], (double)cx[3], 0.0);
+    for (int64_t k = start + lane + 4 * (int64_t)L; k < end; k += 4 * (int64_t)L) {      // rows longer than 4 L entries
+      const int64_t k1 = k + L, k2 = k + 2 * L, k3 = k + 3 * L;
+      const bool p1 = k1 < end, p2 = k2 < end, p3 = k3 < end;
+      const int32_t i0 = __ldg(idx + k);
+      const int32_t i1 = p1 ? __ldg(idx + k1) : 0;
+      const int32_t i2 = p2 ? __ldg(idx + k2) : 0;
+      const int32_t i3 = p3 ? __ldg(idx + k3) : 0;
+      const T a0 = __ldg(val + k);
+      const T a1 = p1 ? __ldg(val + k1) : (T)0;
+      const T a2 = p2 ? __ldg(val + k2) : (T)0;
+      const T a3 = p3 ? __ldg(val + k3) : (T)0;
+      const T x0 = __ldg(x + i0);
+      const T x1 = p1 ? __ldg(x + i1) : (T)0;
+      const T x2 = p2 ? __ldg(x + i2) : (T)0;
+      const T x3 = p3 ? __ldg(x + i3) : (T)0;
+      s0 = fma((double)a0, (double)x0, s0);
+      s1 = fma((double)a1, (double)x1, s1);
+      s2 = fma((double)a2, (double)x2, s2);
+      s3 = fma((double)a3, (double)x3, s3);
+    }
+    double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+    for (int o = L >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (valid && lane == 0) {
+      double t = p.alpha * s;
+      if (p.beta != 0.0) t += p.beta * (double)y[r];
+      y[r] = (T)t;
+    }
+    start = nstart;
+    end = nend;
+    nstart = n2start;
+    nend = n2end;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      ci[u] = ni[u];
+      ca[u] = na[u];
+    }
+  }
+}
+
 // ================================================================== TMA-staged tile kernel
 // The row kernel above is bound by its dependent load chain (ptr -> idx/val -> x: two DRAM latencies and one L2 latency per
 // row batch; measured 47 % DRAM utilisation with the same duration for Float32 and Float64, about 2 us per warp pass).  The
@@ -346,15 +456,17 @@ static inline int spmv_lanes_log2(int64_t nrows, int64_t nnz) {
   while (l < 5 && ((int64_t)1 << l) < want) ++l;
   return l;
 }
-static inline int64_t spmv_grid(int num_sms, int64_t nrows, int lanes_log2) {
+static inline int64_t spmv_grid(int num_sms, int64_t nrows, int lanes_log2, int ctas_per_sm) {
   const int64_t threads = std::max<int64_t>(1, nrows) << lanes_log2;
   const int64_t want = (threads + SP_THREADS - 1) / SP_THREADS;
-  return std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms * SP_CTAS_PER_SM));   // one resident wave, rows grid-strided
+  return std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms * ctas_per_sm));   // one resident wave, rows grid-strided
 }
 
+// pipe: the software-pipelined variant; lanes_override >= 0 forces the lane-group width 2^lanes_override (tuning / tests)
 template <typename T>
 static int spmv_run_impl(int num_sms, B2O_STREAM_T stream, int64_t *launches, const int64_t *ptr, const int32_t *idx, const void *val,
-                         int64_t nrows, int64_t nnz, void *y, const void *x, double alpha, double beta) {
+                         int64_t nrows, int64_t nnz, void *y, const void *x, double alpha, double beta, bool pipe = false,
+                         int lanes_override = -1) {
   if (nrows == 0) return B2O_OK;
   SpmvArgs a;
   a.ptr = ptr;
@@ -365,17 +477,18 @@ static int spmv_run_impl(int num_sms, B2O_STREAM_T stream, int64_t *launches, co
   a.nrows = nrows;
   a.alpha = alpha;
   a.beta = beta;
-  a.lanes_log2 = spmv_lanes_log2(nrows, nnz);
+  a.lanes_log2 = (lanes_override >= 0 && lanes_override <= 5) ? lanes_override : spmv_lanes_log2(nrows, nnz);
   void (*kern)(const SpmvArgs) = nullptr;
   switch (a.lanes_log2) {
-    case 0: kern = spmv_rows_kernel<T, 0>; break;
-    case 1: kern = spmv_rows_kernel<T, 1>; break;
-    case 2: kern = spmv_rows_kernel<T, 2>; break;
-    case 3: kern = spmv_rows_kernel<T, 3>; break;
-    case 4: kern = spmv_rows_kernel<T, 4>; break;
-    default: kern = spmv_rows_kernel<T, 5>; break;
+    case 0: kern = pipe ? spmv_rows_pipe_kernel<T, 0> : spmv_rows_kernel<T, 0>; break;
+    case 1: kern = pipe ? spmv_rows_pipe_kernel<T, 1> : spmv_rows_kernel<T, 1>; break;
+    case 2: kern = pipe ? spmv_rows_pipe_kernel<T, 2> : spmv_rows_kernel<T, 2>; break;
+    case 3: kern = pipe ? spmv_rows_pipe_kernel<T, 3> : spmv_rows_kernel<T, 3>; break;
+    case 4: kern = pipe ? spmv_rows_pipe_kernel<T, 4> : spmv_rows_kernel<T, 4>; break;
+    default: kern = pipe ? spmv_rows_pipe_kernel<T, 5> : spmv_rows_kernel<T, 5>; break;
   }
-  B2O_LAUNCH(kern, dim3((unsigned)spmv_grid(num_sms, nrows, a.lanes_log2)), dim3(SP_THREADS), 0, stream, a);
+  B2O_LAUNCH(kern, dim3((unsigned)spmv_grid(num_sms, nrows, a.lanes_log2, pipe ? SP_PIPE_CTAS_PER_SM : SP_CTAS_PER_SM)),
+             dim3(SP_THREADS), 0, stream, a);
   ++*launches;
   B2O_CUDA(cudaGetLastError());
   return B2O_OK;
@@ -427,7 +540,7 @@ static inline int64_t spmv_build_tiles(const int64_t *ptr, int64_t nrows, int64_
 template <typename T>
 static int spmv_tiles_run_impl(int num_sms, B2O_STREAM_T stream, int64_t *launches, const SpTile *tiles, int64_t ntiles,
                                const int64_t *ptr, const int32_t *idx, const void *val, int64_t nrows, int64_t nnz, void *y,
-                               const void *x, double alpha, double beta) {
+                               const void *x, double alpha, double beta, int lanes_override = -1) {
   if (nrows == 0 || ntiles == 0) return B2O_OK;
   SpTileArgs a;
   a.tiles = tiles;
@@ -442,7 +555,7 @@ static int spmv_tiles_run_impl(int num_sms, B2O_STREAM_T stream, int64_t *launch
   a.alpha = alpha;
   a.beta = beta;
   void (*kern)(const SpTileArgs) = nullptr;
-  switch (spmv_lanes_log2(nrows, nnz)) {
+  switch ((lanes_override >= 0 && lanes_override <= 5) ? lanes_override : spmv_lanes_log2(nrows, nnz)) {
     case 0: kern = spmv_tiles_kernel<T, 0>; break;
     case 1: kern = spmv_tiles_kernel<T, 1>; break;
     case 2: kern = spmv_tiles_kernel<T, 2>; break;

@@ -15,7 +15,7 @@ EMU_API const char *emu_sparse_last_error() { return emu::last_error.c_str(); }
 // fmt 0 CSC / 1 CSR with 1-based host arrays, exactly the arguments of b2o_sparse_create; one product like b2o_sparse_apply
 EMU_API int emu_sparse_apply(int dtype, int fmt, int64_t m, int64_t n, int64_t nnz, const int64_t *ptr1, const int64_t *idx1,
                              const void *vals, int trans, void *res, const void *v, double alpha, double beta, int num_sms,
-                             int64_t *launches, int *lanes_log2, int kernel, int64_t *ntiles_out) {
+                             int64_t *launches, int *lanes_log2, int kernel, int64_t *ntiles_out, int lanes_override) {
   const int64_t np = fmt == 0 ? n : m, nd = fmt == 0 ? m : n;
   std::vector<int64_t> gptr(np + 1), tptr(nd + 1, 0), perm(std::max<int64_t>(nnz, 1));
   std::vector<int32_t> gidx(std::max<int64_t>(nnz, 1)), tidx(std::max<int64_t>(nnz, 1));
@@ -49,7 +49,7 @@ EMU_API int emu_sparse_apply(int dtype, int fmt, int64_t m, int64_t n, int64_t n
   const int32_t *idx = o == given ? gidx.data() : tidx.data();
   const void *val = o == given ? vals : (const void *)tval.data();
   const int64_t out_len = trans ? n : m;
-  *lanes_log2 = spmv_lanes_log2(out_len, nnz);
+  *lanes_log2 = lanes_override >= 0 ? lanes_override : spmv_lanes_log2(out_len, nnz);
   *ntiles_out = 0;
   if (kernel == 2) {
     // the TMA-staged tile kernel: offsets padded with zeros like b2o_sparse_create, every staged array 16-byte aligned
@@ -68,16 +68,20 @@ EMU_API int emu_sparse_apply(int dtype, int fmt, int64_t m, int64_t n, int64_t n
     void *aval = aligned(val, E * nnz, E * nnz);                  // exact size: reads past nnz would be caught by ASan builds
     int rc;
     if (dtype == B2O_F64)
-      rc = spmv_tiles_run_impl<double>(num_sms, nullptr, launches, tiles.data(), ntiles, aptr, aidx, aval, out_len, nnz, res, v, alpha, beta);
+      rc = spmv_tiles_run_impl<double>(num_sms, nullptr, launches, tiles.data(), ntiles, aptr, aidx, aval, out_len, nnz, res, v, alpha, beta,
+                                       lanes_override);
     else
-      rc = spmv_tiles_run_impl<float>(num_sms, nullptr, launches, tiles.data(), ntiles, aptr, aidx, aval, out_len, nnz, res, v, alpha, beta);
+      rc = spmv_tiles_run_impl<float>(num_sms, nullptr, launches, tiles.data(), ntiles, aptr, aidx, aval, out_len, nnz, res, v, alpha, beta,
+                                      lanes_override);
     free(aptr);
     free(aidx);
     free(aval);
     return rc;
   }
-  if (dtype == B2O_F64) return spmv_run_impl<double>(num_sms, nullptr, launches, ptr, idx, val, out_len, nnz, res, v, alpha, beta);
-  return spmv_run_impl<float>(num_sms, nullptr, launches, ptr, idx, val, out_len, nnz, res, v, alpha, beta);
+  const bool pipe = kernel == 3;       // the software-pipelined row kernel
+  if (dtype == B2O_F64)
+    return spmv_run_impl<double>(num_sms, nullptr, launches, ptr, idx, val, out_len, nnz, res, v, alpha, beta, pipe, lanes_override);
+  return spmv_run_impl<float>(num_sms, nullptr, launches, ptr, idx, val, out_len, nnz, res, v, alpha, beta, pipe, lanes_override);
 }
 
 // the tile cut of a 0-based offset array (spmv_build_tiles of the product): descriptors flattened to (e0, r0, ne) triples

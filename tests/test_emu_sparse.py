@@ -29,7 +29,7 @@ def emu():
     vp, i64, i32, d = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double
     L.emu_sparse_apply.restype = i32
     L.emu_sparse_apply.argtypes = [i32, i32, i64, i64, i64, vp, vp, vp, i32, vp, vp, d, d, i32, ctypes.POINTER(i64),
-                                   ctypes.POINTER(i32), i32, ctypes.POINTER(i64)]
+                                   ctypes.POINTER(i32), i32, ctypes.POINTER(i64), i32]
     L.emu_sparse_tiles.restype = i64
     L.emu_sparse_tiles.argtypes = [vp, i64, i64, vp, i64, ctypes.POINTER(i32), ctypes.POINTER(i32)]
     return L
@@ -65,7 +65,7 @@ def test_spmv_kernel_matches_oracle(emu, orc, dtype, fmt):
     assert {0, 1, 2, 3, 4, 5} <= seen          # every lane-group width 1..32 was exercised
 
 
-def run_checked(emu, orc, A, dtype, fmt, trans, alpha, beta, num_sms=2, seed=0, kernel=1, want_tiles=None):
+def run_checked(emu, orc, A, dtype, fmt, trans, alpha, beta, num_sms=2, seed=0, kernel=1, want_tiles=None, force_lanes=-1, out=None):
     """one product through the emulated row kernel (kernel=1) or TMA-staged tile kernel (kernel=2), checked against the
     oracle and, independently, scipy; the starting res is regenerated for β != 0"""
     dt = np.float64 if dtype == F64 else np.float32
@@ -88,8 +88,10 @@ def run_checked(emu, orc, A, dtype, fmt, trans, alpha, beta, num_sms=2, seed=0, 
     launches, lanes, ntiles = ctypes.c_int64(), ctypes.c_int(), ctypes.c_int64()
     rc = emu.emu_sparse_apply(dtype, fmt, m, n, S.nnz, ptr1.ctypes.data, idx1.ctypes.data, vals.ctypes.data, trans,
                               res.ctypes.data, v.ctypes.data, alpha, beta, num_sms, ctypes.byref(launches), ctypes.byref(lanes),
-                              kernel, ctypes.byref(ntiles))
+                              kernel, ctypes.byref(ntiles), force_lanes)
     assert rc == 0
+    if out is not None:
+        out.append(res.copy())
     if want_tiles is not None:
         assert ntiles.value >= want_tiles, (ntiles.value, want_tiles)
     tol = 1e-13 if dtype == F64 else 2e-6
@@ -205,3 +207,28 @@ def test_tile_kernel_matches_oracle(emu, orc, dtype):
         for trans in (0, 1):
             run_checked(emu, orc, Z, dtype, 0, trans, 1.0, 0.0, kernel=2)
             run_checked(emu, orc, Z, dtype, 0, trans, 3.0, 2.0, seed=3, kernel=2)
+
+
+@pytest.mark.parametrize("dtype", [F64, F32])
+def test_pipelined_row_kernel_and_forced_lane_widths(emu, orc, dtype):
+    """the software-pipelined row kernel (sparse_kernel = 3) gives the SAME BITS as the plain row kernel (same lane layout and
+    summation order), also with more CTAs than rows, rows longer than one trip, empty rows; any forced lane-group width
+    (sparse_lanes) stays within the oracle's tolerance for all three kernels"""
+    dt = np.float64 if dtype == F64 else np.float32
+    mats = [random_sparse(300, 200, 0.02, 4, dt, empty_rows=(0, 7, 299)), random_sparse(64, 500, 0.12, 5, dt, dense_row=10),
+            random_sparse(2500, 40, 0.1, 6, dt), sp.identity(700, dtype=dt, format="csc") * 0.5, random_sparse(5, 3000, 0.6, 8, dt)]
+    for k, M in enumerate(mats):
+        M = sp.csc_matrix(M)
+        M.eliminate_zeros()
+        for trans in (0, 1):
+            for (alpha, beta) in ((1.0, 0.0), (2.0, -0.5)):
+                a, b = [], []
+                run_checked(emu, orc, M, dtype, 0, trans, alpha, beta, seed=k, kernel=1, out=a)
+                run_checked(emu, orc, M, dtype, 0, trans, alpha, beta, seed=k, kernel=3, out=b)
+                assert np.array_equal(a[0], b[0], equal_nan=True), (k, trans)
+        for lanes in (0, 2, 5):
+            a, b = [], []
+            run_checked(emu, orc, M, dtype, 1, 0, 1.0, 0.0, seed=k, kernel=1, force_lanes=lanes, out=a)
+            run_checked(emu, orc, M, dtype, 1, 0, 1.0, 0.0, seed=k, kernel=3, force_lanes=lanes, out=b)
+            assert np.array_equal(a[0], b[0], equal_nan=True)
+            run_checked(emu, orc, M, dtype, 1, 0, 1.0, 0.0, seed=k, kernel=2, force_lanes=lanes)

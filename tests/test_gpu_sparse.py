@@ -77,9 +77,9 @@ CASES = [(10, 6, 0.5), (6, 10, 0.5), (200, 300, 0.004), (300, 200, 0.02), (150, 
          (64, 3000, 0.01), (129, 2600, 0.5), (300, 5000, 0.004)]     # the last one gets a 5000-entry row: a direct tile
 
 
-@pytest.fixture(params=[1, 2], ids=["rowkernel", "tilekernel"])
+@pytest.fixture(params=[1, 2, 3], ids=["rowkernel", "tilekernel", "pipekernel"])
 def kernel(request, ctx):
-    """force the row kernel (the default) / the opt-in TMA-staged tile kernel"""
+    """force the row kernel (the default) / the opt-in TMA-staged tile kernel / the software-pipelined row kernel"""
     ctx.set_option("sparse_kernel", request.param)
     yield request.param
     ctx.set_option("sparse_kernel", 0)
@@ -302,6 +302,14 @@ def test_sparse_large_matrix_properties(lo, ctx, orc, dtype):
         ctx.set_option("sparse_kernel", 0)
     assert rel(host(yr), host(y)) <= (1e-14 if dtype == "float64" else 1e-6)
     assert rel(host(zr), host(z)) <= (1e-14 if dtype == "float64" else 1e-6)
+    ctx.set_option("sparse_kernel", 3)                                                # pipelined row kernel: the same bits
+    try:
+        assert torch.equal(op * v, y) and torch.equal(lo.transpose(op) * u, z)
+        ctx.set_option("sparse_lanes", 1)                                             # another lane-group width: rounding only
+        assert rel(host(op * v), host(y)) <= (1e-14 if dtype == "float64" else 1e-6)
+    finally:
+        ctx.set_option("sparse_lanes", -1)
+        ctx.set_option("sparse_kernel", 0)
     off = torch.empty(n * per_row + 1, dtype=dt, device=dev)[1:]
     off.copy_(vals.reshape(-1))
     Moff = torch.sparse_csr_tensor(crow, cols.reshape(-1), off, size=(n, n), device=dev)

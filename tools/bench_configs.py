@@ -27,6 +27,17 @@ def timeit(fn, steps, warmup=3, flush=None):
             flush.zero_()
         fn()
     torch.cuda.synchronize()
+    if flush is None:
+        # working set >> L2: time `steps` back-to-back launches between ONE pair of events.  Timing each launch on its own
+        # charges the host's call overhead (~20-30 us through the Python mirror) to kernels that finish in ~100 us, because
+        # the GPU sits idle between the first event and the launch.
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1) / steps
     tot = 0.0
     for _ in range(steps):
         if flush is not None:
@@ -122,19 +133,28 @@ def main():
                 v = torch.rand(nr, dtype=dtype, device=dev)
                 r = torch.empty(nr, dtype=dtype, device=dev)
                 nnz = int(vals.numel())
-                for kern, kname in ((2, "tile kernel (TMA-staged)"), (1, "row kernel")):
+                knames = {1: "row kernel", 2: "tile kernel (TMA-staged)", 3: "pipelined row kernel"}
+                auto = max(0, min(5, int(np.ceil(np.log2(max(1.0, np.ceil(np.ceil(nnz / nr) / 4.0)))))))
+                for kern in (1, 3, 2):
                     ctx.set_option("sparse_kernel", kern)
                     for trans, tag in ((False, "N"), (True, "T")):
                         o = lo.transpose(op) if trans else op
                         l0 = ctx.launch_count()
                         lo.mul_(r, o, v)
                         nl = ctx.launch_count() - l0
-                        ms = timeit(lambda: lo.mul_(r, o, v), 20)
-                        line("sparse %s %s rows=%d nnz=%d %s, %s" % (tag, pat, nr, nnz, tn, kname), ms, op.apply_bytes(trans),
-                             launches=nl, create_s=round(t_create, 2), nnz_per_s=round(nnz / (ms * 1e-3), 0))
+                        ms = timeit(lambda: lo.mul_(r, o, v), 50)
+                        line("sparse %s %s rows=%d nnz=%d %s, %s" % (tag, pat, nr, nnz, tn, knames[kern]), ms, op.apply_bytes(trans),
+                             launches=nl, create_s=round(t_create, 2), nnz_per_s=round(nnz / (ms * 1e-3), 0), lanes_log2=auto)
+                    # lane-group width sweep around the heuristic's choice (2^k lanes per row)
+                    for k in sorted({max(0, auto - 2), max(0, auto - 1), min(5, auto + 1), min(5, auto + 2)} - {auto}):
+                        ctx.set_option("sparse_lanes", k)
+                        ms = timeit(lambda: lo.mul_(r, op, v), 50)
+                        line("sparse N %s %s, %s, forced 2^%d lanes per row" % (pat, tn, knames[kern], k), ms, op.apply_bytes(False),
+                             lanes_log2=k)
+                    ctx.set_option("sparse_lanes", -1)
                 ctx.set_option("sparse_kernel", 0)
                 v2 = v[:, None].contiguous()
-                ms = timeit(lambda: torch.sparse.mm(M, v2), 20)
+                ms = timeit(lambda: torch.sparse.mm(M, v2), 50)
                 line("cusparse N %s %s (torch.sparse.mm, for comparison)" % (pat, tn), ms, op.apply_bytes(False))
                 del M, op, v, r, v2, cols, vals, crow
                 torch.cuda.empty_cache()
