@@ -177,9 +177,9 @@ extern "C" int b2o_sparse_apply(b2o_sparse *s, int trans, void *res, int64_t res
   b2o_ctx *c = s->ctx;
   B2O_CUDA(cudaSetDevice(c->device));
   const int o = trans ? 1 : 0;
-  // sparse_kernel option: 0 / 1 the row kernel; 2 the TMA-staged tile kernel (needs 16-byte aligned values).  Measured on
-  // B200 the two are within +-8 % of each other on every pattern tried (both sit at ~2.6e11 entries/s: the gathers from x, not
-  // the streamed bytes, set the pace -- profiles/r1_ncu_sparse.md), so the simpler row kernel is the default.
+  // sparse_kernel option: 0 / 3 the software-pipelined row kernel (default), 1 the plain row kernel (same bits), 2 the
+  // TMA-staged tile kernel (needs 16-byte aligned values).  Measured on B200 (profiles/r1_sparse.jsonl): pipelined rows
+  // 0.150 / 0.058 ms, plain rows 0.164 / 0.062 ms, tiles 0.167 / 0.075 ms on the two Float64 test patterns.
   const bool tiles = c->sparse_kernel == 2 && s->ntiles[o] > 0 && ((uintptr_t)s->val[o] & 15) == 0;
   if (tiles) {
     if (s->dtype == B2O_F64)
@@ -188,7 +188,7 @@ extern "C" int b2o_sparse_apply(b2o_sparse *s, int trans, void *res, int64_t res
     return spmv_tiles_run_impl<float>(c->num_sms, c->stream, &c->launches, s->tiles[o], s->ntiles[o], s->ptr[o], s->idx[o],
                                       s->val[o], out_len, s->nnz, res, v, alpha, beta, c->sparse_lanes);
   }
-  const bool pipe = c->sparse_kernel == 3;
+  const bool pipe = c->sparse_kernel != 1;
   if (s->dtype == B2O_F64)
     return spmv_run_impl<double>(c->num_sms, c->stream, &c->launches, s->ptr[o], s->idx[o], s->val[o], out_len, s->nnz, res, v, alpha, beta,
                                  pipe, c->sparse_lanes);

@@ -85,11 +85,12 @@ __global__ void __launch_bounds__(SP_THREADS, SP_CTAS_PER_SM) spmv_rows_kernel(c
   }
 }
 
-// Software-pipelined variant of the row kernel (sparse_kernel = 3): the first four (idx, val) pairs of a lane's NEXT row are
-// loaded into registers while the gathers of the CURRENT row are in flight, so a pass waits for one memory latency (x)
-// instead of two in a row (idx -> x).  Costs registers (one resident CTA fewer per SM); pays off when the gathers from x are
-// local (L1 / L2 hits) and the pass is latency-bound.  Same lane layout, same summation order as spmv_rows_kernel: the two
-// produce identical bits.
+// Software-pipelined variant of the row kernel -- THE DEFAULT (sparse_kernel = 0 or 3): the first four (idx, val) pairs of a
+// lane's NEXT row are loaded into registers while the gathers of the CURRENT row are in flight, so a pass waits for one
+// memory latency (x) instead of two in a row (idx -> x).  Costs registers (one resident CTA fewer per SM) and still wins on
+// every pattern measured: 0.150 vs 0.164 ms (24 entries per row, half of them scattered), 0.058 vs 0.062 ms (5-point
+// Laplacian), Float32 0.140 vs 0.159-0.170 and 0.046 vs 0.052 ms.  Same lane layout, same summation order as
+// spmv_rows_kernel: the two produce identical bits.
 constexpr int SP_PIPE_CTAS_PER_SM = 4;
 template <typename T, int LL>
 __global__ void __launch_bounds__(SP_THREADS, SP_PIPE_CTAS_PER_SM) spmv_rows_pipe_kernel(const __grid_constant__ SpmvArgs p) {
@@ -448,10 +449,12 @@ __global__ void __launch_bounds__(SP_THREADS) perm_gather_kernel(T *dst, const T
 }
 
 // ------------------------------------------------------------------ host side
-// lanes per row: every lane takes four entries per trip, so the smallest power of two >= mean row length / 4, at most a warp
+// lanes per row: the smallest power of two >= mean row length / 5, at most a warp.  Measured (profiles/r1_sparse.jsonl, lane
+// sweep): few lanes with several entries each beat one entry per lane -- 5 entries per row: 1 lane 0.058 ms, 2 lanes 0.078 ms,
+// 4 lanes 0.135 ms; 24 entries per row: 4 or 8 lanes 0.150-0.157 ms, 16 lanes 0.231 ms, 32 lanes 0.407 ms.
 static inline int spmv_lanes_log2(int64_t nrows, int64_t nnz) {
   const int64_t mean = nrows > 0 ? (nnz + nrows - 1) / nrows : 0;
-  const int64_t want = (mean + 3) / 4;
+  const int64_t want = (mean + 4) / 5;
   int l = 0;
   while (l < 5 && ((int64_t)1 << l) < want) ++l;
   return l;

@@ -79,7 +79,7 @@ CASES = [(10, 6, 0.5), (6, 10, 0.5), (200, 300, 0.004), (300, 200, 0.02), (150, 
 
 @pytest.fixture(params=[1, 2, 3], ids=["rowkernel", "tilekernel", "pipekernel"])
 def kernel(request, ctx):
-    """force the row kernel (the default) / the opt-in TMA-staged tile kernel / the software-pipelined row kernel"""
+    """force the plain row kernel / the TMA-staged tile kernel / the software-pipelined row kernel (the default)"""
     ctx.set_option("sparse_kernel", request.param)
     yield request.param
     ctx.set_option("sparse_kernel", 0)
@@ -292,7 +292,7 @@ def test_sparse_large_matrix_properties(lo, ctx, orc, dtype):
     rhs = float(torch.dot(z.double(), v.double()))
     assert abs(lhs - rhs) <= tol * max(abs(lhs), 1.0) * 10
     assert torch.equal(op * v, y) and torch.equal(lo.transpose(op) * u, z)
-    # the TMA-staged tile kernel (opt-in) must agree with the default row kernel to rounding, and is deterministic too;
+    # the TMA-staged tile kernel (opt-in) must agree with the default (pipelined row) kernel to rounding, and is deterministic too;
     # values whose storage is off a 16-byte boundary fall back to the row kernel
     ctx.set_option("sparse_kernel", 2)
     try:
@@ -302,7 +302,7 @@ def test_sparse_large_matrix_properties(lo, ctx, orc, dtype):
         ctx.set_option("sparse_kernel", 0)
     assert rel(host(yr), host(y)) <= (1e-14 if dtype == "float64" else 1e-6)
     assert rel(host(zr), host(z)) <= (1e-14 if dtype == "float64" else 1e-6)
-    ctx.set_option("sparse_kernel", 3)                                                # pipelined row kernel: the same bits
+    ctx.set_option("sparse_kernel", 1)                                                # plain row kernel: the same bits as the pipelined default
     try:
         assert torch.equal(op * v, y) and torch.equal(lo.transpose(op) * u, z)
         ctx.set_option("sparse_lanes", 1)                                             # another lane-group width: rounding only
