@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """One profiled launch of the sparse-matrix kernels (ncu --profile-from-start off; cudaProfilerStart/Stop window below):
-row kernel and TMA-staged tile kernel, Float64, on (a) the 5-point Laplacian of a 2048 x 2048 grid (local gathers) and
+pipelined row kernel (the default), plain row kernel and TMA-staged tile kernel, Float64, on (a) the 5-point Laplacian of a 2048 x 2048 grid (local gathers) and
 (b) 2^21 rows x 24 entries, 12 banded + 12 random columns (scattered gathers)."""
 import os
 import sys
@@ -42,13 +42,13 @@ def main():
     for M, nr in (laplace2d(2048, dtype, dev), band_rand(1 << 21, 24, dtype, dev)):
         op = lo.LinearOperator(M)
         todo.append((op, torch.rand(nr, dtype=dtype, device=dev), torch.empty(nr, dtype=dtype, device=dev)))
-    for kern in (1, 2):
+    for kern in (0, 1, 2):
         ctx.set_option("sparse_kernel", kern)
         for op, v, r in todo:
             lo.mul_(r, op, v)
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
-    for kern in (1, 2):                      # launch order: rows/laplace, rows/band, tiles/laplace, tiles/band
+    for kern in (0, 1, 2):                   # launch order: pipe/laplace, pipe/band, rows/laplace, rows/band, tiles/laplace, tiles/band
         ctx.set_option("sparse_kernel", kern)
         for op, v, r in todo:
             lo.mul_(r, op, v)
