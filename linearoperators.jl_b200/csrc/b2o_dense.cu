@@ -80,6 +80,11 @@ static int dense_run(b2o_dense *d, int trans, void *res, const void *v, double a
 extern "C" int b2o_dense_apply(b2o_dense *d, int trans, void *res, int64_t res_len, const void *v, int64_t v_len, double alpha,
                                double beta) {
   if (!d) B2O_FAIL(B2O_EARG, "null operator");
+  // a matrix leaf multiplies with the WHOLE input vector: on a row-partitioned context (b2o_comm_init) that would need an
+  // all-gather of v, which is not built -- fail loudly instead of multiplying slabs.  One block per GPU (BlockDiagonalOperator)
+  // uses local contexts.
+  if (d->ctx->nranks > 1)
+    B2O_FAIL(B2O_EUNSUPPORTED, "LinearOperator(M) is not row-partitioned: create it on a local (single-GPU) context");
   const int64_t in_len = trans ? d->m : d->n, out_len = trans ? d->n : d->m;
   if (v_len != in_len || res_len != out_len) B2O_FAIL(B2O_ESHAPE, "shape mismatch");
   if ((out_len > 0 && !res) || (in_len > 0 && !v)) B2O_FAIL(B2O_EARG, "null vector");

@@ -103,3 +103,22 @@ def test_ring_slot_release_follows_the_reads_of_the_slot(sass):
             checked += 1
     assert not bad, "\n".join(bad)
     assert checked >= 30
+
+
+def test_sparse_kernels_are_atomics_free_and_the_tile_kernel_uses_tma(sass):
+    """the sparse-matrix leaf claims fixed-order, atomics-free sums (bit-reproducible) in all three kernels, and that the tile
+    kernel stages idx / val / offsets with bulk copies behind an mbarrier ring; the row kernels issue the
+    loads of a whole 4-wide trip (idx, val and the four gathers: >= 8 read-only global loads) before the first multiply-add"""
+    ks = _of(sass, r"spmv_rows_kernel|spmv_rows_pipe_kernel|spmv_tiles_kernel")
+    assert len(ks) == 3 * 6 * 2                              # 3 kernels x 6 lane-group widths x {Float64, Float32}
+    for name, ins in ks.items():
+        text = "\n".join(ins)
+        assert not re.search(r"\b(ATOM|ATOMG|ATOMS|RED)\b", text), name
+        assert "DFMA" in text, name                          # sums are taken in double for both element types
+        if "spmv_tiles_kernel" in name:
+            assert text.count("UBLKCP") >= 3, name           # idx, val, offsets
+            assert "SYNCS.ARRIVE.TRANS64" in text and "SYNCS.PHASECHK.TRANS64.TRYWAIT" in text, name
+        else:
+            first = next(i for i, x in enumerate(ins) if "DFMA" in x)
+            loads = sum(1 for x in ins[max(0, first - 60):first] if re.search(r"LDG\.E(\.64)?\.CONSTANT", x))
+            assert loads >= 8, (name, loads)               # 4 (idx, val) pairs' worth of loads + the 4 gathers, before any multiply
