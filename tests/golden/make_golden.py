@@ -58,6 +58,72 @@ def compute_cases(orc):
     return {k: np.asarray(v, dtype=np.float64).tolist() for k, v in out.items()}
 
 
+def sparse_pattern(orc, m, n, density, seed):
+    """deterministic m x n sparse matrix from the shared counter-based generator: entry (i, j) is stored when
+    u[i*n + j] < density, with value 2*w[i*n + j] - 1; returned as Julia-style CSC (1-based colptr, rowval) + nzval (float64)"""
+    u = orc.uniform(m * n, seed).reshape(m, n)
+    w = orc.uniform(m * n, seed + 1).reshape(m, n)
+    mask = u < density
+    colptr1 = np.concatenate([[1], 1 + np.cumsum(mask.sum(axis=0))]).astype(np.int64)
+    rows, cols = np.nonzero(mask.T)[1], np.nonzero(mask.T)[0]           # column-major order of the stored entries
+    rowval1 = (rows + 1).astype(np.int64)
+    nzval = (2.0 * w[rows, cols] - 1.0).astype(np.float64)
+    return colptr1, rowval1, nzval
+
+
+def compute_cases_v2(orc):
+    """matrix leaves (LinearOperator(M), dense and sparse: src/constructors.jl:15-29), index operators and the α/β quirks
+    Q1-Q4 of SURVEY §8c -- frozen after the oracle passed test_oracle_pinning."""
+    out = {}
+    m, n = 37, 23
+    A = np.asfortranarray((2.0 * orc.uniform(m * n, 11) - 1.0).reshape(n, m).T)          # column-major m x n
+    v, u, r0, t0 = orc.uniform(n, 12), orc.uniform(m, 13), orc.uniform(m, 14), orc.uniform(n, 15)
+    for dt, tag in ((np.float64, "f64"), (np.float32, "f32")):
+        Ad, vd, ud = np.asfortranarray(A.astype(dt)), v.astype(dt), u.astype(dt)
+        res = np.empty(m, dtype=dt)
+        orc.gemv_(res, Ad, vd)
+        out["dense_%s_N" % tag] = res
+        res = np.empty(n, dtype=dt)
+        orc.gemv_(res, Ad, ud, trans=1)
+        out["dense_%s_T" % tag] = res
+        res = r0.astype(dt)
+        orc.gemv_(res, Ad, vd, 1.5, -0.25)
+        out["dense_%s_N_ab" % tag] = res
+    sm, sn = 60, 45
+    colptr1, rowval1, nzval = sparse_pattern(orc, sm, sn, 0.2, 21)
+    sv, su, sr0 = orc.uniform(sn, 23), orc.uniform(sm, 24), orc.uniform(sm, 25)
+    for dt, tag in ((np.float64, "f64"), (np.float32, "f32")):
+        res = np.empty(sm, dtype=dt)
+        orc.spmv_csc_(res, sm, sn, colptr1, rowval1, nzval.astype(dt), sv.astype(dt))
+        out["sparse_%s_N" % tag] = res
+        res = np.empty(sn, dtype=dt)
+        orc.spmv_csc_(res, sm, sn, colptr1, rowval1, nzval.astype(dt), su.astype(dt), trans=1)
+        out["sparse_%s_T" % tag] = res
+        res = sr0.astype(dt)
+        orc.spmv_csc_(res, sm, sn, colptr1, rowval1, nzval.astype(dt), sv.astype(dt), 1.5, -0.25)
+        out["sparse_%s_N_ab" % tag] = res
+    # index operators (exact): restriction ignores α, β (Q1); extension zero-fills and the last duplicate wins (Q4)
+    x10 = orc.uniform(10, 31)
+    idx = np.array([1, 2, 4, 7], dtype=np.int64)
+    res = np.full(4, 9.0)
+    orc.restrict_(res, idx, x10)
+    out["restrict_1247"] = res
+    dup = np.array([3, 7, 3, 10], dtype=np.int64)
+    res = np.full(10, 9.0)
+    orc.extend_(res, dup, x10[:4])
+    out["extend_dup_last_wins"] = res
+    # rectangular eye: tail = β (not β*res) when β != 0 (Q2); rectangular diagonal: tail zeroed whatever β (Q3)
+    v6, r9 = orc.uniform(6, 32), orc.uniform(9, 33)
+    res = r9.copy()
+    orc.eye_(res, v6, 2.0, 0.5, 6)
+    out["eye_9x6_a2_b05"] = res
+    d6 = orc.uniform(6, 34)
+    res = r9.copy()
+    orc.diag_(res, d6, v6, 2.0, 0.5, 6)
+    out["diag_9x6_a2_b05"] = res
+    return {k: np.asarray(val, dtype=np.float64).tolist() for k, val in out.items()}
+
+
 if __name__ == "__main__":
     sys.path.insert(0, os.path.join(HERE, "..", "..", "oracle"))
     import oracle
@@ -67,3 +133,7 @@ if __name__ == "__main__":
     json.dump({"generator": "tests/golden/make_golden.py", "oracle": "oracle/b2o_oracle.c (long-double reductions)",
                "cases": cases}, open(os.path.join(HERE, "golden_v1.json"), "w"), indent=1)
     print("wrote", len(cases), "cases")
+    cases2 = compute_cases_v2(oracle)
+    json.dump({"generator": "tests/golden/make_golden.py (compute_cases_v2)", "oracle": "oracle/b2o_oracle.c (long-double reductions)",
+               "cases": cases2}, open(os.path.join(HERE, "golden_v2.json"), "w"), indent=1)
+    print("wrote", len(cases2), "cases (v2)")

@@ -990,3 +990,61 @@ def test_lsr1_push_streamed_rebuild_equals_generic_passes(lo, ctx, orc, n, mem, 
     assert abs(Ls.data.opnorm_upper_bound - o.opnorm_upper_bound) <= 1e-10 * abs(o.opnorm_upper_bound)
     x = ctx.uniform(n, 7)
     assert rel(host(Ls * x), o.apply(host(x))) <= TOL
+
+
+def test_golden_vectors_v2_on_gpu(lo, ctx, orc):
+    """tests/golden/golden_v2.json on the device: dense and sparse LinearOperator(M) (Float64 <= 1e-12, Float32 <= 1e-5 -- sums in
+    double on both sides), index operators and the α/β quirks Q1-Q4 bit-exact"""
+    import torch
+    from golden.make_golden import sparse_pattern
+    G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_v2.json")))["cases"]
+    device = "cuda:%d" % ctx.device
+
+    def up(a, dt=torch.float64):
+        return torch.as_tensor(np.ascontiguousarray(a)).to(device).to(dt)
+
+    m, n = 37, 23
+    A = (2.0 * orc.uniform(m * n, 11) - 1.0).reshape(n, m)                   # row-major n x m == column-major m x n
+    v, u, r0 = orc.uniform(n, 12), orc.uniform(m, 13), orc.uniform(m, 14)
+    for dt, tag, tol in ((torch.float64, "f64", 1e-12), (torch.float32, "f32", 1e-5)):
+        At = up(A, dt).t()                                                   # column-major m x n view (Julia layout)
+        op = lo.LinearOperator(At)
+        assert rel(host(op * up(v, dt)), G["dense_%s_N" % tag]) <= tol
+        assert rel(host(lo.transpose(op) * up(u, dt)), G["dense_%s_T" % tag]) <= tol
+        res = up(r0, dt)
+        lo.mul_(res, op, up(v, dt), 1.5, -0.25)
+        assert rel(host(res), G["dense_%s_N_ab" % tag]) <= tol
+    sm, sn = 60, 45
+    colptr1, rowval1, nzval = sparse_pattern(orc, sm, sn, 0.2, 21)
+    sv, su, sr0 = orc.uniform(sn, 23), orc.uniform(sm, 24), orc.uniform(sm, 25)
+    for dt, tag, tol in ((torch.float64, "f64", 1e-12), (torch.float32, "f32", 1e-5)):
+        M = torch.sparse_csc_tensor(torch.as_tensor(colptr1 - 1), torch.as_tensor(rowval1 - 1), torch.as_tensor(nzval).to(dt),
+                                    size=(sm, sn), device=device)
+        for kern in (0, 1, 2):
+            ctx.set_option("sparse_kernel", kern)
+            try:
+                op = lo.LinearOperator(M)
+                assert rel(host(op * up(sv, dt)), G["sparse_%s_N" % tag]) <= tol
+                assert rel(host(lo.adjoint(op) * up(su, dt)), G["sparse_%s_T" % tag]) <= tol
+                res = up(sr0, dt)
+                lo.mul_(res, op, up(sv, dt), 1.5, -0.25)
+                assert rel(host(res), G["sparse_%s_N_ab" % tag]) <= tol
+            finally:
+                ctx.set_option("sparse_kernel", 0)
+    # index work and quirks: exact
+    x10 = up(orc.uniform(10, 31))
+    P = lo.opRestriction([1, 2, 4, 7], 10, ctx=ctx)
+    res = torch.full((4,), 9.0, dtype=torch.float64, device=device)
+    lo.mul_(res, P, x10, 3.0, 2.0)                                           # α, β ignored (Q1)
+    assert np.array_equal(host(res), np.array(G["restrict_1247"]))
+    Z = lo.opExtension([3, 7, 3, 10], 10, ctx=ctx)
+    res = torch.full((10,), 9.0, dtype=torch.float64, device=device)
+    lo.mul_(res, Z, x10[:4].contiguous(), 3.0, 2.0)                          # zero fill, last duplicate wins (Q4)
+    assert np.array_equal(host(res), np.array(G["extend_dup_last_wins"]))
+    v6, r9, d6 = up(orc.uniform(6, 32)), up(orc.uniform(9, 33)), up(orc.uniform(6, 34))
+    res = r9.clone()
+    lo.mul_(res, lo.opEye(9, 6, ctx=ctx), v6, 2.0, 0.5)                      # tail = β (Q2)
+    assert np.array_equal(host(res), np.array(G["eye_9x6_a2_b05"]))
+    res = r9.clone()
+    lo.mul_(res, lo.opDiagonal(9, 6, d6, ctx=ctx), v6, 2.0, 0.5)             # tail zeroed (Q3)
+    assert np.array_equal(host(res), np.array(G["diag_9x6_a2_b05"]))

@@ -452,3 +452,29 @@ def test_sparse_matrix_operator_predicates(orc):
         out = np.empty(10)
         orc.spmv_csc_(out, 10, 10, cp, rv, A.data, b, trans=trans)
         assert np.array_equal(out, ref)
+
+
+def test_golden_vectors_v2_matrix_leaves_and_quirks(orc):
+    """tests/golden/golden_v2.json (make_golden.compute_cases_v2): dense / sparse LinearOperator(M) products in Float64 and
+    Float32, index operators and the α/β quirks Q1-Q4, frozen after the predicates above passed"""
+    path = os.path.join(os.path.dirname(__file__), "golden", "golden_v2.json")
+    G = json.load(open(path))["cases"]
+    from golden.make_golden import compute_cases_v2
+    fresh = compute_cases_v2(orc)
+    assert set(fresh) == set(G)
+    for name, val in fresh.items():
+        exact = name.startswith(("restrict", "extend", "eye", "diag"))
+        assert (np.array_equal(val, G[name]) if exact else np.allclose(val, G[name], rtol=1e-14, atol=0)), name
+    # independent of the oracle: the frozen dense / sparse products against plain numpy on the same seeded inputs
+    from golden.make_golden import sparse_pattern
+    A = (2.0 * orc.uniform(37 * 23, 11) - 1.0).reshape(23, 37).T
+    assert np.allclose(G["dense_f64_N"], A @ orc.uniform(23, 12), rtol=1e-13)
+    assert np.allclose(G["dense_f64_T"], A.T @ orc.uniform(37, 13), rtol=1e-13)
+    cp, rv, nz = sparse_pattern(orc, 60, 45, 0.2, 21)
+    S = np.zeros((60, 45))
+    for j in range(45):
+        for k in range(cp[j] - 1, cp[j + 1] - 1):
+            S[rv[k] - 1, j] = nz[k]
+    assert 400 < len(nz) < 700
+    assert np.allclose(G["sparse_f64_N"], S @ orc.uniform(45, 23), rtol=1e-12, atol=1e-15)
+    assert np.allclose(G["sparse_f64_T"], S.T @ orc.uniform(60, 24), rtol=1e-12, atol=1e-15)
