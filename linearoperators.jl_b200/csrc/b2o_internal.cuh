@@ -70,6 +70,7 @@ struct b2o_ctx_s {
   int graph_blocks = 3;  // resident CTAs per SM the fused-graph kernel is compiled for (occupancy hides the dispatch latency)
   int dense_scalar = 0;  // dense-matrix leaf: force the scalar (unvectorised) kernels (testing)
   int sparse_kernel = 0; // sparse-matrix leaf: 0 / 3 software-pipelined row kernel (default), 1 plain row kernel, 2 TMA-staged tile kernel
+  int extend_form = 0;   // opExtension: 0 gather form through the inverse map when the index set is dense enough, 1 always memset + scatter
   int sparse_lanes = -1; // sparse-matrix leaf: force 2^k lanes per row (k = 0..5), -1 = from the mean row length
   // accounting
   int64_t launches = 0;

@@ -423,6 +423,10 @@ struct b2o_index_s {
   int64_t *d_idx0;    // [k] 0-based source rows (gather)
   int64_t *d_wpos;    // [kw] positions in u that win their target (scatter; duplicates: last occurrence wins)
   int64_t kw;
+  // gather form of the extension (dense index sets): d_inv[j] = position in u that lands on row j, -1 when none.  Built on
+  // the host at create time (index work, exact; last occurrence wins like the scatter).  One streaming pass writes res
+  // instead of memset + random 8-byte read-modify-writes.
+  int32_t *d_inv;     // [ncol] or nullptr
 };
 
 extern "C" int b2o_index_create(b2o_ctx *c, const int64_t *idx1, int64_t k, int64_t ncol, b2o_index **out) {
@@ -434,7 +438,16 @@ extern "C" int b2o_index_create(b2o_ctx *c, const int64_t *idx1, int64_t k, int6
   B2O_CUDA(cudaSetDevice(c->device));
   std::vector<int64_t> idx0(k), wpos;
   for (int64_t i = 0; i < k; ++i) idx0[i] = idx1[i] - 1;
-  {
+  // winners of duplicated targets (last occurrence).  Dense index sets go through the inverse map (which the gather form of
+  // the extension keeps anyway), sparse ones through a hash set so that nothing of size ncol is built for them.
+  std::vector<int32_t> inv;
+  const bool dense_set = k > 0 && k >= ncol / 16 && k < 0x7fffffffLL;
+  if (dense_set) {
+    inv.assign((size_t)ncol, -1);
+    for (int64_t i = 0; i < k; ++i) inv[(size_t)idx0[i]] = (int32_t)i;          // later occurrences overwrite earlier ones
+    for (int64_t i = 0; i < k; ++i)
+      if (inv[(size_t)idx0[i]] == (int32_t)i) wpos.push_back(i);
+  } else {
     std::unordered_set<int64_t> seen;
     seen.reserve((size_t)k * 2 + 1);
     for (int64_t i = k - 1; i >= 0; --i)
@@ -447,18 +460,31 @@ extern "C" int b2o_index_create(b2o_ctx *c, const int64_t *idx1, int64_t k, int6
   ix->ncol = ncol;
   ix->kw = (int64_t)wpos.size();
   ix->d_idx0 = ix->d_wpos = nullptr;
+  ix->d_inv = nullptr;
   cudaError_t e1 = cudaMalloc(&ix->d_idx0, sizeof(int64_t) * std::max<int64_t>(k, 1));
   cudaError_t e2 = cudaMalloc(&ix->d_wpos, sizeof(int64_t) * std::max<int64_t>(ix->kw, 1));
+  // the inverse map costs 4 bytes per row of the long vector: worth it when at least one row in 16 is hit (then
+  // 4 n + 8 n + 32 kw bytes in one streaming pass beat 8 n of memset + ~88 kw of sector-granular read-modify-writes)
+  const bool want_inv = dense_set && ix->kw >= ncol / 16;
+  cudaError_t e3 = want_inv ? cudaMalloc(&ix->d_inv, sizeof(int32_t) * (size_t)ncol) : cudaSuccess;
   if (e1 != cudaSuccess || e2 != cudaSuccess) {
     cudaGetLastError();
     cudaFree(ix->d_idx0);
     cudaFree(ix->d_wpos);
+    cudaFree(ix->d_inv);
     delete ix;
     B2O_FAIL(B2O_ENOMEM, "index allocation failed");
+  }
+  if (e3 != cudaSuccess) {          // no room for the inverse map: the scatter form still works
+    cudaGetLastError();
+    ix->d_inv = nullptr;
   }
   if (k > 0) {
     B2O_CUDA(cudaMemcpy(ix->d_idx0, idx0.data(), sizeof(int64_t) * k, cudaMemcpyHostToDevice));
     B2O_CUDA(cudaMemcpy(ix->d_wpos, wpos.data(), sizeof(int64_t) * ix->kw, cudaMemcpyHostToDevice));
+  }
+  if (ix->d_inv) {
+    B2O_CUDA(cudaMemcpy(ix->d_inv, inv.data(), sizeof(int32_t) * (size_t)ncol, cudaMemcpyHostToDevice));
   }
   *out = ix;
   return B2O_OK;
@@ -469,6 +495,7 @@ extern "C" int b2o_index_destroy(b2o_index *ix) {
   cudaStreamSynchronize(ix->ctx->stream);
   cudaFree(ix->d_idx0);
   cudaFree(ix->d_wpos);
+  cudaFree(ix->d_inv);
   delete ix;
   return B2O_OK;
 }
@@ -508,6 +535,27 @@ __global__ void __launch_bounds__(256) scatter_kernel(E *__restrict__ res, const
   }
 }
 
+// extension in gather form: res[j] = inv[j] >= 0 ? u[inv[j]] : 0 -- one streaming pass over res and inv, gathers from u
+template <typename E>
+__global__ void __launch_bounds__(256) extend_gather_kernel(E *__restrict__ res, const E *__restrict__ u,
+                                                            const int32_t *__restrict__ inv, int64_t ncol) {
+  const int64_t base = (int64_t)blockIdx.x * (256 * 4) + threadIdx.x;
+  int32_t src[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int64_t j = base + q * 256;
+    src[q] = (j < ncol) ? __ldcs(&inv[j]) : -1;
+  }
+  E val[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) val[q] = (src[q] >= 0) ? __ldg(&u[src[q]]) : (E)0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int64_t j = base + q * 256;
+    if (j < ncol) __stcs(&res[j], val[q]);
+  }
+}
+
 static int elem_size(int dtype) { return dtype == B2O_F64 ? 8 : dtype == B2O_F32 ? 4 : dtype == B2O_BF16 ? 2 : 0; }
 
 extern "C" int b2o_restrict_apply(b2o_index *ix, int dtype, void *res, int64_t res_len, const void *v, int64_t v_len) {
@@ -538,6 +586,16 @@ extern "C" int b2o_extend_apply(b2o_index *ix, int dtype, void *res, int64_t res
   if (!res || (ix->k > 0 && !u)) B2O_FAIL(B2O_EARG, "null vector");
   b2o_ctx *c = ix->ctx;
   B2O_CUDA(cudaSetDevice(c->device));
+  if (ix->d_inv && c->extend_form != 1) {                                       // dense index set: one gather-form pass
+    const unsigned grid = (unsigned)((ix->ncol + 1023) / 1024);
+    if (es == 8)
+      extend_gather_kernel<double><<<grid, 256, 0, c->stream>>>((double *)res, (const double *)u, ix->d_inv, ix->ncol);
+    else
+      extend_gather_kernel<float><<<grid, 256, 0, c->stream>>>((float *)res, (const float *)u, ix->d_inv, ix->ncol);
+    c->launches++;
+    B2O_CUDA(cudaGetLastError());
+    return B2O_OK;
+  }
   B2O_CUDA(cudaMemsetAsync(res, 0, (size_t)ix->ncol * es, c->stream));          // res .= 0   special-operators.jl:172
   if (ix->kw > 0) {
     const unsigned grid = (unsigned)((ix->kw + 1023) / 1024);

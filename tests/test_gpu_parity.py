@@ -1048,3 +1048,37 @@ def test_golden_vectors_v2_on_gpu(lo, ctx, orc):
     res = r9.clone()
     lo.mul_(res, lo.opDiagonal(9, 6, d6, ctx=ctx), v6, 2.0, 0.5)             # tail zeroed (Q3)
     assert np.array_equal(host(res), np.array(G["diag_9x6_a2_b05"]))
+
+
+@pytest.mark.parametrize("form", [0, 1], ids=["gatherform", "scatterform"])
+def test_extension_forms_agree_bit_exact(lo, ctx, orc, form):
+    """opExtension (src/special-operators.jl:171-174: res .= 0; res[I] = u, last duplicate wins): the gather form through the
+    inverse map (dense index sets) and memset + scatter (sparse ones, or extend_form=1) against the oracle, ==; Float64 and
+    Float32 (test/gpu/nvidia.jl uses Float32 vectors); NaN-filled res is never read"""
+    import torch
+    device = "cuda:%d" % ctx.device
+    rng = np.random.default_rng(3)
+    ctx.set_option("extend_form", form)
+    try:
+        for ncol, k in ((10, 4), (1000, 3), (4099, 4099), (100003, 70001), (100003, 11), (1 << 21, 1 << 19)):
+            idx = rng.integers(1, ncol + 1, size=k)
+            if k >= 8:
+                idx[-3:] = idx[:3]                                               # duplicates: the later occurrence wins
+            Z = lo.opExtension(idx, ncol, ctx=ctx)
+            for dt in (np.float64, np.float32):
+                u = rng.uniform(-1, 1, k).astype(dt)
+                res = torch.full((ncol,), float("nan"), dtype=torch.float64 if dt == np.float64 else torch.float32, device=device)
+                ud = torch.as_tensor(u).to(device)
+                if dt == np.float64:
+                    lo.mul_(res, Z, ud, 3.0, 2.0)                                 # α, β ignored (Q1)
+                else:                                                            # the host mirror's leaves are Float64: raw C ABI
+                    import ctypes
+                    from linearoperators_jl_b200 import _lib
+                    P = lo.opRestriction(idx, ncol, ctx=ctx)
+                    _lib.check(ctx.lib.b2o_extend_apply(P._index.h, _lib.B2O_F32, ctypes.c_void_p(res.data_ptr()), ncol,
+                                                        ctypes.c_void_p(ud.data_ptr()), k))
+                ref = np.zeros(ncol)
+                orc.extend_(ref, idx.astype(np.int64), u.astype(np.float64))
+                assert np.array_equal(host(res).astype(np.float64), ref), (ncol, k, dt)
+    finally:
+        ctx.set_option("extend_form", 0)

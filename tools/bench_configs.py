@@ -159,6 +159,24 @@ def main():
                 del M, op, v, r, v2, cols, vals, crow
                 torch.cuda.empty_cache()
         return
+    if only == ["index"]:
+        # opRestriction / opExtension at n = 1e8 with k = n/4 random indices (duplicates allowed): gather, and the extension in
+        # both forms (one gather-form pass through the inverse map vs memset + scatter)
+        k = n // 4
+        rng = np.random.default_rng(0)
+        idx = rng.integers(1, n + 1, size=k)
+        t0 = time.perf_counter()
+        P = lo.opRestriction(idx, n)
+        t_create = time.perf_counter() - t0
+        v, uk = ctx.uniform(n, 7), ctx.uniform(k, 8)
+        rk, res = ctx.empty(k), ctx.empty(n)
+        line("opRestriction random k=n/4 (gather)", timeit(lambda: lo.mul_(rk, P, v), 20), 24.0 * k, create_s=round(t_create, 2))
+        Z = lo.transpose(P)
+        for form, name in ((0, "gather form (inverse map, one pass)"), (1, "memset + scatter")):
+            ctx.set_option("extend_form", form)
+            line("opExtension random k=n/4, %s" % name, timeit(lambda: lo.mul_(res, Z, uk), 20), 8.0 * n + 24.0 * k)
+        ctx.set_option("extend_form", 0)
+        return
     if only == ["fwdc"]:
         v, res = ctx.uniform(n, 7), ctx.empty(n)
         m = 10
