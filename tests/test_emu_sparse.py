@@ -232,3 +232,26 @@ def test_pipelined_row_kernel_and_forced_lane_widths(emu, orc, dtype):
             run_checked(emu, orc, M, dtype, 1, 0, 1.0, 0.0, seed=k, kernel=3, force_lanes=lanes, out=b)
             assert np.array_equal(a[0], b[0], equal_nan=True)
             run_checked(emu, orc, M, dtype, 1, 0, 1.0, 0.0, seed=k, kernel=2, force_lanes=lanes)
+
+
+def test_randomised_structures_all_kernels(emu, orc):
+    """seeded random structures with power-law row lengths (a few very long rows, many empty ones), random shapes and both
+    storage formats through all three kernels; the plain and the pipelined row kernel must agree bit for bit"""
+    rng = np.random.default_rng(2024)
+    for trial in range(12):
+        m, n = int(rng.integers(1, 400)), int(rng.integers(1, 3000))
+        lens = np.minimum(n, (rng.pareto(1.2, m) * 3).astype(np.int64))
+        lens[rng.uniform(size=m) < 0.2] = 0
+        rows = np.repeat(np.arange(m), lens)
+        cols = np.concatenate([rng.choice(n, size=int(k), replace=False) for k in lens]) if lens.sum() else np.zeros(0, dtype=np.int64)
+        vals = rng.uniform(-1, 1, rows.shape[0])
+        dtype = F64 if trial % 2 == 0 else F32
+        A = sp.csc_matrix((vals.astype(np.float64 if dtype == F64 else np.float32), (rows, cols)), shape=(m, n))
+        A.sort_indices()
+        fmt, trans = trial % 2, (trial // 2) % 2
+        alpha, beta = (1.0, 0.0) if trial % 3 else (-1.5, 0.75)
+        a, b = [], []
+        run_checked(emu, orc, A, dtype, fmt, trans, alpha, beta, seed=trial, kernel=1, out=a)
+        run_checked(emu, orc, A, dtype, fmt, trans, alpha, beta, seed=trial, kernel=3, out=b)
+        assert np.array_equal(a[0], b[0], equal_nan=True), trial
+        run_checked(emu, orc, A, dtype, fmt, trans, alpha, beta, seed=trial, kernel=2)
