@@ -240,3 +240,89 @@ def test_sparse_matrix_leaf_refuses_cpu_and_coo(lo):
             lo.LinearOperator(S)
         with pytest.raises(lo.B2OError, match="sparse_csc or sparse_csr"):
             lo.SparseMatrixOperator(S.to_sparse_coo())
+
+
+def test_kron_of_operators_against_dense_kron(lo):
+    """kron(A, B) for two arbitrary operators (src/kron.jl:10-49) driven with host closures: `Matrix(K)` against np.kron
+    (test/test_kron.jl:3-39: norm(Matrix(K) - kron(A, B)) <= eps * norm), transpose / adjoint, 5-arg form, repeated applies,
+    symmetry flags, shape errors; scaling (test/test_kron.jl:50-58: kron(2A, B) == 2 kron(A, B))"""
+    rng = np.random.default_rng(5)
+    for (m, n, p, q) in ((2, 3, 4, 2), (3, 3, 2, 5), (1, 4, 3, 1), (10, 10, 3, 3)):
+        A, B = rng.uniform(-1, 1, (m, n)), rng.uniform(-1, 1, (p, q))
+        K = lo.kron(dense_op(lo, A), dense_op(lo, B))
+        D = np.kron(A, B)
+        assert lo.size(K) == (m * p, n * q)
+        x, u = rng.uniform(-1, 1, n * q), rng.uniform(-1, 1, m * p)
+        assert np.linalg.norm(lo.Matrix(K, like=x) - D, 1) <= 10 * np.finfo(float).eps * np.linalg.norm(D, 1)
+        assert np.linalg.norm(lo.Matrix(lo.transpose(K), like=u) - D.T, 1) <= 10 * np.finfo(float).eps * np.linalg.norm(D, 1)
+        assert np.allclose(lo.adjoint(K) * u, D.T @ u, rtol=1e-13, atol=1e-14)
+        r0 = rng.uniform(-1, 1, m * p)
+        res = r0.copy()
+        lo.mul_(res, K, x, 2.0, -0.5)
+        assert np.allclose(res, 2.0 * (D @ x) - 0.5 * r0, rtol=1e-13, atol=1e-14)
+        res = np.full(m * p, np.nan)
+        lo.mul_(res, K, x)                                                    # β == 0 never reads res
+        assert np.allclose(res, D @ x, rtol=1e-13, atol=1e-14)
+        y = x.copy()
+        if m * p == n * q:
+            for _ in range(100):                                             # 100 applies stay accurate (test_kron.jl:26-38)
+                y = K * y
+                y /= np.linalg.norm(y)
+            z = x.copy()
+            for _ in range(100):
+                z = D @ z
+                z /= np.linalg.norm(z)
+            assert np.linalg.norm(y - z) <= 1e-10
+        K2 = lo.kron(2.0 * dense_op(lo, A), dense_op(lo, B))
+        assert np.allclose(K2 * x, 2.0 * (K * x), rtol=1e-13, atol=1e-14)
+        with pytest.raises(lo.LinearOperatorException, match="shape mismatch"):
+            K * np.zeros(n * q + 1)
+    S1, S2 = rng.uniform(-1, 1, (3, 3)), rng.uniform(-1, 1, (2, 2))
+    sym = lambda M: lo.LinearOperator(np.float64, M.shape[0], M.shape[0], True, True,
+                                      lambda res, v, a, b: res.__setitem__(slice(None), a * ((M + M.T) @ v) + (b * res if b != 0 else 0)),
+                                      S=lo.Storage("numpy"))
+    Ks = lo.kron(sym(S1), sym(S2))
+    assert lo.issymmetric(Ks) and lo.ishermitian(Ks)
+    assert not lo.issymmetric(lo.kron(dense_op(lo, S1), sym(S2)))
+    xs = rng.uniform(-1, 1, 6)
+    assert np.allclose(lo.transpose(Ks) * xs, np.kron(S1 + S1.T, S2 + S2.T) @ xs, rtol=1e-13)
+
+
+def test_kron_of_operators_torch_tensor_plumbing(lo):
+    """the same kron(A, B) composition with torch tensors (CPU here) instead of numpy arrays: exercises the reshape / t() /
+    contiguous() plumbing the CUDA path takes, with host closures standing in for the kernels"""
+    import torch
+
+    class TorchCPU(lo.Storage):
+        def __init__(self):
+            super().__init__("torchcpu", 0, torch.float64)
+
+        def alloc(self, n, zero=False):
+            return (torch.zeros if zero else torch.empty)(int(n), dtype=torch.float64)
+
+    def top(M):
+        Mt = torch.as_tensor(M)
+
+        def prod(res, v, a, b):
+            assert v.dim() == 1 and (v.numel() <= 1 or v.stride(0) == 1), "closures need unit-stride vectors"
+            assert res.numel() <= 1 or res.stride(0) == 1
+            res[:] = a * (Mt @ v) + (b * res if b != 0 else 0)
+
+        def tprod(res, u, a, b):
+            assert u.numel() <= 1 or u.stride(0) == 1
+            assert res.numel() <= 1 or res.stride(0) == 1
+            res[:] = a * (Mt.t() @ u) + (b * res if b != 0 else 0)
+        return lo.LinearOperator(torch.float64, M.shape[0], M.shape[1], False, False, prod, tprod, tprod, S=TorchCPU())
+
+    rng = np.random.default_rng(6)
+    for (m, n, p, q) in ((2, 3, 4, 2), (5, 1, 1, 6), (7, 7, 3, 4)):
+        A, B = rng.uniform(-1, 1, (m, n)), rng.uniform(-1, 1, (p, q))
+        K = lo.kron(top(A), top(B))
+        D = np.kron(A, B)
+        x, u = torch.as_tensor(rng.uniform(-1, 1, n * q)), torch.as_tensor(rng.uniform(-1, 1, m * p))
+        assert np.allclose((K * x).numpy(), D @ x.numpy(), rtol=1e-13, atol=1e-14)
+        assert np.allclose((lo.transpose(K) * u).numpy(), D.T @ u.numpy(), rtol=1e-13, atol=1e-14)
+        r0 = torch.as_tensor(rng.uniform(-1, 1, m * p))
+        res = r0.clone()
+        lo.mul_(res, K, x, 1.5, 0.25)
+        assert np.allclose(res.numpy(), 1.5 * (D @ x.numpy()) + 0.25 * r0.numpy(), rtol=1e-13, atol=1e-14)
