@@ -63,7 +63,12 @@ const char *b2o_last_error(void);
 int b2o_ctx_create(int device, void *stream, b2o_ctx **out);
 int b2o_ctx_destroy(b2o_ctx *ctx);
 int b2o_ctx_sync(b2o_ctx *ctx);
-/* tuning knobs of the streaming kernels: "tile_rows" (1024|2048|4096), "stages", "grid", "threads" */
+/* tuning knobs of the streaming kernels: "tile_rows" (1024|2048|4096), "stages", "grid", "threads";
+ * fused trees: "graph_jit" (0|1), "graph_blocks" (1..4); host-buffer pipeline: "host_chunks";
+ * matrix leaves: "dense_scalar" (force the unvectorised dense kernels), "sparse_kernel" (0|3 pipelined rows -- default,
+ * 1 plain rows, 2 TMA-staged tiles), "sparse_lanes" (-1 auto | 0..5: 2^k lanes per row);
+ * index sets: "extend_form" (0 gather form through the inverse map when the set is dense enough, 1 always memset + scatter).
+ * Options change which kernel runs, never the result beyond summation order (index work stays exact). */
 int b2o_ctx_set_option(b2o_ctx *ctx, const char *key, int64_t value);
 /* debug: raw read of workspace scalars (e.g. the kron kernel's %globaltimer timeline with option "kron_debug") */
 int b2o_ctx_debug_read(b2o_ctx *ctx, int offset, int count, double *out);
