@@ -67,7 +67,9 @@ int b2o_ctx_sync(b2o_ctx *ctx);
  * fused trees: "graph_jit" (0|1), "graph_blocks" (1..4); host-buffer pipeline: "host_chunks";
  * matrix leaves: "dense_scalar" (force the unvectorised dense kernels), "sparse_kernel" (0|3 pipelined rows -- default,
  * 1 plain rows, 2 TMA-staged tiles), "sparse_lanes" (-1 auto | 0..5: 2^k lanes per row);
- * index sets: "extend_form" (0 gather form through the inverse map when the set is dense enough, 1 always memset + scatter).
+ * index sets: "extend_form" (0 gather form through the inverse map when the set is dense enough, 1 always memset + scatter);
+ * multi-GPU: "use_mailbox" (0|1: NCCL or the in-kernel NVLink mailbox for the inner products of a connected context -- every
+ * rank switches at the same point), "numa_local_host" (0|1: b2o_host_alloc prefers the GPU's NUMA node, default 1).
  * Options change which kernel runs, never the result beyond summation order (index work stays exact). */
 int b2o_ctx_set_option(b2o_ctx *ctx, const char *key, int64_t value);
 /* debug: raw read of workspace scalars (e.g. the kron kernel's %globaltimer timeline with option "kron_debug") */
@@ -82,7 +84,8 @@ int b2o_ctx_kernel_time(b2o_ctx *ctx, int reset, double *ms_total, int64_t *laun
  * A Julia caller passes CuArray pointers instead and never needs these. */
 int b2o_malloc(b2o_ctx *ctx, size_t bytes, void **dptr);
 int b2o_free(b2o_ctx *ctx, void *dptr);
-int b2o_host_alloc(b2o_ctx *ctx, size_t bytes, void **hptr); /* pinned */
+int b2o_host_alloc(b2o_ctx *ctx, size_t bytes, void **hptr); /* pinned; placed on the GPU's own NUMA node when known */
+int b2o_ctx_numa_node(b2o_ctx *ctx, int *node);              /* NUMA node of the context's GPU (-1 = unknown) */
 int b2o_host_free(b2o_ctx *ctx, void *hptr);
 int b2o_memcpy_h2d(b2o_ctx *ctx, void *dst, const void *src, size_t bytes); /* stream-ordered + sync */
 int b2o_memcpy_d2h(b2o_ctx *ctx, void *dst, const void *src, size_t bytes);

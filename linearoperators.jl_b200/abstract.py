@@ -449,8 +449,16 @@ def _mul_matrix(res, op, m, alpha, beta):
     block = getattr(op, "_mul_block", None)
     if block is not None and block(res, m, alpha, beta):
         return res
+    # the reference's matrix mul! never touches the product counters (no increase_nprod! at src/operations.jl:34-36)
+    saved = tuple(getattr(op, c, None) for c in ("nprod", "ntprod", "nctprod"))
     for j in range(m.shape[1]):
         mul_(res[:, j], op, m[:, j], alpha, beta)
+    for c, v in zip(("nprod", "ntprod", "nctprod"), saved):
+        if v is not None:
+            try:
+                setattr(op, c, v)
+            except AttributeError:
+                pass
     return res
 
 
@@ -544,7 +552,19 @@ def Matrix(op, like=None):
 
 # ------------------------------------------------------------------ operator algebra (src/operations.jl:100-234)
 def _promote_eltype(a, b):
-    return a if a == b else (a if b is None else (b if a is None else a))
+    """promote_type(T1, T2) (src/operations.jl:139-147): e.g. an Int64 opRestriction times a Float64 operator is Float64."""
+    if a == b or b is None:
+        return a
+    if a is None:
+        return b
+    try:
+        import torch
+        if isinstance(a, torch.dtype) and isinstance(b, torch.dtype):
+            return torch.promote_types(a, b)
+        import numpy as np
+        return np.promote_types(a, b)
+    except Exception:
+        return a
 
 
 def neg(op):

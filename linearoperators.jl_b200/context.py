@@ -48,9 +48,34 @@ class Context:
         _lib.check(self.lib.b2o_ctx_kernel_time(self.handle, int(reset), ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
 
+    def debug_read(self, offset, count):
+        """raw read of workspace scalars: [0, ncols) the reduced inner products of the last forward / L-SR1 / compact apply,
+        [512, 512+2A) those of the last fused two-loop apply in sweep order, [768, 771) the mailbox timing accumulators
+        (ns CTA 0 waited for its own GPU's CTAs, ns in the NVLink exchange, number of exchanges)."""
+        out = (ctypes.c_double * int(count))()
+        _lib.check(self.lib.b2o_ctx_debug_read(self.handle, int(offset), int(count), out))
+        return list(out)
+
     def empty(self, n, dtype=None):
         torch = _torch()
         return torch.empty(int(n), dtype=dtype or torch.float64, device="cuda:%d" % self.device)
+
+    def host_empty(self, n):
+        """pinned Float64 host vector from b2o_host_alloc (placed on the GPU's own NUMA node when the platform says which),
+        as a torch CPU tensor over that memory.  Freed with the context (or host_free)."""
+        torch = _torch()
+        p = ctypes.c_void_p()
+        _lib.check(self.lib.b2o_host_alloc(self.handle, ctypes.c_size_t(int(n) * 8), ctypes.byref(p)))
+        buf = (ctypes.c_double * int(n)).from_address(p.value)
+        t = torch.frombuffer(buf, dtype=torch.float64, count=int(n))
+        self._host_bufs = getattr(self, "_host_bufs", [])
+        self._host_bufs.append((p, buf))
+        return t
+
+    def numa_node(self):
+        node = ctypes.c_int(-1)
+        _lib.check(self.lib.b2o_ctx_numa_node(self.handle, ctypes.byref(node)))
+        return node.value
 
     def zeros(self, n, dtype=None):
         torch = _torch()
@@ -112,6 +137,9 @@ class Context:
         self.mailbox = False
 
     def close(self):
+        for p, _ in getattr(self, "_host_bufs", []):
+            self.lib.b2o_host_free(self.handle, p)
+        self._host_bufs = []
         if self.handle:
             self.lib.b2o_ctx_destroy(self.handle)
             self.handle = None

@@ -1,7 +1,10 @@
 // b2o_ctx.cu -- context, errors, memory helpers, synthetic data, generic small reductions, NCCL glue.
 #include "b2o_internal.cuh"
+#include <ctype.h>
 #include <dlfcn.h>
 #include <stdarg.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 // ------------------------------------------------------------------ errors
 static thread_local char g_err[1024] = "";
@@ -111,6 +114,14 @@ extern "C" int b2o_ctx_set_option(b2o_ctx *c, const char *key, int64_t value) {
     c->graph_blocks = (int)value;
   } else if (!strcmp(key, "time_kernels")) {
     c->time_kernels = value != 0;
+  } else if (!strcmp(key, "use_mailbox")) {
+    // switch between the in-kernel NVLink mailbox and NCCL for the inner products of a connected context (every rank must switch
+    // at the same point of its call sequence; the peers stay mapped and the epoch counter keeps running)
+    if (value != 0 && !c->mbox_connected) B2O_FAIL(B2O_ESTATE, "mailbox not connected (b2o_mbox_connect)");
+    B2O_CUDA(cudaStreamSynchronize(c->stream));
+    c->mbox_ready = value != 0 ? 1 : 0;
+  } else if (!strcmp(key, "numa_local_host")) {
+    c->numa_local_host = value != 0;
   } else {
     B2O_FAIL(B2O_EARG, "unknown option '%s'", key);
   }
@@ -157,9 +168,42 @@ extern "C" int b2o_free(b2o_ctx *c, void *dptr) {
   B2O_CUDA(cudaFree(dptr));
   return B2O_OK;
 }
+// NUMA node the GPU hangs off (sysfs; -1 = unknown / single node).  Pinned staging buffers that live on the GPU's own node keep
+// the H2D / D2H streams of 8 ranks off the inter-socket link (the round-1 end-to-end collapse at N=8).
+static int gpu_numa_node(int device) {
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  for (char *p = bus; *p; ++p) *p = (char)tolower(*p);
+  char path[128];
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE *f = fopen(path, "r");
+  if (!f) return -1;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  return node;
+}
+extern "C" int b2o_ctx_numa_node(b2o_ctx *c, int *node) {
+  if (!c || !node) B2O_FAIL(B2O_EARG, "null argument");
+  *node = gpu_numa_node(c->device);
+  return B2O_OK;
+}
 extern "C" int b2o_host_alloc(b2o_ctx *c, size_t bytes, void **hptr) {
   if (!c || !hptr) B2O_FAIL(B2O_EARG, "null argument");
+  // MPOL_PREFERRED on the GPU's node for the duration of the allocation: cudaMallocHost populates and pins the pages in this
+  // thread, so they land on that node when it has room (and anywhere otherwise -- never a failure)
+  const int node = c->numa_local_host ? gpu_numa_node(c->device) : -1;
+  bool policy_set = false;
+  if (node >= 0 && node < 1024) {
+    unsigned long mask[16] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1UL << (node % (8 * sizeof(unsigned long)));
+    policy_set = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, (unsigned long)(sizeof(mask) * 8)) == 0;
+  }
   cudaError_t e = cudaMallocHost(hptr, bytes ? bytes : 16);
+  if (policy_set) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0UL);
   if (e != cudaSuccess) {
     cudaGetLastError();
     B2O_FAIL(B2O_ENOMEM, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
@@ -427,16 +471,18 @@ extern "C" int b2o_mbox_connect(b2o_ctx *c, const void *handles, int nranks, int
   c->rank = rank;
   c->mbox_epoch = 0;
   c->mbox_ready = 1;
+  c->mbox_connected = 1;
   return B2O_OK;
 }
 extern "C" int b2o_mbox_disconnect(b2o_ctx *c) {
   if (!c) B2O_FAIL(B2O_EARG, "null context");
-  if (c->mbox_ready) {
+  if (c->mbox_connected) {
     cudaStreamSynchronize(c->stream);
     for (int r = 0; r < c->nranks; ++r)
       if (r != c->rank && c->mbox_peers[r]) cudaIpcCloseMemHandle(c->mbox_peers[r]);
   }
   c->mbox_ready = 0;
+  c->mbox_connected = 0;
   return B2O_OK;
 }
 void b2o_mbox_fill(b2o_ctx *c, MboxDev *m) {

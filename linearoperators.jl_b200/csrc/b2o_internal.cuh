@@ -41,7 +41,9 @@ void b2o_set_error(const char *fmt, ...);
 // ------------------------------------------------------------------ context
 constexpr int B2O_MAX_COLS = 128;      // column streams one launch can address
 constexpr int B2O_MAX_GRID = 1024;     // upper bound on persistent grid
-constexpr int B2O_WS_DOTS = 512;       // doubles reserved for reduced scalars
+constexpr int B2O_WS_DOTS = 1024;      // doubles reserved for reduced scalars
+constexpr int B2O_WS_SWEEP = 512;      // [512, 512+129): inner products of the last fused two-loop launch, sweep order
+constexpr int B2O_WS_QNDBG = 768;      // [768, 771): mailbox timing accumulators (ns waited for local CTAs, ns in the exchange, epochs)
 
 struct b2o_ctx_s {
   int device = 0;
@@ -84,7 +86,9 @@ struct b2o_ctx_s {
   // NVLink peer mailbox (in-kernel all-reduce of the small dot vectors): local buffer + IPC-mapped peers
   void *mbox = nullptr;
   void *mbox_peers[8] = {};
-  int mbox_ready = 0;
+  int mbox_ready = 0;      // in use (option "use_mailbox" toggles it on a connected context)
+  int mbox_connected = 0;  // peers mapped
+  int numa_local_host = 1; // b2o_host_alloc prefers the GPU's own NUMA node
   unsigned long long mbox_epoch = 0;
 };
 
@@ -161,6 +165,11 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
   unsigned long long v;

@@ -424,6 +424,7 @@ static int compact_launch_rows(b2o_qn *q, const CompactArgs &base, double *res, 
   if (coop) a.bar_target = c->bar_base + (unsigned long long)cfg.grid;
   b2o_mbox_fill(c, &a.mbox);
   if (!coop) a.mbox.nranks = 1;
+  a.dbg = c->d_dots + B2O_WS_QNDBG;
   if (grid_out) *grid_out = cfg.grid;
   int st = push_op == OP_PUSH_A                                     ? launch_compact_R<OP_PUSH_A>(c, cfg, a, coop)
            : push_op == OP_PUSH_L                                   ? launch_compact_R<OP_PUSH_L>(c, cfg, a, coop)
@@ -506,6 +507,8 @@ static int qn_apply_twoloop(b2o_qn *q, double *res, const double *x, double alph
   a.bar_off = (uint32_t)cfg.L.bar_off;
   const int nsweeps = 2 * na + 1;
   b2o_mbox_fill(c, &a.mbox);
+  a.sweep_dots = c->d_dots + B2O_WS_SWEEP;
+  a.dbg = c->d_dots + B2O_WS_QNDBG;
   if (c->nranks <= 1 || c->mbox_ready) {
     // single GPU, or row-partitioned with the NVLink mailbox: all 2A+1 sweeps and all 2A all-reduces in ONE launch
     a.sweep_begin = 0;
@@ -919,6 +922,9 @@ extern "C" int b2o_qn_apply_host(b2o_qn *q, void *res_host, const void *x_host, 
     return B2O_OK;
   }
   B2O_TRY(ensure_pipeline(c));
+  // the chunked path launches the phases itself: the compact forward form needs its middle matrix first (qn_apply_dev does this
+  // for the single-launch path)
+  if (q->kind == 0 && !q->inverse && q->fwd_compact && q->w_dirty) B2O_TRY(build_forward_W(q));
   CompactArgs a;
   compact_columns(q, a, alpha, beta);
   const int64_t rows_per = ((q->n + nch - 1) / nch + align - 1) / align * align;
@@ -1153,7 +1159,7 @@ extern "C" int b2o_lbfgs_push_damped_fwd(b2o_qn *q, const void *s_, const void *
     B2O_TRY(ew_axpby(c, q->tmp, th, y, 1 - th, Bs, n));                                         // :316 damped y
     ys = th * ys + (1 - th) * sBs;
     yuse = q->tmp;
-    if (q->scaling) {
+    if (q->scaling || q->fwd_compact) {   // yy of the DAMPED y: scaling factor, and norm_b of the compact forward form
       const double *u2[1] = {q->tmp}, *v2[1] = {q->tmp};
       B2O_TRY(b2o_pair_dots(c, 1, u2, v2, n, c->d_dots + 300));
       B2O_TRY(b2o_read_scalars(c, c->d_dots + 300, 1, &yy));

@@ -41,6 +41,7 @@ struct CompactArgs {
   const double *y2;                  // OP_PUSH_L: y_k (library-owned column)
   const double *W;                   // OP_INV_COMPACT: ncols x ncols middle matrix (row-major), coefficients = W * dots
   int base_div;                      // OP_INV_COMPACT: base term x/γ (compact FORWARD form) instead of γx (compact inverse)
+  double *dbg;                       // [0] += ns CTA 0 waited for the local CTAs, [1] += ns in the mailbox exchange, [2] += epochs
 };
 
 template <int R, int OP>
@@ -134,9 +135,12 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
         atomicAdd(p.bar, 1ULL);
       }
       if (blockIdx.x == 0) {
+        unsigned long long t0 = 0, t1 = 0;
         if (tid == 0) {
+          t0 = globaltimer_ns();
           while (ld_acquire_u64(p.bar) < bar_target) { __nanosleep(32); }
           __threadfence();
+          t1 = globaltimer_ns();
         }
         __syncthreads();
         if (!is_producer) {
@@ -149,6 +153,12 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
         }
         __syncthreads();
         if (warp == 0) mbox_allreduce_warp(p.mbox, epoch, coef, ncols);
+        if (tid == 0 && p.dbg) {
+          const unsigned long long t2 = globaltimer_ns();
+          p.dbg[0] += (double)(t1 - t0);
+          p.dbg[1] += (double)(t2 - t1);
+          p.dbg[2] += 1.0;
+        }
         __syncthreads();
         for (int c = tid; c < ncols; c += B2O_NTHREADS) p.dots[c] = coef[c];
         __threadfence();
@@ -170,7 +180,10 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
           double s = 0.0;
           for (int b = lane; b < (int)grid; b += 32) s += __ldcg(&p.partials[(size_t)b * ncols + c]);
           s = warp_sum(s);
-          if (lane == 0) coef[c] = s;
+          if (lane == 0) {
+            coef[c] = s;
+            if (blockIdx.x == 0) p.dots[c] = s;   // left for the parity tests (b2o_ctx_debug_read)
+          }
         }
       }
       __syncthreads();
@@ -381,6 +394,8 @@ struct TwoLoopArgs {
   int sweep_begin, sweep_end;    // sweeps [begin,end) of 0..2A run in this launch (fused: 0..2A+1)
   uint32_t coef_off, bar_off;
   MboxDev mbox;                  // nranks > 1: each inner product is all-reduced in-kernel through the NVLink peer mailbox
+  double *sweep_dots;            // fused mode: the reduced inner product of sweep w is also left in sweep_dots[w] (parity tests)
+  double *dbg;                   // [0] += ns CTA 0 waited for the local CTAs, [1] += ns in the mailbox exchange, [2] += epochs
 };
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -564,9 +579,12 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_kernel(const __gri
         atomicAdd(p.bar, 1ULL);
       }
       if (blockIdx.x == 0) {
+        unsigned long long t0 = 0, t1 = 0;
         if (tid == 0) {
+          t0 = globaltimer_ns();
           while (ld_acquire_u64(p.bar) < bar_target) { __nanosleep(32); }
           __threadfence();
+          t1 = globaltimer_ns();
         }
         __syncthreads();
         if (warp == 0) {
@@ -579,8 +597,15 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_kernel(const __gri
           if (lane == 0) {
             s_dot = s_mb[0];
             p.dots[0] = s_mb[0];
+            if (p.sweep_dots) p.sweep_dots[w] = s_mb[0];
             __threadfence();
             st_release_gpu_u64(p.mbox.ready, epoch);
+            if (p.dbg) {
+              const unsigned long long t2 = globaltimer_ns();
+              p.dbg[0] += (double)(t1 - t0);
+              p.dbg[1] += (double)(t2 - t1);
+              p.dbg[2] += 1.0;
+            }
           }
         }
       } else {
@@ -598,7 +623,10 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_kernel(const __gri
         double s = 0.0;
         for (int b = lane; b < (int)grid; b += 32) s += __ldcg(&p.partials[b]);
         s = warp_sum(s);
-        if (lane == 0) s_dot = s;
+        if (lane == 0) {
+          s_dot = s;
+          if (blockIdx.x == 0 && p.sweep_dots) p.sweep_dots[w] = s;
+        }
       }
       __syncthreads();
     } else {

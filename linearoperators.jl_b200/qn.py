@@ -182,9 +182,12 @@ def push_(op, s, y, *rest):
         if len(rest) != 0:
             raise TypeError("no such push! method for LSR1Operator")
         _lib.check(lib.b2o_qn_push(op.handle, _vp(s), _vp(y), n, ctypes.byref(acc)))
+        if isinstance(op, LSR1Operator) or (op.damped and not op.inverse):
+            op.nprod += 1          # push! runs mul!(Bs, op, s) first (src/lsr1.jl:125, src/lbfgs.jl:305 through :273-277)
     elif len(rest) == 1:
         (Bs,) = rest
         _lib.check(lib.b2o_lbfgs_push_damped_fwd(op.handle, _vp(s), _vp(y), _vp(Bs), n, ctypes.byref(acc)))
+        op.nprod += 1              # mul!(Bs, op, s)  src/lbfgs.jl:305
     elif len(rest) in (2, 3):
         alpha, g = rest[0], rest[1]
         Bs = rest[2] if len(rest) == 3 else op.ctx.empty(n)      # similar(g)  src/lbfgs.jl:366

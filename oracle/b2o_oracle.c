@@ -153,11 +153,43 @@ struct orc_lbfgs {
   double *ys, *alpha, *norm_b;
   int ins0;                                /* insert-1 */
   double *Ax;
+  /* full-size parity runs (tests only): the columns live on the GPU and are streamed to the host one at a time */
+  orc_fetch_fn fetch;
+  void *fetch_user;
+  double *dots_log;                        /* inner products of the last apply, in the order the reference takes them */
+  int ndots;
 };
+
+/* column k0 of s/y/a/b (which = 0..3): resident, or fetched into the caller's host buffer `slot` (0 or 1) */
+static const double *lbfgs_column(orc_lbfgs *o, int which, int k0, int slot) {
+  if (o->fetch) return o->fetch(o->fetch_user, which, k0, slot);
+  const double *base = which == 0 ? o->s : which == 1 ? o->y : which == 2 ? o->a : o->b;
+  return base + (size_t)k0 * (size_t)o->n;
+}
+static double logged_dot(orc_lbfgs *o, const double *a, const double *b) {
+  double d = orc_dot(a, b, o->n);
+  if (o->dots_log && o->ndots < 4 * o->mem + 4) o->dots_log[o->ndots++] = d;
+  return d;
+}
 
 static inline int pmod(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
 
+static orc_lbfgs *lbfgs_create(int64_t n, int mem, int scaling, int damped, double sigma2, double sigma3, int inverse, int external);
 orc_lbfgs *orc_lbfgs_create(int64_t n, int mem, int scaling, int damped, double sigma2, double sigma3, int inverse) {
+  return lbfgs_create(n, mem, scaling, damped, sigma2, sigma3, inverse, 0);
+}
+/* apply-only operator whose columns are supplied by `fetch` (state scalars through set_gamma / set_insert / ys) */
+orc_lbfgs *orc_lbfgs_create_external(int64_t n, int mem, int scaling, int inverse, orc_fetch_fn fetch, void *user) {
+  orc_lbfgs *o = lbfgs_create(n, mem, scaling, 0, 0.99, 10.0, inverse, 1);
+  o->fetch = fetch;
+  o->fetch_user = user;
+  return o;
+}
+const double *orc_lbfgs_last_dots(orc_lbfgs *o, int *count) {
+  if (count) *count = o->ndots;
+  return o->dots_log;
+}
+static orc_lbfgs *lbfgs_create(int64_t n, int mem, int scaling, int damped, double sigma2, double sigma3, int inverse, int external) {
   /* LBFGSData ctor :26-57.  Q7: the reference clamps data.mem to max(mem,1) but sizes its arrays with the
    * unclamped value (mem=0 would index out of bounds); the oracle sizes with the clamped value. */
   orc_lbfgs *o = (orc_lbfgs *)calloc(1, sizeof(*o));
@@ -165,9 +197,12 @@ orc_lbfgs *orc_lbfgs_create(int64_t n, int mem, int scaling, int damped, double 
   o->n = n; o->mem = mem; o->scaling = scaling; o->damped = damped; o->inverse = inverse;
   o->gamma = 1.0; o->sigma2 = sigma2; o->sigma3 = sigma3; o->opnorm_ub = 1.0;
   size_t nn = (size_t)(n > 0 ? n : 1) * (size_t)mem;
-  o->s = (double *)calloc(nn, sizeof(double));
-  o->y = (double *)calloc(nn, sizeof(double));
-  if (!inverse) {
+  o->dots_log = (double *)calloc((size_t)4 * mem + 4, sizeof(double));
+  if (!external) {
+    o->s = (double *)calloc(nn, sizeof(double));
+    o->y = (double *)calloc(nn, sizeof(double));
+  }
+  if (!inverse && !external) {
     o->a = (double *)calloc(nn, sizeof(double));
     o->b = (double *)calloc(nn, sizeof(double));
   }
@@ -180,7 +215,7 @@ orc_lbfgs *orc_lbfgs_create(int64_t n, int mem, int scaling, int damped, double 
 }
 void orc_lbfgs_destroy(orc_lbfgs *o) {
   if (!o) return;
-  free(o->s); free(o->y); free(o->a); free(o->b); free(o->ys); free(o->alpha); free(o->norm_b); free(o->Ax); free(o);
+  free(o->s); free(o->y); free(o->a); free(o->b); free(o->ys); free(o->alpha); free(o->norm_b); free(o->Ax); free(o->dots_log); free(o);
 }
 double *orc_lbfgs_col(orc_lbfgs *o, int which, int k0) {
   double *base = which == 0 ? o->s : which == 1 ? o->y : which == 2 ? o->a : o->b;
@@ -198,12 +233,13 @@ static void lbfgs_apply_inverse(orc_lbfgs *o, double *res, const double *x, doub
   const int64_t n = o->n;
   const int mem = o->mem;
   double *q = o->Ax;
+  o->ndots = 0;
   PFOR for (int64_t j = 0; j < n; ++j) q[j] = x[j];                         /* :127-128 */
   for (int i = 1; i <= mem; ++i) {                                          /* :130 */
     int k = pmod(o->ins0 - i, mem);                                         /* k = mod(insert-i-1,mem)+1 */
     if (o->ys[k] != 0) {
-      const double *sk = o->s + (size_t)k * n, *yk = o->y + (size_t)k * n;
-      double ak = orc_dot(sk, q, n) / o->ys[k];                             /* :133 */
+      const double *sk = lbfgs_column(o, 0, k, 0), *yk = lbfgs_column(o, 1, k, 1);
+      double ak = logged_dot(o, sk, q) / o->ys[k];                          /* :133 */
       o->alpha[k] = ak;
       PFOR for (int64_t j = 0; j < n; ++j) q[j] -= ak * yk[j];              /* :135 */
     }
@@ -215,8 +251,8 @@ static void lbfgs_apply_inverse(orc_lbfgs *o, double *res, const double *x, doub
   for (int i = 1; i <= mem; ++i) {                                          /* :141 */
     int k = pmod(o->ins0 + i - 1, mem);                                     /* k = mod(insert+i-2,mem)+1 */
     if (o->ys[k] != 0) {
-      const double *sk = o->s + (size_t)k * n, *yk = o->y + (size_t)k * n;
-      double bb = o->alpha[k] - orc_dot(yk, q, n) / o->ys[k];               /* :144-145 */
+      const double *sk = lbfgs_column(o, 0, k, 0), *yk = lbfgs_column(o, 1, k, 1);
+      double bb = o->alpha[k] - logged_dot(o, yk, q) / o->ys[k];            /* :144-145 */
       PFOR for (int64_t j = 0; j < n; ++j) q[j] += bb * sk[j];              /* :146 */
     }
   }
@@ -232,6 +268,7 @@ static void lbfgs_apply_forward(orc_lbfgs *o, double *res, const double *x, doub
   const int64_t n = o->n;
   const int mem = o->mem;
   double *q = o->Ax;
+  o->ndots = 0;
   PFOR for (int64_t j = 0; j < n; ++j) q[j] = x[j];                         /* :183-184 */
   if (o->scaling) {
     double g = o->gamma;
@@ -240,9 +277,9 @@ static void lbfgs_apply_forward(orc_lbfgs *o, double *res, const double *x, doub
   for (int i = 1; i <= mem; ++i) {                                          /* :189 */
     int k = pmod(o->ins0 + i - 1, mem);
     if (o->ys[k] != 0) {
-      const double *ak = o->a + (size_t)k * n, *bk = o->b + (size_t)k * n;
-      double ax = orc_dot(ak, x, n);                                        /* :192 */
-      double bx = orc_dot(bk, x, n);                                        /* :193 */
+      const double *ak = lbfgs_column(o, 2, k, 0), *bk = lbfgs_column(o, 3, k, 1);
+      double ax = logged_dot(o, ak, x);                                     /* :192 */
+      double bx = logged_dot(o, bk, x);                                     /* :193 */
       PFOR for (int64_t j = 0; j < n; ++j) q[j] = q[j] + (bx * bk[j] - ax * ak[j]); /* :194 */
     }
   }

@@ -52,6 +52,14 @@ void orc_extend(double *res, int64_t ncol, const int64_t *idx1, int64_t k, const
 typedef struct orc_lbfgs orc_lbfgs;
 orc_lbfgs *orc_lbfgs_create(int64_t n, int mem, int scaling, int damped, double sigma2, double sigma3, int inverse);
 void orc_lbfgs_destroy(orc_lbfgs *);
+/* Full-size parity runs: an apply-only operator whose columns stay where they are (the GPU) and are handed to the oracle
+ * one at a time by `fetch(user, which, k0, slot)` (which: 0 s, 1 y, 2 a, 3 b; slot 0/1 = which of the caller's two host
+ * buffers to fill: an apply never needs more than two columns at once).  The SAME apply code runs either way. */
+typedef const double *(*orc_fetch_fn)(void *user, int which, int k0, int slot);
+orc_lbfgs *orc_lbfgs_create_external(int64_t n, int mem, int scaling, int inverse, orc_fetch_fn fetch, void *user);
+/* the inner products of the last apply in the order the reference takes them (forward: a_k.x, b_k.x oldest -> newest;
+ * inverse: loop 1 s_k.q newest -> oldest, then loop 2 y_k.q oldest -> newest) */
+const double *orc_lbfgs_last_dots(orc_lbfgs *, int *count);
 void orc_lbfgs_apply(orc_lbfgs *, double *res, const double *x, double alpha, double beta);
 int orc_lbfgs_push(orc_lbfgs *, const double *s, const double *y);                    /* 1 accepted, 0 rejected, <0 error */
 int orc_lbfgs_push_damped_fwd(orc_lbfgs *, const double *s, const double *y, double *Bs);

@@ -23,6 +23,7 @@ def build(force=False):
 
 _lib = None
 c_dp = ctypes.POINTER(ctypes.c_double)
+FETCH_FN = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int)
 
 
 def usable_cpus():
@@ -62,6 +63,8 @@ def lib():
             "orc_lbfgs_gamma": (d, [vp]), "orc_lbfgs_set_gamma": (None, [vp, d]), "orc_lbfgs_insert": (i32, [vp]),
             "orc_lbfgs_set_insert": (None, [vp, i32]), "orc_lbfgs_opnorm_upper_bound": (d, [vp]),
             "orc_lbfgs_solve_shifted": (i32, [vp, vp, vp, d]),
+            "orc_lbfgs_create_external": (vp, [i64, i32, i32, i32, FETCH_FN, vp]),
+            "orc_lbfgs_last_dots": (c_dp, [vp, ctypes.POINTER(i32)]),
             "orc_lsr1_create": (vp, [i64, i32, i32]), "orc_lsr1_destroy": (None, [vp]),
             "orc_lsr1_apply": (None, [vp, vp, vp, d, d]), "orc_lsr1_push": (i32, [vp, vp, vp]),
             "orc_lsr1_diag": (None, [vp, vp]), "orc_lsr1_reset": (None, [vp]), "orc_lsr1_col": (c_dp, [vp, i32, i32]),
@@ -198,6 +201,8 @@ class LBFGS:
     def __init__(self, n, mem=5, scaling=True, damped=False, sigma2=0.99, sigma3=10.0, inverse=False):
         self.n, self.mem, self.inverse = int(n), max(int(mem), 1), bool(inverse)
         self.h = lib().orc_lbfgs_create(self.n, int(mem), int(scaling), int(damped), sigma2, sigma3, int(inverse))
+        if not self.h or not lib().orc_lbfgs_col(self.h, 0, 0) or not (inverse or lib().orc_lbfgs_col(self.h, 2, 0)):
+            raise MemoryError("oracle L-BFGS state of %d x %d doubles does not fit in host memory" % (self.n, self.mem))
 
     def __del__(self):
         try:
@@ -270,6 +275,22 @@ class LBFGS:
 
     def matrix(self):
         return np.stack([self.apply(e) for e in np.eye(self.n)], axis=1)
+
+
+class ExternalLBFGS(LBFGS):
+    """Apply-only L-BFGS oracle whose columns stay with the caller (full-size parity runs: the state lives on the GPU and is
+    streamed to the host one column at a time).  fetch(which, k0, slot) -> address of a host buffer holding column k0 of
+    'syab'[which]; slot in {0, 1} says which of the caller's two buffers to use.  The apply code is the resident one's."""
+
+    def __init__(self, n, mem, inverse, fetch, scaling=True):
+        self.n, self.mem, self.inverse = int(n), max(int(mem), 1), bool(inverse)
+        self._cb = FETCH_FN(lambda user, which, k0, slot: fetch(which, k0, slot))
+        self.h = lib().orc_lbfgs_create_external(self.n, int(mem), int(scaling), int(inverse), self._cb, None)
+
+    def last_dots(self):
+        cnt = ctypes.c_int()
+        p = lib().orc_lbfgs_last_dots(self.h, ctypes.byref(cnt))
+        return np.array([p[i] for i in range(cnt.value)])
 
 
 class LSR1:

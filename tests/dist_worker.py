@@ -117,6 +117,25 @@ def main():
         check_qn(expect_one_launch=False)              # NCCL: one kernel + one all-reduce per inner product
         ctx.connect_mailbox()
         check_qn(expect_one_launch=True)               # NVLink peer mailbox: ONE persistent launch per GPU
+        # mailbox and NCCL all-reduce the same partials: at 2 ranks a+b is order-free, so results must agree bit for bit
+        gm = lo.LBFGSOperator(ns, mem=mem, ctx=ctx)
+        for s, y in P:
+            lo.push_(gm, t(s[lo_:hi_]), t(y[lo_:hi_]))
+        r_mb = (gm * xs).cpu().numpy()
+        d_mb = ctx.debug_read(0, 2 * mem)
+        ctx.set_option("use_mailbox", 0)
+        l0 = ctx.launch_count()
+        r_nc = (gm * xs).cpu().numpy()
+        assert ctx.launch_count() - l0 == 2                       # phase-1 kernel, NCCL all-reduce, phase-2 kernel
+        d_nc = ctx.debug_read(0, 2 * mem)
+        ctx.set_option("use_mailbox", 1)
+        if world == 2:
+            assert d_mb == d_nc and np.array_equal(r_mb, r_nc)
+        else:
+            assert np.allclose(d_mb, d_nc, rtol=1e-14) and np.linalg.norm(r_mb - r_nc) <= 1e-14 * np.linalg.norm(r_nc)
+        assert np.array_equal((gm * xs).cpu().numpy(), r_mb)
+        dbg = ctx.debug_read(768, 3)
+        assert dbg[2] >= 1 and dbg[1] > 0                        # the in-kernel exchange was timed
         ctx.disconnect_mailbox()
         check_qn(expect_one_launch=False)
         # BlockDiagonalOperator, one block per GPU: a LOCAL context (no communicator), block r on rank r, no collective at all

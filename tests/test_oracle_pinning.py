@@ -478,3 +478,34 @@ def test_golden_vectors_v2_matrix_leaves_and_quirks(orc):
     assert 400 < len(nz) < 700
     assert np.allclose(G["sparse_f64_N"], S @ orc.uniform(45, 23), rtol=1e-12, atol=1e-15)
     assert np.allclose(G["sparse_f64_T"], S.T @ orc.uniform(60, 24), rtol=1e-12, atol=1e-15)
+
+
+def test_external_column_oracle_is_the_resident_one():
+    """full-size parity runs stream the state columns from the GPU: same apply code, same bits, same inner products"""
+    import oracle as orc
+    orc.set_mode(True, 1)
+    n, mem = 1003, 4
+    for inverse in (False, True):
+        o = orc.LBFGS(n, mem=mem, inverse=inverse)
+        for i in range(6):
+            s = orc.uniform(n, 100 + i)
+            o.push(s, s + 0.1 * orc.uniform(n, 200 + i))
+        x = orc.uniform(n, 7)
+        ref = o.apply(x)
+        bufs = [np.empty(n), np.empty(n)]
+        calls = []
+
+        def fetch(which, k0, slot):
+            calls.append((which, k0, slot))
+            bufs[slot][:] = o.col("syab"[which], k0)
+            return bufs[slot].ctypes.data
+
+        e = orc.ExternalLBFGS(n, mem, inverse, fetch)
+        e.ys[:] = o.ys
+        e.set_state(o.insert, o.scaling_factor)
+        assert np.array_equal(e.apply(x), ref)
+        d = e.last_dots()
+        assert len(d) == 2 * mem and len(calls) == 4 * mem if inverse else len(calls) == 2 * mem
+        if not inverse:      # a_k.x, b_k.x oldest -> newest
+            k = (o.insert - 1) % mem
+            assert d[0] == orc.dot(o.col("a", k), x) and d[1] == orc.dot(o.col("b", k), x)
