@@ -3,38 +3,53 @@
 // Reference: src/kron.jl:14-40.  prod!:  X = reshape(x, q, n);  res = α·vec(B·X·Aᵀ) + β·res   (A m×n, B p×q, column-major)
 //            tprod!/ctprod!:  X = reshape(x, p, m);  res = α·vec(Bᵀ·X·A) + β·res
 // The reference materialises Matrix(B*X*transpose(A)) through n operator applies (3 GEMVs each).  Here it is exactly two
-// GEMMs on the 5th-generation tensor cores, in ONE cooperative launch:
+// GEMMs on the 5th-generation tensor cores, in ONE plain (non-cooperative) clustered launch:
 //   phase 0   Y[M×N1]  = A1[M×K1] · X'[N1×K1]ᵀ      (fp32 accumulate in TMEM; stored as a bf16 hi/lo pair so that the
-//                                                   intermediate costs no accuracy; 2*M*N1*2 bytes, stays in L2)
-//   phase 1   Z[M×N2]  = [Yhi|Ylo][M×2N1] · [B2|B2]ᵀ    epilogue: res[j*M+i] = α·Z[i,j] (+ β·res), bf16, column-major
+//                                                   intermediate costs no accuracy; stays in L2)
+//   phase 1   Z[M×N2]  = [Yhi|Ylo][M×2N1] · [B2|B2]ᵀ    epilogue: res[j*M+i] = α·Z[i,j] (+ β·res), bf16 or fp32, column-major
 // with every operand K-major (K contiguous) so one code path serves both directions:
 //   prod :  M=p K1=q N1=n N2=m   A1 = B row-major (transposed copy made at create), X' = reshape(x,q,n)ᵀ = x as stored,
 //           B2 = A row-major (transposed copy made at create)
 //   tprod:  M=q K1=p N1=m N2=n   A1 = Bᵀ row-major = B as stored (column-major), X' = x as stored, B2 = Aᵀ row-major = A as stored
-// Per CTA: warp 0 = TMA producer (cp.async.bulk.tensor.2d, 128-byte swizzle, 4-stage mbarrier ring), warp 1 = tcgen05.mma
-// issuer (one elected thread; UMMA 128×BN×16, accumulator in TMEM) + TMEM alloc/dealloc, warps 2-5 = epilogue
-// (tcgen05.ld 32x32b → registers → global).  `nb` right-hand sides are batched by stacking them along N (phase 0) / M (phase 1).
+//
+// Work decomposition (round 2): rows of Z depend only on the same rows of Y, so a 128-row block of one right-hand side is a
+// self-contained UNIT handled by one thread-block CLUSTER of C CTAs -- there is no grid-wide dependency, hence no cooperative
+// launch and no grid barrier.  CTA c of the cluster owns the N tiles c, c+C, ... of both phases.  The A operand of a phase
+// (the 128×K row block of A1, then of [Yhi|Ylo]) is needed by every CTA of the cluster: each CTA fetches 1/C of every k-block
+// and TMA-MULTICASTS it into all C shared memories (the per-row-block operand leaves L2 once per cluster, not once per CTA);
+// smem slots are handed back cluster-wide by tcgen05.commit ... multicast::cluster.  The intermediate is written with TMA
+// stores (UTMASTG) from a swizzled staging tile and published to the cluster through a release/acquire mbarrier in every
+// CTA (y_ready); the B operand of phase 1 is prefetched while that hand-over is in flight.  The result leaves through a TMA
+// store as well (β = 0; the β ≠ 0 read-modify-write keeps direct stores).
+// Per CTA: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected thread; UMMA 128×BN×16, accumulator in TMEM)
+// + TMEM alloc/dealloc, warps 2-5 = epilogue (tcgen05.ld 32x32b → registers → staging → TMA store).
 #include "b2o_internal.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <dlfcn.h>
 #include <algorithm>
 
-constexpr int KR_BM = 128, KR_BK = 64, KR_MAX_STAGES = 12, KR_THREADS = 192;
-// ring depth: the per-SM stream is latency-bound (Little: bytes in flight / L2 latency), so use what shared memory allows
-__host__ __device__ constexpr int kr_stages(int BN) { return (200 * 1024) / (KR_BM * KR_BK * 2 + BN * KR_BK * 2) > KR_MAX_STAGES ? KR_MAX_STAGES : (200 * 1024) / (KR_BM * KR_BK * 2 + BN * KR_BK * 2); }
+constexpr int KR_BM = 128, KR_BK = 64, KR_THREADS = 192;
+constexpr uint32_t KR_A_BYTES = KR_BM * KR_BK * 2;                                   // one 128×64 bf16 k-block of the A operand
+constexpr uint32_t KR_SMEM_LIMIT = 227 * 1024;
+__host__ __device__ constexpr uint32_t kr_b_bytes(int BN) { return (uint32_t)BN * KR_BK * 2; }
+// a ring stage holds TWO (A, B) k-blocks (phase 0: k-blocks 2i, 2i+1; phase 1: Yhi, Ylo k-block i sharing one B2 k-block)
+__host__ __device__ constexpr uint32_t kr_stage_bytes(int BN) { return 2 * KR_A_BYTES + 2 * kr_b_bytes(BN); }
+// epilogue staging: max(Yhi + Ylo tiles, one fp32 result tile) = 512·BN bytes
+__host__ __device__ constexpr uint32_t kr_staging_bytes(int BN) { return 512u * (uint32_t)BN; }
+__host__ __device__ constexpr int kr_stages(int BN) {
+  return (int)((KR_SMEM_LIMIT - 2048 - kr_staging_bytes(BN)) / kr_stage_bytes(BN)) > 6 ? 6 : (int)((KR_SMEM_LIMIT - 2048 - kr_staging_bytes(BN)) / kr_stage_bytes(BN));
+}
 
 struct KronArgs {
   int M, K1, N1, N2, nb;        // see header comment; phase-1 K = N1
-  int ldy;                      // N1 rounded up to 64; a Y row holds [hi: ldy | lo: ldy] elements
-  __nv_bfloat16 *Y;             // [(nb*M) × 2*ldy], padding columns stay zero
+  int ldy;                      // N1 rounded up to 128; a Y row holds [hi: ldy | lo: ldy] elements
+  int rblocks, units;           // 128-row blocks per right-hand side; units = nb * rblocks
   void *res;                    // nb × (M*N2), each column-major M×N2; bf16 or (out_f32) fp32
-  int out_f32;
+  int out_f32, store_tma;       // store_tma: the result tile leaves through a TMA store (beta == 0, 16-byte aligned res)
   float alpha, beta;
-  unsigned long long *bar;
-  unsigned long long bar_target;
   unsigned long long *dbg;      // optional timeline of CTA 0 (%globaltimer, ns): [0] start [1] setup done [2+4*ph] first stage landed
-                                // [3+4*ph] accumulator complete [4+4*ph] epilogue done [5+4*ph] phase end/barrier passed [10] exit
+                                // [3+4*ph] accumulator complete [4+4*ph] epilogue done [5] Y published cluster-wide [10] exit
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -47,16 +62,101 @@ __device__ __forceinline__ unsigned long long gtimer() {
     if (p.dbg && blockIdx.x == 0) p.dbg[idx] = gtimer();                  \
   } while (0)
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t nclusters_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive (release, cluster scope) on the mbarrier at the same shared-memory offset in CTA `cta` of this cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tm, int c0, int c1, uint64_t *bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
                    smem_u32(smem_dst)),
                "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *tm, int c0, int c1, int c2, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+               : "memory");
+}
+// multicast: the box lands at the same CTA-relative offset in every CTA of `mask`, completing bytes on each one's mbarrier
+__device__ __forceinline__ void tma_load_2d_mc(void *smem_dst, const CUtensorMap *tm, int c0, int c1, uint64_t *bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(void *smem_dst, const CUtensorMap *tm, int c0, int c1, int c2, uint64_t *bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *tm, const void *smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tm), "r"(smem_u32(smem_src)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrives on the mbarrier at this offset in every CTA of `mask` when the MMAs issued so far have read their operands
+__device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
@@ -89,205 +189,267 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(const void *smem) {
   return d;
 }
 
-// the kron launch is latency-bound (tens of CTAs): poll the barrier without sleeping
-__device__ __forceinline__ void grid_barrier_tight(unsigned long long *ctr, unsigned long long target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(ctr, 1ULL);
-    while (ld_acquire_u64(ctr) < target) {}
-    __threadfence();
-  }
-  __syncthreads();
-}
-
 // epilogue helpers: the per-element branches (result type, beta, bounds) are hoisted out of the 32-column loops
 template <bool F32, bool BETA>
 __device__ __forceinline__ void kron_store_cols(void *res, size_t off, int M, float alpha, float beta, const uint32_t (&v)[32], int nvalid) {
-  if (nvalid >= 32) {
 #pragma unroll
-    for (int e = 0; e < 32; ++e) {
-      float z = alpha * __uint_as_float(v[e]);
-      if (F32) {
-        float *dst = reinterpret_cast<float *>(res) + off + (size_t)e * M;
-        if (BETA) z += beta * *dst;
-        *dst = z;
-      } else {
-        __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(res) + off + (size_t)e * M;
-        if (BETA) z += beta * __bfloat162float(*dst);
-        *dst = __float2bfloat16_rn(z);
-      }
-    }
-  } else {
-#pragma unroll
-    for (int e = 0; e < 32; ++e) {
-      if (e >= nvalid) continue;   // static register indices: v[] must stay in registers
-      float z = alpha * __uint_as_float(v[e]);
-      if (F32) {
-        float *dst = reinterpret_cast<float *>(res) + off + (size_t)e * M;
-        if (BETA) z += beta * *dst;
-        *dst = z;
-      } else {
-        __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(res) + off + (size_t)e * M;
-        if (BETA) z += beta * __bfloat162float(*dst);
-        *dst = __float2bfloat16_rn(z);
-      }
+  for (int e = 0; e < 32; ++e) {
+    if (e >= nvalid) continue;   // static register indices: v[] must stay in registers
+    float z = alpha * __uint_as_float(v[e]);
+    if (F32) {
+      float *dst = reinterpret_cast<float *>(res) + off + (size_t)e * M;
+      if (BETA) z += beta * *dst;
+      *dst = z;
+    } else {
+      __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(res) + off + (size_t)e * M;
+      if (BETA) z += beta * __bfloat162float(*dst);
+      *dst = __float2bfloat16_rn(z);
     }
   }
 }
 
 template <int BN>
 __global__ void __launch_bounds__(KR_THREADS, 1)
-kron_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmX,
-                      const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmB2,
-                      const __grid_constant__ KronArgs p) {
-  constexpr uint32_t A_BYTES = KR_BM * KR_BK * 2, B_BYTES = BN * KR_BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int KR_STAGES = kr_stages(BN);
+kron_cluster_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmX,
+                    const __grid_constant__ CUtensorMap tmYld, const __grid_constant__ CUtensorMap tmB2,
+                    const __grid_constant__ CUtensorMap tmYhi, const __grid_constant__ CUtensorMap tmYlo,
+                    const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ KronArgs p) {
+  constexpr uint32_t A_BYTES = KR_A_BYTES, B_BYTES = kr_b_bytes(BN), STAGE_BYTES = kr_stage_bytes(BN);
+  constexpr int ST = kr_stages(BN);
+  constexpr int YB = BN < 64 ? BN : 64;                  // columns per Y staging box (TMA swizzle span: 64 or 128 bytes)
+  constexpr int NYB = BN / YB;                           // Y staging boxes per half
+  static_assert(ST >= 2, "ring too shallow");
   // instruction descriptor: D=F32, A=B=BF16, both K-major, N=BN, M=128
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(KR_BM >> 4) << 24);
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SW128 needs 1024 B
-  __shared__ __align__(8) uint64_t full[KR_STAGES], empty[KR_STAGES], tmem_full, tmem_empty;
+  unsigned char *staging = smem + (size_t)ST * STAGE_BYTES;
+  __shared__ __align__(8) uint64_t full[ST], empty[ST], tmem_full, tmem_empty, y_ready;
   __shared__ uint32_t s_tmem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t C = cluster_nctarank(), crank = cluster_ctarank();
+  const uint16_t mc_mask = (uint16_t)((1u << C) - 1u);
+  const int slice_rows = KR_BM / (int)C;                 // rows of every A k-block this CTA fetches for the whole cluster
+  const uint32_t slice_bytes = A_BYTES / C;
   if (threadIdx.x == 0) KR_STAMP(0);
   if (threadIdx.x == 32) {   // hide the descriptor fetches behind the setup
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmYld) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmYhi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmYlo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmRes) : "memory");
   }
-
   if (threadIdx.x == 0) {
-    for (int s = 0; s < KR_STAGES; ++s) {
+    for (int s = 0; s < ST; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], C);       // one multicast commit from every CTA of the cluster
     }
     mbar_init(&tmem_full, 1);
     mbar_init(&tmem_empty, 4);
+    mbar_init(&y_ready, C);          // one remote arrive from every CTA's Y store
     mbar_fence_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"((uint32_t)(BN < 32 ? 32 : BN)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                // every CTA's barriers exist before any peer multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
   if (threadIdx.x == 0) KR_STAMP(1);
 
-  uint32_t stage = 0, sphase = 0;   // smem ring position (producer and MMA warp each keep their own copy)
-  uint32_t tphase = 0;              // accumulator hand-over parity (MMA warp and epilogue warps)
-  unsigned long long bar_target = p.bar_target;
+  uint32_t stage = 0, sphase = 0;    // smem ring position (producer and MMA warp each keep their own copy)
+  uint32_t tphase = 0;               // accumulator hand-over parity (MMA warp and epilogue warps)
+  uint32_t yphase = 0;               // y_ready parity (one completion per unit)
+  const int kb0 = (p.K1 + KR_BK - 1) / KR_BK, ks0 = (kb0 + 1) / 2;   // phase 0: two k-blocks per stage
+  const int ks1 = (p.N1 + KR_BK - 1) / KR_BK;                        // phase 1: one (hi, lo) k-block pair per stage
+  const int nt0 = (p.N1 + BN - 1) / BN, nt1 = (p.N2 + BN - 1) / BN;
+  const int it0 = (nt0 + (int)C - 1) / (int)C, it1 = (nt1 + (int)C - 1) / (int)C;
 
-  for (int ph = 0; ph < 2; ++ph) {
-    const CUtensorMap *tmA = ph == 0 ? &tmA1 : &tmY;
-    const CUtensorMap *tmB = ph == 0 ? &tmX : &tmB2;
-    const int Mrows = ph == 0 ? p.M : p.nb * p.M;
-    const int Ncols = ph == 0 ? p.nb * p.N1 : p.N2;
-    const int Kdim = ph == 0 ? p.K1 : p.N1;
-    const int mt = (Mrows + KR_BM - 1) / KR_BM, nt = (Ncols + BN - 1) / BN;
-    const int khalf = (Kdim + KR_BK - 1) / KR_BK;
-    const int ntiles = mt * nt, kblocks = ph == 0 ? khalf : 2 * khalf;   // phase 1 runs over the hi and the lo half of Y
-
+  for (int u = (int)cluster_id_x(); u < p.units; u += (int)nclusters_x()) {
+    const int b = u / p.rblocks, m0 = (u - b * p.rblocks) * KR_BM;
+    const bool first_unit = u == (int)cluster_id_x();
     if (warp == 0) {
       // ===== TMA producer
       if (lane == 0) {
-        if (ph == 1) asm volatile("fence.proxy.async;" ::: "memory");   // Y was written with generic-proxy stores
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-          const int m0 = (t / nt) * KR_BM, n0 = (t % nt) * BN;
-          for (int kb = 0; kb < kblocks; ++kb) {
+        for (int it = 0; it < it0; ++it) {
+          const int tile = it * (int)C + (int)crank;
+          const bool valid = tile < nt0;
+          for (int ks = 0; ks < ks0; ++ks) {
+            const int npair = min(2, kb0 - 2 * ks);
             mbar_wait(&empty[stage], sphase ^ 1u);
-            mbar_expect_tx(&full[stage], STAGE_BYTES);
+            mbar_expect_tx(&full[stage], (uint32_t)npair * (A_BYTES + (valid ? B_BYTES : 0u)));
             unsigned char *sa = smem + (size_t)stage * STAGE_BYTES;
-            const int kk = kb < khalf ? kb : kb - khalf;
-            const int ka = (ph == 1 && kb >= khalf) ? p.ldy + kk * KR_BK : kk * KR_BK;
-            tma_load_2d(sa, tmA, ka, m0, &full[stage]);
-            tma_load_2d(sa + A_BYTES, tmB, kk * KR_BK, n0, &full[stage]);
-            if (++stage == KR_STAGES) { stage = 0; sphase ^= 1u; }
+            for (int pr = 0; pr < npair; ++pr) {
+              const int kk = (2 * ks + pr) * KR_BK;
+              if (valid) tma_load_3d(sa + 2 * A_BYTES + pr * B_BYTES, &tmX, kk, tile * BN, b, &full[stage]);
+              if (C > 1) tma_load_2d_mc(sa + pr * A_BYTES + crank * slice_bytes, &tmA1, kk, m0 + (int)crank * slice_rows, &full[stage], mc_mask);
+              else tma_load_2d(sa + pr * A_BYTES, &tmA1, kk, m0, &full[stage]);
+            }
+            if (++stage == ST) { stage = 0; sphase ^= 1u; }
+          }
+        }
+        bool y_waited = false;
+        for (int it = 0; it < it1; ++it) {
+          const int tile = it * (int)C + (int)crank;
+          const bool valid = tile < nt1;
+          for (int ks = 0; ks < ks1; ++ks) {
+            mbar_wait(&empty[stage], sphase ^ 1u);
+            mbar_expect_tx(&full[stage], 2 * A_BYTES + (valid ? B_BYTES : 0u));
+            unsigned char *sa = smem + (size_t)stage * STAGE_BYTES;
+            if (valid) tma_load_2d(sa + 2 * A_BYTES, &tmB2, ks * KR_BK, tile * BN, &full[stage]);   // does not depend on Y: prefetched
+            if (!y_waited) {
+              mbar_wait_cluster(&y_ready, yphase);                     // every CTA of the cluster has stored its Y tiles
+              asm volatile("fence.proxy.async;" ::: "memory");          // ... and the bulk reads below must observe them
+              y_waited = true;
+              if (first_unit) KR_STAMP(5);
+            }
+            const int row = m0 + (int)crank * slice_rows;
+            if (C > 1) {
+              tma_load_3d_mc(sa + crank * slice_bytes, &tmYld, ks * KR_BK, row, b, &full[stage], mc_mask);
+              tma_load_3d_mc(sa + A_BYTES + crank * slice_bytes, &tmYld, p.ldy + ks * KR_BK, row, b, &full[stage], mc_mask);
+            } else {
+              tma_load_3d(sa, &tmYld, ks * KR_BK, row, b, &full[stage]);
+              tma_load_3d(sa + A_BYTES, &tmYld, p.ldy + ks * KR_BK, row, b, &full[stage]);
+            }
+            if (++stage == ST) { stage = 0; sphase ^= 1u; }
           }
         }
       }
       __syncwarp();
     } else if (warp == 1) {
       // ===== MMA issuer
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        mbar_wait(&tmem_empty, tphase ^ 1u);      // epilogue has drained the accumulator of the previous tile
-        tc_fence_after();
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&full[stage], sphase);
-          tc_fence_after();
-          if (lane == 0 && kb == 0 && t == (int)blockIdx.x) KR_STAMP(2 + 4 * ph);
-          if (lane == 0) {
-            unsigned char *sa = smem + (size_t)stage * STAGE_BYTES;
-            const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + A_BYTES);
-#pragma unroll
-            for (int k = 0; k < KR_BK / 16; ++k)   // UMMA_K = 16 bf16 = 32 B: advance the start address inside the swizzle atom
-              tc_mma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (kb | k) ? 1u : 0u);
-            tc_commit(&empty[stage]);              // frees the smem stage when these MMAs have read it
-            if (kb == kblocks - 1) tc_commit(&tmem_full);
+      for (int ph = 0; ph < 2; ++ph) {
+        const int iters = ph == 0 ? it0 : it1, nt = ph == 0 ? nt0 : nt1, ksteps = ph == 0 ? ks0 : ks1;
+        for (int it = 0; it < iters; ++it) {
+          const bool valid = it * (int)C + (int)crank < nt;
+          if (valid) {
+            mbar_wait(&tmem_empty, tphase ^ 1u);      // epilogue has drained the accumulator of the previous tile
+            tc_fence_after();
           }
-          __syncwarp();
-          if (++stage == KR_STAGES) { stage = 0; sphase ^= 1u; }
+          for (int ks = 0; ks < ksteps; ++ks) {
+            mbar_wait(&full[stage], sphase);
+            tc_fence_after();
+            if (lane == 0 && ks == 0 && it == 0 && first_unit) KR_STAMP(2 + 4 * ph);
+            if (lane == 0) {
+              unsigned char *sa = smem + (size_t)stage * STAGE_BYTES;
+              if (valid) {
+                const int npair = ph == 0 ? min(2, kb0 - 2 * ks) : 2;
+                for (int pr = 0; pr < npair; ++pr) {
+                  const uint64_t adesc = umma_desc_sw128(sa + pr * A_BYTES);
+                  const uint64_t bdesc = umma_desc_sw128(sa + 2 * A_BYTES + (ph == 0 ? pr * B_BYTES : 0u));
+#pragma unroll
+                  for (int k = 0; k < KR_BK / 16; ++k)   // UMMA_K = 16 bf16 = 32 B: advance the start address inside the swizzle atom
+                    tc_mma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (ks | pr | k) ? 1u : 0u);
+                }
+              }
+              // hand the slot back to EVERY producer of the cluster (their multicasts write into this CTA's copy too)
+              if (C > 1) tc_commit_mc(&empty[stage], mc_mask);
+              else tc_commit(&empty[stage]);
+              if (valid && ks == ksteps - 1) tc_commit(&tmem_full);
+            }
+            __syncwarp();
+            if (++stage == ST) { stage = 0; sphase ^= 1u; }
+          }
+          if (valid) tphase ^= 1u;
         }
-        tphase ^= 1u;
       }
     } else {
       // ===== epilogue: warp w owns TMEM lanes [32*(w%4), +32) = rows of the tile
       const int quarter = warp & 3;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int m0 = (t / nt) * KR_BM, n0 = (t % nt) * BN;
-        mbar_wait(&tmem_full, tphase);
-        tc_fence_after();
-        if (warp == 2 && lane == 0 && t == (int)blockIdx.x) KR_STAMP(3 + 4 * ph);
-        const int r = m0 + quarter * 32 + lane;    // global row of this thread
+      const int rloc = quarter * 32 + lane;      // row inside the 128-row block
+      const bool issuer = threadIdx.x == 64;
+      // ---- phase 0: Y tile -> bf16 hi/lo -> swizzled staging -> TMA store
+      for (int it = 0; it < it0; ++it) {
+        const int tile = it * (int)C + (int)crank;
+        if (tile < nt0) {
+          mbar_wait(&tmem_full, tphase);
+          tc_fence_after();
+          if (warp == 2 && lane == 0 && it == 0 && first_unit) KR_STAMP(3);
+          if (issuer) tma_store_wait_read();      // the staging tile of the previous store has been read
+          epi_sync();
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-          if (ph == 1 && warp == 2 && lane == 0 && t == (int)blockIdx.x) KR_STAMP(11 + 2 * (c0 / 32));
-          if (r < Mrows) {
-            if (ph == 0) {
-              // Y[(b*M + r) * 2*ldy + j] (hi) / + ldy (lo), global column jj = b*N1 + j
-              const int jj0 = n0 + c0;
-              const int b0 = jj0 / p.N1, j0 = jj0 - b0 * p.N1;
-              if (jj0 + 32 <= Ncols && j0 + 32 <= p.N1) {
-                // fast path: the 32 columns belong to one right-hand side; 16-byte stores (j0 is a multiple of 8, ldy of 64)
-                __nv_bfloat16 *dst = p.Y + ((size_t)b0 * p.M + r) * (2 * (size_t)p.ldy) + j0;
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
 #pragma unroll
-                for (int g = 0; g < 32; g += 8) {
-                  uint32_t hi[4], lo[4];
+            for (int g = 0; g < 32; g += 8) {
+              uint32_t hi[4], lo[4];
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float y0 = __uint_as_float(v[g + 2 * e]), y1 = __uint_as_float(v[g + 2 * e + 1]);
-                    const __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
-                    const __nv_bfloat162 l = __floats2bfloat162_rn(y0 - __low2float(h), y1 - __high2float(h));
-                    hi[e] = *reinterpret_cast<const uint32_t *>(&h);
-                    lo[e] = *reinterpret_cast<const uint32_t *>(&l);
-                  }
-                  *reinterpret_cast<uint4 *>(dst + g) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                  *reinterpret_cast<uint4 *>(dst + g + p.ldy) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                }
-              } else {
-#pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                  const int jje = jj0 + e;
-                  if (jje < Ncols) {
-                    const int be = jje / p.N1, je = jje - be * p.N1;
-                    const float y = __uint_as_float(v[e]);
-                    const __nv_bfloat16 h = __float2bfloat16_rn(y);
-                    __nv_bfloat16 *d1 = p.Y + ((size_t)be * p.M + r) * (2 * (size_t)p.ldy) + je;
-                    d1[0] = h;
-                    d1[p.ldy] = __float2bfloat16_rn(y - __bfloat162float(h));
-                  }
-                }
+              for (int e = 0; e < 4; ++e) {
+                const float y0 = __uint_as_float(v[g + 2 * e]), y1 = __uint_as_float(v[g + 2 * e + 1]);
+                const __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
+                const __nv_bfloat162 l = __floats2bfloat162_rn(y0 - __low2float(h), y1 - __high2float(h));
+                hi[e] = *reinterpret_cast<const uint32_t *>(&h);
+                lo[e] = *reinterpret_cast<const uint32_t *>(&l);
               }
-            } else {
-              // res_b[j*M + i] = α·Z (+ β·res), rows r = b*M + i; lanes of a warp write consecutive i: coalesced
-              const int b = r / p.M, i = r - b * p.M;
-              const size_t off = (size_t)b * p.M * p.N2 + i + (size_t)(n0 + c0) * p.M;
-              const int nvalid = Ncols - (n0 + c0);
+              // staging box = [128 rows][YB cols] bf16, rows of YB*2 bytes, TMA 128-/64-byte swizzle on the 16-byte chunk index
+              const int col = c0 + g, box = col / YB, chunk = (col % YB) / 8;
+              const int sw = (YB == 64) ? (chunk ^ (rloc & 7)) : (chunk ^ ((rloc >> 1) & 3));
+              unsigned char *dst = staging + (size_t)box * (KR_BM * YB * 2) + (size_t)rloc * (YB * 2) + sw * 16;
+              *reinterpret_cast<uint4 *>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4 *>(dst + (size_t)NYB * (KR_BM * YB * 2)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty);
+          fence_proxy_async_smem();               // staging writes -> visible to the bulk store
+          epi_sync();
+          if (issuer) {
+#pragma unroll
+            for (int bx = 0; bx < NYB; ++bx) {
+              tma_store_3d(&tmYhi, staging + (size_t)bx * (KR_BM * YB * 2), tile * BN + bx * YB, m0, b);
+              tma_store_3d(&tmYlo, staging + (size_t)(NYB + bx) * (KR_BM * YB * 2), tile * BN + bx * YB, m0, b);
+            }
+            tma_store_commit();
+          }
+          tphase ^= 1u;
+        }
+      }
+      if (issuer) {
+        // publish: all Y tiles of this CTA are in global memory -> release-arrive on y_ready of every CTA of the cluster
+        tma_store_wait_all();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __threadfence();
+        for (uint32_t r = 0; r < C; ++r) mbar_arrive_remote(&y_ready, r);
+        if (first_unit) KR_STAMP(4);
+      }
+      // ---- phase 1: result tile
+      for (int it = 0; it < it1; ++it) {
+        const int tile = it * (int)C + (int)crank;
+        if (tile < nt1) {
+          const int n0 = tile * BN;
+          mbar_wait(&tmem_full, tphase);
+          tc_fence_after();
+          if (warp == 2 && lane == 0 && it == 0 && first_unit) KR_STAMP(7);
+          if (p.store_tma) {
+            if (issuer) tma_store_wait_read();
+            epi_sync();
+          }
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+            if (p.store_tma) {
+              // staging tile [BN cols (j)][128 rows (i)]: lanes write consecutive i -> conflict-free, no swizzle needed
+              if (p.out_f32) {
+                float *st = reinterpret_cast<float *>(staging) + (size_t)c0 * KR_BM + rloc;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) st[(size_t)e * KR_BM] = p.alpha * __uint_as_float(v[e]);
+              } else {
+                __nv_bfloat16 *st = reinterpret_cast<__nv_bfloat16 *>(staging) + (size_t)c0 * KR_BM + rloc;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) st[(size_t)e * KR_BM] = __float2bfloat16_rn(p.alpha * __uint_as_float(v[e]));
+              }
+            } else if (m0 + rloc < p.M) {
+              // res_b[j*M + i] = α·Z (+ β·res); lanes of a warp write consecutive i: coalesced
+              const size_t off = (size_t)b * p.M * p.N2 + (size_t)(m0 + rloc) + (size_t)(n0 + c0) * p.M;
+              const int nvalid = p.N2 - (n0 + c0);
               if (nvalid > 0) {
                 if (p.out_f32) {
                   if (p.beta != 0.f) kron_store_cols<true, true>(p.res, off, p.M, p.alpha, p.beta, v, nvalid);
@@ -299,26 +461,30 @@ kron_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_con
               }
             }
           }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty);
+          if (p.store_tma) {
+            fence_proxy_async_smem();
+            epi_sync();
+            if (issuer) {
+              tma_store_3d(&tmRes, staging, m0, n0, b);
+              tma_store_commit();
+            }
+          }
+          if (warp == 2 && lane == 0 && it == 0 && first_unit) KR_STAMP(8);
+          tphase ^= 1u;
         }
-        tc_fence_before();
-        __syncwarp();
-        if (ph == 1 && warp == 2 && lane == 0 && t == (int)blockIdx.x) KR_STAMP(15);
-        if (lane == 0) mbar_arrive(&tmem_empty);
-        if (warp == 2 && lane == 0 && t == (int)blockIdx.x) KR_STAMP(4 + 4 * ph);
-        tphase ^= 1u;
       }
-      if (ph == 0) asm volatile("fence.proxy.async;" ::: "memory");
     }
-    if (ph == 0) {
-      grid_barrier_tight(p.bar, bar_target);   // all of Y is written before any CTA starts streaming it
-      bar_target += gridDim.x;
-      if (threadIdx.x == 0) KR_STAMP(5);
-    }
+    yphase ^= 1u;
   }
+  if (threadIdx.x == 64) tma_store_wait_all();      // bulk stores must have left shared memory before the CTA exits
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                               // no peer may still multicast into / arrive on this CTA after it exits
   if (threadIdx.x == 0) KR_STAMP(10);
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(BN < 32 ? 32 : BN)) : "memory");
 }
 
 // column-major (rows×cols, ld=rows) -> row-major copy with pitch `ldo`
