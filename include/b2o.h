@@ -214,10 +214,18 @@ int b2o_kron_destroy(b2o_kron *k);
  * trans = 1: tprod!/ctprod!  res = alpha*vec(B^T X A) + beta*res, X = reshape(x, p, m)   (:23-40)
  * x / res hold nb vectors back to back (nb = 1 is the reference call); *_len are the per-vector lengths.
  * res_dtype: B2O_BF16 (the reference's promoted element type; the final rounding alone is 2^-9 relative) or B2O_F32.
- * One cooperative launch: TMA -> tcgen05.mma (fp32 accumulate in TMEM) -> bf16 hi/lo intermediate in L2 -> tcgen05.mma. */
+ * One plain clustered launch (a cluster of CTAs per 128-row block, no grid-wide dependency): multicast TMA -> tcgen05.mma (fp32
+ * accumulate in TMEM) -> bf16 hi/lo intermediate (TMA store, stays in L2, published cluster-wide through an mbarrier) ->
+ * tcgen05.mma -> TMA store of the result. */
 int b2o_kron_apply(b2o_kron *k, int trans, void *res, int res_dtype, int64_t res_len, const void *x, int64_t x_len, int nb,
                    double alpha, double beta);
 int b2o_kron_flops(b2o_kron *k, int nb, double *flops);
+/* tuning overrides: "cluster" (0 auto | 1, 2, 4, 8, 16 CTAs per unit), "tile_m" (0 auto | 64, 128 rows per unit),
+ * "tile_n" (0 auto | 32, 64, 128 columns per CTA tile) */
+int b2o_kron_set_option(b2o_kron *k, const char *key, int64_t value);
+/* measurement aid: an EMPTY kernel launched with a kron configuration's grid, cluster size and dynamic shared memory, so the launch
+ * overhead inside an event-timed kron figure can be stated (honours the ctx option "time_kernels") */
+int b2o_kron_launch_floor(b2o_ctx *ctx, int grid, int cluster, int64_t smem_bytes);
 
 /* ---- LinearOperator(M), dense matrix leaf (src/constructors.jl:15-29) --------------------------- */
 /* M: COLUMN-major (Julia layout) m x n device matrix, leading dimension lda >= max(1,m), dtype B2O_F64 or B2O_F32, aligned to

@@ -29,22 +29,23 @@
 #include <dlfcn.h>
 #include <algorithm>
 
-constexpr int KR_BM = 128, KR_BK = 64, KR_THREADS = 192;
-constexpr uint32_t KR_A_BYTES = KR_BM * KR_BK * 2;                                   // one 128×64 bf16 k-block of the A operand
+constexpr int KR_BK = 64, KR_THREADS = 192;
 constexpr uint32_t KR_SMEM_LIMIT = 227 * 1024;
+__host__ __device__ constexpr uint32_t kr_a_bytes(int BM) { return (uint32_t)BM * KR_BK * 2; }   // one BM×64 bf16 k-block of the A operand
 __host__ __device__ constexpr uint32_t kr_b_bytes(int BN) { return (uint32_t)BN * KR_BK * 2; }
 // a ring stage holds TWO (A, B) k-blocks (phase 0: k-blocks 2i, 2i+1; phase 1: Yhi, Ylo k-block i sharing one B2 k-block)
-__host__ __device__ constexpr uint32_t kr_stage_bytes(int BN) { return 2 * KR_A_BYTES + 2 * kr_b_bytes(BN); }
-// epilogue staging: max(Yhi + Ylo tiles, one fp32 result tile) = 512·BN bytes
-__host__ __device__ constexpr uint32_t kr_staging_bytes(int BN) { return 512u * (uint32_t)BN; }
-__host__ __device__ constexpr int kr_stages(int BN) {
-  return (int)((KR_SMEM_LIMIT - 2048 - kr_staging_bytes(BN)) / kr_stage_bytes(BN)) > 6 ? 6 : (int)((KR_SMEM_LIMIT - 2048 - kr_staging_bytes(BN)) / kr_stage_bytes(BN));
+__host__ __device__ constexpr uint32_t kr_stage_bytes(int BM, int BN) { return 2 * kr_a_bytes(BM) + 2 * kr_b_bytes(BN); }
+// epilogue staging: max(Yhi + Ylo tiles, one fp32 result tile) = 4·BM·BN bytes
+__host__ __device__ constexpr uint32_t kr_staging_bytes(int BM, int BN) { return 4u * (uint32_t)BM * (uint32_t)BN; }
+__host__ __device__ constexpr int kr_stages(int BM, int BN) {
+  return (int)((KR_SMEM_LIMIT - 2048 - kr_staging_bytes(BM, BN)) / kr_stage_bytes(BM, BN)) > 8 ? 8
+                                                                                                : (int)((KR_SMEM_LIMIT - 2048 - kr_staging_bytes(BM, BN)) / kr_stage_bytes(BM, BN));
 }
 
 struct KronArgs {
   int M, K1, N1, N2, nb;        // see header comment; phase-1 K = N1
   int ldy;                      // N1 rounded up to 128; a Y row holds [hi: ldy | lo: ldy] elements
-  int rblocks, units;           // 128-row blocks per right-hand side; units = nb * rblocks
+  int rblocks, units;           // BM-row blocks per right-hand side; units = nb * rblocks
   void *res;                    // nb × (M*N2), each column-major M×N2; bf16 or (out_f32) fp32
   int out_f32, store_tma;       // store_tma: the result tile leaves through a TMA store (beta == 0, 16-byte aligned res)
   float alpha, beta;
@@ -82,16 +83,29 @@ __device__ __forceinline__ uint32_t nclusters_x() {
   asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
   return r;
 }
+// true in exactly one (converged) lane of the warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred e;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, e;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive (release, cluster scope) on the mbarrier at the same shared-memory offset in CTA `cta` of this cluster
+// arrive (relaxed; the caller issues ONE fence.acq_rel.cluster before the loop over peers -- a release per arrive costs
+// ~0.25 us each) on the mbarrier at the same shared-memory offset in CTA `cta` of this cluster
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t cta) {
   asm volatile(
       "{\n"
       ".reg .b32 ra;\n"
       "mapa.shared::cluster.u32 ra, %0, %1;\n"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n"
       "}\n" ::"r"(smem_u32(bar)),
       "r"(cta)
       : "memory");
@@ -168,6 +182,13 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+
+// The producer / MMA warps run their loops with all 32 lanes converged and take ONE `elect_one()` branch per ring stage for
+// the single-thread instructions.  Written the obvious way (`if (lane == 0) { ... }`) ptxas cannot tell that the branch is
+// single-threaded, keeps descriptors / addresses in per-thread registers and wraps every UTCHMMA / UTMALDG in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop: ~140 clk per tcgen05.mma, 4x the MMA itself (measured: stage hand-overs
+// 0.6 us apart whatever the tile shape; with the elected branch the four UTCHMMA of a k-block issue back to back with
+// uniform-datapath address arithmetic -- profiles/r2_kron_timeline.md).
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -208,30 +229,35 @@ __device__ __forceinline__ void kron_store_cols(void *res, size_t off, int M, fl
   }
 }
 
-template <int BN>
+template <int BM, int BN>
 __global__ void __launch_bounds__(KR_THREADS, 1)
 kron_cluster_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmX,
                     const __grid_constant__ CUtensorMap tmYld, const __grid_constant__ CUtensorMap tmB2,
                     const __grid_constant__ CUtensorMap tmYhi, const __grid_constant__ CUtensorMap tmYlo,
                     const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ KronArgs p) {
-  constexpr uint32_t A_BYTES = KR_A_BYTES, B_BYTES = kr_b_bytes(BN), STAGE_BYTES = kr_stage_bytes(BN);
-  constexpr int ST = kr_stages(BN);
+  constexpr uint32_t A_BYTES = kr_a_bytes(BM), B_BYTES = kr_b_bytes(BN), STAGE_BYTES = kr_stage_bytes(BM, BN);
+  constexpr int ST = kr_stages(BM, BN);
+  constexpr int KR_BM = BM;                              // rows of a unit: UMMA M = 128 (one row per TMEM lane) or 64 (16 lanes per quarter)
   constexpr int YB = BN < 64 ? BN : 64;                  // columns per Y staging box (TMA swizzle span: 64 or 128 bytes)
   constexpr int NYB = BN / YB;                           // Y staging boxes per half
   static_assert(ST >= 2, "ring too shallow");
-  // instruction descriptor: D=F32, A=B=BF16, both K-major, N=BN, M=128
+  // instruction descriptor: D=F32, A=B=BF16, both K-major, N=BN, M=BM
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(KR_BM >> 4) << 24);
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SW128 needs 1024 B
   unsigned char *staging = smem + (size_t)ST * STAGE_BYTES;
   __shared__ __align__(8) uint64_t full[ST], empty[ST], tmem_full, tmem_empty, y_ready;
   __shared__ uint32_t s_tmem;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t C = cluster_nctarank(), crank = cluster_ctarank();
+  // warp index through a shuffle: ptxas then KNOWS it is warp-uniform and keeps the role loops' addresses, descriptors and
+  // barrier handles in uniform registers (UTCHMMA / UTMALDG take UR operands)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t C = __shfl_sync(0xffffffffu, cluster_nctarank(), 0), crank = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);
+  const int cid = __shfl_sync(0xffffffffu, (int)cluster_id_x(), 0), ncl = __shfl_sync(0xffffffffu, (int)nclusters_x(), 0);
   const uint16_t mc_mask = (uint16_t)((1u << C) - 1u);
-  const int slice_rows = KR_BM / (int)C;                 // rows of every A k-block this CTA fetches for the whole cluster
-  const uint32_t slice_bytes = A_BYTES / C;
-  if (threadIdx.x == 0) KR_STAMP(0);
+  if (threadIdx.x == 0) {
+    KR_STAMP(0);
+    if (p.dbg && blockIdx.x == 0) p.dbg[32] = (unsigned long long)clock64();
+  }
   if (threadIdx.x == 32) {   // hide the descriptor fetches behind the setup
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
@@ -270,57 +296,63 @@ kron_cluster_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
   const int nt0 = (p.N1 + BN - 1) / BN, nt1 = (p.N2 + BN - 1) / BN;
   const int it0 = (nt0 + (int)C - 1) / (int)C, it1 = (nt1 + (int)C - 1) / (int)C;
 
-  for (int u = (int)cluster_id_x(); u < p.units; u += (int)nclusters_x()) {
+  for (int u = cid; u < p.units; u += ncl) {
     const int b = u / p.rblocks, m0 = (u - b * p.rblocks) * KR_BM;
-    const bool first_unit = u == (int)cluster_id_x();
+    const bool first_unit = u == cid;
     if (warp == 0) {
-      // ===== TMA producer
-      if (lane == 0) {
-        for (int it = 0; it < it0; ++it) {
-          const int tile = it * (int)C + (int)crank;
-          const bool valid = tile < nt0;
-          for (int ks = 0; ks < ks0; ++ks) {
-            const int npair = min(2, kb0 - 2 * ks);
-            mbar_wait(&empty[stage], sphase ^ 1u);
+      // ===== TMA producer: all 32 lanes run the loops and wait on the barriers; ONE elected lane per stage issues
+      for (int it = 0; it < it0; ++it) {
+        const int tile = it * (int)C + (int)crank;
+        const bool valid = tile < nt0;
+        for (int ks = 0; ks < ks0; ++ks) {
+          const int npair = min(2, kb0 - 2 * ks);
+          mbar_wait(&empty[stage], sphase ^ 1u);
+          if (elect_one()) {
             mbar_expect_tx(&full[stage], (uint32_t)npair * (A_BYTES + (valid ? B_BYTES : 0u)));
             unsigned char *sa = smem + (size_t)stage * STAGE_BYTES;
             for (int pr = 0; pr < npair; ++pr) {
               const int kk = (2 * ks + pr) * KR_BK;
               if (valid) tma_load_3d(sa + 2 * A_BYTES + pr * B_BYTES, &tmX, kk, tile * BN, b, &full[stage]);
-              if (C > 1) tma_load_2d_mc(sa + pr * A_BYTES + crank * slice_bytes, &tmA1, kk, m0 + (int)crank * slice_rows, &full[stage], mc_mask);
-              else tma_load_2d(sa + pr * A_BYTES, &tmA1, kk, m0, &full[stage]);
+              // the A operand is shared by the cluster: k-block j is fetched by CTA j mod C and multicast to all C
+              if (C == 1) tma_load_2d(sa + pr * A_BYTES, &tmA1, kk, m0, &full[stage]);
+              else if ((uint32_t)(2 * ks + pr) % C == crank) tma_load_2d_mc(sa + pr * A_BYTES, &tmA1, kk, m0, &full[stage], mc_mask);
             }
-            if (++stage == ST) { stage = 0; sphase ^= 1u; }
           }
-        }
-        bool y_waited = false;
-        for (int it = 0; it < it1; ++it) {
-          const int tile = it * (int)C + (int)crank;
-          const bool valid = tile < nt1;
-          for (int ks = 0; ks < ks1; ++ks) {
-            mbar_wait(&empty[stage], sphase ^ 1u);
-            mbar_expect_tx(&full[stage], 2 * A_BYTES + (valid ? B_BYTES : 0u));
-            unsigned char *sa = smem + (size_t)stage * STAGE_BYTES;
-            if (valid) tma_load_2d(sa + 2 * A_BYTES, &tmB2, ks * KR_BK, tile * BN, &full[stage]);   // does not depend on Y: prefetched
-            if (!y_waited) {
-              mbar_wait_cluster(&y_ready, yphase);                     // every CTA of the cluster has stored its Y tiles
-              asm volatile("fence.proxy.async;" ::: "memory");          // ... and the bulk reads below must observe them
-              y_waited = true;
-              if (first_unit) KR_STAMP(5);
-            }
-            const int row = m0 + (int)crank * slice_rows;
-            if (C > 1) {
-              tma_load_3d_mc(sa + crank * slice_bytes, &tmYld, ks * KR_BK, row, b, &full[stage], mc_mask);
-              tma_load_3d_mc(sa + A_BYTES + crank * slice_bytes, &tmYld, p.ldy + ks * KR_BK, row, b, &full[stage], mc_mask);
-            } else {
-              tma_load_3d(sa, &tmYld, ks * KR_BK, row, b, &full[stage]);
-              tma_load_3d(sa + A_BYTES, &tmYld, p.ldy + ks * KR_BK, row, b, &full[stage]);
-            }
-            if (++stage == ST) { stage = 0; sphase ^= 1u; }
-          }
+          __syncwarp();
+          if (++stage == ST) { stage = 0; sphase ^= 1u; }
         }
       }
-      __syncwarp();
+      bool y_waited = false;
+      for (int it = 0; it < it1; ++it) {
+        const int tile = it * (int)C + (int)crank;
+        const bool valid = tile < nt1;
+        for (int ks = 0; ks < ks1; ++ks) {
+          mbar_wait(&empty[stage], sphase ^ 1u);
+          unsigned char *sa = smem + (size_t)stage * STAGE_BYTES;
+          if (elect_one()) {
+            mbar_expect_tx(&full[stage], 2 * A_BYTES + (valid ? B_BYTES : 0u));
+            if (valid) tma_load_2d(sa + 2 * A_BYTES, &tmB2, ks * KR_BK, tile * BN, &full[stage]);   // does not depend on Y: prefetched
+          }
+          __syncwarp();
+          if (!y_waited) {
+            mbar_wait_cluster(&y_ready, yphase);                     // every CTA of the cluster has stored its Y tiles
+            asm volatile("fence.proxy.async;" ::: "memory");          // ... and the bulk reads below must observe them
+            y_waited = true;
+            if (lane == 0 && first_unit) KR_STAMP(5);
+          }
+          if (elect_one()) {
+            if (C == 1) {
+              tma_load_3d(sa, &tmYld, ks * KR_BK, m0, b, &full[stage]);
+              tma_load_3d(sa + A_BYTES, &tmYld, p.ldy + ks * KR_BK, m0, b, &full[stage]);
+            } else {
+              if ((uint32_t)(2 * ks) % C == crank) tma_load_3d_mc(sa, &tmYld, ks * KR_BK, m0, b, &full[stage], mc_mask);
+              if ((uint32_t)(2 * ks + 1) % C == crank) tma_load_3d_mc(sa + A_BYTES, &tmYld, p.ldy + ks * KR_BK, m0, b, &full[stage], mc_mask);
+            }
+          }
+          __syncwarp();
+          if (++stage == ST) { stage = 0; sphase ^= 1u; }
+        }
+      }
     } else if (warp == 1) {
       // ===== MMA issuer
       for (int ph = 0; ph < 2; ++ph) {
@@ -335,7 +367,8 @@ kron_cluster_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
             mbar_wait(&full[stage], sphase);
             tc_fence_after();
             if (lane == 0 && ks == 0 && it == 0 && first_unit) KR_STAMP(2 + 4 * ph);
-            if (lane == 0) {
+            if (lane == 0 && it == 0 && first_unit && ks < 8) KR_STAMP(16 + 8 * ph + ks);   // arrival of every stage of the first tile
+            if (elect_one()) {      // ONE election per stage; the branch is single-threaded by construction (no waterfall loops)
               unsigned char *sa = smem + (size_t)stage * STAGE_BYTES;
               if (valid) {
                 const int npair = ph == 0 ? min(2, kb0 - 2 * ks) : 2;
@@ -361,7 +394,9 @@ kron_cluster_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
     } else {
       // ===== epilogue: warp w owns TMEM lanes [32*(w%4), +32) = rows of the tile
       const int quarter = warp & 3;
-      const int rloc = quarter * 32 + lane;      // row inside the 128-row block
+      // UMMA M=128: row = TMEM lane.  M=64: rows 16q..16q+15 live in lanes 32q..32q+15 (half sub-partitions), lanes 16-31 idle
+      const bool row_ok = BM == 128 || lane < 16;
+      const int rloc = BM == 128 ? quarter * 32 + lane : quarter * 16 + (lane & 15);      // row inside the unit
       const bool issuer = threadIdx.x == 64;
       // ---- phase 0: Y tile -> bf16 hi/lo -> swizzled staging -> TMA store
       for (int it = 0; it < it0; ++it) {
@@ -376,6 +411,7 @@ kron_cluster_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
           for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
             tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+            if (row_ok) {
 #pragma unroll
             for (int g = 0; g < 32; g += 8) {
               uint32_t hi[4], lo[4];
@@ -394,6 +430,7 @@ kron_cluster_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
               *reinterpret_cast<uint4 *>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               *reinterpret_cast<uint4 *>(dst + (size_t)NYB * (KR_BM * YB * 2)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
+            }
           }
           tc_fence_before();
           __syncwarp();
@@ -403,6 +440,7 @@ kron_cluster_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
           if (issuer) {
 #pragma unroll
             for (int bx = 0; bx < NYB; ++bx) {
+              if (tile * BN + bx * YB >= p.N1) continue;       // box entirely in the padding columns
               tma_store_3d(&tmYhi, staging + (size_t)bx * (KR_BM * YB * 2), tile * BN + bx * YB, m0, b);
               tma_store_3d(&tmYlo, staging + (size_t)(NYB + bx) * (KR_BM * YB * 2), tile * BN + bx * YB, m0, b);
             }
@@ -415,8 +453,8 @@ kron_cluster_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
         // publish: all Y tiles of this CTA are in global memory -> release-arrive on y_ready of every CTA of the cluster
         tma_store_wait_all();
         asm volatile("fence.proxy.async;" ::: "memory");
-        __threadfence();
-        for (uint32_t r = 0; r < C; ++r) mbar_arrive_remote(&y_ready, r);
+        asm volatile("fence.acq_rel.cluster;" ::: "memory");
+        for (uint32_t r = 0; r < C; ++r) mbar_arrive_remote(&y_ready, (crank + 1 + r) % C);   // peers first, own copy last
         if (first_unit) KR_STAMP(4);
       }
       // ---- phase 1: result tile
@@ -436,8 +474,9 @@ kron_cluster_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
             uint32_t v[32];
             tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
             if (p.store_tma) {
-              // staging tile [BN cols (j)][128 rows (i)]: lanes write consecutive i -> conflict-free, no swizzle needed
-              if (p.out_f32) {
+              // staging tile [BN cols (j)][BM rows (i)]: lanes write consecutive i -> conflict-free, no swizzle needed
+              if (!row_ok) {
+              } else if (p.out_f32) {
                 float *st = reinterpret_cast<float *>(staging) + (size_t)c0 * KR_BM + rloc;
 #pragma unroll
                 for (int e = 0; e < 32; ++e) st[(size_t)e * KR_BM] = p.alpha * __uint_as_float(v[e]);
@@ -446,7 +485,7 @@ kron_cluster_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
 #pragma unroll
                 for (int e = 0; e < 32; ++e) st[(size_t)e * KR_BM] = __float2bfloat16_rn(p.alpha * __uint_as_float(v[e]));
               }
-            } else if (m0 + rloc < p.M) {
+            } else if (row_ok && m0 + rloc < p.M) {
               // res_b[j*M + i] = α·Z (+ β·res); lanes of a warp write consecutive i: coalesced
               const size_t off = (size_t)b * p.M * p.N2 + (size_t)(m0 + rloc) + (size_t)(n0 + c0) * p.M;
               const int nvalid = p.N2 - (n0 + c0);
@@ -483,7 +522,10 @@ kron_cluster_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                               // no peer may still multicast into / arrive on this CTA after it exits
-  if (threadIdx.x == 0) KR_STAMP(10);
+  if (threadIdx.x == 0) {
+    KR_STAMP(10);
+    if (p.dbg && blockIdx.x == 0) p.dbg[33] = (unsigned long long)clock64();
+  }
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(BN < 32 ? 32 : BN)) : "memory");
 }
 
@@ -515,34 +557,48 @@ static int load_encode() {
   if (!g_encode) B2O_FAIL(B2O_ECUDA, "cuTensorMapEncodeTiled not found in libcuda");
   return B2O_OK;
 }
-// bf16 matrix [rows][cols], cols contiguous, pitch `ld` elements; box = 64 cols × box_rows rows, 128-byte swizzle, zero OOB fill
-static int make_tmap(CUtensorMap *tm, const void *ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+// rank-2/3 tensor [d2][d1][d0] with d0 contiguous; strides in BYTES for d1, d2; zero OOB fill (loads) / clipping (stores)
+static int make_tmap(CUtensorMap *tm, CUtensorMapDataType dt, int rank, const void *ptr, const uint64_t *dims, const uint64_t *strides_b,
+                     const uint32_t *box, CUtensorMapSwizzle sw) {
   B2O_TRY(load_encode());
-  cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)KR_BK, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) B2O_FAIL(B2O_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu", (int)r,
-                                  (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
+  cuuint64_t d[3], s[2];
+  cuuint32_t b[3], e[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) {
+    d[i] = dims[i];
+    b[i] = box[i];
+  }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = strides_b[i];
+  CUresult r = g_encode(tm, dt, (cuuint32_t)rank, const_cast<void *>(ptr), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    B2O_FAIL(B2O_ECUDA, "cuTensorMapEncodeTiled failed (%d) rank=%d dims=%llu,%llu box=%u,%u", (int)r, rank, (unsigned long long)dims[0],
+             (unsigned long long)dims[1], box[0], box[1]);
   return B2O_OK;
 }
+// bf16 matrix [rows][cols], cols contiguous, pitch `ld` elements; box = 64 cols × box_rows rows, 128-byte swizzle
+static int make_tmap_mat(CUtensorMap *tm, const void *ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  const uint64_t dims[2] = {cols, rows}, str[1] = {ld * 2};
+  const uint32_t box[2] = {(uint32_t)KR_BK, box_rows};
+  return make_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
 
+constexpr int KR_NBN = 3, KR_NBM = 2;         // BN in {128, 64, 32}; BM in {128, 64}
 struct b2o_kron_s {
   b2o_ctx *ctx;
   int m, n, p, q, max_batch;
   const __nv_bfloat16 *A, *B;          // caller's column-major matrices (aliased, like the reference's closures)
-  __nv_bfloat16 *Arm = nullptr, *Brm = nullptr;   // row-major copies, pitch padded to 8
+  __nv_bfloat16 *Arm = nullptr, *Brm = nullptr;   // row-major copies
   int ldArm, ldBrm;
-  __nv_bfloat16 *Y[2] = {nullptr, nullptr};   // [0] prod, [1] tprod workspaces ([hi|lo] rows, zero padded)
+  __nv_bfloat16 *Y[2] = {nullptr, nullptr};   // [0] prod, [1] tprod workspaces: [max_batch][M][hi: ldy | lo: ldy]
   size_t y_elems[2] = {0, 0};
-  CUtensorMap tmA1[2], tmB2[2][3], tmY[2][2];   // [direction][BN index: 128, 64, 32]; fixed operands are encoded once at create
-  int y_rows[2] = {0, 0};              // rows (nb*M) the cached Y map was encoded for
-  CUtensorMap tmX[2];                  // last x map per direction (re-encoded only when x / nb / BN change)
-  const void *x_last[2] = {nullptr, nullptr};
-  int x_nb[2] = {0, 0}, x_bn[2] = {0, 0};
+  // fixed operands are encoded once at create: [direction][...]
+  CUtensorMap tmA1[2][KR_NBM], tmYld[2][KR_NBM];   // box rows = BM
+  CUtensorMap tmB2[2][KR_NBN], tmYhi[2][KR_NBM][KR_NBN], tmYlo[2][KR_NBM][KR_NBN];
+  // per-call descriptors (x, res), re-encoded only when the pointer / batch / tile shape change
+  CUtensorMap tmX[2], tmRes[2];
+  const void *x_last[2] = {nullptr, nullptr}, *res_last[2] = {nullptr, nullptr};
+  int x_nb[2] = {0, 0}, x_bn[2] = {0, 0}, res_nb[2] = {0, 0}, res_bn[2] = {0, 0}, res_bm[2] = {0, 0}, res_f32[2] = {-1, -1};
+  int force_cluster = 0, force_bn = 0, force_bm = 0;   // tuning overrides (b2o_kron_set_option)
 };
 
 static inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
@@ -564,8 +620,10 @@ extern "C" int b2o_kron_create(b2o_ctx *ctx, int dtype, const void *A, int64_t m
   k->B = (const __nv_bfloat16 *)B;
   k->ldArm = (int)n;
   k->ldBrm = (int)q;
-  k->y_elems[0] = (size_t)max_batch * p * 2 * round_up((int)n, 64);
-  k->y_elems[1] = (size_t)max_batch * q * 2 * round_up((int)m, 64);
+  const int ldy[2] = {round_up((int)n, 128), round_up((int)m, 128)};
+  const int Mdir[2] = {(int)p, (int)q};
+  k->y_elems[0] = (size_t)max_batch * p * 2 * ldy[0];
+  k->y_elems[1] = (size_t)max_batch * q * 2 * ldy[1];
   cudaError_t e1 = cudaMalloc(&k->Arm, sizeof(__nv_bfloat16) * m * n), e2 = cudaMalloc(&k->Brm, sizeof(__nv_bfloat16) * p * q),
               e3 = cudaMalloc(&k->Y[0], sizeof(__nv_bfloat16) * k->y_elems[0]),
               e4 = cudaMalloc(&k->Y[1], sizeof(__nv_bfloat16) * k->y_elems[1]);
@@ -575,6 +633,7 @@ extern "C" int b2o_kron_create(b2o_ctx *ctx, int dtype, const void *A, int64_t m
     delete k;
     B2O_FAIL(B2O_ENOMEM, "kron: allocation failed");
   }
+  // padding columns [N1, ldy) of both halves are never stored to and must read as zero in phase 1
   B2O_CUDA(cudaMemsetAsync(k->Y[0], 0, sizeof(__nv_bfloat16) * k->y_elems[0], ctx->stream));
   B2O_CUDA(cudaMemsetAsync(k->Y[1], 0, sizeof(__nv_bfloat16) * k->y_elems[1], ctx->stream));
   dim3 tb(32, 8);
@@ -582,18 +641,35 @@ extern "C" int b2o_kron_create(b2o_ctx *ctx, int dtype, const void *A, int64_t m
   kron_transpose_kernel<<<dim3((p + 31) / 32, (q + 31) / 32), tb, 0, ctx->stream>>>(k->Brm, k->B, (int)p, (int)q, k->ldBrm);
   ctx->launches += 2;
   B2O_CUDA(cudaGetLastError());
-  // prod : A1 = B row-major [p × q], B2 = A row-major [m × n];   tprod: A1 = Bᵀ = [q × p] (B as stored), B2 = Aᵀ = [n × m]
-  int st = make_tmap(&k->tmA1[0], k->Brm, p, q, k->ldBrm, KR_BM);
-  if (st == B2O_OK) st = make_tmap(&k->tmA1[1], k->B, q, p, p, KR_BM);
-  for (int w = 0; w < 3 && st == B2O_OK; ++w) {
-    const int bn = 128 >> w;
-    st = make_tmap(&k->tmB2[0][w], k->Arm, m, n, k->ldArm, bn);                       // prod : B2 = A row-major [m × n]
-    if (st == B2O_OK) st = make_tmap(&k->tmB2[1][w], k->A, n, m, m, bn);              // tprod: B2 = Aᵀ = [n × m], A as stored
+  int st = B2O_OK;
+  for (int mi = 0; mi < KR_NBM && st == B2O_OK; ++mi) {
+    const uint32_t rows = 128u >> mi;
+    // prod : A1 = B row-major [p × q];   tprod: A1 = Bᵀ = [q × p] (B as stored)
+    st = make_tmap_mat(&k->tmA1[0][mi], k->Brm, p, q, k->ldBrm, rows);
+    if (st == B2O_OK) st = make_tmap_mat(&k->tmA1[1][mi], k->B, q, p, p, rows);
+    for (int d = 0; d < 2 && st == B2O_OK; ++d) {   // Y as the phase-1 A operand: [batch][M][2*ldy]
+      const uint64_t dims[3] = {2 * (uint64_t)ldy[d], (uint64_t)Mdir[d], (uint64_t)max_batch};
+      const uint64_t str[2] = {2 * (uint64_t)ldy[d] * 2, (uint64_t)Mdir[d] * 2 * (uint64_t)ldy[d] * 2};
+      const uint32_t box[3] = {(uint32_t)KR_BK, rows, 1};
+      st = make_tmap(&k->tmYld[d][mi], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, k->Y[d], dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    }
+    for (int w = 0; w < KR_NBN && st == B2O_OK; ++w) {
+      const int bn = 128 >> w, yb = std::min(bn, 64);
+      for (int d = 0; d < 2 && st == B2O_OK; ++d) {   // Y store maps: the hi half and the lo half, columns clipped at N1, rows at M
+        const int N1 = d ? (int)m : (int)n;
+        const uint64_t dims[3] = {(uint64_t)N1, (uint64_t)Mdir[d], (uint64_t)max_batch};
+        const uint64_t str[2] = {2 * (uint64_t)ldy[d] * 2, (uint64_t)Mdir[d] * 2 * (uint64_t)ldy[d] * 2};
+        const uint32_t box[3] = {(uint32_t)yb, rows, 1};
+        const CUtensorMapSwizzle sw = yb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+        st = make_tmap(&k->tmYhi[d][mi][w], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, k->Y[d], dims, str, box, sw);
+        if (st == B2O_OK) st = make_tmap(&k->tmYlo[d][mi][w], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, k->Y[d] + ldy[d], dims, str, box, sw);
+      }
+    }
   }
-  if (st == B2O_OK) {                                                                 // Y maps for the full batch capacity
-    const int ldy0 = round_up((int)n, 64), ldy1 = round_up((int)m, 64);
-    st = make_tmap(&k->tmY[0][0], k->Y[0], (uint64_t)max_batch * p, 2 * (uint64_t)ldy0, 2 * (uint64_t)ldy0, KR_BM);
-    if (st == B2O_OK) st = make_tmap(&k->tmY[1][0], k->Y[1], (uint64_t)max_batch * q, 2 * (uint64_t)ldy1, 2 * (uint64_t)ldy1, KR_BM);
+  for (int w = 0; w < KR_NBN && st == B2O_OK; ++w) {
+    const int bn = 128 >> w;
+    st = make_tmap_mat(&k->tmB2[0][w], k->Arm, m, n, k->ldArm, bn);                       // prod : B2 = A row-major [m × n]
+    if (st == B2O_OK) st = make_tmap_mat(&k->tmB2[1][w], k->A, n, m, m, bn);              // tprod: B2 = Aᵀ = [n × m], A as stored
   }
   if (st != B2O_OK) {
     b2o_kron_destroy(k);
@@ -615,18 +691,64 @@ extern "C" int b2o_kron_destroy(b2o_kron *k) {
   return B2O_OK;
 }
 
-template <int BN>
-static int kron_launch(b2o_ctx *c, const CUtensorMap &tA1, const CUtensorMap &tX, const CUtensorMap &tY, const CUtensorMap &tB2,
-                       KronArgs &a, int grid) {
-  const size_t smem = (size_t)kr_stages(BN) * (KR_BM * KR_BK * 2 + BN * KR_BK * 2) + 1024;
+// tuning overrides: "cluster" (0 auto | 1, 2, 4, 8, 16 CTAs per unit), "tile_m" (0 auto | 64, 128 rows per unit), "tile_n" (0 auto | 32, 64, 128)
+extern "C" int b2o_kron_set_option(b2o_kron *k, const char *key, int64_t value) {
+  if (!k || !key) B2O_FAIL(B2O_EARG, "null argument");
+  if (!strcmp(key, "cluster")) {
+    if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16) B2O_FAIL(B2O_EARG, "cluster must be 0, 1, 2, 4, 8 or 16");
+    k->force_cluster = (int)value;
+  } else if (!strcmp(key, "tile_n")) {
+    if (value != 0 && value != 32 && value != 64 && value != 128) B2O_FAIL(B2O_EARG, "tile_n must be 0, 32, 64 or 128");
+    k->force_bn = (int)value;
+  } else if (!strcmp(key, "tile_m")) {
+    if (value != 0 && value != 64 && value != 128) B2O_FAIL(B2O_EARG, "tile_m must be 0, 64 or 128");
+    k->force_bm = (int)value;
+  } else {
+    B2O_FAIL(B2O_EARG, "unknown option '%s'", key);
+  }
+  return B2O_OK;
+}
+
+template <int BM, int BN>
+static int kron_launch(b2o_ctx *c, const CUtensorMap &tA1, const CUtensorMap &tX, const CUtensorMap &tYld, const CUtensorMap &tB2,
+                       const CUtensorMap &tYhi, const CUtensorMap &tYlo, const CUtensorMap &tRes, KronArgs &a, int cluster, int max_clusters) {
+  const size_t smem = (size_t)kr_stages(BM, BN) * kr_stage_bytes(BM, BN) + kr_staging_bytes(BM, BN) + 1024;
   static thread_local bool configured = false;
+  static thread_local int fit[17];                 // co-resident clusters per cluster size (0 = not queried yet)
+  auto kern = kron_cluster_kernel<BM, BN>;
   if (!configured) {
-    B2O_CUDA(cudaFuncSetAttribute(kron_gemm_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2O_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2O_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    memset(fit, 0, sizeof(fit));
     configured = true;
   }
-  void *kargs[] = {(void *)&tA1, (void *)&tX, (void *)&tY, (void *)&tB2, (void *)&a};
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(KR_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = c->stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (!fit[cluster]) {
+    cfg.gridDim = dim3((unsigned)cluster);
+    int nc = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
+    if (e != cudaSuccess || nc < 1) {
+      cudaGetLastError();
+      B2O_FAIL(B2O_ECUDA, "kron: a cluster of %d CTAs with %zu bytes of shared memory does not fit this device", cluster, smem);
+    }
+    fit[cluster] = nc;
+  }
+  // persistent over units: no more clusters than fit at once (the surplus would only queue behind them)
+  const int nclusters = std::max(1, std::min(std::min(a.units, fit[cluster]), max_clusters));
+  cfg.gridDim = dim3((unsigned)(nclusters * cluster));
   if (c->time_kernels) B2O_CUDA(cudaEventRecord(c->ev0, c->stream));
-  B2O_CUDA(cudaLaunchCooperativeKernel((const void *)kron_gemm_pair_kernel<BN>, dim3(grid), dim3(KR_THREADS), kargs, smem, c->stream));
+  B2O_CUDA(cudaLaunchKernelEx(&cfg, kern, tA1, tX, tYld, tB2, tYhi, tYlo, tRes, a));
   c->launches++;
   if (c->time_kernels) {
     B2O_CUDA(cudaEventRecord(c->ev1, c->stream));
@@ -651,38 +773,109 @@ extern "C" int b2o_kron_apply(b2o_kron *k, int trans, void *res, int res_dtype, 
   if (((uintptr_t)x % 16) || ((uintptr_t)res % 4)) B2O_FAIL(B2O_EARG, "kron: x must be 16-byte aligned");
   b2o_ctx *c = k->ctx;
   B2O_CUDA(cudaSetDevice(c->device));
+  const int d = trans ? 1 : 0;
   KronArgs a;
+  memset(&a, 0, sizeof(a));
   a.M = M; a.K1 = K1; a.N1 = N1; a.N2 = N2; a.nb = nb;
-  a.ldy = round_up(N1, 64);
-  a.Y = k->Y[trans ? 1 : 0];
+  a.ldy = round_up(N1, 128);
   a.res = res;
   a.out_f32 = res_dtype == B2O_F32;
   a.alpha = (float)alpha;
   a.beta = (float)beta;
-  a.bar = c->d_bar;
+  a.store_tma = (beta == 0.0 && ((uintptr_t)res % 16) == 0) ? 1 : 0;
   a.dbg = c->kron_debug ? (unsigned long long *)(c->d_dots + 448) : nullptr;
-  const int t0 = ((M + KR_BM - 1) / KR_BM), t1rows = ((nb * M + KR_BM - 1) / KR_BM);
-  // narrower N tiles when the problem has few tiles (latency-bound sizes like 512^3): more CTAs, fewer bytes per CTA
-  int w = 0;
-  while (w < 2 && (int64_t)t0 * (((int64_t)nb * N1 + (128 >> w) - 1) / (128 >> w)) < c->num_sms / 2) ++w;
-  const int BN = 128 >> w;
-  const int tiles0 = t0 * ((nb * N1 + BN - 1) / BN), tiles1 = t1rows * ((N2 + BN - 1) / BN);
-  int grid = std::max(1, std::min(c->num_sms, std::max(tiles0, tiles1)));
-  a.bar_target = c->bar_base + (unsigned long long)grid;
-  const int d = trans ? 1 : 0;
-  if (k->x_last[d] != x || k->x_nb[d] != nb || k->x_bn[d] != BN) {   // the only per-call descriptor: x (host-side encode, ~1 us)
-    B2O_TRY(make_tmap(&k->tmX[d], x, (uint64_t)nb * N1, K1, K1, BN));
+  // Tile shape and cluster size.  An SM takes in operand bytes at ~50 B/clk, far below what its tensor core consumes, so the
+  // time of a phase is (rows + columns of the CTA tile) x K x 2 bytes / that rate: few units (latency-bound sizes like cfg4)
+  // want small tiles on many SMs -- 64-row units, 64 columns per CTA, 8 CTAs per unit (64 CTAs for cfg4; 16-CTA clusters
+  // do not all fit at once and 32-column tiles double the per-CTA tile count, both measured slower);
+  // many units (batched right-hand sides) want wide tiles and small clusters with every SM busy.
+  const int nmax = std::max(N1, N2);
+  int BM = 64, BN = 64, cluster = 8;
+  if ((int64_t)nb * ((M + 63) / 64) * ((nmax + 31) / 32) > 4 * (int64_t)c->num_sms) {
+    BM = 128;
+    BN = 128;
+    cluster = 2;
+  }
+  if (k->force_bm) BM = k->force_bm;
+  if (k->force_bn) BN = k->force_bn;
+  while (cluster > 1 && (cluster / 2) * BN >= nmax) cluster /= 2;  // no more CTAs than N tiles
+  if (k->force_cluster) cluster = k->force_cluster;
+  a.rblocks = (M + BM - 1) / BM;
+  a.units = nb * a.rblocks;
+  const int w = BN == 128 ? 0 : BN == 64 ? 1 : 2, mi = BM == 128 ? 0 : 1;
+  if (k->x_last[d] != x || k->x_nb[d] != nb || k->x_bn[d] != BN) {   // per-call descriptor: X' = [nb][N1][K1] (host-side encode, ~1 us)
+    const uint64_t dims[3] = {(uint64_t)K1, (uint64_t)N1, (uint64_t)nb};
+    const uint64_t str[2] = {(uint64_t)K1 * 2, (uint64_t)K1 * N1 * 2};
+    const uint32_t box[3] = {(uint32_t)KR_BK, (uint32_t)BN, 1};
+    B2O_TRY(make_tmap(&k->tmX[d], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
     k->x_last[d] = x;
     k->x_nb[d] = nb;
     k->x_bn[d] = BN;
   }
-  // Y rows beyond nb*M hold stale (finite) data from larger batches; phase 1 masks its rows with Mrows = nb*M
-  const CUtensorMap &tY = k->tmY[d][0], &tB2 = k->tmB2[d][w];
-  int st = w == 2   ? kron_launch<32>(c, k->tmA1[d], k->tmX[d], tY, tB2, a, grid)
-           : w == 1 ? kron_launch<64>(c, k->tmA1[d], k->tmX[d], tY, tB2, a, grid)
-                    : kron_launch<128>(c, k->tmA1[d], k->tmX[d], tY, tB2, a, grid);
-  if (st == B2O_OK) c->bar_base += (unsigned long long)grid;
-  return st;
+  if (a.store_tma && (k->res_last[d] != res || k->res_nb[d] != nb || k->res_bn[d] != BN || k->res_bm[d] != BM || k->res_f32[d] != a.out_f32)) {
+    // res = [nb][N2 (j)][M (i)] with i contiguous; box = BM i x BN j
+    const uint64_t es = a.out_f32 ? 4 : 2;
+    const uint64_t dims[3] = {(uint64_t)M, (uint64_t)N2, (uint64_t)nb};
+    const uint64_t str[2] = {(uint64_t)M * es, (uint64_t)M * N2 * es};
+    const uint32_t box[3] = {(uint32_t)BM, (uint32_t)BN, 1};
+    B2O_TRY(make_tmap(&k->tmRes[d], a.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, res, dims, str, box,
+                      CU_TENSOR_MAP_SWIZZLE_NONE));
+    k->res_last[d] = res;
+    k->res_nb[d] = nb;
+    k->res_bn[d] = BN;
+    k->res_bm[d] = BM;
+    k->res_f32[d] = a.out_f32;
+  }
+  if (!a.store_tma && k->res_last[d] == nullptr) k->tmRes[d] = k->tmX[d];   // never dereferenced, but must be a valid descriptor
+  const int maxc = 1 << 30;
+#define KR_GO(BMv, BNv)                                                                                                             \
+  return kron_launch<BMv, BNv>(c, k->tmA1[d][mi], k->tmX[d], k->tmYld[d][mi], k->tmB2[d][w], k->tmYhi[d][mi][w], k->tmYlo[d][mi][w], \
+                               k->tmRes[d], a, cluster, maxc)
+  if (BM == 128) {
+    if (BN == 128) KR_GO(128, 128);
+    if (BN == 64) KR_GO(128, 64);
+    KR_GO(128, 32);
+  }
+  if (BN == 128) KR_GO(64, 128);
+  if (BN == 64) KR_GO(64, 64);
+  KR_GO(64, 32);
+#undef KR_GO
+}
+
+// launch-overhead floor for the kron configuration: an EMPTY kernel with the same grid, cluster size and dynamic shared memory
+__global__ void __launch_bounds__(KR_THREADS, 1) kron_floor_kernel(int dummy) {
+  if (dummy == 12345) asm volatile("trap;");
+}
+extern "C" int b2o_kron_launch_floor(b2o_ctx *c, int grid, int cluster, int64_t smem_bytes) {
+  if (!c || grid < 1 || cluster < 1 || grid % cluster) B2O_FAIL(B2O_EARG, "bad argument");
+  B2O_CUDA(cudaSetDevice(c->device));
+  B2O_CUDA(cudaFuncSetAttribute(kron_floor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  B2O_CUDA(cudaFuncSetAttribute(kron_floor_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(KR_THREADS);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = c->stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (c->time_kernels) B2O_CUDA(cudaEventRecord(c->ev0, c->stream));
+  B2O_CUDA(cudaLaunchKernelEx(&cfg, kron_floor_kernel, 0));
+  c->launches++;
+  if (c->time_kernels) {
+    B2O_CUDA(cudaEventRecord(c->ev1, c->stream));
+    B2O_CUDA(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    B2O_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->kern_ms += ms;
+    c->kern_n++;
+  }
+  return B2O_OK;
 }
 
 extern "C" int b2o_kron_flops(b2o_kron *k, int nb, double *flops) {

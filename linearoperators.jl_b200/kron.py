@@ -1,5 +1,5 @@
 """kron(A, B) -- mirror of src/kron.jl: `(A ⊗ B) * vec(X) = vec(B X Aᵀ)`.  The apply is a TMA-fed tcgen05 GEMM pair in one
-cooperative launch (csrc/b2o_kron.cu): bf16 operands, fp32 accumulation in TMEM, bf16 result."""
+clustered launch (csrc/b2o_kron.cu): bf16 operands, fp32 accumulation in TMEM, bf16 result."""
 import ctypes
 
 import numpy as np
@@ -37,6 +37,11 @@ class KronOperator(LinearOperator):
         _lib.check(self.ctx.lib.b2o_kron_apply(self._h, int(trans), rp, rd, nrow, _bf16_ptr(X, "x"), ncol, nb,
                                                float(alpha), float(beta)))
         return res
+
+    def set_option(self, key, value):
+        """tuning overrides of the clustered kernel: "cluster" (CTAs per 128-row unit), "tile_n" (columns per CTA tile); 0 = auto"""
+        _lib.check(self.ctx.lib.b2o_kron_set_option(self._h, key.encode(), int(value)))
+        return self
 
     def flops(self, nb=1):
         out = ctypes.c_double()
