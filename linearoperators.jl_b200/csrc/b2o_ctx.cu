@@ -120,6 +120,13 @@ extern "C" int b2o_ctx_set_option(b2o_ctx *c, const char *key, int64_t value) {
     if (value != 0 && !c->mbox_connected) B2O_FAIL(B2O_ESTATE, "mailbox not connected (b2o_mbox_connect)");
     B2O_CUDA(cudaStreamSynchronize(c->stream));
     c->mbox_ready = value != 0 ? 1 : 0;
+  } else if (!strcmp(key, "l2_fetch_granularity")) {
+    // cudaLimitMaxL2FetchGranularity (a device-wide hint: 32, 64 or 128 bytes fetched from DRAM per L2 miss); random gathers move
+    // fewer unused bytes with a small value, streams are insensitive to it (profiles/r2_index.jsonl)
+    if (value != 32 && value != 64 && value != 128) B2O_FAIL(B2O_EARG, "l2_fetch_granularity must be 32, 64 or 128");
+    B2O_CUDA(cudaSetDevice(c->device));
+    B2O_CUDA(cudaStreamSynchronize(c->stream));
+    B2O_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
   } else if (!strcmp(key, "numa_local_host")) {
     c->numa_local_host = value != 0;
   } else {

@@ -95,3 +95,30 @@ def test_fused_graph_lowering_and_nvrtc_on_cpu(lo):
     res = ctypes.c_void_p(0x3000)
     assert lib.b2o_graph_apply(g, 0, res, 12345, res, 12345, 1.0, 0.0) == _lib.B2O_EARG   # dry graphs cannot be applied
     lib.b2o_graph_destroy(g)
+
+
+def test_julia_shim_binds_every_export_with_the_header_arity():
+    """julia/B200LinearOperators.jl cannot run here (no Julia anywhere): at least every function include/b2o.h declares must
+    be bound there, and every `ccall` must list as many argument types as the C prototype has parameters."""
+    from linearoperators_jl_b200 import _lib
+    decl = {n: len(a) for n, _, a in _lib.declared_functions()}
+    src = open(os.path.join(ROOT, "julia", "B200LinearOperators.jl")).read()
+    seen = {}
+    for m in re.finditer(r"ccall\(\(:(b2o_\w+), libb2o\),\s*(\w+),\s*\(", src):
+        name, i, depth = m.group(1), m.end(), 1
+        j = i
+        while depth:
+            depth += {"(": 1, ")": -1}.get(src[j], 0)
+            j += 1
+        types = src[i:j - 1]
+        # count top-level commas (types like Ptr{Ptr{Cvoid}} contain none outside braces)
+        level, count, has = 0, 0, bool(types.strip().strip(","))
+        for ch in types:
+            level += {"{": 1, "}": -1}.get(ch, 0)
+            count += ch == "," and level == 0
+        nargs = 0 if not has else count + (0 if types.strip().endswith(",") else 1)
+        seen.setdefault(name, set()).add(nargs)
+    missing = sorted(set(decl) - set(seen) - {"b2o_last_error"})
+    assert not missing, missing
+    wrong = {n: (sorted(a), decl[n]) for n, a in seen.items() if n in decl and a != {decl[n]}}
+    assert not wrong, wrong

@@ -176,6 +176,18 @@ def main():
             ctx.set_option("extend_form", form)
             line("opExtension random k=n/4, %s" % name, timeit(lambda: lo.mul_(res, Z, uk), 20), 8.0 * n + 24.0 * k)
         ctx.set_option("extend_form", 0)
+        # the L2 fetch-granularity hint: random 8-byte hits pull in whole lines by default
+        m = 10
+        B = lo.LBFGSOperator(n, mem=m, ctx=ctx)
+        for i in range(m):
+            s = ctx.uniform(n, 100 + i)
+            lo.push_(B, s, s + 0.1 * ctx.uniform(n, 200 + i))
+        del s
+        for g in (32, 64, 128):
+            ctx.set_option("l2_fetch_granularity", g)
+            line("opRestriction random k=n/4 (gather), l2_fetch_granularity=%d" % g, timeit(lambda: lo.mul_(rk, P, v), 20), 24.0 * k)
+            line("opExtension random k=n/4 gather form, l2_fetch_granularity=%d" % g, timeit(lambda: lo.mul_(res, Z, uk), 20), 8.0 * n + 24.0 * k)
+            line("LBFGS(mem=10) forward apply, l2_fetch_granularity=%d" % g, timeit(lambda: lo.mul_(res, B, v), 20), (4 * m + 3) * 8.0 * n)
         return
     if only == ["fwdc"]:
         v, res = ctx.uniform(n, 7), ctx.empty(n)
