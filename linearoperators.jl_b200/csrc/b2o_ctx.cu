@@ -98,6 +98,9 @@ extern "C" int b2o_ctx_set_option(b2o_ctx *c, const char *key, int64_t value) {
     c->host_chunks = (int)value;
   } else if (!strcmp(key, "graph_jit")) {
     c->graph_jit = value != 0;
+  } else if (!strcmp(key, "graph_interp")) {
+    if (value != 0 && value != 2) B2O_FAIL(B2O_EARG, "graph_interp must be 0 (by program size) or 2 (general machine)");
+    c->graph_interp = (int)value;
   } else if (!strcmp(key, "dense_scalar")) {
     c->dense_scalar = value != 0;
   } else if (!strcmp(key, "sparse_kernel")) {

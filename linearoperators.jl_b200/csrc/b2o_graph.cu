@@ -17,7 +17,7 @@
 #include <memory>
 
 constexpr int G_MAX_PROG = 96, G_MAX_PASS = 4, G_MAX_ARR = 12, G_MAX_SCAL = 48, G_MAX_RED = 8;
-constexpr int G_DEPTH = 6, G_SLOTS = 6, G_EPT = 2, G_NT = 256, G_RED_PER_PASS = 4, G_MAX_SOP = 8;
+constexpr int G_DEPTH = 6, G_SLOTS = 6, G_NT = 256, G_RED_PER_PASS = 4, G_MAX_SOP = 8;
 // abstract ops used by the host code generator; the device sees FLAT opcodes (op, stack depth and array slot folded
 // into one number so that one jump-table dispatch reaches code with static register indices)
 enum { I_PUSH_ARR = 0, I_PUSH_SCAL = 1, I_ADD = 2, I_SUB = 3, I_MUL = 4, I_RED = 5, I_STORE = 6, I_BINA = 7, I_BINS = 8 };
@@ -53,7 +53,13 @@ struct GraphArgs {
 #define G_ROW6(M, A) M(A, 0) M(A, 1) M(A, 2) M(A, 3) M(A, 4) M(A, 5)
 #define G_ROW6S(M, A) M(A, 1) M(A, 2) M(A, 3) M(A, 4) M(A, 5) M(A, 6)
 
-template <int MINB>
+// Two instantiations share the body: the SMALL machine (stack depth <= 3, <= 4 vectors per pass: cfg3 and every tree of that
+// size) serves G_EPT = 4 rows per dispatch inside 128 registers; the general one (depth 6, 6 vectors) keeps 2 rows per dispatch.
+// Opcodes are the same for both: static indices beyond a machine's limits are clamped (those cases are unreachable for
+// programs the host routes to it).
+#define SI(x) ((x) < DEPTH ? (x) : 0)
+#define AI(x) ((x) < SLOTS ? (x) : 0)
+template <int MINB, int DEPTH, int SLOTS, int G_EPT>
 __global__ void __launch_bounds__(G_NT, MINB) graph_kernel(const __grid_constant__ GraphArgs p) {
   __shared__ double s_scal[G_MAX_SCAL];
   __shared__ double s_red[G_MAX_RED];
@@ -87,28 +93,40 @@ __global__ void __launch_bounds__(G_NT, MINB) graph_kernel(const __grid_constant
 
     for (int64_t tt = blockIdx.x; tt < ntiles; tt += gridDim.x) {
       const int64_t t = reverse ? (ntiles - 1 - tt) : tt;
-      const int64_t r0 = t * tile_rows + 2 * (int64_t)tid;      // this thread's two rows
-      const bool in0 = r0 < p.n, in1 = r0 + 1 < p.n;
-      double av[G_SLOTS][G_EPT];
+      // this thread's rows: G_EPT/2 pairs, pair q at tile row 2*(q*G_NT + tid) (a warp reads 512 contiguous bytes per pair).
+      // One interpreter dispatch now serves G_EPT = 4 rows (round 1: 2): the dispatch latency per row halves and twice the
+      // loads are in flight per thread -- the interpreter was latency-bound (30 % DRAM throughput, profiles/r1_ncu_all_kernels.md).
+      int64_t rq[G_EPT / 2];
+      bool in[G_EPT];
 #pragma unroll
-      for (int s = 0; s < G_SLOTS; ++s) {
-        av[s][0] = av[s][1] = 0.0;
+      for (int q = 0; q < G_EPT / 2; ++q) {
+        rq[q] = t * tile_rows + 2 * ((int64_t)q * G_NT + tid);
+        in[2 * q] = rq[q] < p.n;
+        in[2 * q + 1] = rq[q] + 1 < p.n;
+      }
+      double av[SLOTS][G_EPT];
+#pragma unroll
+      for (int s = 0; s < SLOTS; ++s) {
+        G_FOR_J av[s][j] = 0.0;
         if (s < narr) {
           const int a = p.arr_of_pass[pass][s];
           const double *base = p.arr[a];
-          if (p.arr_al16[a] && in1) {
-            double2 v = *reinterpret_cast<const double2 *>(base + r0);
-            av[s][0] = v.x;
-            av[s][1] = v.y;
-          } else {
-            if (in0) av[s][0] = base[r0];
-            if (in1) av[s][1] = base[r0 + 1];
+#pragma unroll
+          for (int q = 0; q < G_EPT / 2; ++q) {
+            if (p.arr_al16[a] && in[2 * q + 1]) {
+              double2 v = *reinterpret_cast<const double2 *>(base + rq[q]);
+              av[s][2 * q] = v.x;
+              av[s][2 * q + 1] = v.y;
+            } else {
+              if (in[2 * q]) av[s][2 * q] = base[rq[q]];
+              if (in[2 * q + 1]) av[s][2 * q + 1] = base[rq[q] + 1];
+            }
           }
         }
       }
-      double st[G_DEPTH][G_EPT];
+      double st[DEPTH][G_EPT];
 #pragma unroll
-      for (int d = 0; d < G_DEPTH; ++d) G_FOR_J st[d][j] = 0.0;
+      for (int d = 0; d < DEPTH; ++d) G_FOR_J st[d][j] = 0.0;
 
       uint32_t ins = s_prog[0];
       for (int pc = 0; pc < len; ++pc) {
@@ -116,32 +134,33 @@ __global__ void __launch_bounds__(G_NT, MINB) graph_kernel(const __grid_constant
         ins = s_prog[pc + 1];                       // prefetch the next instruction
         const int arg = cur >> 16;
         switch (cur & 0xffffu) {
-#define C_PUSHA(SL, SP) case F_PUSHA + SL * 8 + SP: G_FOR_J st[SP][j] = av[SL][j]; break;
+#define C_PUSHA(SL, SP) case F_PUSHA + SL * 8 + SP: G_FOR_J st[SI(SP)][j] = av[AI(SL)][j]; break;
           G_ROW6(C_PUSHA, 0) G_ROW6(C_PUSHA, 1) G_ROW6(C_PUSHA, 2) G_ROW6(C_PUSHA, 3) G_ROW6(C_PUSHA, 4) G_ROW6(C_PUSHA, 5)
-#define C_PUSHS(U, SP) case F_PUSHS + SP: { const double c = s_scal[arg]; G_FOR_J st[SP][j] = c; } break;
+#define C_PUSHS(U, SP) case F_PUSHS + SP: { const double c = s_scal[arg]; G_FOR_J st[SI(SP)][j] = c; } break;
           G_ROW6(C_PUSHS, 0)
-#define C_ADD(U, SP) case F_BIN + 0 * 8 + SP: G_FOR_J st[SP - 2][j] = st[SP - 2][j] + st[SP - 1][j]; break;
-#define C_SUB(U, SP) case F_BIN + 1 * 8 + SP: G_FOR_J st[SP - 2][j] = st[SP - 2][j] - st[SP - 1][j]; break;
-#define C_MUL(U, SP) case F_BIN + 2 * 8 + SP: G_FOR_J st[SP - 2][j] = st[SP - 2][j] * st[SP - 1][j]; break;
+#define C_ADD(U, SP) case F_BIN + 0 * 8 + SP: G_FOR_J st[SI(SP - 2)][j] = st[SI(SP - 2)][j] + st[SI(SP - 1)][j]; break;
+#define C_SUB(U, SP) case F_BIN + 1 * 8 + SP: G_FOR_J st[SI(SP - 2)][j] = st[SI(SP - 2)][j] - st[SI(SP - 1)][j]; break;
+#define C_MUL(U, SP) case F_BIN + 2 * 8 + SP: G_FOR_J st[SI(SP - 2)][j] = st[SI(SP - 2)][j] * st[SI(SP - 1)][j]; break;
           C_ADD(0, 2) C_ADD(0, 3) C_ADD(0, 4) C_ADD(0, 5) C_ADD(0, 6)
           C_SUB(0, 2) C_SUB(0, 3) C_SUB(0, 4) C_SUB(0, 5) C_SUB(0, 6)
           C_MUL(0, 2) C_MUL(0, 3) C_MUL(0, 4) C_MUL(0, 5) C_MUL(0, 6)
           // top (op)= array slot
-#define C_ADDA(SL, SP) case F_BINA + (0 * 6 + SL) * 8 + SP: G_FOR_J st[SP - 1][j] = st[SP - 1][j] + av[SL][j]; break;
-#define C_SUBA(SL, SP) case F_BINA + (1 * 6 + SL) * 8 + SP: G_FOR_J st[SP - 1][j] = st[SP - 1][j] - av[SL][j]; break;
-#define C_MULA(SL, SP) case F_BINA + (2 * 6 + SL) * 8 + SP: G_FOR_J st[SP - 1][j] = st[SP - 1][j] * av[SL][j]; break;
+#define C_ADDA(SL, SP) case F_BINA + (0 * 6 + SL) * 8 + SP: G_FOR_J st[SI(SP - 1)][j] = st[SI(SP - 1)][j] + av[AI(SL)][j]; break;
+#define C_SUBA(SL, SP) case F_BINA + (1 * 6 + SL) * 8 + SP: G_FOR_J st[SI(SP - 1)][j] = st[SI(SP - 1)][j] - av[AI(SL)][j]; break;
+#define C_MULA(SL, SP) case F_BINA + (2 * 6 + SL) * 8 + SP: G_FOR_J st[SI(SP - 1)][j] = st[SI(SP - 1)][j] * av[AI(SL)][j]; break;
           G_ROW6S(C_ADDA, 0) G_ROW6S(C_ADDA, 1) G_ROW6S(C_ADDA, 2) G_ROW6S(C_ADDA, 3) G_ROW6S(C_ADDA, 4) G_ROW6S(C_ADDA, 5)
           G_ROW6S(C_SUBA, 0) G_ROW6S(C_SUBA, 1) G_ROW6S(C_SUBA, 2) G_ROW6S(C_SUBA, 3) G_ROW6S(C_SUBA, 4) G_ROW6S(C_SUBA, 5)
           G_ROW6S(C_MULA, 0) G_ROW6S(C_MULA, 1) G_ROW6S(C_MULA, 2) G_ROW6S(C_MULA, 3) G_ROW6S(C_MULA, 4) G_ROW6S(C_MULA, 5)
           // top (op)= scalar
-#define C_ADDS(U, SP) case F_BINS + 0 * 8 + SP: { const double c = s_scal[arg]; G_FOR_J st[SP - 1][j] = st[SP - 1][j] + c; } break;
-#define C_SUBS(U, SP) case F_BINS + 1 * 8 + SP: { const double c = s_scal[arg]; G_FOR_J st[SP - 1][j] = st[SP - 1][j] - c; } break;
-#define C_MULS(U, SP) case F_BINS + 2 * 8 + SP: { const double c = s_scal[arg]; G_FOR_J st[SP - 1][j] = st[SP - 1][j] * c; } break;
+#define C_ADDS(U, SP) case F_BINS + 0 * 8 + SP: { const double c = s_scal[arg]; G_FOR_J st[SI(SP - 1)][j] = st[SI(SP - 1)][j] + c; } break;
+#define C_SUBS(U, SP) case F_BINS + 1 * 8 + SP: { const double c = s_scal[arg]; G_FOR_J st[SI(SP - 1)][j] = st[SI(SP - 1)][j] - c; } break;
+#define C_MULS(U, SP) case F_BINS + 2 * 8 + SP: { const double c = s_scal[arg]; G_FOR_J st[SI(SP - 1)][j] = st[SI(SP - 1)][j] * c; } break;
           G_ROW6S(C_ADDS, 0) G_ROW6S(C_SUBS, 0) G_ROW6S(C_MULS, 0)
           // masked sum of the top of stack into local reduction `arg` (rows >= n contribute nothing)
 #define C_RED(U, SP)                                                   \
   case F_RED + SP: {                                                   \
-    double s = (in0 ? st[SP - 1][0] : 0.0) + (in1 ? st[SP - 1][1] : 0.0); \
+    double s = 0.0;                                                    \
+    G_FOR_J s += in[j] ? st[SI(SP - 1)][j] : 0.0;                          \
     if (arg == 0) racc[0] += s;                                        \
     else if (arg == 1) racc[1] += s;                                   \
     else if (arg == 2) racc[2] += s;                                   \
@@ -150,10 +169,12 @@ __global__ void __launch_bounds__(G_NT, MINB) graph_kernel(const __grid_constant
           G_ROW6S(C_RED, 0)
 #define C_STORE(U, SP)                                                                       \
   case F_STORE + SP: {                                                                       \
-    if (p.out_al16 && in1) stg_stream2(p.out + r0, make_double2(st[SP - 1][0], st[SP - 1][1])); \
-    else {                                                                                   \
-      if (in0) p.out[r0] = st[SP - 1][0];                                                    \
-      if (in1) p.out[r0 + 1] = st[SP - 1][1];                                                \
+    _Pragma("unroll") for (int q = 0; q < G_EPT / 2; ++q) {                                   \
+      if (p.out_al16 && in[2 * q + 1]) stg_stream2(p.out + rq[q], make_double2(st[SI(SP - 1)][2 * q], st[SI(SP - 1)][2 * q + 1])); \
+      else {                                                                                 \
+        if (in[2 * q]) p.out[rq[q]] = st[SI(SP - 1)][2 * q];                                     \
+        if (in[2 * q + 1]) p.out[rq[q] + 1] = st[SI(SP - 1)][2 * q + 1];                         \
+      }                                                                                      \
     }                                                                                        \
   } break;
           G_ROW6S(C_STORE, 0)
@@ -207,6 +228,8 @@ __global__ void __launch_bounds__(G_NT, MINB) graph_kernel(const __grid_constant
   }
 }
 
+#undef SI
+#undef AI
 // ====================================================================================== host: tree -> passes -> stack programs
 namespace {
 
@@ -337,6 +360,7 @@ struct Compiled {
   GraphArgs args;
   std::vector<SExpr> S;                 // scalar expressions; slot i of args.scal
   int alg_arrays_read = 0;
+  int max_depth = 0, max_slots = 0;     // stack depth / vectors per pass the programs need (selects the interpreter instantiation)
   // specialised instantiation (NVRTC): the same passes as straight-line code
   std::string jit_src;
   void *jit_module = nullptr;           // CUmodule
@@ -704,6 +728,7 @@ static int compile_variant(b2o_graph *g, bool tr, bool beta_nz, Compiled &C) {
   memset(&A, 0, sizeof(A));
   A.npass = npass;
   C.alg_arrays_read = 0;
+  C.max_depth = C.max_slots = 0;
   for (int pass = 0; pass < npass; ++pass) {
     std::vector<uint32_t> code;
     std::vector<int> slots;
@@ -714,6 +739,7 @@ static int compile_variant(b2o_graph *g, bool tr, bool beta_nz, Compiled &C) {
       if (nlocal >= G_RED_PER_PASS) B2O_FAIL(B2O_EUNSUPPORTED, "graph: too many reductions in one pass");
       int sp = 0, maxsp = 0;
       if (!gen_code(L, L.R[r].expr, code, sp, maxsp, slots, err)) B2O_FAIL(B2O_EUNSUPPORTED, "graph: %s", err.c_str());
+      C.max_depth = std::max(C.max_depth, maxsp);
       code.push_back((uint32_t)(F_RED + 1) | ((uint32_t)nlocal << 16));
       A.red_of_pass[pass][nlocal++] = (unsigned char)r;
     }
@@ -721,12 +747,14 @@ static int compile_variant(b2o_graph *g, bool tr, bool beta_nz, Compiled &C) {
     if (pass == npass - 1) {
       int sp = 0, maxsp = 0;
       if (!gen_code(L, out, code, sp, maxsp, slots, err)) B2O_FAIL(B2O_EUNSUPPORTED, "graph: %s", err.c_str());
+      C.max_depth = std::max(C.max_depth, maxsp);
       code.push_back((uint32_t)(F_STORE + 1));
     }
     if ((int)code.size() > G_MAX_PROG) B2O_FAIL(B2O_EUNSUPPORTED, "graph: program too long (%zu)", code.size());
     A.prog_len[pass] = (int)code.size();
     for (size_t i = 0; i < code.size(); ++i) A.prog[pass][i] = code[i];
     A.narr_pass[pass] = (int)slots.size();
+    C.max_slots = std::max(C.max_slots, (int)slots.size());
     for (size_t i = 0; i < slots.size(); ++i) A.arr_of_pass[pass][i] = (unsigned char)slots[i];
     C.alg_arrays_read += (int)slots.size();
     // scalars that become computable once the reductions of earlier passes are known
@@ -969,13 +997,20 @@ extern "C" int b2o_graph_apply(b2o_graph *g, int transposed, void *res, int64_t 
   A.dots = c->d_dots + 400;
   A.bar = c->d_bar;
   A.arrive = c->d_bar + 1;
-  const void *kern = c->graph_blocks >= 4 ? (const void *)graph_kernel<4> : c->graph_blocks == 3 ? (const void *)graph_kernel<3> :
-                     c->graph_blocks == 2 ? (const void *)graph_kernel<2> : (const void *)graph_kernel<1>;
+  // small programs (cfg3 and its variants: depth <= 3, <= 4 vectors per pass) run on the 4-rows-per-dispatch machine
+  const bool small = C.max_depth <= 3 && C.max_slots <= 4 && c->graph_interp != 2;
+  const int ept = small ? 4 : 2;
+  const void *kern = small ? (c->graph_blocks >= 2 ? (const void *)graph_kernel<2, 3, 4, 4>      // 117 registers, no spills; 3 CTAs/SM would spill
+                                                   : (const void *)graph_kernel<1, 3, 4, 4>)
+                           : (c->graph_blocks >= 4   ? (const void *)graph_kernel<4, G_DEPTH, G_SLOTS, 2>
+                              : c->graph_blocks == 3 ? (const void *)graph_kernel<3, G_DEPTH, G_SLOTS, 2>
+                              : c->graph_blocks == 2 ? (const void *)graph_kernel<2, G_DEPTH, G_SLOTS, 2>
+                                                     : (const void *)graph_kernel<1, G_DEPTH, G_SLOTS, 2>);
   int blocks_per_sm = 0;
   B2O_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, G_NT, 0));
   if (blocks_per_sm < 1) blocks_per_sm = 1;
-  if (c->graph_blocks > 0) blocks_per_sm = std::min(blocks_per_sm, c->graph_blocks);
-  const int64_t ntiles = (g->n + (int64_t)G_NT * G_EPT - 1) / ((int64_t)G_NT * G_EPT);
+  if (c->graph_blocks > 0) blocks_per_sm = std::min(blocks_per_sm, small ? std::min(c->graph_blocks, 2) : c->graph_blocks);
+  const int64_t ntiles = (g->n + (int64_t)G_NT * ept - 1) / ((int64_t)G_NT * ept);
   int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)c->num_sms * blocks_per_sm));
   grid = std::min(grid, B2O_MAX_GRID);
   void *kargs[] = {(void *)&A};

@@ -69,6 +69,7 @@ struct b2o_ctx_s {
   int grid = 0;          // 0 -> one CTA per SM
   int kron_debug = 0;    // record a %globaltimer timeline of CTA 0 of the kron kernel into d_dots[448..464)
   int graph_jit = 1;     // fused trees: use the NVRTC-specialised kernel when NVRTC + driver are present (else the interpreter)
+  int graph_interp = 0;  // fused trees, interpreter: 0 = pick the machine by program size, 2 = always the general (2 rows per dispatch) one
   int graph_blocks = 3;  // resident CTAs per SM the fused-graph kernel is compiled for (occupancy hides the dispatch latency)
   int dense_scalar = 0;  // dense-matrix leaf: force the scalar (unvectorised) kernels (testing)
   int sparse_kernel = 0; // sparse-matrix leaf: 0 / 3 software-pipelined row kernel (default), 1 plain row kernel, 2 TMA-staged tile kernel

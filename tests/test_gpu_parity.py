@@ -671,11 +671,15 @@ def _mk_vecs(ctx, n):
     return h1, h2, ctx.uniform(n, 4, 0.5, 1.5), ctx.uniform(n, 14, -1.0, 1.0), ctx.uniform(n, 5), ctx.uniform(n, 6)
 
 
-@pytest.fixture(params=["jit", "interpreter"])
+@pytest.fixture(params=["jit", "interpreter", "interpreter-general"])
 def graph_mode(request, ctx):
+    """NVRTC-specialised kernel; built-in interpreter (small programs on the 4-rows-per-dispatch machine); interpreter with
+    every program forced onto the general machine"""
     ctx.set_option("graph_jit", 1 if request.param == "jit" else 0)
-    yield request.param
+    ctx.set_option("graph_interp", 2 if request.param == "interpreter-general" else 0)
+    yield "jit" if request.param == "jit" else "interpreter"
     ctx.set_option("graph_jit", 1)
+    ctx.set_option("graph_interp", 0)
 
 
 @pytest.mark.parametrize("n", [7, 1000, 1024 * 148 * 2 + 13])

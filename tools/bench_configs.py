@@ -354,12 +354,20 @@ def main():
         line("cfg3 closure tree", timeit(lambda: lo.mul_(res, tree, v), 30), 56.0 * n)
         line("cfg3 fused, ONE launch, NVRTC-specialised", timeit(lambda: lo.mul_(res, fused, v), 50), 56.0 * n, jit=fused.info()["jit"])
         line("cfg3 fused 5-arg beta=0.5, NVRTC-specialised", timeit(lambda: lo.mul_(res, fused, v, 2.0, 0.5), 50), 64.0 * n)
-        line("cfg3 fused transpose, NVRTC-specialised", timeit(lambda: lo.mul_(res, lo.transpose(fused), v), 50), 56.0 * n)
+        # transpose(H*D + 0.1 I) = D*H + 0.1 I: the dot reads h, v only -> 6n*8 bytes (b2o_graph_info), not 7n*8
+        tb = fused.info(transposed=True)["alg_bytes"]
+        line("cfg3 fused transpose, NVRTC-specialised", timeit(lambda: lo.mul_(res, lo.transpose(fused), v), 50), tb)
         ctx.set_option("graph_jit", 0)
-        for gb in (2, 3):
-            ctx.set_option("graph_blocks", gb)
-            line("cfg3 fused, ONE launch (graph_blocks=%d)" % gb, timeit(lambda: lo.mul_(res, fused, v), 30), 56.0 * n)
-            line("cfg3 fused 5-arg beta=0.5 (graph_blocks=%d)" % gb, timeit(lambda: lo.mul_(res, fused, v, 2.0, 0.5), 30), 64.0 * n)
+        for interp, name in ((0, "interpreter, 4 rows per dispatch (small-program machine)"), (2, "interpreter, general machine (round-1 form)")):
+            ctx.set_option("graph_interp", interp)
+            for gb in (2, 3):
+                ctx.set_option("graph_blocks", gb)
+                line("cfg3 fused, NO NVRTC: %s, graph_blocks=%d" % (name, gb), timeit(lambda: lo.mul_(res, fused, v), 30), 56.0 * n)
+                line("cfg3 fused 5-arg beta=0.5, NO NVRTC: %s, graph_blocks=%d" % (name, gb), timeit(lambda: lo.mul_(res, fused, v, 2.0, 0.5), 30), 64.0 * n)
+            line("cfg3 fused transpose, NO NVRTC: %s" % name, timeit(lambda: lo.mul_(res, lo.transpose(fused), v), 30), tb)
+        ctx.set_option("graph_interp", 0)
+        ctx.set_option("graph_blocks", 3)
+        ctx.set_option("graph_jit", 1)
         return
     # cfg1: opDiagonal(n=1e6) * v  (24 MB: L2 resident unless flushed)
     n1 = 10**6
