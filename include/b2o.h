@@ -114,6 +114,21 @@ int b2o_zeros_apply(b2o_ctx *ctx, int dtype, int64_t nrow, int64_t ncol, void *r
 /* mulHouseholder! src/linalg.jl:77-83  res = alpha*(v - 2*dot(h,v)*h) (+beta*res); one launch */
 int b2o_householder_apply(b2o_ctx *ctx, int dtype, int64_t n, const void *h, void *res, int64_t res_len,
                           const void *v, int64_t v_len, double alpha, double beta);
+/* ---- ComplexF64 leaves (vectors = interleaved (re, im) pairs, 16-byte aligned).  The reference is generic in the element type:
+ * for complex operators the adjoint / transpose / conjugate wrappers run the conj-sandwich  conj!(res); prod!(res, conj.(v),
+ * conj(α), conj(β)); conj!(res)  (src/adjtrans.jl:128-136, 196-204), opDiagonal's ctprod! uses conj.(d)
+ * (src/special-operators.jl:140) and mulHouseholder!'s dot(h, v) conjugates h (src/linalg.jl:79). */
+int b2o_cdiag_apply(b2o_ctx *ctx, int64_t nrow, int64_t ncol, const void *d, int64_t d_len, int conj_d, void *res, int64_t res_len,
+                    const void *v, int64_t v_len, double alpha_re, double alpha_im, double beta_re, double beta_im);
+int b2o_ceye_apply(b2o_ctx *ctx, int64_t nrow, int64_t ncol, void *res, int64_t res_len, const void *v, int64_t v_len,
+                   double alpha_re, double alpha_im, double beta_re, double beta_im);
+int b2o_czeros_apply(b2o_ctx *ctx, int64_t nrow, int64_t ncol, void *res, int64_t res_len, int64_t v_len, double beta_re,
+                     double beta_im);
+int b2o_chouseholder_apply(b2o_ctx *ctx, int64_t n, const void *h, void *res, int64_t res_len, const void *v, int64_t v_len,
+                           double alpha_re, double alpha_im, double beta_re, double beta_im);
+/* dst = conj(src), n ComplexF64 elements; dst == src is conj!(res) */
+int b2o_conj(b2o_ctx *ctx, void *dst, const void *src, int64_t n);
+
 /* opRestriction ctor :187-201: idx1 = HOST array of k 1-based indices; out-of-range -> B2O_EARG
  * ("indices should be between 1 and ncol").  Duplicates are legal. */
 int b2o_index_create(b2o_ctx *ctx, const int64_t *idx1, int64_t k, int64_t ncol, b2o_index **out);

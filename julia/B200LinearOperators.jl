@@ -483,6 +483,39 @@ function device_dot(a::CuVector{Float64}, b::CuVector{Float64}; c = ctx())
   return out[]
 end
 
+# ---- ComplexF64 leaves and the conj-sandwich primitives (src/adjtrans.jl:128-136, src/special-operators.jl:140, src/linalg.jl:79)
+const CVec = CuVector{ComplexF64}
+function opDiagonal(d::CVec; c = ctx())
+  n = length(d)
+  run(conj_d) = (res, v, α, β) -> check(ccall((:b2o_cdiag_apply, libb2o), Cint,
+    (Ptr{Cvoid}, Int64, Int64, CuPtr{Cvoid}, Int64, Cint, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, Int64, Cdouble, Cdouble, Cdouble, Cdouble),
+    c.handle, length(res), length(v), d, n, conj_d, res, length(res), v, length(v), real(α), imag(α), real(β), imag(β)))
+  LinearOperator{ComplexF64, CVec}(n, n, true, isreal(d), run(Cint(0)), run(Cint(0)), run(Cint(1)))
+end
+function opHouseholder(h::CVec; c = ctx())
+  n = length(h)
+  prod! = (res, v, α, β) -> check(ccall((:b2o_chouseholder_apply, libb2o), Cint,
+    (Ptr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, Int64, Cdouble, Cdouble, Cdouble, Cdouble),
+    c.handle, n, h, res, length(res), v, length(v), real(α), imag(α), real(β), imag(β)))
+  LinearOperator{ComplexF64, CVec}(n, n, isreal(h), true, prod!, nothing, prod!)
+end
+function opEye(::Type{ComplexF64}, nrow::Int, ncol::Int = nrow; c = ctx())
+  prod! = (res, v, α, β) -> check(ccall((:b2o_ceye_apply, libb2o), Cint,
+    (Ptr{Cvoid}, Int64, Int64, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, Int64, Cdouble, Cdouble, Cdouble, Cdouble),
+    c.handle, length(res), length(v), res, length(res), v, length(v), real(α), imag(α), real(β), imag(β)))
+  LinearOperator{ComplexF64, CVec}(nrow, ncol, nrow == ncol, nrow == ncol, prod!, prod!, prod!)
+end
+function opZeros(::Type{ComplexF64}, nrow::Int, ncol::Int; c = ctx())
+  prod! = (res, v, α, β) -> check(ccall((:b2o_czeros_apply, libb2o), Cint,
+    (Ptr{Cvoid}, Int64, Int64, CuPtr{Cvoid}, Int64, Int64, Cdouble, Cdouble),
+    c.handle, length(res), length(v), res, length(res), length(v), real(β), imag(β)))
+  LinearOperator{ComplexF64, CVec}(nrow, ncol, nrow == ncol, nrow == ncol, prod!, prod!, prod!)
+end
+# conj!(res) and conj.(v) of the wrappers' generic mul! then run on the device through CUDA.jl broadcasts; the library's own
+# kernel is available as conj_device!(dst, src) (dst === src is conj!)
+conj_device!(dst::CVec, src::CVec; c = ctx()) =
+  (check(ccall((:b2o_conj, libb2o), Cint, (Ptr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Int64), c.handle, dst, src, length(src))); dst)
+
 # ---- row-partitioned multi-GPU: one Julia process per GPU (MPI.jl or Distributed for the rendezvous) --------------------
 # After comm_init! every vector argument is the calling rank's contiguous row slab and every inner product is all-reduced.
 function comm_unique_id()

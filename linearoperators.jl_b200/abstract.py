@@ -35,18 +35,40 @@ def _is_complex(v):
     return np.iscomplexobj(v)
 
 
+def _device_conj(dst, src):
+    """conj on the device through the library (b2o_conj): complex128 unit-stride CUDA tensors only; False otherwise"""
+    import torch
+    for t in (dst, src):
+        if not (t.is_cuda and t.dtype == torch.complex128 and t.dim() == 1 and (t.numel() <= 1 or t.stride(0) == 1) and not t.is_conj()):
+            return False
+    from . import _lib
+    from .context import default_context
+    import ctypes
+    ctx = default_context(dst.device.index)
+    _lib.check(ctx.lib.b2o_conj(ctx.handle, ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(src.data_ptr()), dst.shape[0]))
+    return True
+
+
 def _conj_inplace(res):
+    """conj!(res)  (src/adjtrans.jl:128,136)"""
     if _is_complex(res):
         if _is_torch(res):
-            res.copy_(res.conj().resolve_conj())
+            if not _device_conj(res, res):
+                res.copy_(res.conj().resolve_conj())
         else:
             np.conjugate(res, out=res)
 
 
 def _conj_copy(v):
+    """conj.(v)  (src/adjtrans.jl:129); real vectors are passed through without a copy"""
     if not _is_complex(v):
         return v
-    return v.conj().resolve_conj() if _is_torch(v) else np.conjugate(v)
+    if _is_torch(v):
+        out = similar(v)
+        if _device_conj(out, v):
+            return out
+        return v.conj().resolve_conj()
+    return np.conjugate(v)
 
 
 def _conj_scalar(x):

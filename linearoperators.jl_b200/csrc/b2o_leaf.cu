@@ -416,6 +416,201 @@ extern "C" int b2o_householder_apply(b2o_ctx *c, int dtype, int64_t n, const voi
   return B2O_OK;
 }
 
+// ------------------------------------------------------------------ ComplexF64 leaves and the conj-sandwich primitives
+// The reference is generic in the element type.  For complex operators `mul!` of an adjoint / transpose / conjugate wrapper
+// (src/adjtrans.jl:128-136, 196-204) runs  conj!(res); prod!(res, conj.(v), conj(α), conj(β)); conj!(res), opDiagonal's ctprod!
+// multiplies by conj.(d) (src/special-operators.jl:140) and mulHouseholder!'s `dot(h, v)` conjugates h (src/linalg.jl:79).
+// Vectors are interleaved (re, im) pairs = one 16-byte element; complex products are Julia's plain
+// (ac - bd) + (ad + bc)i without contraction (the library is built with -fmad=false), so the elementwise operators stay
+// bit-exact against the oracle.
+struct cplx {
+  double re, im;
+};
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return cplx{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return cplx{a.re + b.re, a.im + b.im}; }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return cplx{a.re - b.re, a.im - b.im}; }
+__device__ __forceinline__ cplx cld(const double *p, int64_t i) {
+  const double2 v = ldg_stream2(p + 2 * i);
+  return cplx{v.x, v.y};
+}
+__device__ __forceinline__ void cst(double *p, int64_t i, cplx v) { stg_stream2(p + 2 * i, make_double2(v.re, v.im)); }
+
+enum { CEW_DIAG = 0, CEW_EYE = 1, CEW_ZEROS = 2, CEW_HOUSE = 3, CEW_CONJ = 4 };
+struct CewArgs {
+  const double *a;      // DIAG: d ; HOUSE: h (interleaved complex)
+  const double *v;
+  double *res;
+  int64_t nmin, nrow;
+  cplx alpha, beta, tail;
+  int conj_a;           // DIAG: use conj.(d) (ctprod!)
+  int beta_nz;
+  const double *dscal;  // HOUSE: dot(h, v) as (re, im) device scalars
+};
+template <int OP>
+__global__ void __launch_bounds__(256) cew_kernel(const __grid_constant__ CewArgs p) {
+  cplx tau{0.0, 0.0};
+  if (OP == CEW_HOUSE) tau = cmul(cplx{2.0, 0.0}, cplx{p.dscal[0], p.dscal[1]});      // 2 * dot(h, v)
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.nrow; i += stride) {
+    cplx out;
+    if (i >= p.nmin) {
+      out = p.tail;
+    } else if (OP == CEW_CONJ) {
+      const cplx x = cld(p.v, i);
+      out = cplx{x.re, -x.im};
+    } else {
+      cplx t;
+      if (OP == CEW_DIAG) {
+        cplx d = cld(p.a, i);
+        if (p.conj_a) d.im = -d.im;
+        t = cmul(cmul(p.alpha, d), cld(p.v, i));                                      // α .* d .* v
+      } else if (OP == CEW_EYE) {
+        t = cmul(p.alpha, cld(p.v, i));                                               // α .* v
+      } else if (OP == CEW_ZEROS) {
+        t = cplx{0.0, 0.0};
+      } else {
+        t = cmul(p.alpha, csub(cld(p.v, i), cmul(tau, cld(p.a, i))));                 // α .* (v .- 2 dot(h,v) .* h)
+      }
+      if (OP == CEW_ZEROS) out = p.beta_nz ? cmul(cld(p.res, i), p.beta) : t;        // res .*= β
+      else out = p.beta_nz ? cadd(t, cmul(p.beta, cld(p.res, i))) : t;
+    }
+    cst(p.res, i, out);
+  }
+}
+// dot(h, v) = Σ conj(h_i) v_i: per-block partials of (re, im), the last block sums them in block order (deterministic)
+__global__ void __launch_bounds__(256) cdot_kernel(const double *h, const double *v, int64_t n, double *partials, double *out,
+                                                   unsigned long long *arrive) {
+  __shared__ double sred[2][8];
+  __shared__ bool is_last;
+  double re = 0.0, im = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const cplx a = cld(h, i), b = cld(v, i);
+    re += a.re * b.re + a.im * b.im;
+    im += a.re * b.im - a.im * b.re;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  re = warp_sum(re);
+  im = warp_sum(im);
+  if (lane == 0) {
+    sred[0][warp] = re;
+    sred[1][warp] = im;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += sred[threadIdx.x][w];
+    partials[(size_t)blockIdx.x * 2 + threadIdx.x] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(arrive, 1ULL) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (warp < 2) {
+      double s = 0.0;
+      for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(&partials[(size_t)b * 2 + warp]);
+      s = warp_sum(s);
+      if (lane == 0) out[warp] = s;
+    }
+    if (threadIdx.x == 0) *arrive = 0ULL;
+  }
+}
+static int cew_grid(b2o_ctx *c, int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)c->num_sms * 8)); }
+static int check_c128(b2o_ctx *c, const void *a, const void *b, const void *r) {
+  if (!c) B2O_FAIL(B2O_EARG, "null context");
+  if (((uintptr_t)a | (uintptr_t)b | (uintptr_t)r) % 16) B2O_FAIL(B2O_EARG, "ComplexF64 vectors must be 16-byte aligned");
+  return B2O_OK;
+}
+template <int OP>
+static int cew_launch(b2o_ctx *c, CewArgs &p) {
+  if (p.nrow <= 0) return B2O_OK;
+  B2O_CUDA(cudaSetDevice(c->device));
+  cew_kernel<OP><<<cew_grid(c, p.nrow), 256, 0, c->stream>>>(p);
+  c->launches++;
+  B2O_CUDA(cudaGetLastError());
+  return B2O_OK;
+}
+// mulSquareOpDiagonal! / mulOpDiagonal! for ComplexF64; conj_d != 0: the ctprod! closure (conj.(d))
+extern "C" int b2o_cdiag_apply(b2o_ctx *c, int64_t nrow, int64_t ncol, const void *d, int64_t d_len, int conj_d, void *res,
+                               int64_t res_len, const void *v, int64_t v_len, double alpha_re, double alpha_im, double beta_re,
+                               double beta_im) {
+  B2O_TRY(check_c128(c, d, v, res));
+  if (nrow < 0 || ncol < 0) B2O_FAIL(B2O_EARG, "negative size");
+  if (v_len != ncol || res_len != nrow) B2O_FAIL(B2O_ESHAPE, "shape mismatch");
+  const int64_t nmin = std::min(nrow, ncol);
+  if (d_len < nmin) B2O_FAIL(B2O_EARG, "diagonal shorter than min(nrow,ncol)");
+  if (nrow > 0 && (!res || (nmin > 0 && (!d || !v)))) B2O_FAIL(B2O_EARG, "null vector");
+  CewArgs p;
+  memset(&p, 0, sizeof(p));
+  p.a = (const double *)d; p.v = (const double *)v; p.res = (double *)res;
+  p.nmin = nmin; p.nrow = nrow;
+  p.alpha = cplx{alpha_re, alpha_im}; p.beta = cplx{beta_re, beta_im};
+  p.beta_nz = (beta_re != 0.0 || beta_im != 0.0);
+  p.conj_a = conj_d != 0;
+  return cew_launch<CEW_DIAG>(c, p);
+}
+// mulOpEye! for ComplexF64 (rectangular tail: 0 when β == 0, else the scalar β -- quirk Q2)
+extern "C" int b2o_ceye_apply(b2o_ctx *c, int64_t nrow, int64_t ncol, void *res, int64_t res_len, const void *v, int64_t v_len,
+                              double alpha_re, double alpha_im, double beta_re, double beta_im) {
+  B2O_TRY(check_c128(c, nullptr, v, res));
+  if (v_len != ncol || res_len != nrow) B2O_FAIL(B2O_ESHAPE, "shape mismatch");
+  CewArgs p;
+  memset(&p, 0, sizeof(p));
+  p.v = (const double *)v; p.res = (double *)res;
+  p.nmin = std::min(nrow, ncol); p.nrow = nrow;
+  p.alpha = cplx{alpha_re, alpha_im}; p.beta = cplx{beta_re, beta_im};
+  p.beta_nz = (beta_re != 0.0 || beta_im != 0.0);
+  p.tail = p.beta_nz ? p.beta : cplx{0.0, 0.0};
+  return cew_launch<CEW_EYE>(c, p);
+}
+// mulOpZeros! for ComplexF64
+extern "C" int b2o_czeros_apply(b2o_ctx *c, int64_t nrow, int64_t ncol, void *res, int64_t res_len, int64_t v_len, double beta_re,
+                                double beta_im) {
+  B2O_TRY(check_c128(c, nullptr, nullptr, res));
+  if (v_len != ncol || res_len != nrow) B2O_FAIL(B2O_ESHAPE, "shape mismatch");
+  CewArgs p;
+  memset(&p, 0, sizeof(p));
+  p.res = (double *)res;
+  p.nmin = nrow; p.nrow = nrow;
+  p.beta = cplx{beta_re, beta_im};
+  p.beta_nz = (beta_re != 0.0 || beta_im != 0.0);
+  return cew_launch<CEW_ZEROS>(c, p);
+}
+// conj!(res) (dst == src) / conj.(v): the two halves of the conj-sandwich, src/adjtrans.jl:128-136
+extern "C" int b2o_conj(b2o_ctx *c, void *dst, const void *src, int64_t n) {
+  B2O_TRY(check_c128(c, nullptr, src, dst));
+  if (n > 0 && (!dst || !src)) B2O_FAIL(B2O_EARG, "null vector");
+  CewArgs p;
+  memset(&p, 0, sizeof(p));
+  p.v = (const double *)src; p.res = (double *)dst;
+  p.nmin = n; p.nrow = n;
+  return cew_launch<CEW_CONJ>(c, p);
+}
+// mulHouseholder! for ComplexF64: res = α (v - 2 dot(h, v) h) (+ β res), dot conjugating h
+extern "C" int b2o_chouseholder_apply(b2o_ctx *c, int64_t n, const void *h, void *res, int64_t res_len, const void *v, int64_t v_len,
+                                      double alpha_re, double alpha_im, double beta_re, double beta_im) {
+  B2O_TRY(check_c128(c, h, v, res));
+  if (v_len != n || res_len != n) B2O_FAIL(B2O_ESHAPE, "shape mismatch");
+  if (n == 0) return B2O_OK;
+  if (!h || !res || !v) B2O_FAIL(B2O_EARG, "null vector");
+  if (c->nranks > 1) B2O_FAIL(B2O_EUNSUPPORTED, "complex Householder is not row-partitioned");
+  B2O_CUDA(cudaSetDevice(c->device));
+  const int grid = std::min(cew_grid(c, n), B2O_MAX_GRID);
+  cdot_kernel<<<grid, 256, 0, c->stream>>>((const double *)h, (const double *)v, n, c->d_partials, c->d_dots + 336, c->d_bar + 1);
+  c->launches++;
+  B2O_CUDA(cudaGetLastError());
+  CewArgs p;
+  memset(&p, 0, sizeof(p));
+  p.a = (const double *)h; p.v = (const double *)v; p.res = (double *)res;
+  p.nmin = n; p.nrow = n;
+  p.alpha = cplx{alpha_re, alpha_im}; p.beta = cplx{beta_re, beta_im};
+  p.beta_nz = (beta_re != 0.0 || beta_im != 0.0);
+  p.dscal = c->d_dots + 336;
+  return cew_launch<CEW_HOUSE>(c, p);
+}
+
 // ------------------------------------------------------------------ opRestriction / opExtension
 struct b2o_index_s {
   b2o_ctx *ctx;

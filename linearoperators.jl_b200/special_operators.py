@@ -25,6 +25,28 @@ def _vp(t, what="vector"):
     return ctypes.c_void_p(t.data_ptr())
 
 
+def _cp(t, what="vector"):
+    """raw device pointer of a 1-D unit-stride complex128 CUDA tensor (interleaved re, im)"""
+    import torch
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.B2OError("%s must be a torch CUDA tensor (no CPU fallback)" % what)
+    if t.dtype != torch.complex128:
+        raise _lib.B2OError("%s must be complex128 (got %s)" % (what, t.dtype))
+    if t.dim() != 1 or (t.numel() > 1 and t.stride(0) != 1):
+        raise _lib.B2OError("%s must be a unit-stride 1-D tensor" % what)
+    return ctypes.c_void_p(t.resolve_conj().data_ptr() if t.is_conj() else t.data_ptr())
+
+
+def _is_c128(t):
+    import torch
+    return isinstance(t, torch.Tensor) and t.dtype == torch.complex128
+
+
+def _ri(z):
+    z = complex(z)
+    return float(z.real), float(z.imag)
+
+
 def _ctx_of(like=None, ctx=None):
     if ctx is not None:
         return ctx
@@ -82,6 +104,9 @@ def opEye(*args, T=None, ctx=None, like=None):
 
     def prod_(res, v, a, b):
         # mulOpEye!(res, v, α, β, n_min): n_min = min(nrow, ncol) is the same for prod!/tprod!/ctprod!
+        if _is_c128(res):
+            _lib.check(lib.b2o_ceye_apply(h, res.shape[0], v.shape[0], _cp(res), res.shape[0], _cp(v), v.shape[0], *_ri(a), *_ri(b)))
+            return
         _lib.check(lib.b2o_eye_apply(h, F64, res.shape[0], v.shape[0], _vp(res), res.shape[0], _vp(v), v.shape[0],
                                      float(a), float(b)))
 
@@ -115,6 +140,9 @@ def opZeros(nrow, ncol, T=None, ctx=None, like=None):
     nrow, ncol = int(nrow), int(ncol)
 
     def prod_(res, v, a, b):
+        if _is_c128(res):
+            _lib.check(lib.b2o_czeros_apply(h, res.shape[0], v.shape[0], _cp(res), res.shape[0], v.shape[0], *_ri(b)))
+            return
         _lib.check(lib.b2o_zeros_apply(h, F64, res.shape[0], v.shape[0], _vp(res), res.shape[0], v.shape[0],
                                        float(a), float(b)))
 
@@ -136,6 +164,17 @@ def opDiagonal(*args, ctx=None):
             return opDiagonal(d[:nrow].clone(), ctx=ctx)          # opDiagonal(d[1:nrow]) copies  :159
     ctx = _ctx_of(None, ctx)
     lib, h = ctx.lib, ctx.handle
+    if _is_c128(d):
+        # complex T (src/special-operators.jl:137-141): prod! = tprod! use d, ctprod! uses conj.(d); hermitian only if isreal(d)
+        def cprod(conj_d):
+            def f(res, v, a, b):
+                _lib.check(lib.b2o_cdiag_apply(h, res.shape[0], v.shape[0], _cp(d, "diagonal"), d.shape[0], int(conj_d), _cp(res),
+                                               res.shape[0], _cp(v), v.shape[0], *_ri(a), *_ri(b)))
+            return f
+        herm = bool((d.imag == 0).all().item())
+        if nrow == ncol:
+            return _Leaf(ctx, d.dtype, nrow, ncol, True, herm, cprod(False), cprod(False), cprod(True))
+        return _Leaf(ctx, d.dtype, nrow, ncol, False, False, cprod(False), cprod(False), cprod(True))
     dp = _vp(d, "diagonal")
 
     def prod_(res, v, a, b):
@@ -156,6 +195,11 @@ def opHouseholder(h, ctx=None):
     ctx = _ctx_of(None, ctx)
     lib, hd = ctx.lib, ctx.handle
     n = h.shape[0]
+    if _is_c128(h):
+        # complex h: symmetric only if isreal(h), always hermitian; tprod! is inferred through the conj-sandwich (src/linalg.jl:91-95)
+        def cprod_(res, v, a, b):
+            _lib.check(lib.b2o_chouseholder_apply(hd, n, _cp(h, "h"), _cp(res), res.shape[0], _cp(v), v.shape[0], *_ri(a), *_ri(b)))
+        return _Leaf(ctx, h.dtype, n, n, bool((h.imag == 0).all().item()), True, cprod_, None, cprod_)
     _vp(h, "h")
 
     def prod_(res, v, a, b):

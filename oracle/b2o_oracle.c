@@ -135,6 +135,47 @@ void orc_householder(double *res, const double *h, const double *v, int64_t n, d
   }
 }
 
+/* ---- ComplexF64 leaves (interleaved re, im).  Julia's Complex `*` is (ac - bd) + (ad + bc)i, plain multiplies and adds. ---- */
+typedef struct { double re, im; } orc_c;
+static inline orc_c c_mul(orc_c a, orc_c b) { orc_c r = {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; return r; }
+static inline orc_c c_add(orc_c a, orc_c b) { orc_c r = {a.re + b.re, a.im + b.im}; return r; }
+static inline orc_c c_sub(orc_c a, orc_c b) { orc_c r = {a.re - b.re, a.im - b.im}; return r; }
+/* mulSquareOpDiagonal! with complex T (src/special-operators.jl:125-131); conj_d: the ctprod! closure's conj.(d) (:140) */
+void orc_cdiag(double *res_, const double *d_, const double *v_, int64_t n, int conj_d, const double *alpha, const double *beta) {
+  orc_c *res = (orc_c *)res_;
+  const orc_c *d = (const orc_c *)d_, *v = (const orc_c *)v_;
+  const orc_c a = {alpha[0], alpha[1]}, b = {beta[0], beta[1]};
+  const int bz = (b.re == 0.0 && b.im == 0.0);
+  for (int64_t i = 0; i < n; ++i) {
+    orc_c di = d[i];
+    if (conj_d) di.im = -di.im;
+    orc_c t = c_mul(c_mul(a, di), v[i]);
+    res[i] = bz ? t : c_add(t, c_mul(b, res[i]));
+  }
+}
+/* mulHouseholder! with complex T (src/linalg.jl:77-83): dot(h, v) = sum conj(h_i) v_i */
+void orc_chouseholder(double *res_, const double *h_, const double *v_, int64_t n, const double *alpha, const double *beta) {
+  orc_c *res = (orc_c *)res_;
+  const orc_c *h = (const orc_c *)h_, *v = (const orc_c *)v_;
+  const orc_c a = {alpha[0], alpha[1]}, b = {beta[0], beta[1]};
+  const int bz = (b.re == 0.0 && b.im == 0.0);
+  long double re = 0.0L, im = 0.0L;
+  for (int64_t i = 0; i < n; ++i) {
+    re += (long double)h[i].re * v[i].re + (long double)h[i].im * v[i].im;
+    im += (long double)h[i].re * v[i].im - (long double)h[i].im * v[i].re;
+  }
+  const orc_c two = {2.0, 0.0}, dot = {(double)re, (double)im};
+  const orc_c tau = c_mul(two, dot);
+  for (int64_t i = 0; i < n; ++i) {
+    orc_c t = c_mul(a, c_sub(v[i], c_mul(tau, h[i])));
+    res[i] = bz ? t : c_add(t, c_mul(b, res[i]));
+  }
+}
+/* conj!(res) / conj.(v) (src/adjtrans.jl:128-136) */
+void orc_conj(double *dst, const double *src, int64_t n) {
+  for (int64_t i = 0; i < n; ++i) { dst[2 * i] = src[2 * i]; dst[2 * i + 1] = -src[2 * i + 1]; }
+}
+
 /* ---- mulRestrict! / multRestrict!  src/special-operators.jl:167-174 (Q1 ignore α,β; Q4 last wins) ---- */
 void orc_restrict(double *res, const int64_t *idx1, int64_t k, const double *v) {
   for (int64_t i = 0; i < k; ++i) res[i] = v[idx1[i] - 1];

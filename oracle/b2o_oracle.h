@@ -45,6 +45,10 @@ void orc_zeros(double *res, int64_t nres, double alpha, double beta);
 void orc_diag_square(double *res, const double *d, const double *v, int64_t n, double alpha, double beta);
 void orc_diag_rect(double *res, int64_t nres, const double *d, const double *v, double alpha, double beta, int64_t n_min);
 void orc_householder(double *res, const double *h, const double *v, int64_t n, double alpha, double beta);
+/* ComplexF64 leaves, vectors as interleaved (re, im); alpha / beta point to 2 doubles */
+void orc_cdiag(double *res, const double *d, const double *v, int64_t n, int conj_d, const double *alpha, const double *beta);
+void orc_chouseholder(double *res, const double *h, const double *v, int64_t n, const double *alpha, const double *beta);
+void orc_conj(double *dst, const double *src, int64_t n);
 void orc_restrict(double *res, const int64_t *idx1, int64_t k, const double *v);
 void orc_extend(double *res, int64_t ncol, const int64_t *idx1, int64_t k, const double *u);
 

@@ -54,6 +54,8 @@ def lib():
             "orc_eye": (None, [vp, i64, vp, i64, d, d, i64]), "orc_ones": (None, [vp, i64, vp, i64, d, d]),
             "orc_zeros": (None, [vp, i64, d, d]), "orc_diag_square": (None, [vp, vp, vp, i64, d, d]),
             "orc_diag_rect": (None, [vp, i64, vp, vp, d, d, i64]), "orc_householder": (None, [vp, vp, vp, i64, d, d]),
+            "orc_cdiag": (None, [vp, vp, vp, i64, i32, vp, vp]), "orc_chouseholder": (None, [vp, vp, vp, i64, vp, vp]),
+            "orc_conj": (None, [vp, vp, i64]),
             "orc_restrict": (None, [vp, vp, i64, vp]), "orc_extend": (None, [vp, i64, vp, i64, vp]),
             "orc_lbfgs_create": (vp, [i64, i32, i32, i32, d, d, i32]), "orc_lbfgs_destroy": (None, [vp]),
             "orc_lbfgs_apply": (None, [vp, vp, vp, d, d]), "orc_lbfgs_push": (i32, [vp, vp, vp]),
@@ -135,6 +137,23 @@ def diag_(res, d, v, alpha, beta, n_min=None):
 
 def householder_(res, h, v, alpha, beta):
     lib().orc_householder(_p(res), _p(h), _p(v), res.shape[0], alpha, beta)
+
+
+def _c2(z):
+    return np.array([complex(z).real, complex(z).imag], dtype=np.float64)
+
+
+def cdiag_(res, d, v, alpha=1.0, beta=0.0, conj_d=False):
+    """complex128 mulSquareOpDiagonal! (conj_d: the ctprod! closure); res updated in place"""
+    a, b = _c2(alpha), _c2(beta)
+    lib().orc_cdiag(_p(res), _p(np.ascontiguousarray(d, dtype=np.complex128)), _p(np.ascontiguousarray(v, dtype=np.complex128)),
+                    res.shape[0], int(conj_d), _p(a), _p(b))
+
+
+def chouseholder_(res, h, v, alpha=1.0, beta=0.0):
+    a, b = _c2(alpha), _c2(beta)
+    lib().orc_chouseholder(_p(res), _p(np.ascontiguousarray(h, dtype=np.complex128)), _p(np.ascontiguousarray(v, dtype=np.complex128)),
+                           res.shape[0], _p(a), _p(b))
 
 
 def restrict_(res, idx1, v):

@@ -568,6 +568,71 @@ def test_cfg2_full_size_properties(lo, ctx):
     assert torch.equal(again, Bx)                                                               # deterministic reductions
 
 
+# ---------------------------------------------------------------- complex element types (adjtrans.jl conj-sandwich) on the device
+def test_complex_leaves_and_conj_sandwich(lo, ctx, orc):
+    """ComplexF64 operators on the device: opDiagonal's ctprod! uses conj.(d) (src/special-operators.jl:140), mulHouseholder!'s
+    dot conjugates h (src/linalg.jl:79), and adjoint / transpose / conj of an operator without the matching closure go through
+    conj!(res); prod!(res, conj.(v), conj(α), conj(β)); conj!(res) (src/adjtrans.jl:128-136, 196-204).  Elementwise parts
+    bit-exact against the oracle's complex restatement, reductions <= 1e-12."""
+    import torch
+    dev_ = "cuda:%d" % ctx.device
+    n = 100003
+    cz = lambda a, b: torch.complex(ctx.uniform(n, a, -1.0, 1.0), ctx.uniform(n, b, -1.0, 1.0))
+    d, v, r0 = cz(1, 2), cz(3, 4), cz(5, 6)
+    dn, vn, r0n = host(d), host(v), host(r0)
+    D = lo.opDiagonal(d)
+    assert lo.issymmetric(D) and not lo.ishermitian(D)
+    for alpha, beta in ((1.0, 0.0), (2.0 - 0.5j, 0.0), (0.75 + 1.25j, -0.5 + 2.0j)):
+        for wrap, conj_d, conj_io in ((lambda o: o, False, False), (lo.transpose, False, False), (lo.adjoint, True, False),
+                                      (lo.conj, True, False)):
+            res = r0.clone() if beta != 0 else torch.full((n,), float("nan"), dtype=torch.complex128, device=dev_)
+            lo.mul_(res, wrap(D), v, alpha, beta)
+            ref = r0n.copy()
+            if wrap is lo.conj:
+                # conj(D)*v = conj(D * conj(v)): mul!(res, D, conj.(v), α, β) then conj!(res)   adjtrans.jl:226-249
+                tmp = r0n.copy()
+                orc.cdiag_(tmp, dn, np.conj(vn), alpha, beta)
+                ref = np.conj(tmp)
+            else:
+                orc.cdiag_(ref, dn, vn, alpha, beta, conj_d=conj_d)
+            assert np.array_equal(host(res), ref), (alpha, beta, conj_d)
+    # Householder with a complex unit vector: hermitian, not symmetric; transpose is inferred through the conj-sandwich
+    h = cz(7, 8)
+    h = h / torch.linalg.vector_norm(h)
+    hn = host(h)
+    H = lo.opHouseholder(h)
+    assert lo.ishermitian(H) and not lo.issymmetric(H)
+    ref = np.empty(n, dtype=np.complex128)
+    orc.chouseholder_(ref, hn, vn)
+    assert rel(host(H * v), ref) <= TOL
+    assert rel(host(lo.adjoint(H) * v), ref) <= TOL
+    res, refb = r0.clone(), r0n.copy()
+    lo.mul_(res, H, v, 1.5 - 0.5j, 0.25j)
+    orc.chouseholder_(refb, hn, vn, 1.5 - 0.5j, 0.25j)
+    assert rel(host(res), refb) <= TOL
+    tmp = np.empty(n, dtype=np.complex128)
+    orc.chouseholder_(tmp, hn, np.conj(vn))
+    n0 = H.nctprod
+    assert rel(host(lo.transpose(H) * v), np.conj(tmp)) <= TOL               # conj(Hᴴ conj(v)) = Hᵀ v
+    assert H.nctprod == n0 + 1                                                 # the sandwich runs ctprod!  (adjtrans.jl:180-186)
+    # identity / zeros with complex scalars; rectangular eye tail = β (Q2)
+    E = lo.opEye(n, n - 5)
+    res = r0.clone()
+    lo.mul_(res, E, v[: n - 5], 2.0j, 0.5 - 1.0j)
+    want = np.concatenate([2.0j * vn[: n - 5] + (0.5 - 1.0j) * r0n[: n - 5], np.full(5, 0.5 - 1.0j)])
+    assert np.allclose(host(res), want, rtol=1e-15, atol=0)
+    # a composed complex chain and its adjoint against dense complex algebra
+    m = 300
+    dz, hz, vz = cz(11, 12)[:m].clone(), cz(13, 14)[:m].clone(), cz(15, 16)[:m].clone()
+    hz = hz / torch.linalg.vector_norm(hz)
+    op = lo.opHouseholder(hz) * lo.opDiagonal(dz) + (0.5j) * lo.opEye(m)
+    Hd = np.eye(m) - 2.0 * np.outer(host(hz), np.conj(host(hz)))
+    M = Hd @ np.diag(host(dz)) + 0.5j * np.eye(m)
+    assert rel(host(op * vz), M @ host(vz)) <= TOL
+    assert rel(host(lo.adjoint(op) * vz), M.conj().T @ host(vz)) <= TOL
+    assert rel(host(lo.transpose(op) * vz), M.T @ host(vz)) <= TOL
+
+
 # ---------------------------------------------------------------- full BASELINE size against the oracle itself
 def _full_size_vs_oracle(lo, ctx, orc, inverse, n, mem, record):
     """The oracle's own apply code (oracle/b2o_oracle.c lbfgs_apply_forward / lbfgs_apply_inverse, src/lbfgs.jl:117-202)
@@ -839,6 +904,51 @@ def test_kron_batch_and_launch_count(lo, ctx, orc):
     assert K.flops() == 2.0 * p * q * n + 2.0 * p * n * m
     with pytest.raises(lo.B2OError):
         lo.kron(A[:, :-1].contiguous(), B, ctx=ctx)                                  # dims must be multiples of 8
+
+
+def test_kron_of_general_operators_on_gpu(lo, ctx, orc):
+    """kron(A, B) for operators that are not bf16 matrices (src/kron.jl:10-49, test/test_kron.jl:3-58): Float64 dense matrices,
+    a dense x diagonal pair, a dense x L-BFGS pair -- composed from the operators' own matrix-right-hand-side applies, every
+    multiply one of the library's kernels.  Against the oracle's vec(B X A^T) / the dense Kronecker product."""
+    import torch
+    dev_ = "cuda:%d" % ctx.device
+    rng = np.random.default_rng(11)
+    for (m, n, p, q) in ((6, 5, 7, 4), (16, 16, 9, 9), (3, 40, 33, 2)):
+        An, Bn = rng.uniform(-1, 1, (m, n)), rng.uniform(-1, 1, (p, q))
+        A, B = torch.as_tensor(An).to(dev_), torch.as_tensor(Bn).to(dev_)                 # Float64 CUDA matrices -> LinearOperator(M)
+        K = lo.kron(A, B)
+        assert lo.size(K) == (m * p, n * q)
+        xn, un, r0n = rng.uniform(-1, 1, n * q), rng.uniform(-1, 1, m * p), rng.uniform(-1, 1, m * p)
+        x, u = dev(ctx, xn), dev(ctx, un)
+        D = np.kron(An, Bn)
+        ref = np.empty(m * p)
+        orc.kron_(ref, An, Bn, xn)                                                        # the oracle's vec(B X A^T)  kron.jl:14-22
+        assert rel(ref, D @ xn) <= 1e-13
+        assert rel(host(K * x), D @ xn) <= TOL
+        assert rel(host(lo.transpose(K) * u), D.T @ un) <= TOL
+        assert rel(host(lo.adjoint(K) * u), D.T @ un) <= TOL
+        res = dev(ctx, r0n)
+        lo.mul_(res, K, x, 2.0, -0.5)                                                     # 5-arg form  kron.jl:18-20
+        assert rel(host(res), 2.0 * (D @ xn) - 0.5 * r0n) <= TOL
+        res = ctx.empty(m * p).fill_(float("nan"))
+        lo.mul_(res, K, x)                                                                # beta == 0 never reads res
+        assert rel(host(res), D @ xn) <= TOL
+        K2 = lo.kron(2.0 * lo.LinearOperator(A), B)                                       # test_kron.jl:50-58
+        assert rel(host(K2 * x), 2.0 * (D @ xn)) <= TOL
+        with pytest.raises(lo.LinearOperatorException, match="shape mismatch"):
+            K * ctx.uniform(n * q + 1, 1)
+    # dense (x) diagonal and dense (x) quasi-Newton: the second factor is a matrix-free operator
+    n1, n2 = 5, 300
+    An = rng.uniform(-1, 1, (n1, n1))
+    dn = rng.uniform(0.5, 1.5, n2)
+    Kd = lo.kron(torch.as_tensor(An).to(dev_), lo.opDiagonal(dev(ctx, dn)))
+    xn = rng.uniform(-1, 1, n1 * n2)
+    assert rel(host(Kd * dev(ctx, xn)), np.kron(An, np.diag(dn)) @ xn) <= TOL
+    g, o = build_pair(lo, ctx, orc, "fwd", n2, 4, 5)
+    Kq = lo.kron(torch.as_tensor(An).to(dev_), g)
+    Bq = o.matrix()
+    assert rel(host(Kq * dev(ctx, xn)), np.kron(An, Bq) @ xn) <= 1e-11
+    assert rel(host(lo.transpose(Kq) * dev(ctx, xn)), np.kron(An, Bq).T @ xn) <= 1e-11
 
 
 # ---------------------------------------------------------------- §8f.1: compact-representation inverse apply (extension)

@@ -51,14 +51,19 @@ def test_streaming_kernels_use_tma_bulk_copies(sass):
 
 
 def test_kron_uses_tcgen05_and_tensor_tma(sass):
-    ks = _of(sass, r"kron_gemm_pair_kernel")
-    assert ks
+    ks = _of(sass, r"kron_cluster_kernel")
+    assert len(ks) == 6                                     # BM in {64, 128} x BN in {32, 64, 128}
     for name, ins in ks.items():
         text = "\n".join(ins)
         assert "UTCHMMA" in text, name                      # tcgen05.mma
-        assert "UTMALDG" in text, name                      # cp.async.bulk.tensor
+        assert "UTMALDG" in text, name                      # cp.async.bulk.tensor loads
+        assert "MULTICAST" in text and "UTCBAR.MULTICAST" in text, name   # TMA multicast of the shared operand, cluster-wide slot release
+        assert "UTMASTG" in text, name                      # TMA-store epilogues (intermediate and result)
         assert "LDTM" in text, name                         # tcgen05.ld (TMEM -> registers)
         assert "HMMA" not in text.replace("UTCHMMA", ""), name   # no mma.sync fallback
+        # the MMA / TMA issue must not sit in ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loops (operands in uniform
+        # registers: one elected branch per ring stage) -- round 2 finding, profiles/r2_kron_timeline.md
+        assert "R2UR.BROADCAST" not in text, name
 
 
 def _dest_regs(instr):
