@@ -64,7 +64,7 @@ int b2o_ctx_create(int device, void *stream, b2o_ctx **out);
 int b2o_ctx_destroy(b2o_ctx *ctx);
 int b2o_ctx_sync(b2o_ctx *ctx);
 /* tuning knobs of the streaming kernels: "tile_rows" (1024|2048|4096), "stages", "grid", "threads";
- * fused trees: "graph_jit" (0|1), "graph_blocks" (1..4); host-buffer pipeline: "host_chunks";
+ * fused trees: "graph_jit" (0|1|2, see b2o_graph_variant), "graph_blocks" (1..4), "graph_interp" (0|2); host-buffer pipeline: "host_chunks";
  * matrix leaves: "dense_scalar" (force the unvectorised dense kernels), "sparse_kernel" (0|3 pipelined rows -- default,
  * 1 plain rows, 2 TMA-staged tiles), "sparse_lanes" (-1 auto | 0..5: 2^k lanes per row);
  * index sets: "extend_form" (0 gather form through the inverse map when the set is dense enough, 1 always memset + scatter);
@@ -216,6 +216,11 @@ int b2o_graph_apply(b2o_graph *g, int transposed, void *res, int64_t res_len, co
 int b2o_graph_jit_source(b2o_graph *g, int transposed, double beta, char *buf, int64_t cap, int64_t *len);
 int b2o_graph_jit_check(b2o_graph *g, int64_t *cubin_bytes);
 int b2o_graph_uses_jit(b2o_graph *g, int transposed, double beta, int *out);
+/* executor of the last apply of a variant: 0 interpreter kernel, 1 NVRTC-specialised, 2 ahead-of-time instantiation (the common
+ * chains -- config 3 and its variants, H*D, D1*D2, D + c*I, H1*H2, H*D*H -- are compiled into the library, so they need no
+ * libnvrtc at run time); source_hash = FNV-1a of the variant's generated source, the key of that table.  Context option
+ * "graph_jit": 0 interpreter, 1 (default) table -> NVRTC -> interpreter, 2 table -> interpreter. */
+int b2o_graph_variant(b2o_graph *g, int transposed, double beta, int *executor, uint64_t *source_hash);
 /* passes, reductions and algorithmic DRAM bytes of one apply */
 int b2o_graph_info(b2o_graph *g, int transposed, double beta, int *npasses, int *nreductions, double *alg_bytes);
 

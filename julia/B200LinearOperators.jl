@@ -371,6 +371,12 @@ function graph_info(g::Graph; transposed::Bool = false, β::Real = 0.0)
   check(ccall((:b2o_graph_uses_jit, libb2o), Cint, (Ptr{Cvoid}, Cint, Cdouble, Ptr{Cint}), g.handle, transposed, β, jit))
   return (passes = Int(np[]), reductions = Int(nr[]), alg_bytes = bytes[], jit = jit[] != 0)
 end
+# which executor ran the last apply of a variant (:interpreter, :nvrtc, :aot = compiled into libb2o) and the table key
+function graph_variant(g::Graph; transposed::Bool = false, β::Real = 0.0)
+  ex = Ref{Cint}(0); h = Ref{UInt64}(0)
+  check(ccall((:b2o_graph_variant, libb2o), Cint, (Ptr{Cvoid}, Cint, Cdouble, Ptr{Cint}, Ptr{UInt64}), g.handle, transposed, β, ex, h))
+  return (executor = (:interpreter, :nvrtc, :aot)[ex[] + 1], source_hash = h[])
+end
 function graph_jit_source(g::Graph; transposed::Bool = false, β::Real = 0.0)
   buf = Vector{UInt8}(undef, 1 << 16); len = Ref{Int64}(0)
   check(ccall((:b2o_graph_jit_source, libb2o), Cint, (Ptr{Cvoid}, Cint, Cdouble, Ptr{UInt8}, Int64, Ptr{Int64}),

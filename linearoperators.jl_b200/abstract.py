@@ -112,7 +112,8 @@ class Storage:
 def _dtype_rank(dt):
     """(bits, dtype) with None standing for the default Float64"""
     name = "float64" if dt is None else str(dt).replace("torch.", "")
-    return {"bfloat16": 16, "float16": 16, "float32": 32, "float64": 64}.get(name, 64), dt
+    # complex types rank above every real type: promote_type(Vector{Float64}, Vector{ComplexF64}) == Vector{ComplexF64}
+    return {"bfloat16": 16, "float16": 16, "float32": 32, "float64": 64, "complex64": 96, "complex128": 128}.get(name, 64), dt
 
 
 def promote_storage(a, b):

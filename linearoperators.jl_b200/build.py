@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb2o.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["b2o_ctx.cu", "b2o_leaf.cu", "b2o_qn.cu", "b2o_graph.cu", "b2o_kron.cu", "b2o_dense.cu", "b2o_sparse.cu"]
+SOURCES = ["b2o_ctx.cu", "b2o_leaf.cu", "b2o_qn.cu", "b2o_graph.cu", "b2o_graph_aot.cu", "b2o_kron.cu", "b2o_dense.cu", "b2o_sparse.cu"]
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false",            # reference-faithful rounding: Julia broadcasts never contract a*b+c

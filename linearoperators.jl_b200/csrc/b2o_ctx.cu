@@ -97,7 +97,8 @@ extern "C" int b2o_ctx_set_option(b2o_ctx *c, const char *key, int64_t value) {
     if (value < 1 || value > 16) B2O_FAIL(B2O_EARG, "host_chunks must be 1..16");
     c->host_chunks = (int)value;
   } else if (!strcmp(key, "graph_jit")) {
-    c->graph_jit = value != 0;
+    if (value < 0 || value > 2) B2O_FAIL(B2O_EARG, "graph_jit must be 0 (interpreter), 1 (ahead-of-time table, then NVRTC) or 2 (ahead-of-time table only)");
+    c->graph_jit = (int)value;
   } else if (!strcmp(key, "graph_interp")) {
     if (value != 0 && value != 2) B2O_FAIL(B2O_EARG, "graph_interp must be 0 (by program size) or 2 (general machine)");
     c->graph_interp = (int)value;

@@ -365,7 +365,8 @@ struct Compiled {
   std::string jit_src;
   void *jit_module = nullptr;           // CUmodule
   void *jit_func = nullptr;             // CUfunction
-  int jit_state = 0;                    // 0 not tried, 1 ready, -1 unavailable (interpreter is used)
+  int jit_state = 0;                    // 0 not tried, 1 NVRTC module ready, 2 ahead-of-time instantiation found, -1 unavailable (interpreter)
+  const void *aot_fn = nullptr;         // kernel of csrc/b2o_graph_aot.cu whose source hash matches jit_src
   int jit_blocks_per_sm = 0;
 };
 
@@ -834,32 +835,79 @@ extern "C" int b2o_graph_jit_check(b2o_graph *g, int64_t *cubin_bytes) {
   return B2O_OK;
 }
 
+// Ahead-of-time instantiations (csrc/b2o_graph_aot.cu, generated by tools/gen_graph_aot.py from this file's own code
+// generator): the specialised pass kernels of the common static chains -- BASELINE config 3 and its transpose / beta != 0
+// variants, H*D, D1*D2, D + c*I, H1*H2, H*D*H -- compiled by nvcc with the rest of the library, keyed by the FNV-1a hash of
+// their generated source.  A tree whose lowering produces the same source runs the specialised kernel WITHOUT libnvrtc.
+struct B2oAotKernel {
+  unsigned long long hash;
+  const void *fn;
+};
+extern const B2oAotKernel g_b2o_graph_aot[];
+extern const int g_b2o_graph_aot_n;
+static unsigned long long fnv1a64(const std::string &s) {
+  unsigned long long h = 1469598103934665603ULL;
+  for (unsigned char ch : s) {
+    h ^= ch;
+    h *= 1099511628211ULL;
+  }
+  return h;
+}
+
+// c->graph_jit: 0 interpreter only, 1 (default) ahead-of-time table, then NVRTC, then interpreter, 2 ahead-of-time table only
 static int ensure_jit(b2o_ctx *c, Compiled &C) {
-  if (C.jit_state != 0) return C.jit_state;
-  C.jit_state = -1;
-  jit_load_api();
-  if (!g_jit.ok) return -1;
-  std::vector<char> cubin;
-  std::string log;
-  if (jit_compile_cubin(C.jit_src, cubin, log) != 0) return -1;
-  cudaFree(0);  // make sure the runtime's primary context is current for the driver calls
-  void *mod = nullptr, *fn = nullptr;
-  if (g_jit.ModuleLoadData(&mod, cubin.data()) != 0) return -1;
-  if (g_jit.ModuleGetFunction(&fn, mod, "b2o_fused") != 0) return -1;
-  int nb = 0;
-  if (g_jit.OccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, 256, 0) != 0 || nb < 1) return -1;
-  C.jit_module = mod;
-  C.jit_func = fn;
-  C.jit_blocks_per_sm = nb;
-  (void)c;
-  C.jit_state = 1;
-  return 1;
+  if (C.jit_state == 0 || (C.jit_state == -2 && c->graph_jit == 1)) {
+    C.jit_state = -1;
+    const unsigned long long h = fnv1a64(C.jit_src);
+    for (int i = 0; i < g_b2o_graph_aot_n; ++i)
+      if (g_b2o_graph_aot[i].hash == h) {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, g_b2o_graph_aot[i].fn, 256, 0) == cudaSuccess && nb >= 1) {
+          C.aot_fn = g_b2o_graph_aot[i].fn;
+          C.jit_blocks_per_sm = nb;
+          C.jit_state = 2;
+          return 2;
+        }
+        cudaGetLastError();
+      }
+    if (c->graph_jit == 2) {
+      C.jit_state = -2;     // not in the table and NVRTC not allowed: retried if the option goes back to 1
+      return -1;
+    }
+    jit_load_api();
+    if (!g_jit.ok) return -1;
+    std::vector<char> cubin;
+    std::string log;
+    if (jit_compile_cubin(C.jit_src, cubin, log) != 0) return -1;
+    cudaFree(0);  // make sure the runtime's primary context is current for the driver calls
+    void *mod = nullptr, *fn = nullptr;
+    if (g_jit.ModuleLoadData(&mod, cubin.data()) != 0) return -1;
+    if (g_jit.ModuleGetFunction(&fn, mod, "b2o_fused") != 0) return -1;
+    int nb = 0;
+    if (g_jit.OccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, 256, 0) != 0 || nb < 1) return -1;
+    C.jit_module = mod;
+    C.jit_func = fn;
+    C.jit_blocks_per_sm = nb;
+    C.jit_state = 1;
+    return 1;
+  }
+  if (C.jit_state == 1 && c->graph_jit == 2) return -1;   // "ahead-of-time only" excludes an NVRTC module built earlier
+  return C.jit_state;
 }
 
 // 1 when the last apply of this variant ran the NVRTC-specialised kernel, 0 for the interpreter
 extern "C" int b2o_graph_uses_jit(b2o_graph *g, int transposed, double beta, int *out) {
   if (!g || g->root < 0 || !out) B2O_FAIL(B2O_EARG, "graph not compiled");
-  *out = g->prog[transposed ? 1 : 0][beta != 0.0].jit_state == 1;
+  *out = g->prog[transposed ? 1 : 0][beta != 0.0].jit_state >= 1;
+  return B2O_OK;
+}
+// which executor the last apply of this variant used: 0 interpreter, 1 NVRTC-specialised, 2 ahead-of-time instantiation; and
+// the FNV-1a hash of the variant's generated source (the key of the ahead-of-time table)
+extern "C" int b2o_graph_variant(b2o_graph *g, int transposed, double beta, int *executor, uint64_t *source_hash) {
+  if (!g || g->root < 0) B2O_FAIL(B2O_EARG, "graph not compiled");
+  const Compiled &C = g->prog[transposed ? 1 : 0][beta != 0.0];
+  if (executor) *executor = C.jit_state >= 1 ? C.jit_state : 0;
+  if (source_hash) *source_hash = fnv1a64(C.jit_src);
   return B2O_OK;
 }
 extern "C" int b2o_graph_leaf(b2o_graph *g, int kind, const void *ptr, int *node) {
@@ -930,7 +978,8 @@ extern "C" int b2o_graph_apply(b2o_graph *g, int transposed, void *res, int64_t 
   if (!c) B2O_FAIL(B2O_EARG, "graph was created without a context (dry graph)");
   B2O_CUDA(cudaSetDevice(c->device));
   Compiled &C = g->prog[transposed ? 1 : 0][beta != 0.0];
-  if (c->graph_jit && ensure_jit(c, C) == 1) {
+  const int jit_kind = c->graph_jit ? ensure_jit(c, C) : -1;
+  if (jit_kind >= 1) {
     JitRT R;
     memset(&R, 0, sizeof(R));
     for (int i = 2; i < G_MAX_ARR; ++i) R.arr[i] = C.args.arr[i];
@@ -959,8 +1008,12 @@ extern "C" int b2o_graph_apply(b2o_graph *g, int transposed, void *res, int64_t 
       R.pass_end = C.args.npass;
       R.fused = 1;
       R.bar_target = c->bar_base + (unsigned long long)grid;
-      int rc = g_jit.LaunchCooperativeKernel(C.jit_func, grid, 1, 1, 256, 1, 1, 0, (void *)c->stream, params);
-      if (rc != 0) B2O_FAIL(B2O_ECUDA, "cuLaunchCooperativeKernel failed (%d)", rc);
+      if (jit_kind == 2) {
+        B2O_CUDA(cudaLaunchCooperativeKernel(C.aot_fn, dim3(grid), dim3(256), params, 0, c->stream));
+      } else {
+        int rc = g_jit.LaunchCooperativeKernel(C.jit_func, grid, 1, 1, 256, 1, 1, 0, (void *)c->stream, params);
+        if (rc != 0) B2O_FAIL(B2O_ECUDA, "cuLaunchCooperativeKernel failed (%d)", rc);
+      }
       c->bar_base += (unsigned long long)grid * nbar;
       c->launches++;
     } else {
@@ -968,8 +1021,12 @@ extern "C" int b2o_graph_apply(b2o_graph *g, int transposed, void *res, int64_t 
         R.pass_begin = p;
         R.pass_end = p + 1;
         R.fused = 0;
-        int rc = g_jit.LaunchKernel(C.jit_func, grid, 1, 1, 256, 1, 1, 0, (void *)c->stream, params, nullptr);
-        if (rc != 0) B2O_FAIL(B2O_ECUDA, "cuLaunchKernel failed (%d)", rc);
+        if (jit_kind == 2) {
+          B2O_CUDA(cudaLaunchKernel(C.aot_fn, dim3(grid), dim3(256), params, 0, c->stream));
+        } else {
+          int rc = g_jit.LaunchKernel(C.jit_func, grid, 1, 1, 256, 1, 1, 0, (void *)c->stream, params, nullptr);
+          if (rc != 0) B2O_FAIL(B2O_ECUDA, "cuLaunchKernel failed (%d)", rc);
+        }
         c->launches++;
         for (int r = 0; r < C.args.nred_pass[p]; ++r) B2O_TRY(b2o_allreduce_sum_f64(c, R.dots + C.args.red_of_pass[p][r], 1));
       }

@@ -74,7 +74,10 @@ class FusedOperator(LinearOperator):
                                                ctypes.byref(by)))
         j = ctypes.c_int()
         _lib.check(self.ctx.lib.b2o_graph_uses_jit(self._graph.h, int(transposed), float(beta), ctypes.byref(j)))
-        return {"passes": np_.value, "reductions": nr.value, "alg_bytes": by.value, "jit": bool(j.value)}
+        ex, hs = ctypes.c_int(), ctypes.c_uint64()
+        _lib.check(self.ctx.lib.b2o_graph_variant(self._graph.h, int(transposed), float(beta), ctypes.byref(ex), ctypes.byref(hs)))
+        return {"passes": np_.value, "reductions": nr.value, "alg_bytes": by.value, "jit": bool(j.value),
+                "executor": ("interpreter", "nvrtc", "aot")[ex.value], "source_hash": "%016x" % hs.value}
 
     def source(self, transposed=False, beta=0.0):
         """CUDA source of the NVRTC-specialised kernel for this variant"""

@@ -71,7 +71,10 @@ def _float_type():
 
 class _Leaf(LinearOperator):
     def __init__(self, ctx, T, nrow, ncol, symmetric, hermitian, prod_, tprod_, ctprod_):
-        super().__init__(T, nrow, ncol, symmetric, hermitian, prod_, tprod_, ctprod_, S=Storage("cuda", ctx.device))
+        # storage_type: CuVector{T}; temporaries of composed operators (vtmp, Mv) must carry a complex element type
+        cplx = getattr(T, "is_complex", False)
+        super().__init__(T, nrow, ncol, symmetric, hermitian, prod_, tprod_, ctprod_,
+                         S=Storage("cuda", ctx.device, T if cplx else None))
         self.ctx = ctx
 
 

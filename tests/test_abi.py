@@ -122,3 +122,34 @@ def test_julia_shim_binds_every_export_with_the_header_arity():
     assert not missing, missing
     wrong = {n: (sorted(a), decl[n]) for n, a in seen.items() if n in decl and a != {decl[n]}}
     assert not wrong, wrong
+
+
+def test_fused_graph_aot_table_is_current_and_hits(lo):
+    """csrc/b2o_graph_aot.cu (generated) must match what the library's code generator produces today, and BASELINE config 3
+    must resolve to an ahead-of-time kernel key (so it needs no libnvrtc at run time)"""
+    r = subprocess.run([os.sys.executable, os.path.join(ROOT, "tools", "gen_graph_aot.py"), "--check"], capture_output=True, text=True,
+                       cwd=ROOT)
+    assert r.returncode == 0, r.stdout + r.stderr
+    from linearoperators_jl_b200 import _lib
+    lib = _lib.load()
+    g, node = ctypes.c_void_p(), ctypes.c_int()
+    _lib.check(lib.b2o_graph_create(None, 777, ctypes.byref(g)))
+
+    def leaf(kind, ptr=None):
+        _lib.check(lib.b2o_graph_leaf(g, kind, ptr, ctypes.byref(node)))
+        return node.value
+
+    H, D, E = leaf(4, ctypes.c_void_p(0x5000)), leaf(0, ctypes.c_void_p(0x7000)), leaf(1)
+    _lib.check(lib.b2o_graph_binary(g, 11, H, D, ctypes.byref(node)))
+    P = node.value
+    _lib.check(lib.b2o_graph_unary(g, 12, E, 0.25, ctypes.byref(node)))          # a different scalar: same source, same key
+    S = node.value
+    _lib.check(lib.b2o_graph_binary(g, 10, P, S, ctypes.byref(node)))
+    _lib.check(lib.b2o_graph_compile(g, node.value))
+    table = open(os.path.join(ROOT, "linearoperators.jl_b200", "csrc", "b2o_graph_aot.cu")).read()
+    for tr in (0, 1):
+        for beta in (0.0, 2.0):
+            h = ctypes.c_uint64()
+            _lib.check(lib.b2o_graph_variant(g, tr, beta, None, ctypes.byref(h)))
+            assert "0x%016xULL" % h.value in table, (tr, beta)
+    lib.b2o_graph_destroy(g)

@@ -736,13 +736,14 @@ def _mk_vecs(ctx, n):
     return h1, h2, ctx.uniform(n, 4, 0.5, 1.5), ctx.uniform(n, 14, -1.0, 1.0), ctx.uniform(n, 5), ctx.uniform(n, 6)
 
 
-@pytest.fixture(params=["jit", "interpreter", "interpreter-general"])
+@pytest.fixture(params=["jit", "aot-only", "interpreter", "interpreter-general"])
 def graph_mode(request, ctx):
-    """NVRTC-specialised kernel; built-in interpreter (small programs on the 4-rows-per-dispatch machine); interpreter with
-    every program forced onto the general machine"""
-    ctx.set_option("graph_jit", 1 if request.param == "jit" else 0)
+    """default (ahead-of-time table, then NVRTC); ahead-of-time table only (no NVRTC: trees outside the table fall to the
+    interpreter); built-in interpreter (small programs on the 4-rows-per-dispatch machine); interpreter with every program
+    forced onto the general machine"""
+    ctx.set_option("graph_jit", {"jit": 1, "aot-only": 2}.get(request.param, 0))
     ctx.set_option("graph_interp", 2 if request.param == "interpreter-general" else 0)
-    yield "jit" if request.param == "jit" else "interpreter"
+    yield {"jit": "jit", "aot-only": "aot"}.get(request.param, "interpreter")
     ctx.set_option("graph_jit", 1)
     ctx.set_option("graph_interp", 0)
 
@@ -761,7 +762,9 @@ def test_fused_cfg3_chain(lo, ctx, orc, n, graph_mode):
     assert ctx.launch_count() - l0 == 1
     assert rel(host(out), ref_op(host(v))) <= TOL
     assert rel(host(out), host(tree * v)) <= TOL
-    assert fused.info()["jit"] == (graph_mode == "jit")      # the NVRTC-specialised kernel is the one that ran
+    # the executor that ran: config 3 is in the ahead-of-time table (compiled into libb2o, no libnvrtc needed)
+    assert fused.info()["executor"] == ("interpreter" if graph_mode == "interpreter" else "aot")
+    assert fused.info()["jit"] == (graph_mode != "interpreter")
     for alpha, beta in [(-1.5, 0.75), (2.0, 1.0)]:
         res, ref = r0.clone(), host(r0).copy()
         lo.mul_(res, fused, v, alpha, beta)

@@ -357,6 +357,14 @@ def main():
         # transpose(H*D + 0.1 I) = D*H + 0.1 I: the dot reads h, v only -> 6n*8 bytes (b2o_graph_info), not 7n*8
         tb = fused.info(transposed=True)["alg_bytes"]
         line("cfg3 fused transpose, NVRTC-specialised", timeit(lambda: lo.mul_(res, lo.transpose(fused), v), 50), tb)
+        ctx.set_option("graph_jit", 2)       # ahead-of-time table only: what a deployment without libnvrtc runs
+        fused2 = lo.fuse(tree)
+        line("cfg3 fused, NO NVRTC: ahead-of-time instantiation compiled into libb2o", timeit(lambda: lo.mul_(res, fused2, v), 50), 56.0 * n,
+             executor=fused2.info()["executor"])
+        line("cfg3 fused 5-arg beta=0.5, NO NVRTC: ahead-of-time instantiation", timeit(lambda: lo.mul_(res, fused2, v, 2.0, 0.5), 50), 64.0 * n,
+             executor=fused2.info(beta=0.5)["executor"])
+        line("cfg3 fused transpose, NO NVRTC: ahead-of-time instantiation", timeit(lambda: lo.mul_(res, lo.transpose(fused2), v), 50), tb,
+             executor=fused2.info(transposed=True)["executor"])
         ctx.set_option("graph_jit", 0)
         for interp, name in ((0, "interpreter, 4 rows per dispatch (small-program machine)"), (2, "interpreter, general machine (round-1 form)")):
             ctx.set_option("graph_interp", interp)
