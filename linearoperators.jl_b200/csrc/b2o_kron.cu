@@ -35,8 +35,8 @@ __host__ __device__ constexpr uint32_t kr_a_bytes(int BM) { return (uint32_t)BM 
 __host__ __device__ constexpr uint32_t kr_b_bytes(int BN) { return (uint32_t)BN * KR_BK * 2; }
 // a ring stage holds TWO (A, B) k-blocks (phase 0: k-blocks 2i, 2i+1; phase 1: Yhi, Ylo k-block i sharing one B2 k-block)
 __host__ __device__ constexpr uint32_t kr_stage_bytes(int BM, int BN) { return 2 * kr_a_bytes(BM) + 2 * kr_b_bytes(BN); }
-// epilogue staging: max(Yhi + Ylo tiles, one fp32 result tile) = 4·BM·BN bytes
-__host__ __device__ constexpr uint32_t kr_staging_bytes(int BM, int BN) { return 4u * (uint32_t)BM * (uint32_t)BN; }
+// epilogue staging: max(Yhi + Ylo tiles, one fp32 result tile) = 4·BM·BN bytes (+ an fp32 exchange tile of the same size for BM = 64)
+__host__ __device__ constexpr uint32_t kr_staging_bytes(int BM, int BN) { return (BM == 64 ? 8u : 4u) * (uint32_t)BM * (uint32_t)BN; }
 __host__ __device__ constexpr int kr_stages(int BM, int BN) {
   return (int)((KR_SMEM_LIMIT - 2048 - kr_staging_bytes(BM, BN)) / kr_stage_bytes(BM, BN)) > 8 ? 8
                                                                                                 : (int)((KR_SMEM_LIMIT - 2048 - kr_staging_bytes(BM, BN)) / kr_stage_bytes(BM, BN));
@@ -243,10 +243,14 @@ kron_cluster_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
   static_assert(ST >= 2, "ring too shallow");
   // instruction descriptor: D=F32, A=B=BF16, both K-major, N=BN, M=BM
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(KR_BM >> 4) << 24);
+  constexpr bool STACK = BM == 64;                       // phase 1 issues [Yhi; Ylo] as ONE 128-row operand (see the MMA warp)
+  constexpr uint32_t IDESC_STACK = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr int TCOLS = BN < 32 ? 32 : BN;               // TMEM columns per accumulator; two accumulators are allocated
+  constexpr uint32_t XCH_OFF = 4u * BM * BN;             // STACK: fp32 exchange tile behind the staging tiles
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SW128 needs 1024 B
   unsigned char *staging = smem + (size_t)ST * STAGE_BYTES;
-  __shared__ __align__(8) uint64_t full[ST], empty[ST], tmem_full, tmem_empty, y_ready;
+  __shared__ __align__(8) uint64_t full[ST], empty[ST], tmem_full[2], tmem_empty[2], y_ready[2];
   __shared__ uint32_t s_tmem;
   // warp index through a shuffle: ptxas then KNOWS it is warp-uniform and keeps the role loops' addresses, descriptors and
   // barrier handles in uniform registers (UTCHMMA / UTMALDG take UR operands)
@@ -272,13 +276,15 @@ kron_cluster_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], C);       // one multicast commit from every CTA of the cluster
     }
-    mbar_init(&tmem_full, 1);
-    mbar_init(&tmem_empty, 4);
-    mbar_init(&y_ready, C);          // one remote arrive from every CTA's Y store
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+      mbar_init(&y_ready[a], C);     // one remote arrive from every CTA's Y store
+    }
     mbar_fence_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"((uint32_t)(BN < 32 ? 32 : BN)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"((uint32_t)(2 * TCOLS)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -289,234 +295,286 @@ kron_cluster_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
   if (threadIdx.x == 0) KR_STAMP(1);
 
   uint32_t stage = 0, sphase = 0;    // smem ring position (producer and MMA warp each keep their own copy)
-  uint32_t tphase = 0;               // accumulator hand-over parity (MMA warp and epilogue warps)
-  uint32_t yphase = 0;               // y_ready parity (one completion per unit)
+  uint32_t tcount = 0;               // tiles handed over so far (MMA warp and epilogue warps count alike): accumulator tcount & 1
   const int kb0 = (p.K1 + KR_BK - 1) / KR_BK, ks0 = (kb0 + 1) / 2;   // phase 0: two k-blocks per stage
   const int ks1 = (p.N1 + KR_BK - 1) / KR_BK;                        // phase 1: one (hi, lo) k-block pair per stage
   const int nt0 = (p.N1 + BN - 1) / BN, nt1 = (p.N2 + BN - 1) / BN;
   const int it0 = (nt0 + (int)C - 1) / (int)C, it1 = (nt1 + (int)C - 1) / (int)C;
+  const int nu = cid < p.units ? (p.units - 1 - cid) / ncl + 1 : 0;  // units of this cluster: cid, cid + ncl, ...
 
-  for (int u = cid; u < p.units; u += ncl) {
-    const int b = u / p.rblocks, m0 = (u - b * p.rblocks) * KR_BM;
-    const bool first_unit = u == cid;
+  // Software pipeline over the cluster's units: step i runs phase 0 of unit i and THEN phase 1 of unit i-1, so the hand-over
+  // of Y (TMA store -> cluster-wide publication -> first multicast load) of one unit hides behind the next unit's first GEMM.
+  // Every role walks the same step sequence.  Two y_ready barriers (units alternate), two TMEM accumulators (tiles alternate:
+  // the MMAs of a tile run while the epilogue drains the previous one).
+  for (int i = 0; i <= nu; ++i) {
+    const bool do0 = i < nu, do1 = i >= 1;
+    const int u0 = cid + i * ncl, u1 = cid + (i - 1) * ncl;
+    const int b0 = do0 ? u0 / p.rblocks : 0, m00 = do0 ? (u0 - b0 * p.rblocks) * KR_BM : 0;       // unit of this step's phase 0
+    const int b1 = do1 ? u1 / p.rblocks : 0, m01 = do1 ? (u1 - b1 * p.rblocks) * KR_BM : 0;       // unit of this step's phase 1
+    uint64_t *yr1 = &y_ready[(i - 1) & 1];
+    const uint32_t yphase1 = (uint32_t)((i - 1) >> 1) & 1u;
+    const bool first0 = i == 0, first1 = i == 1;
     if (warp == 0) {
       // ===== TMA producer: all 32 lanes run the loops and wait on the barriers; ONE elected lane per stage issues
-      for (int it = 0; it < it0; ++it) {
-        const int tile = it * (int)C + (int)crank;
-        const bool valid = tile < nt0;
-        for (int ks = 0; ks < ks0; ++ks) {
-          const int npair = min(2, kb0 - 2 * ks);
-          mbar_wait(&empty[stage], sphase ^ 1u);
-          if (elect_one()) {
-            mbar_expect_tx(&full[stage], (uint32_t)npair * (A_BYTES + (valid ? B_BYTES : 0u)));
-            unsigned char *sa = smem + (size_t)stage * STAGE_BYTES;
-            for (int pr = 0; pr < npair; ++pr) {
-              const int kk = (2 * ks + pr) * KR_BK;
-              if (valid) tma_load_3d(sa + 2 * A_BYTES + pr * B_BYTES, &tmX, kk, tile * BN, b, &full[stage]);
-              // the A operand is shared by the cluster: k-block j is fetched by CTA j mod C and multicast to all C
-              if (C == 1) tma_load_2d(sa + pr * A_BYTES, &tmA1, kk, m0, &full[stage]);
-              else if ((uint32_t)(2 * ks + pr) % C == crank) tma_load_2d_mc(sa + pr * A_BYTES, &tmA1, kk, m0, &full[stage], mc_mask);
+      if (do0) {
+        for (int it = 0; it < it0; ++it) {
+          const int tile = it * (int)C + (int)crank;
+          const bool valid = tile < nt0;
+          for (int ks = 0; ks < ks0; ++ks) {
+            const int npair = min(2, kb0 - 2 * ks);
+            mbar_wait(&empty[stage], sphase ^ 1u);
+            if (elect_one()) {
+              mbar_expect_tx(&full[stage], (uint32_t)npair * (A_BYTES + (valid ? B_BYTES : 0u)));
+              unsigned char *sa = smem + (size_t)stage * STAGE_BYTES;
+              for (int pr = 0; pr < npair; ++pr) {
+                const int kk = (2 * ks + pr) * KR_BK;
+                if (valid) tma_load_3d(sa + 2 * A_BYTES + pr * B_BYTES, &tmX, kk, tile * BN, b0, &full[stage]);
+                // the A operand is shared by the cluster: k-block j is fetched by CTA j mod C and multicast to all C
+                if (C == 1) tma_load_2d(sa + pr * A_BYTES, &tmA1, kk, m00, &full[stage]);
+                else if ((uint32_t)(2 * ks + pr) % C == crank) tma_load_2d_mc(sa + pr * A_BYTES, &tmA1, kk, m00, &full[stage], mc_mask);
+              }
             }
+            __syncwarp();
+            if (++stage == ST) { stage = 0; sphase ^= 1u; }
           }
-          __syncwarp();
-          if (++stage == ST) { stage = 0; sphase ^= 1u; }
         }
       }
-      bool y_waited = false;
-      for (int it = 0; it < it1; ++it) {
-        const int tile = it * (int)C + (int)crank;
-        const bool valid = tile < nt1;
-        for (int ks = 0; ks < ks1; ++ks) {
-          mbar_wait(&empty[stage], sphase ^ 1u);
-          unsigned char *sa = smem + (size_t)stage * STAGE_BYTES;
-          if (elect_one()) {
-            mbar_expect_tx(&full[stage], 2 * A_BYTES + (valid ? B_BYTES : 0u));
-            if (valid) tma_load_2d(sa + 2 * A_BYTES, &tmB2, ks * KR_BK, tile * BN, &full[stage]);   // does not depend on Y: prefetched
-          }
-          __syncwarp();
-          if (!y_waited) {
-            mbar_wait_cluster(&y_ready, yphase);                     // every CTA of the cluster has stored its Y tiles
-            asm volatile("fence.proxy.async;" ::: "memory");          // ... and the bulk reads below must observe them
-            y_waited = true;
-            if (lane == 0 && first_unit) KR_STAMP(5);
-          }
-          if (elect_one()) {
-            if (C == 1) {
-              tma_load_3d(sa, &tmYld, ks * KR_BK, m0, b, &full[stage]);
-              tma_load_3d(sa + A_BYTES, &tmYld, p.ldy + ks * KR_BK, m0, b, &full[stage]);
-            } else {
-              if ((uint32_t)(2 * ks) % C == crank) tma_load_3d_mc(sa, &tmYld, ks * KR_BK, m0, b, &full[stage], mc_mask);
-              if ((uint32_t)(2 * ks + 1) % C == crank) tma_load_3d_mc(sa + A_BYTES, &tmYld, p.ldy + ks * KR_BK, m0, b, &full[stage], mc_mask);
+      if (do1) {
+        bool y_waited = false;
+        for (int it = 0; it < it1; ++it) {
+          const int tile = it * (int)C + (int)crank;
+          const bool valid = tile < nt1;
+          for (int ks = 0; ks < ks1; ++ks) {
+            mbar_wait(&empty[stage], sphase ^ 1u);
+            unsigned char *sa = smem + (size_t)stage * STAGE_BYTES;
+            if (elect_one()) {
+              mbar_expect_tx(&full[stage], 2 * A_BYTES + (valid ? B_BYTES : 0u));
+              if (valid) tma_load_2d(sa + 2 * A_BYTES, &tmB2, ks * KR_BK, tile * BN, &full[stage]);   // does not depend on Y: prefetched
             }
+            __syncwarp();
+            if (!y_waited) {
+              mbar_wait_cluster(yr1, yphase1);                         // every CTA of the cluster has stored its Y tiles
+              asm volatile("fence.proxy.async;" ::: "memory");          // ... and the bulk reads below must observe them
+              y_waited = true;
+              if (lane == 0 && first1) KR_STAMP(5);
+            }
+            if (elect_one()) {
+              if (C == 1) {
+                tma_load_3d(sa, &tmYld, ks * KR_BK, m01, b1, &full[stage]);
+                tma_load_3d(sa + A_BYTES, &tmYld, p.ldy + ks * KR_BK, m01, b1, &full[stage]);
+              } else {
+                if ((uint32_t)(2 * ks) % C == crank) tma_load_3d_mc(sa, &tmYld, ks * KR_BK, m01, b1, &full[stage], mc_mask);
+                if ((uint32_t)(2 * ks + 1) % C == crank) tma_load_3d_mc(sa + A_BYTES, &tmYld, p.ldy + ks * KR_BK, m01, b1, &full[stage], mc_mask);
+              }
+            }
+            __syncwarp();
+            if (++stage == ST) { stage = 0; sphase ^= 1u; }
           }
-          __syncwarp();
-          if (++stage == ST) { stage = 0; sphase ^= 1u; }
         }
       }
     } else if (warp == 1) {
       // ===== MMA issuer
       for (int ph = 0; ph < 2; ++ph) {
+        if (ph == 0 ? !do0 : !do1) continue;
         const int iters = ph == 0 ? it0 : it1, nt = ph == 0 ? nt0 : nt1, ksteps = ph == 0 ? ks0 : ks1;
         for (int it = 0; it < iters; ++it) {
           const bool valid = it * (int)C + (int)crank < nt;
+          const uint32_t acc = tcount & 1u, tpar = (tcount >> 1) & 1u;
+          const uint32_t tmem_acc = tmem_base + acc * (uint32_t)TCOLS;
           if (valid) {
-            mbar_wait(&tmem_empty, tphase ^ 1u);      // epilogue has drained the accumulator of the previous tile
+            mbar_wait(&tmem_empty[acc], tpar ^ 1u);   // the epilogue has drained this accumulator (two tiles ago)
             tc_fence_after();
           }
           for (int ks = 0; ks < ksteps; ++ks) {
             mbar_wait(&full[stage], sphase);
             tc_fence_after();
-            if (lane == 0 && ks == 0 && it == 0 && first_unit) KR_STAMP(2 + 4 * ph);
-            if (lane == 0 && it == 0 && first_unit && ks < 8) KR_STAMP(16 + 8 * ph + ks);   // arrival of every stage of the first tile
+            if (lane == 0 && ks == 0 && it == 0 && (ph == 0 ? first0 : first1)) KR_STAMP(2 + 4 * ph);
+            if (lane == 0 && it == 0 && (ph == 0 ? first0 : first1) && ks < 8) KR_STAMP(16 + 8 * ph + ks);   // arrival of every stage of the first tile
             if (elect_one()) {      // ONE election per stage; the branch is single-threaded by construction (no waterfall loops)
               unsigned char *sa = smem + (size_t)stage * STAGE_BYTES;
               if (valid) {
-                const int npair = ph == 0 ? min(2, kb0 - 2 * ks) : 2;
-                for (int pr = 0; pr < npair; ++pr) {
-                  const uint64_t adesc = umma_desc_sw128(sa + pr * A_BYTES);
-                  const uint64_t bdesc = umma_desc_sw128(sa + 2 * A_BYTES + (ph == 0 ? pr * B_BYTES : 0u));
+                if (ph == 1 && STACK) {
+                  // BM = 64: [Yhi; Ylo] are adjacent 64-row blocks of the stage = ONE 128-row A operand.  One M=128 MMA per
+                  // k-slice computes hi*B2^T in TMEM lanes 0-63 and lo*B2^T in lanes 64-127 (the epilogue adds the halves):
+                  // half the tcgen05.mma count of issuing hi and lo separately.
+                  const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + 2 * A_BYTES);
 #pragma unroll
-                  for (int k = 0; k < KR_BK / 16; ++k)   // UMMA_K = 16 bf16 = 32 B: advance the start address inside the swizzle atom
-                    tc_mma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (ks | pr | k) ? 1u : 0u);
+                  for (int k = 0; k < KR_BK / 16; ++k)
+                    tc_mma_bf16(tmem_acc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC_STACK, (ks | k) ? 1u : 0u);
+                } else {
+                  const int npair = ph == 0 ? min(2, kb0 - 2 * ks) : 2;
+                  for (int pr = 0; pr < npair; ++pr) {
+                    const uint64_t adesc = umma_desc_sw128(sa + pr * A_BYTES);
+                    const uint64_t bdesc = umma_desc_sw128(sa + 2 * A_BYTES + (ph == 0 ? pr * B_BYTES : 0u));
+#pragma unroll
+                    for (int k = 0; k < KR_BK / 16; ++k)   // UMMA_K = 16 bf16 = 32 B: advance the start address inside the swizzle atom
+                      tc_mma_bf16(tmem_acc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (ks | pr | k) ? 1u : 0u);
+                  }
                 }
               }
               // hand the slot back to EVERY producer of the cluster (their multicasts write into this CTA's copy too)
               if (C > 1) tc_commit_mc(&empty[stage], mc_mask);
               else tc_commit(&empty[stage]);
-              if (valid && ks == ksteps - 1) tc_commit(&tmem_full);
+              if (valid && ks == ksteps - 1) tc_commit(&tmem_full[acc]);
             }
             __syncwarp();
             if (++stage == ST) { stage = 0; sphase ^= 1u; }
           }
-          if (valid) tphase ^= 1u;
+          if (valid) ++tcount;
         }
       }
     } else {
-      // ===== epilogue: warp w owns TMEM lanes [32*(w%4), +32) = rows of the tile
+      // ===== epilogue: warp w owns TMEM lanes [32*(w%4), +32)
       const int quarter = warp & 3;
       // UMMA M=128: row = TMEM lane.  M=64: rows 16q..16q+15 live in lanes 32q..32q+15 (half sub-partitions), lanes 16-31 idle
       const bool row_ok = BM == 128 || lane < 16;
       const int rloc = BM == 128 ? quarter * 32 + lane : quarter * 16 + (lane & 15);      // row inside the unit
       const bool issuer = threadIdx.x == 64;
       // ---- phase 0: Y tile -> bf16 hi/lo -> swizzled staging -> TMA store
-      for (int it = 0; it < it0; ++it) {
-        const int tile = it * (int)C + (int)crank;
-        if (tile < nt0) {
-          mbar_wait(&tmem_full, tphase);
-          tc_fence_after();
-          if (warp == 2 && lane == 0 && it == 0 && first_unit) KR_STAMP(3);
-          if (issuer) tma_store_wait_read();      // the staging tile of the previous store has been read
-          epi_sync();
-#pragma unroll 1
-          for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-            if (row_ok) {
-#pragma unroll
-            for (int g = 0; g < 32; g += 8) {
-              uint32_t hi[4], lo[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float y0 = __uint_as_float(v[g + 2 * e]), y1 = __uint_as_float(v[g + 2 * e + 1]);
-                const __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
-                const __nv_bfloat162 l = __floats2bfloat162_rn(y0 - __low2float(h), y1 - __high2float(h));
-                hi[e] = *reinterpret_cast<const uint32_t *>(&h);
-                lo[e] = *reinterpret_cast<const uint32_t *>(&l);
-              }
-              // staging box = [128 rows][YB cols] bf16, rows of YB*2 bytes, TMA 128-/64-byte swizzle on the 16-byte chunk index
-              const int col = c0 + g, box = col / YB, chunk = (col % YB) / 8;
-              const int sw = (YB == 64) ? (chunk ^ (rloc & 7)) : (chunk ^ ((rloc >> 1) & 3));
-              unsigned char *dst = staging + (size_t)box * (KR_BM * YB * 2) + (size_t)rloc * (YB * 2) + sw * 16;
-              *reinterpret_cast<uint4 *>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              *reinterpret_cast<uint4 *>(dst + (size_t)NYB * (KR_BM * YB * 2)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
-            }
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty);
-          fence_proxy_async_smem();               // staging writes -> visible to the bulk store
-          epi_sync();
-          if (issuer) {
-#pragma unroll
-            for (int bx = 0; bx < NYB; ++bx) {
-              if (tile * BN + bx * YB >= p.N1) continue;       // box entirely in the padding columns
-              tma_store_3d(&tmYhi, staging + (size_t)bx * (KR_BM * YB * 2), tile * BN + bx * YB, m0, b);
-              tma_store_3d(&tmYlo, staging + (size_t)(NYB + bx) * (KR_BM * YB * 2), tile * BN + bx * YB, m0, b);
-            }
-            tma_store_commit();
-          }
-          tphase ^= 1u;
-        }
-      }
-      if (issuer) {
-        // publish: all Y tiles of this CTA are in global memory -> release-arrive on y_ready of every CTA of the cluster
-        tma_store_wait_all();
-        asm volatile("fence.proxy.async;" ::: "memory");
-        asm volatile("fence.acq_rel.cluster;" ::: "memory");
-        for (uint32_t r = 0; r < C; ++r) mbar_arrive_remote(&y_ready, (crank + 1 + r) % C);   // peers first, own copy last
-        if (first_unit) KR_STAMP(4);
-      }
-      // ---- phase 1: result tile
-      for (int it = 0; it < it1; ++it) {
-        const int tile = it * (int)C + (int)crank;
-        if (tile < nt1) {
-          const int n0 = tile * BN;
-          mbar_wait(&tmem_full, tphase);
-          tc_fence_after();
-          if (warp == 2 && lane == 0 && it == 0 && first_unit) KR_STAMP(7);
-          if (p.store_tma) {
-            if (issuer) tma_store_wait_read();
+      if (do0) {
+        for (int it = 0; it < it0; ++it) {
+          const int tile = it * (int)C + (int)crank;
+          if (tile < nt0) {
+            const uint32_t acc = tcount & 1u, tpar = (tcount >> 1) & 1u;
+            const uint32_t tmem_acc = tmem_base + acc * (uint32_t)TCOLS;
+            mbar_wait(&tmem_full[acc], tpar);
+            tc_fence_after();
+            if (warp == 2 && lane == 0 && it == 0 && first0) KR_STAMP(3);
+            if (issuer) tma_store_wait_read();      // the staging tile of the previous store has been read
             epi_sync();
-          }
 #pragma unroll 1
-          for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-            if (p.store_tma) {
-              // staging tile [BN cols (j)][BM rows (i)]: lanes write consecutive i -> conflict-free, no swizzle needed
-              if (!row_ok) {
-              } else if (p.out_f32) {
-                float *st = reinterpret_cast<float *>(staging) + (size_t)c0 * KR_BM + rloc;
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+              uint32_t v[32];
+              tc_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+              if (row_ok) {
 #pragma unroll
-                for (int e = 0; e < 32; ++e) st[(size_t)e * KR_BM] = p.alpha * __uint_as_float(v[e]);
-              } else {
-                __nv_bfloat16 *st = reinterpret_cast<__nv_bfloat16 *>(staging) + (size_t)c0 * KR_BM + rloc;
+                for (int g = 0; g < 32; g += 8) {
+                  uint32_t hi[4], lo[4];
 #pragma unroll
-                for (int e = 0; e < 32; ++e) st[(size_t)e * KR_BM] = __float2bfloat16_rn(p.alpha * __uint_as_float(v[e]));
-              }
-            } else if (row_ok && m0 + rloc < p.M) {
-              // res_b[j*M + i] = α·Z (+ β·res); lanes of a warp write consecutive i: coalesced
-              const size_t off = (size_t)b * p.M * p.N2 + (size_t)(m0 + rloc) + (size_t)(n0 + c0) * p.M;
-              const int nvalid = p.N2 - (n0 + c0);
-              if (nvalid > 0) {
-                if (p.out_f32) {
-                  if (p.beta != 0.f) kron_store_cols<true, true>(p.res, off, p.M, p.alpha, p.beta, v, nvalid);
-                  else kron_store_cols<true, false>(p.res, off, p.M, p.alpha, p.beta, v, nvalid);
-                } else {
-                  if (p.beta != 0.f) kron_store_cols<false, true>(p.res, off, p.M, p.alpha, p.beta, v, nvalid);
-                  else kron_store_cols<false, false>(p.res, off, p.M, p.alpha, p.beta, v, nvalid);
+                  for (int e = 0; e < 4; ++e) {
+                    const float y0 = __uint_as_float(v[g + 2 * e]), y1 = __uint_as_float(v[g + 2 * e + 1]);
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
+                    const __nv_bfloat162 l = __floats2bfloat162_rn(y0 - __low2float(h), y1 - __high2float(h));
+                    hi[e] = *reinterpret_cast<const uint32_t *>(&h);
+                    lo[e] = *reinterpret_cast<const uint32_t *>(&l);
+                  }
+                  // staging box = [BM rows][YB cols] bf16, rows of YB*2 bytes, TMA 128-/64-byte swizzle on the 16-byte chunk index
+                  const int col = c0 + g, box = col / YB, chunk = (col % YB) / 8;
+                  const int sw = (YB == 64) ? (chunk ^ (rloc & 7)) : (chunk ^ ((rloc >> 1) & 3));
+                  unsigned char *dst = staging + (size_t)box * (KR_BM * YB * 2) + (size_t)rloc * (YB * 2) + sw * 16;
+                  *reinterpret_cast<uint4 *>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                  *reinterpret_cast<uint4 *>(dst + (size_t)NYB * (KR_BM * YB * 2)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 }
               }
             }
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty);
-          if (p.store_tma) {
-            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            fence_proxy_async_smem();               // staging writes -> visible to the bulk store
             epi_sync();
             if (issuer) {
-              tma_store_3d(&tmRes, staging, m0, n0, b);
+#pragma unroll
+              for (int bx = 0; bx < NYB; ++bx) {
+                if (tile * BN + bx * YB >= p.N1) continue;       // box entirely in the padding columns
+                tma_store_3d(&tmYhi, staging + (size_t)bx * (KR_BM * YB * 2), tile * BN + bx * YB, m00, b0);
+                tma_store_3d(&tmYlo, staging + (size_t)(NYB + bx) * (KR_BM * YB * 2), tile * BN + bx * YB, m00, b0);
+              }
               tma_store_commit();
             }
+            ++tcount;
           }
-          if (warp == 2 && lane == 0 && it == 0 && first_unit) KR_STAMP(8);
-          tphase ^= 1u;
+        }
+        if (issuer) {
+          // publish: all Y tiles of this CTA are in global memory -> one cluster-scope release, then an arrive on y_ready of
+          // every CTA of the cluster
+          tma_store_wait_all();
+          asm volatile("fence.proxy.async;" ::: "memory");
+          asm volatile("fence.acq_rel.cluster;" ::: "memory");
+          for (uint32_t r = 0; r < C; ++r) mbar_arrive_remote(&y_ready[i & 1], (crank + 1 + r) % C);   // peers first, own copy last
+          if (first0) KR_STAMP(4);
+        }
+      }
+      // ---- phase 1: result tile
+      if (do1) {
+        for (int it = 0; it < it1; ++it) {
+          const int tile = it * (int)C + (int)crank;
+          if (tile < nt1) {
+            const int n0 = tile * BN;
+            const uint32_t acc = tcount & 1u, tpar = (tcount >> 1) & 1u;
+            const uint32_t tmem_acc = tmem_base + acc * (uint32_t)TCOLS;
+            mbar_wait(&tmem_full[acc], tpar);
+            tc_fence_after();
+            if (warp == 2 && lane == 0 && it == 0 && first1) KR_STAMP(7);
+            if (p.store_tma || STACK) {
+              if (issuer) tma_store_wait_read();
+              epi_sync();
+            }
+            // STACK (BM = 64): TMEM lanes 0-63 hold hi*B2^T, lanes 64-127 lo*B2^T of the same 64 rows: the lo warps (quarters 2, 3)
+            // park their fp32 values in the exchange tile, the hi warps add them.  srow = row inside the unit for both halves.
+            const int srow = STACK ? (quarter & 1) * 32 + lane : rloc;
+            const bool lo_half = STACK && quarter >= 2;
+            const bool r_ok = STACK ? true : row_ok;
+            float *xch = reinterpret_cast<float *>(staging + XCH_OFF);                // [BN][BM] fp32 exchange tile (STACK only)
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+              uint32_t v[32];
+              tc_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+              if (STACK) {
+                if (lo_half) {
+#pragma unroll
+                  for (int e = 0; e < 32; ++e) xch[(size_t)(c0 + e) * KR_BM + srow] = __uint_as_float(v[e]);
+                }
+                epi_sync();
+                if (!lo_half) {
+#pragma unroll
+                  for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + xch[(size_t)(c0 + e) * KR_BM + srow]);
+                }
+              }
+              if (lo_half) continue;
+              if (p.store_tma) {
+                // staging tile [BN cols (j)][BM rows (i)]: lanes write consecutive i -> conflict-free, no swizzle needed
+                if (!r_ok) {
+                } else if (p.out_f32) {
+                  float *st = reinterpret_cast<float *>(staging) + (size_t)c0 * KR_BM + srow;
+#pragma unroll
+                  for (int e = 0; e < 32; ++e) st[(size_t)e * KR_BM] = p.alpha * __uint_as_float(v[e]);
+                } else {
+                  __nv_bfloat16 *st = reinterpret_cast<__nv_bfloat16 *>(staging) + (size_t)c0 * KR_BM + srow;
+#pragma unroll
+                  for (int e = 0; e < 32; ++e) st[(size_t)e * KR_BM] = __float2bfloat16_rn(p.alpha * __uint_as_float(v[e]));
+                }
+              } else if (r_ok && m01 + srow < p.M) {
+                // res_b[j*M + i] = α·Z (+ β·res); lanes of a warp write consecutive i: coalesced
+                const size_t off = (size_t)b1 * p.M * p.N2 + (size_t)(m01 + srow) + (size_t)(n0 + c0) * p.M;
+                const int nvalid = p.N2 - (n0 + c0);
+                if (nvalid > 0) {
+                  if (p.out_f32) {
+                    if (p.beta != 0.f) kron_store_cols<true, true>(p.res, off, p.M, p.alpha, p.beta, v, nvalid);
+                    else kron_store_cols<true, false>(p.res, off, p.M, p.alpha, p.beta, v, nvalid);
+                  } else {
+                    if (p.beta != 0.f) kron_store_cols<false, true>(p.res, off, p.M, p.alpha, p.beta, v, nvalid);
+                    else kron_store_cols<false, false>(p.res, off, p.M, p.alpha, p.beta, v, nvalid);
+                  }
+                }
+              }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (p.store_tma) {
+              fence_proxy_async_smem();
+              epi_sync();
+              if (issuer) {
+                tma_store_3d(&tmRes, staging, m01, n0, b1);
+                tma_store_commit();
+              }
+            }
+            if (warp == 2 && lane == 0 && it == 0 && first1) KR_STAMP(8);
+            ++tcount;
+          }
         }
       }
     }
-    yphase ^= 1u;
   }
   if (threadIdx.x == 64) tma_store_wait_all();      // bulk stores must have left shared memory before the CTA exits
   tc_fence_before();
@@ -526,7 +584,7 @@ kron_cluster_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
     KR_STAMP(10);
     if (p.dbg && blockIdx.x == 0) p.dbg[33] = (unsigned long long)clock64();
   }
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(BN < 32 ? 32 : BN)) : "memory");
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * TCOLS)) : "memory");
 }
 
 // column-major (rows×cols, ld=rows) -> row-major copy with pitch `ldo`

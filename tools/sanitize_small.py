@@ -59,12 +59,28 @@ def main():
             lo.solve_shifted_system_(xs, gc, x, 0.5)
         xh, rh = x.cpu().pin_memory(), torch.empty(n, dtype=torch.float64).pin_memory()
         g.apply_host(rh, xh)
-    f = lo.fuse(lo.opHouseholder(h) * lo.opDiagonal(d) + 0.1 * lo.opEye(n))
-    for jit in (1, 0):
-        ctx.set_option("graph_jit", jit)
-        lo.mul_(r, f, x, 2.0, 0.5)
-        lo.mul_(r, lo.transpose(f), x)
+    h2 = ctx.uniform(n, 13)
+    h2 /= float(np.sqrt(ctx.dot(h2, h2)))
+    for tree in (lo.opHouseholder(h) * lo.opDiagonal(d) + 0.1 * lo.opEye(n),            # in the ahead-of-time table
+                 lo.opHouseholder(h) * lo.opDiagonal(d) * lo.opHouseholder(h2) + lo.opDiagonal(d)):   # not in it: NVRTC / interpreter
+        for jit, interp in ((1, 0), (2, 0), (0, 0), (0, 2)):     # default; ahead-of-time only; interpreter small / general machine
+            ctx.set_option("graph_jit", jit)
+            ctx.set_option("graph_interp", interp)
+            f = lo.fuse(tree)
+            lo.mul_(r, f, x, 2.0, 0.5)
+            lo.mul_(r, lo.transpose(f), x)
     ctx.set_option("graph_jit", 1)
+    ctx.set_option("graph_interp", 0)
+    # ComplexF64 leaves and the conj-sandwich
+    cd = torch.complex(ctx.uniform(n, 21, -1.0, 1.0), ctx.uniform(n, 22, -1.0, 1.0))
+    cv = torch.complex(ctx.uniform(n, 23, -1.0, 1.0), ctx.uniform(n, 24, -1.0, 1.0))
+    ch = torch.complex(ctx.uniform(n, 25, -1.0, 1.0), ctx.uniform(n, 26, -1.0, 1.0))
+    ch = ch / torch.linalg.vector_norm(ch)
+    cop = lo.opHouseholder(ch) * lo.opDiagonal(cd) + 0.5j * lo.opEye(n)
+    for w in (cop, lo.adjoint(cop), lo.transpose(cop), lo.conj(cop)):
+        cr = cv.clone()
+        lo.mul_(cr, w, cv, 1.5 - 0.5j, 0.25j)
+        lo.mul_(cr, w, cv)
     A = torch.randn(64, 72, device="cuda").to(torch.bfloat16)
     B = torch.randn(136, 40, device="cuda").to(torch.bfloat16)
     K = lo.kron(A, B, max_batch=2, ctx=ctx)
@@ -72,6 +88,14 @@ def main():
     K * xk
     lo.transpose(K) * (K * xk)
     K.apply_batch(torch.stack([xk, xk]).contiguous())
+    for bm, bn, cl in ((64, 32, 4), (128, 64, 2), (128, 128, 1), (64, 64, 8)):       # every tile shape of the clustered kernel
+        K.set_option("tile_m", bm)
+        K.set_option("tile_n", bn)
+        K.set_option("cluster", cl)
+        r32 = torch.empty(64 * 136, dtype=torch.float32, device="cuda")
+        lo.mul_(r32, K, xk)
+        lo.mul_(r32, K, xk, 2.0, -0.5)                                               # beta != 0: direct-store epilogue
+        K.apply_batch(torch.stack([xk, xk]).contiguous())
     torch.cuda.synchronize()
     print("SANITIZE_OK launches=%d" % ctx.launch_count())
 
