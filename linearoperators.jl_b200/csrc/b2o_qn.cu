@@ -38,22 +38,54 @@ static inline int pmod(int a, int m) {
 }
 
 // ------------------------------------------------------------------ small elementwise helpers (push!/diag!, not the hot path)
+// One shape for the three elementwise helpers of push!/diag!: 16-byte vector loads, four independent pairs in flight per thread
+// (loads first, then the arithmetic and the streaming stores), scalar tail / scalar path for 8-byte-aligned user views.
+// Round 1 ran these as scalar grid-stride loops at 3.6-3.8 TB/s (profiles/r2_launches_fwd.csv: div_sqrt_dev_kernel 0.42 ms at n=1e8).
+// F: out[i] = f(x[i], y[i]) with the reference's rounding (the library is built with -fmad=false).
+template <typename F>
+__device__ __forceinline__ void ew_stream(double *__restrict__ out, const double *__restrict__ x, const double *__restrict__ y, int64_t n, bool vec,
+                                          F f) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+  if (vec) {
+    const int64_t npair = n >> 1;
+    for (int64_t base = tid; base < npair; base += 4 * nthr) {
+      double2 xv[4], yv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = base + u * nthr;
+        xv[u] = yv[u] = make_double2(0.0, 0.0);
+        if (i < npair) {
+          xv[u] = ldg_stream2(x + 2 * i);
+          if (y) yv[u] = ldg_stream2(y + 2 * i);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = base + u * nthr;
+        if (i < npair) stg_stream2(out + 2 * i, make_double2(f(xv[u].x, yv[u].x), f(xv[u].y, yv[u].y)));
+      }
+    }
+    if ((n & 1) && tid == 0) out[n - 1] = f(x[n - 1], y ? y[n - 1] : 0.0);
+  } else {
+    for (int64_t i = tid; i < n; i += nthr) out[i] = f(x[i], y ? y[i] : 0.0);
+  }
+}
+static inline bool ew_vec_ok(const void *a, const void *b, const void *c) {
+  return (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) % 16) == 0;
+}
 // out = a*x + b*y   (y may be null -> out = a*x);  rounding as the reference's broadcasts (no fma)
-__global__ void axpby_kernel(double *out, double a, const double *x, double b, const double *y, int64_t n) {
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    out[i] = y ? a * x[i] + b * y[i] : a * x[i];
+__global__ void __launch_bounds__(256) axpby_kernel(double *out, double a, const double *x, double b, const double *y, int64_t n, int vec) {
+  if (y) ew_stream(out, x, y, n, vec != 0, [a, b](double xi, double yi) { return a * xi + b * yi; });
+  else ew_stream(out, x, y, n, vec != 0, [a](double xi, double) { return a * xi; });
 }
 // out = x / d
-__global__ void div_kernel(double *out, const double *x, double d, int64_t n) {
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = x[i] / d;
+__global__ void __launch_bounds__(256) div_kernel(double *out, const double *x, double d, int64_t n, int vec) {
+  ew_stream(out, x, nullptr, n, vec != 0, [d](double xi, double) { return xi / d; });
 }
 // out = x / sqrt(*dscal)   (device scalar)
-__global__ void div_sqrt_dev_kernel(double *out, const double *x, const double *dscal, int64_t n) {
+__global__ void __launch_bounds__(256) div_sqrt_dev_kernel(double *out, const double *x, const double *dscal, int64_t n, int vec) {
   const double d = sqrt(*dscal);
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = x[i] / d;
+  ew_stream(out, x, nullptr, n, vec != 0, [d](double xi, double) { return xi / d; });
 }
 
 // *out = partials[0] + ... + partials[count-1] in index order (one warp)
@@ -172,7 +204,7 @@ static inline int ew_grid(b2o_ctx *c, int64_t n) {
 }
 static int ew_axpby(b2o_ctx *c, double *out, double a, const double *x, double b, const double *y, int64_t n) {
   if (n <= 0) return B2O_OK;
-  axpby_kernel<<<ew_grid(c, n), 256, 0, c->stream>>>(out, a, x, b, y, n);
+  axpby_kernel<<<ew_grid(c, n), 256, 0, c->stream>>>(out, a, x, b, y, n, ew_vec_ok(out, x, y));
   c->launches++;
   B2O_CUDA(cudaGetLastError());
   return B2O_OK;
@@ -1027,7 +1059,7 @@ static int lbfgs_push_common(b2o_qn *q, const double *s, const double *y, double
     double *bi = q->col(q->B, ins);
     q->opnorm_ub -= q->aux[ins] * q->aux[ins];                                                  // :231
     if (n > 0) {
-      div_kernel<<<ew_grid(c, n), 256, 0, c->stream>>>(bi, y, sqrt(ys), n);                     // :232 b = y ./ sqrt(ys)
+      div_kernel<<<ew_grid(c, n), 256, 0, c->stream>>>(bi, y, sqrt(ys), n, ew_vec_ok(bi, y, nullptr));                     // :232 b = y ./ sqrt(ys)
       c->launches++;
     }
     {
@@ -1088,7 +1120,7 @@ static int lbfgs_push_common(b2o_qn *q, const double *s, const double *y, double
         sum_partials_kernel<<<1, 32, 0, c->stream>>>(c->d_partials + (size_t)grid * ca.ncols, grid, c->d_dots + 256);
         c->launches++;
         B2O_TRY(b2o_allreduce_sum_f64(c, c->d_dots + 256, 1));
-        div_sqrt_dev_kernel<<<ew_grid(c, n), 256, 0, c->stream>>>(ak, ak, c->d_dots + 256, n);     // :248
+        div_sqrt_dev_kernel<<<ew_grid(c, n), 256, 0, c->stream>>>(ak, ak, c->d_dots + 256, n, ew_vec_ok(ak, nullptr, nullptr));     // :248
         c->launches++;
         prev[nprev++] = k;
         continue;
@@ -1105,7 +1137,7 @@ static int lbfgs_push_common(b2o_qn *q, const double *s, const double *y, double
       if (n > 0) {
         B2O_TRY(lincomb_launch(c, a));
         B2O_TRY(b2o_allreduce_sum_f64(c, c->d_dots + 256, 2));
-        div_sqrt_dev_kernel<<<ew_grid(c, n), 256, 0, c->stream>>>(ak, ak, c->d_dots + 256, n);   // :248
+        div_sqrt_dev_kernel<<<ew_grid(c, n), 256, 0, c->stream>>>(ak, ak, c->d_dots + 256, n, ew_vec_ok(ak, nullptr, nullptr));   // :248
         c->launches++;
       }
       prev[nprev++] = k;
