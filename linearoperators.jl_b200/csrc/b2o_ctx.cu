@@ -306,9 +306,12 @@ __global__ void __launch_bounds__(256) pair_dots_kernel(PairDotArgs a) {
   if (a.vec) {
     // 16-byte loads, two row pairs per pair of vectors in flight per thread (round 1: scalar loads, 3.6 TB/s)
     const int64_t npair = a.n >> 1;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npair; i += 2 * stride) {
+    // many pairs (update_gram: 6-8): one row pair per trip keeps the loads of a trip within the register budget (two per trip
+    // measured 25 % slower there: 128 live registers of loads); few pairs: two row pairs in flight
+    const int64_t step = a.npairs > 4 ? stride : 2 * stride;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npair; i += step) {
       const int64_t j = i + stride;
-      const bool hj = j < npair;
+      const bool hj = a.npairs <= 4 && j < npair;
 #pragma unroll
       for (int p = 0; p < 8; ++p)
         if (p < a.npairs) {
