@@ -587,6 +587,8 @@ kron_cluster_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * TCOLS)) : "memory");
 }
 
+#include "b2o_kron_pair.cuh"
+
 // column-major (rows×cols, ld=rows) -> row-major copy with pitch `ldo`
 __global__ void kron_transpose_kernel(__nv_bfloat16 *out, const __nv_bfloat16 *in, int rows, int cols, int ldo) {
   __shared__ __nv_bfloat16 tile[32][33];
@@ -749,7 +751,8 @@ extern "C" int b2o_kron_destroy(b2o_kron *k) {
   return B2O_OK;
 }
 
-// tuning overrides: "cluster" (0 auto | 1, 2, 4, 8, 16 CTAs per unit), "tile_m" (0 auto | 64, 128 rows per unit), "tile_n" (0 auto | 32, 64, 128)
+// tuning overrides: "cluster" (0 auto | 1, 2, 4, 8, 16 CTAs per unit), "tile_m" (0 auto | 64, 128 rows per unit | 256 = the
+// cta_group::2 pair kernel, which fixes cluster = 2 and 256-column tiles), "tile_n" (0 auto | 32, 64, 128)
 extern "C" int b2o_kron_set_option(b2o_kron *k, const char *key, int64_t value) {
   if (!k || !key) B2O_FAIL(B2O_EARG, "null argument");
   if (!strcmp(key, "cluster")) {
@@ -759,7 +762,7 @@ extern "C" int b2o_kron_set_option(b2o_kron *k, const char *key, int64_t value) 
     if (value != 0 && value != 32 && value != 64 && value != 128) B2O_FAIL(B2O_EARG, "tile_n must be 0, 32, 64 or 128");
     k->force_bn = (int)value;
   } else if (!strcmp(key, "tile_m")) {
-    if (value != 0 && value != 64 && value != 128) B2O_FAIL(B2O_EARG, "tile_m must be 0, 64 or 128");
+    if (value != 0 && value != 64 && value != 128 && value != 256) B2O_FAIL(B2O_EARG, "tile_m must be 0, 64, 128 or 256 (256 = the cta_group::2 pair kernel)");
     k->force_bm = (int)value;
   } else {
     B2O_FAIL(B2O_EARG, "unknown option '%s'", key);
@@ -819,6 +822,54 @@ static int kron_launch(b2o_ctx *c, const CUtensorMap &tA1, const CUtensorMap &tX
   return B2O_OK;
 }
 
+// the cta_group::2 pair kernel: clusters of 2, one cluster per TPC, persistent over the 256-row units
+static int kron_pair_launch(b2o_ctx *c, const CUtensorMap &tA1, const CUtensorMap &tX, const CUtensorMap &tYld, const CUtensorMap &tB2,
+                            const CUtensorMap &tYhi, const CUtensorMap &tYlo, const CUtensorMap &tRes, KronArgs &a) {
+  static thread_local bool configured = false;
+  static thread_local int fit = 0;
+  auto kern = kron_pair_kernel;
+  if (!configured) {
+    B2O_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KP_SMEM));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(KR_THREADS);
+  cfg.dynamicSmemBytes = KP_SMEM;
+  cfg.stream = c->stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (!fit) {
+    cfg.gridDim = dim3(2);
+    int nc = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
+    if (e != cudaSuccess || nc < 1) {
+      cudaGetLastError();
+      B2O_FAIL(B2O_ECUDA, "kron: a CTA pair with %zu bytes of shared memory does not fit this device", (size_t)KP_SMEM);
+    }
+    fit = nc;
+  }
+  const int nclusters = std::max(1, std::min(a.units, fit));
+  cfg.gridDim = dim3((unsigned)(nclusters * 2));
+  if (c->time_kernels) B2O_CUDA(cudaEventRecord(c->ev0, c->stream));
+  B2O_CUDA(cudaLaunchKernelEx(&cfg, kern, tA1, tX, tYld, tB2, tYhi, tYlo, tRes, a));
+  c->launches++;
+  if (c->time_kernels) {
+    B2O_CUDA(cudaEventRecord(c->ev1, c->stream));
+    B2O_CUDA(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    B2O_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->kern_ms += ms;
+    c->kern_n++;
+  }
+  return B2O_OK;
+}
+
 // trans: 0 prod!, 1 tprod! (== ctprod! for real element types).  x: nb vectors back to back, res likewise.
 extern "C" int b2o_kron_apply(b2o_kron *k, int trans, void *res, int res_dtype, int64_t res_len, const void *x, int64_t x_len,
                               int nb, double alpha, double beta) {
@@ -854,13 +905,21 @@ extern "C" int b2o_kron_apply(b2o_kron *k, int trans, void *res, int res_dtype, 
     BN = 128;
     cluster = 2;
   }
-  if (k->force_bm) BM = k->force_bm;
+  // enough 256-row units to keep every TPC busy and tiles wide enough to fill the 256-column pair MMA: the cta_group::2 kernel
+  bool pair = !k->force_bm && M >= 256 && std::min(N1, N2) >= 192 && (int64_t)nb * ((M + 255) / 256) >= c->num_sms / 2;
+  if (k->force_bm == 256) pair = true;
+  if (k->force_bm && !pair) BM = k->force_bm;
   if (k->force_bn) BN = k->force_bn;
   while (cluster > 1 && (cluster / 2) * BN >= nmax) cluster /= 2;  // no more CTAs than N tiles
   if (k->force_cluster) cluster = k->force_cluster;
-  a.rblocks = (M + BM - 1) / BM;
+  if (pair) {            // operand boxes of 128 rows; Y leaves in 32-column boxes, the result in 128 x 32 boxes
+    BM = 128;
+    BN = 128;
+  }
+  a.rblocks = pair ? (M + 255) / 256 : (M + BM - 1) / BM;
   a.units = nb * a.rblocks;
   const int w = BN == 128 ? 0 : BN == 64 ? 1 : 2, mi = BM == 128 ? 0 : 1;
+  const int res_bn = pair ? 32 : BN;
   if (k->x_last[d] != x || k->x_nb[d] != nb || k->x_bn[d] != BN) {   // per-call descriptor: X' = [nb][N1][K1] (host-side encode, ~1 us)
     const uint64_t dims[3] = {(uint64_t)K1, (uint64_t)N1, (uint64_t)nb};
     const uint64_t str[2] = {(uint64_t)K1 * 2, (uint64_t)K1 * N1 * 2};
@@ -870,21 +929,22 @@ extern "C" int b2o_kron_apply(b2o_kron *k, int trans, void *res, int res_dtype, 
     k->x_nb[d] = nb;
     k->x_bn[d] = BN;
   }
-  if (a.store_tma && (k->res_last[d] != res || k->res_nb[d] != nb || k->res_bn[d] != BN || k->res_bm[d] != BM || k->res_f32[d] != a.out_f32)) {
+  if (a.store_tma && (k->res_last[d] != res || k->res_nb[d] != nb || k->res_bn[d] != res_bn || k->res_bm[d] != BM || k->res_f32[d] != a.out_f32)) {
     // res = [nb][N2 (j)][M (i)] with i contiguous; box = BM i x BN j
     const uint64_t es = a.out_f32 ? 4 : 2;
     const uint64_t dims[3] = {(uint64_t)M, (uint64_t)N2, (uint64_t)nb};
     const uint64_t str[2] = {(uint64_t)M * es, (uint64_t)M * N2 * es};
-    const uint32_t box[3] = {(uint32_t)BM, (uint32_t)BN, 1};
+    const uint32_t box[3] = {(uint32_t)BM, (uint32_t)res_bn, 1};
     B2O_TRY(make_tmap(&k->tmRes[d], a.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, res, dims, str, box,
                       CU_TENSOR_MAP_SWIZZLE_NONE));
     k->res_last[d] = res;
     k->res_nb[d] = nb;
-    k->res_bn[d] = BN;
+    k->res_bn[d] = res_bn;
     k->res_bm[d] = BM;
     k->res_f32[d] = a.out_f32;
   }
   if (!a.store_tma && k->res_last[d] == nullptr) k->tmRes[d] = k->tmX[d];   // never dereferenced, but must be a valid descriptor
+  if (pair) return kron_pair_launch(c, k->tmA1[d][0], k->tmX[d], k->tmYld[d][0], k->tmB2[d][0], k->tmYhi[d][0][2], k->tmYlo[d][0][2], k->tmRes[d], a);
   const int maxc = 1 << 30;
 #define KR_GO(BMv, BNv)                                                                                                             \
   return kron_launch<BMv, BNv>(c, k->tmA1[d][mi], k->tmX[d], k->tmYld[d][mi], k->tmB2[d][w], k->tmYhi[d][mi][w], k->tmYlo[d][mi][w], \

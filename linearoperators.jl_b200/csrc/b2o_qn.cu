@@ -19,6 +19,8 @@ struct b2o_qn_s {
   double *S = nullptr, *Y = nullptr, *A = nullptr, *B = nullptr;  // [mem][pitch], zero padded
   double *q = nullptr, *tmp = nullptr;                            // [pitch]
   double *shifted_p = nullptr;                                    // [2*mem][pitch] work matrix of solve_shifted_system! (lazy)
+  double *q_multi = nullptr;                                      // [q_multi_cols][pitch] work vectors of the block two-loop recursion (lazy)
+  int q_multi_cols = 0;
   double *d_alpha = nullptr;                                      // [mem] device copy of data.α (inverse)
   std::vector<double> ys, aux;  // aux: inverse L-BFGS α (host mirror, lazily), forward norm_b, L-SR1 as
   int ins0 = 0;
@@ -248,6 +250,7 @@ extern "C" int b2o_qn_destroy(b2o_qn *q) {
   cudaFree(q->tmp);
   cudaFree(q->d_alpha);
   if (q->shifted_p) cudaFree(q->shifted_p);
+  if (q->q_multi) cudaFree(q->q_multi);
   if (q->d_W) cudaFree(q->d_W);
   if (q->h_W) cudaFreeHost(q->h_W);
   delete q;
@@ -758,6 +761,76 @@ static int multi_launch(b2o_qn *q, const CompactArgs &base, double *res, int64_t
   return st;
 }
 
+// ------------------------------------------------------------------ block two-loop recursion (matrix right-hand sides of H)
+template <int NR>
+static int twoloop_multi_launch(b2o_qn *q, double *res, int64_t ldr, const double *x, int64_t ldx, int nrhs, double alpha, double beta) {
+  b2o_ctx *c = q->ctx;
+  int o2n[B2O_MAX_MEM];
+  const int na = active_old_to_new(q, o2n);
+  if (q->q_multi_cols < NR) {     // work vectors q_r, allocated on the first block apply and kept
+    if (q->q_multi) B2O_CUDA(cudaFree(q->q_multi));
+    q->q_multi = nullptr;
+    q->q_multi_cols = 0;
+    cudaError_t e = cudaMalloc(&q->q_multi, sizeof(double) * (size_t)NR * (size_t)q->pitch);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      B2O_FAIL(B2O_ENOMEM, "block two-loop: cudaMalloc of %d work vectors failed: %s", NR, cudaGetErrorString(e));
+    }
+    B2O_CUDA(cudaMemsetAsync(q->q_multi, 0, sizeof(double) * (size_t)NR * (size_t)q->pitch, c->stream));
+    q->q_multi_cols = NR;
+  }
+  TwoLoopMultiArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int i = 0; i < na; ++i) {   // newest -> oldest (src/lbfgs.jl:130-131)
+    const int k = o2n[na - 1 - i];
+    a.s[i] = q->col(q->S, k);
+    a.y[i] = q->col(q->Y, k);
+    a.ys[i] = q->ys[k];
+  }
+  a.nact = na;
+  a.x = x;
+  a.res = res;
+  a.ldx = ldx;
+  a.ldr = ldr;
+  a.nrhs = nrhs;
+  a.q = q->q_multi;
+  a.qpitch = q->pitch;
+  a.n = q->n;
+  LaunchCfg cfg;
+  cfg.R = c->tile_rows;
+  a.ntiles = (q->n + cfg.R - 1) / cfg.R;
+  B2O_TRY(plan_launch(c, a.ntiles, 0, false, &cfg));
+  // ring | alphas [B2O_MAX_MEM][NR], warp partials [8][NR], dots [NR] | barriers
+  const size_t scal = (size_t)(B2O_MAX_MEM + B2O_CONS_WARPS + 1) * NR * sizeof(double);
+  int stages = cfg.stages;
+  while (stages > 2 && (size_t)stages * cfg.R * sizeof(double) + scal + 2 * stages * sizeof(uint64_t) > B2O_MAX_DYN_SMEM) --stages;
+  cfg.stages = stages;
+  cfg.L.accs_off = (size_t)stages * cfg.R * sizeof(double);
+  cfg.L.bar_off = cfg.L.accs_off + scal;
+  cfg.L.total = cfg.L.bar_off + (size_t)2 * stages * sizeof(uint64_t);
+  a.stages = stages;
+  a.scal_off = (uint32_t)cfg.L.accs_off;
+  a.bar_off = (uint32_t)cfg.L.bar_off;
+  a.alpha = alpha;
+  a.beta = beta;
+  a.gamma = q->gamma;
+  a.scaling = q->scaling ? 1 : 0;
+  a.x_al16 = ((uintptr_t)x % 16) == 0 && (nrhs == 1 || ldx % 2 == 0);
+  a.res_al16 = ((uintptr_t)res % 16) == 0 && (nrhs == 1 || ldr % 2 == 0);
+  a.partials = c->d_partials;
+  a.bar = c->d_bar;
+  a.bar_target = c->bar_base + (unsigned long long)cfg.grid;
+  int st;
+  switch (cfg.R) {
+    case 1024: st = launch_persistent(c, qn_twoloop_multi_kernel<1024, NR>, cfg, a, true); break;
+    case 2048: st = launch_persistent(c, qn_twoloop_multi_kernel<2048, NR>, cfg, a, true); break;
+    case 4096: st = launch_persistent(c, qn_twoloop_multi_kernel<4096, NR>, cfg, a, true); break;
+    default: B2O_FAIL(B2O_EARG, "bad tile_rows");
+  }
+  if (st == B2O_OK) c->bar_base += (unsigned long long)cfg.grid * (unsigned long long)(2 * na);
+  return st;
+}
+
 // mul!(Res, op, X, α, β) with n x nrhs column-major matrices (leading dimensions ldr, ldx)
 extern "C" int b2o_qn_apply_multi(b2o_qn *q, void *res_, int64_t ldr, const void *x_, int64_t ldx, int64_t len, int nrhs,
                                   double alpha, double beta) {
@@ -780,8 +853,22 @@ extern "C" int b2o_qn_apply_multi(b2o_qn *q, void *res_, int64_t ldr, const void
     if (q->kind == 0 && q->inverse && q->w_dirty) B2O_TRY(build_inverse_W(q));
     compact_columns(q, base, alpha, beta);
   }
+  if (twoloop && nrhs > 1 && c->nranks <= 1 && c->twoloop_block) {
+    int o2n[B2O_MAX_MEM];
+    if (active_old_to_new(q, o2n) > 0) {
+      // block two-loop recursion: the update / dot columns of a sweep are staged once for up to 8 right-hand sides
+      for (int r0 = 0; r0 < nrhs;) {
+        const int left = nrhs - r0, k = std::min(left, left > 4 ? 8 : 4);
+        if (left == 1) B2O_TRY(qn_apply_dev(q, res + (int64_t)r0 * ldr, x + (int64_t)r0 * ldx, alpha, beta));
+        else if (k > 4) B2O_TRY(twoloop_multi_launch<8>(q, res + (int64_t)r0 * ldr, ldr, x + (int64_t)r0 * ldx, ldx, k, alpha, beta));
+        else B2O_TRY(twoloop_multi_launch<4>(q, res + (int64_t)r0 * ldr, ldr, x + (int64_t)r0 * ldx, ldx, k, alpha, beta));
+        r0 += k;
+      }
+      return B2O_OK;
+    }
+  }
   if (nrhs == 1 || twoloop || split_ranks || base.ncols == 0 || base.ncols * 4 > B2O_MULTI_MAXV) {
-    // the two-loop recursion is a chain of dependent sweeps and NCCL mode splits the launch: column by column
+    // row-partitioned two-loop handles (dependent all-reduces) and NCCL mode (split launches): column by column
     for (int r = 0; r < nrhs; ++r) B2O_TRY(qn_apply_dev(q, res + (int64_t)r * ldr, x + (int64_t)r * ldx, alpha, beta));
     return B2O_OK;
   }

@@ -423,3 +423,222 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_multi_kernel(const __grid_
     }
   }
 }
+
+// =====================================================================================================
+// Block two-loop recursion: mul!(Res::Matrix, H, X::Matrix, α, β) for the two-loop InverseLBFGSOperator
+// (src/operations.jl:34-36 hands the matrices to the closure; per column this is src/lbfgs.jl:117-154).
+//
+// Same 2A+1 fused sweeps as qn_twoloop_kernel, for NR right-hand sides at once: the update column v1 (y_k or s_k) and the
+// column of the next inner product v2 are staged ONCE per sweep and used for all NR work vectors q_r while they sit in
+// registers.  Algorithmic DRAM bytes per sweep (2·nrhs + 2)·8·n instead of nrhs·4·8·n (q_r must still make its round trip:
+// n doubles do not fit on chip).  Every elementwise statement and every reduction order is that of the vector kernel
+// (per-thread s0/s1 pairs -> warp butterfly -> warps in order -> CTAs in lane-strided order), so column r of the result is
+// BIT-IDENTICAL to the vector kernel applied to column r with the same tile size and grid (tests check ==).
+// =====================================================================================================
+struct TwoLoopMultiArgs {
+  const double *s[B2O_MAX_MEM];  // active slots, newest -> oldest
+  const double *y[B2O_MAX_MEM];
+  double ys[B2O_MAX_MEM];
+  int nact;
+  const double *x;               // column-major n x nrhs
+  double *res;
+  int64_t ldx, ldr;
+  int nrhs;                      // <= NR
+  double *q;                     // library-owned work vectors [NR][qpitch], zero padded
+  int64_t qpitch;
+  int64_t n, ntiles;
+  double alpha, beta, gamma;
+  int scaling;
+  int x_al16, res_al16;
+  double *partials;              // [grid][NR]
+  unsigned long long *bar;
+  unsigned long long bar_target;
+  int stages;
+  uint32_t scal_off, bar_off;    // scal: alphas [B2O_MAX_MEM][NR] | sred [8][NR] | s_dot [NR]
+};
+
+template <int R, int NR>
+__global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_multi_kernel(const __grid_constant__ TwoLoopMultiArgs p) {
+  constexpr int EPT = R / B2O_NCONS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Ring rg;
+  rg.buf = reinterpret_cast<double *>(smem_raw);
+  double *alphas = reinterpret_cast<double *>(smem_raw + p.scal_off);   // [B2O_MAX_MEM][NR]
+  double *sred = alphas + B2O_MAX_MEM * NR;                             // [8 warps][NR]
+  double *s_dot = sred + B2O_CONS_WARPS * NR;                           // [NR]
+  rg.full = reinterpret_cast<uint64_t *>(smem_raw + p.bar_off);
+  rg.empty = rg.full + p.stages;
+  rg.stages = p.stages;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool is_producer = warp == B2O_CONS_WARPS;
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&rg.full[s], 1);
+      mbar_init(&rg.empty[s], B2O_CONS_WARPS);
+    }
+    mbar_fence_init();
+  }
+  if (tid < NR) s_dot[tid] = 0.0;
+  __syncthreads();
+
+  RingPos pos(p.stages);
+  const int A = p.nact, nrhs = p.nrhs;
+  const int64_t grid = gridDim.x;
+  const int64_t my_tiles = (p.ntiles > (int64_t)blockIdx.x) ? (p.ntiles - 1 - blockIdx.x) / grid + 1 : 0;
+  unsigned long long bar_target = p.bar_target;
+
+  for (int w = 0; w <= 2 * A; ++w) {
+    // sweep w, as in qn_twoloop_kernel; c1[r] is the step's coefficient for right-hand side r
+    const bool dot_only = (w == 0);
+    const bool loop1 = (w >= 1 && w <= A);
+    const bool last = (w == 2 * A);
+    const double *v1 = nullptr, *v2 = nullptr;
+    double c1[NR];
+    bool qin_is_x = false, apply_gamma = false;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) c1[r] = 0.0;
+    if (dot_only) {
+      v2 = p.s[0];
+      qin_is_x = true;
+    } else if (loop1) {
+      const int i = w;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) c1[r] = s_dot[r] / p.ys[i - 1];                        // αk = dot(s[k], q) / ys[k]      :133
+      if (tid < NR) alphas[(i - 1) * NR + tid] = s_dot[tid] / p.ys[i - 1];
+      v1 = p.y[i - 1];
+      qin_is_x = (i == 1);
+      apply_gamma = (i == A) && p.scaling;
+      v2 = (i < A) ? p.s[i] : p.y[A - 1];
+    } else {
+      const int i = w - A, o = A - i;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) c1[r] = alphas[o * NR + r] - s_dot[r] / p.ys[o];       // β = αk - dot(y[k], q) / ys[k]  :144-145
+      v1 = p.s[o];
+      v2 = last ? nullptr : p.y[o - 1];
+    }
+    __syncthreads();
+
+    if (is_producer) {
+      if (lane == 0) {
+        fence_proxy_async();
+        for (int64_t i = 0; i < my_tiles; ++i) {
+          const int64_t t = blockIdx.x + i * grid;
+          if (v1) producer_push<R>(rg, pos, v1 + t * R);
+          if (v2) producer_push<R>(rg, pos, v2 + t * R);
+          if (!qin_is_x)
+            for (int r = 0; r < nrhs; ++r) producer_push<R>(rg, pos, p.q + (int64_t)r * p.qpitch + t * R);
+        }
+      }
+      __syncwarp();
+    } else {
+      double acc[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) acc[r] = 0.0;
+      for (int64_t i = 0; i < my_tiles; ++i) {
+        const int64_t t = blockIdx.x + i * grid;
+        double a1[EPT], a2[EPT];
+        uint32_t slot1 = 0xffffffffu, slot2 = 0xffffffffu;
+        if (v1) {
+          mbar_wait(&rg.full[pos.slot], pos.par);
+          const double2 *V = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R);
+#pragma unroll
+          for (int j = 0; j < EPT / 2; ++j) {
+            double2 v = V[j * B2O_NCONS + tid];
+            a1[2 * j] = v.x;
+            a1[2 * j + 1] = v.y;
+          }
+          slot1 = pos.slot;
+          pos.advance();
+        }
+        if (v2) {
+          mbar_wait(&rg.full[pos.slot], pos.par);
+          const double2 *V = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R);
+#pragma unroll
+          for (int j = 0; j < EPT / 2; ++j) {
+            double2 v = V[j * B2O_NCONS + tid];
+            a2[2 * j] = v.x;
+            a2[2 * j + 1] = v.y;
+          }
+          slot2 = pos.slot;
+          pos.advance();
+        }
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          if (r >= nrhs) continue;
+          double q[EPT], rold[EPT];
+          uint32_t q_slot = 0xffffffffu;
+          if (qin_is_x) {
+            load_user_tile<R>(p.x + (int64_t)r * p.ldx, t * R, p.n, p.x_al16, q);          // q .= x   :127-128
+          } else {
+            mbar_wait(&rg.full[pos.slot], pos.par);
+            const double2 *Q = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R);
+#pragma unroll
+            for (int j = 0; j < EPT / 2; ++j) {
+              double2 v = Q[j * B2O_NCONS + tid];
+              q[2 * j] = v.x;
+              q[2 * j + 1] = v.y;
+            }
+            q_slot = pos.slot;
+            pos.advance();
+          }
+          if (last && p.beta != 0.0) load_user_tile<R>(p.res + (int64_t)r * p.ldr, t * R, p.n, p.res_al16, rold);
+          if (v1) {
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) q[j] = loop1 ? q[j] - c1[r] * a1[j] : q[j] + c1[r] * a1[j];   // :135 / :146
+            // slots go back only after arithmetic has consumed the registers loaded from them (see qn_twoloop_kernel)
+            if (q_slot != 0xffffffffu) consumer_release(rg, q_slot);
+            if (apply_gamma) {
+#pragma unroll
+              for (int j = 0; j < EPT; ++j) q[j] = q[j] * p.gamma;                          // q .*= γ            :139
+            }
+            if (last) {
+#pragma unroll
+              for (int j = 0; j < EPT; ++j) q[j] = (p.beta != 0.0) ? p.alpha * q[j] + p.beta * rold[j] : p.alpha * q[j];   // :149-153
+              store_user_tile<R>(p.res + (int64_t)r * p.ldr, t * R, p.n, p.res_al16, q);
+            } else {
+              double2 *Qg = reinterpret_cast<double2 *>(p.q + (int64_t)r * p.qpitch + t * R);
+#pragma unroll
+              for (int j = 0; j < EPT / 2; ++j) Qg[j * B2O_NCONS + tid] = make_double2(q[2 * j], q[2 * j + 1]);
+            }
+          }
+          if (v2) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < EPT / 2; ++j) {
+              s0 = fma(a2[2 * j], q[2 * j], s0);
+              s1 = fma(a2[2 * j + 1], q[2 * j + 1], s1);
+            }
+            acc[r] += s0 + s1;
+          }
+        }
+        if (slot1 != 0xffffffffu) consumer_release(rg, slot1);
+        if (slot2 != 0xffffffffu) consumer_release(rg, slot2);
+      }
+      if (v2) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const double s = warp_sum(acc[r]);
+          if (lane == 0) sred[warp * NR + r] = s;
+        }
+      }
+      fence_proxy_async();  // our generic-proxy stores to q precede the next sweep's TMA reads of q
+    }
+    if (!v2) break;  // the last sweep wrote Res
+    __syncthreads();
+    if (tid < NR) {
+      double s = 0.0;
+      for (int wv = 0; wv < B2O_CONS_WARPS; ++wv) s += sred[wv * NR + tid];
+      p.partials[(size_t)blockIdx.x * NR + tid] = s;
+    }
+    grid_barrier(p.bar, bar_target);
+    bar_target += gridDim.x;
+    if (warp < NR) {
+      double s = 0.0;
+      for (int b = lane; b < (int)grid; b += 32) s += __ldcg(&p.partials[(size_t)b * NR + warp]);
+      s = warp_sum(s);
+      if (lane == 0) s_dot[warp] = s;
+    }
+    __syncthreads();
+  }
+}

@@ -909,6 +909,47 @@ def test_kron_batch_and_launch_count(lo, ctx, orc):
         lo.kron(A[:, :-1].contiguous(), B, ctx=ctx)                                  # dims must be multiples of 8
 
 
+@pytest.mark.parametrize("dims,nb", [((512, 512, 512, 512), 3), ((264, 200, 392, 328), 2), ((128, 64, 256, 192), 1), ((320, 520, 264, 136), 2)])
+def test_kron_pair_kernel_vs_oracle(lo, ctx, orc, dims, nb):
+    """The cta_group::2 pair kernel (256-row units, 256-column pair tiles; picked automatically for many right-hand sides, forced
+    here with tile_m = 256) against the Float64 oracle: full tiles, ragged rows / columns / K (zero-filled boxes, clipped
+    stores), a half of the pair tile that lies entirely outside the matrix, both directions, both result types, beta != 0."""
+    import torch
+    m, n, p, q = dims
+    (A, B), (An, Bn) = _bf16_mats(ctx, orc, [(m, n), (p, q)], [31, 32])
+    dev_ = "cuda:%d" % ctx.device
+    Xn = orc.bf16_round(orc.uniform(nb * n * q, 33, -1.0, 1.0)).reshape(nb, n * q)
+    Xtn = orc.bf16_round(orc.uniform(nb * m * p, 34, -1.0, 1.0)).reshape(nb, m * p)
+    R0n = orc.bf16_round(orc.uniform(nb * m * p, 35, -1.0, 1.0)).reshape(nb, m * p)
+    X = torch.as_tensor(Xn).to(dev_).to(torch.bfloat16).contiguous()
+    Xt = torch.as_tensor(Xtn).to(dev_).to(torch.bfloat16).contiguous()
+    K = lo.kron(A, B, max_batch=4, ctx=ctx)
+    Kref = lo.kron(A, B, max_batch=4, ctx=ctx)               # the single-CTA kernel on the same inputs
+    K.set_option("tile_m", 256)
+    l0 = ctx.launch_count()
+    R32 = K.apply_batch(X, res=torch.empty((nb, m * p), dtype=torch.float32, device=dev_))
+    assert ctx.launch_count() - l0 == 1
+    T32 = K.apply_batch(Xt, res=torch.empty((nb, n * q), dtype=torch.float32, device=dev_), trans=True)
+    R16 = K.apply_batch(X)
+    O32 = torch.as_tensor(R0n, dtype=torch.float32).to(dev_)
+    K.apply_batch(X, alpha=2.0, beta=-0.5, res=O32)
+    O16 = torch.as_tensor(R0n).to(dev_).to(torch.bfloat16).contiguous()
+    K.apply_batch(X, alpha=2.0, beta=-0.5, res=O16)
+    S32 = Kref.apply_batch(X, res=torch.empty((nb, m * p), dtype=torch.float32, device=dev_))
+    for b in range(nb):
+        ref, reft, ref5 = np.empty(m * p), np.empty(n * q), R0n[b].copy()
+        orc.kron_(ref, An, Bn, Xn[b])
+        orc.kron_(reft, An, Bn, Xtn[b], trans=1)
+        orc.kron_(ref5, An, Bn, Xn[b], alpha=2.0, beta=-0.5)
+        assert rel(R32[b].double().cpu().numpy(), ref) <= 1e-5, (b, rel(R32[b].double().cpu().numpy(), ref))
+        assert rel(T32[b].double().cpu().numpy(), reft) <= 1e-5, (b, rel(T32[b].double().cpu().numpy(), reft))
+        assert rel(R16[b].double().cpu().numpy(), orc.bf16_round(ref)) <= 1e-3
+        assert rel(O32[b].double().cpu().numpy(), ref5) <= 1e-5
+        assert rel(O16[b].double().cpu().numpy(), orc.bf16_round(ref5)) <= 1e-3
+        # same arithmetic as the single-CTA kernel (fp32 accumulation over k in the same order, hi + lo in the same accumulator)
+        assert rel(R32[b].double().cpu().numpy(), S32[b].double().cpu().numpy()) <= 1e-6
+
+
 def test_kron_of_general_operators_on_gpu(lo, ctx, orc):
     """kron(A, B) for operators that are not bf16 matrices (src/kron.jl:10-49, test/test_kron.jl:3-58): Float64 dense matrices,
     a dense x diagonal pair, a dense x L-BFGS pair -- composed from the operators' own matrix-right-hand-side applies, every

@@ -36,7 +36,7 @@ An, Bn, xn = mk_np(11, (m, m)), mk_np(12, (m, m)), mk_np(13, (m * m,))
 A, B, x = to_dev(An), to_dev(Bn), to_dev(xn)
 ref = np.empty(m * m)
 orc.kron_(ref, An, Bn, xn)
-K = lo.kron(A, B, max_batch=64, ctx=ctx)
+K = lo.kron(A, B, max_batch=148, ctx=ctx)
 res = torch.empty(m * m, dtype=torch.bfloat16, device="cuda")
 r32 = torch.empty(m * m, dtype=torch.float32, device="cuda")
 fl = K.flops()
@@ -132,7 +132,7 @@ for b in (0, 31, 63):
     rb = np.empty(m * m)
     orc.kron_(rb, An, Bn, Xn[b])
     refs[b] = orc.bf16_round(rb)
-for bm, bn, cluster in [(0, 0, 0)] + ([] if quick else [(128, 128, 2), (128, 128, 4), (128, 128, 1), (128, 64, 4), (64, 128, 4), (128, 64, 8)]):
+for bm, bn, cluster in [(0, 0, 0), (256, 0, 0), (128, 128, 2)] + ([] if quick else [(128, 128, 4), (128, 128, 1), (128, 64, 4), (64, 128, 4), (128, 64, 8)]):
     try:
         K.set_option("cluster", cluster)
         K.set_option("tile_n", bn)
@@ -147,6 +147,24 @@ for bm, bn, cluster in [(0, 0, 0)] + ([] if quick else [(128, 128, 2), (128, 128
                           "frac_of_measured_bf16_burst": round(f / (ms * 1e-3) / 1e12 / PEAK, 4)}), flush=True)
     except Exception as e:
         print(json.dumps({"batch": 64, "tile_m": bm, "tile_n": bn, "cluster": cluster, "error": str(e)[:300]}), flush=True)
+K.set_option("tile_m", 0)
+K.set_option("cluster", 0)
+K.set_option("tile_n", 0)
+# ---- how the two kernels scale with the number of right-hand sides (pair kernel: 256-row units on 74 CTA pairs)
+for nbv in (8, 16, 32, 37, 64, 74, 128, 148):
+    Xv = to_dev(mk_np(15, (nbv, m * m)))
+    Rv = torch.empty((nbv, m * m), dtype=torch.bfloat16, device="cuda")
+    row = {"case": "EXTRA: right-hand-side sweep", "nb": nbv}
+    for name, bm in (("pair_256", 256), ("single_cta_128", 128)):
+        try:
+            K.set_option("tile_m", bm)
+            K.set_option("tile_n", 128 if bm == 128 else 0)
+            K.set_option("cluster", 2 if bm == 128 else 0)
+            ms = timed(lambda: K.apply_batch(Xv, res=Rv), 30, warmup=5)
+            row[name] = {"us": round(ms * 1e3, 2), "TFLOPs_algorithmic": round(K.flops(nbv) / (ms * 1e-3) / 1e12, 1)}
+        except Exception as e:
+            row[name] = {"error": str(e)[:200]}
+    print(json.dumps(row), flush=True)
 K.set_option("tile_m", 0)
 K.set_option("cluster", 0)
 K.set_option("tile_n", 0)
