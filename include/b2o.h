@@ -68,6 +68,7 @@ int b2o_ctx_sync(b2o_ctx *ctx);
  * matrix leaves: "dense_scalar" (force the unvectorised dense kernels), "sparse_kernel" (0|3 pipelined rows -- default,
  * 1 plain rows, 2 TMA-staged tiles), "sparse_lanes" (-1 auto | 0..5: 2^k lanes per row);
  * index sets: "extend_form" (0 gather form through the inverse map when the set is dense enough, 1 always memset + scatter);
+ * matrix right-hand sides of the two-loop inverse: "twoloop_block" (1 block recursion, 4 / 8 columns per sweep -- default; 0 column loop);
  * memory system: "l2_fetch_granularity" (32|64|128: cudaLimitMaxL2FetchGranularity, device-wide);
  * multi-GPU: "use_mailbox" (0|1: NCCL or the in-kernel NVLink mailbox for the inner products of a connected context -- every
  * rank switches at the same point), "numa_local_host" (0|1: b2o_host_alloc prefers the GPU's NUMA node, default 1).

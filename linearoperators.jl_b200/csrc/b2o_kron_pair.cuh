@@ -110,6 +110,7 @@ kron_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   const uint32_t crank = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);
   const int cid = __shfl_sync(0xffffffffu, (int)cluster_id_x(), 0), ncl = __shfl_sync(0xffffffffu, (int)nclusters_x(), 0);
   const bool leader = crank == 0;
+  if (threadIdx.x == 0 && p.dbg && blockIdx.x == 0) p.dbg[0] = gtimer();
   if (threadIdx.x == 32) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
@@ -224,6 +225,7 @@ kron_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
             const uint32_t tmem_acc = tmem_base + acc * KP_TCOLS;
             kp_wait(&tmem_empty[acc], tpar ^ 1u);       // both CTAs' epilogues have drained this accumulator
             tc_fence_after();
+            if (p.dbg && blockIdx.x == 0 && lane == 0 && tcount < 8) p.dbg[16 + 2 * tcount] = gtimer();
             for (int ks = 0; ks < ksteps; ++ks) {
               const uint32_t s0 = slot, p0 = sphase;
               KP_ADVANCE(1);
@@ -261,6 +263,7 @@ kron_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
               }
               __syncwarp();
             }
+            if (p.dbg && blockIdx.x == 0 && lane == 0 && tcount < 8) p.dbg[17 + 2 * tcount] = gtimer();
             ++tcount;
           }
         }
@@ -278,6 +281,7 @@ kron_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           const uint32_t tmem_acc = tmem_base + acc * KP_TCOLS;
           kp_wait(&tmem_full[acc], tpar);
           tc_fence_after();
+          if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 8) p.dbg[48 + 2 * tcount] = gtimer();
 #pragma unroll 1
           for (int c0 = 0; c0 < KP_TN; c0 += 32) {
             const int col0 = t * KP_TN + c0;
@@ -318,6 +322,7 @@ kron_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           tc_fence_before();
           __syncwarp();
           if (lane == 0) kp_arrive_cl(te_leader + acc * 8u);
+          if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 8) p.dbg[49 + 2 * tcount] = gtimer();
           ++tcount;
         }
         if (issuer) {
@@ -333,6 +338,7 @@ kron_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           const uint32_t tmem_acc = tmem_base + acc * KP_TCOLS;
           kp_wait(&tmem_full[acc], tpar);
           tc_fence_after();
+          if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 8) p.dbg[48 + 2 * tcount] = gtimer();
 #pragma unroll 1
           for (int c0 = 0; c0 < KP_TN; c0 += 32) {
             const int n0 = t * KP_TN + c0;
@@ -375,6 +381,7 @@ kron_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           tc_fence_before();
           __syncwarp();
           if (lane == 0) kp_arrive_cl(te_leader + acc * 8u);
+          if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 8) p.dbg[49 + 2 * tcount] = gtimer();
           ++tcount;
         }
       }
@@ -384,6 +391,7 @@ kron_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                               // the leader's MMAs into the peer's TMEM / arrives on the peer are all done
+  if (threadIdx.x == 0 && p.dbg && blockIdx.x == 0) p.dbg[10] = gtimer();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * KP_TCOLS) : "memory");
 }
 #undef KP_ADVANCE

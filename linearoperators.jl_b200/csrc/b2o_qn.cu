@@ -803,11 +803,13 @@ static int twoloop_multi_launch(b2o_qn *q, double *res, int64_t ldr, const doubl
   // ring | alphas [B2O_MAX_MEM][NR], warp partials [8][NR], dots [NR] | barriers
   const size_t scal = (size_t)(B2O_MAX_MEM + B2O_CONS_WARPS + 1) * NR * sizeof(double);
   int stages = cfg.stages;
-  while (stages > 2 && (size_t)stages * cfg.R * sizeof(double) + scal + 2 * stages * sizeof(uint64_t) > B2O_MAX_DYN_SMEM) --stages;
+  const size_t landed = B2O_NCONS * sizeof(unsigned);
+  while (stages > 2 && (size_t)stages * cfg.R * sizeof(double) + scal + landed + 2 * stages * sizeof(uint64_t) > B2O_MAX_DYN_SMEM) --stages;
   cfg.stages = stages;
   cfg.L.accs_off = (size_t)stages * cfg.R * sizeof(double);
   cfg.L.bar_off = cfg.L.accs_off + scal;
-  cfg.L.total = cfg.L.bar_off + (size_t)2 * stages * sizeof(uint64_t);
+  a.landed_off = (uint32_t)(cfg.L.bar_off + (size_t)2 * stages * sizeof(uint64_t));
+  cfg.L.total = a.landed_off + landed;
   a.stages = stages;
   a.scal_off = (uint32_t)cfg.L.accs_off;
   a.bar_off = (uint32_t)cfg.L.bar_off;

@@ -19,12 +19,13 @@ enum { OP_LBFGS_FWD = 0, OP_LSR1 = 1, OP_INV_COMPACT = 2, OP_PUSH_A = 3, OP_PUSH
 // takes as_k = a_k·s_k and ‖a_k‖² on the way out (partials[grid*ncols + 2*cta + {0,1}]).
 enum { MODE_FUSED = 0, MODE_PHASE1 = 1, MODE_PHASE2 = 2 };
 
-struct CompactArgs {
-  const double *cols[B2O_MAX_COLS];  // active columns in reference order (LBFGS: a_k,b_k pairs oldest->newest)
+template <typename T>
+struct CompactArgsT {
+  const T *cols[B2O_MAX_COLS];       // active columns in reference order (LBFGS: a_k,b_k pairs oldest->newest)
   double cdiv[B2O_MAX_COLS];         // LSR1: as[k]
   int ncols;
-  const double *x;
-  double *res;
+  const T *x;
+  T *res;
   int64_t n, ntiles;
   double alpha, beta, gamma;
   int scaling;
@@ -38,18 +39,22 @@ struct CompactArgs {
   int accumulate;                    // split mode: dots[c] += this launch's partial (row-chunked host pipeline)
   uint32_t accs_off, coef_off, bar_off;
   MboxDev mbox;                      // nranks > 1: the dots are all-reduced in-kernel through the NVLink peer mailbox
-  const double *y2;                  // OP_PUSH_L: y_k (library-owned column)
+  const T *y2;                       // OP_PUSH_L: y_k (library-owned column)
   const double *W;                   // OP_INV_COMPACT: ncols x ncols middle matrix (row-major), coefficients = W * dots
   int base_div;                      // OP_INV_COMPACT: base term x/γ (compact FORWARD form) instead of γx (compact inverse)
   double *dbg;                       // [0] += ns CTA 0 waited for the local CTAs, [1] += ns in the mailbox exchange, [2] += epochs
 };
+using CompactArgs = CompactArgsT<double>;
 
-template <int R, int OP>
-__global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __grid_constant__ CompactArgs p) {
+// T = double: the reference's Float64 operators.  T = float: LBFGSOperator(Float32, n) etc. (test/test_lbfgs.jl:162-178) --
+// columns, x and res are Float32, every elementwise statement runs in Float32, every inner product is accumulated in double
+// and rounded to Float32 where the reference's `dot` returns one (the coefficient casts below are no-ops for T = double).
+template <int R, int OP, typename T = double>
+__global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __grid_constant__ CompactArgsT<T> p) {
   constexpr int EPT = R / B2O_NCONS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Ring rg;
-  rg.buf = reinterpret_cast<double *>(smem_raw);
+  rg.buf = smem_raw;
   double *accs = reinterpret_cast<double *>(smem_raw + p.accs_off);
   double *coef = reinterpret_cast<double *>(smem_raw + p.coef_off);
   rg.full = reinterpret_cast<uint64_t *>(smem_raw + p.bar_off);
@@ -87,7 +92,7 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
         __syncwarp();
       } else {
         for (int c = 0; c < gc; ++c) accs[c * B2O_NCONS + tid] = 0.0;
-        double xr[EPT], xn[EPT];
+        T xr[EPT], xn[EPT];
         if (my_tiles > 0) load_user_tile<R>(p.x, (int64_t)blockIdx.x * R, p.n, p.x_al16, xn);
         for (int64_t i = 0; i < my_tiles; ++i) {
           const int64_t t = blockIdx.x + i * grid;
@@ -96,15 +101,9 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
           if (i + 1 < my_tiles) load_user_tile<R>(p.x, (t + grid) * R, p.n, p.x_al16, xn);
           for (int c = 0; c < gc; ++c) {
             mbar_wait(&rg.full[pos.slot], pos.par);
-            const double2 *b = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R);
-            double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-            for (int j = 0; j < EPT / 2; ++j) {
-              double2 v = b[j * B2O_NCONS + tid];
-              s0 = fma(v.x, xr[2 * j], s0);
-              s1 = fma(v.y, xr[2 * j + 1], s1);
-            }
-            accs[c * B2O_NCONS + tid] += s0 + s1;
+            T b[EPT];
+            tile_from_ring<R>(rg, pos.slot, b);
+            accs[c * B2O_NCONS + tid] += tile_dot<EPT>(b, xr);
             consumer_release(rg, pos.slot);
             pos.advance();
           }
@@ -239,14 +238,14 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
     }
     __syncwarp();
   } else {
-    const double alpha = p.alpha, beta = p.beta, gamma = p.gamma;
-    double xn[EPT], q[EPT], rold[EPT];
-    double xc[(OP == OP_PUSH_A || OP == OP_PUSH_L) ? EPT : 1];
+    const T alpha = (T)p.alpha, beta = (T)p.beta, gamma = (T)p.gamma;
+    T xn[EPT], q[EPT], rold[EPT];
+    T xc[(OP == OP_PUSH_A || OP == OP_PUSH_L) ? EPT : 1];
     double racc = 0.0, racc2 = 0.0;
     if (my_tiles > 0) load_user_tile<R>(p.x, (blockIdx.x + (my_tiles - 1) * grid) * R, p.n, p.x_al16, xn);
     for (int64_t i = my_tiles - 1; i >= 0; --i) {
       const int64_t t = blockIdx.x + i * grid;
-      if (beta != 0.0) load_user_tile<R>(p.res, t * R, p.n, p.res_al16, rold);
+      if (beta != (T)0) load_user_tile<R>(p.res, t * R, p.n, p.res_al16, rold);
       if (OP == OP_LBFGS_FWD) {
         // q .= x ; scaling && (q ./= γ)                                   src/lbfgs.jl:183-186
 #pragma unroll
@@ -274,8 +273,8 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
         // q .= α .* x ./ γ (.+ β .* q)                                    src/lsr1.jl:92-96
 #pragma unroll
         for (int j = 0; j < EPT; ++j) {
-          double v = (alpha * xn[j]) / gamma;
-          q[j] = (beta != 0.0) ? v + beta * rold[j] : v;
+          T v = (alpha * xn[j]) / gamma;
+          q[j] = (beta != (T)0) ? v + beta * rold[j] : v;
         }
       }
       if (i > 0) load_user_tile<R>(p.x, (t - grid) * R, p.n, p.x_al16, xn);
@@ -286,21 +285,19 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
           pos.advance();
           const uint32_t sb = pos.slot, pb = pos.par;
           pos.advance();
-          const double ax = coef[c], bx = coef[c + 1];
+          const T ax = (T)coef[c], bx = (T)coef[c + 1];
           mbar_wait(&rg.full[sa], pa);
           mbar_wait(&rg.full[sb], pb);
-          const double2 *A = reinterpret_cast<const double2 *>(rg.buf + (size_t)sa * R);
-          const double2 *B = reinterpret_cast<const double2 *>(rg.buf + (size_t)sb * R);
+          T a[EPT], b[EPT];
+          tile_from_ring<R>(rg, sa, a);
+          tile_from_ring<R>(rg, sb, b);
 #pragma unroll
-          for (int j = 0; j < EPT / 2; ++j) {
-            double2 a = A[j * B2O_NCONS + tid], b = B[j * B2O_NCONS + tid];
+          for (int j = 0; j < EPT; ++j) {
             if (OP == OP_PUSH_A) {
               // a[k] .+= dot(b[l], s[k]) .* b[l] ; a[k] .-= dot(a[l], s[k]) .* a[l]      src/lbfgs.jl:244-245
-              q[2 * j] = (q[2 * j] + bx * b.x) - ax * a.x;
-              q[2 * j + 1] = (q[2 * j + 1] + bx * b.y) - ax * a.y;
+              q[j] = (q[j] + bx * b[j]) - ax * a[j];
             } else {
-              q[2 * j] = q[2 * j] + (bx * b.x - ax * a.x);
-              q[2 * j + 1] = q[2 * j + 1] + (bx * b.y - ax * a.y);
+              q[j] = q[j] + (bx * b[j] - ax * a[j]);
             }
           }
           consumer_release(rg, sa);
@@ -308,42 +305,39 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
         }
         if (OP == OP_PUSH_A) {
 #pragma unroll
-          for (int j = 0; j < EPT; ++j) racc = fma(q[j], xc[j], racc);                           // dot(s[k], a[k])   :248
+          for (int j = 0; j < EPT; ++j) racc = fma((double)q[j], (double)xc[j], racc);           // dot(s[k], a[k])   :248
         } else {
 #pragma unroll
-          for (int j = 0; j < EPT; ++j) q[j] = (beta != 0.0) ? alpha * q[j] + beta * rold[j] : alpha * q[j];  // :197-201
+          for (int j = 0; j < EPT; ++j) q[j] = (beta != (T)0) ? alpha * q[j] + beta * rold[j] : alpha * q[j];  // :197-201
         }
       } else {
         for (int c = 0; c < ncols; ++c) {
           // LSR1: ax = α * dot(a[k], x) / as[k];  q[j] += ax * a[k][j]    src/lsr1.jl:101-104
           // compact inverse: q += c_j * col_j
           // push! of L-SR1: as = dot(a[l], s[k]) / as[l];  a[k] .-= as .* a[l]              src/lsr1.jl:173-174
-          const double ax = (OP == OP_INV_COMPACT) ? coef[c] : (OP == OP_PUSH_L) ? coef[c] / p.cdiv[c] : (alpha * coef[c]) / p.cdiv[c];
+          const T ax = (OP == OP_INV_COMPACT) ? (T)coef[c]
+                       : (OP == OP_PUSH_L)   ? (T)coef[c] / (T)p.cdiv[c]
+                                             : (alpha * (T)coef[c]) / (T)p.cdiv[c];
           mbar_wait(&rg.full[pos.slot], pos.par);
-          const double2 *A = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R);
+          T a[EPT];
+          tile_from_ring<R>(rg, pos.slot, a);
 #pragma unroll
-          for (int j = 0; j < EPT / 2; ++j) {
-            double2 a = A[j * B2O_NCONS + tid];
-            if (OP == OP_PUSH_L) {
-              q[2 * j] = q[2 * j] - ax * a.x;
-              q[2 * j + 1] = q[2 * j + 1] - ax * a.y;
-            } else {
-              q[2 * j] = q[2 * j] + ax * a.x;
-              q[2 * j + 1] = q[2 * j + 1] + ax * a.y;
-            }
+          for (int j = 0; j < EPT; ++j) {
+            if (OP == OP_PUSH_L) q[j] = q[j] - ax * a[j];
+            else q[j] = q[j] + ax * a[j];
           }
           consumer_release(rg, pos.slot);
           pos.advance();
         }
         if (OP == OP_INV_COMPACT) {
 #pragma unroll
-          for (int j = 0; j < EPT; ++j) q[j] = (beta != 0.0) ? alpha * q[j] + beta * rold[j] : alpha * q[j];
+          for (int j = 0; j < EPT; ++j) q[j] = (beta != (T)0) ? alpha * q[j] + beta * rold[j] : alpha * q[j];
         }
         if (OP == OP_PUSH_L) {
 #pragma unroll
           for (int j = 0; j < EPT; ++j) {
-            racc = fma(q[j], xc[j], racc);                                                        // as[k] = dot(a[k], s[k])   :177
-            racc2 = fma(q[j], q[j], racc2);                                                       // norm(a[k])^2              :179
+            racc = fma((double)q[j], (double)xc[j], racc);                                        // as[k] = dot(a[k], s[k])   :177
+            racc2 = fma((double)q[j], (double)q[j], racc2);                                       // norm(a[k])^2              :179
           }
         }
       }
@@ -372,14 +366,15 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __gri
 // =====================================================================================================
 constexpr int B2O_MAX_MEM = 64;
 
-struct TwoLoopArgs {
-  const double *s[B2O_MAX_MEM];  // active slots ordered newest -> oldest (loop-1 order)
-  const double *y[B2O_MAX_MEM];
+template <typename T>
+struct TwoLoopArgsT {
+  const T *s[B2O_MAX_MEM];       // active slots ordered newest -> oldest (loop-1 order)
+  const T *y[B2O_MAX_MEM];
   double ys[B2O_MAX_MEM];
   int nact;
-  const double *x;
-  double *res;
-  double *q;                     // library-owned work vector (data.Ax), padded pitch
+  const T *x;
+  T *res;
+  T *q;                          // library-owned work vector (data.Ax), padded pitch
   double *alpha_out;             // device copy of data.α in loop-1 order (may be null)
   int64_t n, ntiles;
   double alpha, beta, gamma;
@@ -397,15 +392,16 @@ struct TwoLoopArgs {
   double *sweep_dots;            // fused mode: the reduced inner product of sweep w is also left in sweep_dots[w] (parity tests)
   double *dbg;                   // [0] += ns CTA 0 waited for the local CTAs, [1] += ns in the mailbox exchange, [2] += epochs
 };
+using TwoLoopArgs = TwoLoopArgsT<double>;
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-template <int R>
-__global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_kernel(const __grid_constant__ TwoLoopArgs p) {
+template <int R, typename T = double>
+__global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_kernel(const __grid_constant__ TwoLoopArgsT<T> p) {
   constexpr int EPT = R / B2O_NCONS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Ring rg;
-  rg.buf = reinterpret_cast<double *>(smem_raw);
+  rg.buf = smem_raw;
   double *sred = reinterpret_cast<double *>(smem_raw + p.coef_off);  // [8] warp partials + [8..8+64) α_i
   double *alphas = sred + 8;
   rg.full = reinterpret_cast<uint64_t *>(smem_raw + p.bar_off);
@@ -447,8 +443,8 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_kernel(const __gri
     const bool dot_only = (w == 0);
     const bool loop1 = (w >= 1 && w <= A);
     const bool last = (w == 2 * A);
-    const double *v1 = nullptr, *v2 = nullptr;
-    double c1 = 0.0;
+    const T *v1 = nullptr, *v2 = nullptr;
+    T c1 = (T)0;
     bool qin_is_x = false;
     bool apply_gamma = false;
     if (dot_only) {
@@ -456,8 +452,8 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_kernel(const __gri
       qin_is_x = true;
     } else if (loop1) {
       const int i = w;
-      const double ak = s_dot / p.ys[i - 1];                      // αk = dot(s[k], q) / ys[k]      :133
-      if (tid == 0) alphas[i - 1] = ak;
+      const T ak = (T)s_dot / (T)p.ys[i - 1];                     // αk = dot(s[k], q) / ys[k]      :133
+      if (tid == 0) alphas[i - 1] = (double)ak;
       c1 = ak;
       v1 = p.y[i - 1];
       qin_is_x = (i == 1);
@@ -465,7 +461,7 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_kernel(const __gri
       v2 = (i < A) ? p.s[i] : p.y[A - 1];
     } else {
       const int i = w - A, o = A - i;
-      c1 = alphas[o] - s_dot / p.ys[o];                           // β = αk - dot(y[k], q) / ys[k]  :144-145
+      c1 = (T)alphas[o] - (T)s_dot / (T)p.ys[o];                  // β = αk - dot(y[k], q) / ys[k]  :144-145
       v1 = p.s[o];
       v2 = last ? nullptr : p.y[o - 1];
     }
@@ -484,7 +480,8 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_kernel(const __gri
       __syncwarp();
     } else {
       double acc = 0.0;
-      double q[EPT], xn[EPT], rold[EPT];
+      T q[EPT], xn[EPT], rold[EPT];
+      const T alpha = (T)p.alpha, beta = (T)p.beta, gamma = (T)p.gamma;
       if (qin_is_x && my_tiles > 0) load_user_tile<R>(p.x, (int64_t)blockIdx.x * R, p.n, p.x_al16, xn);
       for (int64_t i = 0; i < my_tiles; ++i) {
         const int64_t t = blockIdx.x + i * grid;
@@ -495,64 +492,44 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_kernel(const __gri
           if (i + 1 < my_tiles) load_user_tile<R>(p.x, (t + grid) * R, p.n, p.x_al16, xn);
         } else {
           mbar_wait(&rg.full[pos.slot], pos.par);
-          const double2 *Q = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R);
-#pragma unroll
-          for (int j = 0; j < EPT / 2; ++j) {
-            double2 v = Q[j * B2O_NCONS + tid];
-            q[2 * j] = v.x;
-            q[2 * j + 1] = v.y;
-          }
+          tile_from_ring<R>(rg, pos.slot, q);
           // the slot goes back only after the arithmetic below has consumed the loaded registers: an mbarrier arrive
           // issued behind still-in-flight LDS can let the TMA refill race the read (tests/test_sass_invariants.py)
           q_slot = pos.slot;
           pos.advance();
         }
-        if (last && p.beta != 0.0) load_user_tile<R>(p.res, t * R, p.n, p.res_al16, rold);
+        if (last && beta != (T)0) load_user_tile<R>(p.res, t * R, p.n, p.res_al16, rold);
         if (v1) {
           mbar_wait(&rg.full[pos.slot], pos.par);
-          const double2 *V = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R);
+          T v[EPT];
+          tile_from_ring<R>(rg, pos.slot, v);
 #pragma unroll
-          for (int j = 0; j < EPT / 2; ++j) {
-            double2 v = V[j * B2O_NCONS + tid];
-            if (loop1) {
-              q[2 * j] = q[2 * j] - c1 * v.x;                                          // q .-= αk .* y[k]   :135
-              q[2 * j + 1] = q[2 * j + 1] - c1 * v.y;
-            } else {
-              q[2 * j] = q[2 * j] + c1 * v.x;                                          // q .+= β .* s[k]    :146
-              q[2 * j + 1] = q[2 * j + 1] + c1 * v.y;
-            }
+          for (int j = 0; j < EPT; ++j) {
+            if (loop1) q[j] = q[j] - c1 * v[j];                                        // q .-= αk .* y[k]   :135
+            else q[j] = q[j] + c1 * v[j];                                              // q .+= β .* s[k]    :146
           }
           if (q_slot != 0xffffffffu) consumer_release(rg, q_slot);
           consumer_release(rg, pos.slot);
           pos.advance();
           if (apply_gamma) {
 #pragma unroll
-            for (int j = 0; j < EPT; ++j) q[j] = q[j] * p.gamma;                       // q .*= γ            :139
+            for (int j = 0; j < EPT; ++j) q[j] = q[j] * gamma;                         // q .*= γ            :139
           }
           if (last) {
 #pragma unroll
-            for (int j = 0; j < EPT; ++j)
-              q[j] = (p.beta != 0.0) ? p.alpha * q[j] + p.beta * rold[j] : p.alpha * q[j];  // :149-153
+            for (int j = 0; j < EPT; ++j) q[j] = (beta != (T)0) ? alpha * q[j] + beta * rold[j] : alpha * q[j];  // :149-153
             store_user_tile<R>(p.res, t * R, p.n, p.res_al16, q);
           } else {
             // q is library-owned: pitch is padded, rows >= n hold zeros and stay zero (x loads 0 there)
-            double2 *Qg = reinterpret_cast<double2 *>(p.q + t * R);
-#pragma unroll
-            for (int j = 0; j < EPT / 2; ++j) Qg[j * B2O_NCONS + tid] = make_double2(q[2 * j], q[2 * j + 1]);
+            tile_to_owned<R>(p.q + t * R, q);
           }
         }
         else if (q_slot != 0xffffffffu) consumer_release(rg, q_slot);   // (no sweep reads q without an update vector)
         if (v2) {
           mbar_wait(&rg.full[pos.slot], pos.par);
-          const double2 *V = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R);
-          double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-          for (int j = 0; j < EPT / 2; ++j) {
-            double2 v = V[j * B2O_NCONS + tid];
-            s0 = fma(v.x, q[2 * j], s0);
-            s1 = fma(v.y, q[2 * j + 1], s1);
-          }
-          acc += s0 + s1;
+          T v[EPT];
+          tile_from_ring<R>(rg, pos.slot, v);
+          acc += tile_dot<EPT>(v, q);
           consumer_release(rg, pos.slot);
           pos.advance();
         }

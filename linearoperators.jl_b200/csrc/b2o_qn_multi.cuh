@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_multi_kernel(const __grid_
   constexpr int LPG = 32 / NR;   // lanes per right-hand-side group after the transposing reduce
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Ring rg;
-  rg.buf = reinterpret_cast<double *>(smem_raw);
+  rg.buf = smem_raw;
   double *wacc = reinterpret_cast<double *>(smem_raw + p.wacc_off);   // [8 warps][ncols][32 lanes]
   double *coef = reinterpret_cast<double *>(smem_raw + p.coef_off);   // [ncols*NR]
   rg.full = reinterpret_cast<uint64_t *>(smem_raw + p.bar_off);
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_multi_kernel(const __grid_
     }
     double *my_acc = wacc + (size_t)warp * ncols * 32 + lane;    // cell [warp][c][lane]
     auto take = [&](uint32_t slot, double (&a)[EPT]) {
-      const double2 *b = reinterpret_cast<const double2 *>(rg.buf + (size_t)slot * R);
+      const double2 *b = reinterpret_cast<const double2 *>(rg.buf + (size_t)slot * R * sizeof(double));
 #pragma unroll
       for (int j = 0; j < EPT / 2; ++j) {
         double2 v = b[j * B2O_NCONS + tid];
@@ -359,8 +359,8 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_multi_kernel(const __grid_
           pos.advance();
           mbar_wait(&rg.full[sa], pa);
           mbar_wait(&rg.full[sb], pb);
-          const double2 *A = reinterpret_cast<const double2 *>(rg.buf + (size_t)sa * R);
-          const double2 *B = reinterpret_cast<const double2 *>(rg.buf + (size_t)sb * R);
+          const double2 *A = reinterpret_cast<const double2 *>(rg.buf + (size_t)sa * R * sizeof(double));
+          const double2 *B = reinterpret_cast<const double2 *>(rg.buf + (size_t)sb * R * sizeof(double));
           double a[EPT], b[EPT];
 #pragma unroll
           for (int j = 0; j < EPT / 2; ++j) {
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_multi_kernel(const __grid_
       } else {
         for (int c = 0; c < ncols; ++c) {
           mbar_wait(&rg.full[pos.slot], pos.par);
-          const double2 *A = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R);
+          const double2 *A = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R * sizeof(double));
           double a[EPT];
 #pragma unroll
           for (int j = 0; j < EPT / 2; ++j) {
@@ -455,6 +455,7 @@ struct TwoLoopMultiArgs {
   unsigned long long bar_target;
   int stages;
   uint32_t scal_off, bar_off;    // scal: alphas [B2O_MAX_MEM][NR] | sred [8][NR] | s_dot [NR]
+  uint32_t landed_off;           // [256] one cell per consumer thread (smem_reads_landed)
 };
 
 template <int R, int NR>
@@ -462,13 +463,14 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_multi_kernel(const
   constexpr int EPT = R / B2O_NCONS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Ring rg;
-  rg.buf = reinterpret_cast<double *>(smem_raw);
+  rg.buf = smem_raw;
   double *alphas = reinterpret_cast<double *>(smem_raw + p.scal_off);   // [B2O_MAX_MEM][NR]
   double *sred = alphas + B2O_MAX_MEM * NR;                             // [8 warps][NR]
   double *s_dot = sred + B2O_CONS_WARPS * NR;                           // [NR]
   rg.full = reinterpret_cast<uint64_t *>(smem_raw + p.bar_off);
   rg.empty = rg.full + p.stages;
   rg.stages = p.stages;
+  unsigned *s_landed = reinterpret_cast<unsigned *>(smem_raw + p.landed_off);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool is_producer = warp == B2O_CONS_WARPS;
@@ -541,7 +543,7 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_multi_kernel(const
         uint32_t slot1 = 0xffffffffu, slot2 = 0xffffffffu;
         if (v1) {
           mbar_wait(&rg.full[pos.slot], pos.par);
-          const double2 *V = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R);
+          const double2 *V = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R * sizeof(double));
 #pragma unroll
           for (int j = 0; j < EPT / 2; ++j) {
             double2 v = V[j * B2O_NCONS + tid];
@@ -553,7 +555,7 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_multi_kernel(const
         }
         if (v2) {
           mbar_wait(&rg.full[pos.slot], pos.par);
-          const double2 *V = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R);
+          const double2 *V = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R * sizeof(double));
 #pragma unroll
           for (int j = 0; j < EPT / 2; ++j) {
             double2 v = V[j * B2O_NCONS + tid];
@@ -562,6 +564,14 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_multi_kernel(const
           }
           slot2 = pos.slot;
           pos.advance();
+        }
+        // v1 / v2 live in registers from here on: their slots go back BEFORE the q_r tiles are awaited (a consumer that held
+        // them across the r loop would deadlock a ring with fewer than nrhs + 2 stages).  The hand-back is made data-dependent
+        // on every LDS of the two tiles (see smem_reads_landed above).
+        if (slot1 != 0xffffffffu || slot2 != 0xffffffffu) {
+          smem_reads_landed(&s_landed[tid], (slot1 != 0xffffffffu ? fold_loaded(a1) : 0u) ^ (slot2 != 0xffffffffu ? fold_loaded(a2) : 0u));
+          if (slot1 != 0xffffffffu) consumer_release(rg, slot1);
+          if (slot2 != 0xffffffffu) consumer_release(rg, slot2);
         }
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
@@ -572,7 +582,7 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_multi_kernel(const
             load_user_tile<R>(p.x + (int64_t)r * p.ldx, t * R, p.n, p.x_al16, q);          // q .= x   :127-128
           } else {
             mbar_wait(&rg.full[pos.slot], pos.par);
-            const double2 *Q = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R);
+            const double2 *Q = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R * sizeof(double));
 #pragma unroll
             for (int j = 0; j < EPT / 2; ++j) {
               double2 v = Q[j * B2O_NCONS + tid];
@@ -581,13 +591,13 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_multi_kernel(const
             }
             q_slot = pos.slot;
             pos.advance();
+            smem_reads_landed(&s_landed[tid], fold_loaded(q));
+            consumer_release(rg, q_slot);
           }
           if (last && p.beta != 0.0) load_user_tile<R>(p.res + (int64_t)r * p.ldr, t * R, p.n, p.res_al16, rold);
           if (v1) {
 #pragma unroll
             for (int j = 0; j < EPT; ++j) q[j] = loop1 ? q[j] - c1[r] * a1[j] : q[j] + c1[r] * a1[j];   // :135 / :146
-            // slots go back only after arithmetic has consumed the registers loaded from them (see qn_twoloop_kernel)
-            if (q_slot != 0xffffffffu) consumer_release(rg, q_slot);
             if (apply_gamma) {
 #pragma unroll
               for (int j = 0; j < EPT; ++j) q[j] = q[j] * p.gamma;                          // q .*= γ            :139
@@ -612,8 +622,6 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_multi_kernel(const
             acc[r] += s0 + s1;
           }
         }
-        if (slot1 != 0xffffffffu) consumer_release(rg, slot1);
-        if (slot2 != 0xffffffffu) consumer_release(rg, slot2);
       }
       if (v2) {
 #pragma unroll

@@ -1214,8 +1214,7 @@ def test_block_apply_matches_vector_apply(lo, ctx, orc, kind, n, mem, npush, nrh
         l0 = ctx.launch_count()
         lo.mul_(Res, op, X, alpha, beta)
         nl = ctx.launch_count() - l0
-        if kind != "inverse_twoloop":
-            assert nl == (1 if nrhs <= 8 else 2), nl
+        assert nl == (1 if nrhs <= 8 else 2), nl                   # two-loop inverse: the block recursion, 2A+1 sweeps per launch
         for j in range(nrhs):
             ref = host(R0[:, j]).copy()
             o.apply(host(X[:, j]), alpha, beta, res=ref)
@@ -1223,6 +1222,17 @@ def test_block_apply_matches_vector_apply(lo, ctx, orc, kind, n, mem, npush, nrh
             v = ctx.empty(n).copy_(R0[:, j])
             lo.mul_(v, op, X[:, j].contiguous(), alpha, beta)
             assert rel(host(Res[:, j]), host(v)) <= (1e-13 if tol == 1e-12 else 1e-10)
+            if kind == "inverse_twoloop":
+                # the block recursion keeps every statement and every reduction order of the vector kernel: same bits
+                assert np.array_equal(host(Res[:, j]), host(v)), j
+    if kind == "inverse_twoloop":
+        ctx.set_option("twoloop_block", 0)                          # column loop: same result, nrhs launches
+        Res2 = _colmajor(ctx, n, nrhs, 400, pad)
+        l0 = ctx.launch_count()
+        lo.mul_(Res2, op, X, -0.75, 0.5)
+        ctx.set_option("twoloop_block", 1)
+        assert ctx.launch_count() - l0 == nrhs
+        assert np.array_equal(host(Res2), host(Res))
     with pytest.raises(lo.LinearOperatorException):
         lo.mul_(Res, op, _colmajor(ctx, n + 1, nrhs, 1))
 

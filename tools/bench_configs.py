@@ -287,6 +287,33 @@ def main():
                  rel_diff_vs_vector_apply=diff)
             del Xb, X, Res
             torch.cuda.empty_cache()
+        del B
+        torch.cuda.empty_cache()
+        # block two-loop recursion: matrix right-hand sides of the two-loop InverseLBFGSOperator (src/operations.jl:34-36)
+        m = 20
+        H = lo.InverseLBFGSOperator(n, mem=m, ctx=ctx)
+        for i in range(m):
+            s = ctx.uniform(n, 100 + i)
+            lo.push_(H, s, s + 0.1 * ctx.uniform(n, 200 + i))
+        del s
+        for k in (2, 4, 8):
+            Xb = torch.empty((k, n), dtype=torch.float64, device="cuda")
+            for j in range(k):
+                Xb[j] = ctx.uniform(n, 300 + j)
+            X, Res = Xb.T, torch.empty((k, n), dtype=torch.float64, device="cuda").T
+            ms = timeit(lambda: lo.mul_(Res, H, X), 5)
+            ctx.set_option("twoloop_block", 0)
+            ms_loop = timeit(lambda: lo.mul_(Res, H, X), 3)
+            ctx.set_option("twoloop_block", 1)
+            r = ctx.empty(n)
+            lo.mul_(Res, H, X)
+            lo.mul_(r, H, Xb[k - 1])
+            same = bool(torch.equal(Res[:, k - 1], r))
+            line("InverseLBFGS(mem=20) two-loop, block recursion, %d right-hand sides" % k, ms, ((4 * k + 4) * m + k) * 8.0 * n,
+                 ms_column_by_column=round(ms_loop, 3), speedup=round(ms_loop / ms, 2), vector_equivalent_GBps=round(k * (8 * m + 2) * 8.0 * n / ms / 1e6, 1),
+                 bit_identical_to_vector_apply=same)
+            del Xb, X, Res
+            torch.cuda.empty_cache()
         return
     if only == ["invc"]:
         v, res = ctx.uniform(n, 7), ctx.empty(n)
