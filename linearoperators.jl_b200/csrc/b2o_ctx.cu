@@ -92,7 +92,7 @@ extern "C" int b2o_ctx_set_option(b2o_ctx *c, const char *key, int64_t value) {
     if (value < 0 || value > B2O_MAX_GRID) B2O_FAIL(B2O_EARG, "grid out of range");
     c->grid = (int)value;
   } else if (!strcmp(key, "kron_debug")) {
-    c->kron_debug = value != 0;
+    c->kron_debug = (int)value;
   } else if (!strcmp(key, "host_chunks")) {
     if (value < 1 || value > 16) B2O_FAIL(B2O_EARG, "host_chunks must be 1..16");
     c->host_chunks = (int)value;

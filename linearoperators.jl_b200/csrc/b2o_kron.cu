@@ -48,6 +48,9 @@ struct KronArgs {
   int rblocks, units;           // BM-row blocks per right-hand side; units = nb * rblocks
   void *res;                    // nb × (M*N2), each column-major M×N2; bf16 or (out_f32) fp32
   int out_f32, store_tma;       // store_tma: the result tile leaves through a TMA store (beta == 0, 16-byte aligned res)
+  int y_tma;                    // pair kernel: Y leaves through TMA stores (0: staging + plain 16-byte stores, the default)
+  void *y;                      // pair kernel: Y workspace of this direction
+  int dbg_tile;                 // pair kernel, kron_debug >= 2: chunk-level stamps of accumulator tile kron_debug - 2 (-1: tile-level stamps)
   float alpha, beta;
   unsigned long long *dbg;      // optional timeline of CTA 0 (%globaltimer, ns): [0] start [1] setup done [2+4*ph] first stage landed
                                 // [3+4*ph] accumulator complete [4+4*ph] epilogue done [5] Y published cluster-wide [10] exit
@@ -659,6 +662,7 @@ struct b2o_kron_s {
   const void *x_last[2] = {nullptr, nullptr}, *res_last[2] = {nullptr, nullptr};
   int x_nb[2] = {0, 0}, x_bn[2] = {0, 0}, res_nb[2] = {0, 0}, res_bn[2] = {0, 0}, res_bm[2] = {0, 0}, res_f32[2] = {-1, -1};
   int force_cluster = 0, force_bn = 0, force_bm = 0;   // tuning overrides (b2o_kron_set_option)
+  int pair_tma_stores = 1;                             // pair kernel epilogue: 1 = TMA stores (default), 0 = plain stores (measured slower)
 };
 
 static inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
@@ -764,6 +768,8 @@ extern "C" int b2o_kron_set_option(b2o_kron *k, const char *key, int64_t value) 
   } else if (!strcmp(key, "tile_m")) {
     if (value != 0 && value != 64 && value != 128 && value != 256) B2O_FAIL(B2O_EARG, "tile_m must be 0, 64, 128 or 256 (256 = the cta_group::2 pair kernel)");
     k->force_bm = (int)value;
+  } else if (!strcmp(key, "pair_tma_stores")) {
+    k->pair_tma_stores = value != 0;
   } else {
     B2O_FAIL(B2O_EARG, "unknown option '%s'", key);
   }
@@ -893,6 +899,7 @@ extern "C" int b2o_kron_apply(b2o_kron *k, int trans, void *res, int res_dtype, 
   a.beta = (float)beta;
   a.store_tma = (beta == 0.0 && ((uintptr_t)res % 16) == 0) ? 1 : 0;
   a.dbg = c->kron_debug ? (unsigned long long *)(c->d_dots + 448) : nullptr;
+  a.dbg_tile = c->kron_debug >= 2 ? c->kron_debug - 2 : -1;
   // Tile shape and cluster size.  An SM takes in operand bytes at ~50 B/clk, far below what its tensor core consumes, so the
   // time of a phase is (rows + columns of the CTA tile) x K x 2 bytes / that rate: few units (latency-bound sizes like cfg4)
   // want small tiles on many SMs -- 64-row units, 64 columns per CTA, 8 CTAs per unit (64 CTAs for cfg4; 16-CTA clusters
@@ -915,6 +922,9 @@ extern "C" int b2o_kron_apply(b2o_kron *k, int trans, void *res, int res_dtype, 
   if (pair) {            // operand boxes of 128 rows; Y leaves in 32-column boxes, the result in 128 x 32 boxes
     BM = 128;
     BN = 128;
+    a.y = k->Y[d];
+    a.y_tma = k->pair_tma_stores;
+    if (!k->pair_tma_stores) a.store_tma = 0;   // the result goes out with direct coalesced stores from the registers
   }
   a.rblocks = pair ? (M + 255) / 256 : (M + BM - 1) / BM;
   a.units = nb * a.rblocks;

@@ -225,7 +225,7 @@ kron_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
             const uint32_t tmem_acc = tmem_base + acc * KP_TCOLS;
             kp_wait(&tmem_empty[acc], tpar ^ 1u);       // both CTAs' epilogues have drained this accumulator
             tc_fence_after();
-            if (p.dbg && blockIdx.x == 0 && lane == 0 && tcount < 8) p.dbg[16 + 2 * tcount] = gtimer();
+            if (p.dbg && p.dbg_tile < 0 && blockIdx.x == 0 && lane == 0 && tcount < 8) p.dbg[16 + 2 * tcount] = gtimer();
             for (int ks = 0; ks < ksteps; ++ks) {
               const uint32_t s0 = slot, p0 = sphase;
               KP_ADVANCE(1);
@@ -263,7 +263,7 @@ kron_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
               }
               __syncwarp();
             }
-            if (p.dbg && blockIdx.x == 0 && lane == 0 && tcount < 8) p.dbg[17 + 2 * tcount] = gtimer();
+            if (p.dbg && p.dbg_tile < 0 && blockIdx.x == 0 && lane == 0 && tcount < 8) p.dbg[17 + 2 * tcount] = gtimer();
             ++tcount;
           }
         }
@@ -281,16 +281,24 @@ kron_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           const uint32_t tmem_acc = tmem_base + acc * KP_TCOLS;
           kp_wait(&tmem_full[acc], tpar);
           tc_fence_after();
-          if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 8) p.dbg[48 + 2 * tcount] = gtimer();
+          if (p.dbg && p.dbg_tile < 0 && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 8) p.dbg[48 + 2 * tcount] = gtimer();
 #pragma unroll 1
           for (int c0 = 0; c0 < KP_TN; c0 += 32) {
             const int col0 = t * KP_TN + c0;
             if (col0 >= p.N1) break;
             uint32_t v[32];
+            const bool stamp = p.dbg && p.dbg_tile == (int)tcount && blockIdx.x == 0 && threadIdx.x == 64;
+            if (stamp) p.dbg[16 + 5 * (c0 >> 5)] = gtimer();
             tc_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+            if (stamp) p.dbg[17 + 5 * (c0 >> 5)] = gtimer();
             unsigned char *stg = staging + (size_t)(gcount & 1u) * KP_STG;
-            if (issuer) kp_store_wait_read1();       // the store that used this buffer two chunks ago has read it
-            epi_sync();
+            if (p.y_tma) {
+              if (issuer) kp_store_wait_read1();     // the store that used this buffer two chunks ago has read it
+              epi_sync();
+            }
+            if (stamp) p.dbg[18 + 5 * (c0 >> 5)] = gtimer();
+            // (manual path: the copy-out of the chunk two back was finished by every thread before it passed the epi_sync of
+            //  the previous chunk, so this buffer is free)
 #pragma unroll
             for (int g = 0; g < 32; g += 8) {
               uint32_t hi[4], lo[4];
@@ -302,33 +310,58 @@ kron_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
                 hi[e] = *reinterpret_cast<const uint32_t *>(&h);
                 lo[e] = *reinterpret_cast<const uint32_t *>(&l);
               }
-              // box = [128 rows][32 cols] bf16: rows of 64 bytes, TMA 64-byte swizzle on the 16-byte chunk index
+              // box = [128 rows][32 cols] bf16: rows of 64 bytes, 16-byte chunk index xor-ed with (row / 2) % 4 (= TMA's 64-byte
+              // swizzle): the 32 lanes of a warp write 32 rows conflict-free
               const int sw = (g >> 3) ^ ((rloc >> 1) & 3);
               unsigned char *dst = stg + (size_t)rloc * 64 + sw * 16;
               *reinterpret_cast<uint4 *>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               *reinterpret_cast<uint4 *>(dst + KP_ROWS * 64) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
-            fence_proxy_async_smem();
-            epi_sync();
-            if (issuer) {
-              if (row0 < p.M) {
-                tma_store_3d(&tmYhi, stg, col0, row0, b0);
-                tma_store_3d(&tmYlo, stg + KP_ROWS * 64, col0, row0, b0);
+            if (stamp) p.dbg[19 + 5 * (c0 >> 5)] = gtimer();
+            if (p.y_tma) {
+              fence_proxy_async_smem();
+              epi_sync();
+              if (issuer) {
+                if (row0 < p.M) {
+                  tma_store_3d(&tmYhi, stg, col0, row0, b0);
+                  tma_store_3d(&tmYlo, stg + KP_ROWS * 64, col0, row0, b0);
+                }
+                tma_store_commit();
               }
-              tma_store_commit();
+            } else {
+              // copy-out with plain 16-byte stores: 4 consecutive threads cover the 64 bytes of one row of the box (option
+              // pair_tma_stores = 0; measured slower than the TMA stores: 76 vs 54 us at 64 right-hand sides)
+              epi_sync();
+              const int te = (int)threadIdx.x - 64;
+              __nv_bfloat16 *Yb = reinterpret_cast<__nv_bfloat16 *>(p.y) + (size_t)b0 * p.M * 2 * p.ldy;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int u = te + 128 * k, half = u >> 9, w = u & 511, row = w >> 2, pc = w & 3;
+                const int gcol = col0 + ((pc ^ ((row >> 1) & 3)) << 3), grow = row0 + row;
+                if (grow < p.M && gcol < p.N1)
+                  *reinterpret_cast<uint4 *>(Yb + (size_t)grow * 2 * p.ldy + (size_t)half * p.ldy + gcol) = *reinterpret_cast<const uint4 *>(stg + (size_t)u * 16);
+              }
             }
+            if (stamp) p.dbg[20 + 5 * (c0 >> 5)] = gtimer();
             ++gcount;
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) kp_arrive_cl(te_leader + acc * 8u);
-          if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 8) p.dbg[49 + 2 * tcount] = gtimer();
+          if (p.dbg && p.dbg_tile < 0 && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 8) p.dbg[49 + 2 * tcount] = gtimer();
           ++tcount;
         }
-        if (issuer) {
-          tma_store_wait_all();                         // this CTA's Y rows of the unit are in global memory
-          asm volatile("fence.proxy.async;" ::: "memory");
-          mbar_arrive(&y_ready[i & 1]);
+        if (p.y_tma) {
+          if (issuer) {
+            tma_store_wait_all();                       // this CTA's Y rows of the unit are in global memory
+            asm volatile("fence.proxy.async;" ::: "memory");
+            mbar_arrive(&y_ready[i & 1]);
+          }
+        } else {
+          __threadfence();                              // every thread's Y stores are performed ...
+          asm volatile("fence.proxy.async;" ::: "memory");   // ... and ordered before the bulk (async-proxy) loads that follow the hand-over
+          epi_sync();
+          if (issuer) mbar_arrive(&y_ready[i & 1]);
         }
       }
       // ---- GEMM 2: result tile, 32 columns (j) at a time
@@ -338,17 +371,21 @@ kron_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           const uint32_t tmem_acc = tmem_base + acc * KP_TCOLS;
           kp_wait(&tmem_full[acc], tpar);
           tc_fence_after();
-          if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 8) p.dbg[48 + 2 * tcount] = gtimer();
+          if (p.dbg && p.dbg_tile < 0 && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 8) p.dbg[48 + 2 * tcount] = gtimer();
 #pragma unroll 1
           for (int c0 = 0; c0 < KP_TN; c0 += 32) {
             const int n0 = t * KP_TN + c0;
             if (n0 >= p.N2) break;
             uint32_t v[32];
+            const bool stamp = p.dbg && p.dbg_tile == (int)tcount && blockIdx.x == 0 && threadIdx.x == 64;
+            if (stamp) p.dbg[16 + 5 * (c0 >> 5)] = gtimer();
             tc_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+            if (stamp) p.dbg[17 + 5 * (c0 >> 5)] = gtimer();
             if (p.store_tma) {
               unsigned char *stg = staging + (size_t)(gcount & 1u) * KP_STG;
               if (issuer) kp_store_wait_read1();
               epi_sync();
+              if (stamp) p.dbg[18 + 5 * (c0 >> 5)] = gtimer();
               // staging tile [32 cols (j)][128 rows (i)]: lanes write consecutive i -> conflict-free
               if (p.out_f32) {
                 float *st = reinterpret_cast<float *>(stg) + rloc;
@@ -359,12 +396,14 @@ kron_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
 #pragma unroll
                 for (int e = 0; e < 32; ++e) st[(size_t)e * KP_ROWS] = __float2bfloat16_rn(p.alpha * __uint_as_float(v[e]));
               }
+              if (stamp) p.dbg[19 + 5 * (c0 >> 5)] = gtimer();
               fence_proxy_async_smem();
               epi_sync();
               if (issuer) {
                 if (row1 < p.M) tma_store_3d(&tmRes, stg, row1, n0, b1);
                 tma_store_commit();
               }
+              if (stamp) p.dbg[20 + 5 * (c0 >> 5)] = gtimer();
               ++gcount;
             } else if (row1 + rloc < p.M) {
               const size_t off = (size_t)b1 * p.M * p.N2 + (size_t)(row1 + rloc) + (size_t)n0 * p.M;
@@ -381,7 +420,7 @@ kron_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           tc_fence_before();
           __syncwarp();
           if (lane == 0) kp_arrive_cl(te_leader + acc * 8u);
-          if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 8) p.dbg[49 + 2 * tcount] = gtimer();
+          if (p.dbg && p.dbg_tile < 0 && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 8) p.dbg[49 + 2 * tcount] = gtimer();
           ++tcount;
         }
       }

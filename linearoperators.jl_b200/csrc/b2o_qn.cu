@@ -12,6 +12,7 @@ constexpr size_t B2O_MAX_DYN_SMEM = 227 * 1024 - 1024;  // rows; every supported
 struct b2o_qn_s {
   b2o_ctx *ctx = nullptr;
   int kind = 0;  // 0 = L-BFGS, 1 = L-SR1
+  int esize = 8; // element size: 8 = Float64 (everything below), 4 = Float32 (b2o_qn_f32.inc: the column slabs then hold floats)
   int64_t n = 0, pitch = 0;
   int mem = 1;
   bool scaling = true, damped = false, inverse = false;
@@ -31,8 +32,17 @@ struct b2o_qn_s {
   std::vector<double> SY, YY, SS;   // [mem*mem]: SY[i*mem+j] = s_i·y_j, YY[i*mem+j] = y_i·y_j, SS[i*mem+j] = s_i·s_j
   double *d_W = nullptr;        // [(2*mem)^2]
   double *h_W = nullptr;        // pinned staging
-  double *col(double *base, int k0) const { return base + (size_t)k0 * (size_t)pitch; }
+  double *col(double *base, int k0) const { return base + (size_t)k0 * (size_t)pitch; }   // Float64 handles only
+  void *colv(double *base, int k0) const { return reinterpret_cast<char *>(base) + (size_t)k0 * (size_t)pitch * (size_t)esize; }
 };
+
+// Float32 operators (b2o_qn_f32.inc, included at the end of this file)
+static int qn32_apply(b2o_qn *q, float *res, const float *x, double alpha, double beta);
+static int qn32_push(b2o_qn *q, const float *s, const float *y, int *accepted);
+#define B2O_F64_ONLY(q, what)                                                                                                    \
+  do {                                                                                                                           \
+    if ((q)->esize != 8) B2O_FAIL(B2O_EUNSUPPORTED, what " is not built for Float32 quasi-Newton operators (Float64 only)");      \
+  } while (0)
 
 static inline int pmod(int a, int m) {
   int r = a % m;
@@ -216,7 +226,7 @@ static int ew_axpby(b2o_ctx *c, double *out, double a, const double *x, double b
 static int qn_alloc(b2o_qn *q) {
   b2o_ctx *c = q->ctx;
   B2O_CUDA(cudaSetDevice(c->device));
-  const size_t colb = (size_t)q->pitch * sizeof(double);
+  const size_t colb = (size_t)q->pitch * (size_t)q->esize;
   auto alloc0 = [&](double **p, size_t bytes) -> int {
     cudaError_t e = cudaMalloc(p, bytes);
     if (e != cudaSuccess) {
@@ -259,7 +269,8 @@ extern "C" int b2o_qn_destroy(b2o_qn *q) {
 
 static int qn_create_common(b2o_ctx *ctx, int dtype, int64_t n, int mem, b2o_qn **out, b2o_qn **made) {
   if (!ctx || !out) B2O_FAIL(B2O_EARG, "null argument");
-  B2O_TRY(b2o_check_dtype_f64(dtype));
+  if (dtype != B2O_F64 && dtype != B2O_F32) B2O_FAIL(B2O_EUNSUPPORTED, "quasi-Newton operators: dtype %d not supported (Float64 or Float32)", dtype);
+  if (dtype == B2O_F32 && ctx->nranks > 1) B2O_FAIL(B2O_EUNSUPPORTED, "Float32 quasi-Newton operators are not built for row-partitioned contexts");
   if (n < 0) B2O_FAIL(B2O_EARG, "n must be >= 0");
   if (mem < 1) mem = 1;  // LBFGSData clamps mem to max(mem,1) (src/lbfgs.jl:37)
   if (mem > B2O_MAX_MEM) B2O_FAIL(B2O_EUNSUPPORTED, "mem=%d exceeds the built maximum %d", mem, B2O_MAX_MEM);
@@ -268,6 +279,7 @@ static int qn_create_common(b2o_ctx *ctx, int dtype, int64_t n, int mem, b2o_qn 
   q->n = n;
   q->pitch = std::max<int64_t>(B2O_PITCH_ALIGN, (n + B2O_PITCH_ALIGN - 1) / B2O_PITCH_ALIGN * B2O_PITCH_ALIGN);
   q->mem = mem;
+  q->esize = dtype == B2O_F32 ? 4 : 8;
   *made = q;
   return B2O_OK;
 }
@@ -277,6 +289,10 @@ extern "C" int b2o_lbfgs_create(b2o_ctx *ctx, int dtype, int64_t n, int mem, int
   b2o_qn *q = nullptr;
   B2O_TRY(qn_create_common(ctx, dtype, n, mem, out, &q));
   q->kind = 0;
+  if (q->esize != 8 && damped) {
+    delete q;
+    B2O_FAIL(B2O_EUNSUPPORTED, "damped L-BFGS is not built for Float32 (Float64 only)");
+  }
   q->scaling = scaling != 0;
   q->damped = damped != 0;
   q->inverse = inverse != 0;
@@ -837,6 +853,7 @@ static int twoloop_multi_launch(b2o_qn *q, double *res, int64_t ldr, const doubl
 extern "C" int b2o_qn_apply_multi(b2o_qn *q, void *res_, int64_t ldr, const void *x_, int64_t ldx, int64_t len, int nrhs,
                                   double alpha, double beta) {
   if (!q) B2O_FAIL(B2O_EARG, "null operator");
+  B2O_F64_ONLY(q, "the block apply");
   if (len != q->n) B2O_FAIL(B2O_ESHAPE, "shape mismatch");
   if (nrhs < 0) B2O_FAIL(B2O_EARG, "nrhs must be >= 0");
   if (nrhs == 0 || q->n == 0) return B2O_OK;
@@ -881,10 +898,13 @@ extern "C" int b2o_qn_apply_multi(b2o_qn *q, void *res_, int64_t ldr, const void
       const int k = std::min(left, 8);
       B2O_TRY(multi_launch<8>(q, base, res + (int64_t)r0 * ldr, ldr, x + (int64_t)r0 * ldx, ldx, k));
       r0 += k;
-    } else {
+    } else if (left > 2) {
       const int k = std::min(left, 4);
       B2O_TRY(multi_launch<4>(q, base, res + (int64_t)r0 * ldr, ldr, x + (int64_t)r0 * ldx, ldx, k));
       r0 += k;
+    } else {
+      B2O_TRY(multi_launch<2>(q, base, res + (int64_t)r0 * ldr, ldr, x + (int64_t)r0 * ldx, ldx, left));   // 1 or 2 columns left
+      r0 += left;
     }
   }
   return B2O_OK;
@@ -923,6 +943,7 @@ static int update_gram(b2o_qn *q, int k) {
 // ONE all-reduce instead of 2m dependent ones; different rounding, same operator)
 extern "C" int b2o_qn_set_option(b2o_qn *q, const char *key, int64_t value) {
   if (!q || !key) B2O_FAIL(B2O_EARG, "null argument");
+  if (strcmp(key, "push_mode")) B2O_F64_ONLY(q, "this option");
   if (!strcmp(key, "inverse_mode")) {
     if (!(q->kind == 0 && q->inverse)) B2O_FAIL(B2O_EARG, "inverse_mode applies to InverseLBFGSOperator");
     if (value != 0 && value != 1) B2O_FAIL(B2O_EARG, "inverse_mode must be 0 (two-loop) or 1 (compact)");
@@ -986,8 +1007,9 @@ extern "C" int b2o_qn_apply(b2o_qn *q, void *res, int64_t res_len, const void *x
   if (!q) B2O_FAIL(B2O_EARG, "null operator");
   if (x_len != q->n || res_len != q->n) B2O_FAIL(B2O_ESHAPE, "shape mismatch");
   if ((!res || !x) && q->n > 0) B2O_FAIL(B2O_EARG, "null vector");
-  if (((uintptr_t)res | (uintptr_t)x) % 8) B2O_FAIL(B2O_EARG, "vectors must be 8-byte aligned");
+  if (((uintptr_t)res | (uintptr_t)x) % (uintptr_t)q->esize) B2O_FAIL(B2O_EARG, "vectors must be aligned to the element size");
   B2O_CUDA(cudaSetDevice(q->ctx->device));
+  if (q->esize == 4) return qn32_apply(q, (float *)res, (const float *)x, alpha, beta);
   return qn_apply_dev(q, (double *)res, (const double *)x, alpha, beta);
 }
 
@@ -1024,6 +1046,7 @@ static int ensure_pipeline(b2o_ctx *c) {
 // launch's only per chunk order: the dots are accumulated chunk by chunk in a fixed order (deterministic).
 extern "C" int b2o_qn_apply_host(b2o_qn *q, void *res_host, const void *x_host, int64_t len, double alpha, double beta) {
   if (!q) B2O_FAIL(B2O_EARG, "null operator");
+  B2O_F64_ONLY(q, "the host-buffer apply");
   if (len != q->n) B2O_FAIL(B2O_ESHAPE, "shape mismatch");
   b2o_ctx *c = q->ctx;
   B2O_CUDA(cudaSetDevice(c->device));
@@ -1095,7 +1118,7 @@ extern "C" int b2o_qn_apply_bytes(b2o_qn *q, double beta, double *bytes) {
   else if (q->kind == 0) per_row = na > 0 ? 4.0 * na + 3.0 : 2.0;            // (4m+3) n E
   else per_row = na > 0 ? 2.0 * na + 3.0 : 2.0;                              // (2m+3) n E
   if (beta != 0.0) per_row += 1.0;
-  *bytes = per_row * 8.0 * (double)q->n;
+  *bytes = per_row * (double)q->esize * (double)q->n;
   return B2O_OK;
 }
 
@@ -1242,7 +1265,7 @@ static int lbfgs_push_common(b2o_qn *q, const double *s, const double *y, double
 static int check_vec(const b2o_qn *q, const void *p, int64_t len) {
   if (len != q->n) B2O_FAIL(B2O_ESHAPE, "shape mismatch");
   if (!p && q->n > 0) B2O_FAIL(B2O_EARG, "null vector");
-  if ((uintptr_t)p % 8) B2O_FAIL(B2O_EARG, "vectors must be 8-byte aligned");
+  if ((uintptr_t)p % (uintptr_t)q->esize) B2O_FAIL(B2O_EARG, "vectors must be aligned to the element size");
   return B2O_OK;
 }
 
@@ -1250,6 +1273,7 @@ static int lsr1_push(b2o_qn *q, const double *s, const double *y, int *accepted)
 
 extern "C" int b2o_lbfgs_push_damped_fwd(b2o_qn *q, const void *s_, const void *y_, void *Bs_, int64_t len, int *accepted) {
   if (!q || q->kind != 0) B2O_FAIL(B2O_EARG, "not an L-BFGS operator");
+  B2O_F64_ONLY(q, "damped push!");
   if (!q->damped) B2O_FAIL(B2O_ESTATE, "This push! should be used for damped operators");
   if (q->inverse) B2O_FAIL(B2O_ESTATE, "This function be used for forward operators. Use push!(op, s, y, α, g, Bs) instead.");
   B2O_TRY(check_vec(q, s_, len));
@@ -1294,6 +1318,7 @@ extern "C" int b2o_lbfgs_push_damped_fwd(b2o_qn *q, const void *s_, const void *
 extern "C" int b2o_lbfgs_push_damped_inv(b2o_qn *q, const void *s_, void *y_, double alpha, const void *g_, void *Bs_,
                                          int64_t len, int *accepted) {
   if (!q || q->kind != 0) B2O_FAIL(B2O_EARG, "not an L-BFGS operator");
+  B2O_F64_ONLY(q, "damped push!");
   if (!q->damped) B2O_FAIL(B2O_ESTATE, "This push! should be used for damped operators");
   if (!q->inverse) B2O_FAIL(B2O_ESTATE, "This function be used for inverse operators. Use push!(op, s, y, Bs) instead.");
   B2O_TRY(check_vec(q, s_, len));
@@ -1340,6 +1365,7 @@ extern "C" int b2o_qn_push(b2o_qn *q, const void *s_, const void *y_, int64_t le
   B2O_TRY(check_vec(q, y_, len));
   b2o_ctx *c = q->ctx;
   B2O_CUDA(cudaSetDevice(c->device));
+  if (q->esize == 4) return qn32_push(q, (const float *)s_, (const float *)y_, accepted);
   const double *s = (const double *)s_, *y = (const double *)y_;
   if (accepted) *accepted = 0;
   if (q->kind == 1) return lsr1_push(q, s, y, accepted);
@@ -1494,6 +1520,7 @@ static int lsr1_push(b2o_qn *q, const double *s, const double *y, int *accepted)
 // dots u·p_i and b·p_i fused in; x is assembled at the end in one pass with the reference's statement order.
 extern "C" int b2o_lbfgs_solve_shifted(b2o_qn *q, void *x_, int64_t x_len, const void *b_, int64_t b_len, double sigma) {
   if (!q) B2O_FAIL(B2O_EARG, "null operator");
+  B2O_F64_ONLY(q, "solve_shifted_system!");
   if (q->kind != 0 || q->inverse) B2O_FAIL(B2O_EARG, "solve_shifted_system! needs a forward LBFGSOperator");
   if (sigma < 0) B2O_FAIL(B2O_EARG, "σ must be nonnegative");                                   // ArgumentError :213-215
   if (q->fwd_compact) {
@@ -1632,6 +1659,7 @@ extern "C" int b2o_lbfgs_solve_shifted(b2o_qn *q, void *x_, int64_t x_len, const
 // ------------------------------------------------------------------ diag! / reset! / state
 extern "C" int b2o_qn_diag(b2o_qn *q, void *d, int64_t d_len) {
   if (!q) B2O_FAIL(B2O_EARG, "null operator");
+  B2O_F64_ONLY(q, "diag!");
   if (q->kind == 0 && q->inverse)
     B2O_FAIL(B2O_ESTATE, "only the diagonal of a forward L-BFGS approximation is available");  // src/lbfgs.jl:380-382
   if (q->fwd_compact) B2O_FAIL(B2O_EUNSUPPORTED, "diag! needs the a_k/b_k form (forward_mode 0)");
@@ -1664,7 +1692,7 @@ extern "C" int b2o_qn_reset(b2o_qn *q) {
   if (!q) B2O_FAIL(B2O_EARG, "null operator");
   b2o_ctx *c = q->ctx;
   B2O_CUDA(cudaSetDevice(c->device));
-  const size_t colb = (size_t)q->pitch * sizeof(double) * q->mem;
+  const size_t colb = (size_t)q->pitch * (size_t)q->esize * q->mem;
   B2O_CUDA(cudaMemsetAsync(q->S, 0, colb, c->stream));
   B2O_CUDA(cudaMemsetAsync(q->Y, 0, colb, c->stream));
   if (q->A) B2O_CUDA(cudaMemsetAsync(q->A, 0, colb, c->stream));
@@ -1696,14 +1724,14 @@ extern "C" int b2o_qn_get_col(b2o_qn *q, int which, int k0, void *dst) {
   if (!q || !dst) B2O_FAIL(B2O_EARG, "null argument");
   double *base = qn_base(q, which);
   if (!base || k0 < 0 || k0 >= q->mem) B2O_FAIL(B2O_EARG, "no such column (which=%d, k0=%d)", which, k0);
-  B2O_CUDA(cudaMemcpyAsync(dst, q->col(base, k0), (size_t)q->n * sizeof(double), cudaMemcpyDeviceToDevice, q->ctx->stream));
+  B2O_CUDA(cudaMemcpyAsync(dst, q->colv(base, k0), (size_t)q->n * (size_t)q->esize, cudaMemcpyDeviceToDevice, q->ctx->stream));
   return B2O_OK;
 }
 extern "C" int b2o_qn_set_col(b2o_qn *q, int which, int k0, const void *src) {
   if (!q || !src) B2O_FAIL(B2O_EARG, "null argument");
   double *base = qn_base(q, which);
   if (!base || k0 < 0 || k0 >= q->mem) B2O_FAIL(B2O_EARG, "no such column (which=%d, k0=%d)", which, k0);
-  B2O_CUDA(cudaMemcpyAsync(q->col(base, k0), src, (size_t)q->n * sizeof(double), cudaMemcpyDeviceToDevice, q->ctx->stream));
+  B2O_CUDA(cudaMemcpyAsync(q->colv(base, k0), src, (size_t)q->n * (size_t)q->esize, cudaMemcpyDeviceToDevice, q->ctx->stream));
   if ((q->inv_compact || q->fwd_compact) && (which == 0 || which == 1)) B2O_TRY(update_gram(q, k0));   // imported pair: refresh its Gram row/column
   q->w_dirty = true;
   return B2O_OK;
@@ -1739,3 +1767,5 @@ extern "C" int b2o_qn_set_scalars(b2o_qn *q, int insert1, double gamma, double o
   q->w_dirty = true;
   return B2O_OK;
 }
+
+#include "b2o_qn_f32.inc"

@@ -85,6 +85,14 @@ __device__ __forceinline__ double transpose_fold<4>(double (&s)[4], int lane) {
   return keep + __shfl_xor_sync(F, send, 8);   // r = lane >> 3
 }
 
+template <>
+__device__ __forceinline__ double transpose_fold<2>(double (&s)[2], int lane) {
+  const bool h16 = lane & 16;
+  const double send = h16 ? s[0] : s[1];
+  const double keep = h16 ? s[1] : s[0];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 16);   // r = lane >> 4
+}
+
 // A ring slot is handed back to the TMA producer right after its tile was copied to registers, BEFORE the arithmetic (the
 // shuffle chain is long).  ptxas then schedules the mbarrier arrive a few instructions behind LDS that are still in flight, and
 // with that schedule the block apply showed intermittent 1e-8 errors at n = 1e8 (a tile refilled under the read).  The

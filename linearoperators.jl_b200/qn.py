@@ -13,6 +13,31 @@ from .context import default_context
 from .special_operators import _vp
 
 F64 = _lib.B2O_F64
+F32 = _lib.B2O_F32
+
+
+def _qvp(op, t, what="vector"):
+    """raw device pointer of a unit-stride 1-D CUDA tensor whose dtype is the operator's element type"""
+    import torch
+    if op.eltype == torch.float64:
+        return _vp(t, what)
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.B2OError("%s must be a torch CUDA tensor (no CPU fallback)" % what)
+    if t.dtype != op.eltype:
+        raise _lib.B2OError("%s must be %s (got %s)" % (what, op.eltype, t.dtype))
+    if t.dim() != 1 or (t.numel() > 1 and t.stride(0) != 1):
+        raise _lib.B2OError("%s must be a unit-stride 1-D tensor" % what)
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _eltype_code(T):
+    """LBFGSOperator(T, n; ...) (src/lbfgs.jl:168, src/lsr1.jl:86): Float64 (default) and Float32 are built"""
+    import torch
+    if T is None or T == torch.float64 or T is float or T == np.float64:
+        return torch.float64, F64
+    if T == torch.float32 or T == np.float32:
+        return torch.float32, F32
+    raise _lib.B2OError("quasi-Newton operators are built for Float64 and Float32 (got %r)" % (T,))
 
 
 class _QNData:
@@ -41,13 +66,13 @@ class _QNData:
     def col(self, which, k0):
         """device copy of column `which` ('s','y','a','b') in 0-based ring slot k0"""
         op = self._op
-        out = op.ctx.empty(op.nrow)
-        _lib.check(op.ctx.lib.b2o_qn_get_col(op.handle, "syab".index(which), int(k0), _vp(out)))
+        out = op.ctx.empty(op.nrow, dtype=op.eltype)
+        _lib.check(op.ctx.lib.b2o_qn_get_col(op.handle, "syab".index(which), int(k0), _qvp(op, out)))
         return out
 
     def set_col(self, which, k0, src):
         op = self._op
-        _lib.check(op.ctx.lib.b2o_qn_set_col(op.handle, "syab".index(which), int(k0), _vp(src)))
+        _lib.check(op.ctx.lib.b2o_qn_set_col(op.handle, "syab".index(which), int(k0), _qvp(op, src)))
 
     def set_scalars(self, insert, scaling_factor, opnorm_upper_bound, ys, aux):
         op = self._op
@@ -61,21 +86,20 @@ class AbstractQuasiNewtonOperator(AbstractLinearOperator):
     """AbstractQuasiNewtonOperator{T} (src/qn.jl)."""
     always_allocated5 = True          # has_args5 / isallocated5 are hard-wired true (src/lbfgs.jl:101-102)
 
-    def _common(self, ctx, n, mem):
-        import torch
+    def _common(self, ctx, n, mem, T=None):
         self.ctx = ctx
-        self.eltype = torch.float64
+        self.eltype, self._dt = _eltype_code(T)
         self.nrow = self.ncol = int(n)
         self.symmetric = self.hermitian = True
         self.nprod = self.ntprod = self.nctprod = 0
         self.mem = max(int(mem), 1)
-        self.S = Storage("cuda", ctx.device)
+        self.S = Storage("cuda", ctx.device, dtype=None if self._dt == F64 else self.eltype)
         self.Mv = self.Mtu = None
         self.data = _QNData(self)
         lib, op = ctx.lib, self
 
         def prod_(res, x, a, b):
-            _lib.check(lib.b2o_qn_apply(op.handle, _vp(res), res.shape[0], _vp(x), x.shape[0], float(a), float(b)))
+            _lib.check(lib.b2o_qn_apply(op.handle, _qvp(op, res), res.shape[0], _qvp(op, x), x.shape[0], float(a), float(b)))
 
         self.prod_ = prod_
 
@@ -100,6 +124,8 @@ class AbstractQuasiNewtonOperator(AbstractLinearOperator):
         """mul!(Res::Matrix, op, X::Matrix, α, β) (src/operations.jl:34-36) in one launch per 8 right-hand sides; returns False
         (caller falls back to the column loop) unless both matrices are column-major float64 CUDA tensors."""
         import torch
+        if self._dt != F64:
+            return False                                     # Float32 operators: column loop
         for t in (res, X):
             if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.dim() == 2):
                 return False
@@ -128,15 +154,16 @@ class AbstractQuasiNewtonOperator(AbstractLinearOperator):
 
 
 class LBFGSOperator(AbstractQuasiNewtonOperator):
-    """LBFGSOperator(n; mem=5, scaling=true, damped=false, σ₂=0.99, σ₃=10.0) -- forward form, src/lbfgs.jl:168-208.
-    InverseLBFGSOperator builds the same type with inverse=True (:112-160)."""
+    """LBFGSOperator(T, n; mem=5, scaling=true, damped=false, σ₂=0.99, σ₃=10.0) -- forward form, src/lbfgs.jl:168-208.
+    InverseLBFGSOperator builds the same type with inverse=True (:112-160).  T (keyword here): torch.float64 (default) or
+    torch.float32 -- the Float32 operator keeps its state, x and res in Float32 (test/test_lbfgs.jl:162-178)."""
 
-    def __init__(self, n, mem=5, scaling=True, damped=False, sigma2=0.99, sigma3=10.0, inverse=False, compact=False, ctx=None):
+    def __init__(self, n, mem=5, scaling=True, damped=False, sigma2=0.99, sigma3=10.0, inverse=False, compact=False, ctx=None, T=None):
         ctx = ctx or default_context()
-        self._common(ctx, n, mem)
+        self._common(ctx, n, mem, T)
         self.scaling, self.damped, self.inverse = bool(scaling), bool(damped), bool(inverse)
         self.handle = ctypes.c_void_p()
-        _lib.check(ctx.lib.b2o_lbfgs_create(ctx.handle, F64, int(n), int(mem), int(scaling), int(damped), float(sigma2),
+        _lib.check(ctx.lib.b2o_lbfgs_create(ctx.handle, self._dt, int(n), int(mem), int(scaling), int(damped), float(sigma2),
                                             float(sigma3), int(inverse), ctypes.byref(self.handle)))
         self.tprod_ = self.prod_
         self.ctprod_ = self.prod_
@@ -155,14 +182,15 @@ def InverseLBFGSOperator(n, compact=False, **kw):
 
 
 class LSR1Operator(AbstractQuasiNewtonOperator):
-    """LSR1Operator(n; mem=5, scaling=true) -- src/lsr1.jl:86-113 (tprod!/ctprod! are `nothing`: inferred)."""
+    """LSR1Operator(T, n; mem=5, scaling=true) -- src/lsr1.jl:86-113 (tprod!/ctprod! are `nothing`: inferred).
+    T (keyword): torch.float64 (default) or torch.float32 (test/test_lsr1.jl:74-86)."""
 
-    def __init__(self, n, mem=5, scaling=True, ctx=None):
+    def __init__(self, n, mem=5, scaling=True, ctx=None, T=None):
         ctx = ctx or default_context()
-        self._common(ctx, n, mem)
+        self._common(ctx, n, mem, T)
         self.scaling, self.damped, self.inverse = bool(scaling), False, False
         self.handle = ctypes.c_void_p()
-        _lib.check(ctx.lib.b2o_lsr1_create(ctx.handle, F64, int(n), int(mem), int(scaling), ctypes.byref(self.handle)))
+        _lib.check(ctx.lib.b2o_lsr1_create(ctx.handle, self._dt, int(n), int(mem), int(scaling), ctypes.byref(self.handle)))
         self.tprod_ = None
         self.ctprod_ = None
 
@@ -181,7 +209,7 @@ def push_(op, s, y, *rest):
     if isinstance(op, LSR1Operator) or len(rest) == 0:
         if len(rest) != 0:
             raise TypeError("no such push! method for LSR1Operator")
-        _lib.check(lib.b2o_qn_push(op.handle, _vp(s), _vp(y), n, ctypes.byref(acc)))
+        _lib.check(lib.b2o_qn_push(op.handle, _qvp(op, s), _qvp(op, y), n, ctypes.byref(acc)))
         if isinstance(op, LSR1Operator) or (op.damped and not op.inverse):
             op.nprod += 1          # push! runs mul!(Bs, op, s) first (src/lsr1.jl:125, src/lbfgs.jl:305 through :273-277)
     elif len(rest) == 1:

@@ -909,8 +909,9 @@ def test_kron_batch_and_launch_count(lo, ctx, orc):
         lo.kron(A[:, :-1].contiguous(), B, ctx=ctx)                                  # dims must be multiples of 8
 
 
+@pytest.mark.parametrize("tma_stores", [0, 1])
 @pytest.mark.parametrize("dims,nb", [((512, 512, 512, 512), 3), ((264, 200, 392, 328), 2), ((128, 64, 256, 192), 1), ((320, 520, 264, 136), 2)])
-def test_kron_pair_kernel_vs_oracle(lo, ctx, orc, dims, nb):
+def test_kron_pair_kernel_vs_oracle(lo, ctx, orc, dims, nb, tma_stores):
     """The cta_group::2 pair kernel (256-row units, 256-column pair tiles; picked automatically for many right-hand sides, forced
     here with tile_m = 256) against the Float64 oracle: full tiles, ragged rows / columns / K (zero-filled boxes, clipped
     stores), a half of the pair tile that lies entirely outside the matrix, both directions, both result types, beta != 0."""
@@ -926,6 +927,7 @@ def test_kron_pair_kernel_vs_oracle(lo, ctx, orc, dims, nb):
     K = lo.kron(A, B, max_batch=4, ctx=ctx)
     Kref = lo.kron(A, B, max_batch=4, ctx=ctx)               # the single-CTA kernel on the same inputs
     K.set_option("tile_m", 256)
+    K.set_option("pair_tma_stores", tma_stores)              # epilogue: plain coalesced stores (default) or TMA stores
     l0 = ctx.launch_count()
     R32 = K.apply_batch(X, res=torch.empty((nb, m * p), dtype=torch.float32, device=dev_))
     assert ctx.launch_count() - l0 == 1

@@ -1,0 +1,120 @@
+"""GPU parity for the Float32 quasi-Newton operators (LBFGSOperator(Float32, n), InverseLBFGSOperator(Float32, n),
+LSR1Operator(Float32, n); test/test_lbfgs.jl:162-178, test/test_lsr1.jl:74-86): the Float32 instantiations of the persistent
+TMA-ring kernels against the numpy Float32 restatement (oracle/oracle_f32.py).  Elementwise statements are the same Float32
+operations on both sides; inner products are accumulated in double on both sides in different orders and rounded to Float32,
+so parity is to Float32 rounding: norm-wise relative <= 1e-5 (L-BFGS), <= 1e-4 (L-SR1 recurrences)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    d = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / (d if d > 0 else 1.0)
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def f32(ctx, n, seed, lo=0.0, hi=1.0):
+    import torch
+    return ctx.fill_uniform(ctx.empty(n, dtype=torch.float32), seed, lo, hi)
+
+
+def test_reference_precision_testset_float32(lo, ctx):
+    """test/test_lbfgs.jl:162-178 and test/test_lsr1.jl:74-86 for T = Float32, statement by statement"""
+    import torch
+    n, mem = 10, 5
+    dev = "cuda:%d" % ctx.device
+    B = lo.LBFGSOperator(n, mem=mem, T=torch.float32, ctx=ctx)
+    H = lo.InverseLBFGSOperator(n, mem=mem, T=torch.float32, ctx=ctx)
+    L = lo.LSR1Operator(n, mem=mem, T=torch.float32, ctx=ctx)
+    v = torch.tensor([-(-1.0) ** i for i in range(1, n + 1)], dtype=torch.float32, device=dev)
+    for op in (B, H, L):
+        assert np.array_equal(host(op * v), host(v))                       # identity before the first push
+        s, y = torch.ones(n, dtype=torch.float32, device=dev), torch.ones(n, dtype=torch.float32, device=dev)
+        lo.push_(op, s, y)
+        assert lo.eltype(op) == torch.float32
+        r = op * v
+        assert r.dtype == torch.float32 and r.shape == (n,)
+    with pytest.raises(lo.B2OError):
+        lo.push_(B, torch.ones(n, dtype=torch.float64, device=dev), torch.ones(n, dtype=torch.float64, device=dev))   # wrong element type
+    with pytest.raises(lo.B2OError):
+        lo.diag(B)                                                           # not built for Float32
+    with pytest.raises(lo.B2OError):
+        lo.LBFGSOperator(n, mem=mem, damped=True, T=torch.float32, ctx=ctx)
+
+
+@pytest.mark.parametrize("kind", ["lbfgs", "inverse", "lsr1"])
+@pytest.mark.parametrize("n,mem,npush", [(10, 3, 2), (1000, 5, 7), (4097, 5, 5), (100003, 10, 13), (75776, 3, 3)])
+def test_f32_push_and_apply_vs_numpy_oracle(lo, ctx, kind, n, mem, npush):
+    import torch
+    import oracle_f32 as o32
+    if kind == "lbfgs":
+        op, o = lo.LBFGSOperator(n, mem=mem, T=torch.float32, ctx=ctx), o32.LBFGS32(n, mem)
+    elif kind == "inverse":
+        op, o = lo.InverseLBFGSOperator(n, mem=mem, T=torch.float32, ctx=ctx), o32.LBFGS32(n, mem, inverse=True)
+    else:
+        op, o = lo.LSR1Operator(n, mem=mem, T=torch.float32, ctx=ctx), o32.LSR1_32(n, mem)
+    tol = 1e-5 if kind != "lsr1" else 1e-4
+    for i in range(npush):
+        s = f32(ctx, n, 100 + i)
+        y = (s + 0.1 * f32(ctx, n, 200 + i)) if kind != "lsr1" else f32(ctx, n, 200 + i, -0.5, 1.0)
+        lo.push_(op, s, y)
+        acc = o.push(host(s), host(y))
+        assert bool(op.last_push_accepted) == bool(acc)
+    ins, gamma, ub, ys, aux = op.data._scalars()
+    assert ins == o.insert
+    assert abs(gamma - float(o.gamma)) <= 1e-6 * abs(float(o.gamma))
+    assert np.allclose(ys, o.ys, rtol=1e-6, atol=0)
+    assert abs(ub - float(o.opnorm_upper_bound)) <= 1e-4 * abs(float(o.opnorm_upper_bound))
+    for k in range(mem):
+        assert np.array_equal(host(op.data.col("s", k)), o.s[k]) and np.array_equal(host(op.data.col("y", k)), o.y[k])
+        if kind != "inverse":
+            assert rel(host(op.data.col("a", k)), o.a[k]) <= tol, (k, rel(host(op.data.col("a", k)), o.a[k]))
+        if kind == "lbfgs":
+            assert rel(host(op.data.col("b", k)), o.b[k]) <= 1e-6
+    x, r0 = f32(ctx, n, 7), f32(ctx, n, 8)
+    l0 = ctx.launch_count()
+    res = op * x
+    assert ctx.launch_count() - l0 == 1                                     # ONE persistent launch per apply
+    assert res.dtype == torch.float32
+    assert rel(host(res), o.apply(host(x))) <= tol, rel(host(res), o.apply(host(x)))
+    out = r0.clone()
+    lo.mul_(out, op, x, -0.75, 0.5)                                          # 5-arg form
+    assert rel(host(out), o.apply(host(x), -0.75, 0.5, res=host(r0))) <= tol
+    # unaligned views (4-byte aligned only): same values
+    big = torch.empty(n + 3, dtype=torch.float32, device=x.device)
+    big[1:n + 1] = x
+    out2 = torch.empty(n + 3, dtype=torch.float32, device=x.device)
+    lo.mul_(out2[3:], op, big[1:n + 1])
+    assert np.array_equal(host(out2[3:]), host(res))
+    assert np.array_equal(host(op * x), host(res))                           # run-to-run bit determinism
+    # a pair with non-positive curvature is rejected and leaves the state alone (src/lbfgs.jl:281)
+    if kind != "lsr1":
+        lo.push_(op, x, -x)
+        assert not op.last_push_accepted
+        assert np.array_equal(host(op * x), host(res))
+    lo.reset_(op)                                                            # reset!: identity again
+    assert np.array_equal(host(op * x), host(x))
+
+
+def test_f32_secant_equation_and_inverse_pair_on_gpu(lo, ctx):
+    """the reference's predicates (test/test_lbfgs.jl:45-52) on the Float32 CUDA path: B s = y, H y = s, H (B x) = x"""
+    import torch
+    n, mem = 50000, 6
+    B = lo.LBFGSOperator(n, mem=mem, T=torch.float32, ctx=ctx)
+    H = lo.InverseLBFGSOperator(n, mem=mem, T=torch.float32, ctx=ctx)
+    for i in range(9):
+        s = f32(ctx, n, 100 + i)
+        y = s + 0.1 * f32(ctx, n, 200 + i)
+        lo.push_(B, s, y)
+        lo.push_(H, s, y)
+        assert rel(host(B * s), host(y)) <= 2e-5
+        assert rel(host(H * y), host(s)) <= 2e-5
+    x = f32(ctx, n, 9)
+    assert rel(host(H * (B * x)), host(x)) <= 1e-4
+    assert B.apply_bytes() == (4 * mem + 3) * 4.0 * n                         # half the bytes of the Float64 operator

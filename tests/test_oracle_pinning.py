@@ -509,3 +509,67 @@ def test_external_column_oracle_is_the_resident_one():
         if not inverse:      # a_k.x, b_k.x oldest -> newest
             k = (o.insert - 1) % mem
             assert d[0] == orc.dot(o.col("a", k), x) and d[1] == orc.dot(o.col("b", k), x)
+
+
+# ---------------------------------------------------------------- Float32 quasi-Newton restatement (oracle/oracle_f32.py)
+def _f32_pairs(n, k, lsr1=False):
+    rng = np.random.default_rng(5)
+    out = []
+    for _ in range(k):
+        s = rng.random(n).astype(np.float32)
+        y = (s + 0.1 * rng.random(n)).astype(np.float32) if not lsr1 else (rng.random(n) * 1.5 - 0.5).astype(np.float32)
+        out.append((s, y))
+    return out
+
+
+def test_f32_precision_predicates_of_the_reference():
+    """test/test_lbfgs.jl:162-178, test/test_lsr1.jl:74-86 for T = Float32: s = y = ones, v = (-1)^i; eltype(B*v) == T, and
+    the operator is the identity before the first push (test/test_lbfgs.jl:21-27)."""
+    import oracle_f32 as o32
+    n, mem = 10, 5
+    v = np.array([-(-1.0) ** i for i in range(1, n + 1)], dtype=np.float32)
+    for op in (o32.LBFGS32(n, mem), o32.LBFGS32(n, mem, inverse=True), o32.LSR1_32(n, mem)):
+        assert np.array_equal(op.apply(v), v)
+        op.push(np.ones(n, np.float32), np.ones(n, np.float32))
+        assert op.apply(v).dtype == np.float32
+
+
+def test_f32_secant_equation_and_inverse_pair():
+    """B_{k+1} s_k = y_k, H_{k+1} y_k = s_k and H·B = I (test/test_lbfgs.jl:45-52 predicate) hold to Float32 accuracy"""
+    import oracle_f32 as o32
+    n, mem = 40, 5
+    B, H, L = o32.LBFGS32(n, mem), o32.LBFGS32(n, mem, inverse=True), o32.LSR1_32(n, mem)
+    for (s, y), (sl, yl) in zip(_f32_pairs(n, 8), _f32_pairs(n, 8, lsr1=True)):
+        assert B.push(s, y) and H.push(s, y)
+        L.push(sl, yl)
+        assert np.linalg.norm(B.apply(s) - y) <= 2e-5 * np.linalg.norm(y)
+        assert np.linalg.norm(H.apply(y) - s) <= 2e-5 * np.linalg.norm(s)
+    x = np.random.default_rng(6).random(n).astype(np.float32)
+    assert np.linalg.norm(H.apply(B.apply(x)) - x) <= 1e-4 * np.linalg.norm(x)
+    assert not B.push(x, -x)                                                 # non-positive curvature is rejected  :281
+
+
+def test_f32_restatement_agrees_with_the_float64_oracle():
+    import oracle as orc
+    import oracle_f32 as o32
+    orc.build()
+    n, mem = 200, 4
+    for inverse in (False, True):
+        a, b = o32.LBFGS32(n, mem, inverse=inverse), orc.LBFGS(n, mem=mem, inverse=inverse)
+        for s, y in _f32_pairs(n, 6):
+            a.push(s, y)
+            b.push(s.astype(np.float64), y.astype(np.float64))
+        x = np.random.default_rng(7).random(n).astype(np.float32)
+        r0 = np.random.default_rng(8).random(n).astype(np.float32)
+        ref = r0.astype(np.float64)
+        b.apply(x.astype(np.float64), -0.5, 2.0, res=ref)
+        got = a.apply(x, -0.5, 2.0, res=r0)
+        assert np.linalg.norm(got - ref) <= 2e-5 * np.linalg.norm(ref)
+    a, b = o32.LSR1_32(n, mem), orc.LSR1(n, mem=mem)
+    for s, y in _f32_pairs(n, 6, lsr1=True):
+        a.push(s, y)
+        b.push(s.astype(np.float64), y.astype(np.float64))
+    x = np.random.default_rng(7).random(n).astype(np.float32)
+    ref = np.empty(n)
+    b.apply(x.astype(np.float64), 1.0, 0.0, res=ref)
+    assert np.linalg.norm(a.apply(x) - ref) <= 1e-3 * np.linalg.norm(ref)     # SR1 recurrences amplify Float32 rounding

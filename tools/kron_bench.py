@@ -36,7 +36,7 @@ An, Bn, xn = mk_np(11, (m, m)), mk_np(12, (m, m)), mk_np(13, (m * m,))
 A, B, x = to_dev(An), to_dev(Bn), to_dev(xn)
 ref = np.empty(m * m)
 orc.kron_(ref, An, Bn, xn)
-K = lo.kron(A, B, max_batch=148, ctx=ctx)
+K = lo.kron(A, B, max_batch=296, ctx=ctx)
 res = torch.empty(m * m, dtype=torch.bfloat16, device="cuda")
 r32 = torch.empty(m * m, dtype=torch.float32, device="cuda")
 fl = K.flops()
@@ -151,12 +151,13 @@ K.set_option("tile_m", 0)
 K.set_option("cluster", 0)
 K.set_option("tile_n", 0)
 # ---- how the two kernels scale with the number of right-hand sides (pair kernel: 256-row units on 74 CTA pairs)
-for nbv in (8, 16, 32, 37, 64, 74, 128, 148):
+for nbv in (16, 32, 64, 74, 148, 296):
     Xv = to_dev(mk_np(15, (nbv, m * m)))
     Rv = torch.empty((nbv, m * m), dtype=torch.bfloat16, device="cuda")
     row = {"case": "EXTRA: right-hand-side sweep", "nb": nbv}
-    for name, bm in (("pair_256", 256), ("single_cta_128", 128)):
+    for name, bm in (("pair_256", 256), ("pair_256_tma_stores", 256), ("single_cta_128", 128)):
         try:
+            K.set_option("pair_tma_stores", 1 if name.endswith("tma_stores") else 0)
             K.set_option("tile_m", bm)
             K.set_option("tile_n", 128 if bm == 128 else 0)
             K.set_option("cluster", 2 if bm == 128 else 0)
