@@ -145,6 +145,10 @@ int b2o_extend_apply(b2o_index *ix, int dtype, void *res, int64_t res_len, const
 int b2o_diagqn_push(b2o_ctx *ctx, int kind, void *d, int64_t d_len, const void *s, const void *y, int64_t n);
 
 /* ---- quasi-Newton operators (src/lbfgs.jl, src/lsr1.jl) ---------------------------------- */
+/* dtype: B2O_F64, or B2O_F32 (T = Float32, test/test_lbfgs.jl:162-178, test/test_lsr1.jl:74-86): state columns, x and res are then
+ * Float32 (4-byte aligned), every elementwise statement runs in Float32, inner products are accumulated in double and rounded to
+ * Float32.  Float32 handles support create / push (plain) / apply / reset / get_col / set_col / scalars / apply_bytes on one GPU;
+ * damped push, diag, solve_shifted, the compact modes, apply_multi and apply_host return B2O_EUNSUPPORTED for them. */
 /* LBFGSOperator(T,n;mem,scaling,damped,σ₂,σ₃) :168-208 (inverse=0) / InverseLBFGSOperator :112-160 (inverse=1) */
 int b2o_lbfgs_create(b2o_ctx *ctx, int dtype, int64_t n, int mem, int scaling, int damped, double sigma2,
                      double sigma3, int inverse, b2o_qn **out);
@@ -158,8 +162,10 @@ int b2o_qn_apply_host(b2o_qn *op, void *res_host, const void *x_host, int64_t le
 /* mul!(Res::Matrix, op, X::Matrix, α, β) (src/operations.jl:34-36): Res, X are column-major n x nrhs
  * device matrices with leading dimensions ldr, ldx (>= n).  Extension: every column of Res equals b2o_qn_apply of the matching
  * column of X (to reduction-order rounding), but each state column is streamed once per 8 right-hand sides:
- * (2*ncols + 3*nrhs)*8*n algorithmic bytes per pass.  Two-loop inverse handles and NCCL (non-mailbox) partitions run column by
- * column. */
+ * (2*ncols + 3*nrhs)*8*n algorithmic bytes per pass.  Two-loop inverse handles run the BLOCK two-loop recursion: the update and
+ * dot columns of every sweep are staged once for up to 8 right-hand sides ((4*nrhs + 4)*A + nrhs vector passes instead of
+ * nrhs*(8*A + 1)), results bit-identical to b2o_qn_apply per column; its nrhs work vectors are allocated on the first call.
+ * Row-partitioned two-loop handles and NCCL (non-mailbox) partitions run column by column. */
 int b2o_qn_apply_multi(b2o_qn *op, void *res, int64_t ldr, const void *x, int64_t ldx, int64_t len, int nrhs, double alpha,
                        double beta);
 /* push!(op,s,y) src/lbfgs.jl:269-287, src/lsr1.jl:119-184.  *accepted = 0 when the pair is rejected
@@ -238,12 +244,14 @@ int b2o_kron_destroy(b2o_kron *k);
  * res_dtype: B2O_BF16 (the reference's promoted element type; the final rounding alone is 2^-9 relative) or B2O_F32.
  * One plain clustered launch (a cluster of CTAs per 128-row block, no grid-wide dependency): multicast TMA -> tcgen05.mma (fp32
  * accumulate in TMEM) -> bf16 hi/lo intermediate (TMA store, stays in L2, published cluster-wide through an mbarrier) ->
- * tcgen05.mma -> TMA store of the result. */
+ * tcgen05.mma -> TMA store of the result.  With many right-hand sides (nb * ceil(M/256) >= half the SM count) the launch is the
+ * cta_group::2 kernel instead: CTA pairs, 256 x 256 pair tiles, 256-row units, Y handed over inside each CTA. */
 int b2o_kron_apply(b2o_kron *k, int trans, void *res, int res_dtype, int64_t res_len, const void *x, int64_t x_len, int nb,
                    double alpha, double beta);
 int b2o_kron_flops(b2o_kron *k, int nb, double *flops);
-/* tuning overrides: "cluster" (0 auto | 1, 2, 4, 8, 16 CTAs per unit), "tile_m" (0 auto | 64, 128 rows per unit),
- * "tile_n" (0 auto | 32, 64, 128 columns per CTA tile) */
+/* tuning overrides: "cluster" (0 auto | 1, 2, 4, 8, 16 CTAs per unit), "tile_m" (0 auto | 64, 128 rows per unit | 256 = force the
+ * cta_group::2 pair kernel), "tile_n" (0 auto | 32, 64, 128 columns per CTA tile), "pair_tma_stores" (pair kernel epilogue:
+ * 1 TMA stores -- default, 0 plain stores) */
 int b2o_kron_set_option(b2o_kron *k, const char *key, int64_t value);
 /* measurement aid: an EMPTY kernel launched with a kron configuration's grid, cluster size and dynamic shared memory, so the launch
  * overhead inside an event-timed kron figure can be stated (honours the ctx option "time_kernels") */

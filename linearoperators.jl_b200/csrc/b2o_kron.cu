@@ -913,7 +913,8 @@ extern "C" int b2o_kron_apply(b2o_kron *k, int trans, void *res, int res_dtype, 
     cluster = 2;
   }
   // enough 256-row units to keep every TPC busy and tiles wide enough to fill the 256-column pair MMA: the cta_group::2 kernel
-  bool pair = !k->force_bm && M >= 256 && std::min(N1, N2) >= 192 && (int64_t)nb * ((M + 255) / 256) >= c->num_sms / 2;
+  // (measured crossover at 512^3: 16 right-hand sides 31 vs 26 us, 32: 33 vs 41 us)
+  bool pair = !k->force_bm && M >= 256 && std::min(N1, N2) >= 192 && (int64_t)nb * ((M + 255) / 256) >= c->num_sms / 3;
   if (k->force_bm == 256) pair = true;
   if (k->force_bm && !pair) BM = k->force_bm;
   if (k->force_bn) BN = k->force_bn;

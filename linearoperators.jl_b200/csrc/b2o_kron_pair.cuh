@@ -18,6 +18,15 @@
 //   epilogue = 32-column chunks through two 16 KB staging buffers -> TMA stores (Y as a bf16 hi/lo pair, the result as bf16 /
 //              fp32); the peer's epilogue warps release an accumulator with a remote arrive on the leader's barrier.
 // Units of a cluster are software-pipelined like in kron_cluster_kernel: GEMM 1 of unit i+1 runs before GEMM 2 of unit i.
+// Measured (profiles/r2_kron.jsonl, r2_kron_pair_timeline_v1.jsonl): 64 right-hand sides 54 us = 636 TFLOP/s algorithmic, 954 issued
+// (single-CTA kernel: 80 us); tensor pipe 55 % of active cycles.  What bounds it now: with all 148 SMs streaming operands the chip
+// sits at the L2 -> SM ceiling (a GEMM 1 tile takes 3.7 us for 256 KB per CTA = 10.2 TB/s chip-wide, a GEMM 2 tile 5.2 us for
+// 384 KB = 10.9 TB/s; ~6300 B/clk x 1.7 GHz), i.e. ~19.5 us of MMA issue per unit against 12.9 us at the nominal tensor rate, and
+// the epilogue of a tile (8 chunks x ~0.55 us of TMEM load, conversion, proxy fence, barrier, store issue) is as long as the MMAs
+// of the next tile, so the two-accumulator hand-over adds ~7 us per unit.  Tried and kept as evidence: plain stores instead of
+// TMA stores (option pair_tma_stores = 0: 76 us), two epilogue warp groups draining alternate chunks (56 us: the per-chunk latency
+// rises as much as the concurrency gains -- profiles/r2_kron_pair_two_epilogue_groups*.jsonl).  Next lever: multicast the shared
+// B operand across the two pairs of one right-hand side (-20 % L2 reads).
 // Every wait carries a %globaltimer watchdog (trap after 4 s): a protocol error fails loudly instead of hanging the GPU.
 #pragma once
 
