@@ -66,6 +66,24 @@ def test_kron_uses_tcgen05_and_tensor_tma(sass):
         assert "R2UR.BROADCAST" not in text, name
 
 
+def test_kron_pair_kernel_uses_cta_group_2(sass):
+    """the batched kron kernel: tcgen05.mma.cta_group::2 issued back to back, both CTAs' tensor-map loads completing on the
+    leader's barrier (.2CTA), multicast commits to both CTAs, no waterfall loop around the issue"""
+    ks = _of(sass, r"kron_pair_kernel")
+    assert len(ks) == 1
+    (name, ins), = ks.items()
+    text = "\n".join(ins)
+    assert text.count("UTCHMMA.2CTA") == 12, name              # 4 (GEMM 1) + 8 (GEMM 2: hi and lo) per ring item
+    assert "UTCHMMA" not in text.replace("UTCHMMA.2CTA", ""), name
+    assert text.count("UTMALDG.2D.2CTA") + text.count("UTMALDG.3D.2CTA") == 5, name
+    assert text.count("UTCBAR.2CTA.MULTICAST") >= 5, name
+    assert "UTMASTG" in text and "LDTM" in text, name
+    assert "R2UR.BROADCAST" not in text, name
+    mma = [i for i, x in enumerate(ins) if "UTCHMMA.2CTA" in x]
+    runs = sorted(b - a for a, b in zip(mma, mma[1:]))
+    assert runs[len(runs) // 2] <= 4, runs                     # the MMAs of an item are issued back to back
+
+
 def _dest_regs(instr):
     """registers written by an LDS.{64,128}"""
     m = re.match(r"LDS(?:\.(64|128))?\s+R(\d+)", instr)
@@ -90,7 +108,7 @@ def _src_regs(instr):
 def test_ring_slot_release_follows_the_reads_of_the_slot(sass):
     """between the last LDS.128 of a column tile and the consumer's mbarrier arrive (SYNCS.ARRIVE...A1T0) there is an
     instruction that consumes registers of that load -- so the arrive cannot issue while the load is in flight"""
-    ks = _of(sass, r"qn_compact_kernel|qn_twoloop_kernel|qn_multi_kernel")
+    ks = _of(sass, r"qn_compact_kernel|qn_twoloop_kernel|qn_multi_kernel|qn_twoloop_multi_kernel")
     checked, bad = 0, []
     for name, ins in ks.items():
         for i, instr in enumerate(ins):

@@ -315,6 +315,33 @@ def main():
             del Xb, X, Res
             torch.cuda.empty_cache()
         return
+    if only == ["f32"]:
+        # Float32 quasi-Newton operators: the Float32 instantiations of the persistent kernels (half the bytes per row)
+        f32 = lambda nn, seed: ctx.fill_uniform(ctx.empty(nn, dtype=torch.float32), seed)
+        for nn in (n, 2 * n):
+            x, res = f32(nn, 7), ctx.empty(nn, dtype=torch.float32)
+            for name, mk, m, per_row in (("LBFGSOperator(Float32, n=%d, mem=10)" % nn, lambda: lo.LBFGSOperator(nn, mem=10, T=torch.float32, ctx=ctx), 10, 4 * 10 + 3),
+                                         ("InverseLBFGSOperator(Float32, n=%d, mem=20)" % nn, lambda: lo.InverseLBFGSOperator(nn, mem=20, T=torch.float32, ctx=ctx), 20, 8 * 20 + 2),
+                                         ("LSR1Operator(Float32, n=%d, mem=10)" % nn, lambda: lo.LSR1Operator(nn, mem=10, T=torch.float32, ctx=ctx), 10, 2 * 10 + 3)):
+                op = mk()
+                tpush = 0.0
+                for i in range(m):
+                    s = f32(nn, 100 + i)
+                    y = s + 0.1 * f32(nn, 200 + i) if "LSR1" not in name else ctx.fill_uniform(ctx.empty(nn, dtype=torch.float32), 200 + i, -0.5, 1.0)
+                    torch.cuda.synchronize()
+                    t1 = time.perf_counter()
+                    lo.push_(op, s, y)
+                    torch.cuda.synchronize()
+                    tpush = time.perf_counter() - t1
+                del s, y
+                ms = timeit(lambda: lo.mul_(res, op, x), 20)
+                line(name + " apply", ms, per_row * 4.0 * nn, applies_per_s=round(1e3 / ms, 1), last_push_ms=round(tpush * 1e3, 2),
+                     float64_equivalent_GBps=round(per_row * 8.0 * nn / ms / 1e6, 1))
+                del op
+                torch.cuda.empty_cache()
+            del x, res
+            torch.cuda.empty_cache()
+        return
     if only == ["invc"]:
         v, res = ctx.uniform(n, 7), ctx.empty(n)
         for m in (10, 20):

@@ -40,9 +40,10 @@ def main():
         lo.mul_(r, g, x[:n].clone())
         if kind in ("fwd", "lsr1"):
             lo.diag(g)
-        if kind != "inv":
-            # block apply (NR = 4 and NR = 8 kernels) and, for the forward form, the streamed a_k rebuild ran in push_ above
-            for k in (3, 8):
+        if True:
+            # block apply (NR = 2, 4, 8 kernels; two-loop inverse: the block recursion with 4 / 8 columns) and, for the forward
+            # form, the streamed a_k rebuild ran in push_ above
+            for k in (2, 3, 8):
                 Xb = torch.empty((k, n + 2), dtype=torch.float64, device="cuda")
                 for j in range(k):
                     Xb[j, :n] = ctx.uniform(n, 300 + j)
@@ -96,6 +97,29 @@ def main():
         lo.mul_(r32, K, xk)
         lo.mul_(r32, K, xk, 2.0, -0.5)                                               # beta != 0: direct-store epilogue
         K.apply_batch(torch.stack([xk, xk]).contiguous())
+    # the cta_group::2 pair kernel (ragged rows / columns / K, both store paths, beta != 0)
+    A2 = torch.randn(264, 200, device="cuda").to(torch.bfloat16)
+    B2 = torch.randn(392, 328, device="cuda").to(torch.bfloat16)
+    K2 = lo.kron(A2, B2, max_batch=2, ctx=ctx)
+    K2.set_option("tile_m", 256)
+    X2 = torch.randn(2, 200 * 328, device="cuda").to(torch.bfloat16)
+    for tma in (1, 0):
+        K2.set_option("pair_tma_stores", tma)
+        R2 = K2.apply_batch(X2)
+        K2.apply_batch(X2, alpha=2.0, beta=-0.5, res=R2)
+        K2.apply_batch(R2, trans=True, res=torch.empty((2, 200 * 328), dtype=torch.float32, device="cuda"))
+    # Float32 quasi-Newton operators (Float32 instantiations of the streaming kernels, 4096-row tiles)
+    n32 = 3 * 4096 + 77
+    f32 = lambda seed, lo_=0.0, hi_=1.0: ctx.fill_uniform(ctx.empty(n32, dtype=torch.float32), seed, lo_, hi_)
+    for kind in ("fwd", "inv", "lsr1"):
+        g = lo.LSR1Operator(n32, mem=3, T=torch.float32, ctx=ctx) if kind == "lsr1" else lo.LBFGSOperator(n32, mem=3, inverse=kind == "inv", T=torch.float32, ctx=ctx)
+        for i in range(4):
+            s = f32(100 + i)
+            lo.push_(g, s, s + 0.1 * f32(200 + i) if kind != "lsr1" else f32(200 + i, -0.5, 1.0))
+        r32v = f32(8)
+        lo.mul_(r32v, g, f32(7), 1.5, -0.5)
+        big = torch.zeros(n32 + 3, dtype=torch.float32, device="cuda")
+        lo.mul_(big[3:], g, f32(7))                                                      # 4-byte aligned views
     torch.cuda.synchronize()
     print("SANITIZE_OK launches=%d" % ctx.launch_count())
 
