@@ -14,6 +14,9 @@ import LinearAlgebra: diag
 
 const libb2o = get(ENV, "LIBB2O", "libb2o.so")
 const B2O_F64 = Cint(0)
+const B2O_F32 = Cint(1)
+b2o_dtype(::Type{Float64}) = B2O_F64
+b2o_dtype(::Type{Float32}) = B2O_F32   # quasi-Newton operators (test/test_lbfgs.jl:162-178), dense / sparse matrix leaves
 
 last_error() = unsafe_string(ccall((:b2o_last_error, libb2o), Cstring, ()))
 function check(rc::Cint)
@@ -154,20 +157,23 @@ mutable struct B200LBFGSOperator{T, F} <: AbstractQuasiNewtonOperator{T}
   nctprod::Int
 end
 
-function B200LBFGSOperator(n::Int; mem::Int = 5, scaling::Bool = true, damped::Bool = false, σ₂ = 0.99, σ₃ = 10.0,
-                           inverse::Bool = false, c = ctx())
+# LBFGSOperator(T, n; ...) src/lbfgs.jl:168: T = Float64 or Float32 (Float32: create / push! / mul! / reset!, see include/b2o.h)
+B200LBFGSOperator(n::Int; kw...) = B200LBFGSOperator(Float64, n; kw...)
+function B200LBFGSOperator(::Type{T}, n::Int; mem::Int = 5, scaling::Bool = true, damped::Bool = false, σ₂ = 0.99, σ₃ = 10.0,
+                           inverse::Bool = false, c = ctx()) where {T <: Union{Float64, Float32}}
   h = Ref{Ptr{Cvoid}}(C_NULL)
   check(ccall((:b2o_lbfgs_create, libb2o), Cint,
     (Ptr{Cvoid}, Cint, Int64, Cint, Cint, Cint, Cdouble, Cdouble, Cint, Ptr{Ptr{Cvoid}}),
-    c.handle, B2O_F64, n, mem, scaling, damped, σ₂, σ₃, inverse, h))
+    c.handle, b2o_dtype(T), n, mem, scaling, damped, σ₂, σ₃, inverse, h))
   handle = h[]
   prod! = (res, x, α, β) -> check(ccall((:b2o_qn_apply, libb2o), Cint,
     (Ptr{Cvoid}, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, Int64, Cdouble, Cdouble),
     handle, res, length(res), x, length(x), α, β))
-  op = B200LBFGSOperator{Float64, typeof(prod!)}(n, n, true, true, prod!, prod!, prod!, inverse, handle, c, 0, 0, 0)
+  op = B200LBFGSOperator{T, typeof(prod!)}(n, n, true, true, prod!, prod!, prod!, inverse, handle, c, 0, 0, 0)
   finalizer(o -> ccall((:b2o_qn_destroy, libb2o), Cint, (Ptr{Cvoid},), o.handle), op)
 end
-B200InverseLBFGSOperator(n::Int; kw...) = B200LBFGSOperator(n; inverse = true, kw...)
+B200InverseLBFGSOperator(n::Int; kw...) = B200LBFGSOperator(Float64, n; inverse = true, kw...)
+B200InverseLBFGSOperator(::Type{T}, n::Int; kw...) where {T} = B200LBFGSOperator(T, n; inverse = true, kw...)
 
 has_args5(::B200LBFGSOperator) = true
 isallocated5(::B200LBFGSOperator) = true
@@ -237,15 +243,16 @@ mutable struct B200LSR1Operator{T, F} <: AbstractQuasiNewtonOperator{T}
   ntprod::Int
   nctprod::Int
 end
-function B200LSR1Operator(n::Int; mem::Int = 5, scaling::Bool = true, c = ctx())
+B200LSR1Operator(n::Int; kw...) = B200LSR1Operator(Float64, n; kw...)
+function B200LSR1Operator(::Type{T}, n::Int; mem::Int = 5, scaling::Bool = true, c = ctx()) where {T <: Union{Float64, Float32}}
   h = Ref{Ptr{Cvoid}}(C_NULL)
   check(ccall((:b2o_lsr1_create, libb2o), Cint, (Ptr{Cvoid}, Cint, Int64, Cint, Cint, Ptr{Ptr{Cvoid}}),
-    c.handle, B2O_F64, n, mem, scaling, h))
+    c.handle, b2o_dtype(T), n, mem, scaling, h))
   handle = h[]
   prod! = (res, x, α, β) -> check(ccall((:b2o_qn_apply, libb2o), Cint,
     (Ptr{Cvoid}, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, Int64, Cdouble, Cdouble),
     handle, res, length(res), x, length(x), α, β))
-  op = B200LSR1Operator{Float64, typeof(prod!)}(n, n, true, true, prod!, nothing, nothing, handle, c, 0, 0, 0)
+  op = B200LSR1Operator{T, typeof(prod!)}(n, n, true, true, prod!, nothing, nothing, handle, c, 0, 0, 0)
   finalizer(o -> ccall((:b2o_qn_destroy, libb2o), Cint, (Ptr{Cvoid},), o.handle), op)
 end
 has_args5(::B200LSR1Operator) = true
