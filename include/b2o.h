@@ -69,6 +69,8 @@ int b2o_ctx_sync(b2o_ctx *ctx);
  * 1 plain rows, 2 TMA-staged tiles), "sparse_lanes" (-1 auto | 0..5: 2^k lanes per row);
  * index sets: "extend_form" (0 gather form through the inverse map when the set is dense enough, 1 always memset + scatter);
  * matrix right-hand sides of the two-loop inverse: "twoloop_block" (1 block recursion, 4 / 8 columns per sweep -- default; 0 column loop);
+ * block apply with 5..8 right-hand sides: "multi_mma" (0 the SIMT kernel -- default; 1 the FP64 tensor-core kernel, mma.sync m8n8k4:
+ * same results to a few ulp, measured slower -- 11.3 vs 10.5 ms at n = 1e8, m = 10, 8 right-hand sides);
  * memory system: "l2_fetch_granularity" (32|64|128: cudaLimitMaxL2FetchGranularity, device-wide);
  * multi-GPU: "use_mailbox" (0|1: NCCL or the in-kernel NVLink mailbox for the inner products of a connected context -- every
  * rank switches at the same point), "numa_local_host" (0|1: b2o_host_alloc prefers the GPU's NUMA node, default 1).

@@ -112,6 +112,8 @@ extern "C" int b2o_ctx_set_option(b2o_ctx *c, const char *key, int64_t value) {
     c->extend_form = value != 0;
   } else if (!strcmp(key, "twoloop_block")) {
     c->twoloop_block = value != 0;
+  } else if (!strcmp(key, "multi_mma")) {
+    c->multi_mma = value != 0;
   } else if (!strcmp(key, "sparse_lanes")) {
     if (value < -1 || value > 5) B2O_FAIL(B2O_EARG, "sparse_lanes must be -1 (auto) or 0..5 (2^k lanes per row)");
     c->sparse_lanes = (int)value;

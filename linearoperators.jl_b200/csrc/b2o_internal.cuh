@@ -74,6 +74,7 @@ struct b2o_ctx_s {
   int dense_scalar = 0;  // dense-matrix leaf: force the scalar (unvectorised) kernels (testing)
   int sparse_kernel = 0; // sparse-matrix leaf: 0 / 3 software-pipelined row kernel (default), 1 plain row kernel, 2 TMA-staged tile kernel
   int extend_form = 0;   // opExtension: 0 gather form through the inverse map when the index set is dense enough, 1 always memset + scatter
+  int multi_mma = 0;     // block apply with 5..8 right-hand sides: 0 = the SIMT kernel (default: measured faster), 1 = FP64 tensor-core kernel (DMMA)
   int twoloop_block = 1; // matrix right-hand sides of the two-loop inverse: 1 = block recursion (4 / 8 columns per sweep), 0 = column by column
   int sparse_lanes = -1; // sparse-matrix leaf: force 2^k lanes per row (k = 0..5), -1 = from the mean row length
   // accounting

@@ -1,6 +1,6 @@
 // b2o_qn.cu -- LBFGSOperator / InverseLBFGSOperator / LSR1Operator handles (src/lbfgs.jl, src/lsr1.jl):
 // state, apply (persistent kernels in b2o_qn_kernels.cuh), push!, diag!, reset!, state access.
-#include "b2o_qn_multi.cuh"
+#include "b2o_qn_multi_mma.cuh"
 #include <float.h>
 #include <math.h>
 #include <algorithm>
@@ -777,6 +777,65 @@ static int multi_launch(b2o_qn *q, const CompactArgs &base, double *res, int64_t
   return st;
 }
 
+// block apply for 5..8 right-hand sides on the FP64 tensor cores (b2o_qn_multi_mma.cuh)
+static int multi_mma_launch(b2o_qn *q, const CompactArgs &base, double *res, int64_t ldr, const double *x, int64_t ldx, int nrhs) {
+  b2o_ctx *c = q->ctx;
+  constexpr int NR = 8;
+  MultiArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int i = 0; i < base.ncols; ++i) {
+    a.cols[i] = base.cols[i];
+    a.cdiv[i] = base.cdiv[i];
+  }
+  a.ncols = base.ncols;
+  a.x = x;
+  a.res = res;
+  a.ldx = ldx;
+  a.ldr = ldr;
+  a.nrhs = nrhs;
+  a.n = q->n;
+  a.ntiles = (a.n + MM_R - 1) / MM_R;
+  a.alpha = base.alpha;
+  a.beta = base.beta;
+  a.gamma = base.gamma;
+  a.scaling = base.scaling;
+  a.W = base.W;
+  a.base_div = base.base_div;
+  const int nv = a.ncols * NR;
+  LaunchCfg cfg;
+  cfg.R = MM_R;
+  cfg.group = 0;
+  cfg.stages = MM_STAGES;
+  cfg.L.ring_off = 0;
+  cfg.L.accs_off = (size_t)MM_STAGES * MM_SLOT;                                            // wacc [8 warps][ncols][8]
+  cfg.L.coef_off = cfg.L.accs_off + (size_t)B2O_CONS_WARPS * nv * sizeof(double);
+  cfg.L.bar_off = cfg.L.coef_off + (size_t)nv * sizeof(double);
+  a.landed_off = (uint32_t)(cfg.L.bar_off + (size_t)2 * MM_STAGES * sizeof(uint64_t));
+  cfg.L.total = a.landed_off + B2O_NCONS * sizeof(unsigned);
+  if (cfg.L.total > B2O_MAX_DYN_SMEM) B2O_FAIL(B2O_ECUDA, "shared memory plan does not fit");
+  int g = c->grid > 0 ? c->grid : c->num_sms;
+  g = std::min(g, c->num_sms);
+  cfg.grid = (int)std::max<int64_t>(1, std::min<int64_t>(g, a.ntiles));
+  if ((size_t)cfg.grid * nv > (size_t)B2O_MAX_GRID * B2O_MAX_COLS) B2O_FAIL(B2O_EUNSUPPORTED, "too many columns for the block apply");
+  a.partials = c->d_partials;
+  a.dots = c->d_dots;
+  a.bar = c->d_bar;
+  a.stages = MM_STAGES;
+  a.wacc_off = (uint32_t)cfg.L.accs_off;
+  a.coef_off = (uint32_t)cfg.L.coef_off;
+  a.bar_off = (uint32_t)cfg.L.bar_off;
+  a.bar_target = c->bar_base + (unsigned long long)cfg.grid;
+  b2o_mbox_fill(c, &a.mbox);
+  int st = (q->kind == 0 && (q->inverse || q->fwd_compact)) ? launch_persistent(c, qn_multi_mma_kernel<OP_INV_COMPACT>, cfg, a, true)
+           : q->kind == 0             ? launch_persistent(c, qn_multi_mma_kernel<OP_LBFGS_FWD>, cfg, a, true)
+                                      : launch_persistent(c, qn_multi_mma_kernel<OP_LSR1>, cfg, a, true);
+  if (st == B2O_OK) {
+    c->bar_base += (unsigned long long)cfg.grid;
+    if (a.mbox.nranks > 1) c->mbox_epoch += (unsigned long long)((nv + MBOX_MAXV - 1) / MBOX_MAXV);
+  }
+  return st;
+}
+
 // ------------------------------------------------------------------ block two-loop recursion (matrix right-hand sides of H)
 template <int NR>
 static int twoloop_multi_launch(b2o_qn *q, double *res, int64_t ldr, const double *x, int64_t ldx, int nrhs, double alpha, double beta) {
@@ -896,7 +955,8 @@ extern "C" int b2o_qn_apply_multi(b2o_qn *q, void *res_, int64_t ldr, const void
     const int left = nrhs - r0;
     if (can8 && left > 4) {
       const int k = std::min(left, 8);
-      B2O_TRY(multi_launch<8>(q, base, res + (int64_t)r0 * ldr, ldr, x + (int64_t)r0 * ldx, ldx, k));
+      if (c->multi_mma && base.ncols <= 8 * MM_MAXG) B2O_TRY(multi_mma_launch(q, base, res + (int64_t)r0 * ldr, ldr, x + (int64_t)r0 * ldx, ldx, k));
+      else B2O_TRY(multi_launch<8>(q, base, res + (int64_t)r0 * ldr, ldr, x + (int64_t)r0 * ldx, ldx, k));
       r0 += k;
     } else if (left > 2) {
       const int k = std::min(left, 4);

@@ -1239,6 +1239,44 @@ def test_block_apply_matches_vector_apply(lo, ctx, orc, kind, n, mem, npush, nrh
         lo.mul_(Res, op, _colmajor(ctx, n + 1, nrhs, 1))
 
 
+@pytest.mark.parametrize("kind", ["lbfgs", "lbfgs_compact", "inverse_compact", "lsr1"])
+@pytest.mark.parametrize("n,mem,npush,nrhs", [(4099, 5, 7, 8), (100003, 10, 12, 13), (30011, 4, 4, 5), (1000, 3, 2, 7)])
+def test_block_apply_dmma_kernel(lo, ctx, orc, kind, n, mem, npush, nrhs):
+    """the opt-in FP64 tensor-core block kernel (ctx option multi_mma = 1: mma.sync m8n8k4 for 5..8 right-hand sides): every column
+    equals the vector apply and the oracle; ragged column groups (10, 20, 8, 6, 3 columns), ragged rows, odd leading dimensions"""
+    if kind == "lbfgs":
+        op, o = lo.LBFGSOperator(n, mem=mem, ctx=ctx), orc.LBFGS(n, mem=mem)
+    elif kind == "lbfgs_compact":
+        op, o = lo.LBFGSOperator(n, mem=mem, compact=True, ctx=ctx), orc.LBFGS(n, mem=mem)
+    elif kind == "inverse_compact":
+        op, o = lo.InverseLBFGSOperator(n, mem=mem, compact=True, ctx=ctx), orc.LBFGS(n, mem=mem, inverse=True)
+    else:
+        op, o = lo.LSR1Operator(n, mem=mem, ctx=ctx), orc.LSR1(n, mem=mem)
+    for i in range(npush):
+        s = ctx.uniform(n, 100 + i)
+        y = s + 0.1 * ctx.uniform(n, 200 + i) if kind != "lsr1" else ctx.uniform(n, 200 + i, -0.5, 1.0)
+        lo.push_(op, s, y)
+        o.push(host(s), host(y))
+    X, R0 = _colmajor(ctx, n, nrhs, 300, 1), _colmajor(ctx, n, nrhs, 400, 1)
+    tol = 1e-12 if kind in ("lbfgs", "lsr1") else 1e-9
+    ctx.set_option("multi_mma", 1)
+    try:
+        for alpha, beta in [(1.0, 0.0), (-0.75, 0.5)]:
+            Res = _colmajor(ctx, n, nrhs, 400, 1)
+            if beta == 0:
+                Res.fill_(float("nan"))
+            lo.mul_(Res, op, X, alpha, beta)
+            for j in range(nrhs):
+                ref = host(R0[:, j]).copy()
+                o.apply(host(X[:, j]), alpha, beta, res=ref)
+                assert rel(host(Res[:, j]), ref) <= tol, (j, rel(host(Res[:, j]), ref))
+                v = ctx.empty(n).copy_(R0[:, j])
+                lo.mul_(v, op, X[:, j].contiguous(), alpha, beta)
+                assert rel(host(Res[:, j]), host(v)) <= (1e-13 if tol == 1e-12 else 1e-10)
+    finally:
+        ctx.set_option("multi_mma", 0)
+
+
 @pytest.mark.parametrize("n,mem,npush", [(1000, 5, 7), (100003, 10, 13), (75776, 3, 3)])
 def test_push_streamed_rebuild_equals_generic_passes(lo, ctx, orc, n, mem, npush):
     """push! rebuilds every a_k (src/lbfgs.jl:236-250): the streaming-kernel path (default) and the generic multi-dot +
