@@ -246,7 +246,7 @@ int b2o_kron_destroy(b2o_kron *k);
  * res_dtype: B2O_BF16 (the reference's promoted element type; the final rounding alone is 2^-9 relative) or B2O_F32.
  * One plain clustered launch (a cluster of CTAs per 128-row block, no grid-wide dependency): multicast TMA -> tcgen05.mma (fp32
  * accumulate in TMEM) -> bf16 hi/lo intermediate (TMA store, stays in L2, published cluster-wide through an mbarrier) ->
- * tcgen05.mma -> TMA store of the result.  With many right-hand sides (nb * ceil(M/256) >= half the SM count) the launch is the
+ * tcgen05.mma -> TMA store of the result.  With many right-hand sides (nb * ceil(M/256) >= a third of the SM count) the launch is the
  * cta_group::2 kernel instead: CTA pairs, 256 x 256 pair tiles, 256-row units, Y handed over inside each CTA. */
 int b2o_kron_apply(b2o_kron *k, int trans, void *res, int res_dtype, int64_t res_len, const void *x, int64_t x_len, int nb,
                    double alpha, double beta);
