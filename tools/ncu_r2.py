@@ -43,6 +43,37 @@ def main():
         R64 = torch.empty((64, m * m), dtype=torch.bfloat16, device="cuda")
         targets = [lambda: lo.mul_(r, K, xx), lambda: K.apply_batch(X64, res=R64)]
         pre = targets * 5
+    elif what == "new":
+        # second half of round 2: Float32 forward apply, block two-loop (4 RHS), block apply 8 RHS on the SIMT and on the DMMA kernel
+        f32 = lambda seed: ctx.fill_uniform(ctx.empty(n, dtype=torch.float32), seed)
+        B32 = lo.LBFGSOperator(n, mem=10, T=torch.float32, ctx=ctx)
+        for i in range(10):
+            s = f32(100 + i)
+            lo.push_(B32, s, s + 0.1 * f32(200 + i))
+        x32, r32 = f32(7), ctx.empty(n, dtype=torch.float32)
+        B = lo.LBFGSOperator(n, mem=10, ctx=ctx)
+        for i in range(10):
+            s = ctx.uniform(n, 100 + i)
+            lo.push_(B, s, s + 0.1 * ctx.uniform(n, 200 + i))
+        H = lo.InverseLBFGSOperator(n, mem=10, ctx=ctx)
+        for i in range(10):
+            s = ctx.uniform(n, 100 + i)
+            lo.push_(H, s, s + 0.1 * ctx.uniform(n, 200 + i))
+        del s
+        X8 = torch.empty((8, n), dtype=torch.float64, device="cuda")
+        for j in range(8):
+            X8[j] = ctx.uniform(n, 300 + j)
+        R8 = torch.empty((8, n), dtype=torch.float64, device="cuda")
+
+        def mma(flag, f):
+            def run():
+                ctx.set_option("multi_mma", flag)
+                f()
+                ctx.set_option("multi_mma", 0)
+            return run
+        targets = [lambda: lo.mul_(r32, B32, x32), lambda: lo.mul_(R8[:4].T, H, X8[:4].T), mma(0, lambda: lo.mul_(R8.T, B, X8.T)),
+                   mma(1, lambda: lo.mul_(R8.T, B, X8.T))]
+        pre = targets
     elif what == "index":
         k = n // 4
         v, uk = ctx.uniform(n, 7), ctx.uniform(k, 8)
