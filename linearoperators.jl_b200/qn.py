@@ -30,6 +30,19 @@ def _qvp(op, t, what="vector"):
     return ctypes.c_void_p(t.data_ptr())
 
 
+def _split_T(first, rest, T):
+    """the reference's positional form Op(T, n) beside Op(n, T=...)"""
+    if len(rest) > 1:
+        raise TypeError("expected (n) or (T, n)")
+    if len(rest) == 1:
+        if isinstance(first, (int, np.integer)):
+            raise TypeError("mem, scaling, ... are keyword arguments (src/lbfgs.jl:168); positional forms are Op(n) and Op(T, n)")
+        if T is not None:
+            raise TypeError("element type given twice")
+        return rest[0], first
+    return first, T
+
+
 def _eltype_code(T):
     """LBFGSOperator(T, n; ...) (src/lbfgs.jl:168, src/lsr1.jl:86): Float64 (default) and Float32 are built"""
     import torch
@@ -158,7 +171,8 @@ class LBFGSOperator(AbstractQuasiNewtonOperator):
     InverseLBFGSOperator builds the same type with inverse=True (:112-160).  T (keyword here): torch.float64 (default) or
     torch.float32 -- the Float32 operator keeps its state, x and res in Float32 (test/test_lbfgs.jl:162-178)."""
 
-    def __init__(self, n, mem=5, scaling=True, damped=False, sigma2=0.99, sigma3=10.0, inverse=False, compact=False, ctx=None, T=None):
+    def __init__(self, n, *args, mem=5, scaling=True, damped=False, sigma2=0.99, sigma3=10.0, inverse=False, compact=False, ctx=None, T=None):
+        n, T = _split_T(n, args, T)                          # LBFGSOperator(T, n; ...) or LBFGSOperator(n; ..., T=...)
         ctx = ctx or default_context()
         self._common(ctx, n, mem, T)
         self.scaling, self.damped, self.inverse = bool(scaling), bool(damped), bool(inverse)
@@ -173,19 +187,20 @@ class LBFGSOperator(AbstractQuasiNewtonOperator):
             self.set_option("inverse_mode" if inverse else "forward_mode", 1)
 
 
-def InverseLBFGSOperator(n, compact=False, **kw):
+def InverseLBFGSOperator(n, *args, compact=False, **kw):
     """InverseLBFGSOperator(n; mem, scaling, damped, σ₂, σ₃) (src/lbfgs.jl:112-160).  compact=True switches the apply from the
     reference's two-loop recursion to the mathematically identical compact representation (half the DRAM traffic, one
     all-reduce instead of 2m): an extension, not the reference algorithm -- rounding differs."""
     kw.pop("inverse", None)
-    return LBFGSOperator(n, inverse=True, compact=compact, **kw)
+    return LBFGSOperator(n, *args, inverse=True, compact=compact, **kw)
 
 
 class LSR1Operator(AbstractQuasiNewtonOperator):
     """LSR1Operator(T, n; mem=5, scaling=true) -- src/lsr1.jl:86-113 (tprod!/ctprod! are `nothing`: inferred).
     T (keyword): torch.float64 (default) or torch.float32 (test/test_lsr1.jl:74-86)."""
 
-    def __init__(self, n, mem=5, scaling=True, ctx=None, T=None):
+    def __init__(self, n, *args, mem=5, scaling=True, ctx=None, T=None):
+        n, T = _split_T(n, args, T)
         ctx = ctx or default_context()
         self._common(ctx, n, mem, T)
         self.scaling, self.damped, self.inverse = bool(scaling), False, False
