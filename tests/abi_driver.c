@@ -229,6 +229,61 @@ static void test_qn(void) {
   free(hs); free(hy); free(hu); free(hx); free(got); free(ref);
 }
 
+/* ---- LBFGSOperator(Float32, n) / InverseLBFGSOperator / LSR1Operator(Float32, n): test/test_lbfgs.jl:162-178, test/test_lsr1.jl:74-86.
+ * The reference's precision test pushes s = y = ones and applies to v = (-1)^i.  With s = y the updates leave the identity:
+ * forward: gamma = ys/yy = 1 and a_k == b_k bit for bit, so q + (bx b - ax a) = q exactly -> B v == v in every bit; L-SR1:
+ * y - B s = 0 rejects the pair -> identity; inverse: H = I mathematically, the two-loop recursion returns v to Float32 rounding.
+ * A closed-form check that needs no oracle. */
+static void test_qn_f32(void) {
+  const int64_t n = 10007;
+  float *hs = (float *)malloc((size_t)n * 4), *hv = (float *)malloc((size_t)n * 4), *got = (float *)malloc((size_t)n * 4);
+  void *s, *v, *res;
+  OK(b2o_malloc(ctx, (size_t)n * 4, &s));
+  OK(b2o_malloc(ctx, (size_t)n * 4, &v));
+  OK(b2o_malloc(ctx, (size_t)n * 4, &res));
+  for (int64_t i = 0; i < n; ++i) {
+    hs[i] = 1.0f;
+    hv[i] = (i & 1) ? 1.0f : -1.0f;
+  }
+  h2d(s, hs, (size_t)n * 4);
+  h2d(v, hv, (size_t)n * 4);
+  for (int kind = 0; kind < 3; ++kind) {
+    b2o_qn *op = NULL;
+    if (kind < 2) OK(b2o_lbfgs_create(ctx, B2O_F32, n, 5, 1, 0, 0.99, 10.0, kind == 1, &op));
+    else OK(b2o_lsr1_create(ctx, B2O_F32, n, 5, 1, &op));
+    OK(b2o_qn_apply(op, res, n, v, n, 1.0, 0.0));
+    d2h(got, res, (size_t)n * 4);
+    CHECK(memcmp(got, hv, (size_t)n * 4) == 0, "Float32 kind %d: identity before the first push", kind);
+    int acc = -1;
+    OK(b2o_qn_push(op, s, s, n, &acc));
+    CHECK(acc == (kind < 2 ? 1 : 0), "Float32 kind %d: push!(op, ones, ones) acceptance %d", kind, acc);
+    OK(b2o_qn_apply(op, res, n, v, n, 1.0, 0.0));
+    d2h(got, res, (size_t)n * 4);
+    if (kind != 1) {
+      CHECK(memcmp(got, hv, (size_t)n * 4) == 0, "Float32 kind %d: B v == v after push!(op, ones, ones)", kind);
+    } else {
+      double worst = 0;
+      for (int64_t i = 0; i < n; ++i) worst = fmax(worst, fabs((double)got[i] - (double)hv[i]));
+      CHECK(worst <= 1e-6, "Float32 inverse: H v = v to rounding, worst %g", worst);
+    }
+    OK(b2o_qn_apply(op, res, n, v, n, 2.0, 0.0));
+    d2h(got, res, (size_t)n * 4);
+    double worst2 = 0;
+    for (int64_t i = 0; i < n; ++i) worst2 = fmax(worst2, fabs((double)got[i] - 2.0 * (double)hv[i]));
+    CHECK(worst2 <= (kind == 1 ? 2e-6 : 0.0), "Float32 kind %d: alpha = 2, worst %g", kind, worst2);
+    double bytes = 0;
+    OK(b2o_qn_apply_bytes(op, 0.0, &bytes));
+    CHECK(bytes == (kind == 0 ? 4.0 + 3 : kind == 1 ? 8.0 + 2 : 2.0) * 4.0 * (double)n, "Float32 algorithmic bytes %g", bytes);
+    CHECK(b2o_qn_diag(op, res, n) == B2O_EUNSUPPORTED, "diag! is Float64 only");
+    OK(b2o_qn_destroy(op));
+  }
+  b2o_qn *bad = NULL;
+  CHECK(b2o_lbfgs_create(ctx, B2O_F32, n, 5, 1, 1, 0.99, 10.0, 0, &bad) == B2O_EUNSUPPORTED, "damped Float32 must be refused");
+  CHECK(b2o_lbfgs_create(ctx, B2O_BF16, n, 5, 1, 0, 0.99, 10.0, 0, &bad) == B2O_EUNSUPPORTED, "bf16 quasi-Newton must be refused");
+  OK(b2o_free(ctx, s)); OK(b2o_free(ctx, v)); OK(b2o_free(ctx, res));
+  free(hs); free(hv); free(got);
+}
+
 /* ---- BASELINE config 3 as a fused static tree: (opHouseholder(h) * opDiagonal(d) + 0.1 * opEye(n)) * v --------- */
 static void test_graph(void) {
   const int64_t n = 300007;
@@ -317,6 +372,7 @@ int main(void) {
   test_leaves();
   test_index();
   test_qn();
+  test_qn_f32();
   test_graph();
   test_kron();
   int64_t launches = 0;

@@ -124,6 +124,27 @@ def compute_cases_v2(orc):
     return {k: np.asarray(val, dtype=np.float64).tolist() for k, val in out.items()}
 
 
+def compute_cases_v3(orc):
+    """Float32 quasi-Newton operators (oracle/oracle_f32.py): push! + apply of LBFGSOperator / InverseLBFGSOperator / LSR1Operator
+    with T = Float32 on seeded inputs (the shared generator, rounded to Float32 exactly as b2o_fill_uniform does)."""
+    import oracle_f32 as o32
+    f = lambda n, seed, lo=0.0, hi=1.0: orc.uniform(n, seed, lo, hi).astype(np.float32)
+    out = {}
+    n, mem, npush = 257, 3, 5
+    x, r0 = f(n, 7), f(n, 8)
+    for tag, op in (("lbfgs", o32.LBFGS32(n, mem)), ("inverse", o32.LBFGS32(n, mem, inverse=True)), ("lsr1", o32.LSR1_32(n, mem))):
+        for i in range(npush):
+            s = f(n, 100 + i)
+            y = (s + np.float32(0.1) * f(n, 200 + i)) if tag != "lsr1" else f(n, 200 + i, -0.5, 1.0)
+            op.push(s, y)
+        out["f32_%s_apply" % tag] = op.apply(x)
+        out["f32_%s_apply_ab" % tag] = op.apply(x, -0.75, 0.5, res=r0)
+        out["f32_%s_scalars" % tag] = np.array([op.insert, op.gamma, op.opnorm_upper_bound], dtype=np.float64)
+        if tag != "inverse":
+            out["f32_%s_a_last" % tag] = op.a[(op.insert - 2) % mem]
+    return {k: np.asarray(val, dtype=np.float64).tolist() for k, val in out.items()}
+
+
 if __name__ == "__main__":
     sys.path.insert(0, os.path.join(HERE, "..", "..", "oracle"))
     import oracle
@@ -137,3 +158,7 @@ if __name__ == "__main__":
     json.dump({"generator": "tests/golden/make_golden.py (compute_cases_v2)", "oracle": "oracle/b2o_oracle.c (long-double reductions)",
                "cases": cases2}, open(os.path.join(HERE, "golden_v2.json"), "w"), indent=1)
     print("wrote", len(cases2), "cases (v2)")
+    cases3 = compute_cases_v3(oracle)
+    json.dump({"generator": "tests/golden/make_golden.py (compute_cases_v3)", "oracle": "oracle/oracle_f32.py (numpy Float32 statements, Float64 reductions)",
+               "cases": cases3}, open(os.path.join(HERE, "golden_v3.json"), "w"), indent=1)
+    print("wrote", len(cases3), "cases (v3)")

@@ -118,3 +118,32 @@ def test_f32_secant_equation_and_inverse_pair_on_gpu(lo, ctx):
     x = f32(ctx, n, 9)
     assert rel(host(H * (B * x)), host(x)) <= 1e-4
     assert B.apply_bytes() == (4 * mem + 3) * 4.0 * n                         # half the bytes of the Float64 operator
+
+
+def test_f32_golden_vectors_on_gpu(lo, ctx, orc):
+    """tests/golden/golden_v3.json: frozen outputs of the numpy Float32 restatement (push! x 5 + apply, n = 257, mem = 3) against the
+    CUDA path on the same seeded inputs (b2o_fill_uniform rounds the shared generator to Float32 exactly as the fixture script does)"""
+    import json
+    import os
+    import torch
+    G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_v3.json")))["cases"]
+    n, mem, npush = 257, 3, 5
+    x, r0 = f32(ctx, n, 7), f32(ctx, n, 8)
+    assert np.array_equal(host(x), orc.uniform(n, 7).astype(np.float32))
+    for tag, op in (("lbfgs", lo.LBFGSOperator(torch.float32, n, mem=mem, ctx=ctx)),
+                    ("inverse", lo.InverseLBFGSOperator(torch.float32, n, mem=mem, ctx=ctx)),
+                    ("lsr1", lo.LSR1Operator(torch.float32, n, mem=mem, ctx=ctx))):
+        for i in range(npush):
+            s = f32(ctx, n, 100 + i)
+            y = (s + 0.1 * f32(ctx, n, 200 + i)) if tag != "lsr1" else f32(ctx, n, 200 + i, -0.5, 1.0)
+            lo.push_(op, s, y)
+        tol = 1e-5 if tag != "lsr1" else 1e-4
+        assert rel(host(op * x), G["f32_%s_apply" % tag]) <= tol, (tag, rel(host(op * x), G["f32_%s_apply" % tag]))
+        out = r0.clone()
+        lo.mul_(out, op, x, -0.75, 0.5)
+        assert rel(host(out), G["f32_%s_apply_ab" % tag]) <= tol
+        ins, gamma, ub, _, _ = op.data._scalars()
+        gi, gg, gu = G["f32_%s_scalars" % tag]
+        assert ins == int(gi) and abs(gamma - gg) <= 1e-6 * abs(gg) and abs(ub - gu) <= 1e-4 * abs(gu)
+        if tag != "inverse":
+            assert rel(host(op.data.col("a", (ins - 2) % mem)), G["f32_%s_a_last" % tag]) <= tol

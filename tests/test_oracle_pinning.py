@@ -573,3 +573,17 @@ def test_f32_restatement_agrees_with_the_float64_oracle():
     ref = np.empty(n)
     b.apply(x.astype(np.float64), 1.0, 0.0, res=ref)
     assert np.linalg.norm(a.apply(x) - ref) <= 1e-3 * np.linalg.norm(ref)     # SR1 recurrences amplify Float32 rounding
+
+
+def test_golden_vectors_v3_float32_quasi_newton(orc):
+    """tests/golden/golden_v3.json (make_golden.compute_cases_v3): the numpy Float32 restatement reproduces its frozen outputs bit for
+    bit (regression pin of oracle/oracle_f32.py; the GPU test compares the CUDA path with the same file)"""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden
+    G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_v3.json")))["cases"]
+    now = make_golden.compute_cases_v3(orc)
+    assert set(now) == set(G)
+    for k in G:
+        assert np.array_equal(np.asarray(now[k]), np.asarray(G[k])), k
