@@ -39,6 +39,8 @@ struct b2o_qn_s {
 // Float32 operators (b2o_qn_f32.inc, included at the end of this file)
 static int qn32_apply(b2o_qn *q, float *res, const float *x, double alpha, double beta);
 static int qn32_push(b2o_qn *q, const float *s, const float *y, int *accepted);
+static int qn32_push_damped(b2o_qn *q, const float *s, float *y, bool inverse_form, double alpha, const float *g, float *Bs, int *accepted);
+static int qn32_diag(b2o_qn *q, float *d);
 #define B2O_F64_ONLY(q, what)                                                                                                    \
   do {                                                                                                                           \
     if ((q)->esize != 8) B2O_FAIL(B2O_EUNSUPPORTED, what " is not built for Float32 quasi-Newton operators (Float64 only)");      \
@@ -182,27 +184,31 @@ __global__ void __launch_bounds__(256) lincomb_kernel(const __grid_constant__ Li
 }
 
 // diag!: d = 1 (/γ) ; d += b_k^2 - a_k^2  (L-BFGS :379-395)  |  d += a_k^2/as_k  (L-SR1 :196-211)
-struct DiagArgs {
-  const double *c0[B2O_MAX_MEM];
-  const double *c1[B2O_MAX_MEM];
+template <typename T>
+struct DiagArgsT {
+  const T *c0[B2O_MAX_MEM];
+  const T *c1[B2O_MAX_MEM];
   double cdiv[B2O_MAX_MEM];
   int nact, kind, scaling;
   double gamma;
-  double *d;
+  T *d;
   int64_t n;
 };
-__global__ void qn_diag_kernel(const __grid_constant__ DiagArgs a) {
+using DiagArgs = DiagArgsT<double>;
+template <typename T>
+__global__ void qn_diag_kernel(const __grid_constant__ DiagArgsT<T> a) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const T gamma = (T)a.gamma;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
-    double d = 1.0;
-    if (a.scaling) d = d / a.gamma;
+    T d = (T)1;
+    if (a.scaling) d = d / gamma;
     for (int k = 0; k < a.nact; ++k) {
       if (a.kind == 0) {
-        double av = a.c0[k][i], bv = a.c1[k][i];
+        T av = a.c0[k][i], bv = a.c1[k][i];
         d = d + (bv * bv - av * av);
       } else {
-        double av = a.c0[k][i];
-        d = d + (av * av) / a.cdiv[k];
+        T av = a.c0[k][i];
+        d = d + (av * av) / (T)a.cdiv[k];
       }
     }
     a.d[i] = d;
@@ -270,7 +276,6 @@ extern "C" int b2o_qn_destroy(b2o_qn *q) {
 static int qn_create_common(b2o_ctx *ctx, int dtype, int64_t n, int mem, b2o_qn **out, b2o_qn **made) {
   if (!ctx || !out) B2O_FAIL(B2O_EARG, "null argument");
   if (dtype != B2O_F64 && dtype != B2O_F32) B2O_FAIL(B2O_EUNSUPPORTED, "quasi-Newton operators: dtype %d not supported (Float64 or Float32)", dtype);
-  if (dtype == B2O_F32 && ctx->nranks > 1) B2O_FAIL(B2O_EUNSUPPORTED, "Float32 quasi-Newton operators are not built for row-partitioned contexts");
   if (n < 0) B2O_FAIL(B2O_EARG, "n must be >= 0");
   if (mem < 1) mem = 1;  // LBFGSData clamps mem to max(mem,1) (src/lbfgs.jl:37)
   if (mem > B2O_MAX_MEM) B2O_FAIL(B2O_EUNSUPPORTED, "mem=%d exceeds the built maximum %d", mem, B2O_MAX_MEM);
@@ -289,10 +294,6 @@ extern "C" int b2o_lbfgs_create(b2o_ctx *ctx, int dtype, int64_t n, int mem, int
   b2o_qn *q = nullptr;
   B2O_TRY(qn_create_common(ctx, dtype, n, mem, out, &q));
   q->kind = 0;
-  if (q->esize != 8 && damped) {
-    delete q;
-    B2O_FAIL(B2O_EUNSUPPORTED, "damped L-BFGS is not built for Float32 (Float64 only)");
-  }
   q->scaling = scaling != 0;
   q->damped = damped != 0;
   q->inverse = inverse != 0;
@@ -1333,7 +1334,6 @@ static int lsr1_push(b2o_qn *q, const double *s, const double *y, int *accepted)
 
 extern "C" int b2o_lbfgs_push_damped_fwd(b2o_qn *q, const void *s_, const void *y_, void *Bs_, int64_t len, int *accepted) {
   if (!q || q->kind != 0) B2O_FAIL(B2O_EARG, "not an L-BFGS operator");
-  B2O_F64_ONLY(q, "damped push!");
   if (!q->damped) B2O_FAIL(B2O_ESTATE, "This push! should be used for damped operators");
   if (q->inverse) B2O_FAIL(B2O_ESTATE, "This function be used for forward operators. Use push!(op, s, y, α, g, Bs) instead.");
   B2O_TRY(check_vec(q, s_, len));
@@ -1341,6 +1341,7 @@ extern "C" int b2o_lbfgs_push_damped_fwd(b2o_qn *q, const void *s_, const void *
   B2O_TRY(check_vec(q, Bs_, len));
   b2o_ctx *c = q->ctx;
   B2O_CUDA(cudaSetDevice(c->device));
+  if (q->esize == 4) return qn32_push_damped(q, (const float *)s_, (float *)const_cast<void *>(y_), false, 0.0, nullptr, (float *)Bs_, accepted);
   const double *s = (const double *)s_, *y = (const double *)y_;
   double *Bs = (double *)Bs_;
   const int64_t n = q->n;
@@ -1378,7 +1379,6 @@ extern "C" int b2o_lbfgs_push_damped_fwd(b2o_qn *q, const void *s_, const void *
 extern "C" int b2o_lbfgs_push_damped_inv(b2o_qn *q, const void *s_, void *y_, double alpha, const void *g_, void *Bs_,
                                          int64_t len, int *accepted) {
   if (!q || q->kind != 0) B2O_FAIL(B2O_EARG, "not an L-BFGS operator");
-  B2O_F64_ONLY(q, "damped push!");
   if (!q->damped) B2O_FAIL(B2O_ESTATE, "This push! should be used for damped operators");
   if (!q->inverse) B2O_FAIL(B2O_ESTATE, "This function be used for inverse operators. Use push!(op, s, y, Bs) instead.");
   B2O_TRY(check_vec(q, s_, len));
@@ -1387,6 +1387,7 @@ extern "C" int b2o_lbfgs_push_damped_inv(b2o_qn *q, const void *s_, void *y_, do
   B2O_TRY(check_vec(q, Bs_, len));
   b2o_ctx *c = q->ctx;
   B2O_CUDA(cudaSetDevice(c->device));
+  if (q->esize == 4) return qn32_push_damped(q, (const float *)s_, (float *)y_, true, alpha, (const float *)g_, (float *)Bs_, accepted);
   const double *s = (const double *)s_, *g = (const double *)g_;
   double *y = (double *)y_, *Bs = (double *)Bs_;
   const int64_t n = q->n;
@@ -1719,7 +1720,6 @@ extern "C" int b2o_lbfgs_solve_shifted(b2o_qn *q, void *x_, int64_t x_len, const
 // ------------------------------------------------------------------ diag! / reset! / state
 extern "C" int b2o_qn_diag(b2o_qn *q, void *d, int64_t d_len) {
   if (!q) B2O_FAIL(B2O_EARG, "null operator");
-  B2O_F64_ONLY(q, "diag!");
   if (q->kind == 0 && q->inverse)
     B2O_FAIL(B2O_ESTATE, "only the diagonal of a forward L-BFGS approximation is available");  // src/lbfgs.jl:380-382
   if (q->fwd_compact) B2O_FAIL(B2O_EUNSUPPORTED, "diag! needs the a_k/b_k form (forward_mode 0)");
@@ -1727,6 +1727,7 @@ extern "C" int b2o_qn_diag(b2o_qn *q, void *d, int64_t d_len) {
   b2o_ctx *c = q->ctx;
   B2O_CUDA(cudaSetDevice(c->device));
   if (q->n == 0) return B2O_OK;
+  if (q->esize == 4) return qn32_diag(q, (float *)d);
   int slots[B2O_MAX_MEM];
   const int na = active_old_to_new(q, slots);
   DiagArgs a;
@@ -1742,7 +1743,7 @@ extern "C" int b2o_qn_diag(b2o_qn *q, void *d, int64_t d_len) {
   a.gamma = q->gamma;
   a.d = (double *)d;
   a.n = q->n;
-  qn_diag_kernel<<<ew_grid(c, q->n), 256, 0, c->stream>>>(a);
+  qn_diag_kernel<double><<<ew_grid(c, q->n), 256, 0, c->stream>>>(a);
   c->launches++;
   B2O_CUDA(cudaGetLastError());
   return B2O_OK;

@@ -229,12 +229,12 @@ def push_(op, s, y, *rest):
             op.nprod += 1          # push! runs mul!(Bs, op, s) first (src/lsr1.jl:125, src/lbfgs.jl:305 through :273-277)
     elif len(rest) == 1:
         (Bs,) = rest
-        _lib.check(lib.b2o_lbfgs_push_damped_fwd(op.handle, _vp(s), _vp(y), _vp(Bs), n, ctypes.byref(acc)))
+        _lib.check(lib.b2o_lbfgs_push_damped_fwd(op.handle, _qvp(op, s), _qvp(op, y), _qvp(op, Bs), n, ctypes.byref(acc)))
         op.nprod += 1              # mul!(Bs, op, s)  src/lbfgs.jl:305
     elif len(rest) in (2, 3):
         alpha, g = rest[0], rest[1]
-        Bs = rest[2] if len(rest) == 3 else op.ctx.empty(n)      # similar(g)  src/lbfgs.jl:366
-        _lib.check(lib.b2o_lbfgs_push_damped_inv(op.handle, _vp(s), _vp(y), float(alpha), _vp(g), _vp(Bs), n,
+        Bs = rest[2] if len(rest) == 3 else op.ctx.empty(n, dtype=op.eltype)      # similar(g)  src/lbfgs.jl:366
+        _lib.check(lib.b2o_lbfgs_push_damped_inv(op.handle, _qvp(op, s), _qvp(op, y), float(alpha), _qvp(op, g), _qvp(op, Bs), n,
                                                  ctypes.byref(acc)))
     else:
         raise TypeError("no such push! method")
@@ -244,12 +244,12 @@ def push_(op, s, y, *rest):
 
 def diag_(op, d):
     """diag!(op, d) (src/lbfgs.jl:379-395, src/lsr1.jl:196-211)"""
-    _lib.check(op.ctx.lib.b2o_qn_diag(op.handle, _vp(d), d.shape[0]))
+    _lib.check(op.ctx.lib.b2o_qn_diag(op.handle, _qvp(op, d), d.shape[0]))
     return d
 
 
 def diag(op):
-    return diag_(op, op.ctx.empty(op.nrow))
+    return diag_(op, op.ctx.empty(op.nrow, dtype=op.eltype))
 
 
 def solve_shifted_system_(x, B, b, sigma):

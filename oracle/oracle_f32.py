@@ -22,8 +22,9 @@ def _dot(a, b):
 class LBFGS32:
     """src/lbfgs.jl:36-56 (LBFGSData), :117-154 (inverse apply), :173-202 (forward apply), :210-288 (push!), :401-415 (reset!)"""
 
-    def __init__(self, n, mem=5, scaling=True, inverse=False):
+    def __init__(self, n, mem=5, scaling=True, inverse=False, damped=False, sigma2=0.99, sigma3=10.0):
         self.n, self.mem, self.scaling, self.inverse = n, max(mem, 1), scaling, inverse
+        self.damped, self.sigma2, self.sigma3 = damped, F(sigma2), F(sigma3)
         m = self.mem
         self.s = np.zeros((m, n), F)
         self.y = np.zeros((m, n), F)
@@ -38,9 +39,44 @@ class LBFGS32:
 
     def push(self, s, y):
         s, y = np.asarray(s, F), np.asarray(y, F)
+        if self.damped:                                                      # :274-276
+            return self.push_damped(s, y)
         ys = _dot(y, s)                                                      # :277
         if ys <= np.finfo(F).eps:                                            # :281
             return False
+        return self._push_common(s, y, ys)
+
+    def push_damped(self, s, y, alpha=None, g=None):
+        """push!(op, s, y, Bs) :289-321 (forward) / push!(op, s, y, α, g, Bs) :323-357 (inverse: returns the damped y as well)"""
+        s, y = np.asarray(s, F), np.asarray(y, F)
+        ys = _dot(y, s)
+        Bs = self.apply(s) if not self.inverse else (-F(alpha)) * np.asarray(g, F)      # :305 / :341
+        sBs = _dot(s, Bs)
+        one = F(1)
+        theta = None
+        if ys < (one - self.sigma2) * sBs:                                   # :308-314
+            theta = F(self.sigma2 * sBs / (sBs - ys))
+        elif ys > (one + self.sigma3) * sBs:
+            theta = F(self.sigma3 * sBs / (ys - sBs))
+        if theta is not None:
+            y = theta * y + (one - theta) * Bs                               # :316 / :352
+            ys = F(theta * ys + (one - theta) * sBs)
+        self._push_common(s, y, ys)
+        return y
+
+    def diag(self):
+        """diag! :379-395"""
+        assert not self.inverse
+        d = np.ones(self.n, F)
+        if self.scaling:
+            d = d / self.gamma
+        for i in range(1, self.mem + 1):
+            k = (self.insert + i - 2) % self.mem
+            if self.ys[k] != 0:
+                d = d + (self.b[k] * self.b[k] - self.a[k] * self.a[k])
+        return d
+
+    def _push_common(self, s, y, ys):
         m, ins = self.mem, self.insert - 1
         self.s[ins] = s                                                      # :220-222
         self.y[ins] = y
@@ -135,6 +171,17 @@ class LSR1_32:
                 ax = F(F(alpha * _dot(self.a[k], x)) / self.as_[k])
                 q = q + ax * self.a[k]
         return q.astype(F)
+
+    def diag(self):
+        """diag! src/lsr1.jl:196-211"""
+        d = np.ones(self.n, F)
+        if self.scaling:
+            d = d / self.gamma
+        for i in range(1, self.mem + 1):
+            k = (self.insert + i - 2) % self.mem
+            if self.ys[k] != 0:
+                d = d + (self.a[k] * self.a[k]) / self.as_[k]
+        return d
 
     def push(self, s, y):
         s, y = np.asarray(s, F), np.asarray(y, F)

@@ -274,11 +274,17 @@ static void test_qn_f32(void) {
     double bytes = 0;
     OK(b2o_qn_apply_bytes(op, 0.0, &bytes));
     CHECK(bytes == (kind == 0 ? 4.0 + 3 : kind == 1 ? 8.0 + 2 : 2.0) * 4.0 * (double)n, "Float32 algorithmic bytes %g", bytes);
-    CHECK(b2o_qn_diag(op, res, n) == B2O_EUNSUPPORTED, "diag! is Float64 only");
+    if (kind != 1) {   /* diag!: 1/gamma + b^2 - a^2 with a == b (forward), the identity's diagonal (L-SR1 pair rejected) */
+      OK(b2o_qn_diag(op, res, n));
+      d2h(got, res, (size_t)n * 4);
+      CHECK(memcmp(got, hs, (size_t)n * 4) == 0, "Float32 kind %d: diag! == ones", kind);
+    } else {
+      CHECK(b2o_qn_diag(op, res, n) == B2O_ESTATE, "diag! of an inverse operator must be refused");
+    }
+    CHECK(b2o_qn_apply_host(op, got, hv, n, 1.0, 0.0) == B2O_EUNSUPPORTED, "host-buffer apply is Float64 only");
     OK(b2o_qn_destroy(op));
   }
   b2o_qn *bad = NULL;
-  CHECK(b2o_lbfgs_create(ctx, B2O_F32, n, 5, 1, 1, 0.99, 10.0, 0, &bad) == B2O_EUNSUPPORTED, "damped Float32 must be refused");
   CHECK(b2o_lbfgs_create(ctx, B2O_BF16, n, 5, 1, 0, 0.99, 10.0, 0, &bad) == B2O_EUNSUPPORTED, "bf16 quasi-Newton must be refused");
   OK(b2o_free(ctx, s)); OK(b2o_free(ctx, v)); OK(b2o_free(ctx, res));
   free(hs); free(hv); free(got);

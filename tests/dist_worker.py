@@ -114,9 +114,39 @@ def main():
                 a2 = (g * xs).cpu().numpy()
                 assert np.array_equal(a1, a2)
 
+        def check_qn_f32(expect_one_launch):
+            """Float32 operators row-partitioned (same kernels, T = float): against the GLOBAL numpy Float32 restatement"""
+            import oracle_f32 as o32
+            f = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+            x32 = x.astype(np.float32)
+            for kind in ("fwd", "inv", "lsr1"):
+                if kind == "lsr1":
+                    g, o = lo.LSR1Operator(torch.float32, ns, mem=mem, ctx=ctx), o32.LSR1_32(n, mem)
+                else:
+                    g = lo.LBFGSOperator(torch.float32, ns, mem=mem, inverse=kind == "inv", ctx=ctx)
+                    o = o32.LBFGS32(n, mem, inverse=kind == "inv")
+                for s, y in P:
+                    if kind == "lsr1":
+                        y = 2.0 * s + 3.0 * (y - s)
+                    s32, y32 = s.astype(np.float32), y.astype(np.float32)
+                    lo.push_(g, f(s32[lo_:hi_]), f(y32[lo_:hi_]))
+                    assert bool(g.last_push_accepted) == bool(o.push(s32, y32))
+                assert g.data.insert == o.insert
+                assert abs(g.data.scaling_factor - float(o.gamma)) <= 1e-6 * abs(float(o.gamma))
+                res = torch.empty(ns, dtype=torch.float32, device=dev)
+                l0 = ctx.launch_count()
+                lo.mul_(res, g, f(x32[lo_:hi_]))
+                nl = ctx.launch_count() - l0
+                assert (nl == 1) == expect_one_launch, (kind, nl)
+                ref = o.apply(x32)
+                err = np.linalg.norm(res.cpu().numpy().astype(np.float64) - ref[lo_:hi_]) / np.linalg.norm(ref[lo_:hi_])
+                assert err <= (1e-5 if kind != "lsr1" else 1e-4), ("f32", kind, err)
+
         check_qn(expect_one_launch=False)              # NCCL: one kernel + one all-reduce per inner product
+        check_qn_f32(expect_one_launch=False)
         ctx.connect_mailbox()
         check_qn(expect_one_launch=True)               # NVLink peer mailbox: ONE persistent launch per GPU
+        check_qn_f32(expect_one_launch=True)
         # mailbox and NCCL all-reduce the same partials: at 2 ranks a+b is order-free, so results must agree bit for bit
         gm = lo.LBFGSOperator(ns, mem=mem, ctx=ctx)
         for s, y in P:

@@ -142,6 +142,15 @@ def compute_cases_v3(orc):
         out["f32_%s_scalars" % tag] = np.array([op.insert, op.gamma, op.opnorm_upper_bound], dtype=np.float64)
         if tag != "inverse":
             out["f32_%s_a_last" % tag] = op.a[(op.insert - 2) % mem]
+            out["f32_%s_diag" % tag] = op.diag()
+    # Powell-damped operators: pairs with under- / over-estimated curvature take both damping branches (src/lbfgs.jl:308-314)
+    B, H = o32.LBFGS32(n, mem, damped=True), o32.LBFGS32(n, mem, inverse=True, damped=True)
+    for i in range(npush):
+        s, y, g = f(n, 100 + i), f(n, 200 + i, 0.0, 3.0 if i % 2 else 0.05), f(n, 300 + i)
+        B.push(s, y)
+        H.push_damped(s, y, 0.7, g)
+    out["f32_damped_lbfgs_apply"] = B.apply(x)
+    out["f32_damped_inverse_apply"] = H.apply(x)
     return {k: np.asarray(val, dtype=np.float64).tolist() for k, val in out.items()}
 
 

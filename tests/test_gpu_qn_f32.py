@@ -43,9 +43,7 @@ def test_reference_precision_testset_float32(lo, ctx):
     with pytest.raises(lo.B2OError):
         lo.push_(B, torch.ones(n, dtype=torch.float64, device=dev), torch.ones(n, dtype=torch.float64, device=dev))   # wrong element type
     with pytest.raises(lo.B2OError):
-        lo.diag(B)                                                           # not built for Float32
-    with pytest.raises(lo.B2OError):
-        lo.LBFGSOperator(n, mem=mem, damped=True, T=torch.float32, ctx=ctx)
+        lo.solve_shifted_system_(torch.empty(n, dtype=torch.float32, device=dev), B, v, 0.5)      # Float64 only
 
 
 @pytest.mark.parametrize("kind", ["lbfgs", "inverse", "lsr1"])
@@ -147,3 +145,49 @@ def test_f32_golden_vectors_on_gpu(lo, ctx, orc):
         assert ins == int(gi) and abs(gamma - gg) <= 1e-6 * abs(gg) and abs(ub - gu) <= 1e-4 * abs(gu)
         if tag != "inverse":
             assert rel(host(op.data.col("a", (ins - 2) % mem)), G["f32_%s_a_last" % tag]) <= tol
+            assert rel(host(lo.diag(op)), G["f32_%s_diag" % tag]) <= tol
+    B = lo.LBFGSOperator(torch.float32, n, mem=mem, damped=True, ctx=ctx)
+    H = lo.InverseLBFGSOperator(torch.float32, n, mem=mem, damped=True, ctx=ctx)
+    for i in range(npush):
+        s, y, g = f32(ctx, n, 100 + i), f32(ctx, n, 200 + i, 0.0, 3.0 if i % 2 else 0.05), f32(ctx, n, 300 + i)
+        lo.push_(B, s, y)
+        lo.push_(H, s, y.clone(), 0.7, g)
+    assert rel(host(B * x), G["f32_damped_lbfgs_apply"]) <= 2e-5
+    assert rel(host(H * x), G["f32_damped_inverse_apply"]) <= 2e-5
+
+
+@pytest.mark.parametrize("n,mem,npush", [(1000, 4, 7), (100003, 5, 9)])
+def test_f32_damped_push_and_diag_vs_numpy_oracle(lo, ctx, n, mem, npush):
+    """Powell-damped push! in all calling sequences (src/lbfgs.jl:269-367) and diag! (:379-395, src/lsr1.jl:196-211) for T = Float32;
+    pairs alternate between strongly under- and over-estimated curvature so that both damping branches are taken"""
+    import torch
+    import oracle_f32 as o32
+    B, oB = lo.LBFGSOperator(torch.float32, n, mem=mem, damped=True, ctx=ctx), o32.LBFGS32(n, mem, damped=True)
+    H, oH = lo.InverseLBFGSOperator(torch.float32, n, mem=mem, damped=True, ctx=ctx), o32.LBFGS32(n, mem, inverse=True, damped=True)
+    L, oL = lo.LSR1Operator(torch.float32, n, mem=mem, ctx=ctx), o32.LSR1_32(n, mem)
+    for i in range(npush):
+        s = f32(ctx, n, 100 + i)
+        y = f32(ctx, n, 200 + i, 0.0, 3.0 if i % 2 else 0.05)
+        g = f32(ctx, n, 300 + i)
+        if i % 3 == 0:
+            lo.push_(B, s, y)                                                # push!(op, s, y) on a damped operator  :274-276
+        else:
+            lo.push_(B, s, y, torch.empty_like(s))                           # push!(op, s, y, Bs)
+        oB.push(host(s), host(y))
+        yd = y.clone()
+        lo.push_(H, s, yd, 0.7, g)                                           # push!(op, s, y, α, g): y is overwritten with the damped y
+        yo = oH.push_damped(host(s), host(y), 0.7, host(g))
+        assert rel(host(yd), yo) <= 1e-6
+        yl = f32(ctx, n, 200 + i, -0.5, 1.0)
+        lo.push_(L, s, yl)
+        oL.push(host(s), host(yl))
+    with pytest.raises(lo.B2OError):
+        lo.push_(H, s, y)                                                    # damped inverse operators need α and g  :296-298
+    x = f32(ctx, n, 7)
+    assert rel(host(B * x), oB.apply(host(x))) <= 2e-5
+    assert rel(host(H * x), oH.apply(host(x))) <= 2e-5
+    assert rel(host(lo.diag(B)), oB.diag()) <= 1e-5
+    assert rel(host(lo.diag(L)), oL.diag()) <= 1e-4
+    assert lo.diag(B).dtype == torch.float32
+    with pytest.raises(lo.B2OError):
+        lo.diag(H)                                                           # only forward approximations  :380-382
