@@ -181,7 +181,7 @@ def test_f32_damped_push_and_diag_vs_numpy_oracle(lo, ctx, n, mem, npush):
         yl = f32(ctx, n, 200 + i, -0.5, 1.0)
         lo.push_(L, s, yl)
         oL.push(host(s), host(yl))
-    with pytest.raises(lo.B2OError):
+    with pytest.raises(lo.ErrorException):
         lo.push_(H, s, y)                                                    # damped inverse operators need α and g  :296-298
     x = f32(ctx, n, 7)
     assert rel(host(B * x), oB.apply(host(x))) <= 2e-5
@@ -189,5 +189,5 @@ def test_f32_damped_push_and_diag_vs_numpy_oracle(lo, ctx, n, mem, npush):
     assert rel(host(lo.diag(B)), oB.diag()) <= 1e-5
     assert rel(host(lo.diag(L)), oL.diag()) <= 1e-4
     assert lo.diag(B).dtype == torch.float32
-    with pytest.raises(lo.B2OError):
+    with pytest.raises(lo.LinearOperatorException):
         lo.diag(H)                                                           # only forward approximations  :380-382
