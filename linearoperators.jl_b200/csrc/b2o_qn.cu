@@ -913,15 +913,19 @@ static int twoloop_multi_launch(b2o_qn *q, double *res, int64_t ldr, const doubl
 extern "C" int b2o_qn_apply_multi(b2o_qn *q, void *res_, int64_t ldr, const void *x_, int64_t ldx, int64_t len, int nrhs,
                                   double alpha, double beta) {
   if (!q) B2O_FAIL(B2O_EARG, "null operator");
-  B2O_F64_ONLY(q, "the block apply");
   if (len != q->n) B2O_FAIL(B2O_ESHAPE, "shape mismatch");
   if (nrhs < 0) B2O_FAIL(B2O_EARG, "nrhs must be >= 0");
   if (nrhs == 0 || q->n == 0) return B2O_OK;
   if (!res_ || !x_) B2O_FAIL(B2O_EARG, "null matrix");
   if (nrhs > 1 && (ldr < q->n || ldx < q->n)) B2O_FAIL(B2O_EARG, "leading dimension smaller than n");
-  if (((uintptr_t)res_ | (uintptr_t)x_) % 8) B2O_FAIL(B2O_EARG, "matrices must be 8-byte aligned");
+  if (((uintptr_t)res_ | (uintptr_t)x_) % (uintptr_t)q->esize) B2O_FAIL(B2O_EARG, "matrices must be aligned to the element size");
   b2o_ctx *c = q->ctx;
   B2O_CUDA(cudaSetDevice(c->device));
+  if (q->esize == 4) {
+    // Float32 handles: the reference's semantics (column j of Res = the vector apply of column j of X), one launch per column
+    for (int r = 0; r < nrhs; ++r) B2O_TRY(qn32_apply(q, (float *)res_ + (int64_t)r * ldr, (const float *)x_ + (int64_t)r * ldx, alpha, beta));
+    return B2O_OK;
+  }
   double *res = (double *)res_;
   const double *x = (const double *)x_;
   const bool twoloop = q->kind == 0 && q->inverse && !q->inv_compact;
@@ -1107,10 +1111,20 @@ static int ensure_pipeline(b2o_ctx *c) {
 // launch's only per chunk order: the dots are accumulated chunk by chunk in a fixed order (deterministic).
 extern "C" int b2o_qn_apply_host(b2o_qn *q, void *res_host, const void *x_host, int64_t len, double alpha, double beta) {
   if (!q) B2O_FAIL(B2O_EARG, "null operator");
-  B2O_F64_ONLY(q, "the host-buffer apply");
   if (len != q->n) B2O_FAIL(B2O_ESHAPE, "shape mismatch");
   b2o_ctx *c = q->ctx;
   B2O_CUDA(cudaSetDevice(c->device));
+  if (q->esize == 4) {
+    // Float32 handles: staged copy-in, apply, copy-out (no chunked transfer / compute pipeline)
+    const size_t b32 = (size_t)q->n * sizeof(float);
+    B2O_TRY(ensure_stage(c, std::max<size_t>(b32, 16)));
+    B2O_CUDA(cudaMemcpyAsync(c->stage_x, x_host, b32, cudaMemcpyHostToDevice, c->stream));
+    if (beta != 0.0) B2O_CUDA(cudaMemcpyAsync(c->stage_res, res_host, b32, cudaMemcpyHostToDevice, c->stream));
+    B2O_TRY(qn32_apply(q, (float *)c->stage_res, (const float *)c->stage_x, alpha, beta));
+    B2O_CUDA(cudaMemcpyAsync(res_host, c->stage_res, b32, cudaMemcpyDeviceToHost, c->stream));
+    B2O_CUDA(cudaStreamSynchronize(c->stream));
+    return B2O_OK;
+  }
   const size_t bytes = (size_t)q->n * sizeof(double);
   B2O_TRY(ensure_stage(c, std::max<size_t>(bytes, 16)));
   double *dx = (double *)c->stage_x, *dres = (double *)c->stage_res;

@@ -137,10 +137,8 @@ class AbstractQuasiNewtonOperator(AbstractLinearOperator):
         """mul!(Res::Matrix, op, X::Matrix, α, β) (src/operations.jl:34-36) in one launch per 8 right-hand sides; returns False
         (caller falls back to the column loop) unless both matrices are column-major float64 CUDA tensors."""
         import torch
-        if self._dt != F64:
-            return False                                     # Float32 operators: column loop
         for t in (res, X):
-            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.dim() == 2):
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == self.eltype and t.dim() == 2):
                 return False
             if t.shape[0] > 1 and t.stride(0) != 1:
                 return False

@@ -281,7 +281,13 @@ static void test_qn_f32(void) {
     } else {
       CHECK(b2o_qn_diag(op, res, n) == B2O_ESTATE, "diag! of an inverse operator must be refused");
     }
-    CHECK(b2o_qn_apply_host(op, got, hv, n, 1.0, 0.0) == B2O_EUNSUPPORTED, "host-buffer apply is Float64 only");
+    OK(b2o_qn_apply_host(op, got, hv, n, 1.0, 0.0));   /* host buffers: staged copy-in, apply, copy-out */
+    {
+      double worst3 = 0;
+      for (int64_t i = 0; i < n; ++i) worst3 = fmax(worst3, fabs((double)got[i] - (double)hv[i]));
+      CHECK(worst3 <= (kind == 1 ? 1e-6 : 0.0), "Float32 kind %d: apply_host, worst %g", kind, worst3);
+    }
+    CHECK(b2o_qn_set_option(op, "forward_mode", 1) == B2O_EUNSUPPORTED || kind != 0, "compact forms are Float64 only");
     OK(b2o_qn_destroy(op));
   }
   b2o_qn *bad = NULL;

@@ -91,6 +91,14 @@ def test_f32_push_and_apply_vs_numpy_oracle(lo, ctx, kind, n, mem, npush):
     lo.mul_(out2[3:], op, big[1:n + 1])
     assert np.array_equal(host(out2[3:]), host(res))
     assert np.array_equal(host(op * x), host(res))                           # run-to-run bit determinism
+    # matrix right-hand sides (src/operations.jl:34-36: column j of Res = the vector apply of column j of X) and host buffers
+    Xb = torch.stack([x, r0, x + r0]).contiguous()
+    Rb = torch.empty_like(Xb)
+    lo.mul_(Rb.T, op, Xb.T)
+    assert np.array_equal(host(Rb[0]), host(res)) and np.array_equal(host(Rb[2]), host(op * (x + r0)))
+    xh, rh = x.cpu().pin_memory(), torch.empty(n, dtype=torch.float32).pin_memory()
+    op.apply_host(rh, xh)
+    assert np.array_equal(rh.numpy(), host(res))
     # a pair with non-positive curvature is rejected and leaves the state alone (src/lbfgs.jl:281)
     if kind != "lsr1":
         lo.push_(op, x, -x)

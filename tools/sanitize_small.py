@@ -120,6 +120,17 @@ def main():
         lo.mul_(r32v, g, f32(7), 1.5, -0.5)
         big = torch.zeros(n32 + 3, dtype=torch.float32, device="cuda")
         lo.mul_(big[3:], g, f32(7))                                                      # 4-byte aligned views
+        if kind != "inv":
+            lo.diag(g)
+    for inv in (False, True):                                                            # Powell-damped Float32 push!
+        g = lo.LBFGSOperator(torch.float32, n32, mem=3, damped=True, inverse=inv, ctx=ctx)
+        for i in range(4):
+            s, y = f32(100 + i), f32(200 + i, 0.0, 3.0 if i % 2 else 0.05)
+            if inv:
+                lo.push_(g, s, y, 0.7, f32(300 + i))
+            else:
+                lo.push_(g, s, y)
+        lo.mul_(r32v, g, f32(7))
     torch.cuda.synchronize()
     print("SANITIZE_OK launches=%d" % ctx.launch_count())
 
