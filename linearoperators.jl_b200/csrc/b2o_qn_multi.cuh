@@ -323,6 +323,10 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_multi_kernel(const __grid_
     __syncwarp();
   } else {
     const double alpha = p.alpha, beta = p.beta, gamma = p.gamma;
+    // base term with ONE reciprocal instead of NR x EPT divisions per tile: a double division is ~30 instructions, and with 8
+    // right-hand sides the divisions of `q ./= γ` outweighed the combine's FMAs (ncu source page: 17 % of the warp samples,
+    // profiles/r2_ncu_summary.md).  x * (1/γ) differs from x / γ by at most one ulp -- the block kernels are contracted anyway.
+    const double inv_gamma = 1.0 / gamma;
     double xn[NR][EPT], q[NR][EPT];
     if (my_tiles > 0) {
 #pragma unroll
@@ -340,16 +344,16 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_multi_kernel(const __grid_
       for (int r = 0; r < NR; ++r) {
         if (OP == OP_LBFGS_FWD) {
 #pragma unroll
-          for (int j = 0; j < EPT; ++j) q[r][j] = p.scaling ? xn[r][j] / gamma : xn[r][j];          // src/lbfgs.jl:183-186
+          for (int j = 0; j < EPT; ++j) q[r][j] = p.scaling ? xn[r][j] * inv_gamma : xn[r][j];      // src/lbfgs.jl:183-186
         } else if (OP == OP_INV_COMPACT) {
 #pragma unroll
-          for (int j = 0; j < EPT; ++j) q[r][j] = !p.scaling ? xn[r][j] : (p.base_div ? xn[r][j] / gamma : xn[r][j] * gamma);
+          for (int j = 0; j < EPT; ++j) q[r][j] = !p.scaling ? xn[r][j] : (p.base_div ? xn[r][j] * inv_gamma : xn[r][j] * gamma);
         } else {
           double rold[EPT];
           if (beta != 0.0 && r < nrhs) load_user_tile<R>(p.res + (int64_t)r * p.ldr, t * R, p.n, p.res_al16, rold);
 #pragma unroll
           for (int j = 0; j < EPT; ++j) {                                                           // src/lsr1.jl:92-96
-            const double v = (alpha * xn[r][j]) / gamma;
+            const double v = (alpha * xn[r][j]) * inv_gamma;
             q[r][j] = (beta != 0.0 && r < nrhs) ? v + beta * rold[j] : v;
           }
         }

@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_multi_mma_kernel(const __g
     }
     __syncwarp();
   } else {
-    const double alpha = p.alpha, beta = p.beta, gamma = p.gamma;
+    const double alpha = p.alpha, beta = p.beta, gamma = p.gamma, inv_gamma = 1.0 / p.gamma;
     const int n0 = 2 * lk;                               // the lane's two right-hand sides
     const bool ok0 = n0 < nrhs, ok1 = n0 + 1 < nrhs;
     double xb[MM_RG][2];                                   // X values of the NEXT tile to process (prefetched during the current one)
@@ -293,14 +293,14 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_multi_mma_kernel(const __g
         const bool rok = row < p.n;
         const double x0 = xb[rg][0], x1 = xb[rg][1];
         if (OP == OP_LBFGS_FWD) {
-          C[rg][0] = p.scaling ? x0 / gamma : x0;                                                  // src/lbfgs.jl:183-186
-          C[rg][1] = p.scaling ? x1 / gamma : x1;
+          C[rg][0] = p.scaling ? x0 * inv_gamma : x0;                                              // src/lbfgs.jl:183-186 (one reciprocal)
+          C[rg][1] = p.scaling ? x1 * inv_gamma : x1;
         } else if (OP == OP_INV_COMPACT) {
-          C[rg][0] = !p.scaling ? x0 : (p.base_div ? x0 / gamma : x0 * gamma);
-          C[rg][1] = !p.scaling ? x1 : (p.base_div ? x1 / gamma : x1 * gamma);
+          C[rg][0] = !p.scaling ? x0 : (p.base_div ? x0 * inv_gamma : x0 * gamma);
+          C[rg][1] = !p.scaling ? x1 : (p.base_div ? x1 * inv_gamma : x1 * gamma);
         } else {
-          C[rg][0] = (alpha * x0) / gamma;                                                          // src/lsr1.jl:92-96
-          C[rg][1] = (alpha * x1) / gamma;
+          C[rg][0] = (alpha * x0) * inv_gamma;                                                      // src/lsr1.jl:92-96
+          C[rg][1] = (alpha * x1) * inv_gamma;
           if (beta != 0.0) {
             if (rok && ok0) C[rg][0] += beta * p.res[(int64_t)n0 * p.ldr + row];
             if (rok && ok1) C[rg][1] += beta * p.res[(int64_t)(n0 + 1) * p.ldr + row];
