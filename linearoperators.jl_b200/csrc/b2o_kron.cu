@@ -833,9 +833,10 @@ static int kron_pair_launch(b2o_ctx *c, const CUtensorMap &tA1, const CUtensorMa
                             const CUtensorMap &tYhi, const CUtensorMap &tYlo, const CUtensorMap &tRes, KronArgs &a) {
   static thread_local bool configured = false;
   static thread_local int fit = 0;
-  auto kern = kron_pair_kernel;
+  auto kern = a.dbg ? kron_pair_kernel<true> : kron_pair_kernel<false>;
   if (!configured) {
-    B2O_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KP_SMEM));
+    B2O_CUDA(cudaFuncSetAttribute(kron_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KP_SMEM));
+    B2O_CUDA(cudaFuncSetAttribute(kron_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KP_SMEM));
     configured = true;
   }
   cudaLaunchConfig_t cfg;

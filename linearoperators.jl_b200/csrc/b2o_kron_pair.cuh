@@ -18,8 +18,8 @@
 //   epilogue = 32-column chunks through two 16 KB staging buffers -> TMA stores (Y as a bf16 hi/lo pair, the result as bf16 /
 //              fp32); the peer's epilogue warps release an accumulator with a remote arrive on the leader's barrier.
 // Units of a cluster are software-pipelined like in kron_cluster_kernel: GEMM 1 of unit i+1 runs before GEMM 2 of unit i.
-// Measured (profiles/r2_kron.jsonl, r2_kron_pair_timeline_v1.jsonl): 64 right-hand sides 54 us = 636 TFLOP/s algorithmic, 954 issued
-// (single-CTA kernel: 80 us); tensor pipe 55 % of active cycles.  What bounds it now: with all 148 SMs streaming operands the chip
+// Measured (profiles/r2_kron_pair.jsonl, r2_kron_pair_timeline_v*.jsonl): 64 right-hand sides 49.5 us = 694 TFLOP/s algorithmic, 1041
+// issued (single-CTA kernel: 80 us; first version of this kernel 54 us, tensor pipe 55 % of active cycles); 296: 769 TFLOP/s.  What bounds it now: with all 148 SMs streaming operands the chip
 // sits at the L2 -> SM ceiling (a GEMM 1 tile takes 3.7 us for 256 KB per CTA = 10.2 TB/s chip-wide, a GEMM 2 tile 5.2 us for
 // 384 KB = 10.9 TB/s; ~6300 B/clk x 1.7 GHz), i.e. ~19.5 us of MMA issue per unit against 12.9 us at the nominal tensor rate, and
 // the epilogue of a tile (8 chunks x ~0.55 us of TMEM load, conversion, proxy fence, barrier, store issue) is as long as the MMAs
@@ -39,19 +39,34 @@ __device__ __forceinline__ uint32_t kp_mapa(uint32_t addr, uint32_t cta) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
   return r;
 }
+// CLUSTER = true only where the arrivals come from the peer CTA (tmem_empty): an acquire at cluster scope makes ptxas put a
+// CCTL.IVALL (L1 invalidate) into every polling iteration -- 10 % of the kernel's warp samples when every wait had it
+// (ncu source page, profiles/r2_ncu_summary.md)
+template <bool CLUSTER = false>
 __device__ __forceinline__ void kp_wait(uint64_t *bar, uint32_t parity) {
   uint32_t done = 0, it = 0;
   unsigned long long t0 = 0;
   for (;;) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, P1;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
+    if (CLUSTER)
+      asm volatile(
+          "{\n"
+          ".reg .pred P1;\n"
+          "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n"
+          "selp.u32 %0, 1, 0, P1;\n"
+          "}\n"
+          : "=r"(done)
+          : "r"(smem_u32(bar)), "r"(parity)
+          : "memory");
+    else
+      asm volatile(
+          "{\n"
+          ".reg .pred P1;\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+          "selp.u32 %0, 1, 0, P1;\n"
+          "}\n"
+          : "=r"(done)
+          : "r"(smem_u32(bar)), "r"(parity)
+          : "memory");
     if (done) break;
     if ((++it & 1023u) == 0) {
       const unsigned long long t = globaltimer_ns();
@@ -89,8 +104,11 @@ __device__ __forceinline__ void kp_commit(uint64_t *bar) {
                "h"((uint16_t)3)
                : "memory");
 }
+// The arrive that hands an accumulator back orders nothing in memory (the TMEM reads are complete: tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync precede it, the MMA warp issues tcgen05.fence::after_thread_sync behind its wait): relaxed.
+// A release at cluster scope costs a MEMBAR + ERRBAR per warp and tile (10 % of the warp samples).
 __device__ __forceinline__ void kp_arrive_cl(uint32_t bar_cl) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cl) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cl) : "memory");
 }
 __device__ __forceinline__ void kp_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
@@ -103,6 +121,9 @@ __device__ __forceinline__ void kp_store_wait_read1() { asm volatile("cp.async.b
     }                                                \
   } while (0)
 
+// DBG: the %globaltimer stamps of tools/kron_pair_dbg.py are compiled in only for the debug instantiation (their predicated-off
+// LDC / CS2R / STG still took 15 % of the epilogue's issue slots in the production kernel)
+template <bool DBG>
 __global__ void __launch_bounds__(KR_THREADS, 1)
 kron_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmX,
                  const __grid_constant__ CUtensorMap tmYld, const __grid_constant__ CUtensorMap tmB2,
@@ -119,7 +140,7 @@ kron_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   const uint32_t crank = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);
   const int cid = __shfl_sync(0xffffffffu, (int)cluster_id_x(), 0), ncl = __shfl_sync(0xffffffffu, (int)nclusters_x(), 0);
   const bool leader = crank == 0;
-  if (threadIdx.x == 0 && p.dbg && blockIdx.x == 0) p.dbg[0] = gtimer();
+  if (DBG && threadIdx.x == 0 && p.dbg && blockIdx.x == 0) p.dbg[0] = gtimer();
   if (threadIdx.x == 32) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
@@ -232,9 +253,9 @@ kron_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           for (int t = 0; t < nt; ++t) {
             const uint32_t acc = tcount & 1u, tpar = (tcount >> 1) & 1u;
             const uint32_t tmem_acc = tmem_base + acc * KP_TCOLS;
-            kp_wait(&tmem_empty[acc], tpar ^ 1u);       // both CTAs' epilogues have drained this accumulator
+            kp_wait<true>(&tmem_empty[acc], tpar ^ 1u); // both CTAs' epilogues have drained this accumulator (remote arrives)
             tc_fence_after();
-            if (p.dbg && p.dbg_tile < 0 && blockIdx.x == 0 && lane == 0 && tcount < 8) p.dbg[16 + 2 * tcount] = gtimer();
+            if (DBG && p.dbg && p.dbg_tile < 0 && blockIdx.x == 0 && lane == 0 && tcount < 8) p.dbg[16 + 2 * tcount] = gtimer();
             for (int ks = 0; ks < ksteps; ++ks) {
               const uint32_t s0 = slot, p0 = sphase;
               KP_ADVANCE(1);
@@ -272,7 +293,7 @@ kron_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
               }
               __syncwarp();
             }
-            if (p.dbg && p.dbg_tile < 0 && blockIdx.x == 0 && lane == 0 && tcount < 8) p.dbg[17 + 2 * tcount] = gtimer();
+            if (DBG && p.dbg && p.dbg_tile < 0 && blockIdx.x == 0 && lane == 0 && tcount < 8) p.dbg[17 + 2 * tcount] = gtimer();
             ++tcount;
           }
         }
@@ -290,13 +311,13 @@ kron_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           const uint32_t tmem_acc = tmem_base + acc * KP_TCOLS;
           kp_wait(&tmem_full[acc], tpar);
           tc_fence_after();
-          if (p.dbg && p.dbg_tile < 0 && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 8) p.dbg[48 + 2 * tcount] = gtimer();
+          if (DBG && p.dbg && p.dbg_tile < 0 && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 8) p.dbg[48 + 2 * tcount] = gtimer();
 #pragma unroll 1
           for (int c0 = 0; c0 < KP_TN; c0 += 32) {
             const int col0 = t * KP_TN + c0;
             if (col0 >= p.N1) break;
             uint32_t v[32];
-            const bool stamp = p.dbg && p.dbg_tile == (int)tcount && blockIdx.x == 0 && threadIdx.x == 64;
+            const bool stamp = DBG && p.dbg && p.dbg_tile == (int)tcount && blockIdx.x == 0 && threadIdx.x == 64;
             if (stamp) p.dbg[16 + 5 * (c0 >> 5)] = gtimer();
             tc_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
             if (stamp) p.dbg[17 + 5 * (c0 >> 5)] = gtimer();
@@ -357,7 +378,7 @@ kron_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           tc_fence_before();
           __syncwarp();
           if (lane == 0) kp_arrive_cl(te_leader + acc * 8u);
-          if (p.dbg && p.dbg_tile < 0 && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 8) p.dbg[49 + 2 * tcount] = gtimer();
+          if (DBG && p.dbg && p.dbg_tile < 0 && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 8) p.dbg[49 + 2 * tcount] = gtimer();
           ++tcount;
         }
         if (p.y_tma) {
@@ -380,13 +401,13 @@ kron_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           const uint32_t tmem_acc = tmem_base + acc * KP_TCOLS;
           kp_wait(&tmem_full[acc], tpar);
           tc_fence_after();
-          if (p.dbg && p.dbg_tile < 0 && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 8) p.dbg[48 + 2 * tcount] = gtimer();
+          if (DBG && p.dbg && p.dbg_tile < 0 && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 8) p.dbg[48 + 2 * tcount] = gtimer();
 #pragma unroll 1
           for (int c0 = 0; c0 < KP_TN; c0 += 32) {
             const int n0 = t * KP_TN + c0;
             if (n0 >= p.N2) break;
             uint32_t v[32];
-            const bool stamp = p.dbg && p.dbg_tile == (int)tcount && blockIdx.x == 0 && threadIdx.x == 64;
+            const bool stamp = DBG && p.dbg && p.dbg_tile == (int)tcount && blockIdx.x == 0 && threadIdx.x == 64;
             if (stamp) p.dbg[16 + 5 * (c0 >> 5)] = gtimer();
             tc_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
             if (stamp) p.dbg[17 + 5 * (c0 >> 5)] = gtimer();
@@ -429,7 +450,7 @@ kron_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           tc_fence_before();
           __syncwarp();
           if (lane == 0) kp_arrive_cl(te_leader + acc * 8u);
-          if (p.dbg && p.dbg_tile < 0 && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 8) p.dbg[49 + 2 * tcount] = gtimer();
+          if (DBG && p.dbg && p.dbg_tile < 0 && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 8) p.dbg[49 + 2 * tcount] = gtimer();
           ++tcount;
         }
       }
@@ -439,7 +460,7 @@ kron_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                               // the leader's MMAs into the peer's TMEM / arrives on the peer are all done
-  if (threadIdx.x == 0 && p.dbg && blockIdx.x == 0) p.dbg[10] = gtimer();
+  if (DBG && threadIdx.x == 0 && p.dbg && blockIdx.x == 0) p.dbg[10] = gtimer();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * KP_TCOLS) : "memory");
 }
 #undef KP_ADVANCE

@@ -69,10 +69,14 @@ def test_kron_uses_tcgen05_and_tensor_tma(sass):
 def test_kron_pair_kernel_uses_cta_group_2(sass):
     """the batched kron kernel: tcgen05.mma.cta_group::2 issued back to back, both CTAs' tensor-map loads completing on the
     leader's barrier (.2CTA), multicast commits to both CTAs, no waterfall loop around the issue"""
-    ks = _of(sass, r"kron_pair_kernel")
+    assert len(_of(sass, r"kron_pair_kernel")) == 2            # production + the instantiation with the %globaltimer stamps
+    ks = _of(sass, r"kron_pair_kernelILb0")
     assert len(ks) == 1
     (name, ins), = ks.items()
     text = "\n".join(ins)
+    # polling loops acquire at CTA scope (a cluster-scope acquire puts an L1 invalidate into every iteration): the only CCTL.IVALL
+    # left are the cluster barriers of set-up / tear-down and the one wait whose arrivals are remote (tmem_empty)
+    assert text.count("CCTL.IVALL") <= 8, text.count("CCTL.IVALL")
     assert text.count("UTCHMMA.2CTA") == 12, name              # 4 (GEMM 1) + 8 (GEMM 2: hi and lo) per ring item
     assert "UTCHMMA" not in text.replace("UTCHMMA.2CTA", ""), name
     assert text.count("UTMALDG.2D.2CTA") + text.count("UTMALDG.3D.2CTA") == 5, name
