@@ -26,7 +26,7 @@ def _newer(target, deps):
 
 
 def build_lib(force=False, verbose=False):
-    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inc"))]
     hdrs.append(os.path.join(HERE, "..", "include", "b2o.h"))
     objs, jobs = [], []
     for src in SOURCES:
