@@ -39,11 +39,7 @@ void b2o_set_error(const char *fmt, ...);
 #define B2O_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 
 // ------------------------------------------------------------------ context
-constexpr int B2O_MAX_COLS = 128;      // column streams one launch can address
-constexpr int B2O_MAX_GRID = 1024;     // upper bound on persistent grid
-constexpr int B2O_WS_DOTS = 1024;      // doubles reserved for reduced scalars
-constexpr int B2O_WS_SWEEP = 512;      // [512, 512+129): inner products of the last fused two-loop launch, sweep order
-constexpr int B2O_WS_QNDBG = 768;      // [768, 771): mailbox timing accumulators (ns waited for local CTAs, ns in the exchange, epochs)
+#include "b2o_shared_defs.h"
 
 struct b2o_ctx_s {
   int device = 0;
@@ -95,17 +91,6 @@ struct b2o_ctx_s {
   unsigned long long mbox_epoch = 0;
 };
 
-// ---- peer mailbox layout (one per GPU): vals[2][8][128] doubles, then flags[8] u64
-constexpr int MBOX_MAXV = 128, MBOX_MAXR = 8;
-constexpr size_t MBOX_FLAGS_OFF = sizeof(double) * 2 * MBOX_MAXR * MBOX_MAXV;
-constexpr size_t MBOX_BYTES = MBOX_FLAGS_OFF + sizeof(unsigned long long) * MBOX_MAXR;
-struct MboxDev {
-  double *vals[MBOX_MAXR];                 // vals region of every rank's mailbox (own entry = local memory)
-  unsigned long long *flags[MBOX_MAXR];
-  unsigned long long *ready;               // local "dots are published" flag for the other CTAs of this GPU
-  int nranks, rank;
-  unsigned long long epoch_base;           // epoch of the first all-reduce of this launch is epoch_base + 1
-};
 void b2o_mbox_fill(b2o_ctx *ctx, MboxDev *m);   // nranks = 1 when the mailbox is not connected
 
 int b2o_allreduce_sum_f64(b2o_ctx *ctx, double *dptr, int count);  // no-op when nranks == 1

@@ -52,7 +52,11 @@ using CompactArgs = CompactArgsT<double>;
 template <int R, int OP, typename T = double>
 __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_compact_kernel(const __grid_constant__ CompactArgsT<T> p) {
   constexpr int EPT = R / B2O_NCONS;
+#ifdef B2O_SIMT_EMU
+  unsigned char *smem_raw = emu::dyn_smem();
+#else
   extern __shared__ __align__(128) unsigned char smem_raw[];
+#endif
   Ring rg;
   rg.buf = smem_raw;
   double *accs = reinterpret_cast<double *>(smem_raw + p.accs_off);
@@ -394,12 +398,20 @@ struct TwoLoopArgsT {
 };
 using TwoLoopArgs = TwoLoopArgsT<double>;
 
+#ifdef B2O_SIMT_EMU
+inline void fence_proxy_async() {}
+#else
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+#endif
 
 template <int R, typename T = double>
 __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_kernel(const __grid_constant__ TwoLoopArgsT<T> p) {
   constexpr int EPT = R / B2O_NCONS;
+#ifdef B2O_SIMT_EMU
+  unsigned char *smem_raw = emu::dyn_smem();
+#else
   extern __shared__ __align__(128) unsigned char smem_raw[];
+#endif
   Ring rg;
   rg.buf = smem_raw;
   double *sred = reinterpret_cast<double *>(smem_raw + p.coef_off);  // [8] warp partials + [8..8+64) α_i

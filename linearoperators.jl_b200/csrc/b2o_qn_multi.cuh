@@ -105,9 +105,13 @@ __device__ __forceinline__ unsigned fold_loaded(const double (&a)[EPT]) {
   for (int j = 0; j < EPT; j += 2) v ^= (unsigned)__double2hiint(a[j]);
   return v;
 }
+#ifdef B2O_SIMT_EMU
+inline void smem_reads_landed(unsigned *cell, unsigned v) { *cell = v; }
+#else
 __device__ __forceinline__ void smem_reads_landed(unsigned *cell, unsigned v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(smem_u32(cell)), "r"(v) : "memory");
 }
+#endif
 
 template <int NR>
 struct MultiTile {
@@ -119,7 +123,11 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_multi_kernel(const __grid_
   constexpr int R = MultiTile<NR>::R;
   constexpr int EPT = R / B2O_NCONS;
   constexpr int LPG = 32 / NR;   // lanes per right-hand-side group after the transposing reduce
+#ifdef B2O_SIMT_EMU
+  unsigned char *smem_raw = emu::dyn_smem();
+#else
   extern __shared__ __align__(128) unsigned char smem_raw[];
+#endif
   Ring rg;
   rg.buf = smem_raw;
   double *wacc = reinterpret_cast<double *>(smem_raw + p.wacc_off);   // [8 warps][ncols][32 lanes]
@@ -473,7 +481,11 @@ struct TwoLoopMultiArgs {
 template <int R, int NR>
 __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_twoloop_multi_kernel(const __grid_constant__ TwoLoopMultiArgs p) {
   constexpr int EPT = R / B2O_NCONS;
+#ifdef B2O_SIMT_EMU
+  unsigned char *smem_raw = emu::dyn_smem();
+#else
   extern __shared__ __align__(128) unsigned char smem_raw[];
+#endif
   Ring rg;
   rg.buf = smem_raw;
   double *alphas = reinterpret_cast<double *>(smem_raw + p.scal_off);   // [B2O_MAX_MEM][NR]

@@ -11,7 +11,11 @@
 // (VN = 2 for Float64, 4 for Float32).  The kernels are templates on the element type T; inner products are always
 // accumulated in double, elementwise statements run in T with the reference's rounding (no contraction).
 #pragma once
+#ifdef B2O_SIMT_EMU
+#include "b2o_shared_defs.h"   // host SIMT emulator (tests/emu): the emulator header supplies mbarrier / bulk-copy / barrier stand-ins
+#else
 #include "b2o_internal.cuh"
+#endif
 
 template <typename T>
 struct Vec16;
@@ -37,6 +41,12 @@ __device__ __forceinline__ void vec_unpack(const float4 &v, float *o) {
 }
 __device__ __forceinline__ double2 vec_pack(const double *o) { return make_double2(o[0], o[1]); }
 __device__ __forceinline__ float4 vec_pack(const float *o) { return make_float4(o[0], o[1], o[2], o[3]); }
+#ifdef B2O_SIMT_EMU
+inline float4 ldg_stream16(const float *p) { return make_float4(p[0], p[1], p[2], p[3]); }
+inline double2 ldg_stream16(const double *p) { return make_double2(p[0], p[1]); }
+inline void stg_stream16(float *p, float4 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w; }
+inline void stg_stream16(double *p, double2 v) { p[0] = v.x; p[1] = v.y; }
+#else
 __device__ __forceinline__ float4 ldg_stream16(const float *p) {
   float4 r;
   asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
@@ -47,6 +57,7 @@ __device__ __forceinline__ void stg_stream16(float *p, float4 v) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 __device__ __forceinline__ void stg_stream16(double *p, double2 v) { stg_stream2(p, v); }
+#endif
 
 constexpr int B2O_NCONS = 256;                     // consumer threads
 constexpr int B2O_NTHREADS = B2O_NCONS + 32;       // + producer warp
@@ -72,7 +83,11 @@ struct RingPos {
   }
 };
 
+#ifdef B2O_SIMT_EMU
+inline void consumers_sync() { emu::named_barrier_sync(1, B2O_NCONS); }
+#else
 __device__ __forceinline__ void consumers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(B2O_NCONS) : "memory"); }
+#endif
 
 template <int R, typename T>
 __device__ __forceinline__ void producer_push(const Ring &rg, RingPos &pos, const T *src) {

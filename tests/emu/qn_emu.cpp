@@ -1,0 +1,190 @@
+// qn_emu.cpp -- host build of the streaming quasi-Newton kernels (csrc/b2o_stream.cuh, b2o_qn_kernels.cuh, b2o_qn_multi.cuh) under the
+// SIMT emulator (TEST INFRASTRUCTURE).  One block of 288 OS threads runs the product's own kernel bodies: the TMA ring protocol
+// (mbarrier phases, slot hand-back, producer / consumer item order), the sweep bookkeeping of the two-loop recursion and of its block
+// variant, ragged tiles and unaligned user vectors are checked on a CPU box -- including rings with FEWER slots than a tile has items
+// (the deadlock class that cost a GPU lease in round 2).  It says nothing about PTX, memory ordering or speed.
+#include <atomic>
+#include "simt_emu.h"
+
+namespace emu_qn {
+#include "../../linearoperators.jl_b200/csrc/b2o_shared_defs.h"
+// ---- CUDA vocabulary of these headers that simt_emu.h does not carry
+struct float4 {
+  float x, y, z, w;
+};
+inline double2 make_double2(double a, double b) { return double2{a, b}; }
+inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
+inline double2 ldg_stream2(const double *p) { return double2{p[0], p[1]}; }
+inline void stg_stream2(double *p, double2 v) {
+  p[0] = v.x;
+  p[1] = v.y;
+}
+inline int __double2hiint(double d) {
+  uint64_t u;
+  memcpy(&u, &d, 8);
+  return (int)(u >> 32);
+}
+inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline void __nanosleep(unsigned) { std::this_thread::yield(); }
+inline unsigned long long ld_acquire_u64(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void st_release_gpu_u64(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline unsigned long long globaltimer_ns() { return 0; }
+inline void mbox_allreduce_warp(const MboxDev &, unsigned long long, double *, int) {
+  fprintf(stderr, "emu: the NVLink mailbox is not emulated\n");
+  abort();
+}
+// blocks run one after the other under the emulator: a grid barrier can only be met by a grid of ONE block
+inline void grid_barrier(unsigned long long *ctr, unsigned long long target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (gridDim.x != 1) {
+      fprintf(stderr, "emu: grid barrier with %u blocks\n", gridDim.x);
+      abort();
+    }
+    atomicAdd(ctr, 1ULL);
+    while (ld_acquire_u64(ctr) < target) std::this_thread::yield();
+  }
+  __syncthreads();
+}
+#include "../../linearoperators.jl_b200/csrc/b2o_qn_multi.cuh"
+}  // namespace emu_qn
+using namespace emu_qn;
+#define EMU_API __attribute__((visibility("default")))
+
+namespace {
+struct Work {
+  std::vector<double> partials = std::vector<double>((size_t)B2O_MAX_GRID * B2O_MAX_COLS, 0.0), dots = std::vector<double>(B2O_WS_DOTS, 0.0);
+  unsigned long long bar[2] = {0, 0};
+};
+constexpr int R = 1024;
+}  // namespace
+
+extern "C" {
+// forward LBFGSOperator / LSR1Operator apply on ONE emulated CTA.  cols: [ncols][pitch] (pitch a multiple of R, zero padded, 16-byte aligned)
+EMU_API int emu_qn_compact(int op, int64_t n, int64_t pitch, int ncols, const double *cols, const double *cdiv, const double *x, double *res,
+                           double alpha, double beta, double gamma, int scaling, int stages) {
+  Work w;
+  CompactArgsT<double> a;
+  memset(&a, 0, sizeof(a));
+  for (int c = 0; c < ncols; ++c) {
+    a.cols[c] = cols + (size_t)c * pitch;
+    a.cdiv[c] = cdiv ? cdiv[c] : 1.0;
+  }
+  a.ncols = ncols;
+  a.x = x;
+  a.res = res;
+  a.n = n;
+  a.ntiles = (n + R - 1) / R;
+  a.alpha = alpha;
+  a.beta = beta;
+  a.gamma = gamma;
+  a.scaling = scaling;
+  a.x_al16 = ((uintptr_t)x % 16) == 0;
+  a.res_al16 = ((uintptr_t)res % 16) == 0;
+  a.partials = w.partials.data();
+  a.dots = w.dots.data();
+  a.bar = &w.bar[0];
+  a.arrive = &w.bar[1];
+  a.bar_target = 1;
+  a.mode = ncols > 0 ? MODE_FUSED : MODE_PHASE2;
+  a.stages = stages;
+  a.group = std::max(1, std::min(ncols, 40));
+  const SmemLayout L = smem_layout(R, stages, a.group);
+  a.accs_off = (uint32_t)L.accs_off;
+  a.coef_off = (uint32_t)L.coef_off;
+  a.bar_off = (uint32_t)L.bar_off;
+  a.mbox.nranks = 1;
+  if (op == OP_LBFGS_FWD) {
+    void (*k)(const CompactArgsT<double>) = qn_compact_kernel<R, OP_LBFGS_FWD, double>;
+    B2O_LAUNCH(k, dim3(1), dim3(B2O_NTHREADS), L.total, nullptr, a);
+  } else {
+    void (*k)(const CompactArgsT<double>) = qn_compact_kernel<R, OP_LSR1, double>;
+    B2O_LAUNCH(k, dim3(1), dim3(B2O_NTHREADS), L.total, nullptr, a);
+  }
+  return 0;
+}
+
+// inverse two-loop recursion, vector (nrhs == 0: x, res are vectors) or block (nrhs columns with leading dimensions ldx, ldr; NR = 4 or 8).
+// S, Y: [A][pitch] newest -> oldest; q: [max(1, NR)][pitch] zeroed work vectors
+EMU_API int emu_qn_twoloop(int64_t n, int64_t pitch, int A, const double *S, const double *Y, const double *ys, const double *x, int64_t ldx,
+                           double *res, int64_t ldr, int nrhs, int NR, double *q, double alpha, double beta, double gamma, int scaling, int stages) {
+  Work w;
+  if (nrhs == 0) {
+    TwoLoopArgsT<double> a;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < A; ++i) {
+      a.s[i] = S + (size_t)i * pitch;
+      a.y[i] = Y + (size_t)i * pitch;
+      a.ys[i] = ys[i];
+    }
+    a.nact = A;
+    a.x = x;
+    a.res = res;
+    a.q = q;
+    a.n = n;
+    a.ntiles = (n + R - 1) / R;
+    a.alpha = alpha;
+    a.beta = beta;
+    a.gamma = gamma;
+    a.scaling = scaling;
+    a.x_al16 = ((uintptr_t)x % 16) == 0;
+    a.res_al16 = ((uintptr_t)res % 16) == 0;
+    a.partials = w.partials.data();
+    a.dots = w.dots.data();
+    a.bar = &w.bar[0];
+    a.arrive = &w.bar[1];
+    a.bar_target = 1;
+    a.stages = stages;
+    const SmemLayout L = smem_layout(R, stages, 0);
+    a.coef_off = (uint32_t)L.coef_off;
+    a.bar_off = (uint32_t)L.bar_off;
+    a.sweep_begin = 0;
+    a.sweep_end = 2 * A + 1;
+    a.mbox.nranks = 1;
+    void (*k)(const TwoLoopArgsT<double>) = qn_twoloop_kernel<R, double>;
+    B2O_LAUNCH(k, dim3(1), dim3(B2O_NTHREADS), L.total, nullptr, a);
+    return 0;
+  }
+  TwoLoopMultiArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int i = 0; i < A; ++i) {
+    a.s[i] = S + (size_t)i * pitch;
+    a.y[i] = Y + (size_t)i * pitch;
+    a.ys[i] = ys[i];
+  }
+  a.nact = A;
+  a.x = x;
+  a.res = res;
+  a.ldx = ldx;
+  a.ldr = ldr;
+  a.nrhs = nrhs;
+  a.q = q;
+  a.qpitch = pitch;
+  a.n = n;
+  a.ntiles = (n + R - 1) / R;
+  a.alpha = alpha;
+  a.beta = beta;
+  a.gamma = gamma;
+  a.scaling = scaling;
+  a.x_al16 = ((uintptr_t)x % 16) == 0 && (nrhs == 1 || ldx % 2 == 0);
+  a.res_al16 = ((uintptr_t)res % 16) == 0 && (nrhs == 1 || ldr % 2 == 0);
+  a.partials = w.partials.data();
+  a.bar = &w.bar[0];
+  a.bar_target = 1;
+  a.stages = stages;
+  const size_t scal = (size_t)(B2O_MAX_MEM + B2O_CONS_WARPS + 1) * NR * sizeof(double);
+  a.scal_off = (uint32_t)((size_t)stages * R * sizeof(double));
+  a.bar_off = (uint32_t)(a.scal_off + scal);
+  a.landed_off = (uint32_t)(a.bar_off + (size_t)2 * stages * sizeof(uint64_t));
+  const size_t total = a.landed_off + B2O_NCONS * sizeof(unsigned);
+  if (NR == 4) {
+    void (*k)(const TwoLoopMultiArgs) = qn_twoloop_multi_kernel<R, 4>;
+    B2O_LAUNCH(k, dim3(1), dim3(B2O_NTHREADS), total, nullptr, a);
+  } else {
+    void (*k)(const TwoLoopMultiArgs) = qn_twoloop_multi_kernel<R, 8>;
+    B2O_LAUNCH(k, dim3(1), dim3(B2O_NTHREADS), total, nullptr, a);
+  }
+  return 0;
+}
+}
