@@ -105,6 +105,134 @@ EMU_API int emu_qn_compact(int op, int64_t n, int64_t pitch, int ncols, const do
   return 0;
 }
 
+// the same kernels instantiated for Float32 (LBFGSOperator(Float32, n)): forward apply (inverse = 0) or two-loop recursion (inverse = 1).
+// cols / S, Y: float [..][pitch]; q: float [pitch] zeroed
+EMU_API int emu_qn_f32(int inverse, int64_t n, int64_t pitch, int ncols, const float *c0, const float *c1, const double *ys, const float *x, float *res,
+                       float *q, double alpha, double beta, double gamma, int scaling, int stages) {
+  Work w;
+  if (!inverse) {
+    CompactArgsT<float> a;
+    memset(&a, 0, sizeof(a));
+    for (int c = 0; c < ncols; ++c) {
+      a.cols[c] = c0 + (size_t)c * pitch;
+      a.cdiv[c] = 1.0;
+    }
+    a.ncols = ncols;
+    a.x = x;
+    a.res = res;
+    a.n = n;
+    a.ntiles = (n + R - 1) / R;
+    a.alpha = alpha;
+    a.beta = beta;
+    a.gamma = gamma;
+    a.scaling = scaling;
+    a.x_al16 = ((uintptr_t)x % 16) == 0;
+    a.res_al16 = ((uintptr_t)res % 16) == 0;
+    a.partials = w.partials.data();
+    a.dots = w.dots.data();
+    a.bar = &w.bar[0];
+    a.arrive = &w.bar[1];
+    a.bar_target = 1;
+    a.mode = ncols > 0 ? MODE_FUSED : MODE_PHASE2;
+    a.stages = stages;
+    a.group = std::max(1, std::min(ncols, 40));
+    const SmemLayout L = smem_layout(R, stages, a.group, sizeof(float));
+    a.accs_off = (uint32_t)L.accs_off;
+    a.coef_off = (uint32_t)L.coef_off;
+    a.bar_off = (uint32_t)L.bar_off;
+    a.mbox.nranks = 1;
+    void (*k)(const CompactArgsT<float>) = qn_compact_kernel<R, OP_LBFGS_FWD, float>;
+    B2O_LAUNCH(k, dim3(1), dim3(B2O_NTHREADS), L.total, nullptr, a);
+    return 0;
+  }
+  TwoLoopArgsT<float> a;
+  memset(&a, 0, sizeof(a));
+  for (int i = 0; i < ncols; ++i) {
+    a.s[i] = c0 + (size_t)i * pitch;
+    a.y[i] = c1 + (size_t)i * pitch;
+    a.ys[i] = ys[i];
+  }
+  a.nact = ncols;
+  a.x = x;
+  a.res = res;
+  a.q = q;
+  a.n = n;
+  a.ntiles = (n + R - 1) / R;
+  a.alpha = alpha;
+  a.beta = beta;
+  a.gamma = gamma;
+  a.scaling = scaling;
+  a.x_al16 = ((uintptr_t)x % 16) == 0;
+  a.res_al16 = ((uintptr_t)res % 16) == 0;
+  a.partials = w.partials.data();
+  a.dots = w.dots.data();
+  a.bar = &w.bar[0];
+  a.arrive = &w.bar[1];
+  a.bar_target = 1;
+  a.stages = stages;
+  const SmemLayout L = smem_layout(R, stages, 0, sizeof(float));
+  a.coef_off = (uint32_t)L.coef_off;
+  a.bar_off = (uint32_t)L.bar_off;
+  a.sweep_begin = 0;
+  a.sweep_end = 2 * ncols + 1;
+  a.mbox.nranks = 1;
+  void (*k)(const TwoLoopArgsT<float>) = qn_twoloop_kernel<R, float>;
+  B2O_LAUNCH(k, dim3(1), dim3(B2O_NTHREADS), L.total, nullptr, a);
+  return 0;
+}
+
+// block apply mul!(Res, op, X) of the forward operator (op 0) or L-SR1 (op 1): qn_multi_kernel<NR, OP> on one emulated CTA
+EMU_API int emu_qn_multi(int op, int NR, int64_t n, int64_t pitch, int ncols, const double *cols, const double *cdiv, const double *x, int64_t ldx,
+                         double *res, int64_t ldr, int nrhs, double alpha, double beta, double gamma, int scaling, int stages) {
+  Work w;
+  MultiArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int c = 0; c < ncols; ++c) {
+    a.cols[c] = cols + (size_t)c * pitch;
+    a.cdiv[c] = cdiv ? cdiv[c] : 1.0;
+  }
+  a.ncols = ncols;
+  a.x = x;
+  a.res = res;
+  a.ldx = ldx;
+  a.ldr = ldr;
+  a.nrhs = nrhs;
+  a.n = n;
+  const int RR = NR == 8 ? 1024 : 2048;
+  a.ntiles = (n + RR - 1) / RR;
+  a.alpha = alpha;
+  a.beta = beta;
+  a.gamma = gamma;
+  a.scaling = scaling;
+  a.x_al16 = ((uintptr_t)x % 16) == 0 && (nrhs == 1 || ldx % 2 == 0);
+  a.res_al16 = ((uintptr_t)res % 16) == 0 && (nrhs == 1 || ldr % 2 == 0);
+  const int nv = ncols * NR;
+  a.partials = w.partials.data();
+  a.dots = w.dots.data();
+  a.bar = &w.bar[0];
+  a.bar_target = 1;
+  a.stages = stages;
+  a.wacc_off = (uint32_t)((size_t)stages * RR * sizeof(double));
+  a.coef_off = (uint32_t)(a.wacc_off + (size_t)B2O_CONS_WARPS * ncols * 32 * sizeof(double));
+  a.bar_off = (uint32_t)(a.coef_off + (size_t)nv * sizeof(double));
+  a.landed_off = (uint32_t)(a.bar_off + (size_t)2 * stages * sizeof(uint64_t));
+  const size_t total = a.landed_off + B2O_NCONS * sizeof(unsigned);
+  a.mbox.nranks = 1;
+#define EMU_MULTI(NRv, OPv)                                                 \
+  {                                                                         \
+    void (*k)(const MultiArgs) = qn_multi_kernel<NRv, OPv>;                 \
+    B2O_LAUNCH(k, dim3(1), dim3(B2O_NTHREADS), total, nullptr, a);          \
+    return 0;                                                               \
+  }
+  if (op == 0 && NR == 2) EMU_MULTI(2, OP_LBFGS_FWD)
+  if (op == 0 && NR == 4) EMU_MULTI(4, OP_LBFGS_FWD)
+  if (op == 0 && NR == 8) EMU_MULTI(8, OP_LBFGS_FWD)
+  if (op == 1 && NR == 4) EMU_MULTI(4, OP_LSR1)
+  if (op == 1 && NR == 8) EMU_MULTI(8, OP_LSR1)
+#undef EMU_MULTI
+  return 1;
+}
+
 // inverse two-loop recursion, vector (nrhs == 0: x, res are vectors) or block (nrhs columns with leading dimensions ldx, ldr; NR = 4 or 8).
 // S, Y: [A][pitch] newest -> oldest; q: [max(1, NR)][pitch] zeroed work vectors
 EMU_API int emu_qn_twoloop(int64_t n, int64_t pitch, int A, const double *S, const double *Y, const double *ys, const double *x, int64_t ldx,

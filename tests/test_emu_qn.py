@@ -158,3 +158,99 @@ def test_block_twoloop_equals_vector_kernel_bit_for_bit(emu, NR, nrhs, stages):
                                alpha, beta, 0.8, 1, 7)
             assert np.array_equal(Res[j, :n], rv), (j, rel(Res[j, :n], rv))
             assert rel(rv, numpy_twoloop(S[:, :n], Y[:, :n], ys, xv, alpha, beta, 0.8, R0[j])) <= 1e-14
+
+
+def aligned32(shape, offset=0):
+    n = int(np.prod(shape))
+    raw = np.zeros(n + 16, dtype=np.float32)
+    start = (-(raw.ctypes.data // 4) % 4 + offset // 4) % 16
+    return raw[start:start + n].reshape(shape)
+
+
+def setup_f32(emu):
+    i32, i64, d, vp = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
+    emu.emu_qn_f32.restype = i32
+    emu.emu_qn_f32.argtypes = [i32, i64, i64, i32, vp, vp, vp, vp, vp, vp, d, d, d, i32, i32]
+    emu.emu_qn_multi.restype = i32
+    emu.emu_qn_multi.argtypes = [i32, i32, i64, i64, i32, vp, vp, vp, i64, vp, i64, i32, d, d, d, i32, i32]
+
+
+@pytest.mark.parametrize("n,off", [(2500, 0), (1027, 4), (4096, 12)])
+def test_float32_instantiations(emu, n, off):
+    """qn_compact_kernel<R, LBFGS_FWD, float> and qn_twoloop_kernel<R, float>: 16-byte vectors of FOUR rows, ragged tails, 4-byte
+    aligned views; Float32 statements, inner products in double rounded to Float32 (oracle/oracle_f32.py convention)"""
+    setup_f32(emu)
+    F = np.float32
+    rng = np.random.default_rng(n)
+    pitch = (n + R - 1) // R * R
+    npairs, gamma = 3, F(0.7)
+    cols = aligned32((2 * npairs, pitch))
+    cols[:, :n] = (0.1 * rng.random((2 * npairs, n))).astype(F)
+    x, res = aligned32(n, off), aligned32(n, off)
+    x[:] = rng.random(n).astype(F)
+    r0 = rng.random(n).astype(F)
+    dot = lambda a, b: F(np.dot(a.astype(np.float64), b.astype(np.float64)))
+    for alpha, beta in ((1.0, 0.0), (-0.75, 0.5)):
+        res[:] = r0
+        emu.emu_qn_f32(0, n, pitch, 2 * npairs, cols.ctypes.data, None, None, x.ctypes.data, res.ctypes.data, None, alpha, beta, float(gamma), 1, 5)
+        q = x / gamma
+        for k in range(npairs):
+            a, b = cols[2 * k, :n], cols[2 * k + 1, :n]
+            q = q + (dot(b, x) * b - dot(a, x) * a)
+        ref = F(alpha) * q + F(beta) * r0 if beta != 0 else F(alpha) * q
+        assert res.dtype == F and rel(res.astype(np.float64), ref.astype(np.float64)) <= 1e-6
+    A = 3
+    S, Y = aligned32((A, pitch)), aligned32((A, pitch))
+    S[:, :n] = rng.random((A, n)).astype(F)
+    Y[:, :n] = (S[:, :n] + F(0.1) * rng.random((A, n)).astype(F)).astype(F)
+    ys = aligned(A)
+    ys[:] = [float(dot(S[i, :n], Y[i, :n])) for i in range(A)]
+    q = aligned32(pitch)
+    res[:] = 0
+    emu.emu_qn_f32(1, n, pitch, A, S.ctypes.data, Y.ctypes.data, ys.ctypes.data, x.ctypes.data, res.ctypes.data, q.ctypes.data, 1.0, 0.0, 0.8, 1, 4)
+    qq, al = x.copy(), np.zeros(A, F)
+    for i in range(A):
+        al[i] = F(dot(S[i, :n], qq) / F(ys[i]))
+        qq = qq - al[i] * Y[i, :n]
+    qq = qq * F(0.8)
+    for i in range(A - 1, -1, -1):
+        qq = qq + F(al[i] - F(dot(Y[i, :n], qq) / F(ys[i]))) * S[i, :n]
+    assert rel(res.astype(np.float64), qq.astype(np.float64)) <= 1e-6
+
+
+@pytest.mark.parametrize("op,NR,nrhs,stages", [(0, 2, 2, 3), (0, 4, 3, 4), (0, 8, 8, 5), (0, 8, 5, 14), (1, 4, 4, 3), (1, 8, 7, 6)])
+def test_block_apply_kernel(emu, op, NR, nrhs, stages):
+    """qn_multi_kernel<NR, OP>: mul!(Res, op, X) for the forward operator and L-SR1, every column against the statement-level numpy
+    restatement (the block kernel is contracted and uses one reciprocal for the base term: a few ulp)"""
+    setup_f32(emu)
+    rng = np.random.default_rng(10 * NR + nrhs)
+    n = 4100
+    RR = 1024 if NR == 8 else 2048
+    ncols = 6 if op == 0 else 5
+    pitch = (n + 4095) // 4096 * 4096
+    cols = aligned((ncols, pitch))
+    cols[:, :n] = 0.1 * rng.random((ncols, n))
+    cdiv = aligned(ncols)
+    cdiv[:] = rng.random(ncols) + 0.5
+    ld = n + 2
+    X, Res = aligned((nrhs, ld)), aligned((nrhs, ld))
+    X[:, :n] = rng.random((nrhs, n))
+    R0 = rng.random((nrhs, n))
+    gamma = 0.7
+    for alpha, beta in ((1.0, 0.0), (-0.75, 0.5)):
+        Res[:, :n] = R0
+        assert emu.emu_qn_multi(op, NR, n, pitch, ncols, cols.ctypes.data, cdiv.ctypes.data, X.ctypes.data, ld, Res.ctypes.data, ld, nrhs,
+                                alpha, beta, gamma, 1, stages) == 0
+        for j in range(nrhs):
+            x = X[j, :n]
+            if op == 0:
+                q = x / gamma
+                for k in range(ncols // 2):
+                    a, b = cols[2 * k, :n], cols[2 * k + 1, :n]
+                    q = q + ((b @ x) * b - (a @ x) * a)
+                ref = alpha * q + beta * R0[j] if beta != 0 else alpha * q
+            else:
+                ref = (alpha * x) / gamma + (beta * R0[j] if beta != 0 else 0.0)
+                for k in range(ncols):
+                    ref = ref + ((alpha * (cols[k, :n] @ x)) / cdiv[k]) * cols[k, :n]
+            assert rel(Res[j, :n], ref) <= 1e-13, (j, rel(Res[j, :n], ref))
