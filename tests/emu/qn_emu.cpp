@@ -105,6 +105,54 @@ EMU_API int emu_qn_compact(int op, int64_t n, int64_t pitch, int ncols, const do
   return 0;
 }
 
+// one step of the a_k rebuild inside push! (src/lbfgs.jl:236-250 -> OP_PUSH_A; src/lsr1.jl:166-181 -> OP_PUSH_L): writes the unnormalised a_k to
+// `res` and returns the outgoing inner products (s_k.a_k; for L-SR1 also |a_k|^2) summed over the CTA partials like sum_partials_kernel
+EMU_API int emu_qn_push_step(int lsr1, int64_t n, int64_t pitch, int ncols, const double *cols, const double *cdiv, const double *sk, const double *yk,
+                             double *res, double gamma, int stages, double *out2) {
+  Work w;
+  CompactArgsT<double> a;
+  memset(&a, 0, sizeof(a));
+  for (int c = 0; c < ncols; ++c) {
+    a.cols[c] = cols + (size_t)c * pitch;
+    a.cdiv[c] = cdiv ? cdiv[c] : 1.0;
+  }
+  a.ncols = ncols;
+  a.x = sk;
+  a.res = res;
+  a.y2 = yk;
+  a.n = n;
+  a.ntiles = (n + R - 1) / R;
+  a.alpha = 1.0;
+  a.beta = 0.0;
+  a.gamma = gamma;
+  a.scaling = 1;
+  a.x_al16 = ((uintptr_t)sk % 16) == 0;
+  a.res_al16 = ((uintptr_t)res % 16) == 0;
+  a.partials = w.partials.data();
+  a.dots = w.dots.data();
+  a.bar = &w.bar[0];
+  a.arrive = &w.bar[1];
+  a.bar_target = 1;
+  a.mode = ncols > 0 ? MODE_FUSED : MODE_PHASE2;
+  a.stages = stages;
+  a.group = std::max(1, std::min(ncols, 40));
+  const SmemLayout L = smem_layout(R, stages, a.group);
+  a.accs_off = (uint32_t)L.accs_off;
+  a.coef_off = (uint32_t)L.coef_off;
+  a.bar_off = (uint32_t)L.bar_off;
+  a.mbox.nranks = 1;
+  if (lsr1) {
+    void (*k)(const CompactArgsT<double>) = qn_compact_kernel<R, OP_PUSH_L, double>;
+    B2O_LAUNCH(k, dim3(1), dim3(B2O_NTHREADS), L.total, nullptr, a);
+  } else {
+    void (*k)(const CompactArgsT<double>) = qn_compact_kernel<R, OP_PUSH_A, double>;
+    B2O_LAUNCH(k, dim3(1), dim3(B2O_NTHREADS), L.total, nullptr, a);
+  }
+  out2[0] = w.partials[(size_t)1 * ncols + 0];   // grid = 1: partials[grid*ncols + 2*cta + {0, 1}]
+  out2[1] = w.partials[(size_t)1 * ncols + 1];
+  return 0;
+}
+
 // the same kernels instantiated for Float32 (LBFGSOperator(Float32, n)): forward apply (inverse = 0) or two-loop recursion (inverse = 1).
 // cols / S, Y: float [..][pitch]; q: float [pitch] zeroed
 EMU_API int emu_qn_f32(int inverse, int64_t n, int64_t pitch, int ncols, const float *c0, const float *c1, const double *ys, const float *x, float *res,

@@ -254,3 +254,35 @@ def test_block_apply_kernel(emu, op, NR, nrhs, stages):
                 for k in range(ncols):
                     ref = ref + ((alpha * (cols[k, :n] @ x)) / cdiv[k]) * cols[k, :n]
             assert rel(Res[j, :n], ref) <= 1e-13, (j, rel(Res[j, :n], ref))
+
+
+@pytest.mark.parametrize("stages", [2, 6])
+def test_push_rebuild_steps(emu, stages):
+    """OP_PUSH_A (src/lbfgs.jl:239-248: a_k = s_k/γ, then `.+=` / `.-=` per older pair, dot(s_k, a_k) on the way out) and OP_PUSH_L
+    (src/lsr1.jl:169-179: a_k = y_k - s_k/γ, `.-=` per older column, a_k·s_k and |a_k|² on the way out)"""
+    i32, i64, d, vp = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
+    emu.emu_qn_push_step.restype = i32
+    emu.emu_qn_push_step.argtypes = [i32, i64, i64, i32, vp, vp, vp, vp, vp, d, i32, vp]
+    rng = np.random.default_rng(stages)
+    n, gamma = 2700, 0.6
+    pitch = (n + R - 1) // R * R
+    for nprev in (0, 1, 3):
+        cols = aligned((max(2 * nprev, 1), pitch))
+        cols[:2 * nprev, :n] = 0.1 * rng.random((2 * nprev, n))
+        sk, yk, res, out2 = aligned(pitch), aligned(pitch), aligned(n), aligned(2)
+        sk[:n], yk[:n] = rng.random(n), rng.random(n)
+        emu.emu_qn_push_step(0, n, pitch, 2 * nprev, cols.ctypes.data, None, sk.ctypes.data, yk.ctypes.data, res.ctypes.data, gamma, stages, out2.ctypes.data)
+        a = sk[:n] / gamma
+        for l in range(nprev):
+            al, bl = cols[2 * l, :n], cols[2 * l + 1, :n]
+            a = a + (bl @ sk[:n]) * bl
+            a = a - (al @ sk[:n]) * al
+        assert rel(res, a) <= 1e-14 and abs(out2[0] - sk[:n] @ a) <= 1e-13 * abs(sk[:n] @ a)
+        cdiv = aligned(max(nprev, 1))
+        cdiv[:] = rng.random(max(nprev, 1)) + 0.5
+        emu.emu_qn_push_step(1, n, pitch, nprev, cols.ctypes.data, cdiv.ctypes.data, sk.ctypes.data, yk.ctypes.data, res.ctypes.data, gamma, stages, out2.ctypes.data)
+        a = yk[:n] - sk[:n] / gamma
+        for l in range(nprev):
+            a = a - ((cols[l, :n] @ sk[:n]) / cdiv[l]) * cols[l, :n]
+        assert rel(res, a) <= 1e-14
+        assert abs(out2[0] - a @ sk[:n]) <= 1e-12 * max(1.0, abs(a @ sk[:n])) and abs(out2[1] - a @ a) <= 1e-13 * (a @ a)
