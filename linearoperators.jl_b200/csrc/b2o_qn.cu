@@ -41,6 +41,7 @@ static int qn32_apply(b2o_qn *q, float *res, const float *x, double alpha, doubl
 static int qn32_push(b2o_qn *q, const float *s, const float *y, int *accepted);
 static int qn32_push_damped(b2o_qn *q, const float *s, float *y, bool inverse_form, double alpha, const float *g, float *Bs, int *accepted);
 static int qn32_diag(b2o_qn *q, float *d);
+static int qn32_apply_multi(b2o_qn *q, float *res, int64_t ldr, const float *x, int64_t ldx, int nrhs, double alpha, double beta);
 #define B2O_F64_ONLY(q, what)                                                                                                    \
   do {                                                                                                                           \
     if ((q)->esize != 8) B2O_FAIL(B2O_EUNSUPPORTED, what " is not built for Float32 quasi-Newton operators (Float64 only)");      \
@@ -714,11 +715,11 @@ static int qn_apply_dev(b2o_qn *q, double *res, const double *x, double alpha, d
 }
 
 // ------------------------------------------------------------------ block apply: NR right-hand sides per column pass
-template <int NR>
-static int multi_launch(b2o_qn *q, const CompactArgs &base, double *res, int64_t ldr, const double *x, int64_t ldx, int nrhs) {
+template <int NR, typename T = double>
+static int multi_launch(b2o_qn *q, const CompactArgsT<T> &base, T *res, int64_t ldr, const T *x, int64_t ldx, int nrhs) {
   b2o_ctx *c = q->ctx;
-  constexpr int R = MultiTile<NR>::R;
-  MultiArgs a;
+  constexpr int R = MultiTile<NR, T>::R;
+  MultiArgsT<T> a;
   memset(&a, 0, sizeof(a));
   for (int i = 0; i < base.ncols; ++i) {
     a.cols[i] = base.cols[i];
@@ -738,18 +739,20 @@ static int multi_launch(b2o_qn *q, const CompactArgs &base, double *res, int64_t
   a.scaling = base.scaling;
   a.W = base.W;
   a.base_div = base.base_div;
-  a.x_al16 = ((uintptr_t)x % 16) == 0 && (nrhs == 1 || ldx % 2 == 0);
-  a.res_al16 = ((uintptr_t)res % 16) == 0 && (nrhs == 1 || ldr % 2 == 0);
+  constexpr int64_t VN = 16 / (int64_t)sizeof(T);   // elements per 16-byte vector: every column must start on one
+  a.x_al16 = ((uintptr_t)x % 16) == 0 && (nrhs == 1 || ldx % VN == 0);
+  a.res_al16 = ((uintptr_t)res % 16) == 0 && (nrhs == 1 || ldr % VN == 0);
   const int nv = a.ncols * NR;
   LaunchCfg cfg;
   cfg.R = R;
   cfg.group = 0;
   const size_t fixed = ((size_t)B2O_CONS_WARPS * a.ncols * 32 + nv) * sizeof(double) + B2O_NCONS * sizeof(unsigned);
-  int stages = c->stages > 0 ? std::max(2, c->stages) : std::max(3, (114688 + R * 4) / (R * 8));
-  while (stages > 2 && (size_t)stages * R * sizeof(double) + fixed + 2 * stages * sizeof(uint64_t) + 16 > B2O_MAX_DYN_SMEM) --stages;
+  const int tile_bytes = R * (int)sizeof(T);
+  int stages = c->stages > 0 ? std::max(2, c->stages) : std::max(3, (114688 + tile_bytes / 2) / tile_bytes);
+  while (stages > 2 && (size_t)stages * tile_bytes + fixed + 2 * stages * sizeof(uint64_t) + 16 > B2O_MAX_DYN_SMEM) --stages;
   cfg.stages = stages;
   cfg.L.ring_off = 0;
-  cfg.L.accs_off = (size_t)stages * R * sizeof(double);
+  cfg.L.accs_off = (size_t)stages * tile_bytes;
   cfg.L.coef_off = cfg.L.accs_off + (size_t)B2O_CONS_WARPS * a.ncols * 32 * sizeof(double);
   cfg.L.bar_off = cfg.L.coef_off + (size_t)nv * sizeof(double);
   a.landed_off = (uint32_t)(cfg.L.bar_off + (size_t)2 * stages * sizeof(uint64_t));
@@ -768,9 +771,15 @@ static int multi_launch(b2o_qn *q, const CompactArgs &base, double *res, int64_t
   a.bar_off = (uint32_t)cfg.L.bar_off;
   a.bar_target = c->bar_base + (unsigned long long)cfg.grid;
   b2o_mbox_fill(c, &a.mbox);
-  int st = (q->kind == 0 && (q->inverse || q->fwd_compact)) ? launch_persistent(c, qn_multi_kernel<NR, OP_INV_COMPACT>, cfg, a, true)
-           : q->kind == 0             ? launch_persistent(c, qn_multi_kernel<NR, OP_LBFGS_FWD>, cfg, a, true)
-                                      : launch_persistent(c, qn_multi_kernel<NR, OP_LSR1>, cfg, a, true);
+  int st;
+  if constexpr (sizeof(T) == 8) {
+    st = (q->kind == 0 && (q->inverse || q->fwd_compact)) ? launch_persistent(c, qn_multi_kernel<NR, OP_INV_COMPACT, T>, cfg, a, true)
+         : q->kind == 0                                   ? launch_persistent(c, qn_multi_kernel<NR, OP_LBFGS_FWD, T>, cfg, a, true)
+                                                          : launch_persistent(c, qn_multi_kernel<NR, OP_LSR1, T>, cfg, a, true);
+  } else {   // Float32 handles have no compact forms
+    st = q->kind == 0 ? launch_persistent(c, qn_multi_kernel<NR, OP_LBFGS_FWD, T>, cfg, a, true)
+                      : launch_persistent(c, qn_multi_kernel<NR, OP_LSR1, T>, cfg, a, true);
+  }
   if (st == B2O_OK) {
     c->bar_base += (unsigned long long)cfg.grid;
     if (a.mbox.nranks > 1) c->mbox_epoch += (unsigned long long)((nv + MBOX_MAXV - 1) / MBOX_MAXV);
@@ -921,11 +930,7 @@ extern "C" int b2o_qn_apply_multi(b2o_qn *q, void *res_, int64_t ldr, const void
   if (((uintptr_t)res_ | (uintptr_t)x_) % (uintptr_t)q->esize) B2O_FAIL(B2O_EARG, "matrices must be aligned to the element size");
   b2o_ctx *c = q->ctx;
   B2O_CUDA(cudaSetDevice(c->device));
-  if (q->esize == 4) {
-    // Float32 handles: the reference's semantics (column j of Res = the vector apply of column j of X), one launch per column
-    for (int r = 0; r < nrhs; ++r) B2O_TRY(qn32_apply(q, (float *)res_ + (int64_t)r * ldr, (const float *)x_ + (int64_t)r * ldx, alpha, beta));
-    return B2O_OK;
-  }
+  if (q->esize == 4) return qn32_apply_multi(q, (float *)res_, ldr, (const float *)x_, ldx, nrhs, alpha, beta);
   double *res = (double *)res_;
   const double *x = (const double *)x_;
   const bool twoloop = q->kind == 0 && q->inverse && !q->inv_compact;

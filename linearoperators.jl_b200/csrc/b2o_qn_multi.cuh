@@ -17,12 +17,13 @@
 
 constexpr int B2O_MULTI_MAXV = 256;   // ncols * NR values reduced per launch (fits d_dots and two mailbox epochs)
 
-struct MultiArgs {
-  const double *cols[B2O_MAX_COLS];
+template <typename T>
+struct MultiArgsT {
+  const T *cols[B2O_MAX_COLS];
   double cdiv[B2O_MAX_COLS];
   int ncols;
-  const double *x;   // column-major n x nrhs, leading dimension ldx
-  double *res;       // column-major n x nrhs, leading dimension ldr
+  const T *x;        // column-major n x nrhs, leading dimension ldx
+  T *res;            // column-major n x nrhs, leading dimension ldr
   int64_t ldx, ldr;
   int nrhs;          // <= NR
   int64_t n, ntiles;
@@ -39,6 +40,7 @@ struct MultiArgs {
   const double *W;
   int base_div;
 };
+using MultiArgs = MultiArgsT<double>;
 
 // Transposing butterfly: log2(NR) exchange stages fold the NR per-thread partials into ONE value per lane -- the sum over the
 // NR lanes that differ in the top log2(NR) lane bits -- for right-hand side r = lane / (32/NR).  The remaining 32/NR lanes of a
@@ -105,6 +107,13 @@ __device__ __forceinline__ unsigned fold_loaded(const double (&a)[EPT]) {
   for (int j = 0; j < EPT; j += 2) v ^= (unsigned)__double2hiint(a[j]);
   return v;
 }
+template <int EPT>
+__device__ __forceinline__ unsigned fold_loaded(const float (&a)[EPT]) {   // one register of every LDS.128 (four floats)
+  unsigned v = 0;
+#pragma unroll
+  for (int j = 0; j < EPT; j += 4) v ^= __float_as_uint(a[j]);
+  return v;
+}
 #ifdef B2O_SIMT_EMU
 inline void smem_reads_landed(unsigned *cell, unsigned v) { *cell = v; }
 #else
@@ -113,14 +122,17 @@ __device__ __forceinline__ void smem_reads_landed(unsigned *cell, unsigned v) {
 }
 #endif
 
-template <int NR>
+// rows per tile: 8 KB (8 right-hand sides) or 16 KB of column data per ring stage for either element type
+template <int NR, typename T = double>
 struct MultiTile {
-  static constexpr int R = (NR == 8) ? 1024 : 2048;
+  static constexpr int R = ((NR == 8) ? 1024 : 2048) * (int)(sizeof(double) / sizeof(T));
 };
 
-template <int NR, int OP>
-__global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_multi_kernel(const __grid_constant__ MultiArgs p) {
-  constexpr int R = MultiTile<NR>::R;
+// T = float: the Float32 operators' matrix right-hand sides (columns, X and Res in Float32; the inner products and their
+// reduction stay in double, the combine runs in Float32 FMAs)
+template <int NR, int OP, typename T = double>
+__global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_multi_kernel(const __grid_constant__ MultiArgsT<T> p) {
+  constexpr int R = MultiTile<NR, T>::R;
   constexpr int EPT = R / B2O_NCONS;
   constexpr int LPG = 32 / NR;   // lanes per right-hand-side group after the transposing reduce
 #ifdef B2O_SIMT_EMU
@@ -166,33 +178,25 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_multi_kernel(const __grid_
   } else {
     for (int i = tid; i < B2O_CONS_WARPS * ncols * 32; i += B2O_NCONS) wacc[i] = 0.0;
     consumers_sync();
-    double xr[NR][EPT], xn[NR][EPT];
+    T xr[NR][EPT], xn[NR][EPT];
     if (my_tiles > 0) {
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
         if (r < nrhs) load_user_tile<R>(p.x + (int64_t)r * p.ldx, (int64_t)blockIdx.x * R, p.n, p.x_al16, xn[r]);
         else {
 #pragma unroll
-          for (int j = 0; j < EPT; ++j) xn[r][j] = 0.0;
+          for (int j = 0; j < EPT; ++j) xn[r][j] = (T)0;
         }
       }
     }
     double *my_acc = wacc + (size_t)warp * ncols * 32 + lane;    // cell [warp][c][lane]
-    auto take = [&](uint32_t slot, double (&a)[EPT]) {
-      const double2 *b = reinterpret_cast<const double2 *>(rg.buf + (size_t)slot * R * sizeof(double));
-#pragma unroll
-      for (int j = 0; j < EPT / 2; ++j) {
-        double2 v = b[j * B2O_NCONS + tid];
-        a[2 * j] = v.x;
-        a[2 * j + 1] = v.y;
-      }
-    };
-    auto dots = [&](const double (&a)[EPT], double (&sv)[NR]) {
+    auto take = [&](uint32_t slot, T (&a)[EPT]) { tile_from_ring<R>(rg, slot, a); };
+    auto dots = [&](const T (&a)[EPT], double (&sv)[NR]) {
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
-        double acc = a[0] * xr[r][0];
+        double acc = (double)a[0] * (double)xr[r][0];
 #pragma unroll
-        for (int j = 1; j < EPT; ++j) acc = fma(a[j], xr[r][j], acc);
+        for (int j = 1; j < EPT; ++j) acc = fma((double)a[j], (double)xr[r][j], acc);
         sv[r] = acc;
       }
     };
@@ -213,7 +217,8 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_multi_kernel(const __grid_
         pos.advance();
         const uint32_t s1 = pos.slot, p1 = pos.par;
         pos.advance();
-        double a0[EPT], a1[EPT], v0[NR], v1[NR];
+        T a0[EPT], a1[EPT];
+        double v0[NR], v1[NR];
         mbar_wait(&rg.full[s0], p0);
         take(s0, a0);
         mbar_wait(&rg.full[s1], p1);
@@ -228,7 +233,8 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_multi_kernel(const __grid_
         my_acc[(c + 1) * 32] += f1;
       }
       if (c < ncols) {
-        double a0[EPT], v0[NR];
+        T a0[EPT];
+        double v0[NR];
         mbar_wait(&rg.full[pos.slot], pos.par);
         take(pos.slot, a0);
         smem_reads_landed(&s_landed[tid], fold_loaded(a0));
@@ -330,19 +336,19 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_multi_kernel(const __grid_
     }
     __syncwarp();
   } else {
-    const double alpha = p.alpha, beta = p.beta, gamma = p.gamma;
+    const T alpha = (T)p.alpha, beta = (T)p.beta, gamma = (T)p.gamma;
     // base term with ONE reciprocal instead of NR x EPT divisions per tile: a double division is ~30 instructions, and with 8
     // right-hand sides the divisions of `q ./= γ` outweighed the combine's FMAs (ncu source page: 17 % of the warp samples,
     // profiles/r2_ncu_summary.md).  x * (1/γ) differs from x / γ by at most one ulp -- the block kernels are contracted anyway.
-    const double inv_gamma = 1.0 / gamma;
-    double xn[NR][EPT], q[NR][EPT];
+    const T inv_gamma = (T)1 / gamma;
+    T xn[NR][EPT], q[NR][EPT];
     if (my_tiles > 0) {
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
         if (r < nrhs) load_user_tile<R>(p.x + (int64_t)r * p.ldx, (blockIdx.x + (my_tiles - 1) * grid) * R, p.n, p.x_al16, xn[r]);
         else {
 #pragma unroll
-          for (int j = 0; j < EPT; ++j) xn[r][j] = 0.0;
+          for (int j = 0; j < EPT; ++j) xn[r][j] = (T)0;
         }
       }
     }
@@ -357,12 +363,12 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_multi_kernel(const __grid_
 #pragma unroll
           for (int j = 0; j < EPT; ++j) q[r][j] = !p.scaling ? xn[r][j] : (p.base_div ? xn[r][j] * inv_gamma : xn[r][j] * gamma);
         } else {
-          double rold[EPT];
-          if (beta != 0.0 && r < nrhs) load_user_tile<R>(p.res + (int64_t)r * p.ldr, t * R, p.n, p.res_al16, rold);
+          T rold[EPT];
+          if (beta != (T)0 && r < nrhs) load_user_tile<R>(p.res + (int64_t)r * p.ldr, t * R, p.n, p.res_al16, rold);
 #pragma unroll
           for (int j = 0; j < EPT; ++j) {                                                           // src/lsr1.jl:92-96
-            const double v = (alpha * xn[r][j]) * inv_gamma;
-            q[r][j] = (beta != 0.0 && r < nrhs) ? v + beta * rold[j] : v;
+            const T v = (alpha * xn[r][j]) * inv_gamma;
+            q[r][j] = (beta != (T)0 && r < nrhs) ? v + beta * rold[j] : v;
           }
         }
       }
@@ -379,23 +385,15 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_multi_kernel(const __grid_
           pos.advance();
           mbar_wait(&rg.full[sa], pa);
           mbar_wait(&rg.full[sb], pb);
-          const double2 *A = reinterpret_cast<const double2 *>(rg.buf + (size_t)sa * R * sizeof(double));
-          const double2 *B = reinterpret_cast<const double2 *>(rg.buf + (size_t)sb * R * sizeof(double));
-          double a[EPT], b[EPT];
-#pragma unroll
-          for (int j = 0; j < EPT / 2; ++j) {
-            double2 va = A[j * B2O_NCONS + tid], vb = B[j * B2O_NCONS + tid];
-            a[2 * j] = va.x;
-            a[2 * j + 1] = va.y;
-            b[2 * j] = vb.x;
-            b[2 * j + 1] = vb.y;
-          }
+          T a[EPT], b[EPT];
+          tile_from_ring<R>(rg, sa, a);
+          tile_from_ring<R>(rg, sb, b);
           smem_reads_landed(&s_landed[tid], fold_loaded(a) ^ fold_loaded(b));
           consumer_release(rg, sa);
           consumer_release(rg, sb);
 #pragma unroll
           for (int r = 0; r < NR; ++r) {
-            const double ax = coef[c * NR + r], bx = coef[(c + 1) * NR + r];
+            const T ax = (T)coef[c * NR + r], bx = (T)coef[(c + 1) * NR + r];
 #pragma unroll
             for (int j = 0; j < EPT; ++j) q[r][j] = fma(bx, b[j], fma(-ax, a[j], q[r][j]));          // src/lbfgs.jl:194, contracted
           }
@@ -403,21 +401,15 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_multi_kernel(const __grid_
       } else {
         for (int c = 0; c < ncols; ++c) {
           mbar_wait(&rg.full[pos.slot], pos.par);
-          const double2 *A = reinterpret_cast<const double2 *>(rg.buf + (size_t)pos.slot * R * sizeof(double));
-          double a[EPT];
-#pragma unroll
-          for (int j = 0; j < EPT / 2; ++j) {
-            double2 va = A[j * B2O_NCONS + tid];
-            a[2 * j] = va.x;
-            a[2 * j + 1] = va.y;
-          }
+          T a[EPT];
+          tile_from_ring<R>(rg, pos.slot, a);
           smem_reads_landed(&s_landed[tid], fold_loaded(a));
           consumer_release(rg, pos.slot);
           pos.advance();
-          const double cd = p.cdiv[c];
+          const T cd = (T)p.cdiv[c];
 #pragma unroll
           for (int r = 0; r < NR; ++r) {
-            const double ax = (OP == OP_INV_COMPACT) ? coef[c * NR + r] : (alpha * coef[c * NR + r]) / cd;   // src/lsr1.jl:101
+            const T ax = (OP == OP_INV_COMPACT) ? (T)coef[c * NR + r] : (alpha * (T)coef[c * NR + r]) / cd;   // src/lsr1.jl:101
 #pragma unroll
             for (int j = 0; j < EPT; ++j) q[r][j] = fma(ax, a[j], q[r][j]);
           }
@@ -427,8 +419,8 @@ __global__ void __launch_bounds__(B2O_NTHREADS, 1) qn_multi_kernel(const __grid_
       for (int r = 0; r < NR; ++r) {
         if (r < nrhs) {
           if (OP != OP_LSR1) {
-            if (beta != 0.0) {
-              double rold[EPT];
+            if (beta != (T)0) {
+              T rold[EPT];
               load_user_tile<R>(p.res + (int64_t)r * p.ldr, t * R, p.n, p.res_al16, rold);
 #pragma unroll
               for (int j = 0; j < EPT; ++j) q[r][j] = alpha * q[r][j] + beta * rold[j];             // src/lbfgs.jl:197-201

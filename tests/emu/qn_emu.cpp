@@ -19,6 +19,12 @@ inline void stg_stream2(double *p, double2 v) {
   p[0] = v.x;
   p[1] = v.y;
 }
+inline unsigned __float_as_uint(float f) {
+  unsigned u;
+  memcpy(&u, &f, 4);
+  return u;
+}
+using std::fma;
 inline int __double2hiint(double d) {
   uint64_t u;
   memcpy(&u, &d, 8);
@@ -279,6 +285,56 @@ EMU_API int emu_qn_multi(int op, int NR, int64_t n, int64_t pitch, int ncols, co
   if (op == 1 && NR == 8) EMU_MULTI(8, OP_LSR1)
 #undef EMU_MULTI
   return 1;
+}
+
+// Float32 block apply of the forward operator: qn_multi_kernel<NR, LBFGS_FWD, float>
+EMU_API int emu_qn_multi_f32(int NR, int64_t n, int64_t pitch, int ncols, const float *cols, const float *x, int64_t ldx, float *res, int64_t ldr, int nrhs,
+                             double alpha, double beta, double gamma, int stages) {
+  Work w;
+  MultiArgsT<float> a;
+  memset(&a, 0, sizeof(a));
+  for (int c = 0; c < ncols; ++c) {
+    a.cols[c] = cols + (size_t)c * pitch;
+    a.cdiv[c] = 1.0;
+  }
+  a.ncols = ncols;
+  a.x = x;
+  a.res = res;
+  a.ldx = ldx;
+  a.ldr = ldr;
+  a.nrhs = nrhs;
+  a.n = n;
+  const int RR = NR == 8 ? 2048 : 4096;
+  a.ntiles = (n + RR - 1) / RR;
+  a.alpha = alpha;
+  a.beta = beta;
+  a.gamma = gamma;
+  a.scaling = 1;
+  a.x_al16 = ((uintptr_t)x % 16) == 0 && (nrhs == 1 || ldx % 4 == 0);
+  a.res_al16 = ((uintptr_t)res % 16) == 0 && (nrhs == 1 || ldr % 4 == 0);
+  const int nv = ncols * NR;
+  a.partials = w.partials.data();
+  a.dots = w.dots.data();
+  a.bar = &w.bar[0];
+  a.bar_target = 1;
+  a.stages = stages;
+  a.wacc_off = (uint32_t)((size_t)stages * RR * sizeof(float));
+  a.coef_off = (uint32_t)(a.wacc_off + (size_t)B2O_CONS_WARPS * ncols * 32 * sizeof(double));
+  a.bar_off = (uint32_t)(a.coef_off + (size_t)nv * sizeof(double));
+  a.landed_off = (uint32_t)(a.bar_off + (size_t)2 * stages * sizeof(uint64_t));
+  const size_t total = a.landed_off + B2O_NCONS * sizeof(unsigned);
+  a.mbox.nranks = 1;
+  if (NR == 8) {
+    void (*k)(const MultiArgsT<float>) = qn_multi_kernel<8, OP_LBFGS_FWD, float>;
+    B2O_LAUNCH(k, dim3(1), dim3(B2O_NTHREADS), total, nullptr, a);
+  } else if (NR == 4) {
+    void (*k)(const MultiArgsT<float>) = qn_multi_kernel<4, OP_LBFGS_FWD, float>;
+    B2O_LAUNCH(k, dim3(1), dim3(B2O_NTHREADS), total, nullptr, a);
+  } else {
+    void (*k)(const MultiArgsT<float>) = qn_multi_kernel<2, OP_LBFGS_FWD, float>;
+    B2O_LAUNCH(k, dim3(1), dim3(B2O_NTHREADS), total, nullptr, a);
+  }
+  return 0;
 }
 
 // inverse two-loop recursion, vector (nrhs == 0: x, res are vectors) or block (nrhs columns with leading dimensions ldx, ldr; NR = 4 or 8).

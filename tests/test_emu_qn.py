@@ -286,3 +286,34 @@ def test_push_rebuild_steps(emu, stages):
             a = a - ((cols[l, :n] @ sk[:n]) / cdiv[l]) * cols[l, :n]
         assert rel(res, a) <= 1e-14
         assert abs(out2[0] - a @ sk[:n]) <= 1e-12 * max(1.0, abs(a @ sk[:n])) and abs(out2[1] - a @ a) <= 1e-13 * (a @ a)
+
+
+@pytest.mark.parametrize("NR,nrhs,ld_extra", [(2, 2, 0), (4, 3, 1), (8, 8, 4), (8, 6, 2)])
+def test_block_apply_kernel_float32(emu, NR, nrhs, ld_extra):
+    """qn_multi_kernel<NR, LBFGS_FWD, float>: the Float32 operators' matrix right-hand sides (16-byte vectors of four rows; leading
+    dimensions that keep / break the 16-byte alignment of the columns)"""
+    i32, i64, d, vp = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
+    emu.emu_qn_multi_f32.restype = i32
+    emu.emu_qn_multi_f32.argtypes = [i32, i64, i64, i32, vp, vp, i64, vp, i64, i32, d, d, d, i32]
+    F = np.float32
+    rng = np.random.default_rng(NR + nrhs)
+    n, ncols, gamma = 4104, 6, F(0.7)
+    pitch = (n + 4095) // 4096 * 4096
+    cols = aligned32((ncols, pitch))
+    cols[:, :n] = (0.1 * rng.random((ncols, n))).astype(F)
+    ld = n + ld_extra
+    X, Res = aligned32((nrhs, ld)), aligned32((nrhs, ld))
+    X[:, :n] = rng.random((nrhs, n)).astype(F)
+    R0 = rng.random((nrhs, n)).astype(F)
+    dot = lambda a, b: F(np.dot(a.astype(np.float64), b.astype(np.float64)))
+    for alpha, beta in ((1.0, 0.0), (-0.75, 0.5)):
+        Res[:, :n] = R0
+        emu.emu_qn_multi_f32(NR, n, pitch, ncols, cols.ctypes.data, X.ctypes.data, ld, Res.ctypes.data, ld, nrhs, alpha, beta, float(gamma), 5)
+        for j in range(nrhs):
+            x = X[j, :n]
+            q = x / gamma
+            for k in range(ncols // 2):
+                a, b = cols[2 * k, :n], cols[2 * k + 1, :n]
+                q = q + (dot(b, x) * b - dot(a, x) * a)
+            ref = F(alpha) * q + F(beta) * R0[j] if beta != 0 else F(alpha) * q
+            assert rel(Res[j, :n].astype(np.float64), ref.astype(np.float64)) <= 2e-6, (j, rel(Res[j, :n].astype(np.float64), ref.astype(np.float64)))

@@ -92,10 +92,16 @@ def test_f32_push_and_apply_vs_numpy_oracle(lo, ctx, kind, n, mem, npush):
     assert np.array_equal(host(out2[3:]), host(res))
     assert np.array_equal(host(op * x), host(res))                           # run-to-run bit determinism
     # matrix right-hand sides (src/operations.jl:34-36: column j of Res = the vector apply of column j of X) and host buffers
-    Xb = torch.stack([x, r0, x + r0]).contiguous()
-    Rb = torch.empty_like(Xb)
-    lo.mul_(Rb.T, op, Xb.T)
-    assert np.array_equal(host(Rb[0]), host(res)) and np.array_equal(host(Rb[2]), host(op * (x + r0)))
+    for k in (3, 8, 11):                                                     # NR = 4, 8, 8 + 4 instantiations of the Float32 block kernel
+        Xb = torch.stack([f32(ctx, n, 400 + j) for j in range(k)]).contiguous()
+        Rb = torch.empty_like(Xb)
+        l0 = ctx.launch_count()
+        lo.mul_(Rb.T, op, Xb.T)
+        if kind != "inverse":
+            assert ctx.launch_count() - l0 == (1 if k <= 8 else 2)           # forward / L-SR1: one launch per 8 right-hand sides
+        for j in (0, k - 1):
+            assert rel(host(Rb[j]), host(op * Xb[j])) <= 2e-6                # contracted block kernel vs the vector kernel
+            assert rel(host(Rb[j]), o.apply(host(Xb[j]))) <= tol
     xh, rh = x.cpu().pin_memory(), torch.empty(n, dtype=torch.float32).pin_memory()
     op.apply_host(rh, xh)
     assert np.array_equal(rh.numpy(), host(res))
