@@ -149,7 +149,7 @@ int b2o_diagqn_push(b2o_ctx *ctx, int kind, void *d, int64_t d_len, const void *
 /* ---- quasi-Newton operators (src/lbfgs.jl, src/lsr1.jl) ---------------------------------- */
 /* dtype: B2O_F64, or B2O_F32 (T = Float32, test/test_lbfgs.jl:162-178, test/test_lsr1.jl:74-86): state columns, x and res are then
  * Float32 (4-byte aligned), every elementwise statement runs in Float32, inner products are accumulated in double and rounded to
- * Float32.  Float32 handles support every entry point below (row partitions included; apply_multi runs column by column,
+ * Float32.  Float32 handles support every entry point below (row partitions included; apply_multi on the Float32 block kernel -- two-loop inverse handles column by column --,
  * apply_host through one staged copy) except solve_shifted and the compact modes, which return B2O_EUNSUPPORTED for them. */
 /* LBFGSOperator(T,n;mem,scaling,damped,σ₂,σ₃) :168-208 (inverse=0) / InverseLBFGSOperator :112-160 (inverse=1) */
 int b2o_lbfgs_create(b2o_ctx *ctx, int dtype, int64_t n, int mem, int scaling, int damped, double sigma2,
