@@ -587,3 +587,25 @@ def test_golden_vectors_v3_float32_quasi_newton(orc):
     assert set(now) == set(G)
     for k in G:
         assert np.array_equal(np.asarray(now[k]), np.asarray(G[k])), k
+
+
+def test_compact_forward_form_accuracy_study():
+    """tools/compact_accuracy_study.py (profiles/r2_compact_accuracy.md): over every family of (s, y) pairs the compact forward form stays
+    within a small factor of the reference recursion's own rounding error, measured against a long-double ground truth -- the written
+    basis for offering LBFGSOperator(n, compact=True)"""
+    import importlib.util
+    import io
+    import json
+    from contextlib import redirect_stdout
+    path = os.path.join(os.path.dirname(__file__), "..", "tools", "compact_accuracy_study.py")
+    spec = importlib.util.spec_from_file_location("compact_accuracy_study", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        mod.main()
+    rows = [json.loads(l) for l in buf.getvalue().splitlines() if l.strip()]
+    assert len(rows) >= 10
+    for r in rows:
+        assert r["rel_err_compact_form"] <= max(20.0 * r["rel_err_reference_form"], 5e-15), r
+        assert r["rel_diff_compact_vs_reference"] <= max(1e-12, 5.0 * r["rel_err_reference_form"]), r
