@@ -68,6 +68,13 @@ constexpr int R = 1024;
 
 extern "C" {
 // forward LBFGSOperator / LSR1Operator apply on ONE emulated CTA.  cols: [ncols][pitch] (pitch a multiple of R, zero padded, 16-byte aligned)
+// compact representations (op 2 = OP_INV_COMPACT): coefficients = W * [cols' x]; base_div selects x/γ (compact forward form) or γx (compact inverse)
+static const double *g_W = nullptr;
+static int g_base_div = 0;
+EMU_API void emu_qn_set_compact(const double *W, int base_div) {
+  g_W = W;
+  g_base_div = base_div;
+}
 EMU_API int emu_qn_compact(int op, int64_t n, int64_t pitch, int ncols, const double *cols, const double *cdiv, const double *x, double *res,
                            double alpha, double beta, double gamma, int scaling, int stages) {
   Work w;
@@ -101,8 +108,13 @@ EMU_API int emu_qn_compact(int op, int64_t n, int64_t pitch, int ncols, const do
   a.coef_off = (uint32_t)L.coef_off;
   a.bar_off = (uint32_t)L.bar_off;
   a.mbox.nranks = 1;
+  a.W = g_W;
+  a.base_div = g_base_div;
   if (op == OP_LBFGS_FWD) {
     void (*k)(const CompactArgsT<double>) = qn_compact_kernel<R, OP_LBFGS_FWD, double>;
+    B2O_LAUNCH(k, dim3(1), dim3(B2O_NTHREADS), L.total, nullptr, a);
+  } else if (op == OP_INV_COMPACT) {
+    void (*k)(const CompactArgsT<double>) = qn_compact_kernel<R, OP_INV_COMPACT, double>;
     B2O_LAUNCH(k, dim3(1), dim3(B2O_NTHREADS), L.total, nullptr, a);
   } else {
     void (*k)(const CompactArgsT<double>) = qn_compact_kernel<R, OP_LSR1, double>;

@@ -317,3 +317,30 @@ def test_block_apply_kernel_float32(emu, NR, nrhs, ld_extra):
                 q = q + (dot(b, x) * b - dot(a, x) * a)
             ref = F(alpha) * q + F(beta) * R0[j] if beta != 0 else F(alpha) * q
             assert rel(Res[j, :n].astype(np.float64), ref.astype(np.float64)) <= 2e-6, (j, rel(Res[j, :n].astype(np.float64), ref.astype(np.float64)))
+
+
+@pytest.mark.parametrize("base_div,stages", [(0, 3), (1, 7)])
+def test_compact_representation_kernel(emu, base_div, stages):
+    """qn_compact_kernel<R, INV_COMPACT>: H x = γ x + [S γY] W [S'x; γY'x] (compact inverse) / B x = x/γ + [S Y] W' [S'x; Y'x] (compact
+    forward form): all 2m inner products, the 2m x 2m middle product repeated by the CTA, the combine"""
+    emu.emu_qn_set_compact.restype = None
+    emu.emu_qn_set_compact.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    rng = np.random.default_rng(stages)
+    n, m, gamma = 2600, 3, 0.8
+    cols, pitch = columns(2 * m, n, rng, 0.2)
+    W = aligned((2 * m, 2 * m))
+    W[:] = rng.random((2 * m, 2 * m)) - 0.5
+    x, res = aligned(n), aligned(n)
+    x[:] = rng.random(n)
+    r0 = rng.random(n)
+    emu.emu_qn_set_compact(W.ctypes.data, base_div)
+    try:
+        for alpha, beta in ((1.0, 0.0), (1.5, -0.25)):
+            res[:] = r0
+            emu.emu_qn_compact(2, n, pitch, 2 * m, cols.ctypes.data, None, x.ctypes.data, res.ctypes.data, alpha, beta, gamma, 1, stages)
+            coef = W @ (cols[:, :n] @ x)
+            q = (x / gamma if base_div else x * gamma) + coef @ cols[:, :n]
+            ref = alpha * q + beta * r0 if beta != 0 else alpha * q
+            assert rel(res, ref) <= 1e-13
+    finally:
+        emu.emu_qn_set_compact(None, 0)
