@@ -326,3 +326,26 @@ def test_kron_of_operators_torch_tensor_plumbing(lo):
         res = r0.clone()
         lo.mul_(res, K, x, 1.5, 0.25)
         assert np.allclose(res.numpy(), 1.5 * (D @ x.numpy()) + 0.25 * r0.numpy(), rtol=1e-13, atol=1e-14)
+
+
+def test_quasi_newton_constructor_forms_and_element_types():
+    """LBFGSOperator(T, n; ...) / LBFGSOperator(n; ...) (src/lbfgs.jl:168, 208; src/lsr1.jl:86, 115): the positional element type of the
+    reference, the keyword form of the mirror, Float64 / Float32 built, anything else refused -- pure host logic, no GPU"""
+    import torch
+    from linearoperators_jl_b200 import _lib, qn
+    assert qn._split_T(10, (), None) == (10, None)
+    assert qn._split_T(torch.float32, (10,), None) == (10, torch.float32)
+    assert qn._split_T(10, (), torch.float32) == (10, torch.float32)
+    with pytest.raises(TypeError):
+        qn._split_T(10, (5,), None)                         # mem is a keyword argument in the reference too
+    with pytest.raises(TypeError):
+        qn._split_T(torch.float32, (10,), torch.float64)     # element type given twice
+    with pytest.raises(TypeError):
+        qn._split_T(torch.float32, (10, 5), None)
+    assert qn._eltype_code(None) == (torch.float64, _lib.B2O_F64)
+    assert qn._eltype_code(float) == (torch.float64, _lib.B2O_F64)
+    assert qn._eltype_code(np.float32) == (torch.float32, _lib.B2O_F32)
+    assert qn._eltype_code(torch.float32) == (torch.float32, _lib.B2O_F32)
+    for bad in (torch.float16, torch.bfloat16, torch.complex128):   # Float16 / BigFloat / complex of the reference's precision test: not built
+        with pytest.raises(_lib.B2OError):
+            qn._eltype_code(bad)
