@@ -484,7 +484,7 @@ def main():
         "frac_of_nominal_8TBs_per_gpu": per_gpu / NOMINAL_HBM_GBS,
         "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": "of " + peak_kind,
-                     "kernel": "qn_twoloop_kernel<2048>" if inverse else "qn_compact_kernel<2048,LBFGS_FWD>",
+                     "kernel": "qn_twoloop_kernel<2048, double>" if inverse else "qn_compact_kernel<2048, 0 (LBFGS_FWD), double>",
                      "algorithmic_bytes_per_launch": bytes_step},
         "e2e": e2e, "gpu_launches": int(round(launches_per_step * args.steps)), "clocks": clocks,
         "per_rank_ms": per_rank_ms,
